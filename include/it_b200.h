@@ -1,0 +1,231 @@
+/*
+ * it_b200.h -- C-ABI of the B200-native operator-kernel backend for InfiniTensor.
+ *
+ * Two groups of entry points, both plain C (pointers + sizes, no C++/torch types):
+ *
+ *  (1) KERNEL LAUNCHERS  it_b200_<op>(..., void *stream)
+ *      One per reference CUDA kernel.  All pointers are
+ *      DEVICE pointers, `stream` is a cudaStream_t.  Every launcher is
+ *      CUDA-graph-capturable: no allocation, no synchronisation, no host read of
+ *      device data (contract of reference src/cuda/cuda_runtime.cc:252-283).
+ *      These are what the Kernel::compute() bodies registered through
+ *      REGISTER_KERNEL (reference include/core/kernel.h:186-195) bottom out in.
+ *
+ *  (2) GRAPH / RUNTIME HANDLE API  itb_*  (HOST buffers in copyin/copyout)
+ *      The C spelling of the reference's pybind `backend` module
+ *      (reference src/ffi/ffi_infinitensor.cc:441-638): Runtime, GraphHandler,
+ *      Tensor.  This is the reference-facing boundary a Python/cgo/JNI caller binds.
+ *
+ * dtype codes are the ONNX enum the reference uses (include/core/data_type.h:6-23):
+ *   1 f32, 2 u8, 3 i8, 6 i32, 7 i64, 9 bool, 10 f16, 12 u32, 16 bf16.
+ * Every function returns 0 on success; on failure it returns non-zero and
+ * it_b200_last_error() describes why (the C spelling of infini::Exception,
+ * reference include/core/common.h:44-55).  Nothing here ever falls back to a CPU path.
+ */
+#ifndef IT_B200_H
+#define IT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ITB_F32 1
+#define ITB_U8 2
+#define ITB_I8 3
+#define ITB_I32 6
+#define ITB_I64 7
+#define ITB_BOOL 9
+#define ITB_F16 10
+#define ITB_U32 12
+#define ITB_BF16 16
+
+#define ITB_MAX_RANK 8
+
+const char *it_b200_last_error(void);
+int it_b200_version(void);
+
+/* ---- unary family: replaces unary.cu:31-143 + ActivationCudnn (unary.cc:70-122) ---- */
+enum { ITB_RELU = 0, ITB_SIGMOID, ITB_TANH, ITB_GELU, ITB_SILU, ITB_ERF, ITB_NEG, ITB_ABS,
+       ITB_SQRT, ITB_HARDSIGMOID, ITB_HARDSWISH, ITB_EXP };
+int it_b200_unary(int op, int dtype, const void *x, void *y, int64_t n, void *stream);
+
+/* ---- binary with full numpy broadcast (rank <= 8): replaces ElementWiseCudnn
+ *      (element_wise.cc:8-121) and element_wise.cu:9-131.  strides in elements, 0 = broadcast.
+ *      Comparison ops write uint8 0/1. ---- */
+enum { ITB_ADD = 0, ITB_SUB, ITB_MUL, ITB_DIV, ITB_POW, ITB_MIN, ITB_MAX, ITB_LESS, ITB_EQUAL,
+       ITB_GREATER };
+int it_b200_binary(int op, int dtype, const void *a, const void *b, void *c, int rank,
+                   const int64_t *dims, const int64_t *stride_a, const int64_t *stride_b,
+                   void *stream);
+
+/* ---- Cast: replaces _cast_kernel (unary.cu:145-154, unary.cc:30-68) ---- */
+int it_b200_cast(int from, int to, const void *x, void *y, int64_t n, void *stream);
+
+/* ---- Where: replaces _whereKernel (where.cu:20-41); cond is uint8/bool ---- */
+int it_b200_where(int elem_size, const void *cond, const void *x, const void *y, void *out,
+                  int rank, const int64_t *dims, const int64_t *stride_c,
+                  const int64_t *stride_x, const int64_t *stride_y, void *stream);
+
+/* ---- Expand: replaces _expandKernel/_expandRowKernel (expand.cu:10-49,154-170) ---- */
+int it_b200_expand(int elem_size, const void *x, void *y, int rank, const int64_t *dims,
+                   const int64_t *stride_x, void *stream);
+
+/* ---- Softmax over one axis, tensor viewed [outer, dim, inner]: replaces softmax.cu:18-404 ---- */
+int it_b200_softmax(int dtype, const void *x, void *y, int64_t outer, int dim, int64_t inner,
+                    void *stream);
+
+/* ---- LayerNormalization over one axis with stride: replaces layer_norm.cu:4-557.
+ *      scale_size / bias_size are `dim` or 1 (scalar broadcast); bias may be NULL. ---- */
+int it_b200_layernorm(int dtype, const void *x, const void *scale, const void *bias, void *y,
+                      int64_t outer, int dim, int64_t inner, int scale_size, int bias_size,
+                      float eps, void *stream);
+
+/* ---- RMSNorm: replaces _rmsnorm_kernel (rms_norm.cu:36-54); eps 1e-5, round before weight ---- */
+int it_b200_rmsnorm(int dtype, const void *x, const void *w, void *y, int64_t tokens, int hidden,
+                    void *stream);
+
+/* ---- RoPE: replaces _rope_kernel (rope.cu:7-31); processes every (b, s) row.
+ *      pos_dtype: ITB_I32 / ITB_U32 / ITB_I64. ---- */
+int it_b200_rope(int dtype, const void *pos, int pos_dtype, const void *x, void *y, int B, int S,
+                 int dim_model, int dim_head, void *stream);
+
+/* ---- Transpose (N-d permute): replaces _transpose_kernel (transpose.cu:10-24) ---- */
+int it_b200_transpose(int elem_size, const void *x, void *y, int rank, const int64_t *dims_in,
+                      const int *perm, void *stream);
+
+/* ---- Concat / Split along one axis: replaces _split_concat_kernel (split_concat.cu:28-84).
+ *      Tensors are viewed [outer, axis_len_i * inner]; `parts` are device pointers. ---- */
+int it_b200_concat(int elem_size, int n_parts, const void *const *parts, const int64_t *axis_len,
+                   void *out, int64_t outer, int64_t inner, void *stream);
+int it_b200_split(int elem_size, int n_parts, void *const *parts, const int64_t *axis_len,
+                  const void *in, int64_t outer, int64_t inner, void *stream);
+
+/* ---- Gather along axis: replaces _gather_kernel (gather.cu:31-55). data viewed
+ *      [outer, axis_len, inner]; out [outer, n_idx, inner]. idx_dtype ITB_I32 / ITB_I64. ---- */
+int it_b200_gather(int elem_size, int idx_dtype, const void *data, const void *idx, void *out,
+                   int64_t outer, int64_t axis_len, int64_t inner, int64_t n_idx, void *stream);
+
+/* ---- Reshape/Flatten/Identity/Squeeze/Unsqueeze: replaces CopyCuda (reshape.cc:4-21) ---- */
+int it_b200_copy(const void *src, void *dst, int64_t bytes, void *stream);
+
+/* ---- Pad / Slice: replaces _pad_slice_kernel (pad_slice.cu:6-47).  Generic strided window:
+ *      out[i] = in[start + i*step] per dim when inside [0, dims_in), else 0. ---- */
+int it_b200_pad_slice(int elem_size, const void *in, void *out, int rank, const int64_t *dims_in,
+                      const int64_t *dims_out, const int64_t *start, const int64_t *step,
+                      void *stream);
+
+/* ---- ReduceMean / ReduceSum: replaces ReduceCudnnBase (reduce.cc:7-125).
+ *      reduce_mask[i] != 0 marks a reduced axis. ---- */
+int it_b200_reduce(int dtype, int is_mean, const void *x, void *y, int rank, const int64_t *dims,
+                   const int *reduce_mask, void *stream);
+
+/* ---- MaxPool / AveragePool (count-include-pad): replaces poolingCudnn (pooling.cc:8-95) ---- */
+int it_b200_pool2d(int dtype, int is_max, const void *x, void *y, int N, int C, int H, int W,
+                   int kh, int kw, int dh, int dw, int ph, int pw, int sh, int sw, int OH, int OW,
+                   void *stream);
+
+/* ---- BatchNormalization inference: replaces BatchNormCudnn (batch_norm.cc:9-69).
+ *      mean/var/scale/bias are f32 (as the reference requires). ---- */
+int it_b200_batchnorm(int dtype, const void *x, const float *mean, const float *var,
+                      const float *scale, const float *bias, void *y, int N, int C, int64_t HW,
+                      float eps, void *stream);
+
+/* ---- MatMul: replaces matmulCublas (matmul.cc:66-211).
+ *      C[b,m,n] = op(A)[b,m,k] . op(B)[b,k,n] (+ bias) ; row-major; stride_a / stride_b in
+ *      elements between batches (0 = broadcast, matmul.cc:124-137).  bias (may be NULL) is
+ *      broadcast by bias_stride_{b,m,n} (elements; 0 = broadcast) -- the fused form of the
+ *      reference's expand-into-C + beta=1 (matmul.cc:86-118).  act: 0 none (the reference
+ *      ignores MatmulObj::act on CUDA, quirk q5), 1 relu, 2 sigmoid, 3 tanh (operator attr).
+ *      fp32 accumulate for every dtype.  workspace: device scratch (may be NULL when
+ *      it_b200_matmul_workspace() returns 0). ---- */
+int64_t it_b200_matmul_workspace(int dtype, int64_t b, int m, int n, int k);
+int it_b200_matmul(int dtype, const void *A, const void *B, const void *bias, void *C, int64_t b,
+                   int m, int n, int k, int64_t stride_a, int64_t stride_b, int trans_a,
+                   int trans_b, int64_t bias_stride_b, int64_t bias_stride_m,
+                   int64_t bias_stride_n, int act, void *workspace, int64_t workspace_bytes,
+                   void *stream);
+
+/* ---- Conv (NCHW x FCRS, groups, symmetric pad): replaces convCudnn (conv.cc:36-265).
+ *      im2col into workspace + tensor-core GEMM. ---- */
+int64_t it_b200_conv2d_workspace(int dtype, int N, int C, int H, int W, int F, int R, int S,
+                                 int ph, int pw, int sh, int sw, int dh, int dw, int groups);
+int it_b200_conv2d(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W,
+                   int F, int R, int S, int ph, int pw, int sh, int sw, int dh, int dw, int groups,
+                   void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ---- AttentionKVCache (decode, q-len 1): replaces _attention_kvcache_kernel_128_1/_2
+ *      (attention_kvcache.cu:8-169).  Appends k,v IN PLACE into k_cache/v_cache at
+ *      position_id[0]; caches [B,H,S_max,D], q/k/v/out [B,H,1,D]; D == 128.
+ *      pos_dtype: ITB_I32 / ITB_U32 / ITB_I64 (element 0 is used for every row, .cu:17). ---- */
+int64_t it_b200_attention_kvcache_workspace(int B, int H, int S_max, int D);
+int it_b200_attention_kvcache(int dtype, void *k_cache, void *v_cache, const void *q,
+                              const void *k, const void *v, const void *position_id,
+                              int pos_dtype, void *out, int B, int H, int S_max, int D,
+                              void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ======================================================================
+ * (2) Graph / runtime handle API -- see infinitensor_b200/csrc/host/capi.cc.
+ * Mirrors reference GraphHandlerObj (include/core/graph_handler.h:15-159),
+ * CudaRuntimeObj (include/cuda/cuda_runtime.h:70-110) and the Tensor bindings
+ * (src/ffi/ffi_infinitensor.cc:499-535).  Handles are opaque.
+ * ====================================================================== */
+typedef struct itb_runtime itb_runtime;
+typedef struct itb_graph itb_graph;
+typedef int64_t itb_tensor; /* tensor id inside one graph; -1 = null */
+
+int itb_runtime_create(int device, int64_t cuda_graph_cache_capacity, itb_runtime **out);
+int itb_runtime_destroy(itb_runtime *rt);
+int itb_runtime_init_comm(itb_runtime *rt, const char *name, int world_size, int rank);
+int itb_runtime_init_comm_with_id(itb_runtime *rt, const void *nccl_unique_id, int id_bytes,
+                                  int world_size, int rank);
+int itb_runtime_nccl_unique_id(void *out, int out_bytes);
+int64_t itb_runtime_cuda_graph_cache_size(itb_runtime *rt);
+int64_t itb_runtime_cuda_graph_capture_count(itb_runtime *rt);
+int itb_runtime_clear_cuda_graph_cache(itb_runtime *rt);
+int64_t itb_runtime_kernel_launches(itb_runtime *rt); /* launches issued by our kernels so far */
+void *itb_runtime_stream(itb_runtime *rt);
+
+int itb_graph_create(itb_runtime *rt, itb_graph **out);
+int itb_graph_destroy(itb_graph *g);
+int itb_graph_tensor(itb_graph *g, const int *dims, int rank, int dtype, itb_tensor *out);
+int itb_tensor_set_weight(itb_graph *g, itb_tensor t);
+int itb_tensor_set_input(itb_graph *g, itb_tensor t);
+int itb_tensor_set_output(itb_graph *g, itb_tensor t);
+int itb_tensor_rank(itb_graph *g, itb_tensor t);
+int itb_tensor_shape(itb_graph *g, itb_tensor t, int *dims_out);
+int itb_tensor_dtype(itb_graph *g, itb_tensor t);
+int64_t itb_tensor_bytes(itb_graph *g, itb_tensor t);
+void *itb_tensor_device_ptr(itb_graph *g, itb_tensor t);
+int itb_tensor_copyin(itb_graph *g, itb_tensor t, const void *host, int64_t bytes);
+int itb_tensor_copyout(itb_graph *g, itb_tensor t, void *host, int64_t bytes);
+int itb_tensor_copyin_async(itb_graph *g, itb_tensor t, const void *pinned_host, int64_t bytes);
+int itb_tensor_copyout_async(itb_graph *g, itb_tensor t, void *pinned_host, int64_t bytes);
+
+/* Generic operator insertion: op_type is the reference OpType name ("MatMul", "Conv",
+ * "AttentionKVCache", ...).  inputs/outputs are tensor ids (-1 in outputs = infer + create).
+ * iattrs / fattrs carry the operator's constructor attributes in the reference's argument
+ * order (documented per op in INTEGRATION.md).  The created output ids are written back. */
+int itb_graph_add_op(itb_graph *g, const char *op_type, const itb_tensor *inputs, int n_inputs,
+                     itb_tensor *outputs, int n_outputs, const int64_t *iattrs, int n_iattrs,
+                     const double *fattrs, int n_fattrs);
+int itb_graph_num_ops(itb_graph *g);
+int itb_graph_op_type(itb_graph *g, int index, char *buf, int buf_len);
+int itb_graph_topo_sort(itb_graph *g);
+int itb_graph_shape_infer(itb_graph *g);
+int itb_graph_optimize(itb_graph *g);
+int itb_graph_data_malloc(itb_graph *g, int use_naive_allocator, int64_t mem_pool_size);
+int itb_graph_run(itb_graph *g);
+int itb_graph_run_without_sync(itb_graph *g);
+int itb_graph_run_with_cudagraph(itb_graph *g);
+int itb_graph_tune(itb_graph *g);
+int itb_graph_sync(itb_graph *g);
+double itb_graph_get_perf_time(itb_graph *g);
+int64_t itb_graph_arena_bytes(itb_graph *g, int which /*0 weights, 1 activations*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IT_B200_H */

@@ -1,0 +1,176 @@
+// gemm.cu -- MatMul / Conv entry points: shape dispatch + TMA descriptor helper + im2col.
+//
+// it_b200_matmul replaces matmulCublas (reference src/kernels/cuda/matmul.cc:66-211):
+//   M <= 64, bf16/fp16, [K,N] weights  -> gemm_skinny.cu  (TMA + mbarrier + cluster split-K, HBM-bound)
+//   large aligned bf16/fp16             -> gemm_tc.cu      (tcgen05 + TMEM + TMA)
+//   fp32 (exact, no TF32) and the rest  -> gemm_simt.cu
+// it_b200_conv2d replaces convCudnn (conv.cc:36-265): im2col into the workspace, then the same GEMMs
+// (the "conv/im2col-GEMM path" BASELINE.json names for ResNet-50).
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "gemm.cuh"
+
+namespace itb {
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
+}
+
+bool make_tma_2d_b16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols,
+                     uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
+    auto fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                            : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// ---------------------------------------------------------------- im2col (NCHW -> [N][C*R*S, OH*OW])
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const T *__restrict__ x, T *__restrict__ col, int64_t total,
+                                                     int C, int H, int W, int R, int S, int OH, int OW, int ph,
+                                                     int pw, int sh, int sw, int dh, int dw) {
+    // col[n][(c*R + r)*S + s][oh*OW + ow]; consecutive threads walk ow -> coalesced writes
+    const int64_t P = (int64_t)OH * OW, Kc = (int64_t)C * R * S;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t p = i % P, t = i / P;
+        int64_t kc = t % Kc, n = t / Kc;
+        int s = (int)(kc % S), r = (int)((kc / S) % R), c = (int)(kc / ((int64_t)R * S));
+        int oh = (int)(p / OW), ow = (int)(p % OW);
+        int ih = oh * sh - ph + r * dh, iw = ow * sw - pw + s * dw;
+        T v = from_f<T>(0.f);
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((int64_t)n * C + c) * H + ih) * W + iw];
+        col[i] = v;
+    }
+}
+
+#ifndef ITB_HAVE_GEMM_TC
+int launch_gemm_tc(int, const GemmArgs &, cudaStream_t) { return -1; }
+#endif
+
+static int run_gemm(int dtype, const GemmArgs &g, cudaStream_t st) {
+    if (g.batch == 0 || g.m == 0 || g.n == 0) return 0;
+    int r = launch_gemm_skinny(dtype, g, st);
+    if (r >= 0) return r;
+    r = launch_gemm_tc(dtype, g, st);
+    if (r >= 0) return r;
+    return launch_gemm_simt(dtype, g, st);
+}
+
+}  // namespace itb
+
+using namespace itb;
+
+extern "C" int64_t it_b200_matmul_workspace(int, int64_t, int, int, int) { return 0; }
+
+extern "C" int it_b200_matmul(int dtype, const void *A, const void *B, const void *bias, void *C, int64_t b,
+                              int m, int n, int k, int64_t stride_a, int64_t stride_b, int trans_a, int trans_b,
+                              int64_t bias_stride_b, int64_t bias_stride_m, int64_t bias_stride_n, int act,
+                              void *workspace, int64_t workspace_bytes, void *stream) {
+    (void)workspace;
+    (void)workspace_bytes;
+    ITB_CHECK(dtype == ITB_F32 || dtype == ITB_F16 || dtype == ITB_BF16, "matmul: unsupported dtype %d", dtype);
+    ITB_CHECK(m >= 0 && n >= 0 && k >= 0 && b >= 0, "matmul: negative dimension");
+    ITB_CHECK(act >= 0 && act <= 3, "matmul: bad act %d", act);
+    GemmArgs g{A, B, bias, C, b, m, n, k, stride_a, stride_b, trans_a, trans_b,
+               bias_stride_b, bias_stride_m, bias_stride_n, act};
+    return run_gemm(dtype, g, (cudaStream_t)stream);
+}
+
+static void conv_out(int H, int W, int R, int S, int ph, int pw, int sh, int sw, int dh, int dw, int &OH, int &OW) {
+    OH = (H + 2 * ph - dh * (R - 1) - 1) / sh + 1;  // reference src/operators/conv.cc:85-114
+    OW = (W + 2 * pw - dw * (S - 1) - 1) / sw + 1;
+}
+
+static bool conv_is_1x1_direct(int R, int S, int ph, int pw, int sh, int sw) {
+    return R == 1 && S == 1 && ph == 0 && pw == 0 && sh == 1 && sw == 1;
+}
+
+extern "C" int64_t it_b200_conv2d_workspace(int dtype, int N, int C, int H, int W, int F, int R, int S, int ph,
+                                            int pw, int sh, int sw, int dh, int dw, int groups) {
+    (void)F;
+    (void)groups;
+    if (conv_is_1x1_direct(R, S, ph, pw, sh, sw)) return 0;
+    int OH, OW;
+    conv_out(H, W, R, S, ph, pw, sh, sw, dh, dw, OH, OW);
+    return (int64_t)N * C * R * S * OH * OW * dtype_size(dtype);
+}
+
+extern "C" int it_b200_conv2d(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W, int F,
+                              int R, int S, int ph, int pw, int sh, int sw, int dh, int dw, int groups,
+                              void *workspace, int64_t workspace_bytes, void *stream) {
+    ITB_CHECK(groups >= 1 && C % groups == 0 && F % groups == 0, "conv: bad groups %d for C=%d F=%d", groups, C, F);
+    auto st = (cudaStream_t)stream;
+    int OH, OW;
+    conv_out(H, W, R, S, ph, pw, sh, sw, dh, dw, OH, OW);
+    if ((int64_t)N * F * OH * OW == 0) return 0;
+    const int es = dtype_size(dtype);
+    const int64_t P = (int64_t)OH * OW, Kc = (int64_t)C * R * S;
+    const void *col = x;  // 1x1 s1 p0: the NCHW activation already is [N][C, H*W]
+    if (!conv_is_1x1_direct(R, S, ph, pw, sh, sw)) {
+        int64_t need = it_b200_conv2d_workspace(dtype, N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups);
+        ITB_CHECK(workspace && workspace_bytes >= need, "conv: workspace %lld < %lld bytes",
+                  (long long)workspace_bytes, (long long)need);
+        int64_t total = (int64_t)N * Kc * P;
+        ITB_DISPATCH_FLOAT(dtype, "conv(im2col)", {
+            im2col_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T *)x, (T *)workspace, total, C, H, W, R, S,
+                                                                  OH, OW, ph, pw, sh, sw, dh, dw);
+        });
+        ITB_LAUNCH_CHECK("conv(im2col)");
+        col = workspace;
+    }
+    // y[n][f, p] = W[f, kc] . col[n][kc, p] : A = weights (batch-broadcast), B = col
+    const int Cg = C / groups, Fg = F / groups;
+    const int64_t Kg = (int64_t)Cg * R * S;
+    for (int gi = 0; gi < groups; ++gi) {
+        GemmArgs g{};
+        g.A = (const char *)w + (int64_t)gi * Fg * Kg * es;
+        g.B = (const char *)col + (int64_t)gi * Kg * P * es;
+        g.C = (char *)y + (int64_t)gi * Fg * P * es;
+        g.bias = nullptr;
+        g.batch = N;
+        g.m = Fg;
+        g.n = (int)P;
+        g.k = (int)Kg;
+        g.stride_a = 0;
+        g.stride_b = Kc * P;
+        g.trans_a = g.trans_b = 0;
+        g.act = 0;
+        if (groups == 1) {
+            int r = run_gemm(dtype, g, st);
+            if (r) return r;
+        } else {
+            // grouped: C batch stride is F*P, not Fg*P -> one launch per image
+            for (int n = 0; n < N; ++n) {
+                GemmArgs gn = g;
+                gn.batch = 1;
+                gn.B = (const char *)g.B + (int64_t)n * Kc * P * es;
+                gn.C = (char *)g.C + (int64_t)n * F * P * es;
+                int r = run_gemm(dtype, gn, st);
+                if (r) return r;
+            }
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,241 @@
+// gemm_skinny.cu -- decode-regime MatMul (M <= 64) for sm_100a: pure weight streaming, HBM-bound.
+//
+//   C[M,N] = X[M,K] . W[K,N] (+bias, act)      X, W, C: bf16 / fp16 row-major, fp32 accumulate
+//
+// Replaces the reference's cublasGemmEx call for the Llama decode shapes (matmul.cc:141-168;
+// q/k/v/o 16x4096x4096, gate/up 16x4096x11008, down 16x11008x4096, logits
+// 16x4096x32000).  The weight matrix is read exactly once:
+//   * TMA (cp.async.bulk.tensor.2d, 128B swizzle) streams 64(k) x 64(n) weight tiles and the
+//     matching 16*MT x 64 activation tile into a STAGES-deep shared-memory ring, completion on
+//     mbarriers; one producer lane issues, four consumer warps drain.
+//   * consumers feed legacy mma.sync m16n8k16 from the swizzled tiles with ldmatrix(.trans); at
+//     M = 16 the tensor pipe needs < 5 % of its rate to keep up with HBM, so the legacy path is
+//     not the limiter (the tcgen05 swap-AB variant lives in gemm_tc.cu for M > 64).
+//   * split-K across a thread-block CLUSTER (<= 8 CTAs along K): partial tiles are reduced by the
+//     rank-0 CTA through distributed shared memory, so there is no global workspace, no atomics
+//     and no second kernel; bias / activation / dtype conversion are fused into that store.
+// Grid = ceil(N/64) x splitK CTAs, two co-resident per SM (~100 KB smem each).
+#include <cooperative_groups.h>
+
+#include "gemm.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace itb {
+
+constexpr int SK_BN = 64, SK_BK = 64;
+constexpr int SK_W_BYTES = SK_BN * SK_BK * 2;  // 8 KB
+constexpr int SK_THREADS = 160;                // 4 consumer warps + 1 producer warp
+
+template <int MT> struct SkinnyCfg {
+    static constexpr int X_BYTES = MT * 16 * SK_BK * 2;
+    static constexpr int STAGES = MT == 1 ? 10 : (MT == 2 ? 8 : 6);
+    static constexpr int RED_BYTES = MT * 16 * SK_BN * 4;
+    static constexpr int SMEM = STAGES * (SK_W_BYTES + X_BYTES) + RED_BYTES + 2 * STAGES * 8 + 1024;
+};
+
+template <typename T, int MT>
+__global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_constant__ CUtensorMap mapW,
+                                                                 const __grid_constant__ CUtensorMap mapX,
+                                                                 GemmArgs g, int ktiles, int ktiles_per_split) {
+    using Cfg = SkinnyCfg<MT>;
+    constexpr int S = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled TMA tiles need 1024-byte alignment
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *w_sm = smem;
+    uint8_t *x_sm = smem + S * SK_W_BYTES;
+    float *red = reinterpret_cast<float *>(x_sm + S * Cfg::X_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(red) + Cfg::RED_BYTES);
+    uint64_t *empty = full + S;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * SK_BN;
+    const int split = blockIdx.y, nsplit = gridDim.y;
+    const int kt_begin = split * ktiles_per_split;
+    const int kt_end = min(ktiles, kt_begin + ktiles_per_split);
+    const int my_kt = max(0, kt_end - kt_begin);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&mapW);
+        tma_prefetch_desc(&mapX);
+    }
+    __syncthreads();
+
+    float acc[MT][2][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nb][i] = 0.f;
+
+    if (warp == 4) {
+        // ===== TMA producer (one lane) =====
+        if (lane == 0) {
+            const uint64_t pol_w = l2_policy_evict_first();  // weights are read once per step
+            const uint64_t pol_x = l2_policy_evict_last();   // activations are re-read by every N-tile
+            for (int it = 0; it < my_kt; ++it) {
+                const int s = it % S;
+                if (it >= S) mbar_wait(&empty[s], ((it / S) - 1) & 1);
+                mbar_expect_tx(&full[s], SK_W_BYTES + Cfg::X_BYTES);
+                const int k0 = (kt_begin + it) * SK_BK;
+                tma_load_2d(w_sm + s * SK_W_BYTES, &mapW, &full[s], n0, k0, pol_w);
+                tma_load_2d(x_sm + s * Cfg::X_BYTES, &mapX, &full[s], k0, 0, pol_x);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== consumers: warp w owns columns [16w, 16w+16) of the tile =====
+        const int mi = lane >> 3;             // which 8x8 matrix this lane addresses
+        const int r8 = lane & 7;
+        const uint32_t w_base = smem_u32(w_sm), x_base = smem_u32(x_sm);
+        for (int it = 0; it < my_kt; ++it) {
+            const int s = it % S;
+            mbar_wait(&full[s], (it / S) & 1);
+            const uint32_t wb = w_base + s * SK_W_BYTES, xb = x_base + s * Cfg::X_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < SK_BK / 16; ++kk) {
+                uint32_t a[MT][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int row = mt * 16 + r8 + 8 * (mi & 1);
+                    const int chunk = kk * 2 + (mi >> 1);
+                    ldmatrix_x4(a[mt][0], a[mt][1], a[mt][2], a[mt][3],
+                                xb + row * 128 + ((chunk ^ (row & 7)) << 4));
+                }
+                uint32_t b0, b1, b2, b3;
+                {
+                    const int krow = kk * 16 + r8 + 8 * (mi & 1);
+                    const int nchunk = warp * 2 + (mi >> 1);
+                    ldmatrix_x4_trans(b0, b1, b2, b3, wb + krow * 128 + ((nchunk ^ (krow & 7)) << 4));
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    mma_m16n8k16<T>(acc[mt][0], a[mt], b0, b1);
+                    mma_m16n8k16<T>(acc[mt][1], a[mt], b2, b3);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        // partial tile -> shared memory (fp32)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+                const int row = mt * 16 + (lane >> 2);
+                const int col = warp * 16 + nb * 8 + (lane & 3) * 2;
+                *reinterpret_cast<float2 *>(&red[row * SK_BN + col]) = make_float2(acc[mt][nb][0], acc[mt][nb][1]);
+                *reinterpret_cast<float2 *>(&red[(row + 8) * SK_BN + col]) =
+                    make_float2(acc[mt][nb][2], acc[mt][nb][3]);
+            }
+    }
+
+    // ===== split-K reduction through distributed shared memory + fused epilogue =====
+    if (nsplit > 1) cluster.sync(); else __syncthreads();
+    if (split == 0) {
+        const float *peers[8];
+        for (int r = 0; r < nsplit; ++r)
+            peers[r] = nsplit > 1 ? (const float *)cluster.map_shared_rank(red, r) : red;
+        const T *bias = (const T *)g.bias;
+        T *C = (T *)g.C;
+        for (int idx = threadIdx.x; idx < MT * 16 * (SK_BN / 2); idx += SK_THREADS) {
+            const int row = idx / (SK_BN / 2), col = (idx % (SK_BN / 2)) * 2;
+            const int gn = n0 + col;
+            if (row >= g.m || gn >= g.n) continue;
+            float2 v = make_float2(0.f, 0.f);
+            for (int r = 0; r < nsplit; ++r) {
+                float2 p = *reinterpret_cast<const float2 *>(&peers[r][row * SK_BN + col]);
+                v.x += p.x;
+                v.y += p.y;
+            }
+            if (bias) {
+                v.x += to_f(bias[row * g.bias_sm + gn * g.bias_sn]);
+                if (gn + 1 < g.n) v.y += to_f(bias[row * g.bias_sm + (gn + 1) * g.bias_sn]);
+            }
+            v.x = gemm_act(g.act, v.x);
+            v.y = gemm_act(g.act, v.y);
+            T *dst = C + (int64_t)row * g.n + gn;
+            if (gn + 1 < g.n && (g.n & 1) == 0) {
+                if constexpr (std::is_same<T, __nv_bfloat16>::value)
+                    *reinterpret_cast<__nv_bfloat162 *>(dst) = __floats2bfloat162_rn(v.x, v.y);
+                else
+                    *reinterpret_cast<__half2 *>(dst) = __floats2half2_rn(v.x, v.y);
+            } else {
+                dst[0] = from_f<T>(v.x);
+                if (gn + 1 < g.n) dst[1] = from_f<T>(v.y);
+            }
+        }
+    }
+    if (nsplit > 1) cluster.sync();  // peers' shared memory must outlive the leader's reads
+}
+
+template <typename T, int MT>
+static int launch_skinny_t(const GemmArgs &g, cudaStream_t st) {
+    using Cfg = SkinnyCfg<MT>;
+    CUtensorMap mapW, mapX;
+    if (!make_tma_2d_b16(&mapW, g.B, (uint64_t)g.k, (uint64_t)g.n, (uint64_t)g.n, SK_BK, SK_BN, 128))
+        ITB_FAIL("matmul(skinny): cuTensorMapEncodeTiled(W) failed");
+    if (!make_tma_2d_b16(&mapX, g.A, (uint64_t)g.m, (uint64_t)g.k, (uint64_t)g.k, MT * 16, SK_BK, 128))
+        ITB_FAIL("matmul(skinny): cuTensorMapEncodeTiled(X) failed");
+    const int tiles_n = (g.n + SK_BN - 1) / SK_BN;
+    const int ktiles = (g.k + SK_BK - 1) / SK_BK;
+    // enough CTAs for two per SM, at least 4 k-tiles per CTA, cluster <= 8
+    int splitk = (2 * kNumSMs) / tiles_n;
+    splitk = std::max(1, std::min(splitk, 8));
+    splitk = std::min(splitk, std::max(1, ktiles / 4));
+    int per = (ktiles + splitk - 1) / splitk;
+    splitk = (ktiles + per - 1) / per;  // no empty split
+
+    static bool attr_done = false;
+    auto kern = gemm_skinny_kernel<T, MT>;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        ITB_CHECK(e == cudaSuccess, "matmul(skinny): smem attribute: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tiles_n, splitk, 1);
+    cfg.blockDim = dim3(SK_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = splitk;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapW, mapX, g, ktiles, per);
+    ITB_CHECK(e == cudaSuccess, "matmul(skinny): launch failed: %s", cudaGetErrorString(e));
+    itb::count_launch();
+    return 0;
+}
+
+int launch_gemm_skinny(int dtype, const GemmArgs &g, cudaStream_t st) {
+    if (dtype != ITB_BF16 && dtype != ITB_F16) return -1;
+    if (g.batch != 1 || g.trans_a || g.trans_b || g.m > 64 || g.m < 1) return -1;
+    if (g.n % 8 != 0 || g.k % 8 != 0 || g.n < 64 || g.k < 64) return -1;
+    if (!aligned16(g.A) || !aligned16(g.B) || ((uintptr_t)g.C & 3)) return -1;
+    const int mt = (g.m + 15) / 16;
+#define SK_GO(TT)                                                                              \
+    do {                                                                                       \
+        if (mt == 1) return launch_skinny_t<TT, 1>(g, st);                                     \
+        if (mt == 2) return launch_skinny_t<TT, 2>(g, st);                                     \
+        return launch_skinny_t<TT, 4>(g, st);                                                  \
+    } while (0)
+    if (dtype == ITB_BF16) SK_GO(__nv_bfloat16);
+    SK_GO(__half);
+#undef SK_GO
+}
+
+}  // namespace itb

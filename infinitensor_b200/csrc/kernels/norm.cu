@@ -1,0 +1,301 @@
+// norm.cu -- Softmax, LayerNormalization, RMSNorm, RoPE for sm_100a.
+// HBM-bound row reductions: one read + one write of the tensor, fp32 accumulation, warp-shuffle
+// reductions; rows cached in registers (warp-per-row) or shared memory (block-per-row).
+//
+// Replaces (reference): softmax.cu:18-404, layer_norm.cu:4-557, rms_norm.cu:36-110, rope.cu:7-88.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace itb {
+
+// ------------------------------------------------------------------ last-axis, warp per row
+// MODE 0 softmax, 1 layernorm
+template <typename T, int ITEMS, int MODE>
+__global__ void __launch_bounds__(256) row_warp_kernel(const T *__restrict__ x, T *__restrict__ y,
+                                                       const T *__restrict__ scale, const T *__restrict__ bias,
+                                                       int64_t rows, int dim, int scale_size, int bias_size,
+                                                       float eps) {
+    int lane = threadIdx.x & 31;
+    int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const T *px = x + row * dim;
+    T *py = y + row * dim;
+    float v[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        int d = lane + i * 32;
+        v[i] = d < dim ? to_f(px[d]) : (MODE == 0 ? -INFINITY : 0.f);
+    }
+    if (MODE == 0) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) mx = fmaxf(mx, v[i]);
+        mx = warp_max(mx);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            v[i] = (lane + i * 32 < dim) ? expf(v[i] - mx) : 0.f;
+            s += v[i];
+        }
+        s = warp_sum(s);
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            int d = lane + i * 32;
+            if (d < dim) py[d] = from_f<T>(v[i] / s);
+        }
+    } else {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) s += v[i];
+        float mu = warp_sum(s) / (float)dim;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            float t = (lane + i * 32 < dim) ? v[i] - mu : 0.f;
+            q += t * t;
+        }
+        float rs = rsqrtf(warp_sum(q) / (float)dim + eps);
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            int d = lane + i * 32;
+            if (d < dim) {
+                float sc = to_f(scale[scale_size == dim ? d : 0]);
+                float bi = bias ? to_f(bias[bias_size == dim ? d : 0]) : 0.f;
+                py[d] = from_f<T>(sc * (v[i] - mu) * rs + bi);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ last-axis, block per row
+template <typename T, int MODE>
+__global__ void __launch_bounds__(1024) row_block_kernel(const T *__restrict__ x, T *__restrict__ y,
+                                                         const T *__restrict__ scale, const T *__restrict__ bias,
+                                                         int dim, int scale_size, int bias_size, float eps,
+                                                         int cache_in_smem) {
+    extern __shared__ float srow[];
+    __shared__ float red[32];
+    const T *px = x + blockIdx.x * (int64_t)dim;
+    T *py = y + blockIdx.x * (int64_t)dim;
+    auto ld = [&](int d) { return cache_in_smem ? srow[d] : to_f(px[d]); };
+    if (cache_in_smem) {
+        for (int d = threadIdx.x; d < dim; d += blockDim.x) srow[d] = to_f(px[d]);
+        __syncthreads();
+    }
+    if (MODE == 0) {
+        float mx = -INFINITY;
+        for (int d = threadIdx.x; d < dim; d += blockDim.x) mx = fmaxf(mx, ld(d));
+        mx = block_max(mx, red);
+        float s = 0.f;
+        for (int d = threadIdx.x; d < dim; d += blockDim.x) s += expf(ld(d) - mx);
+        s = block_sum(s, red);
+        for (int d = threadIdx.x; d < dim; d += blockDim.x) py[d] = from_f<T>(expf(ld(d) - mx) / s);
+    } else {
+        float s = 0.f;
+        for (int d = threadIdx.x; d < dim; d += blockDim.x) s += ld(d);
+        float mu = block_sum(s, red) / (float)dim;
+        float q = 0.f;
+        for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+            float t = ld(d) - mu;
+            q += t * t;
+        }
+        float rs = rsqrtf(block_sum(q, red) / (float)dim + eps);
+        for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+            float sc = to_f(scale[scale_size == dim ? d : 0]);
+            float bi = bias ? to_f(bias[bias_size == dim ? d : 0]) : 0.f;
+            py[d] = from_f<T>(sc * (ld(d) - mu) * rs + bi);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ strided axis: thread per (outer, inner)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) strided_kernel(const T *__restrict__ x, T *__restrict__ y,
+                                                      const T *__restrict__ scale, const T *__restrict__ bias,
+                                                      int64_t outer, int dim, int64_t inner, int scale_size,
+                                                      int bias_size, float eps) {
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= outer * inner) return;
+    int64_t o = idx / inner, i = idx - o * inner;
+    const T *px = x + o * dim * inner + i;
+    T *py = y + o * dim * inner + i;
+    if (MODE == 0) {
+        float mx = -INFINITY;
+        for (int d = 0; d < dim; ++d) mx = fmaxf(mx, to_f(px[d * inner]));
+        float s = 0.f;
+        for (int d = 0; d < dim; ++d) s += expf(to_f(px[d * inner]) - mx);
+        for (int d = 0; d < dim; ++d) py[d * inner] = from_f<T>(expf(to_f(px[d * inner]) - mx) / s);
+    } else {
+        float s = 0.f;
+        for (int d = 0; d < dim; ++d) s += to_f(px[d * inner]);
+        float mu = s / (float)dim, q = 0.f;
+        for (int d = 0; d < dim; ++d) {
+            float t = to_f(px[d * inner]) - mu;
+            q += t * t;
+        }
+        float rs = rsqrtf(q / (float)dim + eps);
+        for (int d = 0; d < dim; ++d) {
+            float sc = to_f(scale[scale_size == dim ? d : 0]);
+            float bi = bias ? to_f(bias[bias_size == dim ? d : 0]) : 0.f;
+            py[d * inner] = from_f<T>(sc * (to_f(px[d * inner]) - mu) * rs + bi);
+        }
+    }
+}
+
+template <typename T, int MODE>
+static int launch_rowop(const char *name, const T *x, T *y, const T *scale, const T *bias, int64_t outer,
+                        int dim, int64_t inner, int scale_size, int bias_size, float eps, cudaStream_t st) {
+    if (outer * inner == 0 || dim == 0) return 0;
+    if (inner != 1) {
+        int64_t n = outer * inner;
+        strided_kernel<T, MODE><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, scale, bias, outer, dim,
+                                                                           inner, scale_size, bias_size, eps);
+    } else if (dim <= 1024) {
+        int64_t rows = outer;
+        unsigned grid = (unsigned)((rows * 32 + 255) / 256);
+#define RW(I)                                                                                  \
+    row_warp_kernel<T, I, MODE><<<grid, 256, 0, st>>>(x, y, scale, bias, rows, dim, scale_size, bias_size, eps)
+        if (dim <= 32) RW(1);
+        else if (dim <= 64) RW(2);
+        else if (dim <= 128) RW(4);
+        else if (dim <= 256) RW(8);
+        else if (dim <= 512) RW(16);
+        else RW(32);
+#undef RW
+    } else {
+        int cache = dim <= 12288;
+        int threads = dim >= 8192 ? 1024 : 512;
+        row_block_kernel<T, MODE><<<(unsigned)outer, threads, cache ? dim * sizeof(float) : 0, st>>>(
+            x, y, scale, bias, dim, scale_size, bias_size, eps, cache);
+    }
+    ITB_LAUNCH_CHECK(name);
+    return 0;
+}
+
+// ------------------------------------------------------------------ RMSNorm
+// y = T( T(x * rsqrt(mean(x^2) + 1e-5)) * w )   (rms_norm.cu:46,52 -- round before weight)
+template <typename T>
+__global__ void __launch_bounds__(512) rmsnorm_kernel(const T *__restrict__ x, const T *__restrict__ w,
+                                                      T *__restrict__ y, int hidden, bool vec) {
+    constexpr int V = Vec16<T>::N;
+    __shared__ float red[32];
+    const T *px = x + blockIdx.x * (int64_t)hidden;
+    T *py = y + blockIdx.x * (int64_t)hidden;
+    float ss = 0.f;
+    if (vec) {
+        int nv = hidden / V;
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+            Vec16<T> a = ld16(px + i * V);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float f = to_f(a.v[j]);
+                ss += f * f;
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < hidden; i += blockDim.x) {
+            float f = to_f(px[i]);
+            ss += f * f;
+        }
+    }
+    float r = rsqrtf(block_sum(ss, red) / (float)hidden + 0.00001f);
+    if (vec) {
+        int nv = hidden / V;
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+            Vec16<T> a = ld16(px + i * V), ww = ld16(w + i * V), o;
+#pragma unroll
+            for (int j = 0; j < V; ++j) o.v[j] = from_f<T>(round_t<T>(to_f(a.v[j]) * r) * to_f(ww.v[j]));
+            st16(py + i * V, o);
+        }
+    } else {
+        for (int i = threadIdx.x; i < hidden; i += blockDim.x)
+            py[i] = from_f<T>(round_t<T>(to_f(px[i]) * r) * to_f(w[i]));
+    }
+}
+
+// ------------------------------------------------------------------ RoPE (rotate-half)
+template <typename T, typename P>
+__global__ void __launch_bounds__(256) rope_kernel(const P *__restrict__ pos, const T *__restrict__ x,
+                                                   T *__restrict__ y, int64_t rows, int dim_model,
+                                                   int dim_head) {
+    int half = dim_head >> 1;
+    int pairs_per_row = dim_model >> 1;
+    int64_t total = rows * pairs_per_row;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = i / pairs_per_row;
+        int pr = (int)(i - row * pairs_per_row);
+        int head = pr / half, c = pr - head * half;
+        int lo = head * dim_head + c, hi = lo + half;
+        float p = (float)(int)pos[row];
+        float freq = p * powf(10000.f, -(float)(c * 2) / (float)dim_head);
+        float cs = round_t<T>(cosf(freq)), sn = round_t<T>(sinf(freq));
+        float xl = to_f(x[row * dim_model + lo]), xh = to_f(x[row * dim_model + hi]);
+        // arithmetic in T exactly as rope.cu:21-29: each product and the sum rounded to T
+        float ol = round_t<T>(xl * cs) - round_t<T>(xh * sn);
+        float oh = round_t<T>(xh * cs) + round_t<T>(xl * sn);
+        y[row * dim_model + lo] = from_f<T>(ol);
+        y[row * dim_model + hi] = from_f<T>(oh);
+    }
+}
+
+}  // namespace itb
+
+using namespace itb;
+
+extern "C" int it_b200_softmax(int dtype, const void *x, void *y, int64_t outer, int dim, int64_t inner,
+                               void *stream) {
+    ITB_DISPATCH_FLOAT(dtype, "softmax", {
+        return launch_rowop<T, 0>("softmax", (const T *)x, (T *)y, nullptr, nullptr, outer, dim, inner, 0, 0, 0.f,
+                                  (cudaStream_t)stream);
+    });
+    return 0;
+}
+
+extern "C" int it_b200_layernorm(int dtype, const void *x, const void *scale, const void *bias, void *y,
+                                 int64_t outer, int dim, int64_t inner, int scale_size, int bias_size,
+                                 float eps, void *stream) {
+    ITB_CHECK(scale_size == dim || scale_size == 1, "layernorm: scale size %d must be %d or 1", scale_size, dim);
+    ITB_CHECK(!bias || bias_size == dim || bias_size == 1, "layernorm: bias size %d must be %d or 1", bias_size,
+              dim);
+    ITB_DISPATCH_FLOAT(dtype, "layernorm", {
+        return launch_rowop<T, 1>("layernorm", (const T *)x, (T *)y, (const T *)scale, (const T *)bias, outer, dim,
+                                  inner, scale_size, bias_size, eps, (cudaStream_t)stream);
+    });
+    return 0;
+}
+
+extern "C" int it_b200_rmsnorm(int dtype, const void *x, const void *w, void *y, int64_t tokens, int hidden,
+                               void *stream) {
+    if (tokens == 0 || hidden == 0) return 0;
+    ITB_DISPATCH_FLOAT(dtype, "rmsnorm", {
+        bool vec = aligned16(x) && aligned16(w) && aligned16(y) && hidden % Vec16<T>::N == 0;
+        int threads = hidden >= 4096 ? 512 : (hidden >= 1024 ? 256 : 128);
+        rmsnorm_kernel<T><<<(unsigned)tokens, threads, 0, (cudaStream_t)stream>>>((const T *)x, (const T *)w,
+                                                                                  (T *)y, hidden, vec);
+    });
+    ITB_LAUNCH_CHECK("rmsnorm");
+    return 0;
+}
+
+extern "C" int it_b200_rope(int dtype, const void *pos, int pos_dtype, const void *x, void *y, int B, int S,
+                            int dim_model, int dim_head, void *stream) {
+    ITB_CHECK(dim_head > 0 && dim_head % 2 == 0 && dim_model % dim_head == 0,
+              "rope: dim_model %d must be a multiple of dim_head %d", dim_model, dim_head);
+    int64_t rows = (int64_t)B * S;
+    if (rows == 0) return 0;
+    int64_t total = rows * (dim_model / 2);
+    auto st = (cudaStream_t)stream;
+    ITB_DISPATCH_FLOAT(dtype, "rope", {
+        int g = grid_for(total, 256);
+        if (pos_dtype == ITB_I64)
+            rope_kernel<T, int64_t><<<g, 256, 0, st>>>((const int64_t *)pos, (const T *)x, (T *)y, rows, dim_model, dim_head);
+        else if (pos_dtype == ITB_I32 || pos_dtype == ITB_U32)
+            rope_kernel<T, int32_t><<<g, 256, 0, st>>>((const int32_t *)pos, (const T *)x, (T *)y, rows, dim_model, dim_head);
+        else
+            ITB_FAIL("rope: unsupported position dtype %d", pos_dtype);
+    });
+    ITB_LAUNCH_CHECK("rope");
+    return 0;
+}

@@ -1,0 +1,24 @@
+// support.cu -- error string + launch counter shared by every launcher.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace itb {
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
+}  // namespace itb
+
+extern "C" const char *it_b200_last_error(void) { return itb::g_err; }
+extern "C" int it_b200_version(void) { return 1; }
+extern "C" long long it_b200_launch_count(void) { return itb::launches(); }

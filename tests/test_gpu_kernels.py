@@ -1,0 +1,314 @@
+"""GPU parity tests: every C-ABI launcher vs (a) the reference's golden vectors and (b) the CPU oracle
+on seeded inputs.  Tolerances are the ones SURVEY.md 8(c) states per op, written next to each check.
+Run with `pytest -m gpu` on a B200 (gpurun)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle
+from tests.golden import reference_vectors as G
+
+F32, F16, BF16 = 1, 10, 16
+# relative tolerance of one rounding step in the storage dtype
+EPS = {F32: 2.0 ** -23, F16: 2.0 ** -10, BF16: 2.0 ** -7}
+
+
+@pytest.fixture(scope="module")
+def K():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from tests import kernel_harness
+    return kernel_harness
+
+
+def close(got, exp, rel, abs_):
+    got = np.asarray(got, np.float64).ravel()
+    exp = np.asarray(exp, np.float64).ravel()
+    assert got.shape == exp.shape, (got.shape, exp.shape)
+    np.testing.assert_allclose(got, exp, rtol=rel, atol=abs_)
+
+
+def rnd(shape, seed, dt=F32, scale=1.0):
+    x = (np.random.default_rng(seed).standard_normal(shape) * scale).astype(np.float32)
+    return oracle.round_to(x, dt)
+
+
+# ------------------------------------------------------------------ golden vectors of the reference
+@pytest.mark.parametrize("c", G.MATMUL)
+def test_matmul_golden(K, c):
+    close(K.matmul(c["a"], c["b"], transA=c["tA"], transB=c["tB"]), c["out"], 1e-6, 1e-6)
+
+
+@pytest.mark.parametrize("c", G.CONV)
+def test_conv_golden(K, c):
+    close(K.conv2d(c["x"], c["w"], *c["args"]), c["out"], 1e-6, 1e-6)
+    close(K.conv2d(c["x"], c["w"], *c["args"], dt=F16), oracle.conv2d(c["x"], c["w"], *c["args"], dt=F16), 1e-3, 1e-3)
+
+
+@pytest.mark.parametrize("c", G.SOFTMAX)
+def test_softmax_golden(K, c):
+    close(K.softmax(c["x"], c["axis"], dt=c["dt"]), c["out"], 2e-6 if c["dt"] == 1 else 1e-6, 1e-9)
+
+
+@pytest.mark.parametrize("c", G.LAYERNORM)
+def test_layernorm_golden(K, c):
+    bias = None if c["bias"] is None else np.array(c["bias"], np.float32)
+    got = K.layer_norm(c["x"], np.array(c["scale"], np.float32), bias, 1e-5, c["axis"], dt=c["dt"])
+    close(got, c["out"], 2e-6, 3e-7)
+
+
+def test_attention_golden(K):
+    c = G.ATTENTION
+    z = np.zeros((1, 1, 1, 128), np.float32)
+    one = np.ones((1, 1, 1, 128), np.float32)
+    out, kc, vc = K.attention_kvcache(z, z, one, one, one, c["pos"], pos_np_dtype=np.uint32)
+    close(out, c["out"], 1e-6, 0)
+    assert np.array_equal(kc, one) and np.array_equal(vc, one)  # in-place append
+
+
+def test_rope_golden(K):
+    x = np.zeros((1, 1, 128), np.float32)
+    x[..., :64] = 1.0
+    out = K.rope(np.array([[1]]), x, pos_np_dtype=np.uint32)
+    close(out[0, 0, :32], G.ROPE_COS, 2e-6, 1e-6)
+
+
+@pytest.mark.parametrize("c", G.ELEMENTWISE)
+def test_elementwise_golden(K, c):
+    close(K.binary(c["op"], c["a"], c["b"]), c["out"], 1e-6, 0)
+
+
+@pytest.mark.parametrize("c", G.POOL)
+def test_pool_golden(K, c):
+    close(K.pool2d(c["kind"], c["x"], *c["kdps"]), c["out"], 2e-6, 0)
+
+
+def test_batchnorm_golden(K):
+    c = G.BATCHNORM
+    close(K.batch_norm(c["x"], c["mean"], c["var"], c["scale"], c["bias"], c["eps"]), c["out"], 2e-6, 1e-7)
+
+
+@pytest.mark.parametrize("c", G.REDUCE)
+def test_reduce_golden(K, c):
+    close(K.reduce(c["kind"], c["x"], c["axes"], c["keep"]), c["out"], 1e-6, 0)
+
+
+def test_movement_golden(K):
+    c = G.TRANSPOSE
+    assert K.transpose(c["x"], c["perm"]).ravel().tolist() == c["out"]
+    for c in G.CONCAT:
+        assert K.concat(c["xs"], c["dim"]).ravel().tolist() == c["out"]
+    c = G.SPLIT
+    assert [o.ravel().tolist() for o in K.split(c["x"], c["axis"], [3, 3, 4])] == c["outs"]
+    for c in G.GATHER:
+        assert K.gather(c["x"], c["idx"], c["axis"]).ravel().tolist() == c["out"]
+    for c in G.WHERE:
+        assert K.where(c["c"], c["x"], c["y"]).ravel().tolist() == c["out"]
+    assert K.expand(G.EXPAND["x"], G.EXPAND["dims"]).ravel().tolist() == G.EXPAND["out"]
+    c = G.PAD   # pads {1,0,1,1} axes {0,3} -> start = -begin
+    assert K.pad_slice(c["x"], (3, 2, 3, 3), [-1, 0, 0, 0], [1, 1, 1, 1]).ravel().tolist() == c["out"]
+    c = G.SLICE
+    assert K.pad_slice(c["x"], (1, 2, 1, 4), [1, 0, 0, 1], [1, 1, 1, 1]).ravel().tolist() == c["out"]
+
+
+# ------------------------------------------------------------------ seeded parity vs the oracle
+@pytest.mark.parametrize("dt", [F32, F16, BF16])
+@pytest.mark.parametrize("name", ["relu", "sigmoid", "tanh", "gelu", "silu", "erf", "neg", "abs", "sqrt",
+                                  "hardsigmoid", "hardswish"])
+def test_unary_parity(K, name, dt):
+    x = rnd((3, 7, 129), 1, dt, 2.0)
+    if name == "sqrt":
+        x = np.abs(x)
+    # fp32: <= 2 ulp vs oracle (reference test uses rel 1e-6); half types: 1 rounding step
+    close(K.unary(name, x, dt), oracle.unary(name, x, dt), 4 * EPS[dt] if dt == F32 else 2 * EPS[dt], 1e-7)
+
+
+@pytest.mark.parametrize("dt", [F32, F16, BF16])
+@pytest.mark.parametrize("name", ["add", "sub", "mul", "div", "min", "max", "pow", "less"])
+def test_binary_parity(K, name, dt):
+    a, b = rnd((2, 1, 5, 64), 2, dt), rnd((3, 1, 64), 3, dt)
+    if name in ("div",):
+        b = np.where(np.abs(b) < 0.1, 0.5, b).astype(np.float32)
+    if name == "pow":
+        a = np.abs(a) + 0.1
+    close(K.binary(name, a, b, dt), oracle.binary(name, a, b, dt), 8 * EPS[dt] if name == "pow" else 2 * EPS[dt], 1e-7)
+    # same-shape + scalar fast paths
+    c = rnd((4, 1000), 4, dt)
+    close(K.binary(name, np.abs(c) + 0.1, np.abs(c[::-1].copy()) + 0.2, dt),
+          oracle.binary(name, np.abs(c) + 0.1, np.abs(c[::-1].copy()) + 0.2, dt), 8 * EPS[dt], 1e-7)
+    s = oracle.round_to(np.array([1.5], np.float32), dt)
+    close(K.binary(name, np.abs(c) + 0.1, s, dt), oracle.binary(name, np.abs(c) + 0.1, s, dt), 8 * EPS[dt], 1e-7)
+
+
+@pytest.mark.parametrize("dt", [F32, F16, BF16])
+@pytest.mark.parametrize("shape,axis", [((2, 12, 128, 128), -1), ((4, 3000), 1), ((3, 5, 7), 1), ((2, 20000), -1)])
+def test_softmax_parity(K, shape, axis, dt):
+    x = rnd(shape, 5, dt, 3.0)
+    tol = {F32: 1e-5, F16: 1e-3, BF16: 1e-2}[dt]  # norms/softmax 1e-5 / 1e-3 / 1e-2 rel
+    close(K.softmax(x, axis, dt), oracle.softmax(x, axis, dt), tol, tol * 1e-3)
+
+
+@pytest.mark.parametrize("dt", [F32, F16, BF16])
+@pytest.mark.parametrize("shape,axis", [((1, 128, 768), -1), ((4, 2500), 1), ((3, 5, 6), 1)])
+def test_layernorm_parity(K, shape, axis, dt):
+    x = rnd(shape, 6, dt)
+    dim = shape[axis]
+    sc, bi = rnd((dim,), 7, dt), rnd((dim,), 8, dt)
+    tol = {F32: 1e-5, F16: 1e-3, BF16: 1e-2}[dt]
+    close(K.layer_norm(x, sc, bi, 1e-5, axis, dt), oracle.layer_norm(x, sc, bi, 1e-5, axis, dt), tol, tol)
+    close(K.layer_norm(x, sc[:1], None, 1e-5, axis, dt), oracle.layer_norm(x, sc[:1], None, 1e-5, axis, dt), tol, tol)
+
+
+@pytest.mark.parametrize("dt", [F32, F16, BF16])
+@pytest.mark.parametrize("shape", [(16, 1, 4096), (3, 100), (5, 1000)])
+def test_rmsnorm_parity(K, shape, dt):
+    x, w = rnd(shape, 9, dt), 1 + rnd(shape[-1:], 10, dt, 0.02)
+    w = oracle.round_to(w, dt)
+    tol = {F32: 1e-5, F16: 1e-3, BF16: 1e-2}[dt]
+    got, ref = K.rms_norm(x, w, dt), oracle.rms_norm(x, w, dt)
+    close(got, ref, tol, tol * 1e-2)
+    if dt != F32:  # rounding order of rms_norm.cu:52 reproduced: overwhelmingly bit-identical
+        assert np.mean(got == ref) > 0.98
+
+
+@pytest.mark.parametrize("dt", [F32, F16, BF16])
+def test_rope_parity(K, dt):
+    x = rnd((16, 1, 4096), 11, dt)
+    pos = np.full((16, 1), 511)
+    pos[3, 0] = 0
+    pos[5, 0] = 1023
+    tol = {F32: 2e-4, F16: 2e-3, BF16: 1.6e-2}[dt]  # cos/sin of angles up to 1023 rad in float
+    close(K.rope(pos, x, dt), oracle.rope(pos, x, dt=dt), tol, tol)
+    x2 = rnd((2, 3, 256), 12, dt)
+    pos2 = np.arange(6).reshape(2, 3) * 7
+    close(K.rope(pos2, x2, dt, pos_np_dtype=np.int32), oracle.rope(pos2, x2, dt=dt), tol, tol)
+
+
+@pytest.mark.parametrize("es", [np.uint8, np.float16, np.float32, np.int64])
+def test_movement_parity(K, es):
+    rng = np.random.default_rng(13)
+    def mk(shape):
+        return rng.integers(0, 100, size=shape).astype(es)
+    x = mk((2, 128, 12, 64))
+    assert np.array_equal(K.transpose(x, (0, 2, 1, 3)), oracle.transpose(x, (0, 2, 1, 3)))
+    assert np.array_equal(K.transpose(x, (0, 2, 3, 1)), oracle.transpose(x, (0, 2, 3, 1)))
+    assert np.array_equal(K.transpose(x, (3, 1, 0, 2)), oracle.transpose(x, (3, 1, 0, 2)))
+    y = mk((5, 33, 65))
+    assert np.array_equal(K.transpose(y, (2, 1, 0)), oracle.transpose(y, (2, 1, 0)))
+    assert np.array_equal(K.transpose(y, (0, 2, 1)), oracle.transpose(y, (0, 2, 1)))
+    assert np.array_equal(K.transpose(y, (0, 1, 2)), y)
+    parts = [mk((3, 5, 8)), mk((3, 1, 8)), mk((3, 10, 8))]
+    assert np.array_equal(K.concat(parts, 1), oracle.concat(parts, 1))
+    many = [mk((2, 3)) for _ in range(40)]  # > 32 parts -> two launches
+    assert np.array_equal(K.concat(many, 1), oracle.concat(many, 1))
+    big = mk((1, 128, 2304))
+    for got, ref in zip(K.split(big, 2, [768, 768, 768]), oracle.split(big, 2, 3)):
+        assert np.array_equal(got, ref)
+    emb = mk((1000, 96))
+    idx = rng.integers(0, 1000, size=(16, 1)).astype(np.int64)
+    assert np.array_equal(K.gather(emb, idx, 0), oracle.gather(emb, idx, 0))
+    assert np.array_equal(K.gather(emb, idx.astype(np.int32), 1 - 1), oracle.gather(emb, idx, 0))
+    g3 = mk((4, 9, 5))
+    i3 = np.array([[8, 0], [3, -1]], np.int64)  # negative index wraps (ONNX)
+    assert np.array_equal(K.gather(g3, i3, 1), oracle.gather(g3, i3, 1))
+    c = rng.integers(0, 2, size=(2, 1, 5)).astype(np.uint8)
+    a, b = mk((3, 1)), mk((2, 3, 5))
+    assert np.array_equal(K.where(c, a, b), oracle.where(c, a, b))
+    e = mk((2, 1, 4, 1))
+    assert np.array_equal(K.expand(e, (2, 3, 4, 5)), oracle.expand(e, (2, 3, 4, 5)))
+    s = mk((4, 6, 10))
+    assert np.array_equal(K.pad_slice(s, (2, 3, 4), [1, 0, 9], [1, 2, -2]), oracle.slice_(s, [1, 0, 9], [3, 6, 1], None, [1, 2, -2]))
+    assert np.array_equal(K.pad_slice(s, (5, 6, 13), [-1, 0, -2], [1, 1, 1]), oracle.pad(s, [1, 0, 2, 0, 0, 1]))
+
+
+@pytest.mark.parametrize("dt", [F32, F16, BF16])
+def test_reduce_pool_bn_parity(K, dt):
+    x = rnd((2, 128, 768), 14, dt)
+    tol = {F32: 1e-5, F16: 2e-3, BF16: 1.6e-2}[dt]
+    close(K.reduce("mean", x, [-1], True, dt), oracle.reduce("mean", x, [-1], True, dt), tol, tol * 0.1)
+    close(K.reduce("sum", x, [0, 2], False, dt), oracle.reduce("sum", x, [0, 2], False, dt), tol, tol)
+    img = rnd((2, 8, 17, 19), 15, dt)
+    close(K.pool2d("max", img, 3, 3, 1, 1, 1, 1, 2, 2, dt), oracle.pool2d("max", img, 3, 3, 1, 1, 1, 1, 2, 2, dt=dt), 0, 0)
+    close(K.pool2d("avg", img, 3, 2, 1, 1, 1, 0, 2, 1, dt), oracle.pool2d("avg", img, 3, 2, 1, 1, 1, 0, 2, 1, dt=dt), tol, tol)
+    m, v = rnd((8,), 16), np.abs(rnd((8,), 17)) + 0.5
+    s, b = rnd((8,), 18), rnd((8,), 19)
+    close(K.batch_norm(img, m, v, s, b, 1e-5, dt), oracle.batch_norm(img, m, v, s, b, 1e-5, dt), tol, tol)
+
+
+def gemm_tol(dt, k, amax, bmax):
+    """fp32 rel 1e-5*sqrt(K); 16-bit with fp32 accumulate: abs <= 2^-8 (bf16) / 2^-11 (fp16)
+    * sqrt(K) * max|a| * max|b| against an fp32 oracle fed the same rounded inputs."""
+    if dt == F32:
+        return 1e-5 * np.sqrt(k) * amax * bmax
+    return (2.0 ** -8 if dt == BF16 else 2.0 ** -11) * np.sqrt(k) * amax * bmax
+
+
+@pytest.mark.parametrize("dt", [F32, F16, BF16])
+@pytest.mark.parametrize("shape", [
+    # (A shape, B shape, transA, transB, bias shape)
+    ((512, 512), (512, 512), False, False, None),           # BASELINE config #1
+    ((2, 3, 37, 53), (2, 3, 53, 29), False, False, None),   # batched, odd sizes -> SIMT path
+    ((12, 128, 64), (12, 64, 128), False, False, None),     # GPT-2 q.k^T shape
+    ((4, 70, 33), (33, 50), False, False, (50,)),           # batch-broadcast B + bias
+    ((2, 40, 30), (2, 40, 20), True, False, None),          # transA
+    ((5, 30, 40), (5, 20, 40), False, True, (5, 30, 20)),   # transB + full bias
+])
+def test_matmul_parity(K, shape, dt):
+    sa, sb, tA, tB, sbias = shape
+    a, b = rnd(sa, 20, dt), rnd(sb, 21, dt)
+    bias = rnd(sbias, 22, dt) if sbias else None
+    k = sa[-2] if tA else sa[-1]
+    tol = gemm_tol(dt, k, np.abs(a).max(), np.abs(b).max())
+    close(K.matmul(a, b, bias, tA, tB, dt), oracle.matmul(a, b, bias, tA, tB, dt), 2 * EPS[dt], tol)
+
+
+@pytest.mark.parametrize("dt", [BF16, F16])
+@pytest.mark.parametrize("m,k,n", [(16, 4096, 4096), (16, 4096, 11008), (16, 11008, 4096), (1, 256, 64),
+                                   (7, 320, 200), (16, 4096, 32000), (33, 1024, 1024), (64, 512, 4160), (16, 72, 64)])
+def test_matmul_skinny_parity(K, m, k, n, dt):
+    """Decode-regime GEMM (TMA + cluster split-K kernel) at the Llama-7B shapes of SURVEY 8a row a1."""
+    a, b = rnd((m, k), 23, dt, 0.5), rnd((k, n), 24, dt, 0.05)
+    tol = gemm_tol(dt, k, np.abs(a).max(), np.abs(b).max())
+    got = K.matmul(a, b, None, False, False, dt)
+    ref = oracle.matmul(a, b, None, False, False, dt)
+    close(got, ref, 2 * EPS[dt], tol)
+    bias = rnd((n,), 25, dt)
+    close(K.matmul(a, b, bias, False, False, dt, act=1), np.maximum(oracle.matmul(a, b, bias, False, False, dt), 0),
+          2 * EPS[dt], tol)
+
+
+@pytest.mark.parametrize("dt", [F32, F16, BF16])
+def test_conv_parity(K, dt):
+    tol = {F32: 1e-4, F16: 4e-3, BF16: 3e-2}[dt]
+    for (xs, ws, args) in [((2, 16, 14, 14), (32, 16, 3, 3), (1, 1, 1, 1, 1, 1)),
+                           ((2, 3, 32, 32), (8, 3, 7, 7), (3, 3, 2, 2, 1, 1)),
+                           ((2, 64, 8, 8), (128, 64, 1, 1), (0, 0, 1, 1, 1, 1)),
+                           ((1, 8, 9, 9), (8, 2, 3, 3), (1, 1, 2, 2, 1, 1))]:  # groups = 4
+        x, w = rnd(xs, 26, dt), rnd(ws, 27, dt, 0.2)
+        close(K.conv2d(x, w, *args, dt=dt), oracle.conv2d(x, w, *args, dt=dt), tol, tol)
+
+
+@pytest.mark.parametrize("dt", [F32, F16, BF16])
+@pytest.mark.parametrize("B,H,S,pos", [(2, 4, 64, 0), (2, 4, 64, 37), (16, 32, 1024, 511), (1, 2, 1024, 1023),
+                                       (1, 32, 256, 100)])
+def test_attention_parity(K, B, H, S, pos, dt):
+    kc, vc = rnd((B, H, S, 128), 28, dt, 0.5), rnd((B, H, S, 128), 29, dt, 0.5)
+    q, k, v = rnd((B, H, 1, 128), 30, dt, 0.5), rnd((B, H, 1, 128), 31, dt, 0.5), rnd((B, H, 1, 128), 32, dt, 0.5)
+    kc_ref, vc_ref = kc.copy(), vc.copy()
+    ref = oracle.attention_kvcache(kc_ref, vc_ref, q, k, v, pos, dt)
+    out, kc_got, vc_got = K.attention_kvcache(kc, vc, q, k, v, pos, dt)
+    tol = {F32: 1e-5, F16: 1e-3, BF16: 1e-2}[dt]
+    close(out, ref, tol, tol * 0.05)
+    assert np.array_equal(kc_got, kc_ref) and np.array_equal(vc_got, vc_ref)  # append is bit-exact, rest untouched
+
+
+def test_error_reporting(K):
+    import torch
+    from infinitensor_b200 import _lib as L
+    x = torch.zeros(8, device="cuda")
+    assert L.lib.it_b200_unary(99, 1, K.ptr(x), K.ptr(x), 8, K.stream()) != 0
+    assert "bad op" in L.last_error()
+    with pytest.raises(L.B200BackendError):
+        L.check(L.lib.it_b200_attention_kvcache(1, K.ptr(x), K.ptr(x), K.ptr(x), K.ptr(x), K.ptr(x), K.ptr(x), 7,
+                                                K.ptr(x), 1, 1, 1, 64, None, 0, K.stream()))
