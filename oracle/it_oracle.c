@@ -197,8 +197,9 @@ void orc_softmax(const float *x, float *y, int64_t outer, int dim, int64_t inner
         float *py = y + o * dim * inner + i;
         float mx = -INFINITY;
         for (int d = 0; d < dim; ++d) mx = fmaxf(mx, px[d * inner]);
-        float sum = 0.f;
-        for (int d = 0; d < dim; ++d) sum += expf(px[d * inner] - mx);
+        double sumd = 0.0; /* the reference reduces as a tree (cub::BlockReduce); a double sum is order-free */
+        for (int d = 0; d < dim; ++d) sumd += (double)expf(px[d * inner] - mx);
+        float sum = (float)sumd;
         for (int d = 0; d < dim; ++d) py[d * inner] = orc_round(expf(px[d * inner] - mx) / sum, dt);
     }
 }
@@ -217,15 +218,15 @@ void orc_layernorm(const float *x, const float *scale, const float *bias, float 
         int64_t o = oi / inner, i = oi % inner;
         const float *px = x + o * dim * inner + i;
         float *py = y + o * dim * inner + i;
-        float mu = 0.f;
-        for (int d = 0; d < dim; ++d) mu += px[d * inner];
-        mu /= (float)dim;
-        float var = 0.f;
+        double mud = 0.0; /* order-free sums (the reference reduces as a tree) */
+        for (int d = 0; d < dim; ++d) mud += (double)px[d * inner];
+        float mu = (float)(mud / dim);
+        double vard = 0.0;
         for (int d = 0; d < dim; ++d) {
             float t = px[d * inner] - mu;
-            var += t * t;
+            vard += (double)(t * t);
         }
-        var /= (float)dim;
+        float var = (float)(vard / dim);
         float rs = 1.0f / sqrtf(var + eps);
         for (int d = 0; d < dim; ++d) {
             float s = scale[scaleSize == dim ? d : 0];
