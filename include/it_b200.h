@@ -220,6 +220,8 @@ int itb_graph_data_malloc(itb_graph *g, int use_naive_allocator, int64_t mem_poo
 int itb_graph_run(itb_graph *g);
 int itb_graph_run_without_sync(itb_graph *g);
 int itb_graph_run_with_cudagraph(itb_graph *g);
+/* graph replay without the trailing stream synchronise (serving loop: copyin_async -> launch -> copyout_async -> sync) */
+int itb_graph_launch_cudagraph_async(itb_graph *g);
 int itb_graph_tune(itb_graph *g);
 int itb_graph_sync(itb_graph *g);
 double itb_graph_get_perf_time(itb_graph *g);

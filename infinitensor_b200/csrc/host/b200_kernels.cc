@@ -1,0 +1,482 @@
+// b200_kernels.cc -- the plugin layer: one Kernel subclass per hot operator, registered through
+// REGISTER_KERNEL(Device::CUDA, OpType::X, ...) exactly like the reference's src/kernels/cuda/*.cc,
+// each bottoming out in one extern "C" it_b200_* launcher (include/it_b200.h).  Because the registry
+// rejects duplicate keys (reference include/core/kernel.h:150-156) this set REPLACES the reference's
+// src/kernels/cuda directory in a build; there is no second backend and no CPU fallback.
+#include <nccl.h>
+
+#include "b200_runtime.h"
+#include "it_b200.h"
+#include "operators.h"
+
+namespace infini {
+
+static inline void CK(int ret, const Operator &op) {
+    if (ret != 0) throw Exception(string(it_b200_last_error()) + " in " + op->toString());
+}
+static inline void *S() { return (void *)CUDAStream::getCurrentStream(); }
+static inline const CudaRuntimeObj *RT(const RuntimeObj *ctx) {
+    auto rt = dynamic_cast<const CudaRuntimeObj *>(ctx);
+    IT_ASSERT(rt != nullptr, "kernel invoked on a non-CUDA runtime");
+    return rt;
+}
+static inline int DT(const Tensor &t) { return t->getDTypeIndex(); }
+static inline void *P(const Tensor &t) { return t->getRawDataPtr<void *>(); }
+
+// numpy-broadcast strides of `shape` against `out` (elements; 0 on broadcast dims)
+static vector<int64_t> bstrides(const Shape &shape, const Shape &out) {
+    size_t r = out.size(), off = r - shape.size();
+    vector<int64_t> st(r, 0);
+    int64_t acc = 1;
+    for (int i = (int)shape.size() - 1; i >= 0; --i) {
+        st[off + i] = (shape[i] == 1 && out[off + i] != 1) ? 0 : acc;
+        acc *= shape[i];
+    }
+    return st;
+}
+static vector<int64_t> to64(const Shape &s) { return vector<int64_t>(s.begin(), s.end()); }
+
+// ---------------------------------------------------------------- unary family
+static int unaryCode(OpType t) {
+    switch (t.underlying()) {
+    case OpType::Relu: return ITB_RELU;
+    case OpType::Sigmoid: return ITB_SIGMOID;
+    case OpType::Tanh: return ITB_TANH;
+    case OpType::Gelu: return ITB_GELU;
+    case OpType::Silu: return ITB_SILU;
+    case OpType::Erf: return ITB_ERF;
+    case OpType::Neg: return ITB_NEG;
+    case OpType::Abs: return ITB_ABS;
+    case OpType::Sqrt: return ITB_SQRT;
+    case OpType::HardSigmoid: return ITB_HARDSIGMOID;
+    case OpType::HardSwish: return ITB_HARDSWISH;
+    case OpType::Exp: return ITB_EXP;
+    }
+    return -1;
+}
+class UnaryB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &op, const RuntimeObj *) const override {
+        auto x = op->getInputs(0), y = op->getOutput();
+        CK(it_b200_unary(unaryCode(op->getOpType()), DT(x), P(x), P(y), (int64_t)x->size(), S()), op);
+    }
+};
+
+static int binaryCode(OpType t) {
+    switch (t.underlying()) {
+    case OpType::Add: return ITB_ADD;
+    case OpType::Sub: return ITB_SUB;
+    case OpType::Mul: return ITB_MUL;
+    case OpType::Div: return ITB_DIV;
+    case OpType::Pow: return ITB_POW;
+    case OpType::Min: return ITB_MIN;
+    case OpType::Max: return ITB_MAX;
+    case OpType::Less: return ITB_LESS;
+    case OpType::Equal: return ITB_EQUAL;
+    case OpType::Greater: return ITB_GREATER;
+    }
+    return -1;
+}
+class ElementWiseB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &op, const RuntimeObj *) const override {
+        auto a = op->getInputs(0), b = op->getInputs(1), c = op->getOutput();
+        IT_ASSERT(a->getDType() == b->getDType(), "elementwise operands must share a dtype");
+        auto dims = to64(c->getDims());
+        auto sa = bstrides(a->getDims(), c->getDims()), sb = bstrides(b->getDims(), c->getDims());
+        CK(it_b200_binary(binaryCode(op->getOpType()), DT(a), P(a), P(b), P(c), (int)dims.size(), dims.data(),
+                          sa.data(), sb.data(), S()), op);
+    }
+};
+
+class CastB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &op, const RuntimeObj *) const override {
+        auto x = op->getInputs(0), y = op->getOutput();
+        CK(it_b200_cast(DT(x), DT(y), P(x), P(y), (int64_t)x->size(), S()), op);
+    }
+};
+
+class WhereB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &op, const RuntimeObj *) const override {
+        auto x = op->getInputs(0), y = op->getInputs(1), c = op->getInputs(2), o = op->getOutput();
+        IT_ASSERT(c->getDType().getSize() == 1, "Where: condition must be bool/uint8");
+        auto dims = to64(o->getDims());
+        auto sc = bstrides(c->getDims(), o->getDims()), sx = bstrides(x->getDims(), o->getDims()),
+             sy = bstrides(y->getDims(), o->getDims());
+        CK(it_b200_where((int)x->getDType().getSize(), P(c), P(x), P(y), P(o), (int)dims.size(), dims.data(),
+                         sc.data(), sx.data(), sy.data(), S()), op);
+    }
+};
+
+class ExpandB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &op, const RuntimeObj *) const override {
+        auto x = op->getInputs(0), o = op->getOutput();
+        auto dims = to64(o->getDims());
+        auto sx = bstrides(x->getDims(), o->getDims());
+        CK(it_b200_expand((int)x->getDType().getSize(), P(x), P(o), (int)dims.size(), dims.data(), sx.data(), S()),
+           op);
+    }
+};
+
+// ---------------------------------------------------------------- norms / softmax / rope
+static void axisView(const Shape &d, int axis, int64_t &outer, int &dim, int64_t &inner) {
+    outer = inner = 1;
+    for (int i = 0; i < axis; ++i) outer *= d[i];
+    dim = d[axis];
+    for (int i = axis + 1; i < (int)d.size(); ++i) inner *= d[i];
+}
+class SoftmaxB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *) const override {
+        auto op = as<SoftmaxObj>(_op);
+        auto x = op->getInputs(0);
+        int64_t outer, inner;
+        int dim;
+        axisView(x->getDims(), op->getAxis(), outer, dim, inner);
+        CK(it_b200_softmax(DT(x), P(x), P(op->getOutput()), outer, dim, inner, S()), _op);
+    }
+};
+class LayerNormB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *) const override {
+        auto op = as<LayerNormObj>(_op);
+        auto x = op->getInputs(0), sc = op->getInputs(1);
+        auto bias = op->getBias();
+        int64_t outer, inner;
+        int dim;
+        axisView(x->getDims(), op->getAxis(), outer, dim, inner);
+        CK(it_b200_layernorm(DT(x), P(x), P(sc), bias ? P(bias) : nullptr, P(op->getOutput()), outer, dim, inner,
+                             (int)sc->size(), bias ? (int)bias->size() : 0, op->getEps(), S()), _op);
+    }
+};
+class RMSNormB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &op, const RuntimeObj *) const override {
+        auto x = op->getInputs(0), w = op->getInputs(1);
+        int hidden = x->getDims().back();
+        IT_ASSERT((int)w->size() == hidden, "RMSNorm: weight length must equal the hidden size");
+        CK(it_b200_rmsnorm(DT(x), P(x), P(w), P(op->getOutput()), (int64_t)(x->size() / hidden), hidden, S()), op);
+    }
+};
+class RoPEB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &op, const RuntimeObj *) const override {
+        auto pos = op->getInputs(0), x = op->getInputs(1);
+        auto &d = x->getDims();
+        IT_ASSERT(d.size() == 3 && pos->getRank() == 2, "RoPE: input [B,S,dim_model], pos [B,S]");
+        IT_ASSERT(d[0] == pos->getDims()[0] && d[1] == pos->getDims()[1], "RoPE: pos / input mismatch");
+        const int dim_head = 128;  // hard-coded in the reference (rope.cc:25)
+        CK(it_b200_rope(DT(x), P(pos), DT(pos), P(x), P(op->getOutput()), d[0], d[1], d[2], dim_head, S()), op);
+    }
+};
+
+// ---------------------------------------------------------------- data movement
+class TransposeB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *) const override {
+        auto op = as<TransposeObj>(_op);
+        auto x = op->getInputs(0);
+        auto dims = to64(x->getDims());
+        CK(it_b200_transpose((int)x->getDType().getSize(), P(x), P(op->getOutput()), (int)dims.size(), dims.data(),
+                             op->getPermute().data(), S()), _op);
+    }
+};
+class ConcatB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *) const override {
+        auto op = as<ConcatObj>(_op);
+        auto out = op->getOutput();
+        int dim = op->getDim();
+        int64_t outer = 1, inner = 1;
+        for (int i = 0; i < dim; ++i) outer *= out->getDims()[i];
+        for (int i = dim + 1; i < (int)out->getRank(); ++i) inner *= out->getDims()[i];
+        vector<const void *> parts;
+        vector<int64_t> lens;
+        for (auto &t : op->getInputs()) {
+            if (t->size() == 0) continue;  // empty operands contribute nothing (reference split_concat.cc:64-78)
+            parts.push_back(P(t));
+            lens.push_back(t->getDims()[dim]);
+        }
+        if (parts.empty()) return;
+        CK(it_b200_concat((int)out->getDType().getSize(), (int)parts.size(), parts.data(), lens.data(), P(out), outer,
+                          inner, S()), _op);
+    }
+};
+class SplitB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *) const override {
+        auto op = as<SplitObj>(_op);
+        auto in = op->getInputs(0);
+        int dim = op->getDim();
+        int64_t outer = 1, inner = 1;
+        for (int i = 0; i < dim; ++i) outer *= in->getDims()[i];
+        for (int i = dim + 1; i < (int)in->getRank(); ++i) inner *= in->getDims()[i];
+        vector<void *> parts;
+        vector<int64_t> lens;
+        for (auto &t : op->getOutputs()) {
+            parts.push_back(t->size() ? P(t) : nullptr);
+            lens.push_back(t->getDims()[dim]);
+        }
+        CK(it_b200_split((int)in->getDType().getSize(), (int)parts.size(), parts.data(), lens.data(), P(in), outer,
+                         inner, S()), _op);
+    }
+};
+class GatherB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *) const override {
+        auto op = as<GatherObj>(_op);
+        auto x = op->getInputs(0), idx = op->getInputs(1);
+        int axis = op->getAxis();
+        int64_t outer = 1, inner = 1;
+        for (int i = 0; i < axis; ++i) outer *= x->getDims()[i];
+        for (int i = axis + 1; i < (int)x->getRank(); ++i) inner *= x->getDims()[i];
+        CK(it_b200_gather((int)x->getDType().getSize(), DT(idx), P(x), P(idx), P(op->getOutput()), outer,
+                          x->getDims()[axis], inner, (int64_t)idx->size(), S()), _op);
+    }
+};
+// Reshape / Flatten / Identity / Squeeze / Unsqueeze: a copy into the planner-assigned output
+class CopyB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &op, const RuntimeObj *) const override {
+        auto x = op->getInputs(0), y = op->getOutput();
+        IT_ASSERT(x->getBytes() == y->getBytes(), "reshape-like op changes the byte count");
+        CK(it_b200_copy(P(x), P(y), (int64_t)x->getBytes(), S()), op);
+    }
+};
+class SliceB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *) const override {
+        auto op = as<SliceObj>(_op);
+        auto x = op->getInputs(0), y = op->getOutput();
+        auto din = to64(x->getDims()), dout = to64(y->getDims());
+        auto st = op->getStarts(), sp = op->getSteps();
+        vector<int64_t> start(st.begin(), st.end()), step(sp.begin(), sp.end());
+        CK(it_b200_pad_slice((int)x->getDType().getSize(), P(x), P(y), (int)din.size(), din.data(), dout.data(),
+                             start.data(), step.data(), S()), _op);
+    }
+};
+class PadB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *) const override {
+        auto op = as<PadObj>(_op);
+        auto x = op->getInputs(0), y = op->getOutput();
+        auto din = to64(x->getDims()), dout = to64(y->getDims());
+        int rank = (int)din.size();
+        vector<int64_t> start(rank), step(rank, 1);
+        for (int i = 0; i < rank; ++i) start[i] = -op->getPads()[i];
+        CK(it_b200_pad_slice((int)x->getDType().getSize(), P(x), P(y), rank, din.data(), dout.data(), start.data(),
+                             step.data(), S()), _op);
+    }
+};
+class ReduceB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *) const override {
+        auto op = as<ReduceBaseObj>(_op);
+        auto x = op->getInputs(0);
+        auto dims = to64(x->getDims());
+        vector<int> mask(dims.size());
+        for (int i = 0; i < (int)dims.size(); ++i) mask[i] = op->isReduced(i);
+        CK(it_b200_reduce(DT(x), _op->getOpType() == OpType::ReduceMean, P(x), P(op->getOutput()), (int)dims.size(),
+                          dims.data(), mask.data(), S()), _op);
+    }
+};
+class PoolingB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *) const override {
+        auto op = as<PoolingObj>(_op);
+        auto x = op->getInputs(0), y = op->getOutput();
+        auto [kh, kw, dh, dw, ph, pw, sh, sw] = op->getKDPS();
+        auto &d = x->getDims();
+        auto &o = y->getDims();
+        CK(it_b200_pool2d(DT(x), _op->getOpType() == OpType::MaxPool, P(x), P(y), d[0], d[1], d[2], d[3], kh, kw, dh,
+                          dw, ph, pw, sh, sw, o[2], o[3], S()), _op);
+    }
+};
+class BatchNormB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *) const override {
+        auto op = as<BatchNormObj>(_op);
+        auto x = op->getInputs(0);
+        for (int i = 1; i <= 4; ++i)
+            IT_ASSERT(op->getInputs(i)->getDType() == DataType::Float32, "BatchNorm statistics must be fp32");
+        auto &d = x->getDims();
+        int64_t hw = 1;
+        for (size_t i = 2; i < d.size(); ++i) hw *= d[i];
+        CK(it_b200_batchnorm(DT(x), P(x), op->getInputs(1)->getRawDataPtr<float *>(),
+                             op->getInputs(2)->getRawDataPtr<float *>(), op->getInputs(3)->getRawDataPtr<float *>(),
+                             op->getInputs(4)->getRawDataPtr<float *>(), P(op->getOutput()), d[0], d[1], hw,
+                             op->getEps(), S()), _op);
+    }
+};
+
+// ---------------------------------------------------------------- MatMul / Conv / Attention
+class MatmulB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *ctx) const override {
+        auto op = as<MatmulObj>(_op);
+        auto A = op->getInputs(0), B = op->getInputs(1), C = op->getOutput();
+        IT_ASSERT(A->getDType() == B->getDType(), "MatMul operands must share a dtype");
+        auto [b_, m_, n, k] = op->getBMNK();
+        int b = b_, m = m_;
+        // batch rule of the reference (matmul.cc:124-137): full batch or stride-0 broadcast
+        auto batchOf = [](const Tensor &t) {
+            int64_t v = 1;
+            for (int i = 0; i + 2 < (int)t->getRank(); ++i) v *= t->getDims()[i];
+            return v;
+        };
+        int64_t ba = batchOf(A), bb = batchOf(B);
+        IT_ASSERT((ba == b || ba == 1) && (bb == b || bb == 1), "MatMul: unsupported partial batch broadcast");
+        int64_t sa = (ba == 1 && b > 1) ? 0 : (int64_t)m * k, sb = (bb == 1 && b > 1) ? 0 : (int64_t)n * k;
+        const void *bias = nullptr;
+        int64_t bsb = 0, bsm = 0, bsn = 0;
+        if (auto bt = op->getBias()) {
+            bias = P(bt);
+            Shape c3 = {b, m, n};
+            Shape bd = bt->getDims();
+            // collapse the bias' leading dims against C's batch dims
+            Shape cd = C->getDims();
+            auto st = bstrides(bd, cd);
+            bsn = st[cd.size() - 1];
+            bsm = st[cd.size() - 2];
+            bool anyBatch = false;
+            for (size_t i = 0; i + 2 < cd.size(); ++i) anyBatch = anyBatch || st[i] != 0;
+            if (anyBatch) {
+                int64_t bbias = 1;
+                for (int i = 0; i + 2 < (int)bd.size(); ++i) bbias *= bd[i];
+                IT_ASSERT(bbias == b, "MatMul: bias batch dims must be full or broadcast");
+                bsb = (int64_t)(bd[bd.size() - 2]) * bd[bd.size() - 1];
+            }
+        }
+        // [b, m, k] x [k, n] with the weight broadcast over the batch (how the frontend emits every Linear
+        // layer of a decode step: b = batch, m = 1) is ONE GEMM with M = b*m -- the reference instead runs b
+        // strided-batched GEMMs with stride 0 (matmul.cc:124-168)
+        if (b > 1 && sb == 0 && !op->getTransA() && sa == (int64_t)m * k && (m == 1 || bsb == bsm * m)) {
+            if (m == 1) bsm = bsb;
+            bsb = 0;
+            m = b * m;
+            b = 1;
+            sa = (int64_t)m * k;
+        }
+        int64_t wsb = it_b200_matmul_workspace(DT(A), b, m, n, k);
+        void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
+        CK(it_b200_matmul(DT(A), P(A), P(B), bias, P(C), b, m, n, k, sa, sb, op->getTransA(), op->getTransB(), bsb,
+                          bsm, bsn, 0 /* act ignored like the reference (quirk q5) */, ws, wsb, S()), _op);
+    }
+};
+class ConvB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *ctx) const override {
+        auto op = as<ConvObj>(_op);
+        auto x = op->getInputs(0), w = op->getInputs(1);
+        auto [n, c, h, wd, f, r, s] = op->getNCHWFRS();
+        auto [ph, pw, sh, sw, dh, dw] = op->getPadStrideDilation();
+        int g = op->getNumGroups();
+        int64_t wsb = it_b200_conv2d_workspace(DT(x), n, c, h, wd, f, r, s, ph, pw, sh, sw, dh, dw, g);
+        void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
+        CK(it_b200_conv2d(DT(x), P(x), P(w), P(op->getOutput()), n, c, h, wd, f, r, s, ph, pw, sh, sw, dh, dw, g, ws,
+                          wsb, S()), _op);
+    }
+};
+class AttentionKVCacheB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &op, const RuntimeObj *ctx) const override {
+        auto kc = op->getInputs(0), vc = op->getInputs(1), q = op->getInputs(2), k = op->getInputs(3),
+             v = op->getInputs(4), pos = op->getInputs(5);
+        auto &d = kc->getDims();
+        int64_t wsb = it_b200_attention_kvcache_workspace(d[0], d[1], d[2], d[3]);
+        void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
+        CK(it_b200_attention_kvcache(DT(q), P(kc), P(vc), P(q), P(k), P(v), P(pos), DT(pos), P(op->getOutput()), d[0],
+                                     d[1], d[2], d[3], ws, wsb, S()), op);
+    }
+};
+
+// ---------------------------------------------------------------- collectives (NCCL on the runtime stream,
+// capturable; reference all_reduce.cc:8-63, all_gather.cc:8-43 -- the latter's stream-0 + memcpy fan-out is
+// a defect (quirk q7) and is not reproduced)
+static ncclDataType_t ncclType(DataType dt) {
+    if (dt == DataType::Float32) return ncclFloat;
+    if (dt == DataType::Float16) return ncclHalf;
+    if (dt == DataType::BFloat16) return ncclBfloat16;
+    if (dt == DataType::Int8) return ncclInt8;
+    if (dt == DataType::Int32) return ncclInt32;
+    if (dt == DataType::Int64) return ncclInt64;
+    throw Exception("collective: unsupported dtype " + dt.toString());
+}
+class AllReduceB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &op, const RuntimeObj *ctx) const override {
+        auto x = op->getInputs(0), y = op->getOutput();
+        auto comm = (ncclComm_t)RT(ctx)->getCommunicator().getNcclComm();
+        ncclRedOp_t red;
+        switch (op->getOpType().underlying()) {
+        case OpType::AllReduceSum: red = ncclSum; break;
+        case OpType::AllReduceProd: red = ncclProd; break;
+        case OpType::AllReduceMin: red = ncclMin; break;
+        case OpType::AllReduceMax: red = ncclMax; break;
+        default: red = ncclAvg;
+        }
+        ncclResult_t r = ncclAllReduce(P(x), P(y), x->size(), ncclType(x->getDType()), red, comm,
+                                       CUDAStream::getCurrentStream());
+        IT_ASSERT(r == ncclSuccess, string("ncclAllReduce: ") + ncclGetErrorString(r));
+    }
+};
+class AllGatherB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &op, const RuntimeObj *ctx) const override {
+        auto x = op->getInputs(0);
+        auto rt = RT(ctx);
+        auto &c = rt->getCommunicator();
+        int world = c.getWorldSize();
+        IT_ASSERT((int)op->getOutputs().size() == world, "AllGather: one output per rank");
+        // outputs planned back-to-back -> gather straight into them; otherwise through the workspace
+        bool contiguous = true;
+        char *base = op->getOutput(0)->getRawDataPtr<char *>();
+        for (int i = 0; i < world; ++i)
+            contiguous = contiguous && op->getOutput(i)->getRawDataPtr<char *>() == base + (size_t)i * x->getBytes();
+        auto st = CUDAStream::getCurrentStream();
+        void *dst = contiguous ? (void *)base : rt->getWorkspace(x->getBytes() * world);
+        ncclResult_t r = ncclAllGather(P(x), dst, x->size(), ncclType(x->getDType()), (ncclComm_t)c.getNcclComm(), st);
+        IT_ASSERT(r == ncclSuccess, string("ncclAllGather: ") + ncclGetErrorString(r));
+        if (!contiguous)
+            for (int i = 0; i < world; ++i)
+                CK(it_b200_copy((char *)dst + (size_t)i * x->getBytes(), P(op->getOutput(i)), (int64_t)x->getBytes(),
+                                st), op);
+    }
+};
+
+}  // namespace infini
+
+#define REG(OP, K, NAME) REGISTER_KERNEL(Device::CUDA, OpType::OP, K, NAME)
+REG(Relu, UnaryB200, "Relu_B200")
+REG(Sigmoid, UnaryB200, "Sigmoid_B200")
+REG(Tanh, UnaryB200, "Tanh_B200")
+REG(Gelu, UnaryB200, "Gelu_B200")
+REG(Silu, UnaryB200, "Silu_B200")
+REG(Erf, UnaryB200, "Erf_B200")
+REG(Neg, UnaryB200, "Neg_B200")
+REG(Abs, UnaryB200, "Abs_B200")
+REG(Sqrt, UnaryB200, "Sqrt_B200")
+REG(HardSigmoid, UnaryB200, "HardSigmoid_B200")
+REG(HardSwish, UnaryB200, "HardSwish_B200")
+REG(Exp, UnaryB200, "Exp_B200")
+REG(Add, ElementWiseB200, "Add_B200")
+REG(Sub, ElementWiseB200, "Sub_B200")
+REG(Mul, ElementWiseB200, "Mul_B200")
+REG(Div, ElementWiseB200, "Div_B200")
+REG(Pow, ElementWiseB200, "Pow_B200")
+REG(Min, ElementWiseB200, "Min_B200")
+REG(Max, ElementWiseB200, "Max_B200")
+REG(Less, ElementWiseB200, "Less_B200")
+REG(Equal, ElementWiseB200, "Equal_B200")
+REG(Greater, ElementWiseB200, "Greater_B200")
+REG(Cast, CastB200, "Cast_B200")
+REG(Where, WhereB200, "Where_B200")
+REG(Expand, ExpandB200, "Expand_B200")
+REG(Softmax, SoftmaxB200, "Softmax_B200")
+REG(LayerNormalization, LayerNormB200, "LayerNorm_B200")
+REG(RMSNorm, RMSNormB200, "RMSNorm_B200")
+REG(RoPE, RoPEB200, "RoPE_B200")
+REG(Transpose, TransposeB200, "Transpose_B200")
+REG(Concat, ConcatB200, "Concat_B200")
+REG(Split, SplitB200, "Split_B200")
+REG(Gather, GatherB200, "Gather_B200")
+REG(Reshape, CopyB200, "Reshape_B200")
+REG(Flatten, CopyB200, "Flatten_B200")
+REG(Identity, CopyB200, "Identity_B200")
+REG(Squeeze, CopyB200, "Squeeze_B200")
+REG(Unsqueeze, CopyB200, "Unsqueeze_B200")
+REG(Slice, SliceB200, "Slice_B200")
+REG(Pad, PadB200, "Pad_B200")
+REG(ReduceMean, ReduceB200, "ReduceMean_B200")
+REG(ReduceSum, ReduceB200, "ReduceSum_B200")
+REG(MaxPool, PoolingB200, "MaxPool_B200")
+REG(AveragePool, PoolingB200, "AvgPool_B200")
+REG(BatchNormalization, BatchNormB200, "BatchNorm_B200")
+REG(MatMul, MatmulB200, "Matmul_B200_tcgen05_tma")
+REG(Conv, ConvB200, "Conv_B200_im2col_gemm")
+REG(AttentionKVCache, AttentionKVCacheB200, "AttentionKVCache_B200")
+REG(AllReduceSum, AllReduceB200, "AllReduceSum_B200")
+REG(AllReduceProd, AllReduceB200, "AllReduceProd_B200")
+REG(AllReduceMin, AllReduceB200, "AllReduceMin_B200")
+REG(AllReduceMax, AllReduceB200, "AllReduceMax_B200")
+REG(AllReduceAvg, AllReduceB200, "AllReduceAvg_B200")
+REG(AllGather, AllGatherB200, "AllGather_B200")

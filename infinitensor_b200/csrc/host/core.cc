@@ -200,7 +200,6 @@ void PerfEngine::setPerfData(const Key &key, PerfRecord record) {
     IT_ASSERT(data.find(key) == data.end(), "Perf data already exist");
     data.emplace(key, std::move(record));
 }
-bool operator<(const PerfEngine::Key &a, const PerfEngine::Key &b);
 
 double RuntimeObj::getPerfTime(const Graph &graph) const {
     double total = 0;

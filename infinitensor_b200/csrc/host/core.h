@@ -363,6 +363,7 @@ class GraphObj : public std::enable_shared_from_this<GraphObj> {
         return op;
     }
 
+    void addOperator(const Operator &op) { addOperatorAndConnect(op); }
     bool topo_sort();
     void optimize() {}  // the reference's GraphObj::optimize is an empty switch (graph.cc:184-191)
     void shape_infer();

@@ -1,0 +1,145 @@
+"""GPU graph-level parity: the same graph description (infinitensor_b200/graphs.py) executed by the B200
+backend through the C-ABI graph API and by the CPU oracle.  Covers the run loop, the memory planner, CUDA-graph
+capture / replay / invalidation and the three BASELINE model families at reduced size."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+F32, F16, BF16 = 1, 10, 16
+
+
+@pytest.mark.parametrize("dtype", [F32, F16, BF16])
+@pytest.mark.parametrize("cudagraph", [False, True])
+def test_llama_decode_parity(dtype, cudagraph):
+    from tests.smoke_impl import run_llama_parity
+    worst, launches = run_llama_parity(dtype=dtype, layers=2, batch=4, pos=5, steps=3, cudagraph=cudagraph)
+    assert launches > 0
+
+
+def test_llama_decode_batch16_wide():
+    """d=1024 / ffn=2816 / B=16: the skinny TMA GEMM path (M=16) inside the graph."""
+    from infinitensor_b200 import graphs as G
+    from tests.smoke_impl import run_llama_parity
+    cfg = G.LlamaConfig(layers=2, d_model=1024, heads=8, head_dim=128, ffn=2816, vocab=2048, s_max=128, batch=16, dtype=BF16)
+    run_llama_parity(cfg=cfg, pos=77, steps=2)
+
+
+def test_matmul_512_config1():
+    """BASELINE config #1: MatmulObj fp32 512^3 through the graph API."""
+    from infinitensor_b200 import backend as B, graphs as G
+    import oracle
+    rt = B.CudaRuntime(0)
+    h = B.GraphHandler(rt)
+    a, b, c = G.build_matmul(h)
+    h.data_malloc()
+    A = np.random.default_rng(0).standard_normal((512, 512)).astype(np.float32)
+    Bm = np.random.default_rng(1).standard_normal((512, 512)).astype(np.float32)
+    a.copyin_numpy(A)
+    b.copyin_numpy(Bm)
+    h.run()
+    np.testing.assert_allclose(c.copyout_numpy(), oracle.matmul(A, Bm), rtol=1e-4, atol=1e-5 * np.sqrt(512) * 16)
+
+
+@pytest.mark.parametrize("dtype", [F32, F16])
+def test_gpt2_parity(dtype):
+    from infinitensor_b200 import backend as B, graphs as G
+    from oracle.graph_oracle import OracleHandler
+    cfg = G.GPT2Config.tiny(dtype)
+    rt = B.CudaRuntime(0)
+    h, oh = B.GraphHandler(rt), OracleHandler()
+    g, og = G.build_gpt2(h, cfg), G.build_gpt2(oh, cfg)
+    h.data_malloc()
+    G.fill_gpt2_weights_host(g)
+    G.fill_gpt2_weights_host(og)
+    ids = np.random.default_rng(1).integers(0, cfg.vocab, size=(cfg.batch, cfg.seq)).astype(np.int64)
+    pos = np.arange(cfg.seq, dtype=np.int64).reshape(1, -1).repeat(cfg.batch, 0)
+    for gg in (g, og):
+        gg.input_ids.copyin_numpy(ids)
+        gg.position_ids.copyin_numpy(pos)
+    h.run_with_cudagraph()
+    oh.run()
+    got = G.from_storage(g.out.copyout_numpy(), dtype).astype(np.float64)
+    ref = og.out.f32().astype(np.float64)
+    tol = 1e-3 if dtype == F32 else 1e-2
+    assert np.abs(got - ref).max() / np.abs(ref).max() < tol
+
+
+@pytest.mark.parametrize("dtype", [F32, F16])
+def test_resnet_parity(dtype):
+    from infinitensor_b200 import backend as B, graphs as G
+    from oracle.graph_oracle import OracleHandler
+    cfg = G.ResNetConfig.tiny(dtype)
+    rt = B.CudaRuntime(0)
+    h, oh = B.GraphHandler(rt), OracleHandler()
+    g, og = G.build_resnet50(h, cfg), G.build_resnet50(oh, cfg)
+    h.data_malloc()
+    G.fill_resnet_weights_host(g)
+    G.fill_resnet_weights_host(og)
+    x = np.random.default_rng(3).standard_normal((cfg.batch, 3, cfg.image, cfg.image)).astype(np.float32)
+    g.input.copyin_numpy(G.to_storage(x, dtype))
+    og.input.copyin_numpy(G.to_storage(x, dtype))
+    h.run()
+    oh.run()
+    got = G.from_storage(g.out.copyout_numpy(), dtype).astype(np.float64)
+    ref = og.out.f32().astype(np.float64)
+    tol = 1e-3 if dtype == F32 else 2e-2
+    assert np.abs(got - ref).max() / np.abs(ref).max() < tol
+
+
+def test_cudagraph_cache_semantics():
+    """capture once / replay / invalidate on storage change / LRU (reference test/cuda/test_cudagraph.cc:80-320)."""
+    from infinitensor_b200 import backend as B
+    rt = B.CudaRuntime(0, 2)
+    hs = []
+    for i in range(3):
+        h = B.GraphHandler(rt)
+        a = h.tensor([4, 8], F32)
+        b = h.tensor([4, 8], F32)
+        a.set_input(); b.set_input()
+        c = h.add(a, b, None)
+        d = h.relu(c, None)
+        d.set_output()
+        h.data_malloc()
+        a.copyin_numpy(np.full((4, 8), i + 1.0, np.float32))
+        b.copyin_numpy(np.full((4, 8), -0.5, np.float32))
+        hs.append((h, a, b, d))
+    h, a, b, d = hs[0]
+    h.run_with_cudagraph()
+    assert rt.cuda_graph_capture_count() == 1 and rt.cuda_graph_cache_size() == 1
+    h.run_with_cudagraph()
+    assert rt.cuda_graph_capture_count() == 1  # replayed
+    assert np.all(d.copyout_numpy() == 0.5)
+    a.copyin_numpy(np.full((4, 8), 3.0, np.float32))  # new contents, same storage -> replay sees them
+    h.run_with_cudagraph()
+    assert rt.cuda_graph_capture_count() == 1 and np.all(d.copyout_numpy() == 2.5)
+    h.data_malloc()  # re-plan -> new storage -> recapture
+    a.copyin_numpy(np.full((4, 8), 3.0, np.float32)); b.copyin_numpy(np.full((4, 8), -0.5, np.float32))
+    h.run_with_cudagraph()
+    assert rt.cuda_graph_capture_count() == 2
+    hs[1][0].run_with_cudagraph()
+    hs[2][0].run_with_cudagraph()
+    assert rt.cuda_graph_cache_size() == 2  # LRU capacity
+    rt.clear_cuda_graph_cache()
+    assert rt.cuda_graph_cache_size() == 0
+
+
+def test_error_paths():
+    from infinitensor_b200 import backend as B
+    rt = B.CudaRuntime(0)
+    h = B.GraphHandler(rt)
+    a = h.tensor([2, 3], F32)
+    b = h.tensor([4, 5], F32)
+    with pytest.raises(RuntimeError):
+        h.matmul(a, b, None, False, False, None, 0)  # K mismatch
+    c = h.relu(a, None)
+    with pytest.raises(RuntimeError):
+        h.run()  # no storage yet
+    h.data_malloc()
+    with pytest.raises(RuntimeError):
+        a.copyin_numpy(np.zeros((3, 2), np.float32))  # wrong shape
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()
