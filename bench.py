@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- Llama-7B-shape KV-cache decode (BASELINE.json configs[2] / [4]) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (the B200 backend through the graph API)
+  python bench.py --impl reference --gpus N ...             the reference's CPU path (oracle port) on the host cores
+
+A "step" is one decode step: 16 tokens (batch 16, q-len 1) at position p = 511 over a 1024-slot KV cache,
+32 layers, d = 4096, ffn = 11008, vocab = 32000, bf16 weights / activations / cache.
+For N > 1 the graph is tensor-parallel-sharded exactly where examples/distributed/parallel_opt.py cuts it
+(heads and MLP hidden; 2 in-graph NCCL all-reduces per layer), one process per GPU under torchrun.
+
+Timed regions (device time from CUDA events on the runtime's own stream, max over ranks):
+  value  : K CUDA-graph replays, inputs resident in HBM.
+  e2e    : K steps through the public API with HOST buffers: pinned-host -> device copy of input_ids and
+           position_ids, graph launch, device -> pinned-host copy of the logits, stream sync, every step.
+L2: one step streams >= 17 GB (N = 1) through a 126 MB L2, so successive steps cannot hit; no flush needed.
+PyTorch is plumbing only here: device RNG for the synthetic weights, pinned host buffers, CUDA events on an
+ExternalStream, torch.distributed for the barrier / max-over-ranks / NCCL-id broadcast.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tokens/sec (device-timed) Llama-7B-shape ONNX decode, 1/2/4/8 B200 + CPU ref"
+POS = 511
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=32, help="debug only: anything but 32 marks the line invalid")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="run the op loop without CUDA-graph replay (profiling aid)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_decode_sample(cfg, reps, threads):
+    """Times the reference's algorithm on the host: ONE decoder layer + final norm + logits MatMul of the same
+    workload (fp32 arrays holding bf16-rounded values, OpenMP over all host cores), extrapolated to 32 layers.
+    Returns (tokens_per_s, description)."""
+    import numpy as np
+    from infinitensor_b200 import graphs as G
+    from oracle.graph_oracle import OracleHandler
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    one = G.LlamaConfig(layers=1, d_model=cfg.d_model, heads=cfg.heads, head_dim=cfg.head_dim, ffn=cfg.ffn,
+                        vocab=cfg.vocab, s_max=cfg.s_max, batch=cfg.batch, dtype=cfg.dtype)
+    oh = OracleHandler()
+    g = G.build_llama_decode(oh, one)
+    rng = np.random.default_rng(0)
+    import oracle
+    for name, (t, shape, kind, _) in g.weights.items():
+        w = rng.standard_normal(shape, dtype=np.float32) * np.float32(0.02) + (np.float32(1) if kind == "norm" else 0)
+        t.value = oracle.round_to(w, one.dtype)
+    for c in g.k_caches + g.v_caches:
+        c.value = oracle.round_to(rng.standard_normal(c.dims, dtype=np.float32) * np.float32(0.5), one.dtype)
+    g.input_ids.copyin_numpy(rng.integers(0, one.vocab, size=(one.batch, 1)).astype(np.int64))
+    g.position_ids.copyin_numpy(np.full((one.batch, 1), POS, np.int64))
+    # split ops: [embedding] + layer ops + [final norm, logits]
+    ops = oh.ops
+    head_ops = ops[-2:]
+    layer_ops = ops[1:-2]
+
+    def run(opl):
+        for fn, ins, outs in opl:
+            res = fn()
+            if len(outs) == 1:
+                outs[0].value = res
+            else:
+                for o, r in zip(outs, res):
+                    o.value = r
+    run(ops)  # warm
+    tl, th = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter(); run(layer_ops); t1 = time.perf_counter(); run(head_ops); t2 = time.perf_counter()
+        tl.append(t1 - t0); th.append(t2 - t1)
+    t_step = cfg.layers * statistics.median(tl) + statistics.median(th)
+    desc = (f"1 of {cfg.layers} decoder layers + final norm + logits MatMul of the same workload, {reps} reps, "
+            f"median, extrapolated: {cfg.layers} x {statistics.median(tl) * 1e3:.1f} ms + {statistics.median(th) * 1e3:.1f} ms per step")
+    return cfg.batch / t_step, t_step, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from infinitensor_b200 import graphs as G
+    cfg = G.LlamaConfig(layers=args.layers)
+    threads = os.cpu_count() or 1
+    reps = max(1, min(args.steps, 8))
+    tps, t_step, desc = cpu_decode_sample(cfg, reps, threads)
+    line = {
+        "metric": METRIC, "value": round(tps, 3), "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(t_step * 1e3, 3), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "llama7b_shape_decode_bf16_b16_p511_smax1024", "batch": cfg.batch, "position": POS,
+                   "parallelism": "host-cpu"},
+        "cpu_baseline": {"value": round(tps, 3), "unit": "tokens/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": round(tps, 3), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                       "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from infinitensor_b200 import backend as B
+    from infinitensor_b200 import graphs as G
+    from infinitensor_b200 import _lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1 and args.gpus == 1, f"WORLD_SIZE {world} != --gpus {args.gpus}"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cfg = G.LlamaConfig(layers=args.layers)
+    rt = B.CudaRuntime(local)
+    if world > 1:
+        box = [B.CudaRuntime.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        rt.init_comm_with_id(box[0], world, rank)
+    h = B.GraphHandler(rt)
+    g = G.build_llama_decode(h, cfg, world, rank)
+    h.data_malloc()
+    wbytes, abytes = h.arena_bytes()
+
+    # ---- synthetic weights / cache straight on the device (13 GB: host RNG would take minutes)
+    gen = torch.Generator(device="cuda")
+    ts = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def fill(t, std, mean=0.0, seed=0):
+        shape = t.shape()
+        gen.manual_seed(seed)
+        tmp = torch.empty(shape, dtype=torch.bfloat16, device="cuda").normal_(mean, std, generator=gen)
+        L.check(L.lib.it_b200_copy(ctypes.c_void_p(tmp.data_ptr()), ctypes.c_void_p(t.device_ptr()), t.nbytes(), ts))
+        torch.cuda.current_stream().synchronize()
+
+    for i, (name, (t, shape, kind, shard)) in enumerate(g.weights.items()):
+        fill(t, 0.02, 1.0 if kind == "norm" else 0.0, seed=1000 + i)
+    for li in range(cfg.layers):
+        fill(g.k_caches[li], 0.5, seed=5000 + li)
+        fill(g.v_caches[li], 0.5, seed=7000 + li)
+    ids_host = torch.from_numpy(np.random.default_rng(1).integers(0, cfg.vocab, size=(cfg.batch, 1)).astype(np.int64)).pin_memory()
+    pos_host = torch.full((cfg.batch, 1), POS, dtype=torch.int64).pin_memory()
+    logits_host = torch.empty((cfg.batch, 1, cfg.vocab), dtype=torch.bfloat16).pin_memory()
+    g.input_ids.copyin_numpy(ids_host.numpy())
+    g.position_ids.copyin_numpy(pos_host.numpy())
+
+    stream = torch.cuda.ExternalStream(rt.stream())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step = h.run if args.eager else h.run_with_cudagraph
+    launch_async = h.run_without_sync if args.eager else h.launch_cudagraph_async
+
+    # one eager pass counts our kernel launches per step (graph replay re-issues exactly these)
+    l0 = rt.kernel_launches()
+    h.run()
+    launches_per_step = rt.kernel_launches() - l0
+    for _ in range(max(args.warmup, 3)):
+        step()
+
+    # ---- value: device-timed graph replays, inputs resident
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0.record(stream)
+    for _ in range(args.steps):
+        launch_async()
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    tok_s = cfg.batch * 1000.0 / ms_step
+
+    # ---- e2e: host buffers in, host logits out, every step
+    h2d = ids_host.numel() * 8 + pos_host.numel() * 8
+    d2h = logits_host.numel() * 2
+    for _ in range(3):
+        g.input_ids.copyin_async(ids_host.data_ptr(), ids_host.numel() * 8)
+        g.position_ids.copyin_async(pos_host.data_ptr(), pos_host.numel() * 8)
+        launch_async()
+        g.logits.copyout_async(logits_host.data_ptr(), d2h)
+        h.sync()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        g.input_ids.copyin_async(ids_host.data_ptr(), ids_host.numel() * 8)
+        g.position_ids.copyin_async(pos_host.data_ptr(), pos_host.numel() * 8)
+        launch_async()
+        g.logits.copyout_async(logits_host.data_ptr(), d2h)
+        h.sync()  # the next token depends on this step's logits being on the host
+    e1.record(stream)
+    e1.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / args.steps
+    clocks = sampler.stop() if sampler else None
+    logits_finite = bool(torch.isfinite(logits_host.float()).all())
+
+    # ---- roofline of the dominant kernel (gemm_skinny_kernel): all MatMuls of one step, back to back on the
+    # runtime stream, CUDA events around them, repeated; algorithmic bytes = weight + activation in/out bytes
+    mm = []
+    e = 2
+    d, dl, f, fl, V = cfg.d_model, cfg.d_model // world, cfg.ffn, cfg.ffn // world, cfg.vocab
+    for li in range(cfg.layers):
+        p = f"l{li}."
+        for nm, K_, N_ in ((p + "wq", d, dl), (p + "wk", d, dl), (p + "wv", d, dl), (p + "wo", dl, d), (p + "wg", d, fl),
+                           (p + "wu", d, fl), (p + "wd", fl, d)):
+            mm.append((g.weights[nm][0], K_, N_))
+    mm.append((g.weights["lm_head"][0], d, V))
+    scratch_in = torch.zeros((cfg.batch, max(f, d)), dtype=torch.bfloat16, device="cuda")
+    scratch_out = torch.zeros((cfg.batch, V), dtype=torch.bfloat16, device="cuda")
+    rs = ctypes.c_void_p(rt.stream())
+    gemm_bytes = sum((K_ * N_ + cfg.batch * (K_ + N_)) * e for _, K_, N_ in mm)
+
+    def gemm_pass():
+        for wt, K_, N_ in mm:
+            L.check(L.lib.it_b200_matmul(16, ctypes.c_void_p(scratch_in.data_ptr()), ctypes.c_void_p(wt.device_ptr()), None,
+                                         ctypes.c_void_p(scratch_out.data_ptr()), 1, cfg.batch, N_, K_, cfg.batch * K_, 0,
+                                         0, 0, 0, 0, 0, 0, None, 0, rs))
+    torch.cuda.synchronize()
+    for _ in range(2):
+        gemm_pass()
+    reps = max(3, min(args.steps, 10))
+    e0.record(stream)
+    for _ in range(reps):
+        gemm_pass()
+    e1.record(stream)
+    e1.synchronize()
+    gemm_ms = e0.elapsed_time(e1) / reps
+    achieved = gemm_bytes / (gemm_ms * 1e-3) / 1e9
+
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        try:
+            peak = float(json.load(open(pk))["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "gemm_skinny_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    step_bytes = cfg.algorithmic_bytes(POS, world)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(tok_s, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "llama7b_shape_decode_bf16_b16_p511_smax1024", "layers": cfg.layers, "d_model": cfg.d_model,
+                       "heads": cfg.heads, "ffn": cfg.ffn, "vocab": cfg.vocab, "batch": cfg.batch, "position": POS,
+                       "s_max": cfg.s_max, "parallelism": f"tp{world}", "replay": "eager" if args.eager else "cuda_graph",
+                       "l2": "each step streams >= 17 GB (N=1) through a 126 MB L2; inputs >> L2, no flush",
+                       "weight_arena_bytes": wbytes, "activation_arena_bytes": abytes, "logits_finite": logits_finite},
+            "clocks": clocks,
+            "e2e": {"value": round(cfg.batch * 1000.0 / e2e_ms, 2), "unit": "tokens/s", "ms_per_step": round(e2e_ms, 4),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "roofline": {"kernel": "gemm_skinny_kernel (all MatMuls of one step)", "bound": "hbm",
+                         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": traffic, "peak_source": peak_src, "launches": len(mm),
+                         "algorithmic_bytes_per_step": gemm_bytes, "ms_per_step_in_kernel": round(gemm_ms, 4)},
+            "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": round(step_bytes / (ms_step * 1e-3) / 1e9, 1),
+                              "peak": peak, "unit": "GB/s", "frac": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4)},
+        }
+        if args.layers != 32:
+            line["invalid"] = "debug run: --layers != 32"
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            tps, t_step, desc = cpu_decode_sample(cfg, 3, threads)
+            line["cpu_baseline"] = {"value": round(tps, 3), "unit": "tokens/s", "cores": threads, "kind": "port", "sample": desc}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_b200(a))

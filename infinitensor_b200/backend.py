@@ -124,15 +124,33 @@ class CudaRuntime:
         if h:
             lib.itb_runtime_destroy(h)
 
+    @staticmethod
+    def _preload_nccl():
+        """Make sure the process holds ONE libnccl.so.2: the copy torch bundles (nvidia-nccl wheel) if present,
+        so a later `import torch` finds its own symbols; the C side then picks up whatever is loaded."""
+        import importlib.util
+        import os
+        try:
+            spec = importlib.util.find_spec("nvidia.nccl")
+            if spec and spec.submodule_search_locations:
+                p = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+                if os.path.exists(p):
+                    ctypes.CDLL(p, mode=ctypes.RTLD_GLOBAL)
+        except Exception:
+            pass
+
     def init_comm(self, name: str, world_size: int, rank: int):
+        self._preload_nccl()
         _ck(lib.itb_runtime_init_comm(self._h, name.encode(), world_size, rank))
 
     def init_comm_with_id(self, unique_id: bytes, world_size: int, rank: int):
+        self._preload_nccl()
         buf = ctypes.create_string_buffer(unique_id, len(unique_id))
         _ck(lib.itb_runtime_init_comm_with_id(self._h, buf, len(unique_id), world_size, rank))
 
     @staticmethod
     def nccl_unique_id() -> bytes:
+        CudaRuntime._preload_nccl()
         buf = ctypes.create_string_buffer(256)
         n = lib.itb_runtime_nccl_unique_id(buf, 256)
         if n <= 0:

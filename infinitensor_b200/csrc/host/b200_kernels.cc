@@ -3,9 +3,8 @@
 // each bottoming out in one extern "C" it_b200_* launcher (include/it_b200.h).  Because the registry
 // rejects duplicate keys (reference include/core/kernel.h:150-156) this set REPLACES the reference's
 // src/kernels/cuda directory in a build; there is no second backend and no CPU fallback.
-#include <nccl.h>
-
 #include "b200_runtime.h"
+#include "nccl_dl.h"
 #include "it_b200.h"
 #include "operators.h"
 
@@ -395,9 +394,9 @@ class AllReduceB200 : public CudaKernelWithoutConfig {
         case OpType::AllReduceMax: red = ncclMax; break;
         default: red = ncclAvg;
         }
-        ncclResult_t r = ncclAllReduce(P(x), P(y), x->size(), ncclType(x->getDType()), red, comm,
+        ncclResult_t r = nccl().AllReduce(P(x), P(y), x->size(), ncclType(x->getDType()), red, comm,
                                        CUDAStream::getCurrentStream());
-        IT_ASSERT(r == ncclSuccess, string("ncclAllReduce: ") + ncclGetErrorString(r));
+        IT_ASSERT(r == ncclSuccess, string("ncclAllReduce: ") + nccl().GetErrorString(r));
     }
 };
 class AllGatherB200 : public CudaKernelWithoutConfig {
@@ -414,8 +413,8 @@ class AllGatherB200 : public CudaKernelWithoutConfig {
             contiguous = contiguous && op->getOutput(i)->getRawDataPtr<char *>() == base + (size_t)i * x->getBytes();
         auto st = CUDAStream::getCurrentStream();
         void *dst = contiguous ? (void *)base : rt->getWorkspace(x->getBytes() * world);
-        ncclResult_t r = ncclAllGather(P(x), dst, x->size(), ncclType(x->getDType()), (ncclComm_t)c.getNcclComm(), st);
-        IT_ASSERT(r == ncclSuccess, string("ncclAllGather: ") + ncclGetErrorString(r));
+        ncclResult_t r = nccl().AllGather(P(x), dst, x->size(), ncclType(x->getDType()), (ncclComm_t)c.getNcclComm(), st);
+        IT_ASSERT(r == ncclSuccess, string("ncclAllGather: ") + nccl().GetErrorString(r));
         if (!contiguous)
             for (int i = 0; i < world; ++i)
                 CK(it_b200_copy((char *)dst + (size_t)i * x->getBytes(), P(op->getOutput(i)), (int64_t)x->getBytes(),

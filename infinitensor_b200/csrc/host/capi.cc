@@ -30,7 +30,7 @@ class HostPlanRuntimeObj final : public RuntimeObj {
         throw Exception("planning-only host runtime: no kernels run on the host (there is no CPU fallback)");
     }
     void *alloc(size_t size) override {
-        void *p = std::malloc(std::max<size_t>(size, 1));
+        void *p = std::aligned_alloc(256, ((std::max<size_t>(size, 1) + 255) / 256) * 256);
         if (!p) throw std::bad_alloc();
         return p;
     }

@@ -267,7 +267,19 @@ class OracleHandler:
         return self._rec(lambda: O.where(cond.value, xx.value, yy.value), [xx, yy, cond], [out])
 
     def allReduceSum(self, x, y):
-        raise RuntimeError("OracleHandler is single-rank: run the unsharded graph as the TP reference")
+        """all_reduce.cc:8-63 on the host: a gloo all-reduce across the torch.distributed world (CPU tests
+        of the tensor-parallel path run one OracleHandler per rank)."""
+        out = self._out(y, x.dims, x.dt)
+
+        def run():
+            import torch
+            import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("allReduceSum on the oracle needs an initialised torch.distributed (gloo) world")
+            t = torch.from_numpy(np.ascontiguousarray(x.value, dtype=np.float32).copy())
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return O.round_to(t.numpy(), x.dt)
+        return self._rec(run, [x], [out])
 
     # ---- runtime
     def data_malloc(self, *a, **k):
