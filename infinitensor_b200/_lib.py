@@ -22,7 +22,7 @@ if not os.path.exists(LIB_PATH):
         f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
         "(make -C infinitensor_b200/csrc). There is no CPU fallback.")
 
-lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+lib = ctypes.CDLL(LIB_PATH)  # RTLD_LOCAL: the infini:: C++ symbols must not leak into other loaded libraries
 
 i64p = POINTER(c_int64)
 i32p = POINTER(c_int)

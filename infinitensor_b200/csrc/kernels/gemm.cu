@@ -8,6 +8,8 @@
 // (the "conv/im2col-GEMM path" BASELINE.json names for ResNet-50).
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "gemm.cuh"
@@ -65,13 +67,20 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T *__restrict__ x, T 
     }
 }
 
-#ifndef ITB_HAVE_GEMM_TC
-int launch_gemm_tc(int, const GemmArgs &, cudaStream_t) { return -1; }
-#endif
-
+// Kernel selection.  ITB_GEMM_IMPL = tc | skinny | simt pins one implementation (A/B testing and the parity
+// tests that must exercise each kernel); unset = the production order below.
 static int run_gemm(int dtype, const GemmArgs &g, cudaStream_t st) {
     if (g.batch == 0 || g.m == 0 || g.n == 0) return 0;
-    int r = launch_gemm_skinny(dtype, g, st);
+    const char *pin = std::getenv("ITB_GEMM_IMPL");
+    int r = -1;
+    if (pin && pin[0]) {
+        if (!strcmp(pin, "tc")) r = launch_gemm_tc(dtype, g, st);
+        else if (!strcmp(pin, "skinny")) r = launch_gemm_skinny(dtype, g, st);
+        else if (strcmp(pin, "simt")) ITB_FAIL("matmul: unknown ITB_GEMM_IMPL '%s'", pin);
+        if (r >= 0) return r;
+        return launch_gemm_simt(dtype, g, st);
+    }
+    r = launch_gemm_skinny(dtype, g, st);
     if (r >= 0) return r;
     r = launch_gemm_tc(dtype, g, st);
     if (r >= 0) return r;

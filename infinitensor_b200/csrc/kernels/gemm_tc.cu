@@ -1,0 +1,304 @@
+// gemm_tc.cu -- tcgen05 tensor-core GEMM for sm_100a:  C[M,N] = X[M,K] . W[K,N] (+bias, act)
+//   X, W, C bf16 / fp16 row-major, fp32 accumulation in TENSOR MEMORY.
+//
+// The 5th-gen tensor core is driven "swap-AB": the streamed operand W (row-major [K,N], the layout
+// ONNX MatMul weights and im2col matrices arrive in) is the UMMA A operand in MN-major form, 128 of its
+// columns per instruction, and the <= 256-row operand X is the UMMA B operand (K-major), so
+//     D[n (128 TMEM lanes), m (TMEM columns)] += W^T[n, k16] . X^T[k16, m]
+// runs as one `tcgen05.mma.cta_group::1.kind::f16` per 16 k-values issued by ONE thread; M = 16 decode
+// rows cost 16 TMEM columns instead of a padded 128-row tile.  Per CTA:
+//   warp 4      : TMA producer -- cp.async.bulk.tensor.2d, 128B swizzle, [64k x 64n] x2 weight boxes and
+//                 one [Mpad x 64k] activation box per stage, mbarrier complete_tx
+//   warp 5      : TMEM allocator + MMA issuer; tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 0..3  : epilogue -- tcgen05.ld (32 lanes x 16 columns per warp), optional split-K reduction over the
+//                 thread-block CLUSTER through distributed shared memory, fused bias / activation / dtype
+//                 conversion, coalesced stores
+// Used for every MatMul with transA = transB = 0, batch 1, N % 8 == 0, K % 8 == 0: the Llama decode GEMMs
+// (M = 16, HBM-bound weight streaming, grid = N/128 x splitK clusters), GPT-2 (M = 128) and the
+// im2col GEMMs of Conv (X = filter matrix [F, C*R*S], W = im2col matrix).
+// Replaces the reference's cublasGemmEx dispatch (src/kernels/cuda/matmul.cc:141-168).
+#include <cooperative_groups.h>
+
+#include "gemm.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace itb {
+
+constexpr int TC_BN = 128, TC_BK = 64;
+constexpr int TC_W_BYTES = TC_BN * TC_BK * 2;  // 16 KB: two [64k x 64n] swizzled boxes
+constexpr int TC_THREADS = 192;
+
+// ---- tcgen05 PTX wrappers -------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, fp32 accumulate
+__host__ __device__ inline uint32_t umma_idesc_f16(int is_bf16, int a_mn_major, int b_mn_major, int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                               // c_format = F32
+    d |= (uint32_t)(is_bf16 ? 1 : 0) << 7;      // a_format
+    d |= (uint32_t)(is_bf16 ? 1 : 0) << 10;     // b_format
+    d |= (uint32_t)(a_mn_major ? 1 : 0) << 15;  // a_major
+    d |= (uint32_t)(b_mn_major ? 1 : 0) << 16;  // b_major
+    d |= (uint32_t)(N >> 3) << 17;              // n_dim
+    d |= (uint32_t)(M >> 4) << 24;              // m_dim
+    return d;
+}
+
+struct TcParams {
+    int mpad;        // UMMA N: rows of X rounded up to 16 (16..256)
+    int tmem_cols;   // power of two >= max(32, mpad)
+    int stages;
+    int x_bytes;     // mpad * 128
+    int red_bytes;   // split-K partial tile: mpad * 128 * 4 (0 when splitk == 1)
+    int ktiles, ktiles_per_split;
+    uint32_t idesc;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW,
+                                                             const __grid_constant__ CUtensorMap mapX, GemmArgs g,
+                                                             TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int S = p.stages;
+    uint8_t *w_sm = smem;
+    uint8_t *x_sm = smem + S * TC_W_BYTES;
+    float *red = reinterpret_cast<float *>(x_sm + S * p.x_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(red) + p.red_bytes);
+    uint64_t *empty = full + S;
+    uint64_t *acc_full = empty + S;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * TC_BN;
+    const int split = blockIdx.y, nsplit = gridDim.y;
+    const int kt_begin = split * p.ktiles_per_split;
+    const int kt_end = min(p.ktiles, kt_begin + p.ktiles_per_split);
+    const int my_kt = max(0, kt_end - kt_begin);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&mapW);
+        tma_prefetch_desc(&mapX);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint64_t pol_w = l2_policy_evict_first();
+            const uint64_t pol_x = l2_policy_evict_last();
+            for (int it = 0; it < my_kt; ++it) {
+                const int s = it % S;
+                if (it >= S) mbar_wait(&empty[s], ((it / S) - 1) & 1);
+                mbar_expect_tx(&full[s], TC_W_BYTES + p.x_bytes);
+                const int k0 = (kt_begin + it) * TC_BK;
+                tma_load_2d(w_sm + s * TC_W_BYTES, &mapW, &full[s], n0, k0, pol_w);
+                tma_load_2d(w_sm + s * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[s], n0 + 64, k0, pol_w);
+                tma_load_2d(x_sm + s * p.x_bytes, &mapX, &full[s], k0, 0, pol_x);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            const uint32_t w_base = smem_u32(w_sm), x_base = smem_u32(x_sm);
+            for (int it = 0; it < my_kt; ++it) {
+                const int s = it % S;
+                mbar_wait(&full[s], (it / S) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 16; ++kk) {
+                    // A = W tile, MN-major: 64-column groups 8 KB apart (LBO), 8-row k groups 1 KB apart (SBO);
+                    //     one k16 step = 16 rows x 128 B = 2 KB
+                    const uint64_t a_desc = umma_desc_sw128(w_base + s * TC_W_BYTES + kk * 2048, TC_W_BYTES / 2, 1024);
+                    // B = X tile, K-major: 8-row groups 1 KB apart (SBO); one k16 step = 32 B inside the 128 B row
+                    const uint64_t b_desc = umma_desc_sw128(x_base + s * p.x_bytes + kk * 32, 0, 1024);
+                    tc_mma_f16(tmem_base, a_desc, b_desc, p.idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                }
+                tc_commit(&empty[s]);  // stage reusable once these MMAs have read it
+            }
+            tc_commit(acc_full);  // accumulator complete (also fires when my_kt == 0)
+        }
+        __syncwarp();
+    }
+
+    // ===== epilogue: warps 0..3 own TMEM lanes [32w, 32w+32) = output columns n0 + 32w + lane =====
+    const T *bias = (const T *)g.bias;
+    T *C = (T *)g.C;
+    if (warp < 4) {
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int nl = warp * 32 + lane;  // column inside the tile
+        const int gn = n0 + nl;
+        for (int c0 = 0; c0 < p.mpad; c0 += 16) {
+            uint32_t v[16];
+            if (my_kt > 0) {
+                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0u;
+            }
+            if (nsplit > 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) red[(c0 + j) * TC_BN + nl] = __uint_as_float(v[j]);
+            } else if (gn < g.n) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int m = c0 + j;
+                    if (m < g.m) {
+                        float f = __uint_as_float(v[j]);
+                        if (bias) f += to_f(bias[m * g.bias_sm + gn * g.bias_sn]);
+                        C[(int64_t)m * g.n + gn] = from_f<T>(gemm_act(g.act, f));
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    if (nsplit > 1) {
+        cluster.sync();
+        if (split == 0 && warp < 4) {
+            const float *peers[8];
+            for (int r = 0; r < nsplit; ++r) peers[r] = (const float *)cluster.map_shared_rank(red, r);
+            for (int idx = threadIdx.x; idx < p.mpad * TC_BN; idx += 128) {
+                const int m = idx / TC_BN, nl = idx % TC_BN, gn = n0 + nl;
+                if (m >= g.m || gn >= g.n) continue;
+                float f = 0.f;
+                for (int r = 0; r < nsplit; ++r) f += peers[r][idx];
+                if (bias) f += to_f(bias[m * g.bias_sm + gn * g.bias_sn]);
+                C[(int64_t)m * g.n + gn] = from_f<T>(gemm_act(g.act, f));
+            }
+        }
+        cluster.sync();
+    } else {
+        __syncthreads();
+    }
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+template <typename T>
+static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
+    TcParams p{};
+    p.mpad = ((g.m + 15) / 16) * 16;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.mpad) p.tmem_cols <<= 1;
+    p.x_bytes = p.mpad * 128;
+    const int tiles_n = (g.n + TC_BN - 1) / TC_BN;
+    p.ktiles = (g.k + TC_BK - 1) / TC_BK;
+    // split-K only where the partial tile is small (decode regime); clusters of <= 8 CTAs
+    int splitk = 1;
+    if (p.mpad <= 64) {
+        splitk = (2 * kNumSMs) / tiles_n;
+        splitk = std::max(1, std::min(splitk, 8));
+        splitk = std::min(splitk, std::max(1, p.ktiles / 4));
+    }
+    p.ktiles_per_split = (p.ktiles + splitk - 1) / splitk;
+    splitk = (p.ktiles + p.ktiles_per_split - 1) / p.ktiles_per_split;
+    p.red_bytes = splitk > 1 ? p.mpad * TC_BN * 4 : 0;
+    const int stage_bytes = TC_W_BYTES + p.x_bytes;
+    const int budget = (p.mpad <= 64 ? 104 : 200) * 1024;  // two CTAs per SM in the decode regime
+    p.stages = std::max(2, std::min(8, (budget - p.red_bytes - 2048) / stage_bytes));
+    p.idesc = umma_idesc_f16(is_bf16 ? 1 : 0, /*A = W^T, MN-major*/ 1, /*B = X, K-major*/ 0, 128, p.mpad);
+    const int smem = p.stages * stage_bytes + p.red_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+
+    CUtensorMap mapW, mapX;
+    if (!make_tma_2d_b16(&mapW, g.B, (uint64_t)g.k, (uint64_t)g.n, (uint64_t)g.n, TC_BK, 64, 128))
+        ITB_FAIL("matmul(tcgen05): cuTensorMapEncodeTiled(W) failed");
+    if (!make_tma_2d_b16(&mapX, g.A, (uint64_t)g.m, (uint64_t)g.k, (uint64_t)g.k, (uint32_t)p.mpad, TC_BK, 128))
+        ITB_FAIL("matmul(tcgen05): cuTensorMapEncodeTiled(X) failed");
+
+    static int attr_smem = 0;
+    auto kern = gemm_tc_kernel<T>;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        ITB_CHECK(e == cudaSuccess, "matmul(tcgen05): smem attribute: %s", cudaGetErrorString(e));
+        attr_smem = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tiles_n, splitk, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = splitk;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapW, mapX, g, p);
+    ITB_CHECK(e == cudaSuccess, "matmul(tcgen05): launch failed: %s", cudaGetErrorString(e));
+    itb::count_launch();
+    return 0;
+}
+
+int launch_gemm_tc(int dtype, const GemmArgs &g, cudaStream_t st) {
+    if (dtype != ITB_BF16 && dtype != ITB_F16) return -1;
+    if (g.batch != 1 || g.trans_a || g.trans_b || g.m < 1 || g.m > 256) return -1;
+    if (g.n % 8 != 0 || g.k % 8 != 0 || g.n < 64 || g.k < 64) return -1;
+    if (!aligned16(g.A) || !aligned16(g.B)) return -1;
+    if (dtype == ITB_BF16) return launch_tc_t<__nv_bfloat16>(g, st, true);
+    return launch_tc_t<__half>(g, st, false);
+}
+
+}  // namespace itb

@@ -264,11 +264,18 @@ def test_matmul_parity(K, shape, dt):
     close(K.matmul(a, b, bias, tA, tB, dt), oracle.matmul(a, b, bias, tA, tB, dt), 2 * EPS[dt], tol)
 
 
-@pytest.mark.parametrize("dt", [BF16, F16])
-@pytest.mark.parametrize("m,k,n", [(16, 4096, 4096), (16, 4096, 11008), (16, 11008, 4096), (1, 256, 64),
-                                   (7, 320, 200), (16, 4096, 32000), (33, 1024, 1024), (64, 512, 4160), (16, 72, 64)])
-def test_matmul_skinny_parity(K, m, k, n, dt):
-    """Decode-regime GEMM (TMA + cluster split-K kernel) at the Llama-7B shapes of SURVEY 8a row a1."""
+SKINNY_SHAPES = [(16, 4096, 4096), (16, 4096, 11008), (16, 11008, 4096), (1, 256, 64), (7, 320, 200), (16, 4096, 32000),
+                 (33, 1024, 1024), (64, 512, 4160), (16, 72, 64)]
+TC_SHAPES = SKINNY_SHAPES + [(128, 768, 2304), (128, 3072, 768), (200, 512, 640), (256, 1024, 1024), (96, 64, 128)]
+
+
+@pytest.fixture
+def gemm_impl(request, monkeypatch):
+    monkeypatch.setenv("ITB_GEMM_IMPL", request.param)
+    return request.param
+
+
+def _gemm_case(K, m, k, n, dt):
     a, b = rnd((m, k), 23, dt, 0.5), rnd((k, n), 24, dt, 0.05)
     tol = gemm_tol(dt, k, np.abs(a).max(), np.abs(b).max())
     got = K.matmul(a, b, None, False, False, dt)
@@ -277,6 +284,22 @@ def test_matmul_skinny_parity(K, m, k, n, dt):
     bias = rnd((n,), 25, dt)
     close(K.matmul(a, b, bias, False, False, dt, act=1), np.maximum(oracle.matmul(a, b, bias, False, False, dt), 0),
           2 * EPS[dt], tol)
+
+
+@pytest.mark.parametrize("gemm_impl", ["skinny"], indirect=True)
+@pytest.mark.parametrize("dt", [BF16, F16])
+@pytest.mark.parametrize("m,k,n", SKINNY_SHAPES)
+def test_matmul_skinny_parity(K, gemm_impl, m, k, n, dt):
+    """Decode-regime GEMM (TMA + mma.sync + cluster split-K) at the Llama-7B shapes of SURVEY 8a row a1."""
+    _gemm_case(K, m, k, n, dt)
+
+
+@pytest.mark.parametrize("gemm_impl", ["tc"], indirect=True)
+@pytest.mark.parametrize("dt", [BF16, F16])
+@pytest.mark.parametrize("m,k,n", TC_SHAPES)
+def test_matmul_tcgen05_parity(K, gemm_impl, m, k, n, dt):
+    """tcgen05 / TMEM / TMA swap-AB GEMM: decode shapes (M = 16) plus GPT-2 (M = 128) and M up to 256."""
+    _gemm_case(K, m, k, n, dt)
 
 
 @pytest.mark.parametrize("dt", [F32, F16, BF16])
