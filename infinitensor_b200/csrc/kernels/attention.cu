@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(WARPS * 32) attn_decode_kernel(T *__restrict__
                                                                  const void *__restrict__ position_id,
                                                                  int pos_dtype, T *__restrict__ out, int Smax,
                                                                  int nsplit, float *__restrict__ partial) {
+    pdl_trigger();
+    pdl_wait();
     using C = RowCfg<T>;
     constexpr int EPL = C::EPL, LPR = C::LPR, RPW = C::RPW;
     __shared__ float s_m[WARPS], s_l[WARPS];
@@ -180,6 +182,8 @@ __global__ void __launch_bounds__(WARPS * 32) attn_decode_kernel(T *__restrict__
 template <typename T>
 __global__ void __launch_bounds__(kD) attn_merge_kernel(const float *__restrict__ partial, T *__restrict__ out,
                                                         int nsplit) {
+    pdl_trigger();
+    pdl_wait();
     int bh = blockIdx.x, d = threadIdx.x;
     const float *pp = partial + (int64_t)bh * nsplit * (kD + 2);
     float mx = -INFINITY;
@@ -231,13 +235,13 @@ extern "C" int it_b200_attention_kvcache(int dtype, void *k_cache, void *v_cache
     dim3 grid(BH, ns);
     ITB_DISPATCH_FLOAT(dtype, "AttentionKVCache", {
         constexpr int WARPS = 8, U = 4;
-        attn_decode_kernel<T, WARPS, U><<<grid, WARPS * 32, 0, st>>>((T *)k_cache, (T *)v_cache, (const T *)q,
+        launch_k(attn_decode_kernel<T, WARPS, U>, dim3(grid), dim3(WARPS * 32), 0, st, (T *)k_cache, (T *)v_cache, (const T *)q,
                                                                     (const T *)k, (const T *)v, position_id,
                                                                     pos_dtype, (T *)out, S_max, ns,
                                                                     (float *)workspace);
         ITB_LAUNCH_CHECK("AttentionKVCache");
         if (ns > 1) {
-            attn_merge_kernel<T><<<BH, kD, 0, st>>>((const float *)workspace, (T *)out, ns);
+            launch_k(attn_merge_kernel<T>, dim3(BH), dim3(kD), 0, st, (const float *)workspace, (T *)out, ns);
             ITB_LAUNCH_CHECK("AttentionKVCache.merge");
         }
     });

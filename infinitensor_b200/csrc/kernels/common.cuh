@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "it_b200.h"
 
 namespace itb {
@@ -33,6 +35,32 @@ void count_launch(int n = 1);
     } while (0)
 
 constexpr int kNumSMs = 148;  // B200
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------
+// Every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization, and every kernel begins with
+// pdl_trigger() (lets the NEXT kernel in the stream start its launch + prologue now) and executes pdl_wait() before
+// its first read of an activation or its first global write (blocks until the PREVIOUS kernel has fully completed
+// and flushed).  In a decode step of ~450 short kernels this hides the launch gap, and the GEMM kernels prefetch
+// their weight tiles -- which no kernel in the step writes -- ahead of pdl_wait().
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();  // false when ITB_NO_PDL=1
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 inline int dtype_size(int dt) {
     switch (dt) {

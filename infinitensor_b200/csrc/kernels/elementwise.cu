@@ -33,6 +33,8 @@ __device__ __forceinline__ float apply_unary(int op, float v) {
 template <typename T>
 __global__ void __launch_bounds__(256) unary_kernel(int op, const T *__restrict__ x, T *__restrict__ y,
                                                     int64_t n, bool vec) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int V = Vec16<T>::N;
     int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -71,6 +73,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) binary_flat_kernel(int op, const T *__restrict__ a,
                                                           const T *__restrict__ b, T *__restrict__ c,
                                                           int64_t n, int sa, int sb, bool vec) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int V = Vec16<T>::N;
     int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -99,6 +103,8 @@ __global__ void __launch_bounds__(256) binary_general_kernel(int op, const T *__
                                                              const T *__restrict__ b, OUT *__restrict__ c,
                                                              int64_t n, int rank, Dims8 dims, Dims8 sa,
                                                              Dims8 sb) {
+    pdl_trigger();
+    pdl_wait();
     int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += nthreads) {
         int64_t rem = i, oa = 0, ob = 0;
@@ -159,6 +165,8 @@ template <typename SRC, typename DST> __device__ __forceinline__ DST cast_one(SR
 
 template <typename SRC, typename DST>
 __global__ void __launch_bounds__(256) cast_kernel(const SRC *__restrict__ x, DST *__restrict__ y, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
     int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += nthreads)
         y[i] = cast_one<SRC, DST>(x[i]);
@@ -168,6 +176,8 @@ template <typename E>
 __global__ void __launch_bounds__(256) where_kernel(const uint8_t *__restrict__ cond, const E *__restrict__ x,
                                                     const E *__restrict__ y, E *__restrict__ out, int64_t n,
                                                     int rank, Dims8 dims, Dims8 sc, Dims8 sx, Dims8 sy) {
+    pdl_trigger();
+    pdl_wait();
     int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += nthreads) {
         int64_t rem = i, oc = 0, ox = 0, oy = 0;
@@ -185,6 +195,8 @@ __global__ void __launch_bounds__(256) where_kernel(const uint8_t *__restrict__ 
 template <typename E>
 __global__ void __launch_bounds__(256) expand_kernel(const E *__restrict__ x, E *__restrict__ y, int64_t n,
                                                      int rank, Dims8 dims, Dims8 sx) {
+    pdl_trigger();
+    pdl_wait();
     int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += nthreads) {
         int64_t rem = i, ox = 0;
@@ -208,7 +220,7 @@ extern "C" int it_b200_unary(int op, int dtype, const void *x, void *y, int64_t 
     ITB_DISPATCH_FLOAT(dtype, "unary", {
         bool vec = aligned16(x) && aligned16(y);
         int64_t items = vec ? (n + Vec16<T>::N - 1) / Vec16<T>::N : n;
-        unary_kernel<T><<<grid_for(items, 256), 256, 0, st>>>(op, (const T *)x, (T *)y, n, vec);
+        launch_k(unary_kernel<T>, dim3(grid_for(items, 256)), dim3(256), 0, st, op, (const T *)x, (T *)y, n, vec);
     });
     ITB_LAUNCH_CHECK("unary");
     return 0;
@@ -232,14 +244,11 @@ extern "C" int it_b200_binary(int op, int dtype, const void *a, const void *b, v
         if (flat) {
             bool vec = aligned16(a) && aligned16(b) && aligned16(c);
             int64_t items = vec ? (n + Vec16<T>::N - 1) / Vec16<T>::N : n;
-            binary_flat_kernel<T><<<grid_for(items, 256), 256, 0, st>>>(
-                op, (const T *)a, (const T *)b, (T *)c, n, (int)cs[0].v[0], (int)cs[1].v[0], vec);
+            launch_k(binary_flat_kernel<T>, dim3(grid_for(items, 256)), dim3(256), 0, st, op, (const T *)a, (const T *)b, (T *)c, n, (int)cs[0].v[0], (int)cs[1].v[0], vec);
         } else if (cmp) {
-            binary_general_kernel<T, uint8_t><<<grid_for(n, 256), 256, 0, st>>>(
-                op, (const T *)a, (const T *)b, (uint8_t *)c, n, cr, cd, cs[0], cs[1]);
+            launch_k(binary_general_kernel<T, uint8_t>, dim3(grid_for(n, 256)), dim3(256), 0, st, op, (const T *)a, (const T *)b, (uint8_t *)c, n, cr, cd, cs[0], cs[1]);
         } else {
-            binary_general_kernel<T, T><<<grid_for(n, 256), 256, 0, st>>>(
-                op, (const T *)a, (const T *)b, (T *)c, n, cr, cd, cs[0], cs[1]);
+            launch_k(binary_general_kernel<T, T>, dim3(grid_for(n, 256)), dim3(256), 0, st, op, (const T *)a, (const T *)b, (T *)c, n, cr, cd, cs[0], cs[1]);
         }
     });
     ITB_LAUNCH_CHECK("binary");
@@ -248,7 +257,7 @@ extern "C" int it_b200_binary(int op, int dtype, const void *a, const void *b, v
 
 #define CAST_CASE(FROM, TO, SRC, DST)                                                          \
     if (from == FROM && to == TO) {                                                            \
-        cast_kernel<SRC, DST><<<g, 256, 0, st>>>((const SRC *)x, (DST *)y, n);                 \
+        launch_k(cast_kernel<SRC, DST>, dim3(g), dim3(256), 0, st, (const SRC *)x, (DST *)y, n);                 \
         ITB_LAUNCH_CHECK("cast");                                                              \
         return 0;                                                                              \
     }
@@ -298,7 +307,7 @@ extern "C" int it_b200_where(int elem_size, const void *cond, const void *x, con
     const int64_t *strides[3] = {stride_c, stride_x, stride_y};
     int cr = collapse(rank, dims, strides, 3, cd, cs);
     ELEM_DISPATCH(elem_size, "where", {
-        where_kernel<E><<<grid_for(n, 256), 256, 0, st>>>((const uint8_t *)cond, (const E *)x, (const E *)y,
+        launch_k(where_kernel<E>, dim3(grid_for(n, 256)), dim3(256), 0, st, (const uint8_t *)cond, (const E *)x, (const E *)y,
                                                           (E *)out, n, cr, cd, cs[0], cs[1], cs[2]);
     });
     ITB_LAUNCH_CHECK("where");
@@ -316,7 +325,7 @@ extern "C" int it_b200_expand(int elem_size, const void *x, void *y, int rank, c
     const int64_t *strides[1] = {stride_x};
     int cr = collapse(rank, dims, strides, 1, cd, cs);
     ELEM_DISPATCH(elem_size, "expand", {
-        expand_kernel<E><<<grid_for(n, 256), 256, 0, st>>>((const E *)x, (E *)y, n, cr, cd, cs[0]);
+        launch_k(expand_kernel<E>, dim3(grid_for(n, 256)), dim3(256), 0, st, (const E *)x, (E *)y, n, cr, cd, cs[0]);
     });
     ITB_LAUNCH_CHECK("expand");
     return 0;

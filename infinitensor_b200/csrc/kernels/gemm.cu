@@ -52,6 +52,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) im2col_kernel(const T *__restrict__ x, T *__restrict__ col, int64_t total,
                                                      int C, int H, int W, int R, int S, int OH, int OW, int ph,
                                                      int pw, int sh, int sw, int dh, int dw) {
+    pdl_trigger();
+    pdl_wait();
     // col[n][(c*R + r)*S + s][oh*OW + ow]; consecutive threads walk ow -> coalesced writes
     const int64_t P = (int64_t)OH * OW, Kc = (int64_t)C * R * S;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -143,7 +145,7 @@ extern "C" int it_b200_conv2d(int dtype, const void *x, const void *w, void *y, 
                   (long long)workspace_bytes, (long long)need);
         int64_t total = (int64_t)N * Kc * P;
         ITB_DISPATCH_FLOAT(dtype, "conv(im2col)", {
-            im2col_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T *)x, (T *)workspace, total, C, H, W, R, S,
+            launch_k(im2col_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, (const T *)x, (T *)workspace, total, C, H, W, R, S,
                                                                   OH, OW, ph, pw, sh, sw, dh, dw);
         });
         ITB_LAUNCH_CHECK("conv(im2col)");

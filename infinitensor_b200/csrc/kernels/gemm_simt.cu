@@ -12,6 +12,8 @@ namespace itb {
 
 template <typename T>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int BM = 64, BN = 64, BK = 16;
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
@@ -77,7 +79,7 @@ int launch_gemm_simt(int dtype, const GemmArgs &g, cudaStream_t st) {
     dim3 grid((g.n + 63) / 64, (g.m + 63) / 64, (unsigned)g.batch);
     ITB_CHECK(grid.y < 65536 && grid.z < 65536, "matmul(simt): grid too large (m=%d, batch=%lld)", g.m,
               (long long)g.batch);
-    ITB_DISPATCH_FLOAT(dtype, "matmul(simt)", { gemm_simt_kernel<T><<<grid, 256, 0, st>>>(g); });
+    ITB_DISPATCH_FLOAT(dtype, "matmul(simt)", { launch_k(gemm_simt_kernel<T>, dim3(grid), dim3(256), 0, st, g); });
     ITB_LAUNCH_CHECK("matmul(simt)");
     return 0;
 }

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
     const int kt_end = min(ktiles, kt_begin + ktiles_per_split);
     const int my_kt = max(0, kt_end - kt_begin);
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
@@ -83,9 +84,19 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
         if (lane == 0) {
             const uint64_t pol_w = l2_policy_evict_first();  // weights are read once per step
             const uint64_t pol_x = l2_policy_evict_last();   // activations are re-read by every N-tile
-            for (int it = 0; it < my_kt; ++it) {
+            // PDL: the weights are written by no kernel of the step, so the first ring of weight tiles is
+            // requested BEFORE waiting for the predecessor kernel; activations only after pdl_wait()
+            const int pre = min(S, my_kt);
+            for (int it = 0; it < pre; ++it) {
+                mbar_expect_tx(&full[it], SK_W_BYTES + Cfg::X_BYTES);
+                tma_load_2d(w_sm + it * SK_W_BYTES, &mapW, &full[it], n0, (kt_begin + it) * SK_BK, pol_w);
+            }
+            pdl_wait();
+            for (int it = 0; it < pre; ++it)
+                tma_load_2d(x_sm + it * Cfg::X_BYTES, &mapX, &full[it], (kt_begin + it) * SK_BK, 0, pol_x);
+            for (int it = pre; it < my_kt; ++it) {
                 const int s = it % S;
-                if (it >= S) mbar_wait(&empty[s], ((it / S) - 1) & 1);
+                mbar_wait(&empty[s], ((it / S) - 1) & 1);
                 mbar_expect_tx(&full[s], SK_W_BYTES + Cfg::X_BYTES);
                 const int k0 = (kt_begin + it) * SK_BK;
                 tma_load_2d(w_sm + s * SK_W_BYTES, &mapW, &full[s], n0, k0, pol_w);
@@ -141,6 +152,7 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
     }
 
     // ===== split-K reduction through distributed shared memory + fused epilogue =====
+    pdl_wait();  // every thread that reads bias / writes C is ordered after the predecessor kernel
     if (nsplit > 1) cluster.sync(); else __syncthreads();
     if (split == 0) {
         const float *peers[8];
@@ -208,13 +220,15 @@ static int launch_skinny_t(const GemmArgs &g, cudaStream_t st) {
     cfg.blockDim = dim3(SK_THREADS, 1, 1);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = splitk;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapW, mapX, g, ktiles, per);
     ITB_CHECK(e == cudaSuccess, "matmul(skinny): launch failed: %s", cudaGetErrorString(e));
     itb::count_launch();

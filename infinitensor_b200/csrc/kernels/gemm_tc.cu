@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     const int kt_end = min(p.ktiles, kt_begin + p.ktiles_per_split);
     const int my_kt = max(0, kt_end - kt_begin);
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
@@ -144,9 +145,20 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         if (lane == 0) {
             const uint64_t pol_w = l2_policy_evict_first();
             const uint64_t pol_x = l2_policy_evict_last();
-            for (int it = 0; it < my_kt; ++it) {
+            // PDL: weight tiles of the first ring are requested before waiting for the predecessor kernel
+            const int pre = min(S, my_kt);
+            for (int it = 0; it < pre; ++it) {
+                mbar_expect_tx(&full[it], TC_W_BYTES + p.x_bytes);
+                const int k0 = (kt_begin + it) * TC_BK;
+                tma_load_2d(w_sm + it * TC_W_BYTES, &mapW, &full[it], n0, k0, pol_w);
+                tma_load_2d(w_sm + it * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[it], n0 + 64, k0, pol_w);
+            }
+            pdl_wait();
+            for (int it = 0; it < pre; ++it)
+                tma_load_2d(x_sm + it * p.x_bytes, &mapX, &full[it], (kt_begin + it) * TC_BK, 0, pol_x);
+            for (int it = pre; it < my_kt; ++it) {
                 const int s = it % S;
-                if (it >= S) mbar_wait(&empty[s], ((it / S) - 1) & 1);
+                mbar_wait(&empty[s], ((it / S) - 1) & 1);
                 mbar_expect_tx(&full[s], TC_W_BYTES + p.x_bytes);
                 const int k0 = (kt_begin + it) * TC_BK;
                 tma_load_2d(w_sm + s * TC_W_BYTES, &mapW, &full[s], n0, k0, pol_w);
@@ -183,6 +195,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     const T *bias = (const T *)g.bias;
     T *C = (T *)g.C;
     if (warp < 4) {
+        pdl_wait();
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const int nl = warp * 32 + lane;  // column inside the tile
@@ -279,13 +292,15 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
     cfg.blockDim = dim3(TC_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = splitk;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapW, mapX, g, p);
     ITB_CHECK(e == cudaSuccess, "matmul(tcgen05): launch failed: %s", cudaGetErrorString(e));
     itb::count_launch();

@@ -37,12 +37,22 @@ static int pick_unit(int elem_size, std::initializer_list<int64_t> byte_counts,
     default: ITB_FAIL("%s: unsupported unit size %d", NAME, u);                                \
     }
 
+template <typename E>
+__global__ void __launch_bounds__(256) copy_kernel(const E *__restrict__ x, E *__restrict__ y, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = x[i];
+}
+
 // ---------------------------------------------------------------- transpose
 // rows contiguous on both sides: out_row[r] (len L units) = in + sum(coord * in_stride)
 template <typename E>
 __global__ void __launch_bounds__(256) permute_rows_kernel(const E *__restrict__ x, E *__restrict__ y,
                                                            int64_t n_units, int64_t L, int rank, Dims8 odims,
                                                            Dims8 istr) {
+    pdl_trigger();
+    pdl_wait();
     // odims/istr describe the OUTER dims (units of E for strides); innermost run of L units is contiguous
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_units;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -62,6 +72,8 @@ template <typename E>
 __global__ void __launch_bounds__(256) permute_tiled_kernel(const E *__restrict__ x, E *__restrict__ y, int rank,
                                                             Dims8 odims, Dims8 istr, Dims8 ostr, int q,
                                                             int64_t tiles_j, int64_t tiles_i) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ E tile[32][33];
     int64_t b = blockIdx.x;
     int64_t tj = b % tiles_j;
@@ -100,6 +112,8 @@ struct Parts {
 
 template <typename E, bool SPLIT>
 __global__ void __launch_bounds__(256) concat_split_kernel(Parts parts, E *joined, int64_t outer, int64_t Ltot) {
+    pdl_trigger();
+    pdl_wait();
     int p = blockIdx.y;
     int64_t L = parts.len[p], off = parts.off[p];
     E *part = (E *)parts.ptr[p];
@@ -118,6 +132,8 @@ template <typename E, typename I>
 __global__ void __launch_bounds__(256) gather_kernel(const E *__restrict__ data, const I *__restrict__ idx,
                                                      E *__restrict__ out, int64_t outer, int64_t axis_len,
                                                      int64_t inner, int64_t n_idx) {
+    pdl_trigger();
+    pdl_wait();
     int64_t n = outer * n_idx * inner;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t c = i % inner, t = i / inner;
@@ -132,6 +148,8 @@ __global__ void __launch_bounds__(256) gather_kernel(const E *__restrict__ data,
 template <typename E>
 __global__ void __launch_bounds__(256) pad_slice_kernel(const E *__restrict__ in, E *__restrict__ out, int64_t n,
                                                         int rank, Dims8 din, Dims8 dout, Dims8 start, Dims8 step) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t rem = i, off = 0, mul = 1;
         bool inside = true;
@@ -153,6 +171,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) reduce_kernel(const T *__restrict__ x, T *__restrict__ y, int64_t n_out,
                                                      int64_t R, int krank, Dims8 kdims, Dims8 kstr, int rrank,
                                                      Dims8 rdims, Dims8 rstr, float scale) {
+    pdl_trigger();
+    pdl_wait();
     int lane = threadIdx.x & 31;
     int64_t o = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (o >= n_out) return;
@@ -181,6 +201,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) pool2d_kernel(int is_max, const T *__restrict__ x, T *__restrict__ y,
                                                      int64_t NC, int H, int W, int kh, int kw, int dh, int dw,
                                                      int ph, int pw, int sh, int sw, int OH, int OW) {
+    pdl_trigger();
+    pdl_wait();
     int64_t n = NC * OH * OW;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int ow = (int)(i % OW);
@@ -210,6 +232,8 @@ __global__ void __launch_bounds__(256) batchnorm_kernel(const T *__restrict__ x,
                                                         const float *__restrict__ scale,
                                                         const float *__restrict__ bias, T *__restrict__ y,
                                                         int64_t n, int C, int64_t HW, float eps) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int c = (int)((i / HW) % C);
         float rs = 1.0f / sqrtf(var[c] + eps);
@@ -223,9 +247,15 @@ using namespace itb;
 
 extern "C" int it_b200_copy(const void *src, void *dst, int64_t bytes, void *stream) {
     if (bytes == 0 || src == dst) return 0;
-    cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-    ITB_CHECK(e == cudaSuccess, "copy: %s", cudaGetErrorString(e));
-    itb::count_launch();
+    // a kernel (not cudaMemcpyAsync) so the copy stays inside the PDL chain of the step
+    int u = pick_unit(1, {bytes}, {src, dst});
+    int64_t n = bytes / u;
+    UNIT_DISPATCH(u, "copy", {
+        cudaError_t e = launch_k(copy_kernel<E>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream,
+                                 (const E *)src, (E *)dst, n);
+        ITB_CHECK(e == cudaSuccess, "copy: %s", cudaGetErrorString(e));
+    });
+    ITB_LAUNCH_CHECK("copy");
     return 0;
 }
 
@@ -274,7 +304,7 @@ extern "C" int it_b200_transpose(int elem_size, const void *x, void *y, int rank
         }
         int64_t L = Lb / u, units = n * elem_size / u;
         UNIT_DISPATCH(u, "transpose", {
-            permute_rows_kernel<E><<<grid_for(units, 256), 256, 0, st>>>((const E *)x, (E *)y, units, L, r - 1,
+            launch_k(permute_rows_kernel<E>, dim3(grid_for(units, 256)), dim3(256), 0, st, (const E *)x, (E *)y, units, L, r - 1,
                                                                        odims, istr);
         });
         ITB_LAUNCH_CHECK("transpose");
@@ -298,10 +328,10 @@ extern "C" int it_b200_transpose(int elem_size, const void *x, void *y, int rank
     int64_t blocks = tiles_j * tiles_i * batch;
     ITB_CHECK(blocks < (1ll << 31), "transpose: grid too large");
     switch (elem_size) {
-    case 1: permute_tiled_kernel<uint8_t><<<(unsigned)blocks, 256, 0, st>>>((const uint8_t *)x, (uint8_t *)y, r, odims, istr, ostr, q, tiles_j, tiles_i); break;
-    case 2: permute_tiled_kernel<uint16_t><<<(unsigned)blocks, 256, 0, st>>>((const uint16_t *)x, (uint16_t *)y, r, odims, istr, ostr, q, tiles_j, tiles_i); break;
-    case 4: permute_tiled_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>((const uint32_t *)x, (uint32_t *)y, r, odims, istr, ostr, q, tiles_j, tiles_i); break;
-    case 8: permute_tiled_kernel<uint64_t><<<(unsigned)blocks, 256, 0, st>>>((const uint64_t *)x, (uint64_t *)y, r, odims, istr, ostr, q, tiles_j, tiles_i); break;
+    case 1: launch_k(permute_tiled_kernel<uint8_t>, dim3((unsigned)blocks), dim3(256), 0, st, (const uint8_t *)x, (uint8_t *)y, r, odims, istr, ostr, q, tiles_j, tiles_i); break;
+    case 2: launch_k(permute_tiled_kernel<uint16_t>, dim3((unsigned)blocks), dim3(256), 0, st, (const uint16_t *)x, (uint16_t *)y, r, odims, istr, ostr, q, tiles_j, tiles_i); break;
+    case 4: launch_k(permute_tiled_kernel<uint32_t>, dim3((unsigned)blocks), dim3(256), 0, st, (const uint32_t *)x, (uint32_t *)y, r, odims, istr, ostr, q, tiles_j, tiles_i); break;
+    case 8: launch_k(permute_tiled_kernel<uint64_t>, dim3((unsigned)blocks), dim3(256), 0, st, (const uint64_t *)x, (uint64_t *)y, r, odims, istr, ostr, q, tiles_j, tiles_i); break;
     default: ITB_FAIL("transpose: unsupported element size %d", elem_size);
     }
     ITB_LAUNCH_CHECK("transpose");
@@ -343,7 +373,7 @@ static int concat_split_impl(const char *name, int elem_size, int n_parts, const
         if (max_n == 0) continue;
         dim3 grid(grid_for(max_n, 256, 4), cnt);
         UNIT_DISPATCH(u, name, {
-            concat_split_kernel<E, SPLIT><<<grid, 256, 0, st>>>(ps, (E *)joined, outer, Ltot);
+            launch_k(concat_split_kernel<E, SPLIT>, dim3(grid), dim3(256), 0, st, ps, (E *)joined, outer, Ltot);
         });
         ITB_LAUNCH_CHECK(name);
     }
@@ -373,10 +403,10 @@ extern "C" int it_b200_gather(int elem_size, int idx_dtype, const void *data, co
     int64_t n = outer * n_idx * inner_u;
     UNIT_DISPATCH(u, "gather", {
         if (idx_dtype == ITB_I64)
-            gather_kernel<E, int64_t><<<grid_for(n, 256), 256, 0, st>>>((const E *)data, (const int64_t *)idx,
+            launch_k(gather_kernel<E, int64_t>, dim3(grid_for(n, 256)), dim3(256), 0, st, (const E *)data, (const int64_t *)idx,
                                                                        (E *)out, outer, axis_len, inner_u, n_idx);
         else
-            gather_kernel<E, int32_t><<<grid_for(n, 256), 256, 0, st>>>((const E *)data, (const int32_t *)idx,
+            launch_k(gather_kernel<E, int32_t>, dim3(grid_for(n, 256)), dim3(256), 0, st, (const E *)data, (const int32_t *)idx,
                                                                        (E *)out, outer, axis_len, inner_u, n_idx);
     });
     ITB_LAUNCH_CHECK("gather");
@@ -399,10 +429,10 @@ extern "C" int it_b200_pad_slice(int elem_size, const void *in, void *out, int r
     if (n == 0) return 0;
     auto st = (cudaStream_t)stream;
     switch (elem_size) {
-    case 1: pad_slice_kernel<uint8_t><<<grid_for(n, 256), 256, 0, st>>>((const uint8_t *)in, (uint8_t *)out, n, rank, din, dout, s, t); break;
-    case 2: pad_slice_kernel<uint16_t><<<grid_for(n, 256), 256, 0, st>>>((const uint16_t *)in, (uint16_t *)out, n, rank, din, dout, s, t); break;
-    case 4: pad_slice_kernel<uint32_t><<<grid_for(n, 256), 256, 0, st>>>((const uint32_t *)in, (uint32_t *)out, n, rank, din, dout, s, t); break;
-    case 8: pad_slice_kernel<uint64_t><<<grid_for(n, 256), 256, 0, st>>>((const uint64_t *)in, (uint64_t *)out, n, rank, din, dout, s, t); break;
+    case 1: launch_k(pad_slice_kernel<uint8_t>, dim3(grid_for(n, 256)), dim3(256), 0, st, (const uint8_t *)in, (uint8_t *)out, n, rank, din, dout, s, t); break;
+    case 2: launch_k(pad_slice_kernel<uint16_t>, dim3(grid_for(n, 256)), dim3(256), 0, st, (const uint16_t *)in, (uint16_t *)out, n, rank, din, dout, s, t); break;
+    case 4: launch_k(pad_slice_kernel<uint32_t>, dim3(grid_for(n, 256)), dim3(256), 0, st, (const uint32_t *)in, (uint32_t *)out, n, rank, din, dout, s, t); break;
+    case 8: launch_k(pad_slice_kernel<uint64_t>, dim3(grid_for(n, 256)), dim3(256), 0, st, (const uint64_t *)in, (uint64_t *)out, n, rank, din, dout, s, t); break;
     default: ITB_FAIL("pad_slice: unsupported element size %d", elem_size);
     }
     ITB_LAUNCH_CHECK("pad_slice");
@@ -436,7 +466,7 @@ extern "C" int it_b200_reduce(int dtype, int is_mean, const void *x, void *y, in
     auto st = (cudaStream_t)stream;
     unsigned grid = (unsigned)((n_out * 32 + 255) / 256);
     ITB_DISPATCH_FLOAT(dtype, "reduce", {
-        reduce_kernel<T><<<grid, 256, 0, st>>>((const T *)x, (T *)y, n_out, R, kr, kd, ks, rr, rd, rs, scale);
+        launch_k(reduce_kernel<T>, dim3(grid), dim3(256), 0, st, (const T *)x, (T *)y, n_out, R, kr, kd, ks, rr, rd, rs, scale);
     });
     ITB_LAUNCH_CHECK("reduce");
     return 0;
@@ -448,8 +478,7 @@ extern "C" int it_b200_pool2d(int dtype, int is_max, const void *x, void *y, int
     int64_t n = (int64_t)N * C * OH * OW;
     if (n == 0) return 0;
     ITB_DISPATCH_FLOAT(dtype, "pool2d", {
-        pool2d_kernel<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-            is_max, (const T *)x, (T *)y, (int64_t)N * C, H, W, kh, kw, dh, dw, ph, pw, sh, sw, OH, OW);
+        launch_k(pool2d_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, is_max, (const T *)x, (T *)y, (int64_t)N * C, H, W, kh, kw, dh, dw, ph, pw, sh, sw, OH, OW);
     });
     ITB_LAUNCH_CHECK("pool2d");
     return 0;
@@ -461,7 +490,7 @@ extern "C" int it_b200_batchnorm(int dtype, const void *x, const float *mean, co
     int64_t n = (int64_t)N * C * HW;
     if (n == 0) return 0;
     ITB_DISPATCH_FLOAT(dtype, "batchnorm", {
-        batchnorm_kernel<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T *)x, mean, var, scale, bias,
+        launch_k(batchnorm_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const T *)x, mean, var, scale, bias,
                                                                                (T *)y, n, C, HW, eps);
     });
     ITB_LAUNCH_CHECK("batchnorm");

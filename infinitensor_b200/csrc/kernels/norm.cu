@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) row_warp_kernel(const T *__restrict__ x, 
                                                        const T *__restrict__ scale, const T *__restrict__ bias,
                                                        int64_t rows, int dim, int scale_size, int bias_size,
                                                        float eps) {
+    pdl_trigger();
+    pdl_wait();
     int lane = threadIdx.x & 31;
     int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (row >= rows) return;
@@ -74,6 +76,8 @@ __global__ void __launch_bounds__(1024) row_block_kernel(const T *__restrict__ x
                                                          const T *__restrict__ scale, const T *__restrict__ bias,
                                                          int dim, int scale_size, int bias_size, float eps,
                                                          int cache_in_smem) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float srow[];
     __shared__ float red[32];
     const T *px = x + blockIdx.x * (int64_t)dim;
@@ -115,6 +119,8 @@ __global__ void __launch_bounds__(256) strided_kernel(const T *__restrict__ x, T
                                                       const T *__restrict__ scale, const T *__restrict__ bias,
                                                       int64_t outer, int dim, int64_t inner, int scale_size,
                                                       int bias_size, float eps) {
+    pdl_trigger();
+    pdl_wait();
     int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx >= outer * inner) return;
     int64_t o = idx / inner, i = idx - o * inner;
@@ -149,13 +155,13 @@ static int launch_rowop(const char *name, const T *x, T *y, const T *scale, cons
     if (outer * inner == 0 || dim == 0) return 0;
     if (inner != 1) {
         int64_t n = outer * inner;
-        strided_kernel<T, MODE><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, scale, bias, outer, dim,
+        launch_k(strided_kernel<T, MODE>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, y, scale, bias, outer, dim,
                                                                            inner, scale_size, bias_size, eps);
     } else if (dim <= 1024) {
         int64_t rows = outer;
         unsigned grid = (unsigned)((rows * 32 + 255) / 256);
 #define RW(I)                                                                                  \
-    row_warp_kernel<T, I, MODE><<<grid, 256, 0, st>>>(x, y, scale, bias, rows, dim, scale_size, bias_size, eps)
+    launch_k(row_warp_kernel<T, I, MODE>, dim3(grid), dim3(256), 0, st, x, y, scale, bias, rows, dim, scale_size, bias_size, eps)
         if (dim <= 32) RW(1);
         else if (dim <= 64) RW(2);
         else if (dim <= 128) RW(4);
@@ -166,8 +172,7 @@ static int launch_rowop(const char *name, const T *x, T *y, const T *scale, cons
     } else {
         int cache = dim <= 12288;
         int threads = dim >= 8192 ? 1024 : 512;
-        row_block_kernel<T, MODE><<<(unsigned)outer, threads, cache ? dim * sizeof(float) : 0, st>>>(
-            x, y, scale, bias, dim, scale_size, bias_size, eps, cache);
+        launch_k(row_block_kernel<T, MODE>, dim3((unsigned)outer), dim3(threads), cache ? dim * sizeof(float) : 0, st, x, y, scale, bias, dim, scale_size, bias_size, eps, cache);
     }
     ITB_LAUNCH_CHECK(name);
     return 0;
@@ -178,6 +183,8 @@ static int launch_rowop(const char *name, const T *x, T *y, const T *scale, cons
 template <typename T>
 __global__ void __launch_bounds__(512) rmsnorm_kernel(const T *__restrict__ x, const T *__restrict__ w,
                                                       T *__restrict__ y, int hidden, bool vec) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int V = Vec16<T>::N;
     __shared__ float red[32];
     const T *px = x + blockIdx.x * (int64_t)hidden;
@@ -219,6 +226,8 @@ template <typename T, typename P>
 __global__ void __launch_bounds__(256) rope_kernel(const P *__restrict__ pos, const T *__restrict__ x,
                                                    T *__restrict__ y, int64_t rows, int dim_model,
                                                    int dim_head) {
+    pdl_trigger();
+    pdl_wait();
     int half = dim_head >> 1;
     int pairs_per_row = dim_model >> 1;
     int64_t total = rows * pairs_per_row;
@@ -272,7 +281,7 @@ extern "C" int it_b200_rmsnorm(int dtype, const void *x, const void *w, void *y,
     ITB_DISPATCH_FLOAT(dtype, "rmsnorm", {
         bool vec = aligned16(x) && aligned16(w) && aligned16(y) && hidden % Vec16<T>::N == 0;
         int threads = hidden >= 4096 ? 512 : (hidden >= 1024 ? 256 : 128);
-        rmsnorm_kernel<T><<<(unsigned)tokens, threads, 0, (cudaStream_t)stream>>>((const T *)x, (const T *)w,
+        launch_k(rmsnorm_kernel<T>, dim3((unsigned)tokens), dim3(threads), 0, (cudaStream_t)stream, (const T *)x, (const T *)w,
                                                                                   (T *)y, hidden, vec);
     });
     ITB_LAUNCH_CHECK("rmsnorm");
@@ -290,9 +299,9 @@ extern "C" int it_b200_rope(int dtype, const void *pos, int pos_dtype, const voi
     ITB_DISPATCH_FLOAT(dtype, "rope", {
         int g = grid_for(total, 256);
         if (pos_dtype == ITB_I64)
-            rope_kernel<T, int64_t><<<g, 256, 0, st>>>((const int64_t *)pos, (const T *)x, (T *)y, rows, dim_model, dim_head);
+            launch_k(rope_kernel<T, int64_t>, dim3(g), dim3(256), 0, st, (const int64_t *)pos, (const T *)x, (T *)y, rows, dim_model, dim_head);
         else if (pos_dtype == ITB_I32 || pos_dtype == ITB_U32)
-            rope_kernel<T, int32_t><<<g, 256, 0, st>>>((const int32_t *)pos, (const T *)x, (T *)y, rows, dim_model, dim_head);
+            launch_k(rope_kernel<T, int32_t>, dim3(g), dim3(256), 0, st, (const int32_t *)pos, (const T *)x, (T *)y, rows, dim_model, dim_head);
         else
             ITB_FAIL("rope: unsupported position dtype %d", pos_dtype);
     });

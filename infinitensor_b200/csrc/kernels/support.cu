@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -16,6 +17,14 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = std::getenv("ITB_NO_PDL");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
 }  // namespace itb
 
