@@ -141,12 +141,24 @@ int it_b200_batchnorm(int dtype, const void *x, const float *mean, const float *
  *      ignores MatmulObj::act on CUDA, quirk q5), 1 relu, 2 sigmoid, 3 tanh (operator attr).
  *      fp32 accumulate for every dtype.  workspace: device scratch (may be NULL when
  *      it_b200_matmul_workspace() returns 0). ---- */
+#define ITB_ACT_ROUND_BEFORE_BIAS 0x100 /* OR into `act`: round the product to the storage dtype before the bias
+                                          add -- makes a fused MatMul -> Add bit-identical to the two separate ops */
 int64_t it_b200_matmul_workspace(int dtype, int64_t b, int m, int n, int k);
 int it_b200_matmul(int dtype, const void *A, const void *B, const void *bias, void *C, int64_t b,
                    int m, int n, int k, int64_t stride_a, int64_t stride_b, int trans_a,
                    int trans_b, int64_t bias_stride_b, int64_t bias_stride_m,
                    int64_t bias_stride_n, int act, void *workspace, int64_t workspace_bytes,
                    void *stream);
+
+/* ---- Grouped MatMul: up to 4 weight matrices W_i[K,N_i] sharing one activation operand X[M,K] (the q/k/v and
+ *      gate/up projections of a decoder layer) in ONE launch; C_i[M,N_i] = X . W_i.  No bias / activation.
+ *      Falls back to one it_b200_matmul per group when the shapes are not taken by the grouped kernel. ---- */
+int it_b200_matmul_grouped(int dtype, const void *X, int n_groups, const void *const *W, void *const *C,
+                           const int *N, int m, int k, void *stream);
+
+/* ---- SiLU(gate) * up in one pass (the fused form of Silu -> Mul; the Silu result is rounded to the storage
+ *      dtype before the multiply, exactly as the two separate kernels would). ---- */
+int it_b200_silu_mul(int dtype, const void *gate, const void *up, void *out, int64_t n, void *stream);
 
 /* ---- Conv (NCHW x FCRS, groups, symmetric pad): replaces convCudnn (conv.cc:36-265).
  *      im2col into workspace + tensor-core GEMM. ---- */
@@ -213,6 +225,9 @@ int itb_graph_add_op(itb_graph *g, const char *op_type, const itb_tensor *inputs
                      const double *fattrs, int n_fattrs);
 int itb_graph_num_ops(itb_graph *g);
 int itb_graph_op_type(itb_graph *g, int index, char *buf, int buf_len);
+/* the fused execution schedule derived from the graph ("Kind:Op[+Op...]" per step; see ExecStep, core.h) */
+int itb_graph_num_steps(itb_graph *g);
+int itb_graph_step(itb_graph *g, int index, char *buf, int buf_len);
 int itb_graph_topo_sort(itb_graph *g);
 int itb_graph_shape_infer(itb_graph *g);
 int itb_graph_optimize(itb_graph *g);

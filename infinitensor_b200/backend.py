@@ -82,6 +82,8 @@ _sig = {
                                  c_int, POINTER(c_double), c_int]),
     "itb_graph_num_ops": (c_int, [_h]),
     "itb_graph_op_type": (c_int, [_h, c_int, c_char_p, c_int]),
+    "itb_graph_num_steps": (c_int, [_h]),
+    "itb_graph_step": (c_int, [_h, c_int, c_char_p, c_int]),
     "itb_graph_topo_sort": (c_int, [_h]),
     "itb_graph_shape_infer": (c_int, [_h]),
     "itb_graph_optimize": (c_int, [_h]),
@@ -440,6 +442,18 @@ class GraphHandler:
         out = []
         for i in range(lib.itb_graph_num_ops(self._h)):
             _ck(lib.itb_graph_op_type(self._h, i, buf, 64))
+            out.append(buf.value.decode())
+        return out
+
+    def schedule(self):
+        """The fused execution schedule: one "Kind:Op[+Op...]" string per step."""
+        buf = ctypes.create_string_buffer(256)
+        out = []
+        n = lib.itb_graph_num_steps(self._h)
+        if n < 0:
+            raise RuntimeError(L.last_error())
+        for i in range(n):
+            _ck(lib.itb_graph_step(self._h, i, buf, 256))
             out.append(buf.value.decode())
         return out
 

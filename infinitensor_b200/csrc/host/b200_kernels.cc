@@ -293,56 +293,93 @@ class BatchNormB200 : public CudaKernelWithoutConfig {
 };
 
 // ---------------------------------------------------------------- MatMul / Conv / Attention
+namespace b200 {
+// MatMul with optional fused residual: C = A.B (+ bias) ; when `residual` is given (MatMul -> Add fusion) the
+// product is rounded to the storage dtype first, the residual added in the epilogue and the result written to
+// `outOverride` (the Add's output) -- bit-identical to the two separate kernels.
+void runMatmul(const Operator &_op, const RuntimeObj *ctx, const Tensor &residual, const Tensor &outOverride) {
+    auto op = as<MatmulObj>(_op);
+    auto A = op->getInputs(0), B = op->getInputs(1);
+    auto C = outOverride ? outOverride : op->getOutput();
+    IT_ASSERT(A->getDType() == B->getDType(), "MatMul operands must share a dtype");
+    auto [b_, m_, n, k] = op->getBMNK();
+    int b = b_, m = m_;
+    // batch rule of the reference (matmul.cc:124-137): full batch or stride-0 broadcast
+    auto batchOf = [](const Tensor &t) {
+        int64_t v = 1;
+        for (int i = 0; i + 2 < (int)t->getRank(); ++i) v *= t->getDims()[i];
+        return v;
+    };
+    int64_t ba = batchOf(A), bb = batchOf(B);
+    IT_ASSERT((ba == b || ba == 1) && (bb == b || bb == 1), "MatMul: unsupported partial batch broadcast");
+    int64_t sa = (ba == 1 && b > 1) ? 0 : (int64_t)m * k, sb = (bb == 1 && b > 1) ? 0 : (int64_t)n * k;
+    const void *bias = nullptr;
+    int64_t bsb = 0, bsm = 0, bsn = 0;
+    int act = 0;  // MatmulObj::act is ignored like the reference does (quirk q5)
+    auto bt = residual ? residual : op->getBias();
+    if (bt) {
+        IT_ASSERT(!(residual && op->getBias()), "MatMul: residual fusion needs a bias-free MatMul");
+        bias = P(bt);
+        Shape bd = bt->getDims();
+        Shape cd = op->getOutput()->getDims();
+        auto st = bstrides(bd, cd);
+        bsn = st[cd.size() - 1];
+        bsm = st[cd.size() - 2];
+        bool anyBatch = false;
+        for (size_t i = 0; i + 2 < cd.size(); ++i) anyBatch = anyBatch || st[i] != 0;
+        if (anyBatch) {
+            int64_t bbias = 1;
+            for (int i = 0; i + 2 < (int)bd.size(); ++i) bbias *= bd[i];
+            IT_ASSERT(bbias == b, "MatMul: bias batch dims must be full or broadcast");
+            bsb = (int64_t)(bd[bd.size() - 2]) * bd[bd.size() - 1];
+        }
+        if (residual) act |= ITB_ACT_ROUND_BEFORE_BIAS;
+    }
+    // [b, m, k] x [k, n] with the weight broadcast over the batch (how the frontend emits every Linear layer of a
+    // decode step: b = batch, m = 1) is ONE GEMM with M = b*m -- the reference instead runs b strided-batched GEMMs
+    // with stride 0 (matmul.cc:124-168)
+    if (b > 1 && sb == 0 && !op->getTransA() && sa == (int64_t)m * k && (m == 1 || bsb == bsm * m)) {
+        if (m == 1) bsm = bsb;
+        bsb = 0;
+        m = b * m;
+        b = 1;
+        sa = (int64_t)m * k;
+    }
+    int64_t wsb = it_b200_matmul_workspace(DT(A), b, m, n, k);
+    void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
+    CK(it_b200_matmul(DT(A), P(A), P(B), bias, P(C), b, m, n, k, sa, sb, op->getTransA(), op->getTransB(), bsb, bsm, bsn,
+                      act, ws, wsb, S()), _op);
+}
+
+// q/k/v or gate/up: MatMuls sharing the activation operand, weights [K, N_i]: one grouped launch
+void runMatmulGroup(const OpVec &ops, const RuntimeObj *) {
+    auto A = ops[0]->getInputs(0);
+    int k = as<MatmulObj>(ops[0])->getK();
+    int64_t rows = 1;
+    for (size_t i = 0; i + 1 < A->getRank(); ++i) rows *= A->getDims()[i];
+    const void *W[4];
+    void *C[4];
+    int N[4];
+    IT_ASSERT(ops.size() <= 4);
+    for (size_t i = 0; i < ops.size(); ++i) {
+        W[i] = P(ops[i]->getInputs(1));
+        C[i] = P(ops[i]->getOutput());
+        N[i] = as<MatmulObj>(ops[i])->getN();
+    }
+    CK(it_b200_matmul_grouped(DT(A), P(A), (int)ops.size(), W, C, N, (int)rows, k, S()), ops[0]);
+}
+
+void runSiluMul(const Operator &silu, const Operator &mul, const RuntimeObj *) {
+    auto g = silu->getInputs(0);
+    auto sout = silu->getOutput();
+    auto u = mul->getInputs(0) == sout ? mul->getInputs(1) : mul->getInputs(0);
+    CK(it_b200_silu_mul(DT(g), P(g), P(u), P(mul->getOutput()), (int64_t)g->size(), S()), mul);
+}
+}  // namespace b200
+
 class MatmulB200 : public CudaKernelWithoutConfig {
     void compute(const Operator &_op, const RuntimeObj *ctx) const override {
-        auto op = as<MatmulObj>(_op);
-        auto A = op->getInputs(0), B = op->getInputs(1), C = op->getOutput();
-        IT_ASSERT(A->getDType() == B->getDType(), "MatMul operands must share a dtype");
-        auto [b_, m_, n, k] = op->getBMNK();
-        int b = b_, m = m_;
-        // batch rule of the reference (matmul.cc:124-137): full batch or stride-0 broadcast
-        auto batchOf = [](const Tensor &t) {
-            int64_t v = 1;
-            for (int i = 0; i + 2 < (int)t->getRank(); ++i) v *= t->getDims()[i];
-            return v;
-        };
-        int64_t ba = batchOf(A), bb = batchOf(B);
-        IT_ASSERT((ba == b || ba == 1) && (bb == b || bb == 1), "MatMul: unsupported partial batch broadcast");
-        int64_t sa = (ba == 1 && b > 1) ? 0 : (int64_t)m * k, sb = (bb == 1 && b > 1) ? 0 : (int64_t)n * k;
-        const void *bias = nullptr;
-        int64_t bsb = 0, bsm = 0, bsn = 0;
-        if (auto bt = op->getBias()) {
-            bias = P(bt);
-            Shape c3 = {b, m, n};
-            Shape bd = bt->getDims();
-            // collapse the bias' leading dims against C's batch dims
-            Shape cd = C->getDims();
-            auto st = bstrides(bd, cd);
-            bsn = st[cd.size() - 1];
-            bsm = st[cd.size() - 2];
-            bool anyBatch = false;
-            for (size_t i = 0; i + 2 < cd.size(); ++i) anyBatch = anyBatch || st[i] != 0;
-            if (anyBatch) {
-                int64_t bbias = 1;
-                for (int i = 0; i + 2 < (int)bd.size(); ++i) bbias *= bd[i];
-                IT_ASSERT(bbias == b, "MatMul: bias batch dims must be full or broadcast");
-                bsb = (int64_t)(bd[bd.size() - 2]) * bd[bd.size() - 1];
-            }
-        }
-        // [b, m, k] x [k, n] with the weight broadcast over the batch (how the frontend emits every Linear
-        // layer of a decode step: b = batch, m = 1) is ONE GEMM with M = b*m -- the reference instead runs b
-        // strided-batched GEMMs with stride 0 (matmul.cc:124-168)
-        if (b > 1 && sb == 0 && !op->getTransA() && sa == (int64_t)m * k && (m == 1 || bsb == bsm * m)) {
-            if (m == 1) bsm = bsb;
-            bsb = 0;
-            m = b * m;
-            b = 1;
-            sa = (int64_t)m * k;
-        }
-        int64_t wsb = it_b200_matmul_workspace(DT(A), b, m, n, k);
-        void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
-        CK(it_b200_matmul(DT(A), P(A), P(B), bias, P(C), b, m, n, k, sa, sb, op->getTransA(), op->getTransB(), bsb,
-                          bsm, bsn, 0 /* act ignored like the reference (quirk q5) */, ws, wsb, S()), _op);
+        b200::runMatmul(_op, ctx, nullptr, nullptr);
     }
 };
 class ConvB200 : public CudaKernelWithoutConfig {

@@ -95,28 +95,47 @@ void CudaRuntimeObj::initCommWithId(const void *id, int idBytes, int worldSize, 
 void CudaRuntimeObj::runWithoutSyncImpl(const Graph &graph, bool validate) const {
     if (validate) graph->validateMemory();
     IT_ASSERT(graph->topo_sort(), "graph has a cycle");
-    const auto &ops = graph->getOperators();
+    const auto &sched = graph->getSchedule();
     // resolve kernel pointers + perf records once per (graph, topology epoch) instead of two std::map
     // lookups and a workload-vector hash per op per run (reference cuda_runtime.cc:180-200)
-    if (planGraphId != graph->getGraphId() || planEpoch != graph->getTopologyEpoch() || plan.size() != ops.size()) {
+    if (planGraphId != graph->getGraphId() || planEpoch != graph->getTopologyEpoch() || plan.size() != sched.size()) {
         plan.clear();
-        plan.reserve(ops.size());
+        plan.reserve(sched.size());
         auto &reg = KernelRegistry::getInstance();
         auto &pe = PerfEngine::getInstance();
-        for (auto &op : ops) {
+        for (auto &st : sched) {
+            const auto &op = st.ops.back();
             KernelAttrs attrs{Device::CUDA, op->getOpType().underlying()};
+            for (auto &m : st.ops) reg.getKernel(KernelAttrs{Device::CUDA, m->getOpType().underlying()});  // must exist
             PlanEntry pl{reg.getKernel(attrs), pe.getPerfData({attrs, op->getOpPerfKey()})};
             plan.push_back(std::move(pl));
         }
         planGraphId = graph->getGraphId();
         planEpoch = graph->getTopologyEpoch();
     }
-    for (size_t i = 0; i < ops.size(); ++i) {
-        const auto &op = ops[i];
-        if (plan[i].record)
-            plan[i].kernel->compute(op, *plan[i].record, this);
-        else
-            plan[i].kernel->compute(op, this);
+    for (size_t i = 0; i < sched.size(); ++i) {
+        const auto &st = sched[i];
+        const auto &op = st.ops.back();
+        switch (st.kind) {
+        case ExecStep::Alias:
+            // the planner made the output share the input's storage: nothing to launch
+            if (op->getInputs(0)->rawPtrOrNull() == op->getOutput()->rawPtrOrNull()) break;
+            [[fallthrough]];  // distinct storage (naive allocator): the ordinary copy kernel
+        case ExecStep::Single:
+            if (plan[i].record)
+                plan[i].kernel->compute(op, *plan[i].record, this);
+            else
+                plan[i].kernel->compute(op, this);
+            break;
+        case ExecStep::MatMulGroup: b200::runMatmulGroup(st.ops, this); break;
+        case ExecStep::MatMulAdd: {
+            const auto &mm = st.ops[0], &add = st.ops[1];
+            auto res = add->getInputs(0) == mm->getOutput() ? add->getInputs(1) : add->getInputs(0);
+            b200::runMatmul(mm, this, res, add->getOutput());
+            break;
+        }
+        case ExecStep::SiluMul: b200::runSiluMul(st.ops[0], st.ops[1], this); break;
+        }
         cudaError_t err = cudaPeekAtLastError();
         if (err != cudaSuccess) {
             cudaGetLastError();

@@ -79,7 +79,7 @@ class CudaRuntimeObj : public RuntimeObj {
 
     // per-(graph, topology epoch) dispatch plan: kernel pointers + perf keys resolved once
     struct PlanEntry {
-        Kernel *kernel;
+        Kernel *kernel;  // kernel of the step's LAST operator (the only one used by Single / Alias steps)
         std::optional<PerfRecord> record;
     };
     mutable uint64_t planGraphId = 0, planEpoch = ~0ull;
@@ -128,6 +128,13 @@ class CudaRuntimeObj : public RuntimeObj {
     size_t getCudaGraphCaptureCount() const { return captureCount; }
     bool isCapturing() const { return capturing; }
 };
+
+// fused executors behind the ExecStep kinds (b200_kernels.cc)
+namespace b200 {
+void runMatmul(const Operator &op, const RuntimeObj *ctx, const Tensor &residual, const Tensor &outOverride);
+void runMatmulGroup(const OpVec &ops, const RuntimeObj *ctx);
+void runSiluMul(const Operator &silu, const Operator &mul, const RuntimeObj *ctx);
+}  // namespace b200
 
 // Convenience base for kernels without tunable configs (reference cuda_kernel_wihtout_config.h:7-22)
 class CudaKernelWithoutConfig : public Kernel {

@@ -356,6 +356,25 @@ int itb_graph_op_type(itb_graph *g, int index, char *buf, int buf_len) {
         snprintf(buf, buf_len, "%s", g->g->getOperators()[index]->getOpType().toString());
     })
 }
+int itb_graph_num_steps(itb_graph *g) {
+    try {
+        return (int)g->g->getSchedule().size();
+    } catch (const std::exception &e) {
+        itb::set_error("%s", e.what());
+        return -1;
+    }
+}
+int itb_graph_step(itb_graph *g, int index, char *buf, int buf_len) {
+    ITB_TRY({
+        const auto &sc = g->g->getSchedule();
+        IT_ASSERT(index >= 0 && index < (int)sc.size(), "bad step index");
+        static const char *kinds[] = {"Single", "Alias", "MatMulGroup", "MatMulAdd", "SiluMul"};
+        std::string s = kinds[(int)sc[index].kind];
+        s += ":";
+        for (size_t i = 0; i < sc[index].ops.size(); ++i) s += (i ? "+" : "") + std::string(sc[index].ops[i]->getOpType().toString());
+        snprintf(buf, buf_len, "%s", s.c_str());
+    })
+}
 int itb_graph_topo_sort(itb_graph *g) { ITB_TRY(IT_ASSERT(g->g->topo_sort(), "graph has a cycle")) }
 int itb_graph_shape_infer(itb_graph *g) { ITB_TRY(g->g->shape_infer()) }
 int itb_graph_optimize(itb_graph *g) { ITB_TRY(g->g->optimize()) }

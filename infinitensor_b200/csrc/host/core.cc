@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <atomic>
 #include <numeric>
+#include <unordered_set>
 
 namespace infini {
 
@@ -382,23 +383,56 @@ void GraphObj::dataMalloc(bool useNaiveAllocator, size_t memPoolSize) {
         for (auto &t : tensors)
             if (t->isWeight()) wOff[t.get()] = wAlloc.alloc(t->getBytes());
 
+    // lifetimes follow the EXECUTION SCHEDULE (fused steps allocate all member outputs when the step runs and
+    // release inputs after it); Alias steps make the output share its input's storage (one refcounted root)
+    const auto &sched = getSchedule();
+    std::unordered_map<TensorObj *, TensorObj *> parent;
+    auto root = [&](TensorObj *t) {
+        while (true) {
+            auto it = parent.find(t);
+            if (it == parent.end()) return t;
+            t = it->second;
+        }
+    };
+    if (!useNaiveAllocator)
+        for (auto &st : sched)
+            if (st.kind == ExecStep::Alias) {
+                auto in = st.ops[0]->getInputs(0), out = st.ops[0]->getOutput();
+                if (!in->isWeight() && !out->isWeight()) parent[out.get()] = in.get();
+            }
     std::unordered_map<TensorObj *, int> refs;
+    std::unordered_set<TensorObj *> pinnedRoots;
     auto pinned = [&](const Tensor &t) { return !t->getSource() || !t->hasTarget() || t->isOutput() || t->isInput(); };
     for (auto &t : tensors) {
         if (t->isWeight()) continue;
-        if (pinned(t) || useNaiveAllocator) aOff[t.get()] = aAlloc.alloc(t->getBytes());
-        refs[t.get()] = (int)t->getTargets().size();
+        TensorObj *r = root(t.get());
+        refs[r] += (int)t->getTargets().size();
+        if (pinned(t)) pinnedRoots.insert(r);
+    }
+    for (auto &t : tensors) {
+        if (t->isWeight() || root(t.get()) != t.get()) continue;
+        if (pinnedRoots.count(t.get()) || useNaiveAllocator) aOff[t.get()] = aAlloc.alloc(t->getBytes());
     }
     if (!useNaiveAllocator) {
-        for (auto &op : ops) {
-            for (auto &out : op->getOutputs())
-                if (!out->isWeight() && !aOff.count(out.get())) aOff[out.get()] = aAlloc.alloc(out->getBytes());
-            for (auto &in : op->getInputs()) {
-                if (in->isWeight() || pinned(in)) continue;
-                if (--refs[in.get()] == 0) aAlloc.free(aOff[in.get()], in->getBytes());
-            }
+        for (auto &st : sched) {
+            for (auto &op : st.ops)
+                for (auto &out : op->getOutputs()) {
+                    if (out->isWeight()) continue;
+                    TensorObj *r = root(out.get());
+                    if (!aOff.count(r)) aOff[r] = aAlloc.alloc(r->getBytes());
+                }
+            for (auto &op : st.ops)
+                for (auto &in : op->getInputs()) {
+                    if (in->isWeight()) continue;
+                    TensorObj *r = root(in.get());
+                    if (pinnedRoots.count(r)) continue;
+                    if (--refs[r] == 0) aAlloc.free(aOff[r], r->getBytes());
+                }
         }
     }
+    // every aliased tensor takes its root's offset
+    for (auto &t : tensors)
+        if (!t->isWeight() && root(t.get()) != t.get()) aOff[t.get()] = aOff.at(root(t.get()));
 
     // commit: allocate the arenas first (may throw), then bind views
     Blob newW = weightArena, newA;

@@ -327,6 +327,25 @@ class LazyAllocator {
     void reset();
 };
 
+// ---------------------------------------------------------------- execution schedule (fusion plan)
+// The reference executes one kernel per operator in topological order and its GraphObj::optimize() is an
+// empty hook (src/core/graph.cc:184-191).  Here the graph additionally derives an EXECUTION SCHEDULE: a list
+// of steps, each one operator or a small group of operators that one fused kernel executes with results
+// bit-identical to the unfused sequence.  The memory planner takes tensor lifetimes from the schedule and the
+// runtime dispatches it.  ITB_NO_FUSION=1 yields the 1:1 schedule.
+struct ExecStep {
+    enum Kind {
+        Single,       // one operator, dispatched through the KernelRegistry
+        Alias,        // Reshape / Flatten / Squeeze / Unsqueeze / Identity / size-1-only Transpose whose output
+                      // shares the input's storage (no launch); falls back to the copy kernel if the planner
+                      // gave them distinct storage
+        MatMulGroup,  // 2..4 MatMuls sharing the activation operand (q/k/v, gate/up): one grouped launch
+        MatMulAdd,    // MatMul -> Add(residual): residual added in the GEMM epilogue
+        SiluMul       // Silu -> Mul: one pass
+    } kind = Single;
+    OpVec ops;
+};
+
 // ---------------------------------------------------------------- Graph
 class GraphObj : public std::enable_shared_from_this<GraphObj> {
     Runtime runtime;
@@ -339,8 +358,12 @@ class GraphObj : public std::enable_shared_from_this<GraphObj> {
     bool weightsAllocated = false;
 
     void addOperatorAndConnect(const Operator &op);
+    vector<ExecStep> schedule;
+    uint64_t scheduleEpoch = ~0ull;
 
   public:
+    // steps in execution order; rebuilt when the topology changes
+    const vector<ExecStep> &getSchedule();
     explicit GraphObj(Runtime runtime);
     Runtime getRuntime() const { return runtime; }
     Tensor addTensor(Shape dim, DataType dtype = DataType::Float32);

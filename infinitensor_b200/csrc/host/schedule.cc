@@ -1,0 +1,153 @@
+// schedule.cc -- derives the fused execution schedule of a graph (see ExecStep in core.h).
+// Pure host logic: pattern matching over the operator list; every fusion keeps the graph-visible results
+// bit-identical to the one-kernel-per-operator order the reference runs (src/cuda/cuda_runtime.cc:180-200).
+#include <algorithm>
+#include <cstdlib>
+#include <unordered_map>
+#include <unordered_set>
+
+#include "operators.h"
+
+namespace infini {
+
+static bool fusionEnabled() {
+    const char *e = std::getenv("ITB_NO_FUSION");
+    return !(e && e[0] == '1');
+}
+
+static bool isKvCacheOperand(const Tensor &t) {
+    for (auto &op : t->getTargets())
+        if (op->getOpType() == OpType::AttentionKVCache && (op->getInputs(0) == t || op->getInputs(1) == t)) return true;
+    return false;
+}
+static bool isGraphOutput(const Tensor &t) { return !t->hasTarget() || t->isOutput(); }
+
+// output may share the input's bytes: pure re-interpretation of a contiguous buffer
+static bool aliasable(const Operator &op) {
+    auto t = op->getOpType();
+    bool reshapeLike = t == OpType::Reshape || t == OpType::Flatten || t == OpType::Squeeze || t == OpType::Unsqueeze ||
+                       t == OpType::Identity;
+    if (t == OpType::Transpose) {
+        // a permutation that keeps the relative order of all non-1 dims moves no data
+        auto tr = as<TransposeObj>(op);
+        auto &d = op->getInputs(0)->getDims();
+        int last = -1;
+        reshapeLike = true;
+        for (int p : tr->getPermute()) {
+            if (d[p] == 1) continue;
+            if (p < last) reshapeLike = false;
+            last = p;
+        }
+    }
+    if (!reshapeLike) return false;
+    auto in = op->getInputs(0), out = op->getOutput();
+    if (in->getBytes() != out->getBytes()) return false;
+    if (isGraphOutput(out) || isKvCacheOperand(in) || isKvCacheOperand(out)) return false;
+    return true;
+}
+
+static int64_t rowsOf(const Tensor &t) {  // product of all dims but the last
+    int64_t r = 1;
+    for (size_t i = 0; i + 1 < t->getRank(); ++i) r *= t->getDims()[i];
+    return r;
+}
+
+static bool groupableMatmul(const Operator &op) {
+    auto mm = as<MatmulObj>(op);
+    if (!mm || mm->getBias() || mm->getTransA() || mm->getTransB()) return false;
+    auto A = mm->getInputs(0), B = mm->getInputs(1);
+    auto dt = A->getDType();
+    if (!(dt == DataType::Float16 || dt == DataType::BFloat16) || B->getDType() != dt) return false;
+    if (B->getRank() != 2 || !B->isWeight()) return false;
+    if (rowsOf(A) > 64) return false;  // decode regime: the grouped kernel is the skinny GEMM
+    return true;
+}
+
+const vector<ExecStep> &GraphObj::getSchedule() {
+    if (scheduleEpoch == topologyEpoch && !schedule.empty()) return schedule;
+    IT_ASSERT(topo_sort(), "graph has a cycle");
+    schedule.clear();
+    const bool fuse = fusionEnabled();
+    std::unordered_map<OperatorObj *, int> pos;
+    for (size_t i = 0; i < ops.size(); ++i) pos[ops[i].get()] = (int)i;
+    std::unordered_set<OperatorObj *> consumed;               // executed as part of an earlier (horizontal) step
+    std::unordered_map<OperatorObj *, Operator> deferredInto;  // consumer -> producer executed with it
+    std::unordered_set<OperatorObj *> deferred;
+
+    for (size_t i = 0; i < ops.size(); ++i) {
+        const Operator &op = ops[i];
+        if (consumed.count(op.get()) || deferred.count(op.get())) continue;
+        ExecStep st;
+        st.ops = {op};
+        auto it = deferredInto.find(op.get());
+        if (it != deferredInto.end()) {
+            st.kind = it->second->getOpType() == OpType::MatMul ? ExecStep::MatMulAdd : ExecStep::SiluMul;
+            st.ops = {it->second, op};
+            schedule.push_back(std::move(st));
+            continue;
+        }
+        if (!fuse) {
+            schedule.push_back(std::move(st));
+            continue;
+        }
+        const auto type = op->getOpType();
+        if (aliasable(op)) {
+            st.kind = ExecStep::Alias;
+        } else if (type == OpType::MatMul) {
+            // (1) horizontal: later MatMuls reading the same activation tensor
+            if (groupableMatmul(op)) {
+                auto A = op->getInputs(0);
+                int k = as<MatmulObj>(op)->getK();
+                for (auto &cand : A->getTargets()) {
+                    if (st.ops.size() >= 4) break;
+                    if (cand == op || consumed.count(cand.get()) || deferred.count(cand.get())) continue;
+                    if (cand->getOpType() != OpType::MatMul || cand->getInputs(0) != A) continue;
+                    if (pos[cand.get()] < (int)i || !groupableMatmul(cand) || as<MatmulObj>(cand)->getK() != k) continue;
+                    st.ops.push_back(cand);
+                }
+                if (st.ops.size() > 1) {
+                    st.kind = ExecStep::MatMulGroup;
+                    std::sort(st.ops.begin(), st.ops.end(),
+                              [&](const Operator &a, const Operator &b) { return pos[a.get()] < pos[b.get()]; });
+                    for (size_t j = 1; j < st.ops.size(); ++j) consumed.insert(st.ops[j].get());
+                }
+            }
+            // (2) vertical: MatMul -> Add(residual of identical shape), executed at the Add's position
+            if (st.kind == ExecStep::Single) {
+                auto mm = as<MatmulObj>(op);
+                auto out = op->getOutput();
+                auto targets = out->getTargets();
+                if (!mm->getBias() && out->getDType().isFloat() && targets.size() == 1 && !out->isOutput() &&
+                    targets[0]->getOpType() == OpType::Add && !deferredInto.count(targets[0].get())) {
+                    auto add = targets[0];
+                    auto other = add->getInputs(0) == out ? add->getInputs(1) : add->getInputs(0);
+                    if (other != out && other->getDims() == out->getDims() && other->getDType() == out->getDType() &&
+                        add->getOutput()->getDims() == out->getDims()) {
+                        deferredInto[add.get()] = op;
+                        deferred.insert(op.get());
+                        continue;
+                    }
+                }
+            }
+        } else if (type == OpType::Silu) {
+            auto out = op->getOutput();
+            auto targets = out->getTargets();
+            if (targets.size() == 1 && !out->isOutput() && targets[0]->getOpType() == OpType::Mul &&
+                !deferredInto.count(targets[0].get())) {
+                auto mul = targets[0];
+                auto other = mul->getInputs(0) == out ? mul->getInputs(1) : mul->getInputs(0);
+                if (other != out && other->getDims() == out->getDims() && other->getDType() == out->getDType() &&
+                    mul->getOutput()->getDims() == out->getDims()) {
+                    deferredInto[mul.get()] = op;
+                    deferred.insert(op.get());
+                    continue;
+                }
+            }
+        }
+        schedule.push_back(std::move(st));
+    }
+    scheduleEpoch = topologyEpoch;
+    return schedule;
+}
+
+}  // namespace infini

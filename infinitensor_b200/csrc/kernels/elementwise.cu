@@ -122,6 +122,31 @@ __global__ void __launch_bounds__(256) binary_general_kernel(int op, const T *__
     }
 }
 
+// out = T( T(silu(g)) * u )  -- the Silu -> Mul pair of the Llama MLP in one pass
+template <typename T>
+__global__ void __launch_bounds__(256) silu_mul_kernel(const T *__restrict__ g, const T *__restrict__ u,
+                                                       T *__restrict__ o, int64_t n, bool vec) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int V = Vec16<T>::N;
+    int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    int64_t done = 0;
+    if (vec) {
+        int64_t nv = n / V;
+        for (int64_t i = tid; i < nv; i += nthreads) {
+            Vec16<T> a = ld16_stream(g + i * V), b = ld16_stream(u + i * V), r;
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                r.v[j] = from_f<T>(round_t<T>(apply_unary(ITB_SILU, to_f(a.v[j]))) * to_f(b.v[j]));
+            st16(o + i * V, r);
+        }
+        done = nv * V;
+    }
+    for (int64_t i = done + tid; i < n; i += nthreads)
+        o[i] = from_f<T>(round_t<T>(apply_unary(ITB_SILU, to_f(g[i]))) * to_f(u[i]));
+}
+
 // collapse adjacent dims whose strides chain for every operand
 static int collapse(int rank, const int64_t *dims, const int64_t *const *strides, int nops, Dims8 &od,
                     Dims8 *os) {
@@ -223,6 +248,18 @@ extern "C" int it_b200_unary(int op, int dtype, const void *x, void *y, int64_t 
         launch_k(unary_kernel<T>, dim3(grid_for(items, 256)), dim3(256), 0, st, op, (const T *)x, (T *)y, n, vec);
     });
     ITB_LAUNCH_CHECK("unary");
+    return 0;
+}
+
+extern "C" int it_b200_silu_mul(int dtype, const void *gate, const void *up, void *out, int64_t n, void *stream) {
+    if (n == 0) return 0;
+    ITB_DISPATCH_FLOAT(dtype, "silu_mul", {
+        bool vec = aligned16(gate) && aligned16(up) && aligned16(out);
+        int64_t items = vec ? (n + Vec16<T>::N - 1) / Vec16<T>::N : n;
+        launch_k(silu_mul_kernel<T>, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, (const T *)gate,
+                 (const T *)up, (T *)out, n, vec);
+    });
+    ITB_LAUNCH_CHECK("silu_mul");
     return 0;
 }
 

@@ -18,7 +18,7 @@ struct GemmArgs {
 };
 
 __device__ __forceinline__ float gemm_act(int act, float v) {
-    switch (act) {
+    switch (act & 0xff) {
     case 1: return v > 0.f ? v : 0.f;
     case 2: return 1.f / (1.f + expf(-v));
     case 3: return tanhf(v);
@@ -29,6 +29,8 @@ __device__ __forceinline__ float gemm_act(int act, float v) {
 int launch_gemm_simt(int dtype, const GemmArgs &g, cudaStream_t st);
 // returns 0 = launched, 1 = error, -1 = shape not taken by this kernel
 int launch_gemm_skinny(int dtype, const GemmArgs &g, cudaStream_t st);
+int launch_gemm_skinny_grouped(int dtype, const GemmArgs &g0, int ngroups, const void *const *Ws, void *const *Cs,
+                               const int *Ns, cudaStream_t st);
 int launch_gemm_tc(int dtype, const GemmArgs &g, cudaStream_t st);
 
 // ---- TMA descriptor creation (driver entry point fetched at run time; no link-time libcuda) ----

@@ -68,8 +68,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
             int gn = n0 + tx * 4 + j;
             if (gn >= g.n) continue;
             float v = acc[i][j];
-            if (g.bias)
+            if (g.bias) {
+                if (g.act & ITB_ACT_ROUND_BEFORE_BIAS) v = round_t<T>(v);
                 v += to_f(((const T *)g.bias)[batch * g.bias_sb + gm * g.bias_sm + gn * g.bias_sn]);
+            }
             C[(int64_t)gm * g.n + gn] = from_f<T>(gemm_act(g.act, v));
         }
     }

@@ -34,8 +34,19 @@ template <int MT> struct SkinnyCfg {
     static constexpr int SMEM = STAGES * (SK_W_BYTES + X_BYTES) + RED_BYTES + 2 * STAGES * 8 + 1024;
 };
 
+// Up to 4 weight matrices that share the activation operand X (q/k/v, gate/up) run as ONE launch: the
+// N-tile index selects the group.  A plain MatMul is the 1-group case.
+constexpr int SK_MAX_GROUPS = 4;
+struct SkinnyGroups {
+    CUtensorMap mapW[SK_MAX_GROUPS];
+    void *C[SK_MAX_GROUPS];
+    int n[SK_MAX_GROUPS];
+    int tile_start[SK_MAX_GROUPS + 1];
+    int ngroups;
+};
+
 template <typename T, int MT>
-__global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_constant__ CUtensorMap mapW,
+__global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_constant__ SkinnyGroups grp,
                                                                  const __grid_constant__ CUtensorMap mapX,
                                                                  GemmArgs g, int ktiles, int ktiles_per_split) {
     using Cfg = SkinnyCfg<MT>;
@@ -51,7 +62,13 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
 
     cg::cluster_group cluster = cg::this_cluster();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * SK_BN;
+    int gi = 0;
+#pragma unroll
+    for (int i = 1; i < SK_MAX_GROUPS; ++i)
+        if (i < grp.ngroups && (int)blockIdx.x >= grp.tile_start[i]) gi = i;
+    const CUtensorMap *mapWp = &grp.mapW[gi];
+    const int n0 = ((int)blockIdx.x - grp.tile_start[gi]) * SK_BN;
+    const int gN = grp.n[gi];
     const int split = blockIdx.y, nsplit = gridDim.y;
     const int kt_begin = split * ktiles_per_split;
     const int kt_end = min(ktiles, kt_begin + ktiles_per_split);
@@ -66,7 +83,7 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
         fence_mbar_init();
     }
     if (warp == 4 && lane == 0) {
-        tma_prefetch_desc(&mapW);
+        tma_prefetch_desc(mapWp);
         tma_prefetch_desc(&mapX);
     }
     __syncthreads();
@@ -89,7 +106,7 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
             const int pre = min(S, my_kt);
             for (int it = 0; it < pre; ++it) {
                 mbar_expect_tx(&full[it], SK_W_BYTES + Cfg::X_BYTES);
-                tma_load_2d(w_sm + it * SK_W_BYTES, &mapW, &full[it], n0, (kt_begin + it) * SK_BK, pol_w);
+                tma_load_2d(w_sm + it * SK_W_BYTES, mapWp, &full[it], n0, (kt_begin + it) * SK_BK, pol_w);
             }
             pdl_wait();
             for (int it = 0; it < pre; ++it)
@@ -99,7 +116,7 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
                 mbar_wait(&empty[s], ((it / S) - 1) & 1);
                 mbar_expect_tx(&full[s], SK_W_BYTES + Cfg::X_BYTES);
                 const int k0 = (kt_begin + it) * SK_BK;
-                tma_load_2d(w_sm + s * SK_W_BYTES, &mapW, &full[s], n0, k0, pol_w);
+                tma_load_2d(w_sm + s * SK_W_BYTES, mapWp, &full[s], n0, k0, pol_w);
                 tma_load_2d(x_sm + s * Cfg::X_BYTES, &mapX, &full[s], k0, 0, pol_x);
             }
         }
@@ -159,11 +176,13 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
         for (int r = 0; r < nsplit; ++r)
             peers[r] = nsplit > 1 ? (const float *)cluster.map_shared_rank(red, r) : red;
         const T *bias = (const T *)g.bias;
-        T *C = (T *)g.C;
+        T *C = (T *)grp.C[gi];
+        const bool round_first = (g.act & ITB_ACT_ROUND_BEFORE_BIAS) != 0;
+        const int act = g.act & 0xff;
         for (int idx = threadIdx.x; idx < MT * 16 * (SK_BN / 2); idx += SK_THREADS) {
             const int row = idx / (SK_BN / 2), col = (idx % (SK_BN / 2)) * 2;
             const int gn = n0 + col;
-            if (row >= g.m || gn >= g.n) continue;
+            if (row >= g.m || gn >= gN) continue;
             float2 v = make_float2(0.f, 0.f);
             for (int r = 0; r < nsplit; ++r) {
                 float2 p = *reinterpret_cast<const float2 *>(&peers[r][row * SK_BN + col]);
@@ -171,20 +190,24 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
                 v.y += p.y;
             }
             if (bias) {
+                if (round_first) {  // MatMul -> Add fusion: reproduce the unfused graph's rounding of the MatMul output
+                    v.x = round_t<T>(v.x);
+                    v.y = round_t<T>(v.y);
+                }
                 v.x += to_f(bias[row * g.bias_sm + gn * g.bias_sn]);
-                if (gn + 1 < g.n) v.y += to_f(bias[row * g.bias_sm + (gn + 1) * g.bias_sn]);
+                if (gn + 1 < gN) v.y += to_f(bias[row * g.bias_sm + (gn + 1) * g.bias_sn]);
             }
-            v.x = gemm_act(g.act, v.x);
-            v.y = gemm_act(g.act, v.y);
-            T *dst = C + (int64_t)row * g.n + gn;
-            if (gn + 1 < g.n && (g.n & 1) == 0) {
+            v.x = gemm_act(act, v.x);
+            v.y = gemm_act(act, v.y);
+            T *dst = C + (int64_t)row * gN + gn;
+            if (gn + 1 < gN && (gN & 1) == 0) {
                 if constexpr (std::is_same<T, __nv_bfloat16>::value)
                     *reinterpret_cast<__nv_bfloat162 *>(dst) = __floats2bfloat162_rn(v.x, v.y);
                 else
                     *reinterpret_cast<__half2 *>(dst) = __floats2half2_rn(v.x, v.y);
             } else {
                 dst[0] = from_f<T>(v.x);
-                if (gn + 1 < g.n) dst[1] = from_f<T>(v.y);
+                if (gn + 1 < gN) dst[1] = from_f<T>(v.y);
             }
         }
     }
@@ -192,14 +215,24 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
 }
 
 template <typename T, int MT>
-static int launch_skinny_t(const GemmArgs &g, cudaStream_t st) {
+static int launch_skinny_t(const GemmArgs &g, int ngroups, const void *const *Ws, void *const *Cs, const int *Ns,
+                           cudaStream_t st) {
     using Cfg = SkinnyCfg<MT>;
-    CUtensorMap mapW, mapX;
-    if (!make_tma_2d_b16(&mapW, g.B, (uint64_t)g.k, (uint64_t)g.n, (uint64_t)g.n, SK_BK, SK_BN, 128))
-        ITB_FAIL("matmul(skinny): cuTensorMapEncodeTiled(W) failed");
+    SkinnyGroups grp{};
+    CUtensorMap mapX;
+    grp.ngroups = ngroups;
+    int tiles_n = 0;
+    for (int i = 0; i < ngroups; ++i) {
+        if (!make_tma_2d_b16(&grp.mapW[i], Ws[i], (uint64_t)g.k, (uint64_t)Ns[i], (uint64_t)Ns[i], SK_BK, SK_BN, 128))
+            ITB_FAIL("matmul(skinny): cuTensorMapEncodeTiled(W) failed");
+        grp.C[i] = Cs[i];
+        grp.n[i] = Ns[i];
+        grp.tile_start[i] = tiles_n;
+        tiles_n += (Ns[i] + SK_BN - 1) / SK_BN;
+    }
+    for (int i = ngroups; i <= SK_MAX_GROUPS; ++i) grp.tile_start[i] = tiles_n;
     if (!make_tma_2d_b16(&mapX, g.A, (uint64_t)g.m, (uint64_t)g.k, (uint64_t)g.k, MT * 16, SK_BK, 128))
         ITB_FAIL("matmul(skinny): cuTensorMapEncodeTiled(X) failed");
-    const int tiles_n = (g.n + SK_BN - 1) / SK_BN;
     const int ktiles = (g.k + SK_BK - 1) / SK_BK;
     // enough CTAs for two per SM, at least 4 k-tiles per CTA, cluster <= 8
     int splitk = (2 * kNumSMs) / tiles_n;
@@ -229,27 +262,52 @@ static int launch_skinny_t(const GemmArgs &g, cudaStream_t st) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapW, mapX, g, ktiles, per);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, grp, mapX, g, ktiles, per);
     ITB_CHECK(e == cudaSuccess, "matmul(skinny): launch failed: %s", cudaGetErrorString(e));
     itb::count_launch();
     return 0;
 }
 
-int launch_gemm_skinny(int dtype, const GemmArgs &g, cudaStream_t st) {
-    if (dtype != ITB_BF16 && dtype != ITB_F16) return -1;
-    if (g.batch != 1 || g.trans_a || g.trans_b || g.m > 64 || g.m < 1) return -1;
-    if (g.n % 8 != 0 || g.k % 8 != 0 || g.n < 64 || g.k < 64) return -1;
-    if (!aligned16(g.A) || !aligned16(g.B) || ((uintptr_t)g.C & 3)) return -1;
-    const int mt = (g.m + 15) / 16;
-#define SK_GO(TT)                                                                              \
-    do {                                                                                       \
-        if (mt == 1) return launch_skinny_t<TT, 1>(g, st);                                     \
-        if (mt == 2) return launch_skinny_t<TT, 2>(g, st);                                     \
-        return launch_skinny_t<TT, 4>(g, st);                                                  \
-    } while (0)
-    if (dtype == ITB_BF16) SK_GO(__nv_bfloat16);
-    SK_GO(__half);
-#undef SK_GO
+static bool skinny_ok(int dtype, const GemmArgs &g) {
+    if (dtype != ITB_BF16 && dtype != ITB_F16) return false;
+    if (g.batch != 1 || g.trans_a || g.trans_b || g.m > 64 || g.m < 1) return false;
+    if (g.n % 8 != 0 || g.k % 8 != 0 || g.n < 64 || g.k < 64) return false;
+    if (!aligned16(g.A) || !aligned16(g.B) || ((uintptr_t)g.C & 3)) return false;
+    return true;
 }
+
+#define SK_GO(TT, ...)                                                                         \
+    do {                                                                                       \
+        if (mt == 1) return launch_skinny_t<TT, 1>(__VA_ARGS__);                               \
+        if (mt == 2) return launch_skinny_t<TT, 2>(__VA_ARGS__);                               \
+        return launch_skinny_t<TT, 4>(__VA_ARGS__);                                            \
+    } while (0)
+
+int launch_gemm_skinny(int dtype, const GemmArgs &g, cudaStream_t st) {
+    if (!skinny_ok(dtype, g)) return -1;
+    const int mt = (g.m + 15) / 16;
+    const void *Ws[1] = {g.B};
+    void *Cs[1] = {g.C};
+    int Ns[1] = {g.n};
+    if (dtype == ITB_BF16) SK_GO(__nv_bfloat16, g, 1, Ws, Cs, Ns, st);
+    SK_GO(__half, g, 1, Ws, Cs, Ns, st);
+}
+
+// X[M,K] . {W_i[K,N_i]} -> {C_i[M,N_i]} in one launch (no bias / activation)
+int launch_gemm_skinny_grouped(int dtype, const GemmArgs &g0, int ngroups, const void *const *Ws, void *const *Cs,
+                               const int *Ns, cudaStream_t st) {
+    if (ngroups < 1 || ngroups > SK_MAX_GROUPS) return -1;
+    for (int i = 0; i < ngroups; ++i) {
+        GemmArgs g = g0;
+        g.B = Ws[i];
+        g.C = Cs[i];
+        g.n = Ns[i];
+        if (!skinny_ok(dtype, g)) return -1;
+    }
+    const int mt = (g0.m + 15) / 16;
+    if (dtype == ITB_BF16) SK_GO(__nv_bfloat16, g0, ngroups, Ws, Cs, Ns, st);
+    SK_GO(__half, g0, ngroups, Ws, Cs, Ns, st);
+}
+#undef SK_GO
 
 }  // namespace itb

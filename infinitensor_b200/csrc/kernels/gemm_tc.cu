@@ -217,7 +217,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                     const int m = c0 + j;
                     if (m < g.m) {
                         float f = __uint_as_float(v[j]);
-                        if (bias) f += to_f(bias[m * g.bias_sm + gn * g.bias_sn]);
+                        if (bias) {
+                            if (g.act & ITB_ACT_ROUND_BEFORE_BIAS) f = round_t<T>(f);
+                            f += to_f(bias[m * g.bias_sm + gn * g.bias_sn]);
+                        }
                         C[(int64_t)m * g.n + gn] = from_f<T>(gemm_act(g.act, f));
                     }
                 }
@@ -235,7 +238,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                 if (m >= g.m || gn >= g.n) continue;
                 float f = 0.f;
                 for (int r = 0; r < nsplit; ++r) f += peers[r][idx];
-                if (bias) f += to_f(bias[m * g.bias_sm + gn * g.bias_sn]);
+                if (bias) {
+                    if (g.act & ITB_ACT_ROUND_BEFORE_BIAS) f = round_t<T>(f);
+                    f += to_f(bias[m * g.bias_sm + gn * g.bias_sn]);
+                }
                 C[(int64_t)m * g.n + gn] = from_f<T>(gemm_act(g.act, f));
             }
         }

@@ -231,3 +231,44 @@ def test_tensor_parallel_rule_gloo_world2(tmp_path):
 if __name__ == "__main__" and "--tp-worker" in sys.argv:
     sys.path.insert(0, ROOT)
     _tp_worker()
+
+
+def test_fused_schedule_and_alias_plan(B, monkeypatch):
+    """The execution schedule groups q/k/v and gate/up MatMuls, folds the residual Adds and Silu*Mul, and turns
+    the decode graph's Reshape / size-1 Transpose ops into storage aliases; ITB_NO_FUSION=1 gives the 1:1 order."""
+    import collections
+    from infinitensor_b200 import graphs as G
+    rt = B.HostPlanRuntime()
+    cfg = G.LlamaConfig(layers=2, d_model=512, heads=4, head_dim=128, ffn=1024, vocab=128, s_max=32, batch=16)
+    h = B.GraphHandler(rt)
+    G.build_llama_decode(h, cfg)
+    sc = h.schedule()
+    kinds = collections.Counter(s.split(":")[0] for s in sc)
+    assert kinds == {"Alias": 16, "Single": 13, "MatMulGroup": 4, "MatMulAdd": 4, "SiluMul": 2}
+    assert "MatMulGroup:MatMul+MatMul+MatMul" in sc and "MatMulGroup:MatMul+MatMul" in sc
+    launches = sum(1 for s in sc if not s.startswith("Alias"))
+    assert launches == 2 * 10 + 3  # 10 kernels per layer + gather, final norm, logits
+    h.data_malloc()
+    fused_bytes = h.arena_bytes()[1]
+    monkeypatch.setenv("ITB_NO_FUSION", "1")
+    h2 = B.GraphHandler(rt)
+    G.build_llama_decode(h2, cfg)
+    assert len(h2.schedule()) == len(h2.operators()) and all(s.startswith("Single:") for s in h2.schedule())
+    h2.data_malloc()
+    assert fused_bytes <= 1.1 * h2.arena_bytes()[1]  # grouped steps allocate their outputs together
+    monkeypatch.delenv("ITB_NO_FUSION")
+    # alias: a Reshape's output shares its input's storage unless it is a graph output / KV-cache operand
+    h3 = B.GraphHandler(rt)
+    x = h3.tensor([4, 6], 1); x.set_input()
+    r = h3.reshape(h3.relu(x, None), None, [2, 12])
+    t = h3.transpose(h3.reshape(r, None, [2, 1, 12]), None, [1, 0, 2])   # only moves a size-1 dim
+    y = h3.relu(t, None)
+    z = h3.reshape(y, None, [24])                                         # graph output: must stay a copy
+    h3.data_malloc()
+    sc3 = h3.schedule()
+    assert sc3 == ["Single:Relu", "Alias:Reshape", "Alias:Reshape", "Alias:Transpose", "Single:Relu", "Single:Reshape"]
+    assert r.device_ptr() == t.device_ptr() and z.device_ptr() != y.device_ptr()
+    h4 = B.GraphHandler(rt)
+    a = h4.tensor([2, 3, 4], 1); a.set_input()
+    assert h4.schedule() == [] and h4.transpose(a, None, [0, 2, 1]) is not None
+    assert h4.schedule() == ["Single:Transpose"]                          # a real permutation is never an alias
