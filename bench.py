@@ -288,7 +288,7 @@ def run_b200(args):
         for wt, K_, N_ in mm:
             L.check(L.lib.it_b200_matmul(16, ctypes.c_void_p(scratch_in.data_ptr()), ctypes.c_void_p(wt.device_ptr()), None,
                                          ctypes.c_void_p(scratch_out.data_ptr()), 1, cfg.batch, N_, K_, cfg.batch * K_, 0,
-                                         0, 0, 0, 0, 0, 0, None, 0, rs))
+                                         0, 0, 0, 0, 0, 0x200, None, 0, rs))
     torch.cuda.synchronize()
     for _ in range(2):
         gemm_pass()

@@ -143,6 +143,8 @@ int it_b200_batchnorm(int dtype, const void *x, const float *mean, const float *
  *      it_b200_matmul_workspace() returns 0). ---- */
 #define ITB_ACT_ROUND_BEFORE_BIAS 0x100 /* OR into `act`: round the product to the storage dtype before the bias
                                           add -- makes a fused MatMul -> Add bit-identical to the two separate ops */
+#define ITB_MATMUL_B_CONST 0x200 /* OR into `act`: operand B is a constant (weight) that no kernel of the stream writes;
+                                    lets the GEMM request its first weight tiles ahead of griddepcontrol.wait */
 int64_t it_b200_matmul_workspace(int dtype, int64_t b, int m, int n, int k);
 int it_b200_matmul(int dtype, const void *A, const void *B, const void *bias, void *C, int64_t b,
                    int m, int n, int k, int64_t stride_a, int64_t stride_b, int trans_a,

@@ -335,6 +335,7 @@ void runMatmul(const Operator &_op, const RuntimeObj *ctx, const Tensor &residua
         }
         if (residual) act |= ITB_ACT_ROUND_BEFORE_BIAS;
     }
+    if (B->isWeight()) act |= ITB_MATMUL_B_CONST;
     // [b, m, k] x [k, n] with the weight broadcast over the batch (how the frontend emits every Linear layer of a
     // decode step: b = batch, m = 1) is ONE GEMM with M = b*m -- the reference instead runs b strided-batched GEMMs
     // with stride 0 (matmul.cc:124-168)

@@ -330,8 +330,9 @@ class LazyAllocator {
 // ---------------------------------------------------------------- execution schedule (fusion plan)
 // The reference executes one kernel per operator in topological order and its GraphObj::optimize() is an
 // empty hook (src/core/graph.cc:184-191).  Here the graph additionally derives an EXECUTION SCHEDULE: a list
-// of steps, each one operator or a small group of operators that one fused kernel executes with results
-// bit-identical to the unfused sequence.  The memory planner takes tensor lifetimes from the schedule and the
+// of steps, each one operator or a small group of operators that one fused kernel executes.  Alias / MatMul+Add /
+// Silu*Mul steps are bit-identical to the unfused sequence; a MatMul group may use another split-K partition
+// (fp32 summation order) and is held to the GEMM tolerance.  The memory planner takes tensor lifetimes from the schedule and the
 // runtime dispatches it.  ITB_NO_FUSION=1 yields the 1:1 schedule.
 struct ExecStep {
     enum Kind {

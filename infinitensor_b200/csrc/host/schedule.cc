@@ -14,6 +14,11 @@ static bool fusionEnabled() {
     const char *e = std::getenv("ITB_NO_FUSION");
     return !(e && e[0] == '1');
 }
+// ITB_FUSION_MASK (debug / A-B): bit 0 alias, 1 MatMul groups, 2 MatMul+Add, 3 Silu*Mul; default all
+static int fusionMask() {
+    const char *e = std::getenv("ITB_FUSION_MASK");
+    return e && e[0] ? std::atoi(e) : 15;
+}
 
 static bool isKvCacheOperand(const Tensor &t) {
     for (auto &op : t->getTargets())
@@ -68,6 +73,7 @@ const vector<ExecStep> &GraphObj::getSchedule() {
     IT_ASSERT(topo_sort(), "graph has a cycle");
     schedule.clear();
     const bool fuse = fusionEnabled();
+    const int mask = fusionMask();
     std::unordered_map<OperatorObj *, int> pos;
     for (size_t i = 0; i < ops.size(); ++i) pos[ops[i].get()] = (int)i;
     std::unordered_set<OperatorObj *> consumed;               // executed as part of an earlier (horizontal) step
@@ -91,11 +97,11 @@ const vector<ExecStep> &GraphObj::getSchedule() {
             continue;
         }
         const auto type = op->getOpType();
-        if (aliasable(op)) {
+        if ((mask & 1) && aliasable(op)) {
             st.kind = ExecStep::Alias;
         } else if (type == OpType::MatMul) {
             // (1) horizontal: later MatMuls reading the same activation tensor
-            if (groupableMatmul(op)) {
+            if ((mask & 2) && groupableMatmul(op)) {
                 auto A = op->getInputs(0);
                 int k = as<MatmulObj>(op)->getK();
                 for (auto &cand : A->getTargets()) {
@@ -113,7 +119,7 @@ const vector<ExecStep> &GraphObj::getSchedule() {
                 }
             }
             // (2) vertical: MatMul -> Add(residual of identical shape), executed at the Add's position
-            if (st.kind == ExecStep::Single) {
+            if (st.kind == ExecStep::Single && (mask & 4)) {
                 auto mm = as<MatmulObj>(op);
                 auto out = op->getOutput();
                 auto targets = out->getTargets();
@@ -129,7 +135,7 @@ const vector<ExecStep> &GraphObj::getSchedule() {
                     }
                 }
             }
-        } else if (type == OpType::Silu) {
+        } else if (type == OpType::Silu && (mask & 8)) {
             auto out = op->getOutput();
             auto targets = out->getTargets();
             if (targets.size() == 1 && !out->isOutput() && targets[0]->getOpType() == OpType::Mul &&

@@ -103,7 +103,7 @@ extern "C" int it_b200_matmul(int dtype, const void *A, const void *B, const voi
     (void)workspace_bytes;
     ITB_CHECK(dtype == ITB_F32 || dtype == ITB_F16 || dtype == ITB_BF16, "matmul: unsupported dtype %d", dtype);
     ITB_CHECK(m >= 0 && n >= 0 && k >= 0 && b >= 0, "matmul: negative dimension");
-    ITB_CHECK((act & 0xff) >= 0 && (act & 0xff) <= 3, "matmul: bad act %d", act);
+    ITB_CHECK((act & 0xff) <= 3 && (act & ~0x3ff) == 0, "matmul: bad act %d", act);
     GemmArgs g{A, B, bias, C, b, m, n, k, stride_a, stride_b, trans_a, trans_b,
                bias_stride_b, bias_stride_m, bias_stride_n, act};
     return run_gemm(dtype, g, (cudaStream_t)stream);
@@ -113,7 +113,7 @@ extern "C" int it_b200_matmul_grouped(int dtype, const void *X, int n_groups, co
                                       const int *N, int m, int k, void *stream) {
     ITB_CHECK(n_groups >= 1, "matmul_grouped: no groups");
     auto st = (cudaStream_t)stream;
-    GemmArgs g{X, W[0], nullptr, C[0], 1, m, N[0], k, (int64_t)m * k, 0, 0, 0, 0, 0, 0, 0};
+    GemmArgs g{X, W[0], nullptr, C[0], 1, m, N[0], k, (int64_t)m * k, 0, 0, 0, 0, 0, 0, ITB_MATMUL_B_CONST};
     const char *pin = std::getenv("ITB_GEMM_IMPL");
     if (!(pin && pin[0]) || !strcmp(pin, "skinny")) {
         int r = launch_gemm_skinny_grouped(dtype, g, n_groups, W, C, N, st);

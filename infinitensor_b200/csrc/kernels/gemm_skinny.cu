@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
             // PDL: the weights are written by no kernel of the step, so the first ring of weight tiles is
             // requested BEFORE waiting for the predecessor kernel; activations only after pdl_wait()
             const int pre = min(S, my_kt);
+            if (!(g.act & ITB_MATMUL_B_CONST)) pdl_wait();  // B produced upstream: no early prefetch
             for (int it = 0; it < pre; ++it) {
                 mbar_expect_tx(&full[it], SK_W_BYTES + Cfg::X_BYTES);
                 tma_load_2d(w_sm + it * SK_W_BYTES, mapWp, &full[it], n0, (kt_begin + it) * SK_BK, pol_w);
@@ -305,8 +306,10 @@ int launch_gemm_skinny_grouped(int dtype, const GemmArgs &g0, int ngroups, const
         if (!skinny_ok(dtype, g)) return -1;
     }
     const int mt = (g0.m + 15) / 16;
-    if (dtype == ITB_BF16) SK_GO(__nv_bfloat16, g0, ngroups, Ws, Cs, Ns, st);
-    SK_GO(__half, g0, ngroups, Ws, Cs, Ns, st);
+    GemmArgs gc = g0;
+    gc.act |= ITB_MATMUL_B_CONST;  // grouped weights are constants by contract
+    if (dtype == ITB_BF16) SK_GO(__nv_bfloat16, gc, ngroups, Ws, Cs, Ns, st);
+    SK_GO(__half, gc, ngroups, Ws, Cs, Ns, st);
 }
 #undef SK_GO
 

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             const uint64_t pol_x = l2_policy_evict_last();
             // PDL: weight tiles of the first ring are requested before waiting for the predecessor kernel
             const int pre = min(S, my_kt);
+            if (!(g.act & ITB_MATMUL_B_CONST)) pdl_wait();  // B produced upstream: no early prefetch
             for (int it = 0; it < pre; ++it) {
                 mbar_expect_tx(&full[it], TC_W_BYTES + p.x_bytes);
                 const int k0 = (kt_begin + it) * TC_BK;

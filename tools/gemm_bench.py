@@ -22,7 +22,7 @@ def run(impl, m, k, n, reps=40, nbuf=12):
 
     def go(i):
         L.check(L.lib.it_b200_matmul(16, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(ws[i % nbuf].data_ptr()), None,
-                                     ctypes.c_void_p(y.data_ptr()), 1, m, n, k, m * k, 0, 0, 0, 0, 0, 0, 0, None, 0, st))
+                                     ctypes.c_void_p(y.data_ptr()), 1, m, n, k, m * k, 0, 0, 0, 0, 0, 0, 0x200, None, 0, st))
     for i in range(nbuf):
         go(i)
     torch.cuda.synchronize()
