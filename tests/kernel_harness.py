@@ -261,6 +261,26 @@ def matmul(a, b, bias=None, transA=False, transB=False, dt=F32, act=0):
     return host(c)
 
 
+def matmul_grouped(x, ws, dt=BF16):
+    xd = dev(x, dt)
+    wd = [dev(w, dt) for w in ws]
+    m, k = x.shape
+    outs = [torch.empty((m, w.shape[1]), dtype=xd.dtype, device="cuda") for w in ws]
+    W = (ctypes.c_void_p * len(ws))(*[t.data_ptr() for t in wd])
+    C = (ctypes.c_void_p * len(ws))(*[t.data_ptr() for t in outs])
+    L.check(L.lib.it_b200_matmul_grouped(dt, ptr(xd), len(ws), W, C, L.i32arr([w.shape[1] for w in ws]), m, k, stream()))
+    sync()
+    return [host(o) for o in outs]
+
+
+def silu_mul(g, u, dt=BF16):
+    gd, ud = dev(g, dt), dev(u, dt)
+    o = torch.empty_like(gd)
+    L.check(L.lib.it_b200_silu_mul(dt, ptr(gd), ptr(ud), ptr(o), gd.numel(), stream()))
+    sync()
+    return host(o)
+
+
 def conv2d(x, w, ph, pw, sh, sw, dh, dw, dt=F32):
     xd, wd = dev(x, dt), dev(w, dt)
     N, C, H, W = x.shape

@@ -237,6 +237,15 @@ def test_reduce_pool_bn_parity(K, dt):
     close(K.batch_norm(img, m, v, s, b, 1e-5, dt), oracle.batch_norm(img, m, v, s, b, 1e-5, dt), tol, tol)
 
 
+@pytest.mark.parametrize("dt", [F32, F16, BF16])
+def test_silu_mul_matches_two_kernels(K, dt):
+    g, u = rnd((16, 11008), 50, dt, 2.0), rnd((16, 11008), 51, dt)
+    fused = K.silu_mul(g, u, dt)
+    two = K.binary("mul", K.unary("silu", g, dt), u, dt)
+    assert np.array_equal(fused, two)  # same rounding points as Silu followed by Mul
+    close(fused, oracle.binary("mul", oracle.unary("silu", g, dt), u, dt), 4 * EPS[dt], 1e-6)
+
+
 def gemm_tol(dt, k, amax, bmax):
     """fp32 rel 1e-5*sqrt(K); 16-bit with fp32 accumulate: abs <= 2^-8 (bf16) / 2^-11 (fp16)
     * sqrt(K) * max|a| * max|b| against an fp32 oracle fed the same rounded inputs."""
@@ -292,6 +301,30 @@ def _gemm_case(K, m, k, n, dt):
 def test_matmul_skinny_parity(K, gemm_impl, m, k, n, dt):
     """Decode-regime GEMM (TMA + mma.sync + cluster split-K) at the Llama-7B shapes of SURVEY 8a row a1."""
     _gemm_case(K, m, k, n, dt)
+
+
+@pytest.mark.parametrize("gemm_impl", ["streamk"], indirect=True)
+@pytest.mark.parametrize("dt", [BF16, F16])
+@pytest.mark.parametrize("m,k,n", SKINNY_SHAPES + [(16, 4096, 12288), (48, 2048, 704)])
+def test_matmul_streamk_parity(K, gemm_impl, m, k, n, dt):
+    """Persistent stream-K decode GEMM: k-tile-granular work split, ticketed deterministic partial reduction."""
+    _gemm_case(K, m, k, n, dt)
+    a, b = rnd((m, k), 23, dt, 0.5), rnd((k, n), 24, dt, 0.05)
+    first = K.matmul(a, b, None, False, False, dt)
+    for _ in range(3):  # self-cleaning tickets + fixed-order reduction: repeat launches are bit-identical
+        assert np.array_equal(first, K.matmul(a, b, None, False, False, dt))
+
+
+@pytest.mark.parametrize("gemm_impl", ["skinny", "streamk"], indirect=True)
+@pytest.mark.parametrize("dt", [BF16, F16])
+def test_matmul_grouped_parity(K, gemm_impl, dt):
+    """q/k/v- and gate/up-style grouped launches: several weight matrices sharing X in one kernel."""
+    for m, k, ns in [(16, 4096, [4096, 4096, 4096]), (16, 1024, [2816, 2816]), (5, 512, [64, 128, 192, 256])]:
+        x = rnd((m, k), 40, dt, 0.5)
+        ws = [rnd((k, n), 41 + i, dt, 0.05) for i, n in enumerate(ns)]
+        outs = K.matmul_grouped(x, ws, dt)
+        for w, o in zip(ws, outs):
+            close(o, oracle.matmul(x, w, None, False, False, dt), 2 * EPS[dt], gemm_tol(dt, k, np.abs(x).max(), np.abs(w).max()))
 
 
 @pytest.mark.parametrize("gemm_impl", ["tc"], indirect=True)

@@ -38,7 +38,7 @@ def run(impl, m, k, n, reps=40, nbuf=12):
 
 
 if __name__ == "__main__":
-    impls = sys.argv[1:] or ["skinny", "tc"]
+    impls = sys.argv[1:] or ["skinny", "tc", "streamk"]
     print(f"{'shape':>22s} " + " ".join(f"{i:>22s}" for i in impls))
     for (m, k, n) in SHAPES:
         row = []
