@@ -17,6 +17,8 @@
 // Grid = ceil(N/64) x splitK CTAs, two co-resident per SM (~100 KB smem each).
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "gemm.cuh"
 
 namespace cg = cooperative_groups;
@@ -236,7 +238,12 @@ static int launch_skinny_t(const GemmArgs &g, int ngroups, const void *const *Ws
         ITB_FAIL("matmul(skinny): cuTensorMapEncodeTiled(X) failed");
     const int ktiles = (g.k + SK_BK - 1) / SK_BK;
     // enough CTAs for two per SM, at least 4 k-tiles per CTA, cluster <= 8
-    int splitk = (2 * kNumSMs) / tiles_n;
+    static int target = 0;
+    if (!target) {
+        const char *e = std::getenv("ITB_SKINNY_TARGET_CTAS");
+        target = e && e[0] ? std::atoi(e) : 2 * kNumSMs;
+    }
+    int splitk = target / tiles_n;
     splitk = std::max(1, std::min(splitk, 8));
     splitk = std::min(splitk, std::max(1, ktiles / 4));
     int per = (ktiles + splitk - 1) / splitk;

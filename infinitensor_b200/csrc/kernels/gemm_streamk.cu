@@ -64,8 +64,10 @@ __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_c
     int *s_flag = reinterpret_cast<int *>(empty + S);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long G = gridDim.x, c = blockIdx.x;
-    const long long u0 = c * U / G, u1 = (c + 1) * U / G;
+    const int G = gridDim.x, c = blockIdx.x;
+    const int u0 = (int)((long long)c * U / G), u1 = (int)((long long)(c + 1) * U / G);
+    const int nunits = u1 - u0;
+    const int tile0 = u0 / ktiles, kt0 = u0 - tile0 * ktiles;  // the only divisions: once per CTA
 
     pdl_trigger();
     if (threadIdx.x == 0) {
@@ -86,33 +88,45 @@ __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_c
     };
 
     if (warp == 4) {
-        // ===== TMA producer: one lane streams this CTA's unit range =====
+        // ===== TMA producer: one lane streams this CTA's unit range (tile / k-tile / stage tracked incrementally) =====
         if (lane == 0) {
             const uint64_t pol_w = l2_policy_evict_first(), pol_x = l2_policy_evict_last();
             const bool w_const = (g.act & ITB_MATMUL_B_CONST) != 0;
-            const long long pre_end = u0 + S < u1 ? u0 + S : u1;
+            const int pre = nunits < S ? nunits : S;
+            int tile = tile0, kt = kt0, gi, n0;
+            locate(tile, gi, n0);
             if (!w_const) pdl_wait();
-            for (long long u = u0; u < pre_end; ++u) {  // first ring: weights may go ahead of the PDL wait
-                const int s = (int)(u - u0);
-                int gi, n0;
-                locate((int)(u / ktiles), gi, n0);
-                mbar_expect_tx(&full[s], KS_W_BYTES + Cfg::X_BYTES);
-                tma_load_2d(w_sm + s * KS_W_BYTES, &grp.mapW[gi], &full[s], n0, (int)(u % ktiles) * KS_BK, pol_w);
+            for (int it = 0; it < pre; ++it) {  // first ring: weights may go ahead of the PDL wait
+                mbar_expect_tx(&full[it], KS_W_BYTES + Cfg::X_BYTES);
+                tma_load_2d(w_sm + it * KS_W_BYTES, &grp.mapW[gi], &full[it], n0, kt * KS_BK, pol_w);
+                if (++kt == ktiles) {
+                    kt = 0;
+                    locate(++tile, gi, n0);
+                }
             }
             if (w_const) pdl_wait();
-            for (long long u = u0; u < pre_end; ++u)
-                tma_load_2d(x_sm + (int)(u - u0) * Cfg::X_BYTES, &mapX, &full[(int)(u - u0)], (int)(u % ktiles) * KS_BK,
-                            0, pol_x);
-            for (long long u = pre_end; u < u1; ++u) {
-                const long long it = u - u0;
-                const int s = (int)(it % S);
-                mbar_wait(&empty[s], (uint32_t)(((it / S) - 1) & 1));
-                int gi, n0;
-                locate((int)(u / ktiles), gi, n0);
-                const int k0 = (int)(u % ktiles) * KS_BK;
+            {
+                int kx = kt0;
+                for (int it = 0; it < pre; ++it) {
+                    tma_load_2d(x_sm + it * Cfg::X_BYTES, &mapX, &full[it], kx * KS_BK, 0, pol_x);
+                    if (++kx == ktiles) kx = 0;
+                }
+            }
+            int s = 0;
+            uint32_t phase = 0;  // parity of the `empty` completion that frees stage s for its next use
+            for (int it = pre; it < nunits; ++it) {
+                mbar_wait(&empty[s], phase);
                 mbar_expect_tx(&full[s], KS_W_BYTES + Cfg::X_BYTES);
-                tma_load_2d(w_sm + s * KS_W_BYTES, &grp.mapW[gi], &full[s], n0, k0, pol_w);
-                tma_load_2d(x_sm + s * Cfg::X_BYTES, &mapX, &full[s], k0, 0, pol_x);
+                tma_load_2d(w_sm + s * KS_W_BYTES, &grp.mapW[gi], &full[s], n0, kt * KS_BK, pol_w);
+                tma_load_2d(x_sm + s * Cfg::X_BYTES, &mapX, &full[s], kt * KS_BK, 0, pol_x);
+                if (++kt == ktiles) {
+                    kt = 0;
+                    locate(++tile, gi, n0);
+                }
+                if (++s == S) {
+                    s = 0;
+                    phase ^= 1;
+                }
             }
         }
         __syncwarp();
@@ -126,7 +140,7 @@ __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_c
     const int tid = threadIdx.x;  // 0..127
     const T *bias = (const T *)g.bias;
     const bool round_first = (g.act & ITB_ACT_ROUND_BEFORE_BIAS) != 0;
-    const int first_tile = (int)(u0 / ktiles);
+    const int first_tile = tile0;
 
     float acc[MT][2][4];
     auto zero_acc = [&]() {
@@ -138,12 +152,11 @@ __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_c
                 for (int i = 0; i < 4; ++i) acc[mt][nb][i] = 0.f;
     };
     zero_acc();
-    long long seg_begin = u0;
+    int tile = tile0, kt = kt0, seg_kt = kt0, s = 0;
+    uint32_t phase = 0;
 
-    for (long long u = u0; u < u1; ++u) {
-        const long long it = u - u0;
-        const int s = (int)(it % S);
-        mbar_wait(&full[s], (uint32_t)((it / S) & 1));
+    for (int it = 0; it < nunits; ++it) {
+        mbar_wait(&full[s], phase);
         const uint32_t wb = w_base + s * KS_W_BYTES, xb = x_base + s * Cfg::X_BYTES;
 #pragma unroll
         for (int kk = 0; kk < KS_BK / 16; ++kk) {
@@ -168,15 +181,24 @@ __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_c
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
-
-        const bool seg_end = (u + 1 == u1) || ((u + 1) % ktiles == 0);
+        if (++s == S) {
+            s = 0;
+            phase ^= 1;
+        }
+        const int this_tile = tile, this_kt = kt;
+        if (++kt == ktiles) {
+            kt = 0;
+            ++tile;
+        }
+        const bool seg_end = (it + 1 == nunits) || (kt == 0);
         if (!seg_end) continue;
+        const bool whole = (seg_kt == 0) && (this_kt == ktiles - 1);
+        seg_kt = kt;
+        (void)this_kt;
 
-        // ---------------- flush the finished segment [seg_begin, u] of column tile `tile` ----------------
-        const int tile = (int)(u / ktiles);
-        const bool whole = (seg_begin % ktiles == 0) && ((u + 1) % ktiles == 0);
+        // ---------------- flush the finished segment of column tile `this_tile` ----------------
         int gi, n0;
-        locate(tile, gi, n0);
+        locate(this_tile, gi, n0);
         const int gN = grp.n[gi];
         T *C = (T *)grp.C[gi];
 #pragma unroll
@@ -191,23 +213,23 @@ __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_c
         bar_consumers();
 
         bool finish = whole;  // do I run the epilogue of this tile?
-        long long c_first = c, c_last = c;
+        int c_first = c, c_last = c;
         if (!whole) {
             // publish my partial, take a ticket; the last contributor finishes the tile
-            const int j = (tile == first_tile) ? 0 : 1;
+            const int j = (this_tile == first_tile) ? 0 : 1;
             float *my = slots + ((size_t)c * 2 + j) * Cfg::RED_FLOATS;
             for (int i = tid * 4; i < Cfg::RED_FLOATS; i += 128 * 4)
                 *reinterpret_cast<float4 *>(my + i) = *reinterpret_cast<const float4 *>(red + i);
             __threadfence();
             bar_consumers();
-            const long long t0 = (long long)tile * ktiles;
-            c_first = ((t0 + 1) * G - 1) / U;               // largest c' with c'*U/G <= t0
-            c_last = ((t0 + ktiles) * G - 1) / U;           // largest c' with c'*U/G <= t0 + ktiles - 1
+            const long long t0 = (long long)this_tile * ktiles;
+            c_first = (int)(((t0 + 1) * G - 1) / U);        // largest c' with c'*U/G <= t0
+            c_last = (int)(((t0 + ktiles) * G - 1) / U);    // largest c' with c'*U/G <= t0 + ktiles - 1
             if (tid == 0) {
-                const int ncontrib = (int)(c_last - c_first + 1);
-                const int old = atomicAdd(&tickets[tile], 1);
+                const int ncontrib = c_last - c_first + 1;
+                const int old = atomicAdd(&tickets[this_tile], 1);
                 const int last = (old == ncontrib - 1);
-                if (last) tickets[tile] = 0;  // self-cleaning: every contributor has already arrived
+                if (last) tickets[this_tile] = 0;  // self-cleaning: every contributor has already arrived
                 *s_flag = last;
             }
             bar_consumers();
@@ -225,8 +247,8 @@ __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_c
                     v = *reinterpret_cast<const float2 *>(&red[row * KS_BN + col]);
                 } else {
                     v = make_float2(0.f, 0.f);
-                    for (long long cc = c_first; cc <= c_last; ++cc) {  // fixed order -> deterministic sum
-                        const int jj = ((int)((cc * U / G) / ktiles) == tile) ? 0 : 1;
+                    for (int cc = c_first; cc <= c_last; ++cc) {  // fixed order -> deterministic sum
+                        const int jj = ((int)(((long long)cc * U / G) / ktiles) == this_tile) ? 0 : 1;
                         const float2 p = __ldcg(reinterpret_cast<const float2 *>(
                             slots + ((size_t)cc * 2 + jj) * Cfg::RED_FLOATS + row * KS_BN + col));
                         v.x += p.x;
@@ -257,7 +279,6 @@ __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_c
         }
         bar_consumers();  // `red` is reused by the next segment
         zero_acc();
-        seg_begin = u + 1;
     }
 }
 
