@@ -25,15 +25,19 @@ namespace cg = cooperative_groups;
 
 namespace itb {
 
-constexpr int SK_BN = 64, SK_BK = 64;
-constexpr int SK_W_BYTES = SK_BN * SK_BK * 2;  // 8 KB
+constexpr int SK_BOX = 64, SK_BK = 64;
+constexpr int SK_BOX_BYTES = SK_BOX * SK_BK * 2;  // 8 KB: one [64k x 64n] swizzled TMA box
 constexpr int SK_THREADS = 160;                // 4 consumer warps + 1 producer warp
 
-template <int MT> struct SkinnyCfg {
+// NB = 64-column boxes per tile: NB = 1 -> 64-wide tiles (128 B per weight row), NB = 2 -> 128-wide tiles (256 B
+// contiguous per row: better DRAM efficiency when there are enough column tiles to fill the machine)
+template <int MT, int NB> struct SkinnyCfg {
+    static constexpr int BN = NB * SK_BOX;
+    static constexpr int W_BYTES = NB * SK_BOX_BYTES;
     static constexpr int X_BYTES = MT * 16 * SK_BK * 2;
-    static constexpr int STAGES = MT == 1 ? 10 : (MT == 2 ? 8 : 6);
-    static constexpr int RED_BYTES = MT * 16 * SK_BN * 4;
-    static constexpr int SMEM = STAGES * (SK_W_BYTES + X_BYTES) + RED_BYTES + 2 * STAGES * 8 + 1024;
+    static constexpr int STAGES = (MT == 1 ? 100 : (MT == 2 ? 96 : 92)) * 1024 / (W_BYTES + X_BYTES);
+    static constexpr int RED_BYTES = MT * 16 * BN * 4;
+    static constexpr int SMEM = STAGES * (W_BYTES + X_BYTES) + RED_BYTES + 2 * STAGES * 8 + 1024;
 };
 
 // Up to 4 weight matrices that share the activation operand X (q/k/v, gate/up) run as ONE launch: the
@@ -47,12 +51,13 @@ struct SkinnyGroups {
     int ngroups;
 };
 
-template <typename T, int MT>
+template <typename T, int MT, int NB>
 __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_constant__ SkinnyGroups grp,
                                                                  const __grid_constant__ CUtensorMap mapX,
                                                                  GemmArgs g, int ktiles, int ktiles_per_split) {
-    using Cfg = SkinnyCfg<MT>;
+    using Cfg = SkinnyCfg<MT, NB>;
     constexpr int S = Cfg::STAGES;
+    constexpr int SK_BN = Cfg::BN, SK_W_BYTES = Cfg::W_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled TMA tiles need 1024-byte alignment
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -90,11 +95,11 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
     }
     __syncthreads();
 
-    float acc[MT][2][4];
+    float acc[MT][2 * NB][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
+        for (int nb = 0; nb < 2 * NB; ++nb)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[mt][nb][i] = 0.f;
 
@@ -109,7 +114,10 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
             if (!(g.act & ITB_MATMUL_B_CONST)) pdl_wait();  // B produced upstream: no early prefetch
             for (int it = 0; it < pre; ++it) {
                 mbar_expect_tx(&full[it], SK_W_BYTES + Cfg::X_BYTES);
-                tma_load_2d(w_sm + it * SK_W_BYTES, mapWp, &full[it], n0, (kt_begin + it) * SK_BK, pol_w);
+#pragma unroll
+                for (int bx = 0; bx < NB; ++bx)
+                    tma_load_2d(w_sm + it * SK_W_BYTES + bx * SK_BOX_BYTES, mapWp, &full[it], n0 + bx * SK_BOX,
+                                (kt_begin + it) * SK_BK, pol_w);
             }
             pdl_wait();
             for (int it = 0; it < pre; ++it)
@@ -119,7 +127,9 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
                 mbar_wait(&empty[s], ((it / S) - 1) & 1);
                 mbar_expect_tx(&full[s], SK_W_BYTES + Cfg::X_BYTES);
                 const int k0 = (kt_begin + it) * SK_BK;
-                tma_load_2d(w_sm + s * SK_W_BYTES, mapWp, &full[s], n0, k0, pol_w);
+#pragma unroll
+                for (int bx = 0; bx < NB; ++bx)
+                    tma_load_2d(w_sm + s * SK_W_BYTES + bx * SK_BOX_BYTES, mapWp, &full[s], n0 + bx * SK_BOX, k0, pol_w);
                 tma_load_2d(x_sm + s * Cfg::X_BYTES, &mapX, &full[s], k0, 0, pol_x);
             }
         }
@@ -143,16 +153,17 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
                     ldmatrix_x4(a[mt][0], a[mt][1], a[mt][2], a[mt][3],
                                 xb + row * 128 + ((chunk ^ (row & 7)) << 4));
                 }
-                uint32_t b0, b1, b2, b3;
-                {
+#pragma unroll
+                for (int bx = 0; bx < NB; ++bx) {  // warp w owns columns [16w, 16w+16) of every 64-column box
+                    uint32_t b0, b1, b2, b3;
                     const int krow = kk * 16 + r8 + 8 * (mi & 1);
                     const int nchunk = warp * 2 + (mi >> 1);
-                    ldmatrix_x4_trans(b0, b1, b2, b3, wb + krow * 128 + ((nchunk ^ (krow & 7)) << 4));
-                }
+                    ldmatrix_x4_trans(b0, b1, b2, b3, wb + bx * SK_BOX_BYTES + krow * 128 + ((nchunk ^ (krow & 7)) << 4));
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    mma_m16n8k16<T>(acc[mt][0], a[mt], b0, b1);
-                    mma_m16n8k16<T>(acc[mt][1], a[mt], b2, b3);
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_m16n8k16<T>(acc[mt][bx * 2 + 0], a[mt], b0, b1);
+                        mma_m16n8k16<T>(acc[mt][bx * 2 + 1], a[mt], b2, b3);
+                    }
                 }
             }
             __syncwarp();
@@ -162,9 +173,9 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int nb = 0; nb < 2; ++nb) {
+            for (int nb = 0; nb < 2 * NB; ++nb) {
                 const int row = mt * 16 + (lane >> 2);
-                const int col = warp * 16 + nb * 8 + (lane & 3) * 2;
+                const int col = (nb >> 1) * SK_BOX + warp * 16 + (nb & 1) * 8 + (lane & 3) * 2;
                 *reinterpret_cast<float2 *>(&red[row * SK_BN + col]) = make_float2(acc[mt][nb][0], acc[mt][nb][1]);
                 *reinterpret_cast<float2 *>(&red[(row + 8) * SK_BN + col]) =
                     make_float2(acc[mt][nb][2], acc[mt][nb][3]);
@@ -217,16 +228,17 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
     if (nsplit > 1) cluster.sync();  // peers' shared memory must outlive the leader's reads
 }
 
-template <typename T, int MT>
-static int launch_skinny_t(const GemmArgs &g, int ngroups, const void *const *Ws, void *const *Cs, const int *Ns,
-                           cudaStream_t st) {
-    using Cfg = SkinnyCfg<MT>;
+template <typename T, int MT, int NB>
+static int launch_skinny_nb(const GemmArgs &g, int ngroups, const void *const *Ws, void *const *Cs, const int *Ns,
+                            cudaStream_t st) {
+    using Cfg = SkinnyCfg<MT, NB>;
+    constexpr int SK_BN = Cfg::BN;
     SkinnyGroups grp{};
     CUtensorMap mapX;
     grp.ngroups = ngroups;
     int tiles_n = 0;
     for (int i = 0; i < ngroups; ++i) {
-        if (!make_tma_2d_b16(&grp.mapW[i], Ws[i], (uint64_t)g.k, (uint64_t)Ns[i], (uint64_t)Ns[i], SK_BK, SK_BN, 128))
+        if (!make_tma_2d_b16(&grp.mapW[i], Ws[i], (uint64_t)g.k, (uint64_t)Ns[i], (uint64_t)Ns[i], SK_BK, SK_BOX, 128))
             ITB_FAIL("matmul(skinny): cuTensorMapEncodeTiled(W) failed");
         grp.C[i] = Cs[i];
         grp.n[i] = Ns[i];
@@ -250,7 +262,7 @@ static int launch_skinny_t(const GemmArgs &g, int ngroups, const void *const *Ws
     splitk = (ktiles + per - 1) / per;  // no empty split
 
     static bool attr_done = false;
-    auto kern = gemm_skinny_kernel<T, MT>;
+    auto kern = gemm_skinny_kernel<T, MT, NB>;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         ITB_CHECK(e == cudaSuccess, "matmul(skinny): smem attribute: %s", cudaGetErrorString(e));
@@ -274,6 +286,22 @@ static int launch_skinny_t(const GemmArgs &g, int ngroups, const void *const *Ws
     ITB_CHECK(e == cudaSuccess, "matmul(skinny): launch failed: %s", cudaGetErrorString(e));
     itb::count_launch();
     return 0;
+}
+
+// tile width: 128 columns once 64-wide tiles would already oversubscribe the 2 x 148 CTA slots
+template <typename T, int MT>
+static int launch_skinny_t(const GemmArgs &g, int ngroups, const void *const *Ws, void *const *Cs, const int *Ns,
+                           cudaStream_t st) {
+    static int force = -1;
+    if (force < 0) {
+        const char *e = std::getenv("ITB_SKINNY_NB");
+        force = e && e[0] ? std::atoi(e) : 0;
+    }
+    int tiles64 = 0;
+    for (int i = 0; i < ngroups; ++i) tiles64 += (Ns[i] + 63) / 64;
+    const int nb = force ? force : (tiles64 > 2 * kNumSMs ? 2 : 1);
+    if (nb == 2) return launch_skinny_nb<T, MT, 2>(g, ngroups, Ws, Cs, Ns, st);
+    return launch_skinny_nb<T, MT, 1>(g, ngroups, Ws, Cs, Ns, st);
 }
 
 static bool skinny_ok(int dtype, const GemmArgs &g) {

@@ -26,7 +26,7 @@ constexpr int KS_BN = 64, KS_BK = 64;
 constexpr int KS_W_BYTES = KS_BN * KS_BK * 2;
 constexpr int KS_THREADS = 160;  // 4 consumer warps + 1 producer warp
 constexpr int KS_MAX_GROUPS = 4;
-constexpr int KS_MAX_CTAS = 148 * 2;
+constexpr int KS_MAX_CTAS = 148 * 2;  // stream-K grid; the (tile, split) mode may launch up to 4x this
 constexpr int KS_MAX_TILES = 4096;
 
 struct StreamKGroups {
@@ -49,7 +49,7 @@ __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 128;
 template <typename T, int MT>
 __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_constant__ StreamKGroups grp,
                                                                   const __grid_constant__ CUtensorMap mapX,
-                                                                  GemmArgs g, int ktiles, long long U,
+                                                                  GemmArgs g, int ktiles, long long U, int tiles_mode,
                                                                   float *__restrict__ slots,
                                                                   int *__restrict__ tickets) {
     using Cfg = StreamKCfg<MT>;
@@ -65,7 +65,21 @@ __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x, c = blockIdx.x;
-    const int u0 = (int)((long long)c * U / G), u1 = (int)((long long)(c + 1) * U / G);
+    // tiles_mode == 0: stream-K (contiguous unit ranges).  tiles_mode = T > 0: classic (column tile, k split) grid --
+    // CTA c owns tile c % T and split c / T, so CTAs that run together sweep ADJACENT column tiles at the same k rows
+    // (DRAM-page friendly for row-major [K,N] weights); partial tiles still meet through the ticketed slot reduction.
+    int u0, u1, nsplit_t = 1, per_t = ktiles;
+    if (tiles_mode > 0) {
+        nsplit_t = G / tiles_mode;
+        per_t = (ktiles + nsplit_t - 1) / nsplit_t;
+        const int t = c % tiles_mode, sp = c / tiles_mode;
+        u0 = t * ktiles + sp * per_t;
+        u1 = min(u0 + per_t, (t + 1) * ktiles);
+        if (u1 < u0) u1 = u0;
+    } else {
+        u0 = (int)((long long)c * U / G);
+        u1 = (int)((long long)(c + 1) * U / G);
+    }
     const int nunits = u1 - u0;
     const int tile0 = u0 / ktiles, kt0 = u0 - tile0 * ktiles;  // the only divisions: once per CTA
 
@@ -192,7 +206,7 @@ __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_c
         }
         const bool seg_end = (it + 1 == nunits) || (kt == 0);
         if (!seg_end) continue;
-        const bool whole = (seg_kt == 0) && (this_kt == ktiles - 1);
+        const bool whole = (seg_kt == 0) && (this_kt == ktiles - 1) && (tiles_mode == 0 || nsplit_t == 1);
         seg_kt = kt;
         (void)this_kt;
 
@@ -216,17 +230,24 @@ __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_c
         int c_first = c, c_last = c;
         if (!whole) {
             // publish my partial, take a ticket; the last contributor finishes the tile
-            const int j = (this_tile == first_tile) ? 0 : 1;
+            const int j = (tiles_mode > 0 || this_tile == first_tile) ? 0 : 1;
             float *my = slots + ((size_t)c * 2 + j) * Cfg::RED_FLOATS;
             for (int i = tid * 4; i < Cfg::RED_FLOATS; i += 128 * 4)
                 *reinterpret_cast<float4 *>(my + i) = *reinterpret_cast<const float4 *>(red + i);
             __threadfence();
             bar_consumers();
             const long long t0 = (long long)this_tile * ktiles;
-            c_first = (int)(((t0 + 1) * G - 1) / U);        // largest c' with c'*U/G <= t0
-            c_last = (int)(((t0 + ktiles) * G - 1) / U);    // largest c' with c'*U/G <= t0 + ktiles - 1
+            int ncontrib;
+            if (tiles_mode > 0) {
+                ncontrib = (ktiles + per_t - 1) / per_t;  // non-empty splits of this tile
+                c_first = 0;
+                c_last = ncontrib - 1;                    // split ordinals; CTA = tile + ordinal * T
+            } else {
+                c_first = (int)(((t0 + 1) * G - 1) / U);      // largest c' with c'*U/G <= t0
+                c_last = (int)(((t0 + ktiles) * G - 1) / U);  // largest c' with c'*U/G <= t0 + ktiles - 1
+                ncontrib = c_last - c_first + 1;
+            }
             if (tid == 0) {
-                const int ncontrib = c_last - c_first + 1;
                 const int old = atomicAdd(&tickets[this_tile], 1);
                 const int last = (old == ncontrib - 1);
                 if (last) tickets[this_tile] = 0;  // self-cleaning: every contributor has already arrived
@@ -248,9 +269,15 @@ __global__ void __launch_bounds__(KS_THREADS) gemm_streamk_kernel(const __grid_c
                 } else {
                     v = make_float2(0.f, 0.f);
                     for (int cc = c_first; cc <= c_last; ++cc) {  // fixed order -> deterministic sum
-                        const int jj = ((int)(((long long)cc * U / G) / ktiles) == this_tile) ? 0 : 1;
+                        size_t slot;
+                        if (tiles_mode > 0) {
+                            slot = (size_t)(this_tile + cc * tiles_mode) * 2;
+                        } else {
+                            const int jj = ((int)(((long long)cc * U / G) / ktiles) == this_tile) ? 0 : 1;
+                            slot = (size_t)cc * 2 + jj;
+                        }
                         const float2 p = __ldcg(reinterpret_cast<const float2 *>(
-                            slots + ((size_t)cc * 2 + jj) * Cfg::RED_FLOATS + row * KS_BN + col));
+                            slots + slot * Cfg::RED_FLOATS + row * KS_BN + col));
                         v.x += p.x;
                         v.y += p.y;
                     }
@@ -295,7 +322,7 @@ static StreamKScratch *get_scratch(cudaStream_t st) {
     std::lock_guard<std::mutex> lock(mu);
     auto &sc = table[{dev, st}];
     if (!sc.slots) {
-        const size_t slot_bytes = (size_t)KS_MAX_CTAS * 2 * StreamKCfg<4>::RED_FLOATS * 4;
+        const size_t slot_bytes = (size_t)KS_MAX_CTAS * 4 * 2 * StreamKCfg<4>::RED_FLOATS * 4;
         if (cudaMalloc(&sc.slots, slot_bytes) != cudaSuccess) return nullptr;
         if (cudaMalloc(&sc.tickets, KS_MAX_TILES * sizeof(int)) != cudaSuccess) return nullptr;
         if (cudaMemset(sc.tickets, 0, KS_MAX_TILES * sizeof(int)) != cudaSuccess) return nullptr;
@@ -303,6 +330,14 @@ static StreamKScratch *get_scratch(cudaStream_t st) {
     return &sc;
 }
 
+static bool streamk_pure() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = std::getenv("ITB_STREAMK_PURE");
+        v = e && e[0] == '1';
+    }
+    return v == 1;
+}
 static int streamk_ctas_per_sm() {
     static int v = 0;
     if (!v) {
@@ -336,6 +371,18 @@ static int launch_streamk_t(const GemmArgs &g, int ngroups, const void *const *W
     const long long U = (long long)tiles_n * ktiles;
     long long G = (long long)kNumSMs * streamk_ctas_per_sm();
     if (G > U) G = U;
+    int tiles_mode = 0;
+    if (!streamk_pure()) {
+        // (tile, split) grid: split-K so that the grid comes close to (but not over) the resident-CTA budget
+        int splitk = (int)(G / tiles_n);
+        splitk = std::max(1, std::min(splitk, 16));
+        splitk = std::min(splitk, std::max(1, ktiles / 4));
+        int per = (ktiles + splitk - 1) / splitk;
+        splitk = (ktiles + per - 1) / per;
+        tiles_mode = tiles_n;
+        G = (long long)tiles_n * splitk;
+        if (G > KS_MAX_CTAS * 4) return -1;
+    }
     StreamKScratch *sc = get_scratch(st);
     ITB_CHECK(sc != nullptr, "matmul(streamk): scratch allocation failed");
 
@@ -346,7 +393,7 @@ static int launch_streamk_t(const GemmArgs &g, int ngroups, const void *const *W
         ITB_CHECK(e == cudaSuccess, "matmul(streamk): smem attribute: %s", cudaGetErrorString(e));
         attr_done = true;
     }
-    cudaError_t e = launch_k(kern, dim3((unsigned)G), dim3(KS_THREADS), Cfg::SMEM, st, grp, mapX, g, ktiles, U, sc->slots,
+    cudaError_t e = launch_k(kern, dim3((unsigned)G), dim3(KS_THREADS), Cfg::SMEM, st, grp, mapX, g, ktiles, U, tiles_mode, sc->slots,
                              sc->tickets);
     ITB_CHECK(e == cudaSuccess, "matmul(streamk): launch failed: %s", cudaGetErrorString(e));
     itb::count_launch();
