@@ -45,6 +45,8 @@ constexpr int kNumSMs = 148;  // B200
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();  // false when ITB_NO_PDL=1
+// zero-initialised, self-cleaning int tickets private to (device, stream); nullptr if n exceeds the pool (65536)
+int *stream_tickets(cudaStream_t st, int n);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

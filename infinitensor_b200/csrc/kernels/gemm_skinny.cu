@@ -35,9 +35,12 @@ template <int MT, int NB> struct SkinnyCfg {
     static constexpr int BN = NB * SK_BOX;
     static constexpr int W_BYTES = NB * SK_BOX_BYTES;
     static constexpr int X_BYTES = MT * 16 * SK_BK * 2;
-    static constexpr int STAGES = (MT == 1 ? 100 : (MT == 2 ? 96 : 92)) * 1024 / (W_BYTES + X_BYTES);
     static constexpr int RED_BYTES = MT * 16 * BN * 4;
-    static constexpr int SMEM = STAGES * (W_BYTES + X_BYTES) + RED_BYTES + 2 * STAGES * 8 + 1024;
+    static constexpr int stages_for(int budget_kb) {
+        int s = (budget_kb * 1024 - RED_BYTES - 1024 - 256) / (W_BYTES + X_BYTES);
+        return s < 2 ? 2 : (s > 16 ? 16 : s);
+    }
+    static constexpr int smem_for(int stages) { return stages * (W_BYTES + X_BYTES) + RED_BYTES + 2 * stages * 8 + 1024; }
 };
 
 // Up to 4 weight matrices that share the activation operand X (q/k/v, gate/up) run as ONE launch: the
@@ -54,9 +57,9 @@ struct SkinnyGroups {
 template <typename T, int MT, int NB>
 __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_constant__ SkinnyGroups grp,
                                                                  const __grid_constant__ CUtensorMap mapX,
-                                                                 GemmArgs g, int ktiles, int ktiles_per_split) {
+                                                                 GemmArgs g, int ktiles, int ktiles_per_split,
+                                                                 int S) {
     using Cfg = SkinnyCfg<MT, NB>;
-    constexpr int S = Cfg::STAGES;
     constexpr int SK_BN = Cfg::BN, SK_W_BYTES = Cfg::W_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled TMA tiles need 1024-byte alignment
@@ -122,15 +125,20 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
             pdl_wait();
             for (int it = 0; it < pre; ++it)
                 tma_load_2d(x_sm + it * Cfg::X_BYTES, &mapX, &full[it], (kt_begin + it) * SK_BK, 0, pol_x);
+            int s = 0;
+            uint32_t ph = 0;  // parity of the `empty` completion that frees stage s for its next use
             for (int it = pre; it < my_kt; ++it) {
-                const int s = it % S;
-                mbar_wait(&empty[s], ((it / S) - 1) & 1);
+                mbar_wait(&empty[s], ph);
                 mbar_expect_tx(&full[s], SK_W_BYTES + Cfg::X_BYTES);
                 const int k0 = (kt_begin + it) * SK_BK;
 #pragma unroll
                 for (int bx = 0; bx < NB; ++bx)
                     tma_load_2d(w_sm + s * SK_W_BYTES + bx * SK_BOX_BYTES, mapWp, &full[s], n0 + bx * SK_BOX, k0, pol_w);
                 tma_load_2d(x_sm + s * Cfg::X_BYTES, &mapX, &full[s], k0, 0, pol_x);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
         }
         __syncwarp();
@@ -139,9 +147,10 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
         const int mi = lane >> 3;             // which 8x8 matrix this lane addresses
         const int r8 = lane & 7;
         const uint32_t w_base = smem_u32(w_sm), x_base = smem_u32(x_sm);
+        int s = 0;
+        uint32_t ph = 0;
         for (int it = 0; it < my_kt; ++it) {
-            const int s = it % S;
-            mbar_wait(&full[s], (it / S) & 1);
+            mbar_wait(&full[s], ph);
             const uint32_t wb = w_base + s * SK_W_BYTES, xb = x_base + s * Cfg::X_BYTES;
 #pragma unroll
             for (int kk = 0; kk < SK_BK / 16; ++kk) {
@@ -168,6 +177,10 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == S) {
+                s = 0;
+                ph ^= 1;
+            }
         }
         // partial tile -> shared memory (fp32)
 #pragma unroll
@@ -261,17 +274,24 @@ static int launch_skinny_nb(const GemmArgs &g, int ngroups, const void *const *W
     int per = (ktiles + splitk - 1) / splitk;
     splitk = (ktiles + per - 1) / per;  // no empty split
 
-    static bool attr_done = false;
+    static int budget_kb = 0;
+    if (!budget_kb) {
+        const char *e = std::getenv("ITB_SKINNY_SMEM_KB");
+        budget_kb = e && e[0] ? std::atoi(e) : 106;
+    }
+    const int stages = Cfg::stages_for(budget_kb);
+    const int smem_bytes = Cfg::smem_for(stages);
+    static int attr_smem = 0;
     auto kern = gemm_skinny_kernel<T, MT, NB>;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (smem_bytes > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         ITB_CHECK(e == cudaSuccess, "matmul(skinny): smem attribute: %s", cudaGetErrorString(e));
-        attr_done = true;
+        attr_smem = smem_bytes;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(tiles_n, splitk, 1);
     cfg.blockDim = dim3(SK_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -282,7 +302,7 @@ static int launch_skinny_nb(const GemmArgs &g, int ngroups, const void *const *W
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, grp, mapX, g, ktiles, per);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, grp, mapX, g, ktiles, per, stages);
     ITB_CHECK(e == cudaSuccess, "matmul(skinny): launch failed: %s", cudaGetErrorString(e));
     itb::count_launch();
     return 0;

@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -24,6 +26,21 @@ bool pdl_enabled() {
         v = (e && e[0] == '1') ? 0 : 1;
     }
     return v == 1;
+}
+int *stream_tickets(cudaStream_t st, int n) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, int *> table;
+    constexpr int kPool = 65536;
+    if (n > kPool) return nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    int *&p = table[{dev, st}];
+    if (!p) {
+        if (cudaMalloc(&p, kPool * sizeof(int)) != cudaSuccess) return p = nullptr;
+        if (cudaMemset(p, 0, kPool * sizeof(int)) != cudaSuccess) return nullptr;
+    }
+    return p;
 }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
 }  // namespace itb
