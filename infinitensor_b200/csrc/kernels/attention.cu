@@ -29,14 +29,13 @@ template <typename P> __device__ __forceinline__ int read_pos(const void *p) { r
 
 // partial layout in workspace: [BH, nsplit] x { m, l, acc[128] }
 template <typename T, int WARPS, int U>
-__global__ void __launch_bounds__(WARPS * 32, 1024 / (WARPS * 32)) attn_decode_kernel(T *__restrict__ kcache, T *__restrict__ vcache,
+__global__ void __launch_bounds__(WARPS * 32) attn_decode_kernel(T *__restrict__ kcache, T *__restrict__ vcache,
                                                                  const T *__restrict__ q,
                                                                  const T *__restrict__ kin,
                                                                  const T *__restrict__ vin,
                                                                  const void *__restrict__ position_id,
                                                                  int pos_dtype, T *__restrict__ out, int Smax,
-                                                                 int nsplit, float *__restrict__ partial,
-                                                                 int *__restrict__ tickets) {
+                                                                 int nsplit, float *__restrict__ partial) {
     pdl_trigger();
     pdl_wait();
     using C = RowCfg<T>;
@@ -155,7 +154,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1024 / (WARPS * 32)) attn_decode_k
         }
     }
     __syncthreads();
-    __shared__ int s_last;
     if (threadIdx.x < kD) {
         int d = threadIdx.x;
         float mx = -INFINITY;
@@ -177,42 +175,32 @@ __global__ void __launch_bounds__(WARPS * 32, 1024 / (WARPS * 32)) attn_decode_k
                 pp[0] = mx;
                 pp[1] = L;
             }
-            __threadfence();
-        }
-    }
-    if (nsplit > 1) {
-        // ticketed merge: the last split of this (b, h) to arrive combines all partials in split order
-        // (deterministic) and resets the ticket -- no second kernel, no spinning
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int old = atomicAdd(&tickets[bh], 1);
-            const int last = (old == nsplit - 1);
-            if (last) tickets[bh] = 0;
-            s_last = last;
-        }
-        __syncthreads();
-        if (s_last && threadIdx.x < kD) {
-            __threadfence();
-            const int d = threadIdx.x;
-            const float *pp = partial + (int64_t)bh * nsplit * (kD + 2);
-            float mx = -INFINITY;
-            for (int sidx = 0; sidx < nsplit; ++sidx) mx = fmaxf(mx, __ldcg(pp + sidx * (kD + 2)));
-            float L = 0.f, A = 0.f;
-            for (int sidx = 0; sidx < nsplit; ++sidx) {
-                const float ms = __ldcg(pp + sidx * (kD + 2));
-                const float c = ms > -INFINITY ? expf(ms - mx) : 0.f;
-                L += __ldcg(pp + sidx * (kD + 2) + 1) * c;
-                A += __ldcg(pp + sidx * (kD + 2) + 2 + d) * c;
-            }
-            out[(int64_t)bh * kD + d] = from_f<T>(A / L);
         }
     }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(kD) attn_merge_kernel(const float *__restrict__ partial, T *__restrict__ out,
+                                                        int nsplit) {
+    pdl_trigger();
+    pdl_wait();
+    int bh = blockIdx.x, d = threadIdx.x;
+    const float *pp = partial + (int64_t)bh * nsplit * (kD + 2);
+    float mx = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) mx = fmaxf(mx, pp[s * (kD + 2)]);
+    float L = 0.f, A = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+        float ms = pp[s * (kD + 2)];
+        float c = ms > -INFINITY ? expf(ms - mx) : 0.f;
+        L += pp[s * (kD + 2) + 1] * c;
+        A += pp[s * (kD + 2) + 2 + d] * c;
+    }
+    out[(int64_t)bh * kD + d] = from_f<T>(A / L);
+}
+
 static int choose_nsplit(int BH, int Smax) {
-    // ~6 CTAs of 128 threads per SM so the per-SM CTA count is even (512 (b,h) pairs alone give 3.46 per SM =
-    // 15 % imbalance); never split below 64 positions per CTA
-    int want = (6 * kNumSMs + BH - 1) / BH;
+    // enough CTAs for >= 2 per SM; never split below 64 positions per CTA
+    int want = (2 * kNumSMs + BH - 1) / BH;
     int cap = Smax / 64 > 0 ? Smax / 64 : 1;
     int n = want < cap ? want : cap;
     return n < 1 ? 1 : n;
@@ -246,16 +234,16 @@ extern "C" int it_b200_attention_kvcache(int dtype, void *k_cache, void *v_cache
     auto st = (cudaStream_t)stream;
     dim3 grid(BH, ns);
     ITB_DISPATCH_FLOAT(dtype, "AttentionKVCache", {
-        constexpr int WARPS = 4, U = 2;
-        int *tickets = nullptr;
-        if (ns > 1) {
-            tickets = stream_tickets(st, BH);
-            ITB_CHECK(tickets != nullptr, "AttentionKVCache: ticket scratch allocation failed (B*H = %d)", BH);
-        }
-        launch_k(attn_decode_kernel<T, WARPS, U>, dim3(grid), dim3(WARPS * 32), 0, st, (T *)k_cache, (T *)v_cache,
-                 (const T *)q, (const T *)k, (const T *)v, position_id, pos_dtype, (T *)out, S_max, ns,
-                 (float *)workspace, tickets);
+        constexpr int WARPS = 8, U = 4;  // measured: U=2 at 64 regs (4 CTAs/SM) is 11 % slower end-to-end -- per-thread MLP wins
+        launch_k(attn_decode_kernel<T, WARPS, U>, dim3(grid), dim3(WARPS * 32), 0, st, (T *)k_cache, (T *)v_cache, (const T *)q,
+                                                                    (const T *)k, (const T *)v, position_id,
+                                                                    pos_dtype, (T *)out, S_max, ns,
+                                                                    (float *)workspace);
         ITB_LAUNCH_CHECK("AttentionKVCache");
+        if (ns > 1) {
+            launch_k(attn_merge_kernel<T>, dim3(BH), dim3(kD), 0, st, (const float *)workspace, (T *)out, ns);
+            ITB_LAUNCH_CHECK("AttentionKVCache.merge");
+        }
     });
     return 0;
 }
