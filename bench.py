@@ -270,25 +270,32 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (gemm_skinny_kernel): all MatMuls of one step, back to back on the
     # runtime stream, CUDA events around them, repeated; algorithmic bytes = weight + activation in/out bytes
-    mm = []
     e = 2
     d, dl, f, fl, V = cfg.d_model, cfg.d_model // world, cfg.ffn, cfg.ffn // world, cfg.vocab
+    # the launches the step's schedule issues for MatMul: grouped q/k/v, o, grouped gate/up, down per layer + logits
+    mm = []  # (list of weight tensors, K, N of each)
     for li in range(cfg.layers):
         p = f"l{li}."
-        for nm, K_, N_ in ((p + "wq", d, dl), (p + "wk", d, dl), (p + "wv", d, dl), (p + "wo", dl, d), (p + "wg", d, fl),
-                           (p + "wu", d, fl), (p + "wd", fl, d)):
-            mm.append((g.weights[nm][0], K_, N_))
-    mm.append((g.weights["lm_head"][0], d, V))
+        mm.append(([g.weights[p + "wq"][0], g.weights[p + "wk"][0], g.weights[p + "wv"][0]], d, dl))
+        mm.append(([g.weights[p + "wo"][0]], dl, d))
+        mm.append(([g.weights[p + "wg"][0], g.weights[p + "wu"][0]], d, fl))
+        mm.append(([g.weights[p + "wd"][0]], fl, d))
+    mm.append(([g.weights["lm_head"][0]], d, V))
     scratch_in = torch.zeros((cfg.batch, max(f, d)), dtype=torch.bfloat16, device="cuda")
-    scratch_out = torch.zeros((cfg.batch, V), dtype=torch.bfloat16, device="cuda")
+    scratch_out = [torch.zeros((cfg.batch, V), dtype=torch.bfloat16, device="cuda") for _ in range(3)]
     rs = ctypes.c_void_p(rt.stream())
-    gemm_bytes = sum((K_ * N_ + cfg.batch * (K_ + N_)) * e for _, K_, N_ in mm)
+    gemm_bytes = sum(len(ws) * (K_ * N_ + cfg.batch * N_) * e + cfg.batch * K_ * e for ws, K_, N_ in mm)
+    gemm_launches = len(mm)
+    calls = []
+    for ws, K_, N_ in mm:
+        W = (ctypes.c_void_p * len(ws))(*[w.device_ptr() for w in ws])
+        C = (ctypes.c_void_p * len(ws))(*[scratch_out[i].data_ptr() for i in range(len(ws))])
+        N = (ctypes.c_int * len(ws))(*[N_] * len(ws))
+        calls.append((len(ws), W, C, N, K_))
 
     def gemm_pass():
-        for wt, K_, N_ in mm:
-            L.check(L.lib.it_b200_matmul(16, ctypes.c_void_p(scratch_in.data_ptr()), ctypes.c_void_p(wt.device_ptr()), None,
-                                         ctypes.c_void_p(scratch_out.data_ptr()), 1, cfg.batch, N_, K_, cfg.batch * K_, 0,
-                                         0, 0, 0, 0, 0, 0x200, None, 0, rs))
+        for n_, W, C, N, K_ in calls:
+            L.check(L.lib.it_b200_matmul_grouped(16, ctypes.c_void_p(scratch_in.data_ptr()), n_, W, C, N, cfg.batch, K_, rs))
     torch.cuda.synchronize()
     for _ in range(2):
         gemm_pass()
@@ -313,7 +320,7 @@ def run_b200(args):
     tp = os.path.join(ROOT, "profiles", "gemm_skinny_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")  # measured DRAM bytes, average per launch
         except Exception:
             pass
     step_bytes = cfg.algorithmic_bytes(POS, world)
@@ -333,9 +340,9 @@ def run_b200(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
-            "roofline": {"kernel": "gemm_skinny_kernel (all MatMuls of one step)", "bound": "hbm",
+            "roofline": {"kernel": "gemm_skinny_kernel (every MatMul launch of one step: grouped q/k/v, o, grouped gate/up, down x layers + logits)", "bound": "hbm",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "peak_source": peak_src, "launches": len(mm),
+                         "traffic": traffic, "peak_source": peak_src, "launches": gemm_launches,
                          "algorithmic_bytes_per_step": gemm_bytes, "ms_per_step_in_kernel": round(gemm_ms, 4)},
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": round(step_bytes / (ms_step * 1e-3) / 1e9, 1),
                               "peak": peak, "unit": "GB/s", "frac": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4)},
