@@ -176,6 +176,11 @@ def run_b200(args):
         box = [B.CudaRuntime.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         rt.init_comm_with_id(box[0], world, rank)
+        # NVLink peer-memory comm for the fused one-shot all-reduce (+ residual + RMSNorm)
+        if os.environ.get("ITB_NO_P2P", "0") != "1":
+            handles = [None] * world
+            dist.all_gather_object(handles, rt.p2p_export())
+            rt.p2p_import(handles, world, rank)
     h = B.GraphHandler(rt)
     g = G.build_llama_decode(h, cfg, world, rank)
     h.data_malloc()

@@ -180,6 +180,17 @@ int it_b200_attention_kvcache(int dtype, void *k_cache, void *v_cache, const voi
                               int pos_dtype, void *out, int B, int H, int S_max, int D,
                               void *workspace, int64_t workspace_bytes, void *stream);
 
+/* ---- One-shot all-reduce over NVLink peer memory fused with the residual Add and RMSNorm that follow it in a
+ *      tensor-parallel decoder layer: replaces ncclAllReduce (all_reduce.cc:8-63) + Add + RMSNorm for messages of
+ *      <= 64 rows x 16 KiB.  out = T(T(sum_r in_r) + residual); out_norm = RMSNorm(out) * norm_w (optional).
+ *      peer_ws[world]: every rank's comm workspace (it_b200_allreduce_workspace_bytes(), zero-filled once) as mapped
+ *      in this process (cudaIpcOpenMemHandle); peer_ws[rank] is the local one.  Every rank must issue the same
+ *      sequence of calls.  Stream-ordered, CUDA-graph-capturable. ---- */
+int64_t it_b200_allreduce_workspace_bytes(void);
+int it_b200_allreduce_fused(int dtype, const void *in, const void *residual, const void *norm_w, void *out,
+                            void *out_norm, int tokens, int hidden, void *const *peer_ws, int world, int rank,
+                            void *stream);
+
 /* ======================================================================
  * (2) Graph / runtime handle API -- see infinitensor_b200/csrc/host/capi.cc.
  * Mirrors reference GraphHandlerObj (include/core/graph_handler.h:15-159),
@@ -196,6 +207,9 @@ int itb_runtime_init_comm(itb_runtime *rt, const char *name, int world_size, int
 int itb_runtime_init_comm_with_id(itb_runtime *rt, const void *nccl_unique_id, int id_bytes,
                                   int world_size, int rank);
 int itb_runtime_nccl_unique_id(void *out, int out_bytes);
+/* NVLink peer-memory comm for the fused all-reduce: export this rank's 64-byte cudaIpc handle, then import all ranks' */
+int itb_runtime_p2p_export(itb_runtime *rt, void *handle_out_64_bytes);
+int itb_runtime_p2p_import(itb_runtime *rt, const void *all_handles, int world_size, int rank);
 int64_t itb_runtime_cuda_graph_cache_size(itb_runtime *rt);
 int64_t itb_runtime_cuda_graph_capture_count(itb_runtime *rt);
 int itb_runtime_clear_cuda_graph_cache(itb_runtime *rt);

@@ -58,6 +58,8 @@ _sig = {
     "itb_runtime_init_comm": (c_int, [_h, c_char_p, c_int, c_int]),
     "itb_runtime_init_comm_with_id": (c_int, [_h, c_void_p, c_int, c_int, c_int]),
     "itb_runtime_nccl_unique_id": (c_int, [c_void_p, c_int]),
+    "itb_runtime_p2p_export": (c_int, [_h, c_void_p]),
+    "itb_runtime_p2p_import": (c_int, [_h, c_void_p, c_int, c_int]),
     "itb_runtime_cuda_graph_cache_size": (c_int64, [_h]),
     "itb_runtime_cuda_graph_capture_count": (c_int64, [_h]),
     "itb_runtime_clear_cuda_graph_cache": (c_int, [_h]),
@@ -158,6 +160,19 @@ class CudaRuntime:
         if n <= 0:
             raise RuntimeError(L.last_error())
         return buf.raw[:n]
+
+    def p2p_export(self) -> bytes:
+        """64-byte cudaIpc handle of this rank's NVLink comm workspace (for the fused one-shot all-reduce)."""
+        buf = ctypes.create_string_buffer(64)
+        _ck(lib.itb_runtime_p2p_export(self._h, buf))
+        return buf.raw
+
+    def p2p_import(self, handles, world_size: int, rank: int):
+        """Map every rank's comm workspace; `handles` = list of the world's p2p_export() results in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world_size
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        _ck(lib.itb_runtime_p2p_import(self._h, buf, world_size, rank))
 
     def clear_cuda_graph_cache(self):
         _ck(lib.itb_runtime_clear_cuda_graph_cache(self._h))

@@ -376,6 +376,29 @@ void runSiluMul(const Operator &silu, const Operator &mul, const RuntimeObj *) {
     auto u = mul->getInputs(0) == sout ? mul->getInputs(1) : mul->getInputs(0);
     CK(it_b200_silu_mul(DT(g), P(g), P(u), P(mul->getOutput()), (int64_t)g->size(), S()), mul);
 }
+// AllReduceSum -> Add(residual) [-> RMSNorm] through the one-shot NVLink kernel
+bool runAllReduceAddNorm(const OpVec &ops, const RuntimeObj *ctx) {
+    auto rt = RT(ctx);
+    if (!rt->hasPeerComm()) return false;
+    const auto &ar = ops[0], &add = ops[1];
+    auto in = ar->getInputs(0);
+    auto dt = in->getDType();
+    if (!dt.isFloat()) return false;
+    int hidden = in->getDims().back();
+    int64_t tokens = (int64_t)in->size() / hidden;
+    if (tokens > 64 || (int64_t)hidden * (int64_t)dt.getSize() > 16384 || (hidden * dt.getSize()) % 16 != 0) return false;
+    auto arOut = ar->getOutput();
+    auto res = add->getInputs(0) == arOut ? add->getInputs(1) : add->getInputs(0);
+    const void *nw = nullptr;
+    void *on = nullptr;
+    if (ops.size() > 2) {
+        nw = P(ops[2]->getInputs(1));
+        on = P(ops[2]->getOutput());
+    }
+    CK(it_b200_allreduce_fused(dt.getIndex(), P(in), P(res), nw, P(add->getOutput()), on, (int)tokens, hidden,
+                               rt->peerWorkspaces(), rt->p2pWorldSize(), rt->p2pRank(), S()), ar);
+    return true;
+}
 }  // namespace b200
 
 class MatmulB200 : public CudaKernelWithoutConfig {

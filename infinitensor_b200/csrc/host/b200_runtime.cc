@@ -1,6 +1,8 @@
 // b200_runtime.cc -- see b200_runtime.h.  Run loop, CUDA-graph capture cache, memory, workspace.
 #include "b200_runtime.h"
 
+#include "it_b200.h"
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -20,6 +22,9 @@ CudaRuntimeObj::~CudaRuntimeObj() {
     for (auto &e : cache) destroyEntry(e);
     cache.clear();
     comm.reset();
+    for (int p = 0; p < p2pWorld; ++p)
+        if (p != p2pRankId && p2pWs[p]) cudaIpcCloseMemHandle(p2pWs[p]);
+    if (p2pLocal) cudaFree(p2pLocal);
     if (workspace) cudaFree(workspace);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -80,6 +85,38 @@ void *CudaRuntimeObj::getWorkspace(size_t size) const {
     return workspace;
 }
 
+void CudaRuntimeObj::p2pExport(void *handle64) {
+    checkCudaError(cudaSetDevice(deviceId));
+    if (!p2pLocal) {
+        size_t bytes = (size_t)it_b200_allreduce_workspace_bytes();
+        checkCudaError(cudaMalloc(&p2pLocal, bytes));
+        checkCudaError(cudaMemset(p2pLocal, 0, bytes));
+        checkCudaError(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    checkCudaError(cudaIpcGetMemHandle(&h, p2pLocal));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle64, &h, 64);
+}
+void CudaRuntimeObj::p2pImport(const void *allHandles, int worldSize, int rank) {
+    IT_ASSERT(worldSize >= 1 && worldSize <= 8 && rank >= 0 && rank < worldSize, "p2p: bad world size / rank");
+    IT_ASSERT(p2pLocal != nullptr, "p2p: export the local handle first");
+    checkCudaError(cudaSetDevice(deviceId));
+    for (int p = 0; p < worldSize; ++p) {
+        if (p == rank) {
+            p2pWs[p] = p2pLocal;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char *)allHandles + (size_t)p * 64, 64);
+        void *ptr = nullptr;
+        checkCudaError(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        p2pWs[p] = ptr;
+    }
+    p2pWorld = worldSize;
+    p2pRankId = rank;
+}
+
 void CudaRuntimeObj::initComm(const string &name, int worldSize, int rank) {
     IT_ASSERT(worldSize > 0 && rank >= 0 && rank < worldSize, "bad world size / rank");
     checkCudaError(cudaSetDevice(deviceId));
@@ -135,6 +172,13 @@ void CudaRuntimeObj::runWithoutSyncImpl(const Graph &graph, bool validate) const
             break;
         }
         case ExecStep::SiluMul: b200::runSiluMul(st.ops[0], st.ops[1], this); break;
+        case ExecStep::AllReduceAddNorm:
+            if (!b200::runAllReduceAddNorm(st.ops, this)) {
+                // no NVLink peer comm (or shape outside its limits): the ordinary kernels, one by one
+                auto &reg = KernelRegistry::getInstance();
+                for (auto &m : st.ops) reg.getKernel(KernelAttrs{Device::CUDA, m->getOpType().underlying()})->compute(m, this);
+            }
+            break;
         }
         cudaError_t err = cudaPeekAtLastError();
         if (err != cudaSuccess) {

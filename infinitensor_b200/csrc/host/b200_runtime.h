@@ -58,6 +58,9 @@ class CudaRuntimeObj : public RuntimeObj {
     mutable void *workspace = nullptr;
     mutable size_t workspaceSize = 0;
     Ref<CommunicatorObj> comm;
+    void *p2pLocal = nullptr;
+    void *p2pWs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int p2pWorld = 0, p2pRankId = 0;
     mutable std::recursive_mutex executionMutex;
 
     struct TensorSig {
@@ -115,6 +118,13 @@ class CudaRuntimeObj : public RuntimeObj {
     size_t getWorkspaceSize() const { return workspaceSize; }
     cudaStream_t getStream() const { return stream; }
 
+    // NVLink peer-memory communicator for the fused one-shot all-reduce (kernels/allreduce.cu)
+    void p2pExport(void *handle64);                                      // allocates the local comm workspace
+    void p2pImport(const void *allHandles, int worldSize, int rank);     // maps every peer's workspace
+    bool hasPeerComm() const { return p2pWorld > 0; }
+    void *const *peerWorkspaces() const { return p2pWs; }
+    int p2pWorldSize() const { return p2pWorld; }
+    int p2pRank() const { return p2pRankId; }
     void initComm(const string &name, int worldSize, int rank);
     void initCommWithId(const void *id, int idBytes, int worldSize, int rank);
     CommunicatorObj &getCommunicator() const {
@@ -134,6 +144,8 @@ namespace b200 {
 void runMatmul(const Operator &op, const RuntimeObj *ctx, const Tensor &residual, const Tensor &outOverride);
 void runMatmulGroup(const OpVec &ops, const RuntimeObj *ctx);
 void runSiluMul(const Operator &silu, const Operator &mul, const RuntimeObj *ctx);
+// AllReduceSum -> Add(residual) [-> RMSNorm]: true if the fused NVLink kernel took it, false = run the ops one by one
+bool runAllReduceAddNorm(const OpVec &ops, const RuntimeObj *ctx);
 }  // namespace b200
 
 // Convenience base for kernels without tunable configs (reference cuda_kernel_wihtout_config.h:7-22)

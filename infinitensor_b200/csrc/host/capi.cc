@@ -116,6 +116,10 @@ int itb_runtime_nccl_unique_id(void *out, int n) {
         return 0;
     }
 }
+int itb_runtime_p2p_export(itb_runtime *rt, void *handle64) { ITB_TRY(rt->cuda()->p2pExport(handle64)) }
+int itb_runtime_p2p_import(itb_runtime *rt, const void *all, int world, int rank) {
+    ITB_TRY(rt->cuda()->p2pImport(all, world, rank))
+}
 int64_t itb_runtime_cuda_graph_cache_size(itb_runtime *rt) { return rt->rt ? (int64_t)rt->rt->getCudaGraphCacheSize() : 0; }
 int64_t itb_runtime_cuda_graph_capture_count(itb_runtime *rt) { return rt->rt ? (int64_t)rt->rt->getCudaGraphCaptureCount() : 0; }
 int itb_runtime_clear_cuda_graph_cache(itb_runtime *rt) { ITB_TRY(rt->cuda()->clearCudaGraphCache()) }
@@ -368,7 +372,7 @@ int itb_graph_step(itb_graph *g, int index, char *buf, int buf_len) {
     ITB_TRY({
         const auto &sc = g->g->getSchedule();
         IT_ASSERT(index >= 0 && index < (int)sc.size(), "bad step index");
-        static const char *kinds[] = {"Single", "Alias", "MatMulGroup", "MatMulAdd", "SiluMul"};
+        static const char *kinds[] = {"Single", "Alias", "MatMulGroup", "MatMulAdd", "SiluMul", "AllReduceAddNorm"};
         std::string s = kinds[(int)sc[index].kind];
         s += ":";
         for (size_t i = 0; i < sc[index].ops.size(); ++i) s += (i ? "+" : "") + std::string(sc[index].ops[i]->getOpType().toString());

@@ -342,7 +342,8 @@ struct ExecStep {
                       // gave them distinct storage
         MatMulGroup,  // 2..4 MatMuls sharing the activation operand (q/k/v, gate/up): one grouped launch
         MatMulAdd,    // MatMul -> Add(residual): residual added in the GEMM epilogue
-        SiluMul       // Silu -> Mul: one pass
+        SiluMul,      // Silu -> Mul: one pass
+        AllReduceAddNorm  // AllReduceSum -> Add(residual) [-> RMSNorm]: one NVLink peer-memory kernel (else 3 ops)
     } kind = Single;
     OpVec ops;
 };

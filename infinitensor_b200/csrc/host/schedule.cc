@@ -14,10 +14,10 @@ static bool fusionEnabled() {
     const char *e = std::getenv("ITB_NO_FUSION");
     return !(e && e[0] == '1');
 }
-// ITB_FUSION_MASK (debug / A-B): bit 0 alias, 1 MatMul groups, 2 MatMul+Add, 3 Silu*Mul; default all
+// ITB_FUSION_MASK (debug / A-B): bit 0 alias, 1 MatMul groups, 2 MatMul+Add, 3 Silu*Mul, 4 AllReduce+Add+Norm; default all
 static int fusionMask() {
     const char *e = std::getenv("ITB_FUSION_MASK");
-    return e && e[0] ? std::atoi(e) : 15;
+    return e && e[0] ? std::atoi(e) : 31;
 }
 
 static bool isKvCacheOperand(const Tensor &t) {
@@ -87,8 +87,19 @@ const vector<ExecStep> &GraphObj::getSchedule() {
         st.ops = {op};
         auto it = deferredInto.find(op.get());
         if (it != deferredInto.end()) {
-            st.kind = it->second->getOpType() == OpType::MatMul ? ExecStep::MatMulAdd : ExecStep::SiluMul;
+            auto pt = it->second->getOpType();
+            st.kind = pt == OpType::MatMul ? ExecStep::MatMulAdd : pt == OpType::Silu ? ExecStep::SiluMul : ExecStep::AllReduceAddNorm;
             st.ops = {it->second, op};
+            if (st.kind == ExecStep::AllReduceAddNorm) {
+                // pull in the RMSNorm that normalises the new residual stream (executed early, with the Add)
+                for (auto &t : op->getOutput()->getTargets())
+                    if (t->getOpType() == OpType::RMSNorm && t->getInputs(0) == op->getOutput() && !consumed.count(t.get()) &&
+                        !deferred.count(t.get()) && t->getInputs(1)->isWeight()) {
+                        st.ops.push_back(t);
+                        consumed.insert(t.get());
+                        break;
+                    }
+            }
             schedule.push_back(std::move(st));
             continue;
         }
@@ -133,6 +144,20 @@ const vector<ExecStep> &GraphObj::getSchedule() {
                         deferred.insert(op.get());
                         continue;
                     }
+                }
+            }
+        } else if (type == OpType::AllReduceSum && (mask & 16)) {
+            auto out = op->getOutput();
+            auto targets = out->getTargets();
+            if (out->getDType().isFloat() && targets.size() == 1 && !out->isOutput() && targets[0]->getOpType() == OpType::Add &&
+                !deferredInto.count(targets[0].get())) {
+                auto add = targets[0];
+                auto other = add->getInputs(0) == out ? add->getInputs(1) : add->getInputs(0);
+                if (other != out && other->getDims() == out->getDims() && other->getDType() == out->getDType() &&
+                    add->getOutput()->getDims() == out->getDims()) {
+                    deferredInto[add.get()] = op;
+                    deferred.insert(op.get());
+                    continue;
                 }
             }
         } else if (type == OpType::Silu && (mask & 8)) {
