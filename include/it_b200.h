@@ -191,6 +191,14 @@ int it_b200_allreduce_fused(int dtype, const void *in, const void *residual, con
                             void *out_norm, int tokens, int hidden, void *const *peer_ws, int world, int rank,
                             void *stream);
 
+/* ---- AttentionKVCache with the layer's two RoPE ops folded in: q_pre / k_pre are the PRE-RoPE projections
+ *      ([B, H*128] == [B,H,1,128]); RoPE (rotate-half, dim_head 128, position rope_pos[b]) is applied on load, the
+ *      rotated k is what gets appended -- bit-identical to RoPE -> AttentionKVCache (rope.cu:7-31 + attention_kvcache.cu). ---- */
+int it_b200_attention_kvcache_rope(int dtype, void *k_cache, void *v_cache, const void *q_pre, const void *k_pre,
+                                   const void *v, const void *position_id, int pos_dtype, const void *rope_pos,
+                                   int rope_pos_dtype, void *out, int B, int H, int S_max, int D, void *workspace,
+                                   int64_t workspace_bytes, void *stream);
+
 /* ======================================================================
  * (2) Graph / runtime handle API -- see infinitensor_b200/csrc/host/capi.cc.
  * Mirrors reference GraphHandlerObj (include/core/graph_handler.h:15-159),

@@ -60,6 +60,8 @@ _SIGS = {
     "it_b200_conv2d_workspace": (c_int64, [c_int] * 15),
     "it_b200_conv2d": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, c_int64, vp]),
     "it_b200_attention_kvcache_workspace": (c_int64, [c_int] * 4),
+    "it_b200_attention_kvcache_rope": (c_int, [c_int, vp, vp, vp, vp, vp, vp, c_int, vp, c_int, vp, c_int, c_int, c_int, c_int,
+                                               vp, c_int64, vp]),
     "it_b200_attention_kvcache": (c_int, [c_int, vp, vp, vp, vp, vp, vp, c_int, vp, c_int, c_int, c_int, c_int,
                                           vp, c_int64, vp]),
 }

@@ -376,6 +376,18 @@ void runSiluMul(const Operator &silu, const Operator &mul, const RuntimeObj *) {
     auto u = mul->getInputs(0) == sout ? mul->getInputs(1) : mul->getInputs(0);
     CK(it_b200_silu_mul(DT(g), P(g), P(u), P(mul->getOutput()), (int64_t)g->size(), S()), mul);
 }
+// RoPE(q), RoPE(k) folded into the decode attention kernel (the aliases between them are storage no-ops)
+void runAttentionRope(const Operator &ropeQ, const Operator &ropeK, const Operator &att, const RuntimeObj *ctx) {
+    auto kc = att->getInputs(0), vc = att->getInputs(1), v = att->getInputs(4), pos = att->getInputs(5);
+    auto qpre = ropeQ->getInputs(1), kpre = ropeK->getInputs(1), rpos = ropeQ->getInputs(0);
+    IT_ASSERT(ropeK->getInputs(0) == rpos, "RoPE(q) and RoPE(k) must share the position tensor");
+    auto &d = kc->getDims();
+    int64_t wsb = it_b200_attention_kvcache_workspace(d[0], d[1], d[2], d[3]);
+    void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
+    CK(it_b200_attention_kvcache_rope(DT(qpre), P(kc), P(vc), P(qpre), P(kpre), P(v), P(pos), DT(pos), P(rpos), DT(rpos),
+                                      P(att->getOutput()), d[0], d[1], d[2], d[3], ws, wsb, S()), att);
+}
+
 // AllReduceSum -> Add(residual) [-> RMSNorm] through the one-shot NVLink kernel
 bool runAllReduceAddNorm(const OpVec &ops, const RuntimeObj *ctx) {
     auto rt = RT(ctx);

@@ -172,6 +172,7 @@ void CudaRuntimeObj::runWithoutSyncImpl(const Graph &graph, bool validate) const
             break;
         }
         case ExecStep::SiluMul: b200::runSiluMul(st.ops[0], st.ops[1], this); break;
+        case ExecStep::AttentionRope: b200::runAttentionRope(st.ops[0], st.ops[1], st.ops[2], this); break;
         case ExecStep::AllReduceAddNorm:
             if (!b200::runAllReduceAddNorm(st.ops, this)) {
                 // no NVLink peer comm (or shape outside its limits): the ordinary kernels, one by one

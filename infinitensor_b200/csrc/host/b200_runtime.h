@@ -146,6 +146,7 @@ void runMatmulGroup(const OpVec &ops, const RuntimeObj *ctx);
 void runSiluMul(const Operator &silu, const Operator &mul, const RuntimeObj *ctx);
 // AllReduceSum -> Add(residual) [-> RMSNorm]: true if the fused NVLink kernel took it, false = run the ops one by one
 bool runAllReduceAddNorm(const OpVec &ops, const RuntimeObj *ctx);
+void runAttentionRope(const Operator &ropeQ, const Operator &ropeK, const Operator &att, const RuntimeObj *ctx);
 }  // namespace b200
 
 // Convenience base for kernels without tunable configs (reference cuda_kernel_wihtout_config.h:7-22)

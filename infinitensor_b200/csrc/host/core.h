@@ -343,6 +343,7 @@ struct ExecStep {
         MatMulGroup,  // 2..4 MatMuls sharing the activation operand (q/k/v, gate/up): one grouped launch
         MatMulAdd,    // MatMul -> Add(residual): residual added in the GEMM epilogue
         SiluMul,      // Silu -> Mul: one pass
+        AttentionRope,    // RoPE(q), RoPE(k) -> [aliases] -> AttentionKVCache: RoPE applied inside the attention kernel
         AllReduceAddNorm  // AllReduceSum -> Add(residual) [-> RMSNorm]: one NVLink peer-memory kernel (else 3 ops)
     } kind = Single;
     OpVec ops;

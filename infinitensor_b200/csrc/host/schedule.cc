@@ -14,10 +14,10 @@ static bool fusionEnabled() {
     const char *e = std::getenv("ITB_NO_FUSION");
     return !(e && e[0] == '1');
 }
-// ITB_FUSION_MASK (debug / A-B): bit 0 alias, 1 MatMul groups, 2 MatMul+Add, 3 Silu*Mul, 4 AllReduce+Add+Norm; default all
+// ITB_FUSION_MASK (debug / A-B): bit 0 alias, 1 MatMul groups, 2 MatMul+Add, 3 Silu*Mul, 4 AllReduce+Add+Norm, 5 RoPE->Attention; default all
 static int fusionMask() {
     const char *e = std::getenv("ITB_FUSION_MASK");
-    return e && e[0] ? std::atoi(e) : 31;
+    return e && e[0] ? std::atoi(e) : 63;
 }
 
 static bool isKvCacheOperand(const Tensor &t) {
@@ -77,7 +77,7 @@ const vector<ExecStep> &GraphObj::getSchedule() {
     std::unordered_map<OperatorObj *, int> pos;
     for (size_t i = 0; i < ops.size(); ++i) pos[ops[i].get()] = (int)i;
     std::unordered_set<OperatorObj *> consumed;               // executed as part of an earlier (horizontal) step
-    std::unordered_map<OperatorObj *, Operator> deferredInto;  // consumer -> producer executed with it
+    std::unordered_map<OperatorObj *, OpVec> deferredInto;  // consumer -> producer(s) executed with it
     std::unordered_set<OperatorObj *> deferred;
 
     for (size_t i = 0; i < ops.size(); ++i) {
@@ -87,9 +87,32 @@ const vector<ExecStep> &GraphObj::getSchedule() {
         st.ops = {op};
         auto it = deferredInto.find(op.get());
         if (it != deferredInto.end()) {
-            auto pt = it->second->getOpType();
+            const OpVec &prod = it->second;
+            auto pt = prod[0]->getOpType();
+            if (pt == OpType::RoPE) {
+                // both RoPE(q) and RoPE(k) must have been folded; a lone one simply runs here, just before its consumer
+                Operator rq, rk;
+                for (auto &r : prod) {
+                    Tensor t = r->getOutput();
+                    while (t->getTargets().size() == 1 && t->getTargets()[0] != op) t = t->getTargets()[0]->getOutput();
+                    if (t == op->getInputs(2)) rq = r;
+                    if (t == op->getInputs(3)) rk = r;
+                }
+                if (rq && rk && rq != rk) {
+                    st.kind = ExecStep::AttentionRope;
+                    st.ops = {rq, rk, op};
+                } else {
+                    for (auto &r : prod) {
+                        ExecStep single;
+                        single.ops = {r};
+                        schedule.push_back(std::move(single));
+                    }
+                }
+                schedule.push_back(std::move(st));
+                continue;
+            }
             st.kind = pt == OpType::MatMul ? ExecStep::MatMulAdd : pt == OpType::Silu ? ExecStep::SiluMul : ExecStep::AllReduceAddNorm;
-            st.ops = {it->second, op};
+            st.ops = {prod[0], op};
             if (st.kind == ExecStep::AllReduceAddNorm) {
                 // pull in the RMSNorm that normalises the new residual stream (executed early, with the Add)
                 for (auto &t : op->getOutput()->getTargets())
@@ -140,10 +163,27 @@ const vector<ExecStep> &GraphObj::getSchedule() {
                     auto other = add->getInputs(0) == out ? add->getInputs(1) : add->getInputs(0);
                     if (other != out && other->getDims() == out->getDims() && other->getDType() == out->getDType() &&
                         add->getOutput()->getDims() == out->getDims()) {
-                        deferredInto[add.get()] = op;
+                        deferredInto[add.get()] = {op};
                         deferred.insert(op.get());
                         continue;
                     }
+                }
+            }
+        } else if (type == OpType::RoPE && (mask & 32)) {
+            // RoPE -> (alias-only chain) -> AttentionKVCache q / k operand, S = 1, 128-wide heads: fold into the attention kernel
+            Tensor t = op->getOutput();
+            bool chain = !t->isOutput();
+            while (chain && t->getTargets().size() == 1 && (mask & 1) && aliasable(t->getTargets()[0])) t = t->getTargets()[0]->getOutput();
+            auto &xd = op->getInputs(1)->getDims();
+            if (chain && t->getTargets().size() == 1 && t->getTargets()[0]->getOpType() == OpType::AttentionKVCache &&
+                xd.size() == 3 && xd[1] == 1 && xd[2] % 128 == 0 && op->getInputs(1)->getDType().isFloat()) {
+                auto att = t->getTargets()[0];
+                auto &qd = att->getInputs(2)->getDims();
+                if ((att->getInputs(2) == t || att->getInputs(3) == t) && qd[2] == 1 && qd[3] == 128 && qd[0] == xd[0] &&
+                    qd[1] * 128 == xd[2]) {
+                    deferredInto[att.get()].push_back(op);
+                    deferred.insert(op.get());
+                    continue;
                 }
             }
         } else if (type == OpType::AllReduceSum && (mask & 16)) {
@@ -155,7 +195,7 @@ const vector<ExecStep> &GraphObj::getSchedule() {
                 auto other = add->getInputs(0) == out ? add->getInputs(1) : add->getInputs(0);
                 if (other != out && other->getDims() == out->getDims() && other->getDType() == out->getDType() &&
                     add->getOutput()->getDims() == out->getDims()) {
-                    deferredInto[add.get()] = op;
+                    deferredInto[add.get()] = {op};
                     deferred.insert(op.get());
                     continue;
                 }
@@ -169,7 +209,7 @@ const vector<ExecStep> &GraphObj::getSchedule() {
                 auto other = mul->getInputs(0) == out ? mul->getInputs(1) : mul->getInputs(0);
                 if (other != out && other->getDims() == out->getDims() && other->getDType() == out->getDType() &&
                     mul->getOutput()->getDims() == out->getDims()) {
-                    deferredInto[mul.get()] = op;
+                    deferredInto[mul.get()] = {op};
                     deferred.insert(op.get());
                     continue;
                 }

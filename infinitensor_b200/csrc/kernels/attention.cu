@@ -28,14 +28,43 @@ template <typename T> struct RowCfg {
 template <typename P> __device__ __forceinline__ int read_pos(const void *p) { return (int)((const P *)p)[0]; }
 
 // partial layout in workspace: [BH, nsplit] x { m, l, acc[128] }
-template <typename T, int WARPS, int U>
+// rotate-half RoPE of this lane's EPL dims of one 128-wide head row, arithmetic rounded to T exactly like rope_kernel
+// (norm.cu / reference rope.cu:21-29); the partner dims (+-64) live in lane ^ (LPR/2) of the same row group
+template <typename T, int EPL, int LPR>
+__device__ __forceinline__ Vec16<T> rope_row(const Vec16<T> &x, int col, float p) {
+    Vec16<T> partner, r;
+    {
+        uint4 mine = *reinterpret_cast<const uint4 *>(x.v), other;
+        other.x = __shfl_xor_sync(0xffffffffu, mine.x, LPR / 2);
+        other.y = __shfl_xor_sync(0xffffffffu, mine.y, LPR / 2);
+        other.z = __shfl_xor_sync(0xffffffffu, mine.z, LPR / 2);
+        other.w = __shfl_xor_sync(0xffffffffu, mine.w, LPR / 2);
+        *reinterpret_cast<uint4 *>(partner.v) = other;
+    }
+    const bool lo = col < kD / 2;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+        const int c = (col + j) & (kD / 2 - 1);
+        const float freq = p * powf(10000.f, -(float)(c * 2) / (float)kD);
+        const float cs = round_t<T>(cosf(freq)), sn = round_t<T>(sinf(freq));
+        const float a = round_t<T>(to_f(x.v[j]) * cs), b = round_t<T>(to_f(partner.v[j]) * sn);
+        r.v[j] = from_f<T>(lo ? a - b : a + b);
+    }
+    return r;
+}
+
+// ROPE = true: q and kin are the PRE-RoPE projections; RoPE (position rope_pos[b]) is applied on load, so the two
+// RoPE kernels of the layer disappear (the appended cache row is the rotated k, as in the unfused graph)
+template <typename T, int WARPS, int U, bool ROPE>
 __global__ void __launch_bounds__(WARPS * 32) attn_decode_kernel(T *__restrict__ kcache, T *__restrict__ vcache,
                                                                  const T *__restrict__ q,
                                                                  const T *__restrict__ kin,
                                                                  const T *__restrict__ vin,
                                                                  const void *__restrict__ position_id,
                                                                  int pos_dtype, T *__restrict__ out, int Smax,
-                                                                 int nsplit, float *__restrict__ partial) {
+                                                                 int nsplit, float *__restrict__ partial,
+                                                                 const void *__restrict__ rope_pos,
+                                                                 int rope_pos_dtype, int H) {
     pdl_trigger();
     pdl_wait();
     using C = RowCfg<T>;
@@ -64,15 +93,24 @@ __global__ void __launch_bounds__(WARPS * 32) attn_decode_kernel(T *__restrict__
     const T *kn = kin + (int64_t)bh * kD;
     const T *vn = vin + (int64_t)bh * kD;
 
+    Vec16<T> knew = ld16(kn + col);  // this lane's dims of the new k row
+    Vec16<T> qv = ld16(q + (int64_t)bh * kD + col);
+    if (ROPE) {
+        const int b = bh / H;
+        const float p = rope_pos_dtype == ITB_I64 ? (float)(int)((const int64_t *)rope_pos)[b]
+                                                  : (float)((const int32_t *)rope_pos)[b];
+        knew = rope_row<T, EPL, LPR>(knew, col, p);
+        qv = rope_row<T, EPL, LPR>(qv, col, p);
+    }
+
     // in-place append (one warp of the split that owns `pos`)
     if (pos >= s_begin && pos < s_end && warp == 0 && lane < LPR) {
-        st16(kc + (int64_t)pos * kD + col, ld16(kn + col));
+        st16(kc + (int64_t)pos * kD + col, knew);
         st16(vc + (int64_t)pos * kD + col, ld16(vn + col));
     }
 
     float qf[EPL];
     {
-        Vec16<T> qv = ld16(q + (int64_t)bh * kD + col);
 #pragma unroll
         for (int j = 0; j < EPL; ++j) qf[j] = to_f(qv.v[j]) * 0.08838834764831845f;  // 1/sqrt(128)
     }
@@ -94,6 +132,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_decode_kernel(T *__restrict__
             if (ok[u]) {
                 kv[u] = ld16_stream(kp + col);
                 vv[u] = ld16_stream(vp + col);
+                if (ROPE && s == pos) kv[u] = knew;
             }
         }
         float sc[U];
@@ -216,13 +255,14 @@ extern "C" int64_t it_b200_attention_kvcache_workspace(int B, int H, int S_max, 
     return ns == 1 ? 0 : (int64_t)B * H * ns * (kD + 2) * sizeof(float);
 }
 
-extern "C" int it_b200_attention_kvcache(int dtype, void *k_cache, void *v_cache, const void *q, const void *k,
-                                         const void *v, const void *position_id, int pos_dtype, void *out, int B,
-                                         int H, int S_max, int D, void *workspace, int64_t workspace_bytes,
-                                         void *stream) {
+static int attention_impl(int dtype, void *k_cache, void *v_cache, const void *q, const void *k, const void *v,
+                          const void *position_id, int pos_dtype, const void *rope_pos, int rope_pos_dtype, void *out,
+                          int B, int H, int S_max, int D, void *workspace, int64_t workspace_bytes, void *stream) {
     ITB_CHECK(D == kD, "AttentionKVCache: head dim %d != 128 (reference attention_kvcache.cu:154)", D);
     ITB_CHECK(pos_dtype == ITB_I32 || pos_dtype == ITB_U32 || pos_dtype == ITB_I64,
               "AttentionKVCache: position dtype %d must be int32/uint32/int64", pos_dtype);
+    ITB_CHECK(!rope_pos || rope_pos_dtype == ITB_I32 || rope_pos_dtype == ITB_U32 || rope_pos_dtype == ITB_I64,
+              "AttentionKVCache: rope position dtype %d must be int32/uint32/int64", rope_pos_dtype);
     ITB_CHECK(aligned16(k_cache) && aligned16(v_cache) && aligned16(q) && aligned16(k) && aligned16(v),
               "AttentionKVCache: tensors must be 16-byte aligned");
     int BH = B * H;
@@ -235,10 +275,14 @@ extern "C" int it_b200_attention_kvcache(int dtype, void *k_cache, void *v_cache
     dim3 grid(BH, ns);
     ITB_DISPATCH_FLOAT(dtype, "AttentionKVCache", {
         constexpr int WARPS = 8, U = 4;  // measured: U=2 at 64 regs (4 CTAs/SM) is 11 % slower end-to-end -- per-thread MLP wins
-        launch_k(attn_decode_kernel<T, WARPS, U>, dim3(grid), dim3(WARPS * 32), 0, st, (T *)k_cache, (T *)v_cache, (const T *)q,
-                                                                    (const T *)k, (const T *)v, position_id,
-                                                                    pos_dtype, (T *)out, S_max, ns,
-                                                                    (float *)workspace);
+        if (rope_pos)
+            launch_k(attn_decode_kernel<T, WARPS, U, true>, dim3(grid), dim3(WARPS * 32), 0, st, (T *)k_cache, (T *)v_cache,
+                     (const T *)q, (const T *)k, (const T *)v, position_id, pos_dtype, (T *)out, S_max, ns,
+                     (float *)workspace, rope_pos, rope_pos_dtype, H);
+        else
+            launch_k(attn_decode_kernel<T, WARPS, U, false>, dim3(grid), dim3(WARPS * 32), 0, st, (T *)k_cache, (T *)v_cache,
+                     (const T *)q, (const T *)k, (const T *)v, position_id, pos_dtype, (T *)out, S_max, ns,
+                     (float *)workspace, rope_pos, rope_pos_dtype, H);
         ITB_LAUNCH_CHECK("AttentionKVCache");
         if (ns > 1) {
             launch_k(attn_merge_kernel<T>, dim3(BH), dim3(kD), 0, st, (const float *)workspace, (T *)out, ns);
@@ -246,4 +290,21 @@ extern "C" int it_b200_attention_kvcache(int dtype, void *k_cache, void *v_cache
         }
     });
     return 0;
+}
+
+extern "C" int it_b200_attention_kvcache(int dtype, void *k_cache, void *v_cache, const void *q, const void *k,
+                                         const void *v, const void *position_id, int pos_dtype, void *out, int B,
+                                         int H, int S_max, int D, void *workspace, int64_t workspace_bytes,
+                                         void *stream) {
+    return attention_impl(dtype, k_cache, v_cache, q, k, v, position_id, pos_dtype, nullptr, 0, out, B, H, S_max, D,
+                          workspace, workspace_bytes, stream);
+}
+
+extern "C" int it_b200_attention_kvcache_rope(int dtype, void *k_cache, void *v_cache, const void *q_pre,
+                                              const void *k_pre, const void *v, const void *position_id, int pos_dtype,
+                                              const void *rope_pos, int rope_pos_dtype, void *out, int B, int H,
+                                              int S_max, int D, void *workspace, int64_t workspace_bytes, void *stream) {
+    ITB_CHECK(rope_pos != nullptr, "AttentionKVCache+RoPE: rope positions missing");
+    return attention_impl(dtype, k_cache, v_cache, q_pre, k_pre, v, position_id, pos_dtype, rope_pos, rope_pos_dtype, out,
+                          B, H, S_max, D, workspace, workspace_bytes, stream);
 }

@@ -168,15 +168,16 @@ def _decode_once(dtype, env, monkeypatch):
 
 @pytest.mark.parametrize("dtype", [F32, BF16])
 def test_fused_schedule_matches_unfused(dtype, monkeypatch):
-    """Alias elimination, MatMul+Add epilogue fusion and Silu*Mul fusion give EXACTLY the bits of the
+    """Alias elimination, MatMul+Add epilogue fusion, Silu*Mul fusion and RoPE-in-attention give EXACTLY the bits of the
     one-kernel-per-operator order (ITB_NO_FUSION=1).  Grouping q/k/v and gate/up into one launch may pick a different
     split-K partition (fp32 summation order), so that step is held to the GEMM tolerance instead."""
     from infinitensor_b200 import graphs as G
     _, base, base_k, cfg = _decode_once(dtype, {"ITB_NO_FUSION": "1"}, monkeypatch)
-    sched, got, got_k, _ = _decode_once(dtype, {"ITB_NO_FUSION": "0", "ITB_FUSION_MASK": "13"}, monkeypatch)
+    sched, got, got_k, _ = _decode_once(dtype, {"ITB_NO_FUSION": "0", "ITB_FUSION_MASK": "61"}, monkeypatch)
     assert any(s.startswith("MatMulAdd") for s in sched) and any(s.startswith("Alias") for s in sched)
+    assert any(s.startswith("AttentionRope") for s in sched) and any(s.startswith("SiluMul") for s in sched)
     assert np.array_equal(got, base) and np.array_equal(got_k, base_k)
-    sched, got, got_k, _ = _decode_once(dtype, {"ITB_NO_FUSION": "0", "ITB_FUSION_MASK": "15"}, monkeypatch)
+    sched, got, got_k, _ = _decode_once(dtype, {"ITB_NO_FUSION": "0", "ITB_FUSION_MASK": "63"}, monkeypatch)
     if dtype == BF16:
         assert any(s.startswith("MatMulGroup") for s in sched)
     a, b = G.from_storage(got, dtype).astype(np.float64), G.from_storage(base, dtype).astype(np.float64)

@@ -244,10 +244,16 @@ def test_fused_schedule_and_alias_plan(B, monkeypatch):
     G.build_llama_decode(h, cfg)
     sc = h.schedule()
     kinds = collections.Counter(s.split(":")[0] for s in sc)
-    assert kinds == {"Alias": 16, "Single": 13, "MatMulGroup": 4, "MatMulAdd": 4, "SiluMul": 2}
+    assert kinds == {"Alias": 16, "Single": 7, "MatMulGroup": 4, "MatMulAdd": 4, "SiluMul": 2, "AttentionRope": 2}
+    assert "AttentionRope:RoPE+RoPE+AttentionKVCache" in sc
     assert "MatMulGroup:MatMul+MatMul+MatMul" in sc and "MatMulGroup:MatMul+MatMul" in sc
     launches = sum(1 for s in sc if not s.startswith("Alias"))
-    assert launches == 2 * 10 + 3  # 10 kernels per layer + gather, final norm, logits
+    assert launches == 2 * 8 + 3  # 8 kernels per layer + gather, final norm, logits
+    # tensor-parallel graph: the all-reduce takes the residual Add and the following RMSNorm with it
+    h_tp = B.GraphHandler(rt)
+    G.build_llama_decode(h_tp, cfg, 2, 1)
+    sc_tp = [s for s in h_tp.schedule() if not s.startswith("Alias")]
+    assert sc_tp.count("AllReduceAddNorm:AllReduceSum+Add+RMSNorm") == 4 and sc_tp.count("Single:RMSNorm") == 1
     h.data_malloc()
     fused_bytes = h.arena_bytes()[1]
     monkeypatch.setenv("ITB_NO_FUSION", "1")
