@@ -46,6 +46,9 @@ extern "C" {
 
 const char *it_b200_last_error(void);
 int it_b200_version(void);
+/* tuning hook for tools/gemm_sweep.py: force the decode-GEMM tile width (nb = 1: 64 columns, 2: 128) and split-K factor;
+ * 0 = automatic (the default).  Not part of the reference-facing surface. */
+void it_b200_tune_skinny(int nb, int splitk);
 
 /* ---- unary family: replaces unary.cu:31-143 + ActivationCudnn (unary.cc:70-122) ---- */
 enum { ITB_RELU = 0, ITB_SIGMOID, ITB_TANH, ITB_GELU, ITB_SILU, ITB_ERF, ITB_NEG, ITB_ABS,

@@ -31,6 +31,7 @@ vp = c_void_p
 _SIGS = {
     "it_b200_last_error": (c_char_p, []),
     "it_b200_version": (c_int, []),
+    "it_b200_tune_skinny": (None, [c_int, c_int]),
     "it_b200_launch_count": (c_longlong, []),
     "it_b200_unary": (c_int, [c_int, c_int, vp, vp, c_int64, vp]),
     "it_b200_binary": (c_int, [c_int, c_int, vp, vp, vp, c_int, i64p, i64p, i64p, vp]),

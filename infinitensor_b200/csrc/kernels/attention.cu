@@ -13,7 +13,12 @@
 // holds RPW = 32/LPR rows per load instruction (LPR = lanes per 128-wide row: 16 for 2-byte types,
 // 32 for fp32), U independent K and V loads are issued before any arithmetic so each lane keeps
 // 2*U 16-byte requests in flight.
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+
 #include "common.cuh"
+#include "gemm.cuh"  // mbarrier / bulk-copy PTX helpers
 
 namespace itb {
 
@@ -28,29 +33,32 @@ template <typename T> struct RowCfg {
 template <typename P> __device__ __forceinline__ int read_pos(const void *p) { return (int)((const P *)p)[0]; }
 
 // partial layout in workspace: [BH, nsplit] x { m, l, acc[128] }
-// rotate-half RoPE of this lane's EPL dims of one 128-wide head row, arithmetic rounded to T exactly like rope_kernel
-// (norm.cu / reference rope.cu:21-29); the partner dims (+-64) live in lane ^ (LPR/2) of the same row group
+// rotate-half RoPE of this lane's EPL dims of the q and k rows of one 128-wide head, arithmetic rounded to T exactly
+// like rope_kernel (norm.cu / reference rope.cu:21-29); the partner dims (+-64) live in lane ^ (LPR/2).  cs / sn are
+// the CTA's 64-entry cos / sin tables (already rounded to T) in shared memory.
 template <typename T, int EPL, int LPR>
-__device__ __forceinline__ Vec16<T> rope_row(const Vec16<T> &x, int col, float p) {
-    Vec16<T> partner, r;
-    {
+__device__ __forceinline__ void rope_rows(Vec16<T> &q, Vec16<T> &k, int col, const float *cs_t, const float *sn_t) {
+    auto exchange = [](const Vec16<T> &x) {
+        Vec16<T> o;
         uint4 mine = *reinterpret_cast<const uint4 *>(x.v), other;
         other.x = __shfl_xor_sync(0xffffffffu, mine.x, LPR / 2);
         other.y = __shfl_xor_sync(0xffffffffu, mine.y, LPR / 2);
         other.z = __shfl_xor_sync(0xffffffffu, mine.z, LPR / 2);
         other.w = __shfl_xor_sync(0xffffffffu, mine.w, LPR / 2);
-        *reinterpret_cast<uint4 *>(partner.v) = other;
-    }
+        *reinterpret_cast<uint4 *>(o.v) = other;
+        return o;
+    };
+    const Vec16<T> qp = exchange(q), kp = exchange(k);
     const bool lo = col < kD / 2;
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
         const int c = (col + j) & (kD / 2 - 1);
-        const float freq = p * powf(10000.f, -(float)(c * 2) / (float)kD);
-        const float cs = round_t<T>(cosf(freq)), sn = round_t<T>(sinf(freq));
-        const float a = round_t<T>(to_f(x.v[j]) * cs), b = round_t<T>(to_f(partner.v[j]) * sn);
-        r.v[j] = from_f<T>(lo ? a - b : a + b);
+        const float cs = cs_t[c], sn = sn_t[c];
+        const float qa = round_t<T>(to_f(q.v[j]) * cs), qb = round_t<T>(to_f(qp.v[j]) * sn);
+        const float ka = round_t<T>(to_f(k.v[j]) * cs), kb = round_t<T>(to_f(kp.v[j]) * sn);
+        q.v[j] = from_f<T>(lo ? qa - qb : qa + qb);
+        k.v[j] = from_f<T>(lo ? ka - kb : ka + kb);
     }
-    return r;
 }
 
 // ROPE = true: q and kin are the PRE-RoPE projections; RoPE (position rope_pos[b]) is applied on load, so the two
@@ -96,11 +104,19 @@ __global__ void __launch_bounds__(WARPS * 32) attn_decode_kernel(T *__restrict__
     Vec16<T> knew = ld16(kn + col);  // this lane's dims of the new k row
     Vec16<T> qv = ld16(q + (int64_t)bh * kD + col);
     if (ROPE) {
-        const int b = bh / H;
-        const float p = rope_pos_dtype == ITB_I64 ? (float)(int)((const int64_t *)rope_pos)[b]
-                                                  : (float)((const int32_t *)rope_pos)[b];
-        knew = rope_row<T, EPL, LPR>(knew, col, p);
-        qv = rope_row<T, EPL, LPR>(qv, col, p);
+        // 64 threads evaluate one (cos, sin) each -- the serial chain is one powf + sincos, not 8 per lane -- then every
+        // thread rotates its own copy of the q / k dims from the shared tables
+        __shared__ float s_cs[kD / 2], s_sn[kD / 2];
+        if (threadIdx.x < kD / 2) {
+            const int b = bh / H;
+            const float p = rope_pos_dtype == ITB_I64 ? (float)(int)((const int64_t *)rope_pos)[b]
+                                                      : (float)((const int32_t *)rope_pos)[b];
+            const float freq = p * powf(10000.f, -(float)(threadIdx.x * 2) / (float)kD);
+            s_cs[threadIdx.x] = round_t<T>(cosf(freq));
+            s_sn[threadIdx.x] = round_t<T>(sinf(freq));
+        }
+        __syncthreads();
+        rope_rows<T, EPL, LPR>(qv, knew, col, s_cs, s_sn);
     }
 
     // in-place append (one warp of the split that owns `pos`)
@@ -119,20 +135,20 @@ __global__ void __launch_bounds__(WARPS * 32) attn_decode_kernel(T *__restrict__
 #pragma unroll
     for (int j = 0; j < EPL; ++j) acc[j] = 0.f;
 
+    // the cache rows [s_begin, min(s_end, pos)) stream from HBM; the appended row `pos` is handled after the loop from
+    // registers (keeps every hot-loop load a plain independent global load -- a post-load select costs the MLP).
+    const int s_stop = min(s_end, pos);
     // warp w takes row groups w, w+WARPS, ... ; each group = RPW*U rows
-    for (int s0 = s_begin + warp * RPW * U; s0 < s_end; s0 += WARPS * RPW * U) {
+    for (int s0 = s_begin + warp * RPW * U; s0 < s_stop; s0 += WARPS * RPW * U) {
         Vec16<T> kv[U], vv[U];
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             int s = s0 + u * RPW + sub;
-            ok[u] = s < s_end;
-            const T *kp = (s == pos) ? kn : kc + (int64_t)s * kD;  // the appended row comes from the k input
-            const T *vp = (s == pos) ? vn : vc + (int64_t)s * kD;
+            ok[u] = s < s_stop;
             if (ok[u]) {
-                kv[u] = ld16_stream(kp + col);
-                vv[u] = ld16_stream(vp + col);
-                if (ROPE && s == pos) kv[u] = knew;
+                kv[u] = ld16_stream(kc + (int64_t)s * kD + col);
+                vv[u] = ld16_stream(vc + (int64_t)s * kD + col);
             }
         }
         float sc[U];
@@ -164,6 +180,24 @@ __global__ void __launch_bounds__(WARPS * 32) attn_decode_kernel(T *__restrict__
                     for (int j = 0; j < EPL; ++j) acc[j] = fmaf(p, to_f(vv[u].v[j]), acc[j]);
                 }
             }
+            m = mx;
+        }
+    }
+
+    // the appended row (k / v of this step), from registers: warp 0, sub-row 0 of the split that owns `pos`
+    if (warp == 0 && pos >= s_begin && pos < s_end) {
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) d += qf[j] * to_f(knew.v[j]);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (sub == 0) {
+            const Vec16<T> vnew = ld16(vn + col);
+            const float mx = fmaxf(m, d);
+            const float corr = expf(m - mx), pnew = expf(d - mx);
+            l = l * corr + pnew;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) acc[j] = fmaf(pnew, to_f(vnew.v[j]), acc[j] * corr);
             m = mx;
         }
     }
@@ -218,6 +252,343 @@ __global__ void __launch_bounds__(WARPS * 32) attn_decode_kernel(T *__restrict__
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// attn_stream_kernel: the production decode kernel.  Same arithmetic per cache row as attn_decode_kernel, but
+//   * the (head, 64-row chunk) work units of the whole batch are FLATTENED and dealt out in equal contiguous ranges to
+//     a persistent grid of `ctas_per_sm x 148` CTAs -- B*H = 512 heads over 296 CTA slots no longer costs a 1.73-wave
+//     tail (the split-per-head grid ran at 86 % occupancy of its last wave);
+//   * every chunk of K rows and of V rows is ONE contiguous 16 KiB range of the cache ([B,H,S,128] layout), so a
+//     producer warp streams it HBM -> shared memory with cp.async.bulk (TMA 1-D) through a full/empty mbarrier ring;
+//     bytes in flight are set by the ring depth (3 x 32 KiB per CTA), not by registers per thread;
+//   * a head whose units straddle two or three CTAs is finished by the LAST of them to arrive (self-cleaning ticket per
+//     head), which merges the (m, l, acc) partials in CTA order -- deterministic, no second kernel.
+// The in-place append and the appended row's contribution are done by the CTA that owns the head's last chunk, from
+// registers; chunk loads stop at row pos-1, so the append never races the bulk reads.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar,
+                                             uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+constexpr int AS_MAX_STAGES = 6;
+
+template <typename T, int EPL, int LPR>
+__device__ __forceinline__ void rope_one(Vec16<T> &x, int col, const float *cs_t, const float *sn_t) {
+    Vec16<T> xp;
+    {
+        uint4 mine = *reinterpret_cast<const uint4 *>(x.v), other;
+        other.x = __shfl_xor_sync(0xffffffffu, mine.x, LPR / 2);
+        other.y = __shfl_xor_sync(0xffffffffu, mine.y, LPR / 2);
+        other.z = __shfl_xor_sync(0xffffffffu, mine.z, LPR / 2);
+        other.w = __shfl_xor_sync(0xffffffffu, mine.w, LPR / 2);
+        *reinterpret_cast<uint4 *>(xp.v) = other;
+    }
+    const bool lo = col < kD / 2;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+        const int c = (col + j) & (kD / 2 - 1);
+        const float a = round_t<T>(to_f(x.v[j]) * cs_t[c]), b = round_t<T>(to_f(xp.v[j]) * sn_t[c]);
+        x.v[j] = from_f<T>(lo ? a - b : a + b);
+    }
+}
+
+template <typename T, int WARPS, int U, bool ROPE>
+__global__ void __launch_bounds__((WARPS + 1) * 32, 2)
+    attn_stream_kernel(T *__restrict__ kcache, T *__restrict__ vcache, const T *__restrict__ q,
+                       const T *__restrict__ kin, const T *__restrict__ vin, const void *__restrict__ position_id,
+                       int pos_dtype, T *__restrict__ out, int Smax, int BH, float *__restrict__ partial,
+                       int slots_per_head, int *__restrict__ tickets, const void *__restrict__ rope_pos,
+                       int rope_pos_dtype, int H, int stages) {
+    using C = RowCfg<T>;
+    constexpr int EPL = C::EPL, LPR = C::LPR, RPW = C::RPW;
+    constexpr int CH = WARPS * RPW * U;                       // cache rows per chunk
+    constexpr int CHUNK_BYTES = CH * kD * (int)sizeof(T);     // 16 KiB for every dtype
+    constexpr int CONSUMERS = WARPS * 32;
+    extern __shared__ __align__(128) unsigned char ring[];    // stages x { K chunk | V chunk }
+    __shared__ __align__(8) uint64_t full[AS_MAX_STAGES], empty[AS_MAX_STAGES];
+    __shared__ float s_m[WARPS], s_l[WARPS];
+    __shared__ float s_acc[WARPS][kD];
+    __shared__ float s_cs[kD / 2], s_sn[kD / 2];
+    __shared__ int s_last;
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], WARPS);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    pdl_wait();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int pos = pos_dtype == ITB_I64 ? read_pos<int64_t>(position_id) : read_pos<int32_t>(position_id);
+    if (pos < 0) pos = 0;
+    if (pos >= Smax) pos = Smax - 1;
+    const int nch = pos / CH + 1;  // chunks per head; the last one holds rows [.., pos) of the cache + the appended row
+    int nunits, bh, c;  // this CTA's contiguous range of (head, chunk) units: [u0, u0 + nunits), starting at (bh, c)
+    {
+        // G = CTAs that take part: never more than there are units, so every one owns >= 1 unit and the CTAs sharing a
+        // head are consecutive
+        const int64_t total = (int64_t)BH * nch, G = min((int64_t)gridDim.x, total);
+        if (blockIdx.x >= G) return;
+        const int64_t u0 = blockIdx.x * total / G, u1 = (blockIdx.x + 1) * total / G;
+        nunits = (int)(u1 - u0);
+        bh = (int)(u0 / nch);
+        c = (int)(u0 - (int64_t)bh * nch);
+    }
+
+    if (warp == WARPS) {
+        // ---------------- producer: one elected lane streams chunks into the ring ----------------
+        if (lane == 0) {
+            const uint64_t policy = l2_policy_evict_first();
+            int st = 0, ph = 0;
+            for (int it = 0; it < nunits; ++it) {
+                mbar_wait(&empty[st], ph ^ 1);
+                const int rows = min(CH, pos - c * CH);
+                if (rows > 0) {
+                    const uint32_t bytes = (uint32_t)rows * kD * (uint32_t)sizeof(T);
+                    const int64_t off = ((int64_t)bh * Smax + (int64_t)c * CH) * kD;
+                    mbar_expect_tx(&full[st], 2 * bytes);
+                    bulk_load_1d(ring + (size_t)st * 2 * CHUNK_BYTES, kcache + off, bytes, &full[st], policy);
+                    bulk_load_1d(ring + (size_t)st * 2 * CHUNK_BYTES + CHUNK_BYTES, vcache + off, bytes, &full[st], policy);
+                } else {
+                    mbar_arrive(&full[st]);
+                }
+                if (++c == nch) { c = 0; ++bh; }
+                if (++st == stages) { st = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int sub = lane / LPR;
+    const int col = (lane % LPR) * EPL;
+    float qf[EPL], m = -INFINITY, l = 0.f, acc[EPL];
+    bool seg_from_start = false;
+    int st = 0, ph = 0;
+    for (int it = 0; it < nunits; ++it) {
+        if (it == 0 || c == 0) {
+            // new head segment: reset the running softmax, fetch (and rotate) q
+            seg_from_start = c == 0;
+            m = -INFINITY;
+            l = 0.f;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) acc[j] = 0.f;
+            Vec16<T> qv = ld16(q + (int64_t)bh * kD + col);
+            if (ROPE) {
+                if (threadIdx.x < kD / 2) {
+                    const int b = bh / H;
+                    const float p = rope_pos_dtype == ITB_I64 ? (float)(int)((const int64_t *)rope_pos)[b]
+                                                              : (float)((const int32_t *)rope_pos)[b];
+                    const float freq = p * powf(10000.f, -(float)(threadIdx.x * 2) / (float)kD);
+                    s_cs[threadIdx.x] = round_t<T>(cosf(freq));
+                    s_sn[threadIdx.x] = round_t<T>(sinf(freq));
+                }
+                named_bar_sync(1, CONSUMERS);
+                rope_one<T, EPL, LPR>(qv, col, s_cs, s_sn);
+            }
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) qf[j] = to_f(qv.v[j]) * 0.08838834764831845f;  // 1/sqrt(128)
+        }
+        const int nvalid = pos - c * CH;  // cache rows of this chunk that exist (<= 0: only the appended row)
+        const unsigned char *kb = ring + (size_t)st * 2 * CHUNK_BYTES, *vb = kb + CHUNK_BYTES;
+        mbar_wait(&full[st], ph);
+#ifndef ATTN_DBG_NOCOMPUTE  // (debug builds only: measures the bare HBM -> smem ring)
+        const T *ks = reinterpret_cast<const T *>(kb) + (warp * U * RPW + sub) * kD + col;
+        const T *vs = reinterpret_cast<const T *>(vb) + (warp * U * RPW + sub) * kD + col;
+        if (nvalid >= CH) {
+            // full chunk (every chunk but a head's last): branch-free, so the U rows' load / dot / shuffle chains interleave
+            float sc[U];
+#pragma unroll
+            for (int uu = 0; uu < U; ++uu) {
+                const Vec16<T> kv = ld16(ks + uu * RPW * kD);
+                float d = 0.f;
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) d += qf[j] * to_f(kv.v[j]);
+                sc[uu] = d;
+            }
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) {
+#pragma unroll
+                for (int uu = 0; uu < U; ++uu) sc[uu] += __shfl_xor_sync(0xffffffffu, sc[uu], o);
+            }
+            float mx = m;
+#pragma unroll
+            for (int uu = 0; uu < U; ++uu) mx = fmaxf(mx, sc[uu]);
+            const float corr = expf(m - mx);  // m = -inf -> 0
+            l *= corr;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) acc[j] *= corr;
+#pragma unroll
+            for (int uu = 0; uu < U; ++uu) {
+                const Vec16<T> vv = ld16(vs + uu * RPW * kD);
+                const float p = expf(sc[uu] - mx);
+                l += p;
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) acc[j] = fmaf(p, to_f(vv.v[j]), acc[j]);
+            }
+            m = mx;
+        } else {
+            float sc[U];
+            bool ok[U];
+#pragma unroll
+            for (int uu = 0; uu < U; ++uu) {
+                ok[uu] = (warp * U + uu) * RPW + sub < nvalid;
+                float d = 0.f;
+                if (ok[uu]) {
+                    const Vec16<T> kv = ld16(ks + uu * RPW * kD);
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) d += qf[j] * to_f(kv.v[j]);
+                }
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                sc[uu] = ok[uu] ? d : -INFINITY;
+            }
+            float mx = m;
+#pragma unroll
+            for (int uu = 0; uu < U; ++uu) mx = fmaxf(mx, sc[uu]);
+            if (mx > -INFINITY) {
+                const float corr = expf(m - mx);  // m = -inf -> 0
+                l *= corr;
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) acc[j] *= corr;
+#pragma unroll
+                for (int uu = 0; uu < U; ++uu) {
+                    if (ok[uu]) {
+                        const Vec16<T> vv = ld16(vs + uu * RPW * kD);
+                        const float p = expf(sc[uu] - mx);
+                        l += p;
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) acc[j] = fmaf(p, to_f(vv.v[j]), acc[j]);
+                    }
+                }
+                m = mx;
+            }
+        }
+#endif
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the stage
+        if (++st == stages) { st = 0; ph ^= 1; }
+
+        const bool last_chunk = c == nch - 1;
+        if (last_chunk && warp == 0) {
+            // the row appended this step: rotate k if asked, store k / v in place, add its contribution from registers
+            Vec16<T> knew = ld16(kin + (int64_t)bh * kD + col);
+            if (ROPE) rope_one<T, EPL, LPR>(knew, col, s_cs, s_sn);
+            float d = 0.f;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) d += qf[j] * to_f(knew.v[j]);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            if (sub == 0) {
+                const Vec16<T> vnew = ld16(vin + (int64_t)bh * kD + col);
+                st16(kcache + ((int64_t)bh * Smax + pos) * kD + col, knew);
+                st16(vcache + ((int64_t)bh * Smax + pos) * kD + col, vnew);
+                const float mx2 = fmaxf(m, d);
+                const float corr = expf(m - mx2), pnew = expf(d - mx2);
+                l = l * corr + pnew;
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) acc[j] = fmaf(pnew, to_f(vnew.v[j]), acc[j] * corr);
+                m = mx2;
+            }
+        }
+
+        if (last_chunk || it == nunits - 1) {
+            // ---- segment end: fold sub-rows, warps, and (when the head is shared between CTAs) the other CTAs' partials
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+                const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+                const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
+                const float mm = fmaxf(m, m2);
+                const float c1 = mm > -INFINITY ? expf(m - mm) : 0.f, c2 = mm > -INFINITY ? expf(m2 - mm) : 0.f;
+                l = l * c1 + l2 * c2;
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) {
+                    const float a2 = __shfl_xor_sync(0xffffffffu, acc[j], o);
+                    acc[j] = acc[j] * c1 + a2 * c2;
+                }
+                m = mm;
+            }
+            if (sub == 0) {
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) s_acc[warp][col + j] = acc[j];
+                if (lane == 0) {
+                    s_m[warp] = m;
+                    s_l[warp] = l;
+                }
+            }
+            named_bar_sync(1, CONSUMERS);
+            const bool whole = seg_from_start && last_chunk;
+            // which CTAs share this head:  cta(u) = floor(((u + 1) G - 1) / total)
+            const int64_t hu0 = (int64_t)bh * nch, total = (int64_t)BH * nch, G = min((int64_t)gridDim.x, total);
+            const int first_cta = (int)(((hu0 + 1) * G - 1) / total);
+            const int last_cta = (int)(((hu0 + nch) * G - 1) / total);
+            const int nseg = last_cta - first_cta + 1;
+            float *slots = partial + (int64_t)bh * slots_per_head * (kD + 2);
+            if (threadIdx.x < kD) {
+                const int d = threadIdx.x;
+                float mw = -INFINITY;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) mw = fmaxf(mw, s_m[w]);
+                float L = 0.f, A = 0.f;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) {
+                    const float cw = s_m[w] > -INFINITY ? expf(s_m[w] - mw) : 0.f;
+                    L += s_l[w] * cw;
+                    A += s_acc[w][d] * cw;
+                }
+                if (whole) {
+                    out[(int64_t)bh * kD + d] = from_f<T>(A / L);
+                } else {
+                    float *pp = slots + (int64_t)((int)blockIdx.x - first_cta) * (kD + 2);
+                    __stcg(pp + 2 + d, A);
+                    if (d == 0) {
+                        __stcg(pp, mw);
+                        __stcg(pp + 1, L);
+                    }
+                    __threadfence();
+                }
+            }
+            if (!whole) {
+                named_bar_sync(1, CONSUMERS);
+                if (threadIdx.x == 0) {
+                    const int old = atomicAdd(tickets + bh, 1);
+                    s_last = old == nseg - 1;
+                    if (s_last) tickets[bh] = 0;  // self-cleaning: every other sharer has already arrived
+                    __threadfence();
+                }
+                named_bar_sync(1, CONSUMERS);
+                if (s_last && threadIdx.x < kD) {
+                    const int d = threadIdx.x;
+                    float mw = -INFINITY;
+                    for (int s = 0; s < nseg; ++s) mw = fmaxf(mw, __ldcg(slots + (int64_t)s * (kD + 2)));
+                    float L = 0.f, A = 0.f;
+                    for (int s = 0; s < nseg; ++s) {
+                        const float *pp = slots + (int64_t)s * (kD + 2);
+                        const float ms = __ldcg(pp);
+                        const float cw = ms > -INFINITY ? expf(ms - mw) : 0.f;
+                        L += __ldcg(pp + 1) * cw;
+                        A += __ldcg(pp + 2 + d) * cw;
+                    }
+                    out[(int64_t)bh * kD + d] = from_f<T>(A / L);
+                }
+            }
+            named_bar_sync(1, CONSUMERS);  // s_acc / s_m / s_last are reused by the next segment
+        }
+        if (++c == nch) { c = 0; ++bh; }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kD) attn_merge_kernel(const float *__restrict__ partial, T *__restrict__ out,
                                                         int nsplit) {
@@ -249,10 +620,55 @@ static int choose_nsplit(int BH, int Smax) {
 
 using namespace itb;
 
+static int env_int(const char *name, int dflt) {
+    const char *e = std::getenv(name);
+    return e && *e ? std::atoi(e) : dflt;
+}
+// ITB_ATTN_IMPL=split selects the one-CTA-per-(head, split) kernel; default is the streaming kernel
+static bool attn_use_split() {
+    static const bool v = [] {
+        const char *e = std::getenv("ITB_ATTN_IMPL");
+        return e && std::string(e) == "split";
+    }();
+    return v;
+}
+static int stream_slots_per_head(int S_max) { return S_max / 32 + 1; }  // >= chunks per head for every dtype
+
 extern "C" int64_t it_b200_attention_kvcache_workspace(int B, int H, int S_max, int D) {
     (void)D;
     int ns = choose_nsplit(B * H, S_max);
-    return ns == 1 ? 0 : (int64_t)B * H * ns * (kD + 2) * sizeof(float);
+    int64_t split = ns == 1 ? 0 : (int64_t)B * H * ns * (kD + 2) * sizeof(float);
+    int64_t stream = (int64_t)B * H * stream_slots_per_head(S_max) * (kD + 2) * sizeof(float);
+    return split > stream ? split : stream;
+}
+
+template <typename T, bool ROPE, int WARPS, int U>
+static int launch_attn_stream_cfg(T *kc, T *vc, const T *q, const T *k, const T *v, const void *position_id, int pos_dtype,
+                              const void *rope_pos, int rope_pos_dtype, T *out, int BH, int H, int S_max,
+                              float *workspace, cudaStream_t st) {
+    constexpr int CH = WARPS * RowCfg<T>::RPW * U;
+    static const int stages = std::max(2, std::min(AS_MAX_STAGES, env_int("ITB_ATTN_STAGES", 2)));
+    static const int per_sm = std::max(1, std::min(2, env_int("ITB_ATTN_CTAS_PER_SM", 2)));
+    const size_t smem = (size_t)stages * 2 * CH * kD * sizeof(T);
+    auto kern = attn_stream_kernel<T, WARPS, U, ROPE>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+        configured = true;
+    }
+    int *tickets = stream_tickets(st, BH);
+    if (!tickets) return 1;
+    const int64_t max_units = (int64_t)BH * (S_max / CH + 1);
+    const int grid = (int)std::min<int64_t>(max_units, (int64_t)per_sm * kNumSMs);
+    cudaError_t e = launch_k(kern, dim3(grid), dim3((WARPS + 1) * 32), smem, st, kc, vc, q, k, v, position_id, pos_dtype,
+                             out, S_max, BH, workspace, stream_slots_per_head(S_max), tickets, rope_pos, rope_pos_dtype,
+                             H, stages);
+    return e == cudaSuccess ? 0 : 1;
+}
+// consumer warps x rows per lane and chunk: 8 x 4 (default, measured best) or 16 x 2 (ITB_ATTN_WARPS=16)
+template <typename T, bool ROPE, typename... A> static int launch_attn_stream(A... a) {
+    static const int warps = env_int("ITB_ATTN_WARPS", 8);
+    return warps == 8 ? launch_attn_stream_cfg<T, ROPE, 8, 4>(a...) : launch_attn_stream_cfg<T, ROPE, 16, 2>(a...);
 }
 
 static int attention_impl(int dtype, void *k_cache, void *v_cache, const void *q, const void *k, const void *v,
@@ -272,6 +688,22 @@ static int attention_impl(int dtype, void *k_cache, void *v_cache, const void *q
     ITB_CHECK(ns == 1 || (workspace && workspace_bytes >= need), "AttentionKVCache: workspace %lld < %lld bytes",
               (long long)workspace_bytes, (long long)need);
     auto st = (cudaStream_t)stream;
+    if (!attn_use_split() && BH <= 65536) {
+        ITB_CHECK(workspace && workspace_bytes >= need, "AttentionKVCache: workspace %lld < %lld bytes",
+                  (long long)workspace_bytes, (long long)need);
+        ITB_DISPATCH_FLOAT(dtype, "AttentionKVCache", {
+            int rc = rope_pos ? launch_attn_stream<T, true>((T *)k_cache, (T *)v_cache, (const T *)q, (const T *)k,
+                                                            (const T *)v, position_id, pos_dtype, rope_pos,
+                                                            rope_pos_dtype, (T *)out, BH, H, S_max, (float *)workspace, st)
+                              : launch_attn_stream<T, false>((T *)k_cache, (T *)v_cache, (const T *)q, (const T *)k,
+                                                             (const T *)v, position_id, pos_dtype, nullptr, 0, (T *)out,
+                                                             BH, H, S_max, (float *)workspace, st);
+            ITB_CHECK(rc == 0, "AttentionKVCache: streaming kernel launch failed: %s",
+                      cudaGetErrorString(cudaGetLastError()));
+            ITB_LAUNCH_CHECK("AttentionKVCache");
+        });
+        return 0;
+    }
     dim3 grid(BH, ns);
     ITB_DISPATCH_FLOAT(dtype, "AttentionKVCache", {
         constexpr int WARPS = 8, U = 4;  // measured: U=2 at 64 regs (4 CTAs/SM) is 11 % slower end-to-end -- per-thread MLP wins

@@ -241,6 +241,9 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
     if (nsplit > 1) cluster.sync();  // peers' shared memory must outlive the leader's reads
 }
 
+// tuning hook (tools/gemm_sweep.py): force the tile width (NB boxes of 64 columns) and the split-K factor; 0 = automatic
+static int g_nb_override = 0, g_splitk_override = 0;
+
 template <typename T, int MT, int NB>
 static int launch_skinny_nb(const GemmArgs &g, int ngroups, const void *const *Ws, void *const *Cs, const int *Ns,
                             cudaStream_t st) {
@@ -271,6 +274,7 @@ static int launch_skinny_nb(const GemmArgs &g, int ngroups, const void *const *W
     int splitk = target / tiles_n;
     splitk = std::max(1, std::min(splitk, 8));
     splitk = std::min(splitk, std::max(1, ktiles / 4));
+    if (g_splitk_override) splitk = std::max(1, std::min(g_splitk_override, 8));
     int per = (ktiles + splitk - 1) / splitk;
     splitk = (ktiles + per - 1) / per;  // no empty split
 
@@ -319,7 +323,7 @@ static int launch_skinny_t(const GemmArgs &g, int ngroups, const void *const *Ws
     }
     int tiles64 = 0;
     for (int i = 0; i < ngroups; ++i) tiles64 += (Ns[i] + 63) / 64;
-    const int nb = force ? force : (tiles64 > 2 * kNumSMs ? 2 : 1);
+    const int nb = g_nb_override ? g_nb_override : force ? force : (tiles64 > 2 * kNumSMs ? 2 : 1);
     if (nb == 2) return launch_skinny_nb<T, MT, 2>(g, ngroups, Ws, Cs, Ns, st);
     return launch_skinny_nb<T, MT, 1>(g, ngroups, Ws, Cs, Ns, st);
 }
@@ -369,3 +373,8 @@ int launch_gemm_skinny_grouped(int dtype, const GemmArgs &g0, int ngroups, const
 #undef SK_GO
 
 }  // namespace itb
+
+extern "C" void it_b200_tune_skinny(int nb, int splitk) {
+    itb::g_nb_override = nb == 1 || nb == 2 ? nb : 0;
+    itb::g_splitk_override = splitk > 0 ? splitk : 0;
+}

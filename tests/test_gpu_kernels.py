@@ -348,7 +348,7 @@ def test_conv_parity(K, dt):
 
 @pytest.mark.parametrize("dt", [F32, F16, BF16])
 @pytest.mark.parametrize("B,H,S,pos", [(2, 4, 64, 0), (2, 4, 64, 37), (16, 32, 1024, 511), (1, 2, 1024, 1023),
-                                       (1, 32, 256, 100)])
+                                       (1, 32, 256, 100), (7, 9, 512, 257), (1, 1, 2048, 2047), (3, 40, 128, 64)])
 def test_attention_parity(K, B, H, S, pos, dt):
     kc, vc = rnd((B, H, S, 128), 28, dt, 0.5), rnd((B, H, S, 128), 29, dt, 0.5)
     q, k, v = rnd((B, H, 1, 128), 30, dt, 0.5), rnd((B, H, 1, 128), 31, dt, 0.5), rnd((B, H, 1, 128), 32, dt, 0.5)
