@@ -327,7 +327,10 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
         fence_mbar_init();
     }
     __syncthreads();
-    pdl_wait();
+    // No griddepcontrol.wait yet: the position input and the cache rows BELOW `pos` were written by earlier steps (the
+    // append of row pos-1 is a whole step of launches upstream), so the producer starts streaming while the previous
+    // kernel of the chain drains.  Everything this step produced (q, k, v, RoPE positions) is read by the consumers,
+    // after their wait; this kernel's own append touches row `pos` only, which the bulk loads never include.
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int pos = pos_dtype == ITB_I64 ? read_pos<int64_t>(position_id) : read_pos<int32_t>(position_id);
@@ -371,6 +374,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
     }
 
     // ---------------- consumers ----------------
+    pdl_wait();
     const int sub = lane / LPR;
     const int col = (lane % LPR) * EPL;
     float qf[EPL], m = -INFINITY, l = 0.f, acc[EPL];

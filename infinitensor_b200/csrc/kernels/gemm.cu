@@ -47,19 +47,40 @@ bool make_tma_2d_b16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t
     return r == CUDA_SUCCESS;
 }
 
+// 3-D tensor [batch][rows][cols] of 2-byte elements (batch stride in elements), box [1, box_rows, box_cols], 128B swizzle
+bool make_tma_3d_b16(CUtensorMap *map, const void *base, uint64_t batch, uint64_t rows, uint64_t cols,
+                     uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows, uint32_t box_cols) {
+    auto fn = get_encode_fn();
+    if (!fn) return false;
+    if (batch <= 1) {
+        batch = 1;
+        batch_stride_elems = rows * row_stride_elems;  // unused dimension; must still be a legal stride
+    }
+    cuuint64_t gdim[3] = {cols, rows, batch};
+    cuuint64_t gstride[2] = {row_stride_elems * 2, batch_stride_elems * 2};
+    cuuint32_t box[3] = {box_cols, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // ---------------------------------------------------------------- im2col (NCHW -> [N][C*R*S, OH*OW])
-template <typename T>
+// FOLD = false: col[n][kc][p] (one [Kc, P] matrix per image);  FOLD = true: col[kc][n * P + p] (the batch folded into
+// the GEMM columns -- one [Kc, N*P] matrix, legal for TMA whenever N*P % 8 == 0 even if P is odd, e.g. 7x7 / 14x14 maps)
+template <typename T, bool FOLD>
 __global__ void __launch_bounds__(256) im2col_kernel(const T *__restrict__ x, T *__restrict__ col, int64_t total,
-                                                     int C, int H, int W, int R, int S, int OH, int OW, int ph,
+                                                     int NB, int C, int H, int W, int R, int S, int OH, int OW, int ph,
                                                      int pw, int sh, int sw, int dh, int dw) {
     pdl_trigger();
     pdl_wait();
-    // col[n][(c*R + r)*S + s][oh*OW + ow]; consecutive threads walk ow -> coalesced writes
+    // kc = (c*R + r)*S + s, p = oh*OW + ow; consecutive threads walk ow -> coalesced writes
     const int64_t P = (int64_t)OH * OW, Kc = (int64_t)C * R * S;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         int64_t p = i % P, t = i / P;
-        int64_t kc = t % Kc, n = t / Kc;
+        int64_t kc = FOLD ? t / NB : t % Kc, n = FOLD ? t % NB : t / Kc;
         int s = (int)(kc % S), r = (int)((kc / S) % R), c = (int)(kc / ((int64_t)R * S));
         int oh = (int)(p / OW), ow = (int)(p % OW);
         int ih = oh * sh - ph + r * dh, iw = ow * sw - pw + s * dw;
@@ -144,14 +165,19 @@ static bool conv_is_1x1_direct(int R, int S, int ph, int pw, int sh, int sw) {
     return R == 1 && S == 1 && ph == 0 && pw == 0 && sh == 1 && sw == 1;
 }
 
+// the folded im2col GEMM ([F, Kc] x [Kc, N*P], scattered back to NCHW by the epilogue) runs on the tcgen05 kernel
+static bool conv_fold_ok(int dtype, int N, int64_t P, int64_t Kc, int F, int groups) {
+    return (dtype == ITB_F16 || dtype == ITB_BF16) && groups == 1 && (N * P) % 8 == 0 && Kc % 8 == 0 && Kc >= 64 &&
+           N * P >= 64 && N * P < (1ll << 31) && F >= 1;
+}
+
 extern "C" int64_t it_b200_conv2d_workspace(int dtype, int N, int C, int H, int W, int F, int R, int S, int ph,
                                             int pw, int sh, int sw, int dh, int dw, int groups) {
-    (void)F;
-    (void)groups;
-    if (conv_is_1x1_direct(R, S, ph, pw, sh, sw)) return 0;
     int OH, OW;
     conv_out(H, W, R, S, ph, pw, sh, sw, dh, dw, OH, OW);
-    return (int64_t)N * C * R * S * OH * OW * dtype_size(dtype);
+    const int64_t P = (int64_t)OH * OW, Kc = (int64_t)C * R * S;
+    if (conv_is_1x1_direct(R, S, ph, pw, sh, sw) && (P % 8 == 0 || !conv_fold_ok(dtype, N, P, Kc, F, groups))) return 0;
+    return (int64_t)N * Kc * P * dtype_size(dtype);
 }
 
 extern "C" int it_b200_conv2d(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W, int F,
@@ -164,18 +190,46 @@ extern "C" int it_b200_conv2d(int dtype, const void *x, const void *w, void *y, 
     if ((int64_t)N * F * OH * OW == 0) return 0;
     const int es = dtype_size(dtype);
     const int64_t P = (int64_t)OH * OW, Kc = (int64_t)C * R * S;
-    const void *col = x;  // 1x1 s1 p0: the NCHW activation already is [N][C, H*W]
-    if (!conv_is_1x1_direct(R, S, ph, pw, sh, sw)) {
+    const bool direct = conv_is_1x1_direct(R, S, ph, pw, sh, sw);
+    // 1x1 s1 p0 with P % 8 == 0: the NCHW activation already is [N][C, P] -> batched GEMM, no repack.
+    // otherwise fold the batch into the GEMM columns when that makes the matrix TMA-legal (tensor-core path).
+    const bool direct_tc = direct && P % 8 == 0;
+    const bool fold = !direct_tc && conv_fold_ok(dtype, N, P, Kc, F, groups);
+    const void *col = x;
+    if (!direct || fold) {
         int64_t need = it_b200_conv2d_workspace(dtype, N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups);
         ITB_CHECK(workspace && workspace_bytes >= need, "conv: workspace %lld < %lld bytes",
                   (long long)workspace_bytes, (long long)need);
         int64_t total = (int64_t)N * Kc * P;
         ITB_DISPATCH_FLOAT(dtype, "conv(im2col)", {
-            launch_k(im2col_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, (const T *)x, (T *)workspace, total, C, H, W, R, S,
-                                                                  OH, OW, ph, pw, sh, sw, dh, dw);
+            if (fold)
+                launch_k(im2col_kernel<T, true>, dim3(grid_for(total, 256)), dim3(256), 0, st, (const T *)x,
+                         (T *)workspace, total, N, C, H, W, R, S, OH, OW, ph, pw, sh, sw, dh, dw);
+            else
+                launch_k(im2col_kernel<T, false>, dim3(grid_for(total, 256)), dim3(256), 0, st, (const T *)x,
+                         (T *)workspace, total, N, C, H, W, R, S, OH, OW, ph, pw, sh, sw, dh, dw);
         });
         ITB_LAUNCH_CHECK("conv(im2col)");
         col = workspace;
+    }
+    if (fold) {
+        // y[n][f][p] = sum_kc W[f, kc] . col[kc, n*P + p]
+        GemmArgs g{};
+        g.A = w;
+        g.B = col;
+        g.C = y;
+        g.batch = 1;
+        g.m = F;
+        g.n = (int)(N * P);
+        g.k = (int)Kc;
+        g.stride_a = (int64_t)F * Kc;
+        g.stride_b = Kc * N * P;
+        g.c_block = (int)P;
+        g.c_block_stride = (int64_t)F * P;
+        int r = launch_gemm_tc(dtype, g, st);
+        ITB_CHECK(r >= 0, "conv: the tensor-core GEMM refused a folded im2col matrix (F=%d Kc=%lld N*P=%lld)", F,
+                  (long long)Kc, (long long)(N * P));
+        return r;
     }
     // y[n][f, p] = W[f, kc] . col[n][kc, p] : A = weights (batch-broadcast), B = col
     const int Cg = C / groups, Fg = F / groups;

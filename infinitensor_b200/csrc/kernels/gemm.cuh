@@ -15,6 +15,11 @@ struct GemmArgs {
     int trans_a, trans_b;
     int64_t bias_sb, bias_sm, bias_sn;  // bias strides in elements (0 = broadcast)
     int act;                            // 0 none, 1 relu, 2 sigmoid, 3 tanh
+    // optional output scatter (conv with the batch folded into the GEMM columns): column gn of row m goes to
+    // C[(gn / c_block) * c_block_stride + m * c_block + gn % c_block]; 0 = plain row-major C[m * n + gn].
+    // Honoured by the tcgen05 kernel only (launch_gemm_tc is called directly for it).
+    int c_block = 0;
+    int64_t c_block_stride = 0;
 };
 
 __device__ __forceinline__ float gemm_act(int act, float v) {
@@ -40,6 +45,9 @@ int launch_gemm_streamk_grouped(int dtype, const GemmArgs &g0, int ngroups, cons
 // 2-D row-major tensor [rows, cols] of 2-byte elements, box [box_rows, box_cols], 128B swizzle.
 bool make_tma_2d_b16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols,
                      uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
+
+bool make_tma_3d_b16(CUtensorMap *map, const void *base, uint64_t batch, uint64_t rows, uint64_t cols,
+                     uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows, uint32_t box_cols);
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,6 +108,17 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
         " [%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+          "l"(policy)
+        : "memory");
+}
+
+// 3-D tile load: (c0 = column, c1 = row, c2 = batch)
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
           "l"(policy)
         : "memory");
 }

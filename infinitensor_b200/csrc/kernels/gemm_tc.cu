@@ -95,6 +95,9 @@ struct TcParams {
     int x_bytes;     // mpad * 128
     int red_bytes;   // split-K partial tile: mpad * 128 * 4 (0 when splitk == 1)
     int ktiles, ktiles_per_split;
+    int m_chunks;    // ceil(M / mpad): grid.z = batch * m_chunks
+    int a_batched;   // X has a batch dimension (stride_a != 0); otherwise it is broadcast over the batch
+    int b_batched;   // same for W
     uint32_t idesc;
 };
 
@@ -116,6 +119,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     cg::cluster_group cluster = cg::this_cluster();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * TC_BN;
+    const int bz = (int)blockIdx.z / p.m_chunks;                  // batch index
+    const int m0 = ((int)blockIdx.z % p.m_chunks) * p.mpad;      // first row of this CTA's row chunk
+    const int bx = p.a_batched ? bz : 0, bw = p.b_batched ? bz : 0;
     const int split = blockIdx.y, nsplit = gridDim.y;
     const int kt_begin = split * p.ktiles_per_split;
     const int kt_end = min(p.ktiles, kt_begin + p.ktiles_per_split);
@@ -151,20 +157,20 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             for (int it = 0; it < pre; ++it) {
                 mbar_expect_tx(&full[it], TC_W_BYTES + p.x_bytes);
                 const int k0 = (kt_begin + it) * TC_BK;
-                tma_load_2d(w_sm + it * TC_W_BYTES, &mapW, &full[it], n0, k0, pol_w);
-                tma_load_2d(w_sm + it * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[it], n0 + 64, k0, pol_w);
+                tma_load_3d(w_sm + it * TC_W_BYTES, &mapW, &full[it], n0, k0, bw, pol_w);
+                tma_load_3d(w_sm + it * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[it], n0 + 64, k0, bw, pol_w);
             }
             pdl_wait();
             for (int it = 0; it < pre; ++it)
-                tma_load_2d(x_sm + it * p.x_bytes, &mapX, &full[it], (kt_begin + it) * TC_BK, 0, pol_x);
+                tma_load_3d(x_sm + it * p.x_bytes, &mapX, &full[it], (kt_begin + it) * TC_BK, m0, bx, pol_x);
             for (int it = pre; it < my_kt; ++it) {
                 const int s = it % S;
                 mbar_wait(&empty[s], ((it / S) - 1) & 1);
                 mbar_expect_tx(&full[s], TC_W_BYTES + p.x_bytes);
                 const int k0 = (kt_begin + it) * TC_BK;
-                tma_load_2d(w_sm + s * TC_W_BYTES, &mapW, &full[s], n0, k0, pol_w);
-                tma_load_2d(w_sm + s * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[s], n0 + 64, k0, pol_w);
-                tma_load_2d(x_sm + s * p.x_bytes, &mapX, &full[s], k0, 0, pol_x);
+                tma_load_3d(w_sm + s * TC_W_BYTES, &mapW, &full[s], n0, k0, bw, pol_w);
+                tma_load_3d(w_sm + s * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[s], n0 + 64, k0, bw, pol_w);
+                tma_load_3d(x_sm + s * p.x_bytes, &mapX, &full[s], k0, m0, bx, pol_x);
             }
         }
         __syncwarp();
@@ -193,14 +199,17 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     }
 
     // ===== epilogue: warps 0..3 own TMEM lanes [32w, 32w+32) = output columns n0 + 32w + lane =====
-    const T *bias = (const T *)g.bias;
-    T *C = (T *)g.C;
+    const T *bias = g.bias ? (const T *)g.bias + (int64_t)bz * g.bias_sb : nullptr;
+    T *C = (T *)g.C + (int64_t)bz * g.m * g.n;
     if (warp < 4) {
         pdl_wait();
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const int nl = warp * 32 + lane;  // column inside the tile
         const int gn = n0 + nl;
+        // element (m, gn) lives at C[c_off + m * c_ld] (plain row-major, or the conv scatter of GemmArgs::c_block)
+        const int64_t c_ld = g.c_block ? g.c_block : g.n;
+        const int64_t c_off = g.c_block ? (int64_t)(gn / g.c_block) * g.c_block_stride + gn % g.c_block : gn;
         for (int c0 = 0; c0 < p.mpad; c0 += 16) {
             uint32_t v[16];
             if (my_kt > 0) {
@@ -215,14 +224,14 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             } else if (gn < g.n) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int m = c0 + j;
+                    const int m = m0 + c0 + j;
                     if (m < g.m) {
                         float f = __uint_as_float(v[j]);
                         if (bias) {
                             if (g.act & ITB_ACT_ROUND_BEFORE_BIAS) f = round_t<T>(f);
                             f += to_f(bias[m * g.bias_sm + gn * g.bias_sn]);
                         }
-                        C[(int64_t)m * g.n + gn] = from_f<T>(gemm_act(g.act, f));
+                        C[c_off + (int64_t)m * c_ld] = from_f<T>(gemm_act(g.act, f));
                     }
                 }
             }
@@ -235,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             const float *peers[8];
             for (int r = 0; r < nsplit; ++r) peers[r] = (const float *)cluster.map_shared_rank(red, r);
             for (int idx = threadIdx.x; idx < p.mpad * TC_BN; idx += 128) {
-                const int m = idx / TC_BN, nl = idx % TC_BN, gn = n0 + nl;
+                const int m = m0 + idx / TC_BN, nl = idx % TC_BN, gn = n0 + nl;
                 if (m >= g.m || gn >= g.n) continue;
                 float f = 0.f;
                 for (int r = 0; r < nsplit; ++r) f += peers[r][idx];
@@ -243,7 +252,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                     if (g.act & ITB_ACT_ROUND_BEFORE_BIAS) f = round_t<T>(f);
                     f += to_f(bias[m * g.bias_sm + gn * g.bias_sn]);
                 }
-                C[(int64_t)m * g.n + gn] = from_f<T>(gemm_act(g.act, f));
+                const int64_t off = g.c_block ? (int64_t)(gn / g.c_block) * g.c_block_stride + (int64_t)m * g.c_block + gn % g.c_block
+                                              : (int64_t)m * g.n + gn;
+                C[off] = from_f<T>(gemm_act(g.act, f));
             }
         }
         cluster.sync();
@@ -259,7 +270,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
 template <typename T>
 static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
     TcParams p{};
-    p.mpad = ((g.m + 15) / 16) * 16;
+    p.mpad = g.m > 256 ? 256 : ((g.m + 15) / 16) * 16;
+    p.m_chunks = (g.m + p.mpad - 1) / p.mpad;
+    p.a_batched = g.batch > 1 && g.stride_a != 0;
+    p.b_batched = g.batch > 1 && g.stride_b != 0;
     p.tmem_cols = 32;
     while (p.tmem_cols < p.mpad) p.tmem_cols <<= 1;
     p.x_bytes = p.mpad * 128;
@@ -267,7 +281,7 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
     p.ktiles = (g.k + TC_BK - 1) / TC_BK;
     // split-K only where the partial tile is small (decode regime); clusters of <= 8 CTAs
     int splitk = 1;
-    if (p.mpad <= 64) {
+    if (p.mpad <= 64 && g.batch == 1) {
         splitk = (2 * kNumSMs) / tiles_n;
         splitk = std::max(1, std::min(splitk, 8));
         splitk = std::min(splitk, std::max(1, p.ktiles / 4));
@@ -282,9 +296,11 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
     const int smem = p.stages * stage_bytes + p.red_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
 
     CUtensorMap mapW, mapX;
-    if (!make_tma_2d_b16(&mapW, g.B, (uint64_t)g.k, (uint64_t)g.n, (uint64_t)g.n, TC_BK, 64, 128))
+    if (!make_tma_3d_b16(&mapW, g.B, p.b_batched ? (uint64_t)g.batch : 1, (uint64_t)g.k, (uint64_t)g.n, (uint64_t)g.n,
+                         (uint64_t)g.stride_b, TC_BK, 64))
         ITB_FAIL("matmul(tcgen05): cuTensorMapEncodeTiled(W) failed");
-    if (!make_tma_2d_b16(&mapX, g.A, (uint64_t)g.m, (uint64_t)g.k, (uint64_t)g.k, (uint32_t)p.mpad, TC_BK, 128))
+    if (!make_tma_3d_b16(&mapX, g.A, p.a_batched ? (uint64_t)g.batch : 1, (uint64_t)g.m, (uint64_t)g.k, (uint64_t)g.k,
+                         (uint64_t)g.stride_a, (uint32_t)p.mpad, TC_BK))
         ITB_FAIL("matmul(tcgen05): cuTensorMapEncodeTiled(X) failed");
 
     static int attr_smem = 0;
@@ -295,7 +311,7 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
         attr_smem = smem;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(tiles_n, splitk, 1);
+    cfg.gridDim = dim3(tiles_n, splitk, (unsigned)(g.batch * p.m_chunks));
     cfg.blockDim = dim3(TC_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -316,9 +332,15 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
 
 int launch_gemm_tc(int dtype, const GemmArgs &g, cudaStream_t st) {
     if (dtype != ITB_BF16 && dtype != ITB_F16) return -1;
-    if (g.batch != 1 || g.trans_a || g.trans_b || g.m < 1 || g.m > 256) return -1;
+    if (g.batch < 1 || g.trans_a || g.trans_b || g.m < 1) return -1;
     if (g.n % 8 != 0 || g.k % 8 != 0 || g.n < 64 || g.k < 64) return -1;
     if (!aligned16(g.A) || !aligned16(g.B)) return -1;
+    if (g.batch > 1) {
+        // batches must be dense [b][K][N] / [b][M][K] (or X broadcast): that is what the 3-D tensor maps describe
+        if (g.stride_b != 0 && g.stride_b != (int64_t)g.k * g.n) return -1;
+        if (g.stride_a != 0 && g.stride_a != (int64_t)g.m * g.k) return -1;
+        if ((int64_t)g.batch * ((g.m + 255) / 256) > 65535) return -1;
+    }
     if (dtype == ITB_BF16) return launch_tc_t<__nv_bfloat16>(g, st, true);
     return launch_tc_t<__half>(g, st, false);
 }

@@ -335,6 +335,38 @@ def test_matmul_tcgen05_parity(K, gemm_impl, m, k, n, dt):
     _gemm_case(K, m, k, n, dt)
 
 
+@pytest.mark.parametrize("gemm_impl", ["tc"], indirect=True)
+@pytest.mark.parametrize("dt", [BF16, F16])
+@pytest.mark.parametrize("sa,sb", [((600, 256), (256, 384)),            # M > 256: row chunks of 256 on grid.z
+                                   ((257, 72), (72, 200)),              # ragged last chunk, K and N not tile multiples
+                                   ((12, 128, 64), (12, 64, 128)),      # GPT-2 q.k^T, batched on both sides
+                                   ((12, 128, 128), (12, 128, 64)),     # GPT-2 p.v
+                                   ((512, 576), (5, 576, 200)),         # conv form: broadcast filters x batched im2col
+                                   ((3, 300, 64), (64, 96))])           # batched X, broadcast W
+def test_matmul_tcgen05_batched_parity(K, gemm_impl, sa, sb, dt):
+    """tcgen05 GEMM over grid.z = batch x 256-row chunks with 3-D tensor maps (conv im2col GEMMs, GPT-2 attention)."""
+    a, b = rnd(sa, 28, dt, 0.5), rnd(sb, 29, dt, 0.1)
+    tol = gemm_tol(dt, sa[-1], np.abs(a).max(), np.abs(b).max())
+    close(K.matmul(a, b, None, False, False, dt), oracle.matmul(a, b, None, False, False, dt), 2 * EPS[dt], tol)
+    bias = rnd((sb[-1],), 30, dt)
+    close(K.matmul(a, b, bias, False, False, dt, act=1),
+          np.maximum(oracle.matmul(a, b, bias, False, False, dt), 0), 2 * EPS[dt], tol)
+
+
+@pytest.mark.parametrize("dt", [F16, BF16])
+def test_conv_resnet_shapes_parity(K, dt):
+    """ResNet-50 bottleneck shapes (reduced batch): 1x1, 3x3 s1/s2, 7x7-stage P = 49, F up to 2048."""
+    tol = {F16: 8e-3, BF16: 6e-2}[dt]
+    for (xs, ws, args) in [((2, 64, 56, 56), (256, 64, 1, 1), (0, 0, 1, 1, 1, 1)),
+                           ((2, 128, 28, 28), (128, 128, 3, 3), (1, 1, 1, 1, 1, 1)),
+                           ((2, 256, 28, 28), (256, 256, 3, 3), (1, 1, 2, 2, 1, 1)),
+                           ((2, 1024, 14, 14), (2048, 1024, 1, 1), (0, 0, 2, 2, 1, 1)),
+                           ((2, 512, 7, 7), (512, 512, 3, 3), (1, 1, 1, 1, 1, 1)),
+                           ((2, 2048, 7, 7), (512, 2048, 1, 1), (0, 0, 1, 1, 1, 1))]:
+        x, w = rnd(xs, 26, dt), rnd(ws, 27, dt, 0.05)
+        close(K.conv2d(x, w, *args, dt=dt), oracle.conv2d(x, w, *args, dt=dt), tol, tol)
+
+
 @pytest.mark.parametrize("dt", [F32, F16, BF16])
 def test_conv_parity(K, dt):
     tol = {F32: 1e-4, F16: 4e-3, BF16: 3e-2}[dt]
