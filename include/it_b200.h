@@ -135,6 +135,10 @@ int it_b200_pool2d(int dtype, int is_max, const void *x, void *y, int N, int C, 
 int it_b200_batchnorm(int dtype, const void *x, const float *mean, const float *var,
                       const float *scale, const float *bias, void *y, int N, int C, int64_t HW,
                       float eps, void *stream);
+/* BatchNorm followed by ReLU in one pass (bit-identical to the two kernels). */
+int it_b200_batchnorm_relu(int dtype, const void *x, const float *mean, const float *var, const float *scale,
+                           const float *bias, void *y, int N, int C, int64_t HW, float eps, void *stream);
+
 
 /* ---- MatMul: replaces matmulCublas (matmul.cc:66-211).
  *      C[b,m,n] = op(A)[b,m,k] . op(B)[b,k,n] (+ bias) ; row-major; stride_a / stride_b in
@@ -172,6 +176,16 @@ int64_t it_b200_conv2d_workspace(int dtype, int N, int C, int H, int W, int F, i
 int it_b200_conv2d(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W,
                    int F, int R, int S, int ph, int pw, int sh, int sw, int dh, int dw, int groups,
                    void *workspace, int64_t workspace_bytes, void *stream);
+/* Conv with the tail of a ResNet bottleneck folded into the tensor-core GEMM epilogue: Conv -> BatchNorm (fp32
+ * statistics; all four vectors or none) -> [+ residual, laid out like y] -> [ReLU].  Every stage rounds to the storage
+ * dtype exactly as the separate kernels would, so the result is bit-identical to running them one by one.
+ * Returns 0 = done, 1 = error, 2 = this shape does not take the tensor-core path (nothing launched: run the operators
+ * separately).  Same workspace as it_b200_conv2d. */
+int it_b200_conv2d_fused(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W, int F, int R,
+                         int S, int ph, int pw, int sh, int sw, int dh, int dw, int groups, const float *bn_mean,
+                         const float *bn_var, const float *bn_scale, const float *bn_bias, float bn_eps,
+                         const void *residual, int relu, void *workspace, int64_t workspace_bytes, void *stream);
+
 
 /* ---- AttentionKVCache (decode, q-len 1): replaces _attention_kvcache_kernel_128_1/_2
  *      (attention_kvcache.cu:8-169).  Appends k,v IN PLACE into k_cache/v_cache at

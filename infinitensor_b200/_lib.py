@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libit_b200.so")
+# ITB_LIB_PATH: load another BUILD of the same library (instrumented / A-B variants made by tools/); never a fallback
+LIB_PATH = os.environ.get("ITB_LIB_PATH") or os.path.join(_HERE, "libit_b200.so")
 
 
 class B200BackendError(RuntimeError):
@@ -58,6 +59,8 @@ _SIGS = {
     "it_b200_silu_mul": (c_int, [c_int, vp, vp, vp, c_int64, vp]),
     "it_b200_allreduce_workspace_bytes": (c_int64, []),
     "it_b200_allreduce_fused": (c_int, [c_int, vp, vp, vp, vp, vp, c_int, c_int, POINTER(vp), c_int, c_int, vp]),
+    "it_b200_batchnorm_relu": (c_int, [c_int, vp, vp, vp, vp, vp, vp, c_int, c_int, c_int64, c_float, vp]),
+    "it_b200_conv2d_fused": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, vp, vp, vp, c_float, vp, c_int, vp, c_int64, vp]),
     "it_b200_conv2d_workspace": (c_int64, [c_int] * 15),
     "it_b200_conv2d": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, c_int64, vp]),
     "it_b200_attention_kvcache_workspace": (c_int64, [c_int] * 4),

@@ -388,6 +388,38 @@ void runAttentionRope(const Operator &ropeQ, const Operator &ropeK, const Operat
                                       P(att->getOutput()), d[0], d[1], d[2], d[3], ws, wsb, S()), att);
 }
 
+// Conv -> BatchNorm -> [Add(residual)] -> [Relu]: ops = {conv, bn, [add], [relu]}
+bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx) {
+    auto conv = as<ConvObj>(ops[0]);
+    auto bn = as<BatchNormObj>(ops[1]);
+    Operator add, relu;
+    for (size_t i = 2; i < ops.size(); ++i) {
+        if (ops[i]->getOpType() == OpType::Add) add = ops[i];
+        if (ops[i]->getOpType() == OpType::Relu) relu = ops[i];
+    }
+    auto x = conv->getInputs(0), w = conv->getInputs(1);
+    auto [n, c, h, wd, f, r, s] = conv->getNCHWFRS();
+    auto [ph, pw, sh, sw, dh, dw] = conv->getPadStrideDilation();
+    int g = conv->getNumGroups();
+    for (int i = 1; i <= 4; ++i)
+        if (bn->getInputs(i)->getDType() != DataType::Float32) return false;
+    Tensor res;
+    if (add) {
+        Tensor prev = bn->getOutput();
+        res = add->getInputs(0) == prev ? add->getInputs(1) : add->getInputs(0);
+    }
+    int64_t wsb = it_b200_conv2d_workspace(DT(x), n, c, h, wd, f, r, s, ph, pw, sh, sw, dh, dw, g);
+    void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
+    int rc = it_b200_conv2d_fused(DT(x), P(x), P(w), P(ops.back()->getOutput()), n, c, h, wd, f, r, s, ph, pw, sh, sw, dh,
+                                  dw, g, bn->getInputs(1)->getRawDataPtr<float *>(),
+                                  bn->getInputs(2)->getRawDataPtr<float *>(), bn->getInputs(3)->getRawDataPtr<float *>(),
+                                  bn->getInputs(4)->getRawDataPtr<float *>(), bn->getEps(), res ? P(res) : nullptr,
+                                  relu ? 1 : 0, ws, wsb, S());
+    if (rc == 2) return false;
+    CK(rc, ops.back());
+    return true;
+}
+
 // AllReduceSum -> Add(residual) [-> RMSNorm] through the one-shot NVLink kernel
 bool runAllReduceAddNorm(const OpVec &ops, const RuntimeObj *ctx) {
     auto rt = RT(ctx);

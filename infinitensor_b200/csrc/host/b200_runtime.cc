@@ -173,6 +173,12 @@ void CudaRuntimeObj::runWithoutSyncImpl(const Graph &graph, bool validate) const
         }
         case ExecStep::SiluMul: b200::runSiluMul(st.ops[0], st.ops[1], this); break;
         case ExecStep::AttentionRope: b200::runAttentionRope(st.ops[0], st.ops[1], st.ops[2], this); break;
+        case ExecStep::ConvBnAct:
+            if (!b200::runConvBnAct(st.ops, this)) {
+                auto &reg = KernelRegistry::getInstance();
+                for (auto &m : st.ops) reg.getKernel(KernelAttrs{Device::CUDA, m->getOpType().underlying()})->compute(m, this);
+            }
+            break;
         case ExecStep::AllReduceAddNorm:
             if (!b200::runAllReduceAddNorm(st.ops, this)) {
                 // no NVLink peer comm (or shape outside its limits): the ordinary kernels, one by one

@@ -146,6 +146,8 @@ void runMatmulGroup(const OpVec &ops, const RuntimeObj *ctx);
 void runSiluMul(const Operator &silu, const Operator &mul, const RuntimeObj *ctx);
 // AllReduceSum -> Add(residual) [-> RMSNorm]: true if the fused NVLink kernel took it, false = run the ops one by one
 bool runAllReduceAddNorm(const OpVec &ops, const RuntimeObj *ctx);
+// Conv -> BatchNorm -> [Add] -> [Relu] in the GEMM epilogue; false = shape not taken (nothing launched)
+bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx);
 void runAttentionRope(const Operator &ropeQ, const Operator &ropeK, const Operator &att, const RuntimeObj *ctx);
 }  // namespace b200
 

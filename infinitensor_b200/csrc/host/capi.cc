@@ -372,7 +372,7 @@ int itb_graph_step(itb_graph *g, int index, char *buf, int buf_len) {
     ITB_TRY({
         const auto &sc = g->g->getSchedule();
         IT_ASSERT(index >= 0 && index < (int)sc.size(), "bad step index");
-        static const char *kinds[] = {"Single", "Alias", "MatMulGroup", "MatMulAdd", "SiluMul", "AttentionRope", "AllReduceAddNorm"};
+        static const char *kinds[] = {"Single", "Alias", "MatMulGroup", "MatMulAdd", "SiluMul", "AttentionRope", "AllReduceAddNorm", "ConvBnAct"};
         std::string s = kinds[(int)sc[index].kind];
         s += ":";
         for (size_t i = 0; i < sc[index].ops.size(); ++i) s += (i ? "+" : "") + std::string(sc[index].ops[i]->getOpType().toString());

@@ -344,7 +344,9 @@ struct ExecStep {
         MatMulAdd,    // MatMul -> Add(residual): residual added in the GEMM epilogue
         SiluMul,      // Silu -> Mul: one pass
         AttentionRope,    // RoPE(q), RoPE(k) -> [aliases] -> AttentionKVCache: RoPE applied inside the attention kernel
-        AllReduceAddNorm  // AllReduceSum -> Add(residual) [-> RMSNorm]: one NVLink peer-memory kernel (else 3 ops)
+        AllReduceAddNorm, // AllReduceSum -> Add(residual) [-> RMSNorm]: one NVLink peer-memory kernel (else 3 ops)
+        ConvBnAct         // Conv -> BatchNorm -> [Add(residual)] -> [Relu]: the tail runs in the tensor-core GEMM epilogue
+                          // (bit-identical to the separate kernels); shapes the GEMM does not take run one by one
     } kind = Single;
     OpVec ops;
 };

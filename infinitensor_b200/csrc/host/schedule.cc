@@ -14,10 +14,10 @@ static bool fusionEnabled() {
     const char *e = std::getenv("ITB_NO_FUSION");
     return !(e && e[0] == '1');
 }
-// ITB_FUSION_MASK (debug / A-B): bit 0 alias, 1 MatMul groups, 2 MatMul+Add, 3 Silu*Mul, 4 AllReduce+Add+Norm, 5 RoPE->Attention; default all
+// ITB_FUSION_MASK (debug / A-B): bit 0 alias, 1 MatMul groups, 2 MatMul+Add, 3 Silu*Mul, 4 AllReduce+Add+Norm, 5 RoPE->Attention, 6 Conv+BatchNorm[+Add][+Relu]; default all
 static int fusionMask() {
     const char *e = std::getenv("ITB_FUSION_MASK");
-    return e && e[0] ? std::atoi(e) : 63;
+    return e && e[0] ? std::atoi(e) : 127;
 }
 
 static bool isKvCacheOperand(const Tensor &t) {
@@ -111,6 +111,13 @@ const vector<ExecStep> &GraphObj::getSchedule() {
                 schedule.push_back(std::move(st));
                 continue;
             }
+            if (pt == OpType::Conv) {
+                st.kind = ExecStep::ConvBnAct;
+                st.ops = prod;
+                st.ops.push_back(op);
+                schedule.push_back(std::move(st));
+                continue;
+            }
             st.kind = pt == OpType::MatMul ? ExecStep::MatMulAdd : pt == OpType::Silu ? ExecStep::SiluMul : ExecStep::AllReduceAddNorm;
             st.ops = {prod[0], op};
             if (st.kind == ExecStep::AllReduceAddNorm) {
@@ -197,6 +204,42 @@ const vector<ExecStep> &GraphObj::getSchedule() {
                     add->getOutput()->getDims() == out->getDims()) {
                     deferredInto[add.get()] = {op};
                     deferred.insert(op.get());
+                    continue;
+                }
+            }
+        } else if (type == OpType::Conv && (mask & 64)) {
+            // Conv -> BatchNorm -> [Add(x, same shape)] -> [Relu], every link single-consumer: the chain runs as ONE step at
+            // the position of its last operator (the Add's other operand is then already computed)
+            OpVec chain = {op};
+            Tensor t = op->getOutput();
+            auto sole = [&](const Tensor &x) -> Operator {
+                if (x->isOutput() || x->getTargets().size() != 1) return nullptr;
+                auto c = x->getTargets()[0];
+                if (consumed.count(c.get()) || deferred.count(c.get()) || deferredInto.count(c.get())) return nullptr;
+                return c;
+            };
+            Operator nx = sole(t);
+            if (t->getDType().isFloat() && nx && nx->getOpType() == OpType::BatchNormalization && nx->getInputs(0) == t) {
+                bool statsOk = true;
+                for (int k = 1; k <= 4; ++k) statsOk = statsOk && nx->getInputs(k)->getDType() == DataType::Float32;
+                if (statsOk) {
+                    chain.push_back(nx);
+                    t = nx->getOutput();
+                    nx = sole(t);
+                    if (nx && nx->getOpType() == OpType::Add) {
+                        auto other = nx->getInputs(0) == t ? nx->getInputs(1) : nx->getInputs(0);
+                        if (other != t && other->getDims() == t->getDims() && other->getDType() == t->getDType() &&
+                            nx->getOutput()->getDims() == t->getDims()) {
+                            chain.push_back(nx);
+                            t = nx->getOutput();
+                            nx = sole(t);
+                        }
+                    }
+                    if (nx && nx->getOpType() == OpType::Relu && nx->getInputs(0) == t) chain.push_back(nx);
+                    auto last = chain.back();
+                    chain.pop_back();
+                    deferredInto[last.get()] = chain;
+                    for (auto &m : chain) deferred.insert(m.get());
                     continue;
                 }
             }

@@ -93,6 +93,13 @@ template <typename T> __device__ __forceinline__ T from_f(float v) { return Type
 // round a float to T and back (the reference's "(T)(expr)" points)
 template <typename T> __device__ __forceinline__ float round_t(float v) { return to_f<T>(from_f<T>(v)); }
 
+// inference BatchNorm arithmetic, spelled with intrinsics so the stand-alone kernel and the conv epilogue round alike:
+//   y = scale * (x - mean) * rs + bias,  rs = 1 / sqrt(var + eps)      (reference batch_norm.cc:9-69 via cuDNN)
+__device__ __forceinline__ float bn_rs(float var, float eps) { return 1.0f / sqrtf(var + eps); }
+__device__ __forceinline__ float bn_apply(float x, float mean, float rs, float scale, float bias) {
+    return __fmaf_rn(__fmul_rn(scale, __fsub_rn(x, mean)), rs, bias);
+}
+
 // 16-byte vector of T
 template <typename T> struct Vec16 {
     static constexpr int N = 16 / sizeof(T);

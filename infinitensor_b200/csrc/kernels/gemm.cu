@@ -68,25 +68,58 @@ bool make_tma_3d_b16(CUtensorMap *map, const void *base, uint64_t batch, uint64_
 
 // ---------------------------------------------------------------- im2col (NCHW -> [N][C*R*S, OH*OW])
 // FOLD = false: col[n][kc][p] (one [Kc, P] matrix per image);  FOLD = true: col[kc][n * P + p] (the batch folded into
-// the GEMM columns -- one [Kc, N*P] matrix, legal for TMA whenever N*P % 8 == 0 even if P is odd, e.g. 7x7 / 14x14 maps)
-template <typename T, bool FOLD>
+// the GEMM columns -- one [Kc, N*P] matrix, legal for TMA whenever N*P % 8 == 0 even if P is odd, e.g. 7x7 / 14x14 maps).
+// kc = (c*R + r)*S + s, p = oh*OW + ow.  VEC: one thread produces 8 consecutive elements of one col row (row length % 8
+// == 0) with one 16-byte store and incremental (ow, oh, n) stepping -- one div/mod set per 8 elements, 32-bit math.
+template <typename T, bool FOLD, bool VEC>
 __global__ void __launch_bounds__(256) im2col_kernel(const T *__restrict__ x, T *__restrict__ col, int64_t total,
                                                      int NB, int C, int H, int W, int R, int S, int OH, int OW, int ph,
                                                      int pw, int sh, int sw, int dh, int dw) {
     pdl_trigger();
     pdl_wait();
-    // kc = (c*R + r)*S + s, p = oh*OW + ow; consecutive threads walk ow -> coalesced writes
-    const int64_t P = (int64_t)OH * OW, Kc = (int64_t)C * R * S;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t p = i % P, t = i / P;
-        int64_t kc = FOLD ? t / NB : t % Kc, n = FOLD ? t % NB : t / Kc;
-        int s = (int)(kc % S), r = (int)((kc / S) % R), c = (int)(kc / ((int64_t)R * S));
-        int oh = (int)(p / OW), ow = (int)(p % OW);
-        int ih = oh * sh - ph + r * dh, iw = ow * sw - pw + s * dw;
-        T v = from_f<T>(0.f);
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((int64_t)n * C + c) * H + ih) * W + iw];
-        col[i] = v;
+    const int P = OH * OW, Kc = C * R * S;
+    if (VEC) {
+        constexpr int V = 8;
+        static_assert(sizeof(T) == 2 || !VEC, "vector im2col is for 2-byte types");
+        const int rowlen = FOLD ? NB * P : P, row8 = rowlen / V;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total / V;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t rowid = i / row8;  // FOLD: kc;  else n * Kc + kc
+            const int j0 = (int)(i - rowid * row8) * V;
+            const int kc = FOLD ? (int)rowid : (int)(rowid % Kc);
+            int n = FOLD ? j0 / P : (int)(rowid / Kc);
+            const int p0 = FOLD ? j0 - n * P : j0;
+            const int s = kc % S, r = (kc / S) % R, c = kc / (R * S);
+            int oh = p0 / OW, ow = p0 - oh * OW;
+            T out[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const int ih = oh * sh - ph + r * dh, iw = ow * sw - pw + s * dw;
+                T v = from_f<T>(0.f);
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((int64_t)n * C + c) * H + ih) * W + iw];
+                out[e] = v;
+                if (++ow == OW) {
+                    ow = 0;
+                    if (++oh == OH) {
+                        oh = 0;
+                        ++n;
+                    }
+                }
+            }
+            *reinterpret_cast<uint4 *>(col + rowid * rowlen + j0) = *reinterpret_cast<const uint4 *>(out);
+        }
+    } else {
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            int64_t p = i % P, t = i / P;
+            int64_t kc = FOLD ? t / NB : t % Kc, n = FOLD ? t % NB : t / Kc;
+            int s = (int)(kc % S), r = (int)((kc / S) % R), c = (int)(kc / ((int64_t)R * S));
+            int oh = (int)(p / OW), ow = (int)(p % OW);
+            int ih = oh * sh - ph + r * dh, iw = ow * sw - pw + s * dw;
+            T v = from_f<T>(0.f);
+            if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((int64_t)n * C + c) * H + ih) * W + iw];
+            col[i] = v;
+        }
     }
 }
 
@@ -180,9 +213,19 @@ extern "C" int64_t it_b200_conv2d_workspace(int dtype, int N, int C, int H, int 
     return (int64_t)N * Kc * P * dtype_size(dtype);
 }
 
-extern "C" int it_b200_conv2d(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W, int F,
-                              int R, int S, int ph, int pw, int sh, int sw, int dh, int dw, int groups,
-                              void *workspace, int64_t workspace_bytes, void *stream) {
+struct ConvTail {
+    const float *mean = nullptr, *var = nullptr, *scale = nullptr, *bias = nullptr;
+    float eps = 0.f;
+    const void *residual = nullptr;
+    int relu = 0;
+    bool any() const { return scale || residual || relu; }
+};
+
+// returns 0 done, 1 error, 2 = a fused tail was asked for but this shape does not run on the tensor-core GEMM (nothing
+// was launched; the caller executes the operators one by one)
+static int conv_impl(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W, int F, int R, int S,
+                     int ph, int pw, int sh, int sw, int dh, int dw, int groups, const ConvTail &tail, void *workspace,
+                     int64_t workspace_bytes, void *stream) {
     ITB_CHECK(groups >= 1 && C % groups == 0 && F % groups == 0, "conv: bad groups %d for C=%d F=%d", groups, C, F);
     auto st = (cudaStream_t)stream;
     int OH, OW;
@@ -195,19 +238,43 @@ extern "C" int it_b200_conv2d(int dtype, const void *x, const void *w, void *y, 
     // otherwise fold the batch into the GEMM columns when that makes the matrix TMA-legal (tensor-core path).
     const bool direct_tc = direct && P % 8 == 0;
     const bool fold = !direct_tc && conv_fold_ok(dtype, N, P, Kc, F, groups);
+    auto with_tail = [&](GemmArgs &g) {
+        g.bn_mean = tail.mean;
+        g.bn_var = tail.var;
+        g.bn_scale = tail.scale;
+        g.bn_bias = tail.bias;
+        g.bn_eps = tail.eps;
+        g.residual = tail.residual;
+        g.post_relu = tail.relu;
+    };
+    if (tail.any()) {
+        // the tail is implemented by the tcgen05 epilogue: decide BEFORE launching anything
+        const bool tc_batched = direct_tc && groups == 1 && (dtype == ITB_F16 || dtype == ITB_BF16) && Kc % 8 == 0 &&
+                                Kc >= 64 && P >= 64 && aligned16(x) && aligned16(w) && (int64_t)N * ((F + 255) / 256) <= 65535;
+        if (!fold && !tc_batched) return 2;
+        if (fold && (!aligned16(w) || !aligned16(workspace))) return 2;
+    }
     const void *col = x;
     if (!direct || fold) {
         int64_t need = it_b200_conv2d_workspace(dtype, N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups);
         ITB_CHECK(workspace && workspace_bytes >= need, "conv: workspace %lld < %lld bytes",
                   (long long)workspace_bytes, (long long)need);
         int64_t total = (int64_t)N * Kc * P;
+        const int64_t rowlen = fold ? (int64_t)N * P : P;
         ITB_DISPATCH_FLOAT(dtype, "conv(im2col)", {
-            if (fold)
-                launch_k(im2col_kernel<T, true>, dim3(grid_for(total, 256)), dim3(256), 0, st, (const T *)x,
-                         (T *)workspace, total, N, C, H, W, R, S, OH, OW, ph, pw, sh, sw, dh, dw);
-            else
-                launch_k(im2col_kernel<T, false>, dim3(grid_for(total, 256)), dim3(256), 0, st, (const T *)x,
-                         (T *)workspace, total, N, C, H, W, R, S, OH, OW, ph, pw, sh, sw, dh, dw);
+            auto go = [&](auto kern, int64_t items) {
+                return launch_k(kern, dim3(grid_for(items, 256)), dim3(256), 0, st, (const T *)x, (T *)workspace, total, N, C, H,
+                                W, R, S, OH, OW, ph, pw, sh, sw, dh, dw);
+            };
+            if constexpr (sizeof(T) == 2) {
+                if (rowlen % 8 == 0 && aligned16(workspace)) {
+                    if (fold) go(im2col_kernel<T, true, true>, total / 8); else go(im2col_kernel<T, false, true>, total / 8);
+                } else {
+                    if (fold) go(im2col_kernel<T, true, false>, total); else go(im2col_kernel<T, false, false>, total);
+                }
+            } else {
+                if (fold) go(im2col_kernel<T, true, false>, total); else go(im2col_kernel<T, false, false>, total);
+            }
         });
         ITB_LAUNCH_CHECK("conv(im2col)");
         col = workspace;
@@ -226,6 +293,8 @@ extern "C" int it_b200_conv2d(int dtype, const void *x, const void *w, void *y, 
         g.stride_b = Kc * N * P;
         g.c_block = (int)P;
         g.c_block_stride = (int64_t)F * P;
+        g.no_splitk = 1;
+        with_tail(g);
         int r = launch_gemm_tc(dtype, g, st);
         ITB_CHECK(r >= 0, "conv: the tensor-core GEMM refused a folded im2col matrix (F=%d Kc=%lld N*P=%lld)", F,
                   (long long)Kc, (long long)(N * P));
@@ -248,7 +317,13 @@ extern "C" int it_b200_conv2d(int dtype, const void *x, const void *w, void *y, 
         g.stride_b = Kc * P;
         g.trans_a = g.trans_b = 0;
         g.act = 0;
-        if (groups == 1) {
+        g.no_splitk = 1;
+        if (groups == 1 && tail.any()) {
+            with_tail(g);
+            int r = launch_gemm_tc(dtype, g, st);
+            ITB_CHECK(r >= 0, "conv: the tensor-core GEMM refused a fused 1x1 conv (F=%d C=%d P=%lld)", F, C, (long long)P);
+            if (r) return r;
+        } else if (groups == 1) {
             int r = run_gemm(dtype, g, st);
             if (r) return r;
         } else {
@@ -264,4 +339,31 @@ extern "C" int it_b200_conv2d(int dtype, const void *x, const void *w, void *y, 
         }
     }
     return 0;
+}
+
+extern "C" int it_b200_conv2d(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W, int F,
+                              int R, int S, int ph, int pw, int sh, int sw, int dh, int dw, int groups,
+                              void *workspace, int64_t workspace_bytes, void *stream) {
+    return conv_impl(dtype, x, w, y, N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups, ConvTail{}, workspace,
+                     workspace_bytes, stream);
+}
+
+extern "C" int it_b200_conv2d_fused(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W,
+                                    int F, int R, int S, int ph, int pw, int sh, int sw, int dh, int dw, int groups,
+                                    const float *bn_mean, const float *bn_var, const float *bn_scale,
+                                    const float *bn_bias, float bn_eps, const void *residual, int relu,
+                                    void *workspace, int64_t workspace_bytes, void *stream) {
+    ITB_CHECK((bn_scale == nullptr) == (bn_mean == nullptr) && (bn_scale == nullptr) == (bn_var == nullptr) &&
+                  (bn_scale == nullptr) == (bn_bias == nullptr),
+              "conv_fused: the four BatchNorm parameter vectors go together");
+    ConvTail t;
+    t.mean = bn_mean;
+    t.var = bn_var;
+    t.scale = bn_scale;
+    t.bias = bn_bias;
+    t.eps = bn_eps;
+    t.residual = residual;
+    t.relu = relu;
+    return conv_impl(dtype, x, w, y, N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups, t, workspace, workspace_bytes,
+                     stream);
 }

@@ -20,6 +20,14 @@ struct GemmArgs {
     // Honoured by the tcgen05 kernel only (launch_gemm_tc is called directly for it).
     int c_block = 0;
     int64_t c_block_stride = 0;
+    // optional fused conv tail (tcgen05 kernel only), applied per output ROW m (= conv filter) after the product has been
+    // rounded to the storage dtype, each stage rounded like the separate kernel it replaces:
+    //   BatchNorm (fp32 statistics, bn_scale != nullptr) -> + residual (same layout as C) -> ReLU
+    const float *bn_mean = nullptr, *bn_var = nullptr, *bn_scale = nullptr, *bn_bias = nullptr;
+    float bn_eps = 0.f;
+    const void *residual = nullptr;
+    int post_relu = 0;
+    int no_splitk = 0;  // keep one CTA per output tile (conv GEMMs: same fp32 summation order with and without a tail)
 };
 
 __device__ __forceinline__ float gemm_act(int act, float v) {

@@ -330,7 +330,7 @@ static int launch_skinny_t(const GemmArgs &g, int ngroups, const void *const *Ws
 
 static bool skinny_ok(int dtype, const GemmArgs &g) {
     if (dtype != ITB_BF16 && dtype != ITB_F16) return false;
-    if (g.batch != 1 || g.trans_a || g.trans_b || g.m > 64 || g.m < 1) return false;
+    if (g.batch != 1 || g.trans_a || g.trans_b || g.m > 64 || g.m < 1 || g.no_splitk) return false;
     if (g.n % 8 != 0 || g.k % 8 != 0 || g.n < 64 || g.k < 64) return false;
     if (!aligned16(g.A) || !aligned16(g.B) || ((uintptr_t)g.C & 3)) return false;
     return true;

@@ -19,6 +19,9 @@
 // Replaces the reference's cublasGemmEx dispatch (src/kernels/cuda/matmul.cc:141-168).
 #include <cooperative_groups.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "gemm.cuh"
 
 namespace cg = cooperative_groups;
@@ -88,6 +91,20 @@ __host__ __device__ inline uint32_t umma_idesc_f16(int is_bf16, int a_mn_major, 
     return d;
 }
 
+#ifdef ITB_TC_TRACE
+__device__ unsigned long long g_tc_trace[16];
+#define TC_MARK(i)                                                                         \
+    do {                                                                                   \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {                       \
+            unsigned long long t_;                                                         \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                         \
+            g_tc_trace[i] = t_;                                                            \
+        }                                                                                  \
+    } while (0)
+#else
+#define TC_MARK(i) do {} while (0)
+#endif
+
 struct TcParams {
     int mpad;        // UMMA N: rows of X rounded up to 16 (16..256)
     int tmem_cols;   // power of two >= max(32, mpad)
@@ -115,6 +132,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     uint64_t *empty = full + S;
     uint64_t *acc_full = empty + S;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+    float *bn_sm = reinterpret_cast<float *>(tmem_slot + 2);  // [4][mpad]: mean, rs, scale, bias of this row chunk
 
     cg::cluster_group cluster = cg::this_cluster();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,6 +146,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     const int my_kt = max(0, kt_end - kt_begin);
 
     pdl_trigger();
+    if (threadIdx.x == 0) TC_MARK(0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
@@ -145,6 +164,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_MARK(1);
 
     if (warp == 4) {
         // ===== TMA producer =====
@@ -160,7 +180,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                 tma_load_3d(w_sm + it * TC_W_BYTES, &mapW, &full[it], n0, k0, bw, pol_w);
                 tma_load_3d(w_sm + it * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[it], n0 + 64, k0, bw, pol_w);
             }
+            TC_MARK(2);
             pdl_wait();
+            TC_MARK(3);
             for (int it = 0; it < pre; ++it)
                 tma_load_3d(x_sm + it * p.x_bytes, &mapX, &full[it], (kt_begin + it) * TC_BK, m0, bx, pol_x);
             for (int it = pre; it < my_kt; ++it) {
@@ -181,6 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             for (int it = 0; it < my_kt; ++it) {
                 const int s = it % S;
                 mbar_wait(&full[s], (it / S) & 1);
+                if (it == 0) TC_MARK(4);
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < TC_BK / 16; ++kk) {
@@ -194,6 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                 tc_commit(&empty[s]);  // stage reusable once these MMAs have read it
             }
             tc_commit(acc_full);  // accumulator complete (also fires when my_kt == 0)
+            TC_MARK(5);
         }
         __syncwarp();
     }
@@ -201,15 +225,28 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     // ===== epilogue: warps 0..3 own TMEM lanes [32w, 32w+32) = output columns n0 + 32w + lane =====
     const T *bias = g.bias ? (const T *)g.bias + (int64_t)bz * g.bias_sb : nullptr;
     T *C = (T *)g.C + (int64_t)bz * g.m * g.n;
+    const bool tail = g.bn_scale != nullptr || g.residual != nullptr || g.post_relu;
     if (warp < 4) {
         pdl_wait();
+        if (g.bn_scale) {
+            for (int r = threadIdx.x; r < p.mpad; r += 128) {
+                const int m = min(m0 + r, g.m - 1);
+                bn_sm[r] = g.bn_mean[m];
+                bn_sm[p.mpad + r] = bn_rs(g.bn_var[m], g.bn_eps);
+                bn_sm[2 * p.mpad + r] = g.bn_scale[m];
+                bn_sm[3 * p.mpad + r] = g.bn_bias[m];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         mbar_wait(acc_full, 0);
+        if (threadIdx.x == 0) TC_MARK(6);
         tc_fence_after();
         const int nl = warp * 32 + lane;  // column inside the tile
         const int gn = n0 + nl;
         // element (m, gn) lives at C[c_off + m * c_ld] (plain row-major, or the conv scatter of GemmArgs::c_block)
         const int64_t c_ld = g.c_block ? g.c_block : g.n;
         const int64_t c_off = g.c_block ? (int64_t)(gn / g.c_block) * g.c_block_stride + gn % g.c_block : gn;
+        const int mode = (bias || (g.act & 0xff)) ? 2 : tail ? 1 : 0;  // (launch_tc_t refuses bias/act together with a tail)
         for (int c0 = 0; c0 < p.mpad; c0 += 16) {
             uint32_t v[16];
             if (my_kt > 0) {
@@ -222,21 +259,49 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 16; ++j) red[(c0 + j) * TC_BN + nl] = __uint_as_float(v[j]);
             } else if (gn < g.n) {
+                // three specialisations of the per-element tail, chosen by CTA-uniform flags, so the common cases do
+                // not carry the generic bias / activation code (that alone made the epilogue instruction-bound)
+                const int rows = min(16, g.m - (m0 + c0));  // valid rows of this 16-row group
+                T *cp = C + c_off + (int64_t)(m0 + c0) * c_ld;
+                if (mode == 0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int m = m0 + c0 + j;
-                    if (m < g.m) {
+                    for (int j = 0; j < 16; ++j)
+                        if (j < rows) cp[(int64_t)j * c_ld] = from_f<T>(__uint_as_float(v[j]));
+                } else if (mode == 1) {
+                    float resv[16];
+                    if (g.residual) {  // all 16 residual loads in flight before the first (possibly aliasing) store
+                        const T *rp = (const T *)g.residual + (int64_t)bz * g.m * g.n + c_off + (int64_t)(m0 + c0) * c_ld;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) resv[j] = j < rows ? to_f(rp[(int64_t)j * c_ld]) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int r = c0 + j;
+                        float f = round_t<T>(__uint_as_float(v[j]));  // the Conv output as the separate kernel stores it
+                        if (g.bn_scale)
+                            f = round_t<T>(bn_apply(f, bn_sm[r], bn_sm[p.mpad + r], bn_sm[2 * p.mpad + r], bn_sm[3 * p.mpad + r]));
+                        if (g.residual) f = round_t<T>(f + resv[j]);
+                        if (g.post_relu) f = fmaxf(f, 0.f);
+                        if (j < rows) cp[(int64_t)j * c_ld] = from_f<T>(f);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j >= rows) break;
+                        const int m = m0 + c0 + j;
                         float f = __uint_as_float(v[j]);
                         if (bias) {
                             if (g.act & ITB_ACT_ROUND_BEFORE_BIAS) f = round_t<T>(f);
                             f += to_f(bias[m * g.bias_sm + gn * g.bias_sn]);
                         }
-                        C[c_off + (int64_t)m * c_ld] = from_f<T>(gemm_act(g.act, f));
+                        f = gemm_act(g.act, f);
+                        cp[(int64_t)j * c_ld] = from_f<T>(f);
                     }
                 }
             }
         }
         tc_fence_before();
+        if (threadIdx.x == 0) TC_MARK(7);
     }
     if (nsplit > 1) {
         cluster.sync();
@@ -264,6 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        if (lane == 0) TC_MARK(8);
     }
 }
 
@@ -281,7 +347,8 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
     p.ktiles = (g.k + TC_BK - 1) / TC_BK;
     // split-K only where the partial tile is small (decode regime); clusters of <= 8 CTAs
     int splitk = 1;
-    if (p.mpad <= 64 && g.batch == 1) {
+    const bool tail = g.bn_scale || g.residual || g.post_relu;  // the fused conv tail lives in the direct epilogue only
+    if (p.mpad <= 64 && g.batch == 1 && !tail && !g.no_splitk) {
         splitk = (2 * kNumSMs) / tiles_n;
         splitk = std::max(1, std::min(splitk, 8));
         splitk = std::min(splitk, std::max(1, p.ktiles / 4));
@@ -290,10 +357,14 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
     splitk = (p.ktiles + p.ktiles_per_split - 1) / p.ktiles_per_split;
     p.red_bytes = splitk > 1 ? p.mpad * TC_BN * 4 : 0;
     const int stage_bytes = TC_W_BYTES + p.x_bytes;
-    const int budget = (p.mpad <= 64 ? 104 : 200) * 1024;  // two CTAs per SM in the decode regime
-    p.stages = std::max(2, std::min(8, (budget - p.red_bytes - 2048) / stage_bytes));
+    static const int budget_kb = [] {
+        const char *e = std::getenv("ITB_TC_SMEM_KB");
+        return e && e[0] ? std::atoi(e) : 0;
+    }();
+    const int budget = (budget_kb ? budget_kb : p.mpad <= 64 ? 104 : 200) * 1024;  // two CTAs per SM in the decode regime
+    p.stages = std::max(2, std::min(8, (budget - p.red_bytes - 2048 - 16 * p.mpad) / stage_bytes));
     p.idesc = umma_idesc_f16(is_bf16 ? 1 : 0, /*A = W^T, MN-major*/ 1, /*B = X, K-major*/ 0, 128, p.mpad);
-    const int smem = p.stages * stage_bytes + p.red_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+    const int smem = p.stages * stage_bytes + p.red_bytes + (2 * p.stages + 1) * 8 + 16 + 4 * p.mpad * 4 + 1024;
 
     CUtensorMap mapW, mapX;
     if (!make_tma_3d_b16(&mapW, g.B, p.b_batched ? (uint64_t)g.batch : 1, (uint64_t)g.k, (uint64_t)g.n, (uint64_t)g.n,
@@ -327,6 +398,20 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapW, mapX, g, p);
     ITB_CHECK(e == cudaSuccess, "matmul(tcgen05): launch failed: %s", cudaGetErrorString(e));
     itb::count_launch();
+#ifdef ITB_TC_TRACE
+    {
+        static int n = 0;
+        if (++n % 16 == 0) {
+            cudaStreamSynchronize(st);
+            unsigned long long h[16];
+            cudaMemcpyFromSymbol(h, g_tc_trace, sizeof(h));
+            fprintf(stderr, "tc trace m=%d n=%d k=%d grid=(%d,%d,%d) stages=%d:", g.m, g.n, g.k, tiles_n, splitk,
+                    (int)(g.batch * p.m_chunks), p.stages);
+            for (int i = 1; i <= 8; ++i) fprintf(stderr, " t%d=%+.2fus", i, ((double)h[i] - (double)h[0]) / 1e3);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     return 0;
 }
 
@@ -341,6 +426,7 @@ int launch_gemm_tc(int dtype, const GemmArgs &g, cudaStream_t st) {
         if (g.stride_a != 0 && g.stride_a != (int64_t)g.m * g.k) return -1;
         if ((int64_t)g.batch * ((g.m + 255) / 256) > 65535) return -1;
     }
+    if ((g.bn_scale || g.residual || g.post_relu) && (g.bias || (g.act & 0xff))) return -1;  // tail excludes bias / act
     if (dtype == ITB_BF16) return launch_tc_t<__nv_bfloat16>(g, st, true);
     return launch_tc_t<__half>(g, st, false);
 }

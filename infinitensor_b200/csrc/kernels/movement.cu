@@ -226,18 +226,36 @@ __global__ void __launch_bounds__(256) pool2d_kernel(int is_max, const T *__rest
     }
 }
 
-template <typename T>
+// y = scale[c] * (x - mean[c]) / sqrt(var[c] + eps) + bias[c] over NCHW (batch_norm.cc:9-69 semantics; fp32 parameters).
+// VEC: one thread = one 16-byte vector inside a single (n, c) plane (HW % V == 0), one channel lookup per vector.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) batchnorm_kernel(const T *__restrict__ x, const float *__restrict__ mean,
                                                         const float *__restrict__ var,
                                                         const float *__restrict__ scale,
                                                         const float *__restrict__ bias, T *__restrict__ y,
-                                                        int64_t n, int C, int64_t HW, float eps) {
+                                                        int64_t n, int C, int64_t HW, float eps, int relu) {
     pdl_trigger();
     pdl_wait();
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)((i / HW) % C);
-        float rs = 1.0f / sqrtf(var[c] + eps);
-        y[i] = from_f<T>(scale[c] * (to_f(x[i]) - mean[c]) * rs + bias[c]);
+    constexpr int V = VEC ? Vec16<T>::N : 1;
+    const int64_t nv = n / V;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(((i * V) / HW) % C);
+        const float rs = bn_rs(var[c], eps), sc = scale[c], mu = mean[c], bi = bias[c];
+        if (VEC) {
+            const Vec16<T> in = ld16(x + i * V);
+            Vec16<T> out;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float v = bn_apply(to_f(in.v[j]), mu, rs, sc, bi);
+                if (relu) v = round_t<T>(v) > 0.f ? v : 0.f;
+                out.v[j] = from_f<T>(v);
+            }
+            st16(y + i * V, out);
+        } else {
+            float v = bn_apply(to_f(x[i]), mu, rs, sc, bi);
+            if (relu) v = round_t<T>(v) > 0.f ? v : 0.f;
+            y[i] = from_f<T>(v);
+        }
     }
 }
 
@@ -484,15 +502,31 @@ extern "C" int it_b200_pool2d(int dtype, int is_max, const void *x, void *y, int
     return 0;
 }
 
-extern "C" int it_b200_batchnorm(int dtype, const void *x, const float *mean, const float *var,
-                                 const float *scale, const float *bias, void *y, int N, int C, int64_t HW,
-                                 float eps, void *stream) {
+static int batchnorm_impl(int dtype, const void *x, const float *mean, const float *var, const float *scale,
+                          const float *bias, void *y, int N, int C, int64_t HW, float eps, int relu, void *stream) {
     int64_t n = (int64_t)N * C * HW;
     if (n == 0) return 0;
     ITB_DISPATCH_FLOAT(dtype, "batchnorm", {
-        launch_k(batchnorm_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const T *)x, mean, var, scale, bias,
-                                                                               (T *)y, n, C, HW, eps);
+        constexpr int V = Vec16<T>::N;
+        if (HW % V == 0 && aligned16(x) && aligned16(y))
+            launch_k(batchnorm_kernel<T, true>, dim3(grid_for(n / V, 256)), dim3(256), 0, (cudaStream_t)stream, (const T *)x,
+                     mean, var, scale, bias, (T *)y, n, C, HW, eps, relu);
+        else
+            launch_k(batchnorm_kernel<T, false>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const T *)x,
+                     mean, var, scale, bias, (T *)y, n, C, HW, eps, relu);
     });
     ITB_LAUNCH_CHECK("batchnorm");
     return 0;
+}
+
+extern "C" int it_b200_batchnorm(int dtype, const void *x, const float *mean, const float *var,
+                                 const float *scale, const float *bias, void *y, int N, int C, int64_t HW,
+                                 float eps, void *stream) {
+    return batchnorm_impl(dtype, x, mean, var, scale, bias, y, N, C, HW, eps, 0, stream);
+}
+
+extern "C" int it_b200_batchnorm_relu(int dtype, const void *x, const float *mean, const float *var,
+                                      const float *scale, const float *bias, void *y, int N, int C, int64_t HW,
+                                      float eps, void *stream) {
+    return batchnorm_impl(dtype, x, mean, var, scale, bias, y, N, C, HW, eps, 1, stream);
 }

@@ -236,6 +236,41 @@ def batch_norm(x, mean, var, scale, bias, eps, dt=F32):
     return host(out)
 
 
+def batch_norm_relu(x, mean, var, scale, bias, eps, dt=F32):
+    xd = dev(x, dt)
+    ms = [dev(np.asarray(v, np.float32)) for v in (mean, var, scale, bias)]
+    out = torch.empty_like(xd)
+    N, C = x.shape[:2]
+    HW = int(np.prod(x.shape[2:])) if x.ndim > 2 else 1
+    L.check(L.lib.it_b200_batchnorm_relu(dt, ptr(xd), ptr(ms[0]), ptr(ms[1]), ptr(ms[2]), ptr(ms[3]), ptr(out), N, C, HW,
+                                         eps, stream()))
+    sync()
+    return host(out)
+
+
+def conv2d_fused(x, w, ph, pw, sh, sw, dh, dw, bn, eps, residual, relu, dt=F16):
+    """Returns the fused result, or None when the C-ABI reports the shape as not taken (rc 2)."""
+    xd, wd = dev(x, dt), dev(w, dt)
+    N, C, H, W = x.shape
+    F, Cg, R, S = w.shape
+    groups = C // Cg
+    OH = (H + 2 * ph - dh * (R - 1) - 1) // sh + 1
+    OW = (W + 2 * pw - dw * (S - 1) - 1) // sw + 1
+    y = torch.empty((N, F, OH, OW), dtype=xd.dtype, device="cuda")
+    ms = [dev(np.asarray(v, np.float32)) for v in bn] if bn is not None else [None] * 4
+    rd = dev(residual, dt) if residual is not None else None
+    wsb = L.lib.it_b200_conv2d_workspace(dt, N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups)
+    ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device="cuda")
+    rc = L.lib.it_b200_conv2d_fused(dt, ptr(xd), ptr(wd), ptr(y), N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups,
+                                    ptr(ms[0]), ptr(ms[1]), ptr(ms[2]), ptr(ms[3]), eps, ptr(rd), int(relu), ptr(ws),
+                                    int(wsb), stream())
+    if rc == 2:
+        return None
+    L.check(rc)
+    sync()
+    return host(y)
+
+
 def matmul(a, b, bias=None, transA=False, transB=False, dt=F32, act=0):
     ad, bd = dev(a, dt), dev(b, dt)
     m = a.shape[-1] if transA else a.shape[-2]

@@ -182,3 +182,32 @@ def test_fused_schedule_matches_unfused(dtype, monkeypatch):
         assert any(s.startswith("MatMulGroup") for s in sched)
     a, b = G.from_storage(got, dtype).astype(np.float64), G.from_storage(base, dtype).astype(np.float64)
     assert np.abs(a - b).max() <= (0 if dtype == F32 else 2.0 ** -6 * np.abs(b).max())
+
+
+def _resnet_once(cfg, env, monkeypatch):
+    from infinitensor_b200 import backend as B, graphs as G
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rt = B.CudaRuntime(0)
+    h = B.GraphHandler(rt)
+    g = G.build_resnet50(h, cfg)
+    sched = h.schedule()
+    h.data_malloc()
+    G.fill_resnet_weights_host(g)
+    x = np.random.default_rng(3).standard_normal((cfg.batch, 3, cfg.image, cfg.image)).astype(np.float32)
+    g.input.copyin_numpy(G.to_storage(x, cfg.dtype))
+    h.run_with_cudagraph()
+    h.run_with_cudagraph()
+    return sched, g.out.copyout_numpy().copy()
+
+
+def test_resnet_conv_tail_fusion_is_bit_identical(monkeypatch):
+    """Full-width ResNet-50 (reduced image / batch): Conv+BatchNorm(+Add)(+Relu) steps on the tcgen05 epilogue produce the
+    very bits of the one-kernel-per-operator schedule."""
+    from infinitensor_b200 import graphs as G
+    cfg = G.ResNetConfig(batch=4, image=64, dtype=F16)
+    s1, fused = _resnet_once(cfg, {"ITB_FUSION_MASK": "127"}, monkeypatch)
+    s0, plain = _resnet_once(cfg, {"ITB_FUSION_MASK": "63"}, monkeypatch)
+    assert sum(s.startswith("ConvBnAct") for s in s1) == 53 and not any(s.startswith("ConvBnAct") for s in s0)
+    assert np.isfinite(G.from_storage(fused, F16)).all()
+    assert np.array_equal(fused, plain)

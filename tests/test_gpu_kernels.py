@@ -367,6 +367,46 @@ def test_conv_resnet_shapes_parity(K, dt):
         close(K.conv2d(x, w, *args, dt=dt), oracle.conv2d(x, w, *args, dt=dt), tol, tol)
 
 
+@pytest.mark.parametrize("dt", [F16, BF16])
+def test_conv_fused_tail_bit_identical(K, dt):
+    """Conv -> BatchNorm -> [+ residual] -> [ReLU] in the tcgen05 epilogue equals the separate kernels bit for bit, and the
+    oracle chain within the conv tolerance; shapes off the tensor-core path answer rc 2 (nothing launched)."""
+    tol = {F16: 2e-2, BF16: 1.5e-1}[dt]
+    cases = [((2, 64, 56, 56), (256, 64, 1, 1), (0, 0, 1, 1, 1, 1)),      # batched 1x1, no repack
+             ((2, 128, 28, 28), (128, 128, 3, 3), (1, 1, 1, 1, 1, 1)),   # folded im2col
+             ((8, 256, 14, 14), (300, 256, 3, 3), (1, 1, 2, 2, 1, 1)),   # P = 49, F > 256 (two row chunks, ragged)
+             ((8, 512, 7, 7), (128, 512, 1, 1), (0, 0, 1, 1, 1, 1))]     # 1x1 with P % 8 != 0 -> folded
+    for ci, (xs, ws, args) in enumerate(cases):
+        x, w = rnd(xs, 50 + ci, dt), rnd(ws, 60 + ci, dt, 0.05)
+        F = ws[0]
+        rng = np.random.default_rng(70 + ci)
+        bn = (rng.standard_normal(F).astype(np.float32) * 0.1, rng.uniform(0.5, 1.5, F).astype(np.float32),
+              rng.uniform(0.5, 1.5, F).astype(np.float32), rng.standard_normal(F).astype(np.float32) * 0.1)
+        conv = K.conv2d(x, w, *args, dt=dt)
+        res = rnd(conv.shape, 80 + ci, dt)
+        for use_res, relu in [(False, False), (False, True), (True, True)]:
+            got = K.conv2d_fused(x, w, *args, bn, 1e-5, res if use_res else None, relu, dt=dt)
+            assert got is not None
+            ref = K.batch_norm(conv, *bn, 1e-5, dt=dt)
+            ora = oracle.batch_norm(oracle.conv2d(x, w, *args, dt=dt), *bn, 1e-5, dt)
+            if use_res:
+                ref = K.binary("add", ref, res, dt=dt)
+                ora = oracle.binary("add", ora, res, dt)
+            if relu:
+                ref = np.maximum(ref, 0)
+                ora = None if ora is None else np.maximum(ora, 0)
+            assert np.array_equal(got, ref), f"case {ci} res={use_res} relu={relu}: max diff {np.abs(got - ref).max()}"
+            if ora is not None:
+                close(got, ora, tol, tol)
+    # fp32 / grouped / tiny-K convs are not taken: rc 2, the runtime runs the operators one by one
+    x, w = rnd((2, 3, 32, 32), 90, dt), rnd((8, 3, 7, 7), 91, dt, 0.2)
+    z = np.zeros(8, np.float32)
+    assert K.conv2d_fused(x, w, 3, 3, 2, 2, 1, 1, (z, z + 1, z + 1, z), 1e-5, None, True, dt=dt) is None
+    x = rnd((2, 16, 8, 8), 92, dt)
+    close(K.batch_norm_relu(x, *[np.full(16, v, np.float32) for v in (0.1, 1.3, 0.9, -0.2)], 1e-5, dt=dt),
+          np.maximum(K.batch_norm(x, *[np.full(16, v, np.float32) for v in (0.1, 1.3, 0.9, -0.2)], 1e-5, dt=dt), 0), 0, 0)
+
+
 @pytest.mark.parametrize("dt", [F32, F16, BF16])
 def test_conv_parity(K, dt):
     tol = {F32: 1e-4, F16: 4e-3, BF16: 3e-2}[dt]

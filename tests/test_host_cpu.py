@@ -233,6 +233,27 @@ if __name__ == "__main__" and "--tp-worker" in sys.argv:
     _tp_worker()
 
 
+def test_conv_bn_act_schedule(B, monkeypatch):
+    """ResNet-50: every Conv takes its BatchNorm (+ residual Add) (+ Relu) into one ConvBnAct step; mask bit 6 off -> 1:1."""
+    import collections
+    from infinitensor_b200 import graphs as G
+    rt = B.HostPlanRuntime()
+    h = B.GraphHandler(rt)
+    G.build_resnet50(h, G.ResNetConfig(batch=2, image=64))
+    sc = h.schedule()
+    kinds = collections.Counter(s.split(":")[0] for s in sc)
+    assert kinds["ConvBnAct"] == 53
+    assert sc.count("ConvBnAct:Conv+BatchNormalization+Relu") == 1 + 16 * 2          # stem + conv1/conv2 of 16 blocks
+    assert sc.count("ConvBnAct:Conv+BatchNormalization+Add+Relu") == 16              # conv3 of every block
+    assert sc.count("ConvBnAct:Conv+BatchNormalization") == 4                        # the four downsample branches
+    assert not any(s.startswith("Single:BatchNormalization") or s == "Single:Relu" or s == "Single:Add" for s in sc)
+    h.data_malloc()
+    monkeypatch.setenv("ITB_FUSION_MASK", "63")
+    h2 = B.GraphHandler(rt)
+    G.build_resnet50(h2, G.ResNetConfig(batch=2, image=64))
+    assert not any(s.startswith("ConvBnAct") for s in h2.schedule())
+
+
 def test_fused_schedule_and_alias_plan(B, monkeypatch):
     """The execution schedule groups q/k/v and gate/up MatMuls, folds the residual Adds and Silu*Mul, and turns
     the decode graph's Reshape / size-1 Transpose ops into storage aliases; ITB_NO_FUSION=1 gives the 1:1 order."""

@@ -14,6 +14,7 @@ SHAPES = [(16, 4096, 4096), (16, 4096, 11008), (16, 11008, 4096), (16, 4096, 320
 
 
 def run(impl, m, k, n, reps=40, nbuf=12):
+    nbuf = max(2, min(nbuf, int(1.5e9 / (k * n * 2))))
     os.environ["ITB_GEMM_IMPL"] = impl
     ws = [torch.randn(k, n, device="cuda", dtype=torch.bfloat16) * 0.02 for _ in range(nbuf)]
     x = torch.randn(m, k, device="cuda", dtype=torch.bfloat16)
@@ -38,6 +39,8 @@ def run(impl, m, k, n, reps=40, nbuf=12):
 
 
 if __name__ == "__main__":
+    if os.environ.get("GEMM_BENCH_SHAPES"):  # "m,k,n;m,k,n;..."
+        SHAPES = [tuple(int(v) for v in t.split(",")) for t in os.environ["GEMM_BENCH_SHAPES"].split(";")]
     impls = sys.argv[1:] or ["skinny", "tc", "streamk"]
     print(f"{'shape':>22s} " + " ".join(f"{i:>22s}" for i in impls))
     for (m, k, n) in SHAPES:
