@@ -75,6 +75,7 @@ template <typename T, bool FOLD, bool VEC>
 __global__ void __launch_bounds__(256) im2col_kernel(const T *__restrict__ x, T *__restrict__ col, int64_t total,
                                                      int NB, int C, int H, int W, int R, int S, int OH, int OW, int ph,
                                                      int pw, int sh, int sw, int dh, int dw) {
+    // (FOLD: `total` may cover more than C*R*S rows -- the extra rows, c >= C, are the zero padding of K to a multiple of 8)
     pdl_trigger();
     pdl_wait();
     const int P = OH * OW, Kc = C * R * S;
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T *__restrict__ x, T 
             for (int e = 0; e < V; ++e) {
                 const int ih = oh * sh - ph + r * dh, iw = ow * sw - pw + s * dw;
                 T v = from_f<T>(0.f);
-                if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((int64_t)n * C + c) * H + ih) * W + iw];
+                if (c < C && ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((int64_t)n * C + c) * H + ih) * W + iw];
                 out[e] = v;
                 if (++ow == OW) {
                     ow = 0;
@@ -117,9 +118,22 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T *__restrict__ x, T 
             int oh = (int)(p / OW), ow = (int)(p % OW);
             int ih = oh * sh - ph + r * dh, iw = ow * sw - pw + s * dw;
             T v = from_f<T>(0.f);
-            if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((int64_t)n * C + c) * H + ih) * W + iw];
+            if (c < C && ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((int64_t)n * C + c) * H + ih) * W + iw];
             col[i] = v;
         }
+    }
+}
+
+// filters [F, Kc] -> [F, Kp] with zero fill (Kc not a multiple of 8, e.g. the 3x7x7 stem of ResNet)
+template <typename T>
+__global__ void __launch_bounds__(256) pad_rows_kernel(const T *__restrict__ w, T *__restrict__ out, int64_t total, int Kc,
+                                                       int Kp) {
+    pdl_trigger();
+    pdl_wait();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = i / Kp;
+        const int k = (int)(i - f * Kp);
+        out[i] = k < Kc ? w[f * Kc + k] : from_f<T>(0.f);
     }
 }
 
@@ -200,7 +214,8 @@ static bool conv_is_1x1_direct(int R, int S, int ph, int pw, int sh, int sw) {
 
 // the folded im2col GEMM ([F, Kc] x [Kc, N*P], scattered back to NCHW by the epilogue) runs on the tcgen05 kernel
 static bool conv_fold_ok(int dtype, int N, int64_t P, int64_t Kc, int F, int groups) {
-    return (dtype == ITB_F16 || dtype == ITB_BF16) && groups == 1 && (N * P) % 8 == 0 && Kc % 8 == 0 && Kc >= 64 &&
+    // (Kc itself need not be a multiple of 8: the im2col rows and a copy of the filters are zero-padded to Kp = ceil8(Kc))
+    return (dtype == ITB_F16 || dtype == ITB_BF16) && groups == 1 && (N * P) % 8 == 0 && ((Kc + 7) & ~7ll) >= 64 &&
            N * P >= 64 && N * P < (1ll << 31) && F >= 1;
 }
 
@@ -209,8 +224,12 @@ extern "C" int64_t it_b200_conv2d_workspace(int dtype, int N, int C, int H, int 
     int OH, OW;
     conv_out(H, W, R, S, ph, pw, sh, sw, dh, dw, OH, OW);
     const int64_t P = (int64_t)OH * OW, Kc = (int64_t)C * R * S;
-    if (conv_is_1x1_direct(R, S, ph, pw, sh, sw) && (P % 8 == 0 || !conv_fold_ok(dtype, N, P, Kc, F, groups))) return 0;
-    return (int64_t)N * Kc * P * dtype_size(dtype);
+    const bool foldable = conv_fold_ok(dtype, N, P, Kc, F, groups);
+    if (conv_is_1x1_direct(R, S, ph, pw, sh, sw) && (P % 8 == 0 || !foldable)) return 0;
+    const int64_t Kp = foldable ? (Kc + 7) & ~7ll : Kc;
+    int64_t bytes = (int64_t)N * Kp * P * dtype_size(dtype);
+    if (Kp != Kc) bytes = ((bytes + 255) & ~255ll) + (int64_t)F * Kp * dtype_size(dtype);  // + zero-padded filter copy
+    return bytes;
 }
 
 struct ConvTail {
@@ -238,6 +257,7 @@ static int conv_impl(int dtype, const void *x, const void *w, void *y, int N, in
     // otherwise fold the batch into the GEMM columns when that makes the matrix TMA-legal (tensor-core path).
     const bool direct_tc = direct && P % 8 == 0;
     const bool fold = !direct_tc && conv_fold_ok(dtype, N, P, Kc, F, groups);
+    const int64_t Kp = fold ? (Kc + 7) & ~7ll : Kc;  // GEMM K (zero-padded when folded)
     auto with_tail = [&](GemmArgs &g) {
         g.bn_mean = tail.mean;
         g.bn_var = tail.var;
@@ -252,14 +272,14 @@ static int conv_impl(int dtype, const void *x, const void *w, void *y, int N, in
         const bool tc_batched = direct_tc && groups == 1 && (dtype == ITB_F16 || dtype == ITB_BF16) && Kc % 8 == 0 &&
                                 Kc >= 64 && P >= 64 && aligned16(x) && aligned16(w) && (int64_t)N * ((F + 255) / 256) <= 65535;
         if (!fold && !tc_batched) return 2;
-        if (fold && (!aligned16(w) || !aligned16(workspace))) return 2;
+        if (fold && ((Kp == Kc && !aligned16(w)) || !aligned16(workspace))) return 2;
     }
     const void *col = x;
     if (!direct || fold) {
         int64_t need = it_b200_conv2d_workspace(dtype, N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups);
         ITB_CHECK(workspace && workspace_bytes >= need, "conv: workspace %lld < %lld bytes",
                   (long long)workspace_bytes, (long long)need);
-        int64_t total = (int64_t)N * Kc * P;
+        int64_t total = (int64_t)N * Kp * P;
         const int64_t rowlen = fold ? (int64_t)N * P : P;
         ITB_DISPATCH_FLOAT(dtype, "conv(im2col)", {
             auto go = [&](auto kern, int64_t items) {
@@ -281,16 +301,27 @@ static int conv_impl(int dtype, const void *x, const void *w, void *y, int N, in
     }
     if (fold) {
         // y[n][f][p] = sum_kc W[f, kc] . col[kc, n*P + p]
+        const void *wmat = w;
+        if (Kp != Kc) {
+            char *wpad = (char *)workspace + (((int64_t)N * Kp * P * es + 255) & ~255ll);
+            const int64_t wt = (int64_t)F * Kp;
+            ITB_DISPATCH_FLOAT(dtype, "conv(pad filters)", {
+                launch_k(pad_rows_kernel<T>, dim3(grid_for(wt, 256)), dim3(256), 0, st, (const T *)w, (T *)wpad, wt, (int)Kc,
+                         (int)Kp);
+            });
+            ITB_LAUNCH_CHECK("conv(pad filters)");
+            wmat = wpad;
+        }
         GemmArgs g{};
-        g.A = w;
+        g.A = wmat;
         g.B = col;
         g.C = y;
         g.batch = 1;
         g.m = F;
         g.n = (int)(N * P);
-        g.k = (int)Kc;
-        g.stride_a = (int64_t)F * Kc;
-        g.stride_b = Kc * N * P;
+        g.k = (int)Kp;
+        g.stride_a = (int64_t)F * Kp;
+        g.stride_b = Kp * N * P;
         g.c_block = (int)P;
         g.c_block_stride = (int64_t)F * P;
         g.no_splitk = 1;

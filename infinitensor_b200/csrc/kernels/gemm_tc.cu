@@ -30,7 +30,8 @@ namespace itb {
 
 constexpr int TC_BN = 128, TC_BK = 64;
 constexpr int TC_W_BYTES = TC_BN * TC_BK * 2;  // 16 KB: two [64k x 64n] swizzled boxes
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                      // two warps per TMEM lane quadrant, each takes half of the accumulator columns
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;  // + TMA producer warp + MMA issuer warp
 
 // ---- tcgen05 PTX wrappers -------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
@@ -115,6 +116,7 @@ struct TcParams {
     int m_chunks;    // ceil(M / mpad): grid.z = batch * m_chunks
     int a_batched;   // X has a batch dimension (stride_a != 0); otherwise it is broadcast over the batch
     int b_batched;   // same for W
+    int w_kmajor;    // trans_b: W is stored [N, K] (ONNX Gemm transB): one [128 n x 64 k] K-major box per stage
     uint32_t idesc;
 };
 
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     uint64_t *empty = full + S;
     uint64_t *acc_full = empty + S;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
-    float *bn_sm = reinterpret_cast<float *>(tmem_slot + 2);  // [4][mpad]: mean, rs, scale, bias of this row chunk
+    float *bn_sm = reinterpret_cast<float *>(tmem_slot + 2);  // float4[mpad]: {mean, rs, scale, bias} of this row chunk (16-B aligned)
 
     cg::cluster_group cluster = cg::this_cluster();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,8 +157,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    if (warp == 4 && lane == 0) {
+    if (warp == TC_EPI_WARPS + 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == TC_EPI_WARPS && lane == 0) {
         tma_prefetch_desc(&mapW);
         tma_prefetch_desc(&mapX);
     }
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) TC_MARK(1);
 
-    if (warp == 4) {
+    if (warp == TC_EPI_WARPS) {
         // ===== TMA producer =====
         if (lane == 0) {
             const uint64_t pol_w = l2_policy_evict_first();
@@ -177,8 +179,12 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             for (int it = 0; it < pre; ++it) {
                 mbar_expect_tx(&full[it], TC_W_BYTES + p.x_bytes);
                 const int k0 = (kt_begin + it) * TC_BK;
-                tma_load_3d(w_sm + it * TC_W_BYTES, &mapW, &full[it], n0, k0, bw, pol_w);
-                tma_load_3d(w_sm + it * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[it], n0 + 64, k0, bw, pol_w);
+                if (p.w_kmajor) {
+                    tma_load_3d(w_sm + it * TC_W_BYTES, &mapW, &full[it], k0, n0, bw, pol_w);
+                } else {
+                    tma_load_3d(w_sm + it * TC_W_BYTES, &mapW, &full[it], n0, k0, bw, pol_w);
+                    tma_load_3d(w_sm + it * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[it], n0 + 64, k0, bw, pol_w);
+                }
             }
             TC_MARK(2);
             pdl_wait();
@@ -190,13 +196,17 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                 mbar_wait(&empty[s], ((it / S) - 1) & 1);
                 mbar_expect_tx(&full[s], TC_W_BYTES + p.x_bytes);
                 const int k0 = (kt_begin + it) * TC_BK;
-                tma_load_3d(w_sm + s * TC_W_BYTES, &mapW, &full[s], n0, k0, bw, pol_w);
-                tma_load_3d(w_sm + s * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[s], n0 + 64, k0, bw, pol_w);
+                if (p.w_kmajor) {
+                    tma_load_3d(w_sm + s * TC_W_BYTES, &mapW, &full[s], k0, n0, bw, pol_w);
+                } else {
+                    tma_load_3d(w_sm + s * TC_W_BYTES, &mapW, &full[s], n0, k0, bw, pol_w);
+                    tma_load_3d(w_sm + s * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[s], n0 + 64, k0, bw, pol_w);
+                }
                 tma_load_3d(x_sm + s * p.x_bytes, &mapX, &full[s], k0, m0, bx, pol_x);
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == TC_EPI_WARPS + 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             const uint32_t w_base = smem_u32(w_sm), x_base = smem_u32(x_sm);
@@ -209,7 +219,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                 for (int kk = 0; kk < TC_BK / 16; ++kk) {
                     // A = W tile, MN-major: 64-column groups 8 KB apart (LBO), 8-row k groups 1 KB apart (SBO);
                     //     one k16 step = 16 rows x 128 B = 2 KB
-                    const uint64_t a_desc = umma_desc_sw128(w_base + s * TC_W_BYTES + kk * 2048, TC_W_BYTES / 2, 1024);
+                    // (trans_b: the tile is [128 n rows x 128 B of k], K-major like X: 8-row groups 1 KB apart, k16 = +32 B)
+                    const uint64_t a_desc = p.w_kmajor ? umma_desc_sw128(w_base + s * TC_W_BYTES + kk * 32, 0, 1024)
+                                                       : umma_desc_sw128(w_base + s * TC_W_BYTES + kk * 2048, TC_W_BYTES / 2, 1024);
                     // B = X tile, K-major: 8-row groups 1 KB apart (SBO); one k16 step = 32 B inside the 128 B row
                     const uint64_t b_desc = umma_desc_sw128(x_base + s * p.x_bytes + kk * 32, 0, 1024);
                     tc_mma_f16(tmem_base, a_desc, b_desc, p.idesc, (it > 0 || kk > 0) ? 1u : 0u);
@@ -226,31 +238,34 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     const T *bias = g.bias ? (const T *)g.bias + (int64_t)bz * g.bias_sb : nullptr;
     T *C = (T *)g.C + (int64_t)bz * g.m * g.n;
     const bool tail = g.bn_scale != nullptr || g.residual != nullptr || g.post_relu;
-    if (warp < 4) {
+    if (warp < TC_EPI_WARPS) {
         pdl_wait();
         if (g.bn_scale) {
-            for (int r = threadIdx.x; r < p.mpad; r += 128) {
+            float4 *bn4 = reinterpret_cast<float4 *>(bn_sm);  // {mean, rs, scale, bias} of row r
+            for (int r = threadIdx.x; r < p.mpad; r += TC_EPI_WARPS * 32) {
                 const int m = min(m0 + r, g.m - 1);
-                bn_sm[r] = g.bn_mean[m];
-                bn_sm[p.mpad + r] = bn_rs(g.bn_var[m], g.bn_eps);
-                bn_sm[2 * p.mpad + r] = g.bn_scale[m];
-                bn_sm[3 * p.mpad + r] = g.bn_bias[m];
+                bn4[r] = make_float4(g.bn_mean[m], bn_rs(g.bn_var[m], g.bn_eps), g.bn_scale[m], g.bn_bias[m]);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
         }
         mbar_wait(acc_full, 0);
         if (threadIdx.x == 0) TC_MARK(6);
         tc_fence_after();
-        const int nl = warp * 32 + lane;  // column inside the tile
+        // warp w reads TMEM lanes [32 (w & 3), +32) (the hardware binds a warp to that quadrant) = output columns
+        // n0 + 32 (w & 3) + lane; warps 0-3 take the first half of the 16-row groups (TMEM columns), warps 4-7 the second
+        const int quad = warp & 3;
+        const int groups16 = p.mpad / 16, g_split = (groups16 + 1) / 2;
+        const int c_begin = (warp < 4 ? 0 : g_split) * 16, c_end = (warp < 4 ? g_split : groups16) * 16;
+        const int nl = quad * 32 + lane;  // column inside the tile
         const int gn = n0 + nl;
         // element (m, gn) lives at C[c_off + m * c_ld] (plain row-major, or the conv scatter of GemmArgs::c_block)
         const int64_t c_ld = g.c_block ? g.c_block : g.n;
         const int64_t c_off = g.c_block ? (int64_t)(gn / g.c_block) * g.c_block_stride + gn % g.c_block : gn;
         const int mode = (bias || (g.act & 0xff)) ? 2 : tail ? 1 : 0;  // (launch_tc_t refuses bias/act together with a tail)
-        for (int c0 = 0; c0 < p.mpad; c0 += 16) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
             uint32_t v[16];
             if (my_kt > 0) {
-                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0u;
@@ -278,8 +293,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                     for (int j = 0; j < 16; ++j) {
                         const int r = c0 + j;
                         float f = round_t<T>(__uint_as_float(v[j]));  // the Conv output as the separate kernel stores it
-                        if (g.bn_scale)
-                            f = round_t<T>(bn_apply(f, bn_sm[r], bn_sm[p.mpad + r], bn_sm[2 * p.mpad + r], bn_sm[3 * p.mpad + r]));
+                        if (g.bn_scale) {
+                            const float4 bp = reinterpret_cast<const float4 *>(bn_sm)[r];
+                            f = round_t<T>(bn_apply(f, bp.x, bp.y, bp.z, bp.w));
+                        }
                         if (g.residual) f = round_t<T>(f + resv[j]);
                         if (g.post_relu) f = fmaxf(f, 0.f);
                         if (j < rows) cp[(int64_t)j * c_ld] = from_f<T>(f);
@@ -305,10 +322,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     }
     if (nsplit > 1) {
         cluster.sync();
-        if (split == 0 && warp < 4) {
+        if (split == 0 && warp < TC_EPI_WARPS) {
             const float *peers[8];
             for (int r = 0; r < nsplit; ++r) peers[r] = (const float *)cluster.map_shared_rank(red, r);
-            for (int idx = threadIdx.x; idx < p.mpad * TC_BN; idx += 128) {
+            for (int idx = threadIdx.x; idx < p.mpad * TC_BN; idx += TC_EPI_WARPS * 32) {
                 const int m = m0 + idx / TC_BN, nl = idx % TC_BN, gn = n0 + nl;
                 if (m >= g.m || gn >= g.n) continue;
                 float f = 0.f;
@@ -326,7 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     } else {
         __syncthreads();
     }
-    if (warp == 5) {
+    if (warp == TC_EPI_WARPS + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
         if (lane == 0) TC_MARK(8);
@@ -361,14 +378,21 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
         const char *e = std::getenv("ITB_TC_SMEM_KB");
         return e && e[0] ? std::atoi(e) : 0;
     }();
-    const int budget = (budget_kb ? budget_kb : p.mpad <= 64 ? 104 : 200) * 1024;  // two CTAs per SM in the decode regime
+    const int budget = (budget_kb ? budget_kb : p.mpad <= 64 ? 104 : 110) * 1024;  // two CTAs per SM: one CTA's epilogue overlaps the
+                                                                                   // other's main loop (TMEM: 2 x <= 256 columns)
     p.stages = std::max(2, std::min(8, (budget - p.red_bytes - 2048 - 16 * p.mpad) / stage_bytes));
-    p.idesc = umma_idesc_f16(is_bf16 ? 1 : 0, /*A = W^T, MN-major*/ 1, /*B = X, K-major*/ 0, 128, p.mpad);
-    const int smem = p.stages * stage_bytes + p.red_bytes + (2 * p.stages + 1) * 8 + 16 + 4 * p.mpad * 4 + 1024;
+    p.w_kmajor = g.trans_b ? 1 : 0;
+    p.idesc = umma_idesc_f16(is_bf16 ? 1 : 0, /*A = W^T: MN-major for [K,N] weights, K-major for [N,K]*/ p.w_kmajor ? 0 : 1,
+                             /*B = X, K-major*/ 0, 128, p.mpad);
+    const int smem = p.stages * stage_bytes + p.red_bytes + (2 * p.stages + 1) * 8 + 32 + 4 * p.mpad * 4 + 1024;
 
     CUtensorMap mapW, mapX;
-    if (!make_tma_3d_b16(&mapW, g.B, p.b_batched ? (uint64_t)g.batch : 1, (uint64_t)g.k, (uint64_t)g.n, (uint64_t)g.n,
-                         (uint64_t)g.stride_b, TC_BK, 64))
+    const bool w_ok = p.w_kmajor
+                          ? make_tma_3d_b16(&mapW, g.B, p.b_batched ? (uint64_t)g.batch : 1, (uint64_t)g.n, (uint64_t)g.k,
+                                            (uint64_t)g.k, (uint64_t)g.stride_b, TC_BN, TC_BK)
+                          : make_tma_3d_b16(&mapW, g.B, p.b_batched ? (uint64_t)g.batch : 1, (uint64_t)g.k, (uint64_t)g.n,
+                                            (uint64_t)g.n, (uint64_t)g.stride_b, TC_BK, 64);
+    if (!w_ok)
         ITB_FAIL("matmul(tcgen05): cuTensorMapEncodeTiled(W) failed");
     if (!make_tma_3d_b16(&mapX, g.A, p.a_batched ? (uint64_t)g.batch : 1, (uint64_t)g.m, (uint64_t)g.k, (uint64_t)g.k,
                          (uint64_t)g.stride_a, (uint32_t)p.mpad, TC_BK))
@@ -417,7 +441,7 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
 
 int launch_gemm_tc(int dtype, const GemmArgs &g, cudaStream_t st) {
     if (dtype != ITB_BF16 && dtype != ITB_F16) return -1;
-    if (g.batch < 1 || g.trans_a || g.trans_b || g.m < 1) return -1;
+    if (g.batch < 1 || g.trans_a || g.m < 1) return -1;
     if (g.n % 8 != 0 || g.k % 8 != 0 || g.n < 64 || g.k < 64) return -1;
     if (!aligned16(g.A) || !aligned16(g.B)) return -1;
     if (g.batch > 1) {

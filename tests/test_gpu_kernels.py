@@ -353,6 +353,19 @@ def test_matmul_tcgen05_batched_parity(K, gemm_impl, sa, sb, dt):
           np.maximum(oracle.matmul(a, b, bias, False, False, dt), 0), 2 * EPS[dt], tol)
 
 
+@pytest.mark.parametrize("gemm_impl", ["tc"], indirect=True)
+@pytest.mark.parametrize("dt", [BF16, F16])
+@pytest.mark.parametrize("sa,sb", [((64, 2048), (1000, 2048)),      # ResNet-50 classifier (ONNX Gemm, transB = 1)
+                                   ((128, 768), (2304, 768)), ((300, 72), (200, 72)), ((16, 4096), (4096, 4096))])
+def test_matmul_tcgen05_transb_parity(K, gemm_impl, sa, sb, dt):
+    """[N, K] weights (transB) feed the UMMA A operand K-major: one [128 x 64] box per stage, no transpose pass."""
+    a, b = rnd(sa, 31, dt, 0.5), rnd(sb, 32, dt, 0.05)
+    tol = gemm_tol(dt, sa[-1], np.abs(a).max(), np.abs(b).max())
+    close(K.matmul(a, b, None, False, True, dt), oracle.matmul(a, b, None, False, True, dt), 2 * EPS[dt], tol)
+    bias = rnd((sb[0],), 33, dt)
+    close(K.matmul(a, b, bias, False, True, dt), oracle.matmul(a, b, bias, False, True, dt), 2 * EPS[dt], tol)
+
+
 @pytest.mark.parametrize("dt", [F16, BF16])
 def test_conv_resnet_shapes_parity(K, dt):
     """ResNet-50 bottleneck shapes (reduced batch): 1x1, 3x3 s1/s2, 7x7-stage P = 49, F up to 2048."""
@@ -362,7 +375,8 @@ def test_conv_resnet_shapes_parity(K, dt):
                            ((2, 256, 28, 28), (256, 256, 3, 3), (1, 1, 2, 2, 1, 1)),
                            ((2, 1024, 14, 14), (2048, 1024, 1, 1), (0, 0, 2, 2, 1, 1)),
                            ((2, 512, 7, 7), (512, 512, 3, 3), (1, 1, 1, 1, 1, 1)),
-                           ((2, 2048, 7, 7), (512, 2048, 1, 1), (0, 0, 1, 1, 1, 1))]:
+                           ((2, 2048, 7, 7), (512, 2048, 1, 1), (0, 0, 1, 1, 1, 1)),
+                           ((2, 3, 64, 64), (64, 3, 7, 7), (3, 3, 2, 2, 1, 1))]:
         x, w = rnd(xs, 26, dt), rnd(ws, 27, dt, 0.05)
         close(K.conv2d(x, w, *args, dt=dt), oracle.conv2d(x, w, *args, dt=dt), tol, tol)
 
@@ -375,7 +389,8 @@ def test_conv_fused_tail_bit_identical(K, dt):
     cases = [((2, 64, 56, 56), (256, 64, 1, 1), (0, 0, 1, 1, 1, 1)),      # batched 1x1, no repack
              ((2, 128, 28, 28), (128, 128, 3, 3), (1, 1, 1, 1, 1, 1)),   # folded im2col
              ((8, 256, 14, 14), (300, 256, 3, 3), (1, 1, 2, 2, 1, 1)),   # P = 49, F > 256 (two row chunks, ragged)
-             ((8, 512, 7, 7), (128, 512, 1, 1), (0, 0, 1, 1, 1, 1))]     # 1x1 with P % 8 != 0 -> folded
+             ((8, 512, 7, 7), (128, 512, 1, 1), (0, 0, 1, 1, 1, 1)),     # 1x1 with P % 8 != 0 -> folded
+             ((4, 3, 64, 64), (64, 3, 7, 7), (3, 3, 2, 2, 1, 1))]        # stem: K = 147 zero-padded to 152
     for ci, (xs, ws, args) in enumerate(cases):
         x, w = rnd(xs, 50 + ci, dt), rnd(ws, 60 + ci, dt, 0.05)
         F = ws[0]
@@ -399,9 +414,9 @@ def test_conv_fused_tail_bit_identical(K, dt):
             if ora is not None:
                 close(got, ora, tol, tol)
     # fp32 / grouped / tiny-K convs are not taken: rc 2, the runtime runs the operators one by one
-    x, w = rnd((2, 3, 32, 32), 90, dt), rnd((8, 3, 7, 7), 91, dt, 0.2)
+    x, w = rnd((1, 8, 9, 9), 90, dt), rnd((8, 2, 3, 3), 91, dt, 0.2)  # groups = 4
     z = np.zeros(8, np.float32)
-    assert K.conv2d_fused(x, w, 3, 3, 2, 2, 1, 1, (z, z + 1, z + 1, z), 1e-5, None, True, dt=dt) is None
+    assert K.conv2d_fused(x, w, 1, 1, 2, 2, 1, 1, (z, z + 1, z + 1, z), 1e-5, None, True, dt=dt) is None
     x = rnd((2, 16, 8, 8), 92, dt)
     close(K.batch_norm_relu(x, *[np.full(16, v, np.float32) for v in (0.1, 1.3, 0.9, -0.2)], 1e-5, dt=dt),
           np.maximum(K.batch_norm(x, *[np.full(16, v, np.float32) for v in (0.1, 1.3, 0.9, -0.2)], 1e-5, dt=dt), 0), 0, 0)
