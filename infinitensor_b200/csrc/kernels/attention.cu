@@ -374,6 +374,21 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
     }
 
     // ---------------- consumers ----------------
+    // RoPE cos / sin table of the CTA's first batch row: the RoPE positions are a step-old graph input like the cache
+    // position, so the powf / sincosf chain runs ahead of the wait; recomputed only when a later segment changes batch row
+    int table_b = -1;
+    auto rope_table = [&](int b) {
+        if (threadIdx.x < kD / 2) {
+            const float p = rope_pos_dtype == ITB_I64 ? (float)(int)((const int64_t *)rope_pos)[b]
+                                                      : (float)((const int32_t *)rope_pos)[b];
+            const float freq = p * powf(10000.f, -(float)(threadIdx.x * 2) / (float)kD);
+            s_cs[threadIdx.x] = round_t<T>(cosf(freq));
+            s_sn[threadIdx.x] = round_t<T>(sinf(freq));
+        }
+        named_bar_sync(1, CONSUMERS);
+        table_b = b;
+    };
+    if (ROPE) rope_table(bh / H);
     pdl_wait();
     const int sub = lane / LPR;
     const int col = (lane % LPR) * EPL;
@@ -390,15 +405,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
             for (int j = 0; j < EPL; ++j) acc[j] = 0.f;
             Vec16<T> qv = ld16(q + (int64_t)bh * kD + col);
             if (ROPE) {
-                if (threadIdx.x < kD / 2) {
-                    const int b = bh / H;
-                    const float p = rope_pos_dtype == ITB_I64 ? (float)(int)((const int64_t *)rope_pos)[b]
-                                                              : (float)((const int32_t *)rope_pos)[b];
-                    const float freq = p * powf(10000.f, -(float)(threadIdx.x * 2) / (float)kD);
-                    s_cs[threadIdx.x] = round_t<T>(cosf(freq));
-                    s_sn[threadIdx.x] = round_t<T>(sinf(freq));
-                }
-                named_bar_sync(1, CONSUMERS);
+                if (bh / H != table_b) rope_table(bh / H);  // (every earlier reader is behind the previous segment's barriers)
                 rope_one<T, EPL, LPR>(qv, col, s_cs, s_sn);
             }
 #pragma unroll
