@@ -1,0 +1,732 @@
+"""ONNX ingestion without the `onnx` package.
+
+The reference drives its backend through `OnnxStub(model, runtime)` (pyinfinitensor/src/pyinfinitensor/onnx.py:41-1136):
+one `handler.<op>(...)` call per ONNX node.  That module needs `onnx` + `onnxsim`, which this image does not have, so this
+file carries the two pieces the path needs from them and nothing else:
+
+  * a protobuf WIRE reader / writer for the handful of ONNX messages involved (ModelProto, GraphProto, NodeProto,
+    AttributeProto, TensorProto, ValueInfoProto; field numbers from onnx.proto3, IR version 8) -- `load_model`,
+    `save_model`;
+  * `OnnxStub`: the node -> handler-call lowering for every operator this backend has a kernel for, with the
+    reference frontend's conventions (quirk ledger q12): dynamic dims become 1 (onnx.py:1625-1626), Gemm needs
+    alpha = beta = 1 (:298-300), Conv bias becomes Reshape + Add (:159-190), asymmetric Conv pads become an explicit
+    Pad (:150-155), GlobalAveragePool becomes AveragePool with k = (H, W) (:489-503), Dropout becomes Identity
+    (:898-910), ReduceSum with a `communicator` attribute becomes AllReduceSum (:917-923), Constant nodes and
+    initializers become weight tensors.
+
+`OnnxStub` takes any object with the GraphHandler surface (backend.GraphHandler in the product; the CPU tests hand it the
+oracle's handler).  No onnxsim pass is run: the graph is lowered as written.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+
+# ONNX TensorProto.DataType codes used by the backend (include/core/data_type.h:6-23 has the same numbering)
+F32, U8, I8, I16, I32, I64, BOOL, F16, F64, U32, BF16 = 1, 2, 3, 5, 6, 7, 9, 10, 11, 12, 16
+_NP = {F32: np.float32, U8: np.uint8, I8: np.int8, I16: np.int16, I32: np.int32, I64: np.int64, BOOL: np.bool_,
+       F16: np.float16, F64: np.float64, U32: np.uint32, BF16: np.uint16}
+
+
+# ------------------------------------------------------------------------------------------------ wire format
+def _varint(buf, i):
+    r = s = 0
+    while True:
+        b = buf[i]
+        i += 1
+        r |= (b & 0x7F) << s
+        if b < 0x80:
+            return r, i
+        s += 7
+
+
+def _fields(buf):
+    """(field number, wire type, value) triples of one message; length-delimited values are memoryviews."""
+    buf = memoryview(buf)
+    i, n = 0, len(buf)
+    while i < n:
+        key, i = _varint(buf, i)
+        no, wt = key >> 3, key & 7
+        if wt == 0:
+            v, i = _varint(buf, i)
+        elif wt == 1:
+            v, i = bytes(buf[i:i + 8]), i + 8
+        elif wt == 2:
+            ln, i = _varint(buf, i)
+            v, i = buf[i:i + ln], i + ln
+        elif wt == 5:
+            v, i = bytes(buf[i:i + 4]), i + 4
+        else:
+            raise ValueError(f"protobuf wire type {wt} not supported")
+        yield no, wt, v
+
+
+def _sint64(v):  # int64 fields carry negatives as 64-bit two's complement varints
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _packed_ints(wt, v):
+    if wt == 0:
+        return [_sint64(v)]
+    out, i = [], 0
+    while i < len(v):
+        x, i = _varint(v, i)
+        out.append(_sint64(x))
+    return out
+
+
+def _packed_f32(wt, v):
+    return list(struct.unpack("<f", v)) if wt == 5 else list(np.frombuffer(v, dtype="<f4"))
+
+
+def _enc_varint(x):
+    x &= (1 << 64) - 1
+    out = bytearray()
+    while True:
+        b = x & 0x7F
+        x >>= 7
+        out.append(b | (0x80 if x else 0))
+        if not x:
+            return bytes(out)
+
+
+def _key(no, wt):
+    return _enc_varint((no << 3) | wt)
+
+
+def _ld(no, payload: bytes):
+    return _key(no, 2) + _enc_varint(len(payload)) + payload
+
+
+# ------------------------------------------------------------------------------------------------ messages
+@dataclass
+class TensorProto:
+    name: str = ""
+    dims: List[int] = field(default_factory=list)
+    data_type: int = F32
+    array: Optional[np.ndarray] = None  # storage-typed values (fp16 as float16, bf16 as uint16 bit patterns)
+
+    @staticmethod
+    def parse(buf) -> "TensorProto":
+        t = TensorProto()
+        raw = None
+        f32, i32, i64, f64, u64 = [], [], [], [], []
+        for no, wt, v in _fields(buf):
+            if no == 1: t.dims += _packed_ints(wt, v)
+            elif no == 2: t.data_type = v
+            elif no == 4: f32 += _packed_f32(wt, v)
+            elif no == 5: i32 += _packed_ints(wt, v)
+            elif no == 7: i64 += _packed_ints(wt, v)
+            elif no == 8: t.name = bytes(v).decode()
+            elif no == 9: raw = bytes(v)
+            elif no == 10: f64 += list(np.frombuffer(v, dtype="<f8")) if wt == 2 else list(struct.unpack("<d", v))
+            elif no == 11: u64 += _packed_ints(wt, v)
+            elif no == 14 and v != 0: raise ValueError(f"tensor {t.name}: external data is not supported")
+        dt = _NP.get(t.data_type)
+        if dt is None:
+            raise ValueError(f"tensor {t.name}: ONNX data type {t.data_type} not supported")
+        if raw is not None:
+            arr = np.frombuffer(raw, dtype=np.dtype(dt).newbyteorder("<")).astype(dt, copy=True)
+        elif t.data_type in (F16, BF16):  # 16-bit patterns travel in int32_data
+            arr = np.array(i32, dtype=np.int64).astype(np.uint16)
+            arr = arr.view(np.float16) if t.data_type == F16 else arr
+        elif t.data_type == F32: arr = np.array(f32, dtype=np.float32)
+        elif t.data_type == F64: arr = np.array(f64, dtype=np.float64)
+        elif t.data_type == I64: arr = np.array(i64, dtype=np.int64)
+        elif t.data_type == U32: arr = np.array(u64, dtype=np.uint32)
+        else: arr = np.array(i32, dtype=np.int64).astype(dt)
+        t.array = arr.reshape(t.dims) if t.dims else arr.reshape(())
+        return t
+
+    def encode(self) -> bytes:
+        out = b"".join(_key(1, 0) + _enc_varint(d) for d in self.dims)
+        out += _key(2, 0) + _enc_varint(self.data_type)
+        out += _ld(8, self.name.encode())
+        out += _ld(9, np.ascontiguousarray(self.array).astype(_NP[self.data_type], copy=False).tobytes())
+        return out
+
+
+@dataclass
+class ValueInfo:
+    name: str = ""
+    elem_type: int = F32
+    dims: List[int] = field(default_factory=list)  # dim_param / missing -> 0 (lowered to 1 by the stub)
+
+    @staticmethod
+    def parse(buf) -> "ValueInfo":
+        vi = ValueInfo()
+        for no, _, v in _fields(buf):
+            if no == 1: vi.name = bytes(v).decode()
+            elif no == 2:
+                for n2, _, v2 in _fields(v):
+                    if n2 != 1: continue  # TypeProto.tensor_type
+                    for n3, _, v3 in _fields(v2):
+                        if n3 == 1: vi.elem_type = v3
+                        elif n3 == 2:  # TensorShapeProto
+                            for n4, _, v4 in _fields(v3):
+                                if n4 != 1: continue
+                                val = 0
+                                for n5, _, v5 in _fields(v4):
+                                    if n5 == 1: val = _sint64(v5)
+                                vi.dims.append(val)
+        return vi
+
+    def encode(self) -> bytes:
+        shape = b"".join(_ld(1, _key(1, 0) + _enc_varint(d)) for d in self.dims)
+        tensor_type = _key(1, 0) + _enc_varint(self.elem_type) + _ld(2, shape)
+        return _ld(1, self.name.encode()) + _ld(2, _ld(1, tensor_type))
+
+
+@dataclass
+class Node:
+    op_type: str = ""
+    inputs: List[str] = field(default_factory=list)
+    outputs: List[str] = field(default_factory=list)
+    name: str = ""
+    attrs: Dict[str, Any] = field(default_factory=dict)  # int | float | bytes | list | TensorProto
+
+    @staticmethod
+    def parse(buf) -> "Node":
+        nd = Node()
+        for no, _, v in _fields(buf):
+            if no == 1: nd.inputs.append(bytes(v).decode())
+            elif no == 2: nd.outputs.append(bytes(v).decode())
+            elif no == 3: nd.name = bytes(v).decode()
+            elif no == 4: nd.op_type = bytes(v).decode()
+            elif no == 5:
+                k, val = Node._attr(v)
+                nd.attrs[k] = val
+        return nd
+
+    @staticmethod
+    def _attr(buf):
+        name, kind = "", 0
+        f = i = s = t = None
+        floats, ints, strings = [], [], []
+        for no, wt, v in _fields(buf):
+            if no == 1: name = bytes(v).decode()
+            elif no == 2: f = struct.unpack("<f", v)[0]
+            elif no == 3: i = _sint64(v)
+            elif no == 4: s = bytes(v)
+            elif no == 5: t = TensorProto.parse(v)
+            elif no == 7: floats += _packed_f32(wt, v)
+            elif no == 8: ints += _packed_ints(wt, v)
+            elif no == 9: strings.append(bytes(v))
+            elif no == 20: kind = v
+        # AttributeProto.AttributeType: 1 FLOAT 2 INT 3 STRING 4 TENSOR 6 FLOATS 7 INTS 8 STRINGS
+        val = {1: f, 2: i, 3: s, 4: t, 6: floats, 7: ints, 8: strings}.get(kind)
+        if kind == 0:  # writers that omit `type`: take whichever member is present
+            val = next((x for x in (t, s, f, i) if x is not None), ints or floats or strings)
+        if kind not in (0, 1, 2, 3, 4, 6, 7, 8):
+            raise ValueError(f"attribute {name}: type {kind} (graph / sparse tensor) not supported")
+        return name, val
+
+    def encode(self) -> bytes:
+        out = b"".join(_ld(1, x.encode()) for x in self.inputs) + b"".join(_ld(2, x.encode()) for x in self.outputs)
+        out += _ld(3, self.name.encode()) + _ld(4, self.op_type.encode())
+        for k, v in self.attrs.items():
+            a = _ld(1, k.encode())
+            if isinstance(v, bool) or isinstance(v, (int, np.integer)): a += _key(3, 0) + _enc_varint(int(v)) + _key(20, 0) + _enc_varint(2)
+            elif isinstance(v, float): a += _key(2, 5) + struct.pack("<f", v) + _key(20, 0) + _enc_varint(1)
+            elif isinstance(v, (bytes, str)): a += _ld(4, v.encode() if isinstance(v, str) else v) + _key(20, 0) + _enc_varint(3)
+            elif isinstance(v, TensorProto): a += _ld(5, v.encode()) + _key(20, 0) + _enc_varint(4)
+            elif len(v) and isinstance(v[0], float): a += b"".join(_key(7, 5) + struct.pack("<f", x) for x in v) + _key(20, 0) + _enc_varint(6)
+            else: a += _ld(8, b"".join(_enc_varint(int(x)) for x in v)) + _key(20, 0) + _enc_varint(7)
+            out += _ld(5, a)
+        return out
+
+
+@dataclass
+class Graph:
+    nodes: List[Node] = field(default_factory=list)
+    initializers: List[TensorProto] = field(default_factory=list)
+    inputs: List[ValueInfo] = field(default_factory=list)
+    outputs: List[ValueInfo] = field(default_factory=list)
+    name: str = "graph"
+
+    @staticmethod
+    def parse(buf) -> "Graph":
+        g = Graph()
+        for no, _, v in _fields(buf):
+            if no == 1: g.nodes.append(Node.parse(v))
+            elif no == 2: g.name = bytes(v).decode()
+            elif no == 5: g.initializers.append(TensorProto.parse(v))
+            elif no == 11: g.inputs.append(ValueInfo.parse(v))
+            elif no == 12: g.outputs.append(ValueInfo.parse(v))
+        return g
+
+    def encode(self) -> bytes:
+        return (b"".join(_ld(1, n.encode()) for n in self.nodes) + _ld(2, self.name.encode()) +
+                b"".join(_ld(5, t.encode()) for t in self.initializers) +
+                b"".join(_ld(11, v.encode()) for v in self.inputs) + b"".join(_ld(12, v.encode()) for v in self.outputs))
+
+
+@dataclass
+class Model:
+    graph: Graph = field(default_factory=Graph)
+    ir_version: int = 8
+    opset: int = 17
+
+
+def load_model(src) -> Model:
+    """`src`: path, bytes or an already parsed Model."""
+    if isinstance(src, Model):
+        return src
+    if isinstance(src, str):
+        with open(src, "rb") as f:
+            src = f.read()
+    m = Model()
+    for no, _, v in _fields(src):
+        if no == 1: m.ir_version = v
+        elif no == 7: m.graph = Graph.parse(v)
+        elif no == 8:
+            for n2, _, v2 in _fields(v):
+                if n2 == 2: m.opset = v2
+    return m
+
+
+def save_model(m: Model) -> bytes:
+    opset = _ld(1, b"") + _key(2, 0) + _enc_varint(m.opset)
+    return _key(1, 0) + _enc_varint(m.ir_version) + _ld(2, b"infinitensor_b200") + _ld(7, m.graph.encode()) + _ld(8, opset)
+
+
+# ------------------------------------------------------------------------------------------------ lowering
+class OnnxStub:
+    """Mirror of pyinfinitensor.onnx.OnnxStub for the operators this backend implements: builds the graph through
+    `handler`, allocates (`data_malloc`) and uploads the initializers.  `inputs` / `outputs` map ONNX names to tensors."""
+
+    def __init__(self, model, runtime=None, handler=None, use_naive_allocator: bool = False, upload: bool = True):
+        if handler is None:
+            from . import backend
+            handler = backend.GraphHandler(runtime)
+        self.handler = handler
+        self.model = load_model(model)
+        self.inputs: Dict[str, Any] = {}
+        self.outputs: Dict[str, Any] = {}
+        self.tensors: Dict[str, Any] = {}
+        self._data: Dict[str, TensorProto] = {}
+        self.use_naive_allocator = use_naive_allocator
+        self._build()
+        if upload:  # (False: build and plan only, e.g. on the planning runtime of the CPU tests)
+            self.init()
+
+    # -- the reference's entry points (onnx.py:1138-1160 region)
+    def init(self):
+        self.handler.data_malloc(self.use_naive_allocator) if self.use_naive_allocator else self.handler.data_malloc()
+        for name, proto in self._data.items():
+            self.tensors[name].copyin_numpy(np.ascontiguousarray(proto.array))
+
+    def optimize(self): self.handler.optimize()
+    def tune(self): self.handler.tune()
+    def run(self): self.handler.run()
+    def run_with_cudagraph(self): self.handler.run_with_cudagraph()
+    def get_perf_time(self): return self.handler.get_perf_time()
+
+    # -- helpers
+    def _const(self, name) -> Optional[np.ndarray]:
+        p = self._data.get(name)
+        return None if p is None else p.array
+
+    def _ints(self, node, idx, attr=None, required=False):
+        if len(node.inputs) > idx and node.inputs[idx]:
+            c = self._const(node.inputs[idx])
+            if c is None:
+                raise NotImplementedError(f"{node.op_type} {node.name}: input {idx} must be a constant (no dynamic shapes)")
+            return [int(x) for x in np.asarray(c).reshape(-1)]
+        if attr is not None and attr in node.attrs:
+            return [int(x) for x in node.attrs[attr]]
+        if required:
+            raise ValueError(f"{node.op_type} {node.name}: missing `{attr}`")
+        return None
+
+    def _weight(self, name, proto: TensorProto):
+        t = self.handler.tensor(list(proto.dims), proto.data_type)
+        t.set_weight()
+        self.tensors[name] = t
+        self._data[name] = proto
+        return t
+
+    def _build(self):
+        g, h, T = self.model.graph, self.handler, self.tensors
+        for init in g.initializers:
+            self._weight(init.name, init)
+        for vi in g.inputs:
+            if vi.name not in T:
+                T[vi.name] = h.tensor([d if d > 0 else 1 for d in vi.dims], vi.elem_type)
+                T[vi.name].set_input()
+                self.inputs[vi.name] = T[vi.name]
+        # topological order over tensor availability (the file order of exported models is not guaranteed)
+        known = set(T)
+        pending = list(range(len(g.nodes)))
+        order = []
+        while pending:
+            rest = []
+            for i in pending:
+                if all(x in known or x == "" for x in g.nodes[i].inputs):
+                    order.append(i)
+                    known.update(g.nodes[i].outputs)
+                else:
+                    rest.append(i)
+            if len(rest) == len(pending):
+                bad = g.nodes[rest[0]]
+                raise ValueError(f"ONNX graph has a cycle or a missing input near {bad.op_type} {bad.name}: "
+                                 f"{[x for x in bad.inputs if x and x not in known]}")
+            pending = rest
+        for i in order:
+            self._lower(g.nodes[i])
+        for vo in g.outputs:
+            T[vo.name].set_output()
+            self.outputs[vo.name] = T[vo.name]
+
+    _UNARY = {"Relu": "relu", "Silu": "silu", "Gelu": "gelu", "Sigmoid": "sigmoid", "Tanh": "tanh", "Erf": "erf",
+              "Abs": "abs", "Sqrt": "sqrt", "Neg": "neg", "HardSigmoid": "hardSigmoid", "HardSwish": "hardSwish",
+              "Identity": "identity", "Exp": "exp"}
+    _BINARY = {"Add": "add", "Sub": "sub", "Mul": "mul", "Div": "div", "Pow": "pow", "Min": "min", "Max": "max",
+               "Less": "less", "Equal": "equal", "Greater": "greater"}
+    _ALLREDUCE = {"AllReduceSum": "allReduceSum", "AllReduceProd": "allReduceProd", "AllReduceMin": "allReduceMin",
+                  "AllReduceMax": "allReduceMax", "AllReduceAvg": "allReduceAvg"}
+
+    def _lower(self, nd: Node):
+        h, T, op, a = self.handler, self.tensors, nd.op_type, nd.attrs
+        I = lambda k: T[nd.inputs[k]]
+        out0 = nd.outputs[0] if nd.outputs else None
+        if op in self._UNARY:
+            T[out0] = getattr(h, self._UNARY[op])(I(0), None)
+        elif op in self._BINARY:
+            T[out0] = getattr(h, self._BINARY[op])(I(0), I(1), None)
+        elif op in self._ALLREDUCE:
+            T[out0] = getattr(h, self._ALLREDUCE[op])(I(0), None)
+        elif op == "Dropout":
+            T[out0] = h.identity(I(0), None)
+        elif op == "MatMul":
+            T[out0] = h.matmul(I(0), I(1), None, False, False, None, 0)
+        elif op == "Gemm":
+            if a.get("alpha", 1.0) != 1.0 or a.get("beta", 1.0) != 1.0:
+                raise NotImplementedError("Gemm: alpha / beta other than 1 are not supported (reference onnx.py:298-300)")
+            bias = I(2) if len(nd.inputs) > 2 and nd.inputs[2] else None
+            T[out0] = h.matmul(I(0), I(1), None, a.get("transA", 0) == 1, a.get("transB", 0) == 1, bias, 0)
+        elif op == "Conv":
+            d, p, s = a.get("dilations", [1, 1]), list(a.get("pads", [0, 0, 0, 0])), a.get("strides", [1, 1])
+            if a.get("group", 1) != 1 and I(1).shape()[1] * a["group"] != I(0).shape()[1]:
+                raise ValueError("Conv: `group` does not match the filter's channel count")
+            x = I(0)
+            if p[0] != p[2] or p[1] != p[3]:  # asymmetric padding: explicit Pad on H, W
+                x = h.pad(x, None, p, [-2, -1])
+                p = [0, 0, 0, 0]
+            y = h.conv(x, I(1), None, p[0], p[1], s[0], s[1], d[0], d[1])
+            if len(nd.inputs) > 2 and nd.inputs[2]:
+                b = I(2)
+                y = h.add(y, h.reshape(b, None, [1, int(np.prod(b.shape())), 1, 1]), None)
+            T[out0] = y
+        elif op == "BatchNormalization":
+            T[out0] = h.batchNormalization(I(0), None, I(3), I(4), I(1), I(2), float(a.get("momentum", 0.9)),
+                                           float(a.get("epsilon", 1e-5)), a.get("training_mode", 0) != 0)
+        elif op == "LayerNormalization":
+            bias = I(2) if len(nd.inputs) > 2 and nd.inputs[2] else None
+            T[out0] = h.layerNormalization(I(0), I(1), None, bias, float(a.get("epsilon", 1e-5)), a.get("axis", -1),
+                                           a.get("stash_type", 1))
+        elif op == "RMSNorm":
+            T[out0] = h.RMSNorm(I(0), I(1), None)
+        elif op == "RoPE":
+            T[out0] = h.RoPE(I(0), I(1), None)
+        elif op == "AttentionKVCache":
+            T[out0] = h.attentionKVCache(I(0), I(1), I(2), I(3), I(4), I(5), None)
+        elif op in ("MaxPool", "AveragePool"):
+            k = a["kernel_shape"]
+            d, p, s = a.get("dilations", [1, 1]), list(a.get("pads", [0, 0, 0, 0])), a.get("strides", [1, 1])
+            x = I(0)
+            if p[0] != p[2] or p[1] != p[3]:
+                x = h.pad(x, None, p, [-2, -1])
+                p = [0, 0, 0, 0]
+            fn = h.maxPool if op == "MaxPool" else h.avgPool
+            T[out0] = fn(x, None, k[0], k[1], d[0], d[1], p[0], p[1], s[0], s[1], a.get("ceil_mode", 0))
+        elif op == "GlobalAveragePool":
+            hh, ww = I(0).shape()[2:4]
+            T[out0] = h.avgPool(I(0), None, hh, ww, 1, 1, 0, 0, 1, 1, 0)
+        elif op == "Softmax":
+            T[out0] = h.softmax(I(0), None, a.get("axis", -1))
+        elif op == "Flatten":
+            T[out0] = h.flatten(I(0), None, a.get("axis", 1))
+        elif op == "Transpose":
+            perm = a.get("perm") or list(range(len(I(0).shape())))[::-1]
+            T[out0] = h.transpose(I(0), None, [int(x) for x in perm])
+        elif op == "Reshape":
+            shape = self._ints(nd, 1, "shape", required=True)
+            src = I(0).shape()
+            shape = [src[i] if v == 0 and not a.get("allowzero", 0) else v for i, v in enumerate(shape)]
+            if -1 in shape:
+                known = int(np.prod([v for v in shape if v != -1])) or 1
+                shape[shape.index(-1)] = int(np.prod(src)) // known
+            T[out0] = h.reshape(I(0), None, shape)
+        elif op == "Squeeze":
+            axes = self._ints(nd, 1, "axes")
+            if axes is None:
+                axes = [i for i, v in enumerate(I(0).shape()) if v == 1]
+            T[out0] = h.squeeze(I(0), None, axes)
+        elif op == "Unsqueeze":
+            T[out0] = h.unsqueeze(I(0), None, self._ints(nd, 1, "axes", required=True))
+        elif op == "Concat":
+            T[out0] = h.concat([T[x] for x in nd.inputs], None, a["axis"])
+        elif op == "Split":
+            axis = a.get("axis", 0)
+            split = self._ints(nd, 1, "split")
+            outs = h.split(I(0), None, axis, split if split is not None else len(nd.outputs))
+            for name, t in zip(nd.outputs, outs):
+                T[name] = t
+        elif op == "Gather":
+            T[out0] = h.gather(I(0), I(1), None, a.get("axis", 0))
+        elif op in ("ReduceMean", "ReduceSum"):
+            if op == "ReduceSum" and "communicator" in a:
+                T[out0] = h.allReduceSum(I(0), None)
+            else:
+                axes = self._ints(nd, 1, "axes")
+                fn = h.reduceMean if op == "ReduceMean" else h.reduceSum
+                T[out0] = fn(I(0), None, axes, a.get("keepdims", 1) != 0)
+        elif op == "Slice":
+            starts, ends = self._ints(nd, 1, "starts", required=True), self._ints(nd, 2, "ends", required=True)
+            lim = np.iinfo(np.int32)
+            clamp = lambda v: [max(lim.min, min(lim.max, int(x))) for x in v]
+            T[out0] = h.slice(I(0), None, clamp(starts), clamp(ends), self._ints(nd, 3, "axes"), self._ints(nd, 4, "steps"))
+        elif op == "Pad":
+            if a.get("mode", b"constant") not in (b"constant", "constant"):
+                raise NotImplementedError("Pad: only constant mode")
+            T[out0] = h.pad(I(0), None, self._ints(nd, 1, "pads", required=True), self._ints(nd, 3, "axes"))
+        elif op == "Cast":
+            T[out0] = h.cast(I(0), None, a["to"])
+        elif op == "Expand":
+            T[out0] = h.expand(I(0), None, self._ints(nd, 1, "shape", required=True))
+        elif op == "Where":
+            T[out0] = h.where(I(1), I(2), I(0), None)
+        elif op == "AllGather":
+            outs = h.allGather(I(0), None, len(nd.outputs))
+            for name, t in zip(nd.outputs, outs):
+                T[name] = t
+        elif op == "Constant":
+            value = a.get("value")
+            if not isinstance(value, TensorProto):
+                raise NotImplementedError("Constant: only the `value` tensor form is supported")
+            self._weight(out0, value)
+        else:
+            raise NotImplementedError(f'Unsupported operator "{op}" (no B200 kernel behind it)')
+
+
+# ------------------------------------------------------------------------------------------------ export
+class _ExportTensor:
+    """Tensor of the wrapped handler + the ONNX name it is exported under; records uploaded weight values."""
+
+    def __init__(self, exporter, inner, name):
+        self._x, self.inner, self.name = exporter, inner, name
+
+    def shape(self): return self.inner.shape()
+    def dtype(self): return self.inner.dtype()
+    def fuid(self): return self.inner.fuid() if hasattr(self.inner, "fuid") else id(self.inner)
+
+    def set_weight(self):
+        self.inner.set_weight()
+        self._x._weights[self.name] = None
+
+    def set_input(self):
+        self.inner.set_input()
+        self._x._inputs.append(self)
+
+    def set_output(self):
+        self.inner.set_output()
+        self._x._outputs.append(self)
+
+    def copyin_numpy(self, arr):
+        if self.name in self._x._weights:
+            self._x._weights[self.name] = np.array(arr, copy=True)
+        else:
+            self.inner.copyin_numpy(arr)
+
+    def copyout_numpy(self): return self.inner.copyout_numpy()
+
+
+class OnnxExporter:
+    """Handler decorator that records every call as an ONNX node (the direction of the reference's `OnnxStub.to_onnx`,
+    onnx.py:1138-1482): build any graph through it -- e.g. `graphs.build_llama_decode(OnnxExporter(h), cfg)` -- then
+    `model()` / `save()` give the ONNX file `OnnxStub` reads back.  Shapes come from the wrapped handler."""
+
+    def __init__(self, inner):
+        self.inner = inner
+        self.nodes: List[Node] = []
+        self._weights: Dict[str, Optional[np.ndarray]] = {}
+        self._inputs: List[_ExportTensor] = []
+        self._outputs: List[_ExportTensor] = []
+        self._all: List[_ExportTensor] = []
+        self._by_inner: Dict[Any, _ExportTensor] = {}
+        self._const_protos: Dict[str, TensorProto] = {}
+        self._n = 0
+
+    @staticmethod
+    def _tid(t):
+        return ("id", t.fuid()) if hasattr(t, "fuid") else ("py", id(t))
+
+    def _wrap(self, t, prefix="t"):
+        k = self._tid(t)
+        if k in self._by_inner:  # an output tensor the builder created up front and passed in
+            return self._by_inner[k]
+        w = _ExportTensor(self, t, f"{prefix}{self._n}")
+        self._n += 1
+        self._all.append(w)
+        self._by_inner[k] = w
+        return w
+
+    def tensor(self, dims, dtype):
+        return self._wrap(self.inner.tensor(dims, dtype), "v")
+
+    def _const(self, values, dtype=I64):
+        arr = np.asarray(values, dtype=_NP[dtype])
+        w = _ExportTensor(self, None, f"c{self._n}")
+        self._n += 1
+        self._weights[w.name] = arr
+        self._const_protos[w.name] = TensorProto(w.name, list(arr.shape), dtype, arr)
+        return w.name
+
+    def _emit(self, op, ins, inner_out, attrs=None, extra_inputs=()):
+        outs = inner_out if isinstance(inner_out, (list, tuple)) else [inner_out]
+        wrapped = [self._wrap(o) for o in outs]
+        names = [("" if t is None else t.name) for t in ins] + list(extra_inputs)
+        self.nodes.append(Node(op, names, [w.name for w in wrapped], f"{op}_{len(self.nodes)}", dict(attrs or {})))
+        return wrapped if isinstance(inner_out, (list, tuple)) else wrapped[0]
+
+    @staticmethod
+    def _in(t): return None if t is None else t.inner
+
+    # ---- operators: same signatures as backend.GraphHandler
+    def matmul(self, a, b, y, transA, transB, bias, act, matmul_compute_type="default"):
+        r = self.inner.matmul(a.inner, b.inner, self._in(y), transA, transB, self._in(bias), act)
+        if not transA and not transB and bias is None:
+            return self._emit("MatMul", [a, b], r)
+        return self._emit("Gemm", [a, b] + ([bias] if bias is not None else []), r,
+                          {"transA": int(bool(transA)), "transB": int(bool(transB))})
+
+    def conv(self, x, w, y, ph, pw, sh, sw, dh, dw):
+        r = self.inner.conv(x.inner, w.inner, self._in(y), ph, pw, sh, sw, dh, dw)
+        return self._emit("Conv", [x, w], r, {"pads": [ph, pw, ph, pw], "strides": [sh, sw], "dilations": [dh, dw],
+                                              "group": x.shape()[1] // w.shape()[1]})
+
+    def batchNormalization(self, x, y, mean, var, scale, bias, momentum, eps, training):
+        r = self.inner.batchNormalization(x.inner, self._in(y), mean.inner, var.inner, scale.inner, bias.inner, momentum, eps,
+                                          training)
+        return self._emit("BatchNormalization", [x, scale, bias, mean, var], r,
+                          {"momentum": float(momentum), "epsilon": float(eps), "training_mode": int(bool(training))})
+
+    def layerNormalization(self, x, scale, y, bias, eps, axis, stash_type):
+        r = self.inner.layerNormalization(x.inner, scale.inner, self._in(y), self._in(bias), eps, axis, stash_type)
+        return self._emit("LayerNormalization", [x, scale] + ([bias] if bias is not None else []), r,
+                          {"epsilon": float(eps), "axis": int(axis), "stash_type": int(stash_type)})
+
+    def RMSNorm(self, x, w, y): return self._emit("RMSNorm", [x, w], self.inner.RMSNorm(x.inner, w.inner, self._in(y)))
+    def RoPE(self, pos, x, y): return self._emit("RoPE", [pos, x], self.inner.RoPE(pos.inner, x.inner, self._in(y)))
+
+    def attentionKVCache(self, kc, vc, q, k, v, pos, y):
+        r = self.inner.attentionKVCache(kc.inner, vc.inner, q.inner, k.inner, v.inner, pos.inner, self._in(y))
+        return self._emit("AttentionKVCache", [kc, vc, q, k, v, pos], r)
+
+    def _pool(self, op, fn, x, y, kh, kw, dh, dw, ph, pw, sh, sw, ceil):
+        r = fn(x.inner, self._in(y), kh, kw, dh, dw, ph, pw, sh, sw, ceil)
+        return self._emit(op, [x], r, {"kernel_shape": [kh, kw], "dilations": [dh, dw], "pads": [ph, pw, ph, pw],
+                                       "strides": [sh, sw], "ceil_mode": int(ceil)})
+
+    def maxPool(self, x, y, *a): return self._pool("MaxPool", self.inner.maxPool, x, y, *a)
+    def avgPool(self, x, y, *a): return self._pool("AveragePool", self.inner.avgPool, x, y, *a)
+
+    def softmax(self, x, y, axis): return self._emit("Softmax", [x], self.inner.softmax(x.inner, self._in(y), axis), {"axis": int(axis)})
+    def flatten(self, x, y, axis): return self._emit("Flatten", [x], self.inner.flatten(x.inner, self._in(y), axis), {"axis": int(axis)})
+
+    def transpose(self, x, y, perm):
+        return self._emit("Transpose", [x], self.inner.transpose(x.inner, self._in(y), perm), {"perm": [int(p) for p in perm]})
+
+    def reshape(self, x, y, shape):
+        r = self.inner.reshape(x.inner, self._in(y), shape)
+        return self._emit("Reshape", [x], r, extra_inputs=[self._const(list(shape))])
+
+    def squeeze(self, x, y, axes):
+        return self._emit("Squeeze", [x], self.inner.squeeze(x.inner, self._in(y), axes), extra_inputs=[self._const(list(axes))])
+
+    def unsqueeze(self, x, y, axes):
+        return self._emit("Unsqueeze", [x], self.inner.unsqueeze(x.inner, self._in(y), axes), extra_inputs=[self._const(list(axes))])
+
+    def concat(self, inputs, y, dim):
+        return self._emit("Concat", list(inputs), self.inner.concat([t.inner for t in inputs], self._in(y), dim), {"axis": int(dim)})
+
+    def split(self, x, outputs, axis, numOrRatio):
+        inner_outs = None if outputs is None else [self._in(o) for o in outputs]
+        r = self.inner.split(x.inner, inner_outs, axis, numOrRatio)
+        r = list(r) if isinstance(r, (list, tuple)) else [r]
+        if isinstance(numOrRatio, int):
+            return self._emit("Split", [x], r, {"axis": int(axis)})
+        # ONNX wants element counts; the handler takes ratios -> scale them to the axis length
+        n = x.shape()[axis]
+        sizes = [n * int(v) // int(sum(numOrRatio)) for v in numOrRatio]
+        return self._emit("Split", [x], r, {"axis": int(axis)}, extra_inputs=[self._const(sizes)])
+
+    def gather(self, data, idx, y, axis):
+        return self._emit("Gather", [data, idx], self.inner.gather(data.inner, idx.inner, self._in(y), axis), {"axis": int(axis)})
+
+    def _reduce(self, op, fn, x, y, axes, keepdims):
+        r = fn(x.inner, self._in(y), axes, keepdims)
+        extra = [] if axes is None else [self._const(list(axes))]
+        return self._emit(op, [x], r, {"keepdims": int(bool(keepdims))}, extra_inputs=extra)
+
+    def reduceMean(self, x, y, axes, keepdims): return self._reduce("ReduceMean", self.inner.reduceMean, x, y, axes, keepdims)
+    def reduceSum(self, x, y, axes, keepdims): return self._reduce("ReduceSum", self.inner.reduceSum, x, y, axes, keepdims)
+
+    def slice(self, x, y, starts, ends, axes, steps):
+        r = self.inner.slice(x.inner, self._in(y), starts, ends, axes, steps)
+        n = len(starts)
+        extra = [self._const(list(starts)), self._const(list(ends)), self._const(list(axes) if axes is not None else list(range(n))),
+                 self._const(list(steps) if steps is not None else [1] * n)]
+        return self._emit("Slice", [x], r, extra_inputs=extra)
+
+    def pad(self, x, y, pads, axes):
+        r = self.inner.pad(x.inner, self._in(y), pads, axes)
+        extra = [self._const(list(pads))] + ([] if axes is None else ["", self._const(list(axes))])
+        return self._emit("Pad", [x], r, extra_inputs=extra)
+
+    def cast(self, x, y, to): return self._emit("Cast", [x], self.inner.cast(x.inner, self._in(y), to), {"to": int(to)})
+
+    def expand(self, x, y, dims):
+        return self._emit("Expand", [x], self.inner.expand(x.inner, self._in(y), dims), extra_inputs=[self._const(list(dims))])
+
+    def where(self, xx, yy, cond, y):
+        return self._emit("Where", [cond, xx, yy], self.inner.where(xx.inner, yy.inner, cond.inner, self._in(y)))
+
+    def allGather(self, x, outputs, n):
+        inner_outs = None if outputs is None else [self._in(o) for o in outputs]
+        return self._emit("AllGather", [x], list(self.inner.allGather(x.inner, inner_outs, n)))
+
+    def __getattr__(self, name):
+        # unary / binary / all-reduce families share one shape: (inputs..., output)
+        onnx_name = {v: k for k, v in {**OnnxStub._UNARY, **OnnxStub._BINARY, **OnnxStub._ALLREDUCE}.items()}.get(name)
+        if onnx_name is None:
+            return getattr(self.inner, name)  # data_malloc, run, schedule, ... go straight through
+
+        def call(*args):
+            ins = list(args[:-1])
+            return self._emit(onnx_name, ins, getattr(self.inner, name)(*[t.inner for t in ins], self._in(args[-1])))
+        return call
+
+    # ---- result
+    def model(self) -> Model:
+        g = Graph(nodes=list(self.nodes))
+        consts = self._const_protos
+        by_name = {t.name: t for t in self._all}
+        for name, arr in self._weights.items():
+            if name in consts:
+                g.initializers.append(consts[name])
+                continue
+            t = by_name[name]
+            if arr is None:
+                arr = np.zeros(t.shape(), dtype=_NP[t.dtype()])
+            g.initializers.append(TensorProto(name, list(t.shape()), t.dtype(), np.asarray(arr)))
+        g.inputs = [ValueInfo(t.name, t.dtype(), list(t.shape())) for t in self._inputs]
+        g.outputs = [ValueInfo(t.name, t.dtype(), list(t.shape())) for t in self._outputs]
+        return Model(graph=g)
+
+    def save(self) -> bytes:
+        return save_model(self.model())

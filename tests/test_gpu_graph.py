@@ -211,3 +211,31 @@ def test_resnet_conv_tail_fusion_is_bit_identical(monkeypatch):
     assert sum(s.startswith("ConvBnAct") for s in s1) == 53 and not any(s.startswith("ConvBnAct") for s in s0)
     assert np.isfinite(G.from_storage(fused, F16)).all()
     assert np.array_equal(fused, plain)
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_onnx_stub_drives_the_backend(dtype):
+    """an ONNX file (written by OnnxExporter, read by the package-free protobuf reader) lowered by
+    OnnxStub onto the CUDA runtime gives the oracle's logits for the same file."""
+    from infinitensor_b200 import backend as B, graphs as G, onnx_lite as X
+    from oracle.graph_oracle import OracleHandler
+    cfg = G.LlamaConfig(layers=2, d_model=256, heads=2, head_dim=128, ffn=384, vocab=96, s_max=16, batch=3, dtype=dtype)
+    exp = X.OnnxExporter(OracleHandler())
+    ge = G.build_llama_decode(exp, cfg)
+    exp.data_malloc()
+    G.fill_llama_weights_host(ge)
+    blob = exp.save()
+    gpu = X.OnnxStub(blob, B.CudaRuntime(0))
+    cpu = X.OnnxStub(blob, handler=OracleHandler())
+    rng = np.random.default_rng(5)
+    for name, t in gpu.inputs.items():
+        shp, dt = t.shape(), t.dtype()
+        v = rng.integers(0, 7, size=shp).astype(np.int64) if dt == 7 else G.to_storage((rng.standard_normal(shp) * 0.5).astype(np.float32), dt)
+        t.copyin_numpy(v)
+        cpu.inputs[name].copyin_numpy(v)
+    gpu.run_with_cudagraph()
+    cpu.run()
+    (name, out), = [(k, v) for k, v in gpu.outputs.items()][:1]
+    got = G.from_storage(out.copyout_numpy(), dtype).astype(np.float64)
+    ref = cpu.outputs[name].f32().astype(np.float64)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < (1e-3 if dtype == F32 else 3e-2)

@@ -1,0 +1,157 @@
+"""ONNX ingestion without the onnx package: wire format, node lowering, export -> import round trips.
+CPU tier: graphs run on the oracle's handler; the GPU tier test lives in test_gpu_graph.py."""
+import struct
+
+import numpy as np
+import pytest
+
+from infinitensor_b200 import onnx_lite as X
+
+F32, F16, BF16, I64 = 1, 10, 16, 7
+
+
+def test_wire_roundtrip_all_attribute_and_tensor_forms():
+    rng = np.random.default_rng(0)
+    w = rng.standard_normal((3, 4)).astype(np.float32)
+    h16 = rng.standard_normal((2, 5)).astype(np.float16)
+    b16 = rng.integers(0, 65535, size=(7,)).astype(np.uint16)
+    node = X.Node("Foo", ["a", "", "w"], ["y", "z"], "n0",
+                  {"i": -3, "f": 0.25, "s": b"half_pixel", "ints": [1, -2, 3 << 40], "floats": [0.5, -1.5],
+                   "t": X.TensorProto("tv", [2], I64, np.array([9, -9], np.int64))})
+    g = X.Graph([node], [X.TensorProto("w", [3, 4], F32, w), X.TensorProto("h", [2, 5], F16, h16),
+                         X.TensorProto("b", [7], BF16, b16)],
+                [X.ValueInfo("a", F32, [0, 4])], [X.ValueInfo("y", F16, [2, 5])])
+    m = X.load_model(X.save_model(X.Model(g, opset=17)))
+    assert m.opset == 17 and m.ir_version == 8
+    n = m.graph.nodes[0]
+    assert (n.op_type, n.inputs, n.outputs, n.name) == ("Foo", ["a", "", "w"], ["y", "z"], "n0")
+    assert n.attrs["i"] == -3 and n.attrs["f"] == 0.25 and n.attrs["s"] == b"half_pixel"
+    assert n.attrs["ints"] == [1, -2, 3 << 40] and n.attrs["floats"] == [0.5, -1.5]
+    assert n.attrs["t"].array.tolist() == [9, -9]
+    got = {t.name: t for t in m.graph.initializers}
+    assert np.array_equal(got["w"].array, w) and np.array_equal(got["h"].array, h16) and np.array_equal(got["b"].array, b16)
+    assert got["h"].array.dtype == np.float16 and got["b"].array.dtype == np.uint16
+    assert m.graph.inputs[0].dims == [0, 4] and m.graph.outputs[0].elem_type == F16
+
+
+def test_typed_repeated_fields_as_other_writers_emit_them():
+    """float_data (packed), int64_data (packed), fp16 in int32_data, unpacked repeated ints: not just raw_data."""
+    def ld(no, b): return X._key(no, 2) + X._enc_varint(len(b)) + b
+    dims = X._key(1, 0) + X._enc_varint(3)
+    t_f = dims + X._key(2, 0) + X._enc_varint(F32) + ld(4, struct.pack("<3f", 1.5, -2.0, 3.25)) + ld(8, b"f")
+    t_i = ld(1, X._enc_varint(3)) + X._key(2, 0) + X._enc_varint(I64) + ld(7, b"".join(X._enc_varint(v) for v in (7, -1, 1 << 33)))
+    h = np.array([1.0, -0.5, 65504.0], np.float16)
+    t_h = dims + X._key(2, 0) + X._enc_varint(F16) + b"".join(X._key(5, 0) + X._enc_varint(int(v)) for v in h.view(np.uint16))
+    assert X.TensorProto.parse(t_f).array.tolist() == [1.5, -2.0, 3.25]
+    assert X.TensorProto.parse(t_i).array.tolist() == [7, -1, 1 << 33]
+    assert np.array_equal(X.TensorProto.parse(t_h).array, h)
+
+
+def _oracle():
+    from oracle.graph_oracle import OracleHandler
+    return OracleHandler()
+
+
+def test_cnn_lowering_matches_direct_oracle_calls():
+    """Conv(+bias, asymmetric pads) -> BatchNorm -> Relu -> MaxPool -> GlobalAveragePool -> Flatten -> Gemm(transB) -> Softmax,
+    lowered with the reference frontend's conventions (quirk ledger q12)."""
+    import oracle as O
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, 3, 9, 9)).astype(np.float32)
+    w = (rng.standard_normal((8, 3, 3, 3)) * 0.2).astype(np.float32)
+    cb = rng.standard_normal(8).astype(np.float32)
+    bn = [rng.uniform(0.5, 1.5, 8).astype(np.float32), rng.standard_normal(8).astype(np.float32) * 0.1,
+          rng.standard_normal(8).astype(np.float32) * 0.1, rng.uniform(0.5, 1.5, 8).astype(np.float32)]  # scale bias mean var
+    fc, fb = (rng.standard_normal((5, 8)) * 0.3).astype(np.float32), rng.standard_normal(5).astype(np.float32)
+    T = lambda n, a: X.TensorProto(n, list(a.shape), F32, a)
+    nodes = [X.Node("Conv", ["x", "w", "cb"], ["c"], "", {"pads": [1, 0, 2, 1], "strides": [1, 1], "dilations": [1, 1]}),
+             X.Node("BatchNormalization", ["c", "s", "b", "m", "v"], ["n"], "", {"epsilon": 1e-5}),
+             X.Node("Relu", ["n"], ["r"]), X.Node("Dropout", ["r"], ["d"]),
+             X.Node("MaxPool", ["d"], ["p"], "", {"kernel_shape": [2, 2], "strides": [2, 2]}),
+             X.Node("GlobalAveragePool", ["p"], ["g"]), X.Node("Flatten", ["g"], ["f"], "", {"axis": 1}),
+             X.Node("Gemm", ["f", "fc", "fb"], ["l"], "", {"transB": 1}), X.Node("Softmax", ["l"], ["y"], "", {"axis": -1})]
+    g = X.Graph(nodes, [T("w", w), T("cb", cb), T("s", bn[0]), T("b", bn[1]), T("m", bn[2]), T("v", bn[3]), T("fc", fc),
+                        T("fb", fb)], [X.ValueInfo("x", F32, [2, 3, 9, 9])], [X.ValueInfo("y", F32, [2, 5])])
+    stub = X.OnnxStub(X.save_model(X.Model(g)), handler=_oracle())
+    stub.inputs["x"].copyin_numpy(x)
+    stub.run()
+    xp = np.pad(x, ((0, 0), (0, 0), (1, 2), (0, 1)))
+    c = O.binary("add", O.conv2d(xp, w, 0, 0, 1, 1, 1, 1), cb.reshape(1, 8, 1, 1))
+    r = np.maximum(O.batch_norm(c, bn[2], bn[3], bn[0], bn[1], 1e-5), 0)
+    p = O.pool2d("max", r, 2, 2, 1, 1, 0, 0, 2, 2)
+    gap = O.pool2d("avg", p, p.shape[2], p.shape[3], 1, 1, 0, 0, 1, 1).reshape(2, 8)
+    ref = O.softmax(O.matmul(gap, fc, fb, False, True), -1)
+    np.testing.assert_array_equal(stub.outputs["y"].copyout_numpy(), ref)
+    assert len(stub.handler.ops) == 12  # + Pad, Reshape(bias), Add; Dropout -> Identity
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_llama_decode_export_import_roundtrip(dtype):
+    """build_llama_decode through OnnxExporter -> ONNX bytes -> OnnxStub on a fresh handler: same schedule, same logits."""
+    from infinitensor_b200 import graphs as G
+    cfg = G.LlamaConfig(layers=2, d_model=256, heads=2, head_dim=128, ffn=384, vocab=96, s_max=16, batch=3, dtype=dtype)
+    exp = X.OnnxExporter(_oracle())
+    ge = G.build_llama_decode(exp, cfg)
+    exp.data_malloc()
+    G.fill_llama_weights_host(ge)          # weight uploads are captured as initializers
+    blob = exp.save()
+    m = X.load_model(blob)
+    assert {n.op_type for n in m.graph.nodes} >= {"MatMul", "RMSNorm", "RoPE", "AttentionKVCache", "Gather", "Reshape", "Silu", "Mul", "Add"}
+    stub = X.OnnxStub(blob, handler=_oracle())
+    oh = _oracle()                          # the same graph built directly
+    gd = G.build_llama_decode(oh, cfg)
+    oh.data_malloc()
+    G.fill_llama_weights_host(gd)
+    rng = np.random.default_rng(5)
+    names_in = [t.name for t in exp._inputs]
+    assert len(stub.inputs) == len(names_in)
+    # feed token ids, positions and caches: the builder's input order is the exporter's
+    gi = [t for t in oh.tensors if t.is_input]
+    assert len(gi) == len(names_in)
+    for name, t in zip(names_in, gi):
+        shp, dt = t.shape(), t.dtype()
+        if dt == I64:
+            v = rng.integers(0, 7, size=shp).astype(np.int64)
+        else:
+            v = G.to_storage((rng.standard_normal(shp) * 0.5).astype(np.float32), dt)
+        t.copyin_numpy(v)
+        stub.inputs[name].copyin_numpy(v)
+    oh.run()
+    stub.run()
+    out_direct = [t for t in oh.tensors if t.is_output]
+    assert len(out_direct) == len(stub.outputs)
+    for t, (name, s) in zip(out_direct, stub.outputs.items()):
+        np.testing.assert_array_equal(t.copyout_numpy(), s.copyout_numpy())
+
+
+def test_exported_graph_plans_and_schedules_like_the_direct_build():
+    """Through the C++ host (planning-only runtime): the imported ONNX graph gets the same fused schedule."""
+    from infinitensor_b200 import backend as B, graphs as G
+    rt = B.HostPlanRuntime()
+    cfg = G.LlamaConfig(layers=2, d_model=512, heads=4, head_dim=128, ffn=1024, vocab=128, s_max=32, batch=16)
+    h = B.GraphHandler(rt)
+    G.build_llama_decode(h, cfg)
+    exp = X.OnnxExporter(B.GraphHandler(rt))
+    G.build_llama_decode(exp, cfg)
+    stub_h = B.GraphHandler(rt)
+    X.OnnxStub(exp.save(), handler=stub_h, upload=False)  # plan only: the planning runtime has no device to upload to
+    assert stub_h.schedule() == h.schedule()
+    res = B.GraphHandler(rt)
+    expr = X.OnnxExporter(res)
+    G.build_resnet50(expr, G.ResNetConfig(batch=2, image=64))
+    h2 = B.GraphHandler(rt)
+    X.OnnxStub(expr.save(), handler=h2, upload=False)
+    assert h2.schedule() == res.schedule() and sum(x.startswith("ConvBnAct") for x in h2.schedule()) == 53
+
+
+def test_unsupported_and_dynamic_inputs_are_refused_loudly():
+    g = X.Graph([X.Node("Resize", ["x"], ["y"])], [], [X.ValueInfo("x", F32, [1, 3, 4, 4])], [X.ValueInfo("y", F32, [1, 3, 8, 8])])
+    with pytest.raises(NotImplementedError, match="Resize"):
+        X.OnnxStub(X.Model(g), handler=_oracle())
+    g = X.Graph([X.Node("Reshape", ["x", "s"], ["y"])], [], [X.ValueInfo("x", F32, [2, 3]), X.ValueInfo("s", I64, [1])],
+                [X.ValueInfo("y", F32, [6])])
+    with pytest.raises(NotImplementedError, match="constant"):
+        X.OnnxStub(X.Model(g), handler=_oracle())
+    g = X.Graph([X.Node("Relu", ["nope"], ["y"])], [], [X.ValueInfo("x", F32, [2])], [X.ValueInfo("y", F32, [2])])
+    with pytest.raises(ValueError, match="missing input"):
+        X.OnnxStub(X.Model(g), handler=_oracle())
