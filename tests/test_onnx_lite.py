@@ -155,3 +155,38 @@ def test_unsupported_and_dynamic_inputs_are_refused_loudly():
     g = X.Graph([X.Node("Relu", ["nope"], ["y"])], [], [X.ValueInfo("x", F32, [2])], [X.ValueInfo("y", F32, [2])])
     with pytest.raises(ValueError, match="missing input"):
         X.OnnxStub(X.Model(g), handler=_oracle())
+
+
+def _roundtrip(build, fill, cfg):
+    exp = X.OnnxExporter(_oracle())
+    ge = build(exp, cfg)
+    exp.data_malloc()
+    fill(ge)
+    blob = exp.save()
+    stub = X.OnnxStub(blob, handler=_oracle())
+    oh = _oracle()
+    gd = build(oh, cfg)
+    oh.data_malloc()
+    fill(gd)
+    rng = np.random.default_rng(11)
+    from infinitensor_b200 import graphs as G
+    for name, t in zip([t.name for t in exp._inputs], [t for t in oh.tensors if t.is_input]):
+        shp, dt = t.shape(), t.dtype()
+        v = rng.integers(0, 7, size=shp).astype(np.int64) if dt == I64 else G.to_storage(rng.standard_normal(shp).astype(np.float32), dt)
+        t.copyin_numpy(v)
+        stub.inputs[name].copyin_numpy(v)
+    oh.run()
+    stub.run()
+    outs = [t for t in oh.tensors if t.is_output]
+    assert len(outs) == len(stub.outputs) >= 1
+    for t, s_ in zip(outs, stub.outputs.values()):
+        np.testing.assert_array_equal(t.copyout_numpy(), s_.copyout_numpy())
+    return X.load_model(blob)
+
+
+def test_gpt2_and_resnet_export_import_roundtrip():
+    from infinitensor_b200 import graphs as G
+    m = _roundtrip(G.build_gpt2, G.fill_gpt2_weights_host, G.GPT2Config.tiny(F32))
+    assert {"LayerNormalization", "Softmax", "Transpose", "Gelu", "Gather"} <= {n.op_type for n in m.graph.nodes}
+    m = _roundtrip(G.build_resnet50, G.fill_resnet_weights_host, G.ResNetConfig.tiny(F32))
+    assert {"Conv", "BatchNormalization", "Relu", "MaxPool", "AveragePool", "Gemm"} <= {n.op_type for n in m.graph.nodes}
