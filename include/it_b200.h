@@ -89,6 +89,10 @@ int it_b200_layernorm(int dtype, const void *x, const void *scale, const void *b
 /* ---- RMSNorm: replaces _rmsnorm_kernel (rms_norm.cu:36-54); eps 1e-5, round before weight ---- */
 int it_b200_rmsnorm(int dtype, const void *x, const void *w, void *y, int64_t tokens, int hidden,
                     void *stream);
+/* same, when `w` is a graph constant (written by no kernel of the step): the weight row is fetched ahead of the
+ * programmatic-dependent-launch wait */
+int it_b200_rmsnorm_constw(int dtype, const void *x, const void *w, void *y, int64_t tokens, int hidden,
+                           void *stream);
 
 /* ---- RoPE: replaces _rope_kernel (rope.cu:7-31); processes every (b, s) row.
  *      pos_dtype: ITB_I32 / ITB_U32 / ITB_I64. ---- */

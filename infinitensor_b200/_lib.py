@@ -42,6 +42,7 @@ _SIGS = {
     "it_b200_softmax": (c_int, [c_int, vp, vp, c_int64, c_int, c_int64, vp]),
     "it_b200_layernorm": (c_int, [c_int, vp, vp, vp, vp, c_int64, c_int, c_int64, c_int, c_int, c_float, vp]),
     "it_b200_rmsnorm": (c_int, [c_int, vp, vp, vp, c_int64, c_int, vp]),
+    "it_b200_rmsnorm_constw": (c_int, [c_int, vp, vp, vp, c_int64, c_int, vp]),
     "it_b200_rope": (c_int, [c_int, vp, c_int, vp, vp, c_int, c_int, c_int, c_int, vp]),
     "it_b200_transpose": (c_int, [c_int, vp, vp, c_int, i64p, i32p, vp]),
     "it_b200_concat": (c_int, [c_int, c_int, POINTER(vp), i64p, vp, c_int64, c_int64, vp]),

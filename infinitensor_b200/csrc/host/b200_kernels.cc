@@ -149,7 +149,8 @@ class RMSNormB200 : public CudaKernelWithoutConfig {
         auto x = op->getInputs(0), w = op->getInputs(1);
         int hidden = x->getDims().back();
         IT_ASSERT((int)w->size() == hidden, "RMSNorm: weight length must equal the hidden size");
-        CK(it_b200_rmsnorm(DT(x), P(x), P(w), P(op->getOutput()), (int64_t)(x->size() / hidden), hidden, S()), op);
+        auto fn = w->isWeight() ? it_b200_rmsnorm_constw : it_b200_rmsnorm;
+        CK(fn(DT(x), P(x), P(w), P(op->getOutput()), (int64_t)(x->size() / hidden), hidden, S()), op);
     }
 };
 class RoPEB200 : public CudaKernelWithoutConfig {

@@ -380,7 +380,10 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
         const char *e = std::getenv("ITB_TC_SMEM_KB");
         return e && e[0] ? std::atoi(e) : 0;
     }();
-    const int budget = (budget_kb ? budget_kb : p.mpad <= 64 ? 104 : 110) * 1024;  // two CTAs per SM: one CTA's epilogue overlaps the
+    // a grid that cannot fill the SMs anyway (GPT-2's 6..24-tile projections) takes the whole shared memory for a deep ring:
+    // one CTA per SM walking K serially is bound by bytes in flight / latency (3 stages: 0.4 us per k-tile, 6 stages: 0.2)
+    const bool small_grid = (int64_t)tiles_n * splitk * g.batch * p.m_chunks <= kNumSMs;
+    const int budget = (budget_kb ? budget_kb : p.mpad <= 64 ? 104 : small_grid ? 200 : 110) * 1024;  // two CTAs per SM: one CTA's epilogue overlaps the
                                                                                    // other's main loop (TMEM: 2 x <= 256 columns)
     p.stages = std::max(2, std::min(8, (budget - p.red_bytes - 2048 - 16 * p.mpad) / stage_bytes));
     p.w_kmajor = g.trans_b ? 1 : 0;

@@ -180,15 +180,40 @@ static int launch_rowop(const char *name, const T *x, T *y, const T *scale, cons
 
 // ------------------------------------------------------------------ RMSNorm
 // y = T( T(x * rsqrt(mean(x^2) + 1e-5)) * w )   (rms_norm.cu:46,52 -- round before weight)
-template <typename T>
+// ONE = the row fits one 16-byte vector per thread (hidden <= 8 * blockDim for 2-byte types): the row stays in registers
+// between the two passes.  WCONST = the weight is a graph constant: it is fetched ahead of griddepcontrol.wait.
+template <typename T, bool ONE, bool WCONST>
 __global__ void __launch_bounds__(512) rmsnorm_kernel(const T *__restrict__ x, const T *__restrict__ w,
                                                       T *__restrict__ y, int hidden, bool vec) {
     pdl_trigger();
-    pdl_wait();
     constexpr int V = Vec16<T>::N;
     __shared__ float red[32];
     const T *px = x + blockIdx.x * (int64_t)hidden;
     T *py = y + blockIdx.x * (int64_t)hidden;
+    if (ONE) {
+        const int i = threadIdx.x, nv = hidden / V;
+        Vec16<T> a, ww, o;
+        if (WCONST && i < nv) ww = ld16(w + i * V);
+        pdl_wait();
+        float ss = 0.f;
+        if (i < nv) {
+            a = ld16(px + i * V);
+            if (!WCONST) ww = ld16(w + i * V);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float f = to_f(a.v[j]);
+                ss += f * f;
+            }
+        }
+        const float r = rsqrtf(block_sum(ss, red) / (float)hidden + 0.00001f);
+        if (i < nv) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) o.v[j] = from_f<T>(round_t<T>(to_f(a.v[j]) * r) * to_f(ww.v[j]));
+            st16(py + i * V, o);
+        }
+        return;
+    }
+    pdl_wait();
     float ss = 0.f;
     if (vec) {
         int nv = hidden / V;
@@ -275,17 +300,33 @@ extern "C" int it_b200_layernorm(int dtype, const void *x, const void *scale, co
     return 0;
 }
 
-extern "C" int it_b200_rmsnorm(int dtype, const void *x, const void *w, void *y, int64_t tokens, int hidden,
-                               void *stream) {
+static int rmsnorm_impl(int dtype, const void *x, const void *w, void *y, int64_t tokens, int hidden, bool w_const,
+                        void *stream) {
     if (tokens == 0 || hidden == 0) return 0;
     ITB_DISPATCH_FLOAT(dtype, "rmsnorm", {
         bool vec = aligned16(x) && aligned16(w) && aligned16(y) && hidden % Vec16<T>::N == 0;
         int threads = hidden >= 4096 ? 512 : (hidden >= 1024 ? 256 : 128);
-        launch_k(rmsnorm_kernel<T>, dim3((unsigned)tokens), dim3(threads), 0, (cudaStream_t)stream, (const T *)x, (const T *)w,
-                                                                                  (T *)y, hidden, vec);
+        const bool one = vec && hidden / Vec16<T>::N <= threads;
+        auto go = [&](auto kern) {
+            launch_k(kern, dim3((unsigned)tokens), dim3(threads), 0, (cudaStream_t)stream, (const T *)x, (const T *)w, (T *)y,
+                     hidden, vec);
+        };
+        if (one && w_const) go(rmsnorm_kernel<T, true, true>);
+        else if (one) go(rmsnorm_kernel<T, true, false>);
+        else go(rmsnorm_kernel<T, false, false>);
     });
     ITB_LAUNCH_CHECK("rmsnorm");
     return 0;
+}
+
+extern "C" int it_b200_rmsnorm(int dtype, const void *x, const void *w, void *y, int64_t tokens, int hidden,
+                               void *stream) {
+    return rmsnorm_impl(dtype, x, w, y, tokens, hidden, false, stream);
+}
+
+extern "C" int it_b200_rmsnorm_constw(int dtype, const void *x, const void *w, void *y, int64_t tokens, int hidden,
+                                      void *stream) {
+    return rmsnorm_impl(dtype, x, w, y, tokens, hidden, true, stream);
 }
 
 extern "C" int it_b200_rope(int dtype, const void *pos, int pos_dtype, const void *x, void *y, int B, int S,

@@ -99,10 +99,11 @@ def layer_norm(x, scale, bias, eps, axis, dt=F32):
     return host(y)
 
 
-def rms_norm(x, w, dt=F32):
+def rms_norm(x, w, dt=F32, const_w=False):
     xd, wd = dev(x, dt), dev(w, dt)
     y = torch.empty_like(xd)
-    L.check(L.lib.it_b200_rmsnorm(dt, ptr(xd), ptr(wd), ptr(y), xd.numel() // x.shape[-1], x.shape[-1], stream()))
+    fn = L.lib.it_b200_rmsnorm_constw if const_w else L.lib.it_b200_rmsnorm
+    L.check(fn(dt, ptr(xd), ptr(wd), ptr(y), xd.numel() // x.shape[-1], x.shape[-1], stream()))
     sync()
     return host(y)
 

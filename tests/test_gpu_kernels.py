@@ -169,6 +169,7 @@ def test_rmsnorm_parity(K, shape, dt):
     tol = {F32: 1e-5, F16: 1e-3, BF16: 1e-2}[dt]
     got, ref = K.rms_norm(x, w, dt), oracle.rms_norm(x, w, dt)
     close(got, ref, tol, tol * 1e-2)
+    assert np.array_equal(got, K.rms_norm(x, w, dt, const_w=True))  # weight fetched ahead of the PDL wait: same bits
     if dt != F32:  # rounding order of rms_norm.cu:52 reproduced: overwhelmingly bit-identical
         assert np.mean(got == ref) > 0.98
 
