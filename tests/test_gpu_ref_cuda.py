@@ -35,7 +35,10 @@ def _p(t):
 
 
 def _ulps16(a, b):
-    return np.abs(a.astype(np.float16).view(np.int16).astype(np.int32) - b.astype(np.float16).view(np.int16).astype(np.int32))
+    def order(v):  # sign-magnitude bit pattern -> monotonic integer
+        bits = v.astype(np.float16).view(np.int16).astype(np.int32)
+        return np.where(bits < 0, -(bits & 0x7FFF), bits)
+    return np.abs(order(a) - order(b))
 
 
 @pytest.mark.parametrize("dt", [F32, F16])
