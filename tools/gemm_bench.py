@@ -15,6 +15,21 @@ SHAPES = [(16, 4096, 4096), (16, 4096, 11008), (16, 11008, 4096), (16, 4096, 320
 
 def run(impl, m, k, n, reps=40, nbuf=12):
     nbuf = max(2, min(nbuf, int(1.5e9 / (k * n * 2))))
+    if impl == "cublas":  # what the reference's matmulCublas dispatches to (matmul.cc:141-168), through torch.matmul
+        ws = [torch.randn(k, n, device="cuda", dtype=torch.bfloat16) * 0.02 for _ in range(nbuf)]
+        x = torch.randn(m, k, device="cuda", dtype=torch.bfloat16)
+        y = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+        for i in range(nbuf):
+            torch.matmul(x, ws[i], out=y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            torch.matmul(x, ws[i % nbuf], out=y)
+        e1.record()
+        e1.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        return us, (k * n + m * (k + n)) * 2 / 1e9 / (us * 1e-6)
     os.environ["ITB_GEMM_IMPL"] = impl
     ws = [torch.randn(k, n, device="cuda", dtype=torch.bfloat16) * 0.02 for _ in range(nbuf)]
     x = torch.randn(m, k, device="cuda", dtype=torch.bfloat16)
