@@ -15,7 +15,11 @@ file carries the two pieces the path needs from them and nothing else:
     initializers become weight tensors.
 
 `OnnxStub` takes any object with the GraphHandler surface (backend.GraphHandler in the product; the CPU tests hand it the
-oracle's handler).  No onnxsim pass is run: the graph is lowered as written.
+oracle's handler).  onnxsim is replaced by the one thing the reference needs it for: COMPILE-TIME CONSTANT FOLDING of the
+shape arithmetic exporters emit (Shape -> Gather -> Unsqueeze -> Concat -> Reshape, ConstantOfShape / Range / Equal / Where
+mask builders, Cast / Slice / Mul on those...).  All shapes are static here, so `Shape` of any tensor is a constant and
+every node whose inputs are constants is evaluated with numpy at load time (`_FOLD`); constants become device weights only
+when a lowered operator actually consumes them.
 """
 from __future__ import annotations
 
@@ -307,7 +311,9 @@ class OnnxStub:
         self.inputs: Dict[str, Any] = {}
         self.outputs: Dict[str, Any] = {}
         self.tensors: Dict[str, Any] = {}
-        self._data: Dict[str, TensorProto] = {}
+        self._data: Dict[str, TensorProto] = {}      # constants materialised as weight tensors (uploaded by init())
+        self._consts: Dict[str, Any] = {}              # every compile-time constant: name -> (ndarray, ONNX dtype)
+        self.folded: List[str] = []                    # op types evaluated at load time, in order (introspection / tests)
         self.use_naive_allocator = use_naive_allocator
         self._build()
         if upload:  # (False: build and plan only, e.g. on the planning runtime of the CPU tests)
@@ -327,8 +333,8 @@ class OnnxStub:
 
     # -- helpers
     def _const(self, name) -> Optional[np.ndarray]:
-        p = self._data.get(name)
-        return None if p is None else p.array
+        c = self._consts.get(name)
+        return None if c is None else c[0]
 
     def _ints(self, node, idx, attr=None, required=False):
         if len(node.inputs) > idx and node.inputs[idx]:
@@ -342,24 +348,36 @@ class OnnxStub:
             raise ValueError(f"{node.op_type} {node.name}: missing `{attr}`")
         return None
 
-    def _weight(self, name, proto: TensorProto):
-        t = self.handler.tensor(list(proto.dims), proto.data_type)
-        t.set_weight()
-        self.tensors[name] = t
-        self._data[name] = proto
+    def _set_const(self, name, arr, dtype=None):
+        arr = np.asarray(arr)
+        if dtype is None:
+            dtype = next((k for k, v in _NP.items() if k != BF16 and np.dtype(v) == arr.dtype), None)
+            if dtype is None:
+                raise NotImplementedError(f"constant {name}: numpy dtype {arr.dtype} has no ONNX code here")
+        self._consts[name] = (arr, dtype)
+
+    def _operand(self, name):
+        """Tensor for an operator input; a compile-time constant becomes a weight tensor on first use."""
+        t = self.tensors.get(name)
+        if t is None:
+            arr, dtype = self._consts[name]
+            t = self.handler.tensor(list(arr.shape), dtype)
+            t.set_weight()
+            self.tensors[name] = t
+            self._data[name] = TensorProto(name, list(arr.shape), dtype, arr)
         return t
 
     def _build(self):
         g, h, T = self.model.graph, self.handler, self.tensors
         for init in g.initializers:
-            self._weight(init.name, init)
+            self._set_const(init.name, init.array, init.data_type)
         for vi in g.inputs:
-            if vi.name not in T:
+            if vi.name not in self._consts:
                 T[vi.name] = h.tensor([d if d > 0 else 1 for d in vi.dims], vi.elem_type)
                 T[vi.name].set_input()
                 self.inputs[vi.name] = T[vi.name]
         # topological order over tensor availability (the file order of exported models is not guaranteed)
-        known = set(T)
+        known = set(T) | set(self._consts)
         pending = list(range(len(g.nodes)))
         order = []
         while pending:
@@ -376,10 +394,92 @@ class OnnxStub:
                                  f"{[x for x in bad.inputs if x and x not in known]}")
             pending = rest
         for i in order:
-            self._lower(g.nodes[i])
+            nd = g.nodes[i]
+            if not self._fold(nd):
+                self._lower(nd)
         for vo in g.outputs:
-            T[vo.name].set_output()
+            self._operand(vo.name).set_output()
             self.outputs[vo.name] = T[vo.name]
+
+    # ---- load-time evaluation of constant subgraphs (what the reference delegates to onnxsim)
+    def _fold(self, nd: Node) -> bool:
+        op, a = nd.op_type, nd.attrs
+        if op == "Constant":
+            v = a.get("value")
+            if isinstance(v, TensorProto):
+                self._set_const(nd.outputs[0], v.array, v.data_type)
+            elif "value_int" in a: self._set_const(nd.outputs[0], np.array(a["value_int"], np.int64))
+            elif "value_ints" in a: self._set_const(nd.outputs[0], np.array(a["value_ints"], np.int64))
+            elif "value_float" in a: self._set_const(nd.outputs[0], np.array(a["value_float"], np.float32))
+            elif "value_floats" in a: self._set_const(nd.outputs[0], np.array(a["value_floats"], np.float32))
+            else: raise NotImplementedError("Constant: unsupported value form")
+            return True
+        if op == "Shape":  # static shapes: the shape of ANY tensor is known now
+            src = nd.inputs[0]
+            shp = list(self._consts[src][0].shape) if src in self._consts else list(self.tensors[src].shape())
+            n = len(shp)
+            st, en = a.get("start", 0), a.get("end", n)
+            st, en = (st + n if st < 0 else st), (en + n if en < 0 else en)
+            self._set_const(nd.outputs[0], np.array(shp[max(st, 0):min(en, n)], np.int64))
+            self.folded.append(op)
+            return True
+        fn = self._FOLD.get(op)
+        if fn is None or not all(x == "" or x in self._consts for x in nd.inputs):
+            return False
+        ins = [None if x == "" else self._consts[x][0] for x in nd.inputs]
+        dts = [None if x == "" else self._consts[x][1] for x in nd.inputs]
+        out = fn(ins, a)
+        outs = out if isinstance(out, list) else [out]
+        for name, arr in zip(nd.outputs, outs):
+            arr = np.asarray(arr)
+            keep = op not in ("Cast", "Equal", "Less", "Greater", "Not", "ConstantOfShape", "Range") and dts and dts[0] is not None \
+                and np.dtype(_NP[dts[0]]) == arr.dtype
+            self._set_const(name, arr, dts[0] if keep else (a["to"] if op == "Cast" else None))
+        self.folded.append(op)
+        return True
+
+    @staticmethod
+    def _slice_np(ins, a):
+        x = ins[0]
+        starts = [int(v) for v in (ins[1] if len(ins) > 1 and ins[1] is not None else a["starts"])]
+        ends = [int(v) for v in (ins[2] if len(ins) > 2 and ins[2] is not None else a["ends"])]
+        axes = [int(v) for v in (ins[3] if len(ins) > 3 and ins[3] is not None else a.get("axes", range(len(starts))))]
+        steps = [int(v) for v in (ins[4] if len(ins) > 4 and ins[4] is not None else [1] * len(starts))]
+        sl = [slice(None)] * x.ndim
+        for s0, e0, ax, st in zip(starts, ends, axes, steps):
+            sl[ax] = slice(s0, e0, st)  # numpy clamps out-of-range bounds exactly like ONNX Slice
+        return x[tuple(sl)]
+
+    @staticmethod
+    def _div_np(a, b):
+        if np.issubdtype(np.asarray(a).dtype, np.integer):
+            return np.trunc(np.asarray(a, np.float64) / np.asarray(b, np.float64)).astype(np.asarray(a).dtype)  # C-style
+        return a / b
+
+    _FOLD = {
+        "Identity": lambda i, a: i[0],
+        "Gather": lambda i, a: np.take(i[0], np.asarray(i[1], np.int64), axis=a.get("axis", 0)),
+        "Unsqueeze": lambda i, a: np.expand_dims(i[0], tuple(int(v) for v in (i[1] if len(i) > 1 else a["axes"]))),
+        "Squeeze": lambda i, a: np.squeeze(i[0], tuple(int(v) for v in (i[1] if len(i) > 1 and i[1] is not None else a["axes"]))
+                                           if (len(i) > 1 and i[1] is not None) or "axes" in a else None),
+        "Concat": lambda i, a: np.concatenate([np.atleast_1d(v) for v in i], axis=a["axis"]),
+        "Cast": lambda i, a: i[0].astype(_NP[a["to"]]),
+        "Slice": lambda i, a: OnnxStub._slice_np(i, a),
+        "Add": lambda i, a: i[0] + i[1], "Sub": lambda i, a: i[0] - i[1], "Mul": lambda i, a: i[0] * i[1],
+        "Div": lambda i, a: OnnxStub._div_np(i[0], i[1]),
+        "Neg": lambda i, a: -i[0], "Sqrt": lambda i, a: np.sqrt(i[0]),
+        "Min": lambda i, a: np.minimum(i[0], i[1]), "Max": lambda i, a: np.maximum(i[0], i[1]),
+        "Equal": lambda i, a: np.equal(i[0], i[1]), "Less": lambda i, a: np.less(i[0], i[1]),
+        "Greater": lambda i, a: np.greater(i[0], i[1]), "Not": lambda i, a: np.logical_not(i[0]),
+        "Where": lambda i, a: np.where(i[0], i[1], i[2]),
+        "Reshape": lambda i, a: i[0].reshape([i[0].shape[k] if v == 0 else int(v) for k, v in enumerate(i[1])]),
+        "Expand": lambda i, a: np.broadcast_to(i[0], np.broadcast_shapes(i[0].shape, tuple(int(v) for v in i[1]))).copy(),
+        "Transpose": lambda i, a: np.transpose(i[0], a.get("perm")),
+        "ReduceProd": lambda i, a: np.prod(i[0], axis=tuple(a["axes"]) if "axes" in a else None, keepdims=bool(a.get("keepdims", 1))),
+        "ConstantOfShape": lambda i, a: np.full([int(v) for v in i[0]], a["value"].array.reshape(-1)[0] if "value" in a else np.float32(0),
+                                                dtype=a["value"].array.dtype if "value" in a else np.float32),
+        "Range": lambda i, a: np.arange(i[0], i[1], i[2]).astype(np.asarray(i[0]).dtype),
+    }
 
     _UNARY = {"Relu": "relu", "Silu": "silu", "Gelu": "gelu", "Sigmoid": "sigmoid", "Tanh": "tanh", "Erf": "erf",
               "Abs": "abs", "Sqrt": "sqrt", "Neg": "neg", "HardSigmoid": "hardSigmoid", "HardSwish": "hardSwish",
@@ -391,7 +491,7 @@ class OnnxStub:
 
     def _lower(self, nd: Node):
         h, T, op, a = self.handler, self.tensors, nd.op_type, nd.attrs
-        I = lambda k: T[nd.inputs[k]]
+        I = lambda k: self._operand(nd.inputs[k])
         out0 = nd.outputs[0] if nd.outputs else None
         if op in self._UNARY:
             T[out0] = getattr(h, self._UNARY[op])(I(0), None)
@@ -469,7 +569,7 @@ class OnnxStub:
         elif op == "Unsqueeze":
             T[out0] = h.unsqueeze(I(0), None, self._ints(nd, 1, "axes", required=True))
         elif op == "Concat":
-            T[out0] = h.concat([T[x] for x in nd.inputs], None, a["axis"])
+            T[out0] = h.concat([self._operand(x) for x in nd.inputs], None, a["axis"])
         elif op == "Split":
             axis = a.get("axis", 0)
             split = self._ints(nd, 1, "split")
@@ -504,11 +604,6 @@ class OnnxStub:
             outs = h.allGather(I(0), None, len(nd.outputs))
             for name, t in zip(nd.outputs, outs):
                 T[name] = t
-        elif op == "Constant":
-            value = a.get("value")
-            if not isinstance(value, TensorProto):
-                raise NotImplementedError("Constant: only the `value` tensor form is supported")
-            self._weight(out0, value)
         else:
             raise NotImplementedError(f'Unsupported operator "{op}" (no B200 kernel behind it)')
 

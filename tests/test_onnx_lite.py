@@ -190,3 +190,45 @@ def test_gpt2_and_resnet_export_import_roundtrip():
     assert {"LayerNormalization", "Softmax", "Transpose", "Gelu", "Gather"} <= {n.op_type for n in m.graph.nodes}
     m = _roundtrip(G.build_resnet50, G.fill_resnet_weights_host, G.ResNetConfig.tiny(F32))
     assert {"Conv", "BatchNormalization", "Relu", "MaxPool", "AveragePool", "Gemm"} <= {n.op_type for n in m.graph.nodes}
+
+
+def test_constant_folding_replaces_onnxsim_for_exporter_shape_arithmetic():
+    """Shape -> Gather -> Unsqueeze -> Concat -> Reshape and a Range / Less / Cast / Mul mask builder (what torch.onnx.export
+    leaves behind and the reference removes with onnxsim) are evaluated at load time; only real compute reaches the handler."""
+    import oracle as O
+    C = lambda name, arr: X.Node("Constant", [], [name], "", {"value": X.TensorProto("", list(np.shape(arr)), I64 if np.asarray(arr).dtype == np.int64 else F32, np.asarray(arr))})
+    nodes = [
+        X.Node("Shape", ["x"], ["s"]), C("i0", np.array(0, np.int64)), X.Node("Gather", ["s", "i0"], ["b"], "", {"axis": 0}),
+        X.Node("Unsqueeze", ["b"], ["b1"], "", {"axes": [0]}), C("m1", np.array([-1], np.int64)),
+        X.Node("Concat", ["b1", "m1"], ["shp"], "", {"axis": 0}), X.Node("Reshape", ["x", "shp"], ["y"]),
+        X.Node("Shape", ["y"], ["sy"], "", {"start": 1}), C("zero", np.array(0, np.int64)), C("one", np.array(1, np.int64)),
+        X.Node("Squeeze", ["sy"], ["n"]), X.Node("Range", ["zero", "n", "one"], ["r"]), C("half", np.array(12, np.int64)),
+        X.Node("Less", ["r", "half"], ["lt"]), X.Node("Cast", ["lt"], ["ltf"], "", {"to": F32}), C("neg", np.array(-2.0, np.float32)),
+        X.Node("Mul", ["ltf", "neg"], ["bias"]), X.Node("Add", ["y", "bias"], ["z"]), X.Node("Softmax", ["z"], ["out"], "", {"axis": -1}),
+        # a constant-only branch nobody consumes must not create device tensors
+        X.Node("ConstantOfShape", ["shp0"], ["dead"], "", {"value": X.TensorProto("", [1], F32, np.array([3.0], np.float32))}),
+    ]
+    g = X.Graph(nodes, [X.TensorProto("shp0", [2], I64, np.array([4, 5], np.int64))], [X.ValueInfo("x", F32, [2, 3, 8])],
+                [X.ValueInfo("out", F32, [2, 24])])
+    stub = X.OnnxStub(X.save_model(X.Model(g)), handler=_oracle())
+    assert stub.folded == ["Shape", "Gather", "Unsqueeze", "Concat", "Shape", "Squeeze", "Range", "Less", "Cast", "Mul", "ConstantOfShape"]
+    assert len(stub.handler.ops) == 3                      # Reshape, Add, Softmax
+    assert sorted(stub._data) == ["bias"]                  # the only constant that became a device weight
+    x = np.random.default_rng(2).standard_normal((2, 3, 8)).astype(np.float32)
+    stub.inputs["x"].copyin_numpy(x)
+    stub.run()
+    bias = np.where(np.arange(24) < 12, np.float32(-2.0), np.float32(0.0)).astype(np.float32)
+    np.testing.assert_array_equal(stub.outputs["out"].copyout_numpy(), O.softmax(O.binary("add", x.reshape(2, 24), bias), -1))
+
+
+def test_fold_helpers_follow_onnx_semantics():
+    f = X.OnnxStub._FOLD
+    a = np.arange(24, dtype=np.int64).reshape(2, 3, 4)
+    assert np.array_equal(X.OnnxStub._slice_np([a, np.array([1]), np.array([2 ** 40]), np.array([2]), np.array([2])], {}), a[:, :, 1::2])
+    assert np.array_equal(X.OnnxStub._slice_np([a, np.array([-1]), np.array([-5]), np.array([1]), np.array([-1])], {}), a[:, ::-1, :][:, :3, :])
+    assert f["Div"]([np.array([7, -7], np.int64), np.array([2, 2], np.int64)], {}).tolist() == [3, -3]  # truncation, not floor
+    assert f["Expand"]([np.array([[1], [2]], np.int64), np.array([1, 3], np.int64)], {}).tolist() == [[1, 1, 1], [2, 2, 2]]
+    assert f["Reshape"]([a, np.array([0, -1], np.int64)], {}).shape == (2, 12)
+    assert f["Squeeze"]([np.zeros((1, 3, 1))], {}).shape == (3,) and f["Squeeze"]([np.zeros((1, 3, 1)), np.array([0])], {}).shape == (3, 1)
+    assert f["ConstantOfShape"]([np.array([2, 2], np.int64)], {}).dtype == np.float32
+    assert f["Where"]([np.array([True, False]), np.array([1, 2]), np.array([3, 4])], {}).tolist() == [1, 4]
