@@ -299,3 +299,44 @@ def test_fused_schedule_and_alias_plan(B, monkeypatch):
     a = h4.tensor([2, 3, 4], 1); a.set_input()
     assert h4.schedule() == [] and h4.transpose(a, None, [0, 2, 1]) is not None
     assert h4.schedule() == ["Single:Transpose"]                          # a real permutation is never an alias
+
+
+def test_conv_bn_act_matcher_edge_cases(B):
+    """The ConvBnAct step only swallows single-consumer links, same-shape residuals and fp32 BatchNorm statistics."""
+    F16, F32 = 10, 1
+    rt = B.HostPlanRuntime()
+
+    def net(build):
+        h = B.GraphHandler(rt)
+        x = h.tensor([2, 16, 8, 8], F16); x.set_input()
+        w = h.tensor([16, 16, 3, 3], F16); w.set_weight()
+        stats = [h.tensor([16], F32) for _ in range(4)]
+        for s in stats: s.set_weight()
+        build(h, x, w, stats)
+        return h.schedule()
+
+    def bn(h, t, stats, dtype_stats=None):
+        return h.batchNormalization(t, None, stats[0], stats[1], stats[2], stats[3], 0.9, 1e-5, False)
+
+    # plain chain, BN output is the graph output
+    sc = net(lambda h, x, w, s: bn(h, h.conv(x, w, None, 1, 1, 1, 1, 1, 1), s).set_output())
+    assert sc == ["ConvBnAct:Conv+BatchNormalization"]
+    # conv output read twice: nothing may be folded (the second reader needs the tensor)
+    def two_readers(h, x, w, s):
+        c = h.conv(x, w, None, 1, 1, 1, 1, 1, 1)
+        h.relu(c, None).set_output()
+        bn(h, c, s).set_output()
+    sc = net(two_readers)
+    assert sorted(sc) == ["Single:BatchNormalization", "Single:Conv", "Single:Relu"]
+    # residual of another shape (broadcast add): chain stops at the BatchNorm
+    def bcast(h, x, w, s):
+        r = h.tensor([1, 16, 1, 1], F16); r.set_input()
+        h.relu(h.add(bn(h, h.conv(x, w, None, 1, 1, 1, 1, 1, 1), s), r, None), None).set_output()
+    sc = net(bcast)
+    assert sc == ["ConvBnAct:Conv+BatchNormalization", "Single:Add", "Single:Relu"]
+    # same-shape residual + relu: everything in one step, the residual producer scheduled before it
+    def residual(h, x, w, s):
+        r = h.relu(x, None)
+        h.relu(h.add(r, bn(h, h.conv(x, w, None, 1, 1, 1, 1, 1, 1), s), None), None).set_output()
+    sc = net(residual)
+    assert sc == ["Single:Relu", "ConvBnAct:Conv+BatchNormalization+Add+Relu"]
