@@ -25,6 +25,17 @@ def test_llama_decode_batch16_wide():
     run_llama_parity(cfg=cfg, pos=77, steps=2)
 
 
+def test_llama_decode_baseline_width():
+    """The BASELINE config's own per-layer shapes -- d = 4096, 32 heads, ffn = 11008, vocab = 32000, S_max = 1024, B = 16,
+    position 511, bf16 -- two layers deep (the oracle stays within seconds): every GEMM shape of the bench (grouped q/k/v
+    and gate/up, o, down, the 32000-wide logits), the 512-head streaming attention with folded RoPE, the fused schedule and
+    CUDA-graph replay, end to end against the oracle."""
+    from infinitensor_b200 import graphs as G
+    from tests.smoke_impl import run_llama_parity
+    cfg = G.LlamaConfig(layers=2, d_model=4096, heads=32, head_dim=128, ffn=11008, vocab=32000, s_max=1024, batch=16, dtype=BF16)
+    run_llama_parity(cfg=cfg, pos=511, steps=1)
+
+
 def test_matmul_512_config1():
     """BASELINE config #1: MatmulObj fp32 512^3 through the graph API."""
     from infinitensor_b200 import backend as B, graphs as G
