@@ -361,6 +361,8 @@ class OnnxStub:
         t = self.tensors.get(name)
         if t is None:
             arr, dtype = self._consts[name]
+            if arr.ndim == 0:
+                arr = arr.reshape(1)  # scalars travel as [1] (same broadcasting; rank-0 device tensors are avoided)
             t = self.handler.tensor(list(arr.shape), dtype)
             t.set_weight()
             self.tensors[name] = t

@@ -232,3 +232,72 @@ def test_fold_helpers_follow_onnx_semantics():
     assert f["Squeeze"]([np.zeros((1, 3, 1))], {}).shape == (3,) and f["Squeeze"]([np.zeros((1, 3, 1)), np.array([0])], {}).shape == (3, 1)
     assert f["ConstantOfShape"]([np.array([2, 2], np.int64)], {}).dtype == np.float32
     assert f["Where"]([np.array([True, False]), np.array([1, 2]), np.array([3, 4])], {}).tolist() == [1, 4]
+
+
+def test_hf_style_gpt2_block_with_exporter_shape_arithmetic():
+    """One GPT-2 block the way torch.onnx.export writes it (Conv1D as MatMul + Add, Split, Shape-driven Reshapes, a causal mask
+    sliced out of a constant tril buffer with Shape / Sub / Slice, Where, the tanh GELU spelled with Pow / Tanh): loads without
+    onnx / onnxsim, folds every shape computation, and matches a direct numpy transcription."""
+    rng = np.random.default_rng(7)
+    S, D, H, P = 6, 16, 2, 8
+    dh = D // H
+    W = lambda *s: (rng.standard_normal(s) * 0.2).astype(np.float32)
+    init = {"ln_g": 1 + W(D) * 0.1, "ln_b": W(D) * 0.1, "w_qkv": W(D, 3 * D), "b_qkv": W(3 * D), "w_o": W(D, D), "b_o": W(D),
+            "w_fc": W(D, 4 * D), "b_fc": W(4 * D), "w_pr": W(4 * D, D), "b_pr": W(D),
+            "tril": np.tril(np.ones((1, 1, P, P), np.bool_)), "neg": np.array(-1e4, np.float32),
+            "scale": np.array(np.sqrt(dh), np.float32), "three": np.array(3.0, np.float32), "c0": np.array(0.044715, np.float32),
+            "c1": np.array(np.sqrt(2 / np.pi), np.float32), "one": np.array(1.0, np.float32), "halfc": np.array(0.5, np.float32)}
+    I = lambda v: X.TensorProto("", list(np.shape(v)), I64, np.asarray(v, np.int64))
+    C = lambda name, v: X.Node("Constant", [], [name], "", {"value": I(v)})
+    N = X.Node
+    nodes = [
+        N("LayerNormalization", ["x", "ln_g", "ln_b"], ["h"], "", {"axis": -1, "epsilon": 1e-5}),
+        N("MatMul", ["h", "w_qkv"], ["qkv0"]), N("Add", ["qkv0", "b_qkv"], ["qkv"]),
+        N("Split", ["qkv", "split3"], ["q", "k", "v"], "", {"axis": 2}), C("split3", [D, D, D]),
+        # new_shape = concat(shape(q)[:-1], [H, dh])
+        N("Shape", ["q"], ["qs"]), C("i0", 0), C("i1", 1), N("Gather", ["qs", "i0"], ["bdim"]), N("Gather", ["qs", "i1"], ["sdim"]),
+        N("Unsqueeze", ["bdim", "ax0"], ["b1"]), N("Unsqueeze", ["sdim", "ax0"], ["s1"]), C("ax0", [0]), C("hd", [H, dh]),
+        N("Concat", ["b1", "s1", "hd"], ["hshape"], "", {"axis": 0}),
+        N("Reshape", ["q", "hshape"], ["q4"]), N("Reshape", ["k", "hshape"], ["k4"]), N("Reshape", ["v", "hshape"], ["v4"]),
+        N("Transpose", ["q4"], ["qt"], "", {"perm": [0, 2, 1, 3]}), N("Transpose", ["k4"], ["kt"], "", {"perm": [0, 2, 3, 1]}),
+        N("Transpose", ["v4"], ["vt"], "", {"perm": [0, 2, 1, 3]}),
+        N("MatMul", ["qt", "kt"], ["sc0"]), N("Div", ["sc0", "scale"], ["sc"]),
+        # causal mask = tril[:, :, k_len - q_len : k_len, :k_len]
+        N("Shape", ["sc"], ["scs"]), C("im2", -2), C("im1", -1), N("Gather", ["scs", "im2"], ["qlen"]), N("Gather", ["scs", "im1"], ["klen"]),
+        N("Sub", ["klen", "qlen"], ["off"]), N("Unsqueeze", ["off", "ax0"], ["off1"]), N("Unsqueeze", ["klen", "ax0"], ["kl1"]),
+        C("ax2", [2]), C("ax3", [3]), C("z1", [0]), C("st1", [1]),
+        N("Slice", ["tril", "off1", "kl1", "ax2", "st1"], ["m0"]), N("Slice", ["m0", "z1", "kl1", "ax3", "st1"], ["mask"]),
+        N("Where", ["mask", "sc", "neg"], ["scm"]), N("Softmax", ["scm"], ["pr"], "", {"axis": -1}),
+        N("MatMul", ["pr", "vt"], ["ctx"]), N("Transpose", ["ctx"], ["ctxt"], "", {"perm": [0, 2, 1, 3]}),
+        C("dmodel", [D]), N("Concat", ["b1", "s1", "dmodel"], ["mshape"], "", {"axis": 0}), N("Reshape", ["ctxt", "mshape"], ["merged"]),
+        N("MatMul", ["merged", "w_o"], ["o0"]), N("Add", ["o0", "b_o"], ["o"]), N("Add", ["x", "o"], ["r1"]),
+        N("MatMul", ["r1", "w_fc"], ["f0"]), N("Add", ["f0", "b_fc"], ["f"]),
+        N("Pow", ["f", "three"], ["f3"]), N("Mul", ["f3", "c0"], ["f3c"]), N("Add", ["f", "f3c"], ["inner"]), N("Mul", ["inner", "c1"], ["arg"]),
+        N("Tanh", ["arg"], ["th"]), N("Add", ["th", "one"], ["th1"]), N("Mul", ["f", "halfc"], ["fh"]), N("Mul", ["fh", "th1"], ["gelu"]),
+        N("MatMul", ["gelu", "w_pr"], ["p0"]), N("Add", ["p0", "b_pr"], ["pp"]), N("Add", ["r1", "pp"], ["y"]),
+    ]
+    dt = lambda v: 9 if v.dtype == np.bool_ else F32
+    g = X.Graph(nodes, [X.TensorProto(k, list(v.shape), dt(v), v) for k, v in init.items()],
+                [X.ValueInfo("x", F32, [1, S, D])], [X.ValueInfo("y", F32, [1, S, D])])
+    stub = X.OnnxStub(X.save_model(X.Model(g)), handler=_oracle())
+    lowered = {"Shape", "Gather", "Unsqueeze", "Concat", "Sub", "Slice"}
+    assert lowered <= set(stub.folded) and stub.folded.count("Slice") == 2
+    x = rng.standard_normal((1, S, D)).astype(np.float32)
+    stub.inputs["x"].copyin_numpy(x)
+    stub.run()
+    # float64 transcription
+    f8 = {k: v.astype(np.float64) for k, v in init.items() if v.dtype == np.float32}
+    xx = x.astype(np.float64)
+    mu, var = xx.mean(-1, keepdims=True), xx.var(-1, keepdims=True)
+    hh = (xx - mu) / np.sqrt(var + 1e-5) * f8["ln_g"] + f8["ln_b"]
+    qkv = hh @ f8["w_qkv"] + f8["b_qkv"]
+    q, k, v = [t.reshape(1, S, H, dh).transpose(0, 2, 1, 3) for t in np.split(qkv, 3, axis=2)]
+    sc = q @ k.transpose(0, 1, 3, 2) / np.sqrt(dh)
+    sc = np.where(init["tril"][:, :, :S, :S], sc, -1e4)
+    pr = np.exp(sc - sc.max(-1, keepdims=True)); pr /= pr.sum(-1, keepdims=True)
+    o = (pr @ v).transpose(0, 2, 1, 3).reshape(1, S, D) @ f8["w_o"] + f8["b_o"]
+    r1 = xx + o
+    f = r1 @ f8["w_fc"] + f8["b_fc"]
+    gelu = 0.5 * f * (1 + np.tanh(np.sqrt(2 / np.pi) * (f + 0.044715 * f ** 3)))
+    ref = r1 + gelu @ f8["w_pr"] + f8["b_pr"]
+    np.testing.assert_allclose(stub.outputs["y"].copyout_numpy(), ref, rtol=2e-4, atol=2e-5)
