@@ -279,7 +279,14 @@ def test_hf_style_gpt2_block_with_exporter_shape_arithmetic():
     dt = lambda v: 9 if v.dtype == np.bool_ else F32
     g = X.Graph(nodes, [X.TensorProto(k, list(v.shape), dt(v), v) for k, v in init.items()],
                 [X.ValueInfo("x", F32, [1, S, D])], [X.ValueInfo("y", F32, [1, S, D])])
-    stub = X.OnnxStub(X.save_model(X.Model(g)), handler=_oracle())
+    blob = X.save_model(X.Model(g))
+    # the C++ host accepts the lowered graph too (shape inference + memory plan on the planning-only runtime)
+    from infinitensor_b200 import backend as B
+    hp = B.GraphHandler(B.HostPlanRuntime())
+    sp = X.OnnxStub(blob, handler=hp, upload=False)
+    hp.data_malloc()
+    assert sp.outputs["y"].shape() == [1, S, D] and not any(s_.startswith("Single:Shape") for s_ in hp.schedule())
+    stub = X.OnnxStub(blob, handler=_oracle())
     lowered = {"Shape", "Gather", "Unsqueeze", "Concat", "Sub", "Slice"}
     assert lowered <= set(stub.folded) and stub.folded.count("Slice") == 2
     x = rng.standard_normal((1, S, D)).astype(np.float32)
