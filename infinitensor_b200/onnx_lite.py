@@ -314,6 +314,7 @@ class OnnxStub:
         self._data: Dict[str, TensorProto] = {}      # constants materialised as weight tensors (uploaded by init())
         self._consts: Dict[str, Any] = {}              # every compile-time constant: name -> (ndarray, ONNX dtype)
         self.folded: List[str] = []                    # op types evaluated at load time, in order (introspection / tests)
+        self.lowered_nodes: List[Node] = []            # the nodes that reached the handler, in topological order
         self.use_naive_allocator = use_naive_allocator
         self._build()
         if upload:  # (False: build and plan only, e.g. on the planning runtime of the CPU tests)
@@ -399,6 +400,7 @@ class OnnxStub:
             nd = g.nodes[i]
             if not self._fold(nd):
                 self._lower(nd)
+                self.lowered_nodes.append(nd)
         for vo in g.outputs:
             self._operand(vo.name).set_output()
             self.outputs[vo.name] = T[vo.name]
@@ -827,3 +829,184 @@ class OnnxExporter:
 
     def save(self) -> bytes:
         return save_model(self.model())
+
+
+# ------------------------------------------------------------------------------------------------ model-level passes
+def _planning_handler():
+    from . import backend
+    return backend.GraphHandler(backend.HostPlanRuntime())
+
+
+def simplify(model, new_handler=None) -> Model:
+    """What the reference runs onnxsim for (onnx.py:49-58): the constant subgraphs -- exporter shape arithmetic -- are evaluated
+    and removed; their results become initializers.  Shapes come from lowering the model once on a fresh handler from
+    `new_handler()` (default: the planning-only runtime, no GPU needed).  Nodes come out in topological order."""
+    m = load_model(model)
+    stub = OnnxStub(m, handler=(new_handler or _planning_handler)(), upload=False)
+    kept = [nd for nd in stub.lowered_nodes]
+    used = {x for nd in kept for x in nd.inputs} | {o.name for o in m.graph.outputs}
+    inits = [TensorProto(name, list(arr.shape), dt, arr) for name, (arr, dt) in stub._consts.items() if name in used]
+    inputs = [ValueInfo(v.name, v.elem_type, [d if d > 0 else 1 for d in v.dims]) for v in m.graph.inputs if v.name not in stub._consts]
+    return Model(Graph(kept, inits, inputs, list(m.graph.outputs), m.graph.name), m.ir_version, m.opset)
+
+
+def tensor_shapes(model, new_handler=None) -> Dict[str, List[int]]:
+    """Static shape of every tensor of the model (constants included), from one lowering pass."""
+    stub = OnnxStub(load_model(model), handler=(new_handler or _planning_handler)(), upload=False)
+    shapes = {name: list(arr.shape) for name, (arr, _) in stub._consts.items()}
+    shapes.update({name: list(t.shape()) for name, t in stub.tensors.items()})
+    return shapes
+
+
+def parallel_model(model, world: int, rank: int, new_handler=None) -> Model:
+    """Tensor-parallel rewrite of an ONNX model for rank `rank` of `world` -- the job of the reference's
+    examples/distributed/parallel_opt.py::parallel_model, on this module's Model classes:
+
+      * a MatMul / Gemm with a constant weight fed by a REPLICATED activation is column-split (per group when a Split of the
+        packed result follows within two nodes); its output is sharded on the last axis;
+      * fed by an activation sharded on its last axis it is row-split, and a `ReduceSum(communicator=0)` node -- which the
+        frontend lowers to AllReduceSum (onnx.py:917-923) -- makes the result replicated again; a Gemm bias is added once, after;
+      * the last MatMul (the one producing a graph output) stays replicated, like embeddings, norms and the residual stream;
+      * placements flow through unary / binary ops, RoPE, Transpose (through the permutation), Split, AttentionKVCache (heads;
+        the cache INPUTS shrink on the head axis) and Reshape (the output axis whose row-major prefix product equals the
+        sharded input axis' takes the division).
+    The model is simplified first, so Reshape targets are plain initializers."""
+    m = simplify(model, new_handler)
+    if world == 1:
+        return m
+    shapes = tensor_shapes(m, new_handler)
+    g = m.graph
+    consts = {t.name: t for t in g.initializers}
+    outputs = {o.name for o in g.outputs}
+    inputs = {v.name: v for v in g.inputs}
+    place: Dict[str, Any] = {}          # tensor -> sharded axis (int); absent = replicated
+    nodes: List[Node] = []
+    fresh = [0]
+
+    def shard_array(arr, axis, groups=1):
+        axis %= arr.ndim
+        n = arr.shape[axis]
+        if n % (groups * world):
+            raise ValueError(f"axis of {n} elements does not split into {groups} groups x {world} ranks")
+        seg = n // groups // world
+        view = arr.reshape(arr.shape[:axis] + (groups, n // groups) + arr.shape[axis + 1:])
+        return np.ascontiguousarray(np.take(view, range(rank * seg, (rank + 1) * seg), axis=axis + 1)).reshape(
+            arr.shape[:axis] + (n // world,) + arr.shape[axis + 1:])
+
+    def new_const(base, arr, dtype):
+        fresh[0] += 1
+        name = f"{base}@tp{fresh[0]}"
+        consts[name] = TensorProto(name, list(arr.shape), dtype, arr)
+        return name
+
+    def last_axis(name):
+        return len(shapes[name]) - 1
+
+    unary_like = set(OnnxStub._UNARY) | {"Softmax", "Cast", "Dropout"}
+    for idx, nd in enumerate(g.nodes):
+        nd = Node(nd.op_type, list(nd.inputs), list(nd.outputs), nd.name, dict(nd.attrs))
+        op = nd.op_type
+        if op in ("MatMul", "Gemm") and len(nd.inputs) > 1 and nd.inputs[1] in consts and len(shapes[nd.inputs[1]]) == 2:
+            nxt = g.nodes[idx + 1] if idx + 1 < len(g.nodes) else None
+            if nd.outputs[0] in outputs or (nxt is not None and nxt.outputs and nxt.outputs[0] in outputs):
+                nodes.append(nd)  # the final projection stays replicated
+                continue
+            x, w = nd.inputs[0], consts[nd.inputs[1]]
+            trans_b = int(nd.attrs.get("transB", 0)) if op == "Gemm" else 0
+            groups = next((len(s.outputs) for s in g.nodes[idx + 1:idx + 3] if s.op_type == "Split"), 1)
+            bias = nd.inputs[2] if len(nd.inputs) > 2 and nd.inputs[2] else None
+            if x not in place:                       # column split
+                nd.inputs[1] = new_const(w.name, shard_array(w.array, 0 if trans_b else 1, groups), w.data_type)
+                if bias is not None:
+                    b = consts[bias]
+                    nd.inputs[2] = new_const(bias, shard_array(b.array, b.array.ndim - 1, groups), b.data_type)
+                place[nd.outputs[0]] = last_axis(nd.outputs[0])
+                nodes.append(nd)
+            elif place[x] == last_axis(x):           # row split + all-reduce (+ bias once, after the reduction)
+                nd.inputs[1] = new_const(w.name, shard_array(w.array, 1 if trans_b else 0), w.data_type)
+                out = nd.outputs[0]
+                partial = out + ":partial"
+                nd.outputs[0] = partial
+                nd.inputs = nd.inputs[:2]
+                nodes.append(nd)
+                reduced = out if bias is None else out + ":reduced"
+                nodes.append(Node("ReduceSum", [partial], [reduced], nd.name + "/all_reduce", {"communicator": 0, "noop_with_empty_axes": 1}))
+                if bias is not None:
+                    nodes.append(Node("Add", [reduced, bias], [out], nd.name + "/bias"))
+            else:
+                raise NotImplementedError(f"{op} {nd.name}: activation sharded on axis {place[x]}, not the contraction axis")
+            continue
+        ins = [x for x in nd.inputs if x]
+        sharded = [x for x in ins if x in place]
+        if not sharded:
+            nodes.append(nd)
+            continue
+        if op in unary_like:
+            place[nd.outputs[0]] = place[nd.inputs[0]]
+        elif op in OnnxStub._BINARY or op == "Where":
+            acts = [x for x in ins if x not in consts]
+            axes = {place.get(x) for x in acts}
+            if len(axes) != 1:
+                raise NotImplementedError(f"{op} {nd.name}: operands are placed differently ({axes})")
+            ax = axes.pop()
+            out_rank = len(shapes[nd.outputs[0]])
+            for k, x in enumerate(nd.inputs):
+                if x in consts:  # a broadcast constant that spans the sharded axis is split with it
+                    c = consts[x]
+                    cax = ax - (out_rank - c.array.ndim)
+                    if cax >= 0 and c.array.shape[cax] == shapes[nd.outputs[0]][ax]:
+                        nd.inputs[k] = new_const(x, shard_array(c.array, cax), c.data_type)
+            place[nd.outputs[0]] = ax
+        elif op == "RoPE":
+            place[nd.outputs[0]] = place[nd.inputs[1]]
+        elif op == "Transpose":
+            perm = [int(p) for p in nd.attrs.get("perm") or range(len(shapes[nd.inputs[0]]))[::-1]]
+            place[nd.outputs[0]] = perm.index(place[nd.inputs[0]])
+        elif op == "Reshape":
+            src, k = shapes[nd.inputs[0]], place[nd.inputs[0]]
+            tgt = consts[nd.inputs[1]]
+            dims = [int(v) for v in tgt.array]
+            dims = [src[i] if v == 0 else v for i, v in enumerate(dims)]
+            if -1 in dims:
+                dims[dims.index(-1)] = int(np.prod(src)) // max(int(np.prod([v for v in dims if v != -1])), 1)
+            left = int(np.prod(src[:k]))
+            cand = [j for j in range(len(dims)) if int(np.prod(dims[:j])) == left and dims[j] % world == 0 and dims[j] >= world]
+            if not cand:
+                raise NotImplementedError(f"Reshape {nd.name}: no output axis lines up with sharded input axis {k} ({src} -> {dims})")
+            j = cand[-1]
+            dims[j] //= world
+            nd.inputs[1] = new_const(tgt.name, np.array(dims, np.int64), I64)
+            place[nd.outputs[0]] = j
+        elif op == "Split":
+            ax, k = int(nd.attrs.get("axis", 0)) % len(shapes[nd.inputs[0]]), place[nd.inputs[0]]
+            if ax == k and len(nd.inputs) > 1 and nd.inputs[1] in consts:
+                c = consts[nd.inputs[1]]
+                nd.inputs[1] = new_const(c.name, c.array // world, c.data_type)
+            for o in nd.outputs:
+                place[o] = k
+        elif op == "AttentionKVCache":
+            if {place.get(x) for x in nd.inputs[2:5]} != {1}:
+                raise NotImplementedError("AttentionKVCache: q, k, v must all be sharded by head (axis 1)")
+            for cache in nd.inputs[:2]:
+                if cache not in inputs:
+                    raise NotImplementedError("AttentionKVCache: the caches must be graph inputs to be sharded by head")
+                if cache not in place:
+                    v = inputs[cache]
+                    inputs[cache] = ValueInfo(v.name, v.elem_type, [d // world if i == 1 else d for i, d in enumerate(v.dims)])
+                    place[cache] = 1
+            place[nd.outputs[0]] = 1
+        elif op == "MatMul":
+            a_ax, b_ax = place.get(nd.inputs[0]), place.get(nd.inputs[1])
+            ra = len(shapes[nd.inputs[0]])
+            if a_ax != b_ax or a_ax is None or a_ax >= ra - 2:
+                raise NotImplementedError(f"MatMul {nd.name}: activation operands must be sharded on the same batch axis")
+            place[nd.outputs[0]] = a_ax
+        else:
+            raise NotImplementedError(f"{op} {nd.name}: a sharded input reaches an operator with no tensor-parallel rule")
+        nodes.append(nd)
+    for o in g.outputs:
+        if o.name in place:
+            raise NotImplementedError(f"graph output {o.name} would be sharded on axis {place[o.name]}")
+    used = {x for nd in nodes for x in nd.inputs}
+    return Model(Graph(nodes, [t for n_, t in consts.items() if n_ in used], [inputs[v.name] for v in g.inputs], list(g.outputs),
+                       f"{g.name}_{rank}"), m.ir_version, m.opset)

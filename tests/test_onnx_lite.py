@@ -1,10 +1,13 @@
 """ONNX ingestion without the onnx package: wire format, node lowering, export -> import round trips.
 CPU tier: graphs run on the oracle's handler; the GPU tier test lives in test_gpu_graph.py."""
+import os
 import struct
+import sys
 
 import numpy as np
 import pytest
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # (also run as a torchrun worker script)
 from infinitensor_b200 import onnx_lite as X
 
 F32, F16, BF16, I64 = 1, 10, 16, 7
@@ -308,3 +311,103 @@ def test_hf_style_gpt2_block_with_exporter_shape_arithmetic():
     gelu = 0.5 * f * (1 + np.tanh(np.sqrt(2 / np.pi) * (f + 0.044715 * f ** 3)))
     ref = r1 + gelu @ f8["w_pr"] + f8["b_pr"]
     np.testing.assert_allclose(stub.outputs["y"].copyout_numpy(), ref, rtol=2e-4, atol=2e-5)
+
+
+def test_simplify_removes_constant_subgraphs():
+    from oracle.graph_oracle import OracleHandler
+    nodes = [X.Node("Shape", ["x"], ["s"]), X.Node("Constant", [], ["i"], "", {"value": X.TensorProto("", [], I64, np.array(1, np.int64))}),
+             X.Node("Gather", ["s", "i"], ["n"]), X.Node("Unsqueeze", ["n"], ["n1"], "", {"axes": [0]}),
+             X.Node("Constant", [], ["m1"], "", {"value": X.TensorProto("", [1], I64, np.array([-1], np.int64))}),
+             X.Node("Concat", ["n1", "m1"], ["shp"], "", {"axis": 0}), X.Node("Reshape", ["x", "shp"], ["y"]), X.Node("Relu", ["y"], ["z"])]
+    g = X.Graph(nodes, [], [X.ValueInfo("x", F32, [2, 3, 4])], [X.ValueInfo("z", F32, [3, 8])])
+    m = X.simplify(X.Model(g), OracleHandler)
+    assert [n.op_type for n in m.graph.nodes] == ["Reshape", "Relu"]
+    assert {t.name: t.array.tolist() for t in m.graph.initializers} == {"shp": [3, -1]}
+    assert X.tensor_shapes(m, OracleHandler)["z"] == [3, 8]
+    m2 = X.load_model(X.save_model(m))  # and it still round-trips through the wire format
+    assert [n.op_type for n in m2.graph.nodes] == ["Reshape", "Relu"]
+
+
+def _tp_onnx_worker():
+    """one rank of a world-size-2 gloo run: the UNSHARDED Llama ONNX file, rewritten by parallel_model for this rank"""
+    import os
+    import torch.distributed as dist
+    from infinitensor_b200 import graphs as G
+    from oracle.graph_oracle import OracleHandler
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cfg = G.LlamaConfig.tiny(dtype=1, layers=2, batch=3)
+    exp = X.OnnxExporter(OracleHandler())
+    ge = G.build_llama_decode(exp, cfg)
+    exp.data_malloc()
+    G.fill_llama_weights_host(ge)
+    names = {"ids": ge.input_ids.name, "pos": ge.position_ids.name, "k": [t.name for t in ge.k_caches], "v": [t.name for t in ge.v_caches],
+             "logits": ge.logits.name}
+    sharded = X.parallel_model(exp.save(), world, rank, OracleHandler)
+    ops = [n.op_type for n in sharded.graph.nodes]
+    assert ops.count("ReduceSum") == 2 * cfg.layers, ops
+    stub = X.OnnxStub(X.save_model(sharded), handler=OracleHandler())
+    for li in range(cfg.layers):
+        stub.inputs[names["k"][li]].copyin_numpy(G.llama_cache_values(cfg, li, "k", world, rank))
+        stub.inputs[names["v"][li]].copyin_numpy(G.llama_cache_values(cfg, li, "v", world, rank))
+    stub.inputs[names["ids"]].copyin_numpy(np.array([[1], [5], [7]], np.int64))
+    stub.inputs[names["pos"]].copyin_numpy(np.full((3, 1), 9, np.int64))
+    stub.run()
+    np.save(os.environ["TP_OUT"] + f".{rank}.npy", stub.outputs[names["logits"]].f32())
+    dist.barrier()
+
+
+def test_parallel_model_rewrite_gloo_world2(tmp_path):
+    """parallel_opt.py's job on the package-free ONNX classes: the unsharded Llama file rewritten per rank (column / row split,
+    ReduceSum(communicator) -> AllReduceSum, head-sharded caches, Reshape targets) reproduces the single-rank logits."""
+    import os
+    import subprocess
+    import sys
+    from infinitensor_b200 import graphs as G
+    from oracle.graph_oracle import OracleHandler
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "tp_onnx")
+    env = dict(os.environ, TP_OUT=out, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", os.path.abspath(__file__), "--tp-onnx-worker"]
+    subprocess.run(cmd, check=True, env=env, cwd=root, timeout=240)
+    cfg = G.LlamaConfig.tiny(dtype=1, layers=2, batch=3)
+    oh = OracleHandler()
+    g = G.build_llama_decode(oh, cfg)
+    G.fill_llama_weights_host(g)
+    for li in range(cfg.layers):
+        g.k_caches[li].copyin_numpy(G.llama_cache_values(cfg, li, "k"))
+        g.v_caches[li].copyin_numpy(G.llama_cache_values(cfg, li, "v"))
+    g.input_ids.copyin_numpy(np.array([[1], [5], [7]], np.int64))
+    g.position_ids.copyin_numpy(np.full((3, 1), 9, np.int64))
+    oh.run()
+    for r in range(2):
+        np.testing.assert_allclose(np.load(out + f".{r}.npy"), g.logits.f32(), rtol=1e-4, atol=1e-5)
+
+
+if __name__ == "__main__":
+    import os
+    import sys
+    if "--tp-onnx-worker" in sys.argv:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        _tp_onnx_worker()
+
+
+def test_parallel_model_schedule_matches_the_direct_tp_build():
+    """On the C++ host: the rank-1-of-2 rewrite of the unsharded file plans and schedules exactly like the graph that
+    graphs.build_llama_decode(world=2, rank=1) builds directly (AllReduce + Add + RMSNorm steps included)."""
+    from infinitensor_b200 import backend as B, graphs as G
+    rt = B.HostPlanRuntime()
+    cfg = G.LlamaConfig(layers=2, d_model=512, heads=4, head_dim=128, ffn=1024, vocab=128, s_max=32, batch=16)
+    direct = B.GraphHandler(rt)
+    G.build_llama_decode(direct, cfg, 2, 1)
+    exp = X.OnnxExporter(B.GraphHandler(rt))
+    G.build_llama_decode(exp, cfg)
+    sharded = X.parallel_model(exp.save(), 2, 1)
+    h = B.GraphHandler(rt)
+    X.OnnxStub(sharded, handler=h, upload=False)
+    assert h.schedule() == direct.schedule()
+    assert sum(s.startswith("AllReduceAddNorm") for s in h.schedule()) == 4
+    h.data_malloc()
+    direct.data_malloc()
+    assert h.arena_bytes() == direct.arena_bytes()
