@@ -328,6 +328,11 @@ def test_simplify_removes_constant_subgraphs():
     assert [n.op_type for n in m2.graph.nodes] == ["Reshape", "Relu"]
 
 
+def _tp_gpt2_inputs(cfg):
+    ids = np.random.default_rng(1).integers(0, cfg.vocab, size=(cfg.batch, cfg.seq)).astype(np.int64)
+    return ids, np.arange(cfg.seq, dtype=np.int64).reshape(1, -1).repeat(cfg.batch, 0)
+
+
 def _tp_onnx_worker():
     """one rank of a world-size-2 gloo run: the UNSHARDED Llama ONNX file, rewritten by parallel_model for this rank"""
     import os
@@ -336,6 +341,22 @@ def _tp_onnx_worker():
     from oracle.graph_oracle import OracleHandler
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
+    if os.environ.get("TP_MODEL") == "gpt2":
+        cfg = G.GPT2Config.tiny(1)
+        exp = X.OnnxExporter(OracleHandler())
+        ge = G.build_gpt2(exp, cfg)
+        exp.data_malloc()
+        G.fill_gpt2_weights_host(ge)
+        sharded = X.parallel_model(exp.save(), world, rank, OracleHandler)
+        assert [n.op_type for n in sharded.graph.nodes].count("ReduceSum") == 2 * cfg.layers
+        stub = X.OnnxStub(X.save_model(sharded), handler=OracleHandler())
+        ids, pos = _tp_gpt2_inputs(cfg)
+        stub.inputs[ge.input_ids.name].copyin_numpy(ids)
+        stub.inputs[ge.position_ids.name].copyin_numpy(pos)
+        stub.run()
+        np.save(os.environ["TP_OUT"] + f".{rank}.npy", stub.outputs[ge.out.name].f32())
+        dist.barrier()
+        return
     cfg = G.LlamaConfig.tiny(dtype=1, layers=2, batch=3)
     exp = X.OnnxExporter(OracleHandler())
     ge = G.build_llama_decode(exp, cfg)
@@ -383,6 +404,31 @@ def test_parallel_model_rewrite_gloo_world2(tmp_path):
     oh.run()
     for r in range(2):
         np.testing.assert_allclose(np.load(out + f".{r}.npy"), g.logits.f32(), rtol=1e-4, atol=1e-5)
+
+
+def test_parallel_model_gpt2_packed_qkv_gloo_world2(tmp_path):
+    """The generic rules on a second topology: packed q/k/v Gemm split per group before its Split, sharded Gemm biases,
+    head-sharded activation x activation MatMuls, Softmax, the bias of a row-split Gemm added once after the all-reduce."""
+    import subprocess
+    from infinitensor_b200 import graphs as G
+    from oracle.graph_oracle import OracleHandler
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "tp_gpt2")
+    env = dict(os.environ, TP_OUT=out, TP_MODEL="gpt2", MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29615", os.path.abspath(__file__), "--tp-onnx-worker"]
+    subprocess.run(cmd, check=True, env=env, cwd=root, timeout=240)
+    cfg = G.GPT2Config.tiny(1)
+    oh = OracleHandler()
+    g = G.build_gpt2(oh, cfg)
+    oh.data_malloc()
+    G.fill_gpt2_weights_host(g)
+    ids, pos = _tp_gpt2_inputs(cfg)
+    g.input_ids.copyin_numpy(ids)
+    g.position_ids.copyin_numpy(pos)
+    oh.run()
+    for r in range(2):
+        np.testing.assert_allclose(np.load(out + f".{r}.npy"), g.out.f32(), rtol=2e-4, atol=2e-5)
 
 
 if __name__ == "__main__":
