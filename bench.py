@@ -53,7 +53,14 @@ def cpu_decode_sample(cfg, reps, threads):
     import numpy as np
     from infinitensor_b200 import graphs as G
     from oracle.graph_oracle import OracleHandler
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers): set the env for a runtime that
+    # is not initialised yet and the ICV of one that is
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
+    except OSError:
+        pass
     one = G.LlamaConfig(layers=1, d_model=cfg.d_model, heads=cfg.heads, head_dim=cfg.head_dim, ffn=cfg.ffn,
                         vocab=cfg.vocab, s_max=cfg.s_max, batch=cfg.batch, dtype=cfg.dtype)
     oh = OracleHandler()
