@@ -285,6 +285,12 @@ int itb_graph_launch_cudagraph_async(itb_graph *g);
 int itb_graph_tune(itb_graph *g);
 int itb_graph_sync(itb_graph *g);
 double itb_graph_get_perf_time(itb_graph *g);
+/* PerfEngine table (filled by itb_graph_tune) <-> JSON file, in the layout of the reference's savePerfEngineData /
+ * loadPerfEngineData (src/core/perf_engine.cc:7-22): files are interchangeable; load replaces the table. */
+int itb_perf_engine_save(const char *path);
+int itb_perf_engine_load(const char *path);
+int64_t itb_perf_engine_size(void);
+void itb_perf_engine_clear(void);
 int64_t itb_graph_arena_bytes(itb_graph *g, int which /*0 weights, 1 activations*/);
 
 #ifdef __cplusplus

@@ -15,6 +15,7 @@ There is no CPU runtime here (`cpu_runtime()` raises): this package is the B200 
 from __future__ import annotations
 
 import ctypes
+import os
 import enum
 from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int64, c_void_p
 
@@ -97,6 +98,10 @@ _sig = {
     "itb_graph_tune": (c_int, [_h]),
     "itb_graph_sync": (c_int, [_h]),
     "itb_graph_get_perf_time": (c_double, [_h]),
+    "itb_perf_engine_save": (c_int, [c_char_p]),
+    "itb_perf_engine_load": (c_int, [c_char_p]),
+    "itb_perf_engine_size": (c_int64, []),
+    "itb_perf_engine_clear": (None, []),
     "itb_graph_arena_bytes": (c_int64, [_h, c_int]),
 }
 for _n, (_r, _a) in _sig.items():
@@ -276,6 +281,22 @@ class Tensor:
 
     def copyout_async(self, host_ptr: int, nbytes: int):
         _ck(lib.itb_tensor_copyout_async(self._gh(), self._id, c_void_p(host_ptr), nbytes))
+
+
+class PerfEngine:
+    """The process-wide PerfEngine table that `GraphHandler.tune()` fills (reference include/core/perf_engine.h:8-50)."""
+
+    @staticmethod
+    def save(path: str): _ck(lib.itb_perf_engine_save(os.fsencode(path)))
+
+    @staticmethod
+    def load(path: str): _ck(lib.itb_perf_engine_load(os.fsencode(path)))
+
+    @staticmethod
+    def size() -> int: return int(lib.itb_perf_engine_size())
+
+    @staticmethod
+    def clear(): lib.itb_perf_engine_clear()
 
 
 def _ids(ts):

@@ -396,6 +396,11 @@ double itb_graph_get_perf_time(itb_graph *g) {
         return -1.0;
     }
 }
+int itb_perf_engine_save(const char *path) { ITB_TRY(PerfEngine::getInstance().savePerfEngineData(path)) }
+int itb_perf_engine_load(const char *path) { ITB_TRY(PerfEngine::getInstance().loadPerfEngineData(path)) }
+int64_t itb_perf_engine_size(void) { return (int64_t)PerfEngine::getInstance().size(); }
+void itb_perf_engine_clear(void) { PerfEngine::getInstance().clear(); }
+
 int64_t itb_graph_arena_bytes(itb_graph *g, int which) {
     return (int64_t)(which == 0 ? g->g->getWeightArenaBytes() : g->g->getActivationArenaBytes());
 }

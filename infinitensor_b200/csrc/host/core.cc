@@ -1,6 +1,11 @@
 // core.cc -- Tensor / Operator / Graph / planner / registries (see core.h for the reference map).
 #include "core.h"
 
+#include <cctype>
+#include <cstdlib>
+#include <fstream>
+#include <sstream>
+
 #include <algorithm>
 #include <atomic>
 #include <numeric>
@@ -200,6 +205,117 @@ std::optional<PerfRecord> PerfEngine::getPerfData(const Key &key) const {
 void PerfEngine::setPerfData(const Key &key, PerfRecord record) {
     IT_ASSERT(data.find(key) == data.end(), "Perf data already exist");
     data.emplace(key, std::move(record));
+}
+
+// ---- PerfEngine <-> JSON (a tiny reader for exactly the value kinds that layout uses: arrays, objects, numbers)
+namespace {
+struct JVal {
+    enum Kind { Num, Arr, Obj } kind = Num;
+    double num = 0;
+    unsigned long long u64 = 0;  // exact value of a non-negative integer literal (hashes are 64-bit)
+    vector<JVal> arr;
+    vector<std::pair<string, JVal>> obj;
+    const JVal &at(const string &k) const {
+        for (auto &kv : obj)
+            if (kv.first == k) return kv.second;
+        throw Exception("perf-engine json: missing key '" + k + "'");
+    }
+};
+struct JParser {
+    const string &s;
+    size_t i = 0;
+    explicit JParser(const string &text) : s(text) {}
+    void ws() {
+        while (i < s.size() && (s[i] == ' ' || s[i] == '\n' || s[i] == '\t' || s[i] == '\r')) ++i;
+    }
+    void expect(char c) {
+        ws();
+        IT_ASSERT(i < s.size() && s[i] == c, string("perf-engine json: expected '") + c + "' at offset " + std::to_string(i));
+        ++i;
+    }
+    bool peek(char c) {
+        ws();
+        return i < s.size() && s[i] == c;
+    }
+    string str() {
+        expect('"');
+        size_t b = i;
+        while (i < s.size() && s[i] != '"') ++i;
+        IT_ASSERT(i < s.size(), "perf-engine json: unterminated string");
+        return s.substr(b, i++ - b);
+    }
+    JVal value() {
+        ws();
+        JVal v;
+        if (peek('[')) {
+            v.kind = JVal::Arr;
+            ++i;
+            if (peek(']')) { ++i; return v; }
+            do v.arr.push_back(value()); while (peek(',') && ++i);
+            expect(']');
+        } else if (peek('{')) {
+            v.kind = JVal::Obj;
+            ++i;
+            if (peek('}')) { ++i; return v; }
+            do {
+                string k = str();
+                expect(':');
+                v.obj.emplace_back(std::move(k), value());
+            } while (peek(',') && ++i);
+            expect('}');
+        } else {
+            size_t b = i;
+            while (i < s.size() && (std::isdigit((unsigned char)s[i]) || s[i] == '-' || s[i] == '+' || s[i] == '.' || s[i] == 'e' || s[i] == 'E')) ++i;
+            IT_ASSERT(i > b, "perf-engine json: unexpected character at offset " + std::to_string(b));
+            const string tok = s.substr(b, i - b);
+            v.num = std::strtod(tok.c_str(), nullptr);
+            if (tok.find_first_of(".eE-") == string::npos) v.u64 = std::strtoull(tok.c_str(), nullptr, 10);
+            else v.u64 = (unsigned long long)v.num;
+        }
+        return v;
+    }
+};
+}  // namespace
+
+void PerfEngine::savePerfEngineData(const string &path) const {
+    std::ofstream out(path, std::ios::out | std::ios::trunc | std::ios::binary);
+    IT_ASSERT(out.good(), "cannot write " + path);
+    out << "{\"data\":[";
+    bool first = true;
+    for (auto &[key, rec] : data) {
+        const auto &[attrs, perfKey] = key;
+        out << (first ? "" : ",") << "[[[" << (int)attrs.device << "," << (long long)attrs.op << "],{\"attrs\":[";
+        for (size_t k = 0; k < perfKey.attrs.size(); ++k) out << (k ? "," : "") << perfKey.attrs[k];
+        out << "],\"hashType\":" << (unsigned long long)perfKey.hash << ",\"opType\":" << (long long)perfKey.opType << "}],{\"data\":";
+        out.precision(17);
+        out << rec->time << ",\"type\":0}]";
+        first = false;
+    }
+    out << "]}" << std::endl;
+}
+
+void PerfEngine::loadPerfEngineData(const string &path) {
+    std::ifstream in(path, std::ios::in | std::ios::binary);
+    IT_ASSERT(in.good(), "cannot read " + path);
+    std::stringstream ss;
+    ss << in.rdbuf();
+    const string text = ss.str();
+    JParser p(text);
+    JVal root = p.value();
+    std::map<Key, PerfRecord> fresh;
+    for (auto &entry : root.at("data").arr) {
+        IT_ASSERT(entry.arr.size() == 2 && entry.arr[0].arr.size() == 2 && entry.arr[0].arr[0].arr.size() == 2, "perf-engine json: bad entry");
+        const JVal &ka = entry.arr[0].arr[0], &pk = entry.arr[0].arr[1], &rec = entry.arr[1];
+        OpPerfKey perfKey;
+        perfKey.hash = (HashType)pk.at("hashType").u64;
+        perfKey.opType = (OpType::underlying_t)pk.at("opType").num;
+        for (auto &a : pk.at("attrs").arr) perfKey.attrs.push_back((int)a.num);
+        IT_ASSERT((int)rec.at("type").num == 0, "perf-engine json: only the plain PerfRecord (type 0) is supported");
+        auto r = make_ref<PerfRecordObj>();
+        r->time = rec.at("data").num;
+        fresh[Key{KernelAttrs{(Device)(int)ka.arr[0].num, (OpType::underlying_t)ka.arr[1].num}, perfKey}] = r;
+    }
+    data = std::move(fresh);
 }
 
 double RuntimeObj::getPerfTime(const Graph &graph) const {

@@ -278,6 +278,13 @@ class PerfEngine {
     std::optional<PerfRecord> getPerfData(const Key &key) const;
     void setPerfData(const Key &key, PerfRecord record);  // duplicate -> throws (perf_engine.h:40-43)
     size_t size() const { return data.size(); }
+    void clear() { data.clear(); }
+    // JSON in the layout nlohmann gives the reference's map (src/core/perf_engine.cc:7-62): files are interchangeable.
+    //   {"data": [ [ [[device, opType], {"attrs": [...], "hashType": h, "opType": o}], {"data": ms, "type": 0} ], ... ]}
+    // load REPLACES the table, like the reference's set_data; the time is read as a double (the reference reads it back
+    // as an int, quirk q13 -- not reproduced).
+    void savePerfEngineData(const string &path) const;
+    void loadPerfEngineData(const string &path);
 
   private:
     std::map<Key, PerfRecord> data;

@@ -340,3 +340,29 @@ def test_conv_bn_act_matcher_edge_cases(B):
         h.relu(h.add(r, bn(h, h.conv(x, w, None, 1, 1, 1, 1, 1, 1), s), None), None).set_output()
     sc = net(residual)
     assert sc == ["Single:Relu", "ConvBnAct:Conv+BatchNormalization+Add+Relu"]
+
+
+def test_perf_engine_json_roundtrip_in_the_reference_layout(B, tmp_path):
+    """savePerfEngineData / loadPerfEngineData (reference src/core/perf_engine.cc:7-62): a file in nlohmann's layout of the
+    reference's map (keys in any order, 64-bit hashes) loads, saves back with the same content, and load replaces the table."""
+    import json
+    ref_style = {"data": [
+        [[[2, 7], {"opType": 7, "hashType": 18446744073709551557, "attrs": [16, 4096, 4096, 0, 0]}], {"type": 0, "data": 0.0125}],
+        [[[2, 3], {"attrs": [], "hashType": 42, "opType": 3}], {"data": 3, "type": 0}],
+    ]}
+    p = tmp_path / "perf.json"
+    p.write_text(json.dumps(ref_style, indent=1))
+    B.PerfEngine.clear()
+    B.PerfEngine.load(str(p))
+    assert B.PerfEngine.size() == 2
+    out = tmp_path / "perf_out.json"
+    B.PerfEngine.save(str(out))
+    back = json.loads(out.read_text())
+    canon = lambda d: sorted((tuple(e[0][0]), e[0][1]["hashType"], e[0][1]["opType"], tuple(e[0][1]["attrs"]), float(e[1]["data"]), e[1]["type"])
+                             for e in d["data"])
+    assert canon(back) == canon(ref_style)
+    p.write_text(json.dumps({"data": []}))
+    B.PerfEngine.load(str(p))
+    assert B.PerfEngine.size() == 0
+    with pytest.raises(RuntimeError):
+        B.PerfEngine.load(str(tmp_path / "missing.json"))
