@@ -331,6 +331,7 @@ class LazyAllocator {
     void free(size_t offset, size_t size);
     size_t getPeak() const { return peak; }
     size_t getUsed() const { return used; }
+    size_t numFreeBlocks() const { return freeByAddr.size(); }
     void reset();
 };
 

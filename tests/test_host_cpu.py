@@ -366,3 +366,17 @@ def test_perf_engine_json_roundtrip_in_the_reference_layout(B, tmp_path):
     assert B.PerfEngine.size() == 0
     with pytest.raises(RuntimeError):
         B.PerfEngine.load(str(tmp_path / "missing.json"))
+
+
+def test_native_host_core(tmp_path):
+    """C++ unit tests of the host contract compiled against core.cc / operators.cc / schedule.cc alone (no CUDA): the
+    LazyAllocator scenarios of the reference's test_lazy_allocator.cc, KernelRegistry / PerfEngine duplicate-key rules,
+    topological sort + planner through GraphObj."""
+    host = os.path.join(ROOT, "infinitensor_b200", "csrc", "host")
+    exe = str(tmp_path / "test_host_core")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-O1", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + host, "-o", exe,
+           os.path.join(ROOT, "tests", "native", "test_host_core.cc")] + [os.path.join(host, f) for f in ("core.cc", "operators.cc", "schedule.cc")]
+    subprocess.run(cmd, check=True, timeout=300)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "passed" in r.stdout, r.stdout + r.stderr
