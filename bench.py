@@ -233,6 +233,9 @@ def run_b200(args):
     step = h.run if args.eager else h.run_with_cudagraph
     launch_async = h.run_without_sync if args.eager else h.launch_cudagraph_async
 
+    # ranks finish building at slightly different times; the peer-memory all-reduce spins on its peers (bounded), so line
+    # them up before the first collective
+    barrier()
     # one eager pass counts our kernel launches per step (graph replay re-issues exactly these)
     l0 = rt.kernel_launches()
     h.run()
