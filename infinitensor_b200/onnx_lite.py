@@ -326,6 +326,14 @@ class OnnxStub:
         for name, proto in self._data.items():
             self.tensors[name].copyin_numpy(np.ascontiguousarray(proto.array))
 
+    def to_onnx(self, name: str = "") -> bytes:
+        """The loaded model back as ONNX bytes, constant subgraphs already folded (reference `OnnxStub.to_onnx`, onnx.py:1138)."""
+        used = {x for nd in self.lowered_nodes for x in nd.inputs} | set(self.outputs)
+        inits = [TensorProto(n, list(a.shape), dt, a) for n, (a, dt) in self._consts.items() if n in used]
+        g = self.model.graph
+        return save_model(Model(Graph(list(self.lowered_nodes), inits, [v for v in g.inputs if v.name in self.inputs], list(g.outputs),
+                                      name or g.name), self.model.ir_version, self.model.opset))
+
     def optimize(self): self.handler.optimize()
     def tune(self): self.handler.tune()
     def run(self): self.handler.run()

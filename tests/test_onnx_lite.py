@@ -326,6 +326,9 @@ def test_simplify_removes_constant_subgraphs():
     assert X.tensor_shapes(m, OracleHandler)["z"] == [3, 8]
     m2 = X.load_model(X.save_model(m))  # and it still round-trips through the wire format
     assert [n.op_type for n in m2.graph.nodes] == ["Reshape", "Relu"]
+    stub = X.OnnxStub(X.Model(g), handler=OracleHandler())
+    m3 = X.load_model(stub.to_onnx())       # OnnxStub.to_onnx(): the same folded model
+    assert [n.op_type for n in m3.graph.nodes] == ["Reshape", "Relu"] and [t.name for t in m3.graph.initializers] == ["shp"]
 
 
 def _tp_gpt2_inputs(cfg):
