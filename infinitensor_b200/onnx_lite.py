@@ -611,7 +611,16 @@ class OnnxStub:
         elif op == "Expand":
             T[out0] = h.expand(I(0), None, self._ints(nd, 1, "shape", required=True))
         elif op == "Where":
-            T[out0] = h.where(I(1), I(2), I(0), None)
+            cond, alt = self._const(nd.inputs[0]), self._const(nd.inputs[2])
+            if cond is not None and alt is not None and alt.size == 1 and (np.isneginf(alt).all() or (alt < -3e38).all()):
+                # a constant mask selecting between x and a single -inf (causal masks): an additive 0 / -inf bias instead of a
+                # three-operand select (the reference's rewrite, onnx.py:1055-1081)
+                name = nd.inputs[0] + "_alt"
+                if name not in self._consts:
+                    self._set_const(name, np.where(cond, 0, -np.inf).astype(alt.dtype), self._consts[nd.inputs[2]][1])
+                T[out0] = h.add(I(1), self._operand(name), None)
+            else:
+                T[out0] = h.where(I(1), I(2), I(0), None)
         elif op == "AllGather":
             outs = h.allGather(I(0), None, len(nd.outputs))
             for name, t in zip(nd.outputs, outs):

@@ -460,3 +460,19 @@ def test_parallel_model_schedule_matches_the_direct_tp_build():
     h.data_malloc()
     direct.data_malloc()
     assert h.arena_bytes() == direct.arena_bytes()
+
+
+def test_where_with_constant_mask_and_neg_inf_becomes_add():
+    """reference onnx.py:1055-1081: Where(const mask, x, -inf) is lowered as x + (0 / -inf bias); other Wheres stay selects."""
+    mask = np.tril(np.ones((1, 1, 4, 4), np.bool_))
+    inits = [X.TensorProto("mask", [1, 1, 4, 4], 9, mask), X.TensorProto("ninf", [], F32, np.array(-np.inf, np.float32)),
+             X.TensorProto("small", [], F32, np.array(-1e4, np.float32))]
+    g = X.Graph([X.Node("Where", ["mask", "x", "ninf"], ["a"]), X.Node("Where", ["mask", "x", "small"], ["b"])], inits,
+                [X.ValueInfo("x", F32, [2, 3, 4, 4])], [X.ValueInfo("a", F32, [2, 3, 4, 4]), X.ValueInfo("b", F32, [2, 3, 4, 4])])
+    stub = X.OnnxStub(X.Model(g), handler=_oracle())
+    assert "mask_alt" in stub._data and stub._data["mask_alt"].array.dtype == np.float32
+    x = np.random.default_rng(0).standard_normal((2, 3, 4, 4)).astype(np.float32)
+    stub.inputs["x"].copyin_numpy(x)
+    stub.run()
+    np.testing.assert_array_equal(stub.outputs["a"].copyout_numpy(), np.where(mask, x, -np.inf).astype(np.float32))
+    np.testing.assert_array_equal(stub.outputs["b"].copyout_numpy(), np.where(mask, x, np.float32(-1e4)))
