@@ -380,3 +380,49 @@ def test_native_host_core(tmp_path):
     subprocess.run(cmd, check=True, timeout=300)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "passed" in r.stdout, r.stdout + r.stderr
+
+
+def test_attention_unit_partition_properties():
+    """The streaming attention kernel deals the flattened (head, chunk) units to CTAs with
+         G = min(grid, total);  CTA i owns [i*total//G, (i+1)*total//G);  cta(u) = ((u+1)*G - 1)//total
+       (attention.cu, attn_stream_kernel).  Re-stated here and checked exhaustively over small shapes: every unit is owned
+       once, owners of a head are CONSECUTIVE CTAs (the partial-slot index blockIdx - first_cta stays below the slot
+       count), and the closed form agrees with the ranges.  The first version of the kernel broke exactly this for
+       total < grid."""
+    for BH in (1, 2, 3, 7, 16, 33):
+        for nch in (1, 2, 3, 5, 8, 16, 33):
+            total = BH * nch
+            for grid in (1, 2, 3, 5, 8, 31, 64, 296):
+                G = min(grid, total)
+                owner = {}
+                for i in range(G):
+                    u0, u1 = i * total // G, (i + 1) * total // G
+                    assert u1 > u0, "every participating CTA owns at least one unit"
+                    for u in range(u0, u1):
+                        assert u not in owner
+                        owner[u] = i
+                        assert ((u + 1) * G - 1) // total == i
+                assert len(owner) == total
+                for bh in range(BH):
+                    first = ((bh * nch + 1) * G - 1) // total
+                    last = ((bh * nch + nch) * G - 1) // total
+                    touching = sorted({owner[bh * nch + c] for c in range(nch)})
+                    assert touching == list(range(first, last + 1))
+                    assert last - first + 1 <= nch  # slots_per_head >= chunks per head covers the slot index
+
+
+def test_skinny_gemm_split_k_partition_properties():
+    """gemm_skinny.cu / gemm_tc.cu split-K: splitk = clamp(target // tiles, 1, 8), at least 4 k-tiles per split, then
+    `per = ceil(ktiles / splitk)` and `splitk = ceil(ktiles / per)` so that NO split is empty and the splits cover K once."""
+    for tiles in (1, 6, 32, 64, 172, 192, 250, 344, 500):
+        for ktiles in (1, 2, 3, 4, 8, 16, 43, 64, 172):
+            splitk = max(1, min(296 // tiles, 8))
+            splitk = min(splitk, max(1, ktiles // 4))
+            per = -(-ktiles // splitk)
+            splitk = -(-ktiles // per)
+            covered = []
+            for s in range(splitk):
+                b, e = s * per, min(ktiles, (s + 1) * per)
+                assert e > b, (tiles, ktiles, splitk, per)
+                covered += list(range(b, e))
+            assert covered == list(range(ktiles)) and 1 <= splitk <= 8
