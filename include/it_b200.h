@@ -194,7 +194,12 @@ int it_b200_conv2d_fused(int dtype, const void *x, const void *w, void *y, int N
 /* ---- AttentionKVCache (decode, q-len 1): replaces _attention_kvcache_kernel_128_1/_2
  *      (attention_kvcache.cu:8-169).  Appends k,v IN PLACE into k_cache/v_cache at
  *      position_id[0]; caches [B,H,S_max,D], q/k/v/out [B,H,1,D]; D == 128.
- *      pos_dtype: ITB_I32 / ITB_U32 / ITB_I64 (element 0 is used for every row, .cu:17). ---- */
+ *      pos_dtype: ITB_I32 / ITB_U32 / ITB_I64 (element 0 is used for every row, .cu:17).
+ *      Ordering contract (programmatic dependent launch): q / k / v (and the RoPE positions of the _rope variant) may come from
+ *      the kernel launched just before on the same stream; `position_id` and the cache rows BELOW the position are read
+ *      ahead of griddepcontrol.wait, so they must be OLDER than that -- graph inputs or the previous step's appends, as in
+ *      every decode graph the frontend emits.  A caller that produces the position with a kernel of this library in the
+ *      same step sets ITB_NO_PDL=1.  The workspace is always required (per-head partial slots). ---- */
 int64_t it_b200_attention_kvcache_workspace(int B, int H, int S_max, int D);
 int it_b200_attention_kvcache(int dtype, void *k_cache, void *v_cache, const void *q,
                               const void *k, const void *v, const void *position_id,
