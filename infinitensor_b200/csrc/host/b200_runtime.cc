@@ -3,6 +3,8 @@
 
 #include "it_b200.h"
 
+#include <nvtx3/nvToolsExt.h>  // header-only; the ranges cost nothing unless a profiler is attached AND ITB_NVTX=1
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -150,9 +152,27 @@ void CudaRuntimeObj::runWithoutSyncImpl(const Graph &graph, bool validate) const
         planGraphId = graph->getGraphId();
         planEpoch = graph->getTopologyEpoch();
     }
+    // ITB_NVTX=1: one NVTX range per schedule step (nsys / ncu timelines show operator names; the reference's per-op
+    // profiling table, runtime.cc:49-63, halts on CUDA -- cuda_runtime.cc:472-473)
+    static const bool nvtx = [] {
+        const char *e = std::getenv("ITB_NVTX");
+        return e && e[0] == '1';
+    }();
     for (size_t i = 0; i < sched.size(); ++i) {
         const auto &st = sched[i];
         const auto &op = st.ops.back();
+        struct Range {
+            bool on;
+            Range(bool enable, const ExecStep &s) : on(enable) {
+                if (!on) return;
+                string name;
+                for (auto &m : s.ops) name += (name.empty() ? "" : "+") + string(m->getOpType().toString());
+                nvtxRangePushA(name.c_str());
+            }
+            ~Range() {
+                if (on) nvtxRangePop();
+            }
+        } range(nvtx, st);
         switch (st.kind) {
         case ExecStep::Alias:
             // the planner made the output share the input's storage: nothing to launch
