@@ -9,6 +9,14 @@ import sys
 import numpy as np
 import pytest
 
+
+def _free_port():
+    """an unused TCP port for the torchrun rendezvous of the gloo world-2 tests"""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -210,7 +218,7 @@ def test_tensor_parallel_rule_gloo_world2(tmp_path):
     out = str(tmp_path / "tp")
     env = dict(os.environ, TP_OUT=out, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29611", os.path.abspath(__file__), "--tp-worker"]
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.abspath(__file__), "--tp-worker"]
     subprocess.run(cmd, check=True, env=env, cwd=ROOT, timeout=240)
     cfg = G.LlamaConfig.tiny(dtype=1, layers=2, batch=3)
     oh = OracleHandler()

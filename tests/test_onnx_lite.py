@@ -7,6 +7,14 @@ import sys
 import numpy as np
 import pytest
 
+
+def _free_port():
+    """an unused TCP port for the torchrun rendezvous of the gloo world-2 tests"""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # (also run as a torchrun worker script)
 from infinitensor_b200 import onnx_lite as X
 
@@ -393,7 +401,7 @@ def test_parallel_model_rewrite_gloo_world2(tmp_path):
     out = str(tmp_path / "tp_onnx")
     env = dict(os.environ, TP_OUT=out, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29613", os.path.abspath(__file__), "--tp-onnx-worker"]
+           "--master-port", str(_free_port()), os.path.abspath(__file__), "--tp-onnx-worker"]
     subprocess.run(cmd, check=True, env=env, cwd=root, timeout=240)
     cfg = G.LlamaConfig.tiny(dtype=1, layers=2, batch=3)
     oh = OracleHandler()
@@ -419,7 +427,7 @@ def test_parallel_model_gpt2_packed_qkv_gloo_world2(tmp_path):
     out = str(tmp_path / "tp_gpt2")
     env = dict(os.environ, TP_OUT=out, TP_MODEL="gpt2", MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29615", os.path.abspath(__file__), "--tp-onnx-worker"]
+           "--master-port", str(_free_port()), os.path.abspath(__file__), "--tp-onnx-worker"]
     subprocess.run(cmd, check=True, env=env, cwd=root, timeout=240)
     cfg = G.GPT2Config.tiny(1)
     oh = OracleHandler()
