@@ -46,7 +46,7 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_decode_sample(cfg, reps, threads):
+def cpu_decode_sample(cfg, reps, threads, full_steps=1, budget_s=90.0):
     """Times the reference's algorithm on the host: ONE decoder layer + final norm + logits MatMul of the same
     workload (fp32 arrays holding bf16-rounded values, OpenMP over all host cores), extrapolated to 32 layers.
     Returns (tokens_per_s, description)."""
@@ -88,14 +88,30 @@ def cpu_decode_sample(cfg, reps, threads):
                 for o, r in zip(outs, res):
                     o.value = r
     run(ops)  # warm
+    x_in, x_out = ops[0][2][0], layer_ops[-1][2][0]   # residual stream entering / leaving the decoder layer
     tl, th = [], []
     for _ in range(reps):
         t0 = time.perf_counter(); run(layer_ops); t1 = time.perf_counter(); run(head_ops); t2 = time.perf_counter()
         tl.append(t1 - t0); th.append(t2 - t1)
-    t_step = cfg.layers * statistics.median(tl) + statistics.median(th)
-    desc = (f"1 of {cfg.layers} decoder layers + final norm + logits MatMul of the same workload, {reps} reps, "
-            f"median, extrapolated: {cfg.layers} x {statistics.median(tl) * 1e3:.1f} ms + {statistics.median(th) * 1e3:.1f} ms per step")
-    return cfg.batch / t_step, t_step, desc
+    t_est = cfg.layers * statistics.median(tl) + statistics.median(th)
+    # FULL-DEPTH steps, measured (not extrapolated): the layer ops run cfg.layers times, each pass fed the previous pass's
+    # residual stream (the one layer's weights are re-used: 0.8 GB of fp32 per pass, far larger than the host caches, so
+    # every pass streams from DRAM like distinct layers would), then final norm + logits.  As many as fit `budget_s`.
+    n_full = max(1, min(full_steps, int(budget_s / max(t_est, 1e-6))))
+    full = []
+    for _ in range(n_full):
+        t0 = time.perf_counter()
+        run(ops[:1])
+        for _l in range(cfg.layers):
+            run(layer_ops)
+            x_in.value = x_out.value
+        run(head_ops)
+        full.append(time.perf_counter() - t0)
+    t_step = statistics.median(full)
+    desc = (f"{n_full} full-depth decode step(s) measured on {threads} host threads: embedding + {cfg.layers} x decoder-layer ops "
+            f"(one layer's weights re-used, residual stream chained) + final norm + logits MatMul, median {t_step * 1e3:.0f} ms/step; "
+            f"single-layer sample: {cfg.layers} x {statistics.median(tl) * 1e3:.1f} ms + {statistics.median(th) * 1e3:.1f} ms")
+    return cfg.batch / t_step, t_step, desc, n_full
 
 
 def run_reference(args):
@@ -105,14 +121,14 @@ def run_reference(args):
     from infinitensor_b200 import graphs as G
     cfg = G.LlamaConfig(layers=args.layers)
     threads = os.cpu_count() or 1
-    reps = max(1, min(args.steps, 8))
-    tps, t_step, desc = cpu_decode_sample(cfg, reps, threads)
+    tps, t_step, desc, n_full = cpu_decode_sample(cfg, 2, threads, full_steps=max(1, args.steps), budget_s=150.0)
     line = {
-        "metric": METRIC, "value": round(tps, 3), "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(t_step * 1e3, 3), "higher_is_better": True, "scaling": "strong",
+        "metric": METRIC, "value": round(tps, 3), "unit": "tokens/s", "n_gpus": args.gpus, "steps": n_full,
+        "steps_requested": args.steps, "warmup": 1, "ms_per_step": round(t_step * 1e3, 3), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "llama7b_shape_decode_bf16_b16_p511_smax1024", "batch": cfg.batch, "position": POS,
-                   "parallelism": "host-cpu"},
+        "config": {"workload": "llama7b_shape_decode_bf16_b16_p511_smax1024", "layers": cfg.layers, "d_model": cfg.d_model,
+                   "heads": cfg.heads, "ffn": cfg.ffn, "vocab": cfg.vocab, "batch": cfg.batch, "position": POS,
+                   "s_max": cfg.s_max, "parallelism": "host-cpu"},
         "cpu_baseline": {"value": round(tps, 3), "unit": "tokens/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": round(tps, 3), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -197,18 +213,30 @@ def run_b200(args):
     gen = torch.Generator(device="cuda")
     ts = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def fill(t, std, mean=0.0, seed=0):
-        shape = t.shape()
+    def fill(t, std, mean=0.0, seed=0, shard=None, w=1, r=0):
+        """The FULL (unsharded) tensor is drawn from the seed, then this rank's slice is taken exactly like
+        parallel_opt.py:21-59 shards it -- so every world size sees the same model and the N > 1 logits can be compared
+        with the N = 1 graph (tp_parity below)."""
+        shape = list(t.shape())
+        if shard is not None and w > 1:
+            shape[{"col": 1, "row": 0, "head": 1}[shard]] *= w
         gen.manual_seed(seed)
         tmp = torch.empty(shape, dtype=torch.bfloat16, device="cuda").normal_(mean, std, generator=gen)
+        if shard is not None and w > 1:
+            ax = {"col": 1, "row": 0, "head": 1}[shard]
+            n = shape[ax] // w
+            tmp = tmp.narrow(ax, r * n, n).contiguous()
         L.check(L.lib.it_b200_copy(ctypes.c_void_p(tmp.data_ptr()), ctypes.c_void_p(t.device_ptr()), t.nbytes(), ts))
         torch.cuda.current_stream().synchronize()
 
-    for i, (name, (t, shape, kind, shard)) in enumerate(g.weights.items()):
-        fill(t, 0.02, 1.0 if kind == "norm" else 0.0, seed=1000 + i)
-    for li in range(cfg.layers):
-        fill(g.k_caches[li], 0.5, seed=5000 + li)
-        fill(g.v_caches[li], 0.5, seed=7000 + li)
+    def fill_graph(gr, w, r):
+        for i, (name, (t, shape, kind, shard)) in enumerate(gr.weights.items()):
+            fill(t, 0.02, 1.0 if kind == "norm" else 0.0, seed=1000 + i, shard=shard[0] if shard else None, w=w, r=r)
+        for li in range(cfg.layers):
+            fill(gr.k_caches[li], 0.5, seed=5000 + li, shard="head", w=w, r=r)
+            fill(gr.v_caches[li], 0.5, seed=7000 + li, shard="head", w=w, r=r)
+
+    fill_graph(g, world, rank)
     ids_host = torch.from_numpy(np.random.default_rng(1).integers(0, cfg.vocab, size=(cfg.batch, 1)).astype(np.int64)).pin_memory()
     pos_host = torch.full((cfg.batch, 1), POS, dtype=torch.int64).pin_memory()
     logits_host = torch.empty((cfg.batch, 1, cfg.vocab), dtype=torch.bfloat16).pin_memory()
@@ -244,18 +272,29 @@ def run_b200(args):
         step()
 
     # ---- value: device-timed graph replays, inputs resident
+    # The clock sampler (a fork of nvidia-smi) starts BEFORE the barrier, and one UNTIMED replay follows the barrier: its
+    # in-graph all-reduces put the ranks in device lock-step, and it gives every host 2-3 ms of queued device work to
+    # enqueue e0 and the timed replays behind -- so no rank's start event can land while a peer is already spinning in a
+    # collective of the timed region (round 1's N = 2 line was inflated by exactly that skew).
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    launch_async()
     e0.record(stream)
     for _ in range(args.steps):
         launch_async()
     e1.record(stream)
     e1.synchronize()
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_mine = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(ms_mine)
     ms_step = ms_total / args.steps
     tok_s = cfg.batch * 1000.0 / ms_step
+    ms_ranks = [ms_mine / args.steps]
+    if world > 1:
+        allms = [None] * world
+        dist.all_gather_object(allms, ms_mine / args.steps)
+        ms_ranks = [float(x) for x in allms]
 
     # ---- e2e: host buffers in, host logits out, every step
     h2d = ids_host.numel() * 8 + pos_host.numel() * 8
@@ -267,6 +306,8 @@ def run_b200(args):
         g.logits.copyout_async(logits_host.data_ptr(), d2h)
         h.sync()
     barrier()
+    launch_async()  # untimed: device lock-step across ranks, as above
+    h.sync()
     t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
@@ -335,10 +376,49 @@ def run_b200(args):
     tp = os.path.join(ROOT, "profiles", "gemm_skinny_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")  # measured DRAM bytes, average per launch
+            tj = json.load(open(tp))
+            # measured DRAM bytes, average per launch, from an ncu capture of THIS world size's launch list (null when none
+            # was taken: per-launch bytes shrink with 1/N for the sharded GEMMs)
+            traffic = tj.get("by_world", {}).get(str(world), {}).get("dram_bytes_per_launch")
+            if traffic is None and world == 1:
+                traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
     step_bytes = cfg.algorithmic_bytes(POS, world)
+
+    # ---- tensor-parallel parity, checked IN the bench (the driver's pytest box has one GPU, so this is where a broken
+    # sharded path must fail loudly): rank 0 builds the UNSHARDED graph of the same seeds on its own GPU, runs one step
+    # through the N = 1 path (itself oracle-checked at this width by tests/test_gpu_graph.py) and compares the logits the
+    # N ranks just produced.  Tolerance: bf16 storage, 32 layers, a different fp32 summation order per row-split GEMM
+    # -> rel-to-max 3e-2 (the end-to-end criterion of tests/test_gpu_multi.py), and >= 90 % identical argmax tokens.
+    tp_parity = None
+    if world > 1 and os.environ.get("ITB_BENCH_NO_TP_PARITY", "0") != "1":
+        ok = [True]
+        if rank == 0:
+            h1 = B.GraphHandler(rt)
+            g1 = G.build_llama_decode(h1, cfg, 1, 0)
+            h1.data_malloc()
+            fill_graph(g1, 1, 0)
+            g1.input_ids.copyin_numpy(ids_host.numpy())
+            g1.position_ids.copyin_numpy(pos_host.numpy())
+            h1.run()
+            ref = G.from_storage(g1.logits.copyout_numpy(), cfg.dtype).astype(np.float64).reshape(cfg.batch, -1)
+            got = logits_host.float().numpy().astype(np.float64).reshape(cfg.batch, -1)
+            rel = float(np.abs(got - ref).max() / np.abs(ref).max())
+            agree = float((got.argmax(-1) == ref.argmax(-1)).mean())
+            tp_parity = {"tp_parity_rel_err": rel, "argmax_agreement": agree, "tolerance": 3e-2,
+                         "against": "unsharded graph of the same seeds, one step on rank 0's GPU (N = 1 path)",
+                         "pass": bool(rel < 3e-2 and agree >= 0.9 and logits_finite)}
+            ok[0] = tp_parity["pass"]
+            del h1, g1
+        dist.broadcast_object_list(ok, src=0)
+        if not ok[0]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "n_gpus": world, "invalid": "tensor-parallel parity FAILED",
+                                  "tp_parity": tp_parity}), flush=True)
+            dist.barrier()
+            dist.destroy_process_group()
+            return 3
 
     if rank == 0:
         line = {
@@ -351,6 +431,9 @@ def run_b200(args):
                        "l2": "each step streams >= 17 GB (N=1) through a 126 MB L2; inputs >> L2, no flush",
                        "weight_arena_bytes": wbytes, "activation_arena_bytes": abytes, "logits_finite": logits_finite},
             "clocks": clocks,
+            "ms_per_step_ranks": [round(x, 4) for x in ms_ranks],
+            "tp_parity": tp_parity,
+            "tp_parity_rel_err": tp_parity["tp_parity_rel_err"] if tp_parity else None,
             "e2e": {"value": round(cfg.batch * 1000.0 / e2e_ms, 2), "unit": "tokens/s", "ms_per_step": round(e2e_ms, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_step * args.steps),
@@ -366,7 +449,7 @@ def run_b200(args):
             line["invalid"] = "debug run: --layers != 32"
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            tps, t_step, desc = cpu_decode_sample(cfg, 3, threads)
+            tps, t_step, desc, _n = cpu_decode_sample(cfg, 2, threads, full_steps=1, budget_s=60.0)
             line["cpu_baseline"] = {"value": round(tps, 3), "unit": "tokens/s", "cores": threads, "kind": "port", "sample": desc}
         print(json.dumps(line), flush=True)
     if world > 1:

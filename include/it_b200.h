@@ -198,8 +198,14 @@ int it_b200_conv2d_fused(int dtype, const void *x, const void *w, void *y, int N
  *      Ordering contract (programmatic dependent launch): q / k / v (and the RoPE positions of the _rope variant) may come from
  *      the kernel launched just before on the same stream; `position_id` and the cache rows BELOW the position are read
  *      ahead of griddepcontrol.wait, so they must be OLDER than that -- graph inputs or the previous step's appends, as in
- *      every decode graph the frontend emits.  A caller that produces the position with a kernel of this library in the
- *      same step sets ITB_NO_PDL=1.  The workspace is always required (per-head partial slots). ---- */
+ *      every decode graph the frontend emits.  A caller that produces any of them with a kernel of this library in the
+ *      same step ORs ITB_POS_IN_STEP into pos_dtype (the host kernels do, whenever one of those tensors has a source
+ *      operator).  The workspace is always required (per-head partial slots). ---- */
+#define ITB_POS_PER_ROW 0x100 /* OR into pos_dtype: batch row b uses position_id[b] (ragged batches) instead of the
+                                 reference's element 0 for every row */
+#define ITB_POS_IN_STEP 0x200 /* OR into pos_dtype: position_id / the RoPE positions / cache rows below the position may be written by a
+                                 kernel of the SAME step (in-graph position arithmetic, a Concat of the past): nothing is read ahead of
+                                 griddepcontrol.wait */
 int64_t it_b200_attention_kvcache_workspace(int B, int H, int S_max, int D);
 int it_b200_attention_kvcache(int dtype, void *k_cache, void *v_cache, const void *q,
                               const void *k, const void *v, const void *position_id,
@@ -211,11 +217,13 @@ int it_b200_attention_kvcache(int dtype, void *k_cache, void *v_cache, const voi
  *      <= 64 rows x 16 KiB.  out = T(T(sum_r in_r) + residual); out_norm = RMSNorm(out) * norm_w (optional).
  *      peer_ws[world]: every rank's comm workspace (it_b200_allreduce_workspace_bytes(), zero-filled once) as mapped
  *      in this process (cudaIpcOpenMemHandle); peer_ws[rank] is the local one.  Every rank must issue the same
- *      sequence of calls.  Stream-ordered, CUDA-graph-capturable. ---- */
+ *      sequence of calls.  Stream-ordered, CUDA-graph-capturable.  timeout_flag: device-visible int (host-mapped) set
+ *      non-zero when a peer's packets never arrive -- the step then completes with garbage and the caller raises after
+ *      its next synchronise; NULL = trap instead. ---- */
 int64_t it_b200_allreduce_workspace_bytes(void);
 int it_b200_allreduce_fused(int dtype, const void *in, const void *residual, const void *norm_w, void *out,
                             void *out_norm, int tokens, int hidden, void *const *peer_ws, int world, int rank,
-                            void *stream);
+                            int *timeout_flag, void *stream);
 
 /* ---- AttentionKVCache with the layer's two RoPE ops folded in: q_pre / k_pre are the PRE-RoPE projections
  *      ([B, H*128] == [B,H,1,128]); RoPE (rotate-half, dim_head 128, position rope_pos[b]) is applied on load, the

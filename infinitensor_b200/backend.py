@@ -402,12 +402,20 @@ class GraphHandler:
     def unsqueeze(self, input, output, axes):
         return self._op1("Unsqueeze", [input], output, list(axes))
 
+    def depthToSpace(self, input, output, blocksize, mode):
+        if isinstance(mode, bytes):
+            mode = mode.decode()
+        return self._op1("DepthToSpace", [input], output, [int(blocksize), 1 if mode == "CRD" else 0])
+
     def concat(self, inputs, output, dim):
         return self._op1("Concat", list(inputs), output, [dim])
 
-    def attentionKVCache(self, input_k_cache, input_v_cache, input_q, input_k, input_v, position_id, output_matmul):
+    def attentionKVCache(self, input_k_cache, input_v_cache, input_q, input_k, input_v, position_id, output_matmul,
+                         per_row_positions=False):
+        """per_row_positions (extension): batch row b attends up to / appends at position_id[b]; the default is
+        the reference's rule -- element 0 for every row (attention_kvcache.cu:17)."""
         return self._op1("AttentionKVCache", [input_k_cache, input_v_cache, input_q, input_k, input_v, position_id],
-                         output_matmul)
+                         output_matmul, [1] if per_row_positions else [])
 
     def RoPE(self, pos, input, output):
         return self._op1("RoPE", [pos, input], output)

@@ -174,6 +174,18 @@ class TransposeB200 : public CudaKernelWithoutConfig {
                              op->getPermute().data(), S()), _op);
     }
 };
+// DepthToSpace = the rank-6 permutation of the operator's reshaped view (reference transpose.cc:48-90)
+class DepthToSpaceB200 : public CudaKernelWithoutConfig {
+    void compute(const Operator &_op, const RuntimeObj *) const override {
+        auto op = as<DepthToSpaceObj>(_op);
+        auto x = op->getInputs(0);
+        auto &rd = op->getReshapeDim();
+        vector<int64_t> dims(rd.begin(), rd.end());
+        auto perm = op->getPermute();
+        CK(it_b200_transpose((int)x->getDType().getSize(), P(x), P(op->getOutput()), (int)dims.size(), dims.data(), perm.data(),
+                             S()), _op);
+    }
+};
 class ConcatB200 : public CudaKernelWithoutConfig {
     void compute(const Operator &_op, const RuntimeObj *) const override {
         auto op = as<ConcatObj>(_op);
@@ -377,6 +389,21 @@ void runSiluMul(const Operator &silu, const Operator &mul, const RuntimeObj *) {
     auto u = mul->getInputs(0) == sout ? mul->getInputs(1) : mul->getInputs(0);
     CK(it_b200_silu_mul(DT(g), P(g), P(u), P(mul->getOutput()), (int64_t)g->size(), S()), mul);
 }
+// position dtype + ITB_POS_* flags of an AttentionKVCache launch.  The kernel reads the position, the RoPE positions and the
+// cache rows below the position AHEAD of griddepcontrol.wait, which is only sound when a whole step separates them from their
+// writer: any of them produced by an operator of this graph (in-graph position arithmetic, Concat of the past) -> IN_STEP.
+static int attnPosFlags(const Operator &att, const Tensor &ropePos) {
+    auto pos = att->getInputs(5);
+    int flags = DT(pos);
+    if (as<AttentionKVCacheObj>(att)->getPerRowPositions()) {
+        IT_ASSERT((int64_t)pos->size() >= att->getInputs(0)->getDims()[0], "AttentionKVCache: per-row positions need one entry per batch row");
+        flags |= ITB_POS_PER_ROW;
+    }
+    bool inStep = pos->getSource() != nullptr || att->getInputs(0)->getSource() != nullptr || att->getInputs(1)->getSource() != nullptr;
+    if (ropePos && ropePos->getSource() != nullptr) inStep = true;
+    if (inStep) flags |= ITB_POS_IN_STEP;
+    return flags;
+}
 // RoPE(q), RoPE(k) folded into the decode attention kernel (the aliases between them are storage no-ops)
 void runAttentionRope(const Operator &ropeQ, const Operator &ropeK, const Operator &att, const RuntimeObj *ctx) {
     auto kc = att->getInputs(0), vc = att->getInputs(1), v = att->getInputs(4), pos = att->getInputs(5);
@@ -385,7 +412,7 @@ void runAttentionRope(const Operator &ropeQ, const Operator &ropeK, const Operat
     auto &d = kc->getDims();
     int64_t wsb = it_b200_attention_kvcache_workspace(d[0], d[1], d[2], d[3]);
     void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
-    CK(it_b200_attention_kvcache_rope(DT(qpre), P(kc), P(vc), P(qpre), P(kpre), P(v), P(pos), DT(pos), P(rpos), DT(rpos),
+    CK(it_b200_attention_kvcache_rope(DT(qpre), P(kc), P(vc), P(qpre), P(kpre), P(v), P(pos), attnPosFlags(att, rpos), P(rpos), DT(rpos),
                                       P(att->getOutput()), d[0], d[1], d[2], d[3], ws, wsb, S()), att);
 }
 
@@ -441,7 +468,7 @@ bool runAllReduceAddNorm(const OpVec &ops, const RuntimeObj *ctx) {
         on = P(ops[2]->getOutput());
     }
     CK(it_b200_allreduce_fused(dt.getIndex(), P(in), P(res), nw, P(add->getOutput()), on, (int)tokens, hidden,
-                               rt->peerWorkspaces(), rt->p2pWorldSize(), rt->p2pRank(), S()), ar);
+                               rt->peerWorkspaces(), rt->p2pWorldSize(), rt->p2pRank(), rt->p2pTimeoutFlagDevice(), S()), ar);
     return true;
 }
 }  // namespace b200
@@ -471,7 +498,7 @@ class AttentionKVCacheB200 : public CudaKernelWithoutConfig {
         auto &d = kc->getDims();
         int64_t wsb = it_b200_attention_kvcache_workspace(d[0], d[1], d[2], d[3]);
         void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
-        CK(it_b200_attention_kvcache(DT(q), P(kc), P(vc), P(q), P(k), P(v), P(pos), DT(pos), P(op->getOutput()), d[0],
+        CK(it_b200_attention_kvcache(DT(q), P(kc), P(vc), P(q), P(k), P(v), P(pos), b200::attnPosFlags(op, nullptr), P(op->getOutput()), d[0],
                                      d[1], d[2], d[3], ws, wsb, S()), op);
     }
 };
@@ -561,6 +588,7 @@ REG(LayerNormalization, LayerNormB200, "LayerNorm_B200")
 REG(RMSNorm, RMSNormB200, "RMSNorm_B200")
 REG(RoPE, RoPEB200, "RoPE_B200")
 REG(Transpose, TransposeB200, "Transpose_B200")
+REG(DepthToSpace, DepthToSpaceB200, "DepthToSpace_B200")
 REG(Concat, ConcatB200, "Concat_B200")
 REG(Split, SplitB200, "Split_B200")
 REG(Gather, GatherB200, "Gather_B200")
@@ -576,7 +604,7 @@ REG(ReduceSum, ReduceB200, "ReduceSum_B200")
 REG(MaxPool, PoolingB200, "MaxPool_B200")
 REG(AveragePool, PoolingB200, "AvgPool_B200")
 REG(BatchNormalization, BatchNormB200, "BatchNorm_B200")
-REG(MatMul, MatmulB200, "Matmul_B200_tcgen05_tma")
+REG(MatMul, MatmulB200, "Matmul_B200_tma")  // decode shapes: TMA + mma.sync (gemm_skinny.cu); the rest: tcgen05/TMEM (gemm_tc.cu)
 REG(Conv, ConvB200, "Conv_B200_im2col_gemm")
 REG(AttentionKVCache, AttentionKVCacheB200, "AttentionKVCache_B200")
 REG(AllReduceSum, AllReduceB200, "AllReduceSum_B200")

@@ -27,6 +27,7 @@ CudaRuntimeObj::~CudaRuntimeObj() {
     for (int p = 0; p < p2pWorld; ++p)
         if (p != p2pRankId && p2pWs[p]) cudaIpcCloseMemHandle(p2pWs[p]);
     if (p2pLocal) cudaFree(p2pLocal);
+    if (p2pTimeoutHost) cudaFreeHost(p2pTimeoutHost);
     if (workspace) cudaFree(workspace);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -45,7 +46,20 @@ void CudaRuntimeObj::dealloc(void *ptr) {
     cudaSetDevice(deviceId);
     cudaFree(ptr);
 }
-void CudaRuntimeObj::sync() const { checkCudaError(cudaStreamSynchronize(stream)); }
+void CudaRuntimeObj::sync() const {
+    checkCudaError(cudaStreamSynchronize(stream));
+    checkPeerTimeout();
+}
+// the peer-memory all-reduce gave up waiting for a rank (allreduce.cu): surfaced here, after the step, as a recoverable error
+void CudaRuntimeObj::checkPeerTimeout() const {
+    if (!p2pTimeoutHost) return;
+    int v = *(volatile int *)p2pTimeoutHost;
+    if (v == 0) return;
+    *(volatile int *)p2pTimeoutHost = 0;
+    int code = v - 1;
+    throw Exception("peer-memory all-reduce timed out: rank " + std::to_string(code / 16) + " never received the packets of rank " +
+                    std::to_string(code % 16) + " (dead or stalled peer); the step's outputs are invalid");
+}
 
 void CudaRuntimeObj::copyBlobFromCPU(void *dst, const void *src, size_t bytes) const {
     checkCudaError(cudaSetDevice(deviceId));
@@ -94,6 +108,9 @@ void CudaRuntimeObj::p2pExport(void *handle64) {
         checkCudaError(cudaMalloc(&p2pLocal, bytes));
         checkCudaError(cudaMemset(p2pLocal, 0, bytes));
         checkCudaError(cudaDeviceSynchronize());
+        checkCudaError(cudaHostAlloc((void **)&p2pTimeoutHost, sizeof(int), cudaHostAllocMapped));
+        *p2pTimeoutHost = 0;
+        checkCudaError(cudaHostGetDevicePointer((void **)&p2pTimeoutDev, p2pTimeoutHost, 0));
     }
     cudaIpcMemHandle_t h;
     checkCudaError(cudaIpcGetMemHandle(&h, p2pLocal));
@@ -223,6 +240,7 @@ void CudaRuntimeObj::run(const Graph &graph, bool tuneFlag, bool profiling) cons
     if (tuneFlag) tune(graph);
     runWithoutSyncImpl(graph, true);
     checkCudaError(cudaStreamSynchronize(stream));
+    checkPeerTimeout();
 }
 
 void CudaRuntimeObj::runWithoutSync(const Graph &graph) const {
@@ -311,7 +329,10 @@ void CudaRuntimeObj::runWithCudaGraph(const Graph &graph, bool syncAfter) const 
             it->storageEpoch == graph->getStorageEpoch() && it->sig == sig) {
             cache.splice(cache.begin(), cache, it);  // LRU touch
             checkCudaError(cudaGraphLaunch(cache.front().exec, stream));
-            if (syncAfter) checkCudaError(cudaStreamSynchronize(stream));
+            if (syncAfter) {
+                checkCudaError(cudaStreamSynchronize(stream));
+                checkPeerTimeout();
+            }
             return;
         }
     }
@@ -364,7 +385,10 @@ void CudaRuntimeObj::runWithCudaGraph(const Graph &graph, bool syncAfter) const 
         cache.pop_back();
     }
     checkCudaError(cudaGraphLaunch(cache.front().exec, stream));
-    if (syncAfter) checkCudaError(cudaStreamSynchronize(stream));
+    if (syncAfter) {
+        checkCudaError(cudaStreamSynchronize(stream));
+        checkPeerTimeout();
+    }
 }
 
 }  // namespace infini

@@ -61,6 +61,8 @@ class CudaRuntimeObj : public RuntimeObj {
     void *p2pLocal = nullptr;
     void *p2pWs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int p2pWorld = 0, p2pRankId = 0;
+    int *p2pTimeoutHost = nullptr, *p2pTimeoutDev = nullptr;  // host-mapped flag the all-reduce kernel raises when a peer never arrives
+    void checkPeerTimeout() const;
     mutable std::recursive_mutex executionMutex;
 
     struct TensorSig {
@@ -125,6 +127,7 @@ class CudaRuntimeObj : public RuntimeObj {
     void *const *peerWorkspaces() const { return p2pWs; }
     int p2pWorldSize() const { return p2pWorld; }
     int p2pRank() const { return p2pRankId; }
+    int *p2pTimeoutFlagDevice() const { return p2pTimeoutDev; }
     void initComm(const string &name, int worldSize, int rank);
     void initCommWithId(const void *id, int idBytes, int worldSize, int rank);
     CommunicatorObj &getCommunicator() const {

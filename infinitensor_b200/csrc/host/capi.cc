@@ -233,7 +233,7 @@ static Operator build_op(itb_graph *h, const string &name, const TensorVec &in, 
                                  (int)I(5, 1));
     case OpType::AttentionKVCache:
         need(6);
-        return g->addOp<AttentionKVCacheObj>(in[0], in[1], in[2], in[3], in[4], in[5], o0);
+        return g->addOp<AttentionKVCacheObj>(in[0], in[1], in[2], in[3], in[4], in[5], o0, (bool)I(0, 0));
     case OpType::Softmax: need(1); return g->addOp<SoftmaxObj>(in[0], o0, (int)I(0, -1));
     case OpType::LayerNormalization:
         need(2);
@@ -259,6 +259,7 @@ static Operator build_op(itb_graph *h, const string &name, const TensorVec &in, 
         return op;
     }
     case OpType::Transpose: need(1); return g->addOp<TransposeObj>(in[0], o0, ivec(ia, 0, ni));
+    case OpType::DepthToSpace: need(1); return g->addOp<DepthToSpaceObj>(in[0], o0, (int)I(0, 1), I(1, 0) ? "CRD" : "DCR");
     case OpType::Concat: need(1); return g->addOp<ConcatObj>(in, o0, (int)I(0));
     case OpType::Split: {
         need(1);

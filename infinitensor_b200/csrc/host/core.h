@@ -156,9 +156,15 @@ class TensorObj : public std::enable_shared_from_this<TensorObj> {
     Runtime getRuntime() const { return runtime; }
     UidBaseType getGuid() const { return guid; }
     UidBaseType getFuid() const { return fuid; }
-    void setWeight() { weightFlag = true; }
-    void setInput() { inputFlag = true; }
-    void setOutput() { outputFlag = true; }
+    // fusion and alias decisions read these flags (isOutput / isWeight / isInput), so changing one must invalidate every cached
+    // schedule, dispatch plan and captured CUDA graph: a process-wide counter the graphs fold into their topology epoch
+    static uint64_t &flagsEpoch() {
+        static uint64_t e = 0;
+        return e;
+    }
+    void setWeight() { if (!weightFlag) ++flagsEpoch(); weightFlag = true; }
+    void setInput() { if (!inputFlag) ++flagsEpoch(); inputFlag = true; }
+    void setOutput() { if (!outputFlag) ++flagsEpoch(); outputFlag = true; }
     bool isWeight() const { return weightFlag; }
     bool isInput() const { return inputFlag; }
     bool isOutput() const { return outputFlag; }
@@ -365,7 +371,8 @@ class GraphObj : public std::enable_shared_from_this<GraphObj> {
     TensorVec tensors;
     OpVec ops;
     bool sorted = true;
-    uint64_t graphId, topologyEpoch = 0, storageEpoch = 0;
+    uint64_t graphId, storageEpoch = 0;
+    mutable uint64_t topologyEpoch = 0, seenFlagsEpoch = 0;
     Blob weightArena, activationArena;
     size_t weightBytes = 0, activationBytes = 0;
     bool weightsAllocated = false;
@@ -385,7 +392,13 @@ class GraphObj : public std::enable_shared_from_this<GraphObj> {
     const OpVec &getOperators() const { return ops; }
     Tensor getTensorByFuid(UidBaseType fuid) const;
     uint64_t getGraphId() const { return graphId; }
-    uint64_t getTopologyEpoch() const { return topologyEpoch; }
+    uint64_t getTopologyEpoch() const {
+        if (seenFlagsEpoch != TensorObj::flagsEpoch()) {  // a tensor flag changed somewhere: treat as a topology change
+            seenFlagsEpoch = TensorObj::flagsEpoch();
+            ++topologyEpoch;
+        }
+        return topologyEpoch;
+    }
     uint64_t getStorageEpoch() const { return storageEpoch; }
 
     template <typename T, typename... Args> Ref<T> addOp(Args &&...args) {

@@ -69,9 +69,10 @@ vector<int> ConvObj::getWorkloadVector() const {
 // ---------------------------------------------------------------- AttentionKVCache (attention_kvcache.cc:5-27)
 AttentionKVCacheObj::AttentionKVCacheObj(GraphObj *graph, Tensor input_k_cache, Tensor input_v_cache,
                                          Tensor input_q, Tensor input_k, Tensor input_v, Tensor position_id,
-                                         Tensor output_matmul)
+                                         Tensor output_matmul, bool perRowPositions)
     : OperatorObj(OpType::AttentionKVCache, {input_k_cache, input_v_cache, input_q, input_k, input_v, position_id},
-                  {output_matmul}) {
+                  {output_matmul}),
+      perRowPositions(perRowPositions) {
     IT_ASSERT(checkValid(graph));
 }
 std::optional<vector<Shape>> AttentionKVCacheObj::inferShape(const TensorVec &ins) {
@@ -148,6 +149,27 @@ vector<int> TransposeObj::getOpAttrVector() const {
     vector<int> r{(int)type.underlying()};
     r.insert(r.end(), transposePermute.begin(), transposePermute.end());
     return r;
+}
+
+DepthToSpaceObj::DepthToSpaceObj(GraphObj *graph, Tensor input, Tensor output, int blocksize, string mode)
+    : OperatorObj(OpType::DepthToSpace, {input}, {output}), blockSize(blocksize), d2sMode(mode == "CRD" ? 1 : 0),
+      modeString(mode == "CRD" ? "CRD" : "DCR") {
+    IT_ASSERT(blocksize >= 1, "DepthToSpace: blocksize must be positive");
+    IT_ASSERT(checkValid(graph));
+}
+std::optional<vector<Shape>> DepthToSpaceObj::inferShape(const TensorVec &ins) {
+    const auto &d = ins[0]->getDims();
+    IT_ASSERT(d.size() == 4, "DepthToSpace expects NCHW");
+    const int b = blockSize, c = d[1] / (b * b);
+    IT_ASSERT(c * b * b == d[1], "DepthToSpace: channels must be a multiple of blocksize^2");
+    // the input viewed as rank 6, and where each of those axes lands (ONNX DepthToSpace: DCR splits the channel axis as
+    // (b, b, c), CRD as (c, b, b)); the output interleaves (H, b) and (W, b)
+    reshapeDim = d2sMode == 0 ? vector<int>{d[0], b, b, c, d[2], d[3]} : vector<int>{d[0], c, b, b, d[2], d[3]};
+    const auto perm = getPermute();
+    transposeDim.assign(6, 1);
+    for (int i = 0; i < 6; ++i) transposeDim[i] = reshapeDim[perm[i]];
+    outDim = {d[0], c, d[2] * b, d[3] * b};
+    return {{outDim}};
 }
 
 ConcatObj::ConcatObj(GraphObj *graph, TensorVec inputs, Tensor output, int dim_)

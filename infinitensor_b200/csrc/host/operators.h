@@ -59,9 +59,14 @@ class ConvObj : public OperatorObj {
 };
 
 class AttentionKVCacheObj : public OperatorObj {
+    bool perRowPositions;  // extension: row b attends up to position_id[b]; false = the reference's element-0 rule
+
   public:
     AttentionKVCacheObj(GraphObj *graph, Tensor input_k_cache, Tensor input_v_cache, Tensor input_q,
-                        Tensor input_k, Tensor input_v, Tensor position_id, Tensor output_matmul);
+                        Tensor input_k, Tensor input_v, Tensor position_id, Tensor output_matmul,
+                        bool perRowPositions = false);
+    bool getPerRowPositions() const { return perRowPositions; }
+    vector<int> getOpAttrVector() const override { return {(int)type.underlying(), (int)perRowPositions}; }
     std::optional<vector<Shape>> inferShape(const TensorVec &inputs) override;
     vector<DataType> inferDataType(const TensorVec &ins) const override { return {ins[2]->getDType()}; }
 };
@@ -157,6 +162,26 @@ class TransposeObj : public OperatorObj {
     std::optional<vector<Shape>> inferShape(const TensorVec &inputs) override;
     const vector<int> &getPermute() const { return transposePermute; }
     vector<int> getOpAttrVector() const override;
+};
+
+// DepthToSpace (reference include/operators/transpose.h:23-49, src/operators/transpose.cc:53-107): [N, C, H, W] ->
+// [N, C / b^2, H b, W b]; executed as the rank-6 permutation the ONNX specification defines for each mode.
+class DepthToSpaceObj : public OperatorObj {
+    int blockSize, d2sMode;  // mode 0 = "DCR" (depth-column-row), 1 = "CRD"
+    string modeString;
+    mutable vector<int> reshapeDim, transposeDim, outDim;
+
+  public:
+    DepthToSpaceObj(GraphObj *graph, Tensor input, Tensor output, int blocksize, string mode);
+    std::optional<vector<Shape>> inferShape(const TensorVec &inputs) override;
+    int getBlockSize() const { return blockSize; }
+    int getMode() const { return d2sMode; }
+    const string &getModeString() const { return modeString; }
+    const vector<int> &getReshapeDim() const { return reshapeDim; }
+    const vector<int> &getTransposeDim() const { return transposeDim; }
+    const vector<int> &getOutDim() const { return outDim; }
+    vector<int> getPermute() const { return d2sMode == 0 ? vector<int>{0, 3, 4, 1, 5, 2} : vector<int>{0, 1, 4, 2, 5, 3}; }
+    vector<int> getOpAttrVector() const override { return {(int)type.underlying(), blockSize, d2sMode}; }
 };
 
 class ConcatObj : public OperatorObj {

@@ -69,7 +69,7 @@ static bool groupableMatmul(const Operator &op) {
 }
 
 const vector<ExecStep> &GraphObj::getSchedule() {
-    if (scheduleEpoch == topologyEpoch && !schedule.empty()) return schedule;
+    if (scheduleEpoch == getTopologyEpoch() && !schedule.empty()) return schedule;
     IT_ASSERT(topo_sort(), "graph has a cycle");
     schedule.clear();
     const bool fuse = fusionEnabled();
@@ -165,7 +165,8 @@ const vector<ExecStep> &GraphObj::getSchedule() {
                 auto out = op->getOutput();
                 auto targets = out->getTargets();
                 if (!mm->getBias() && out->getDType().isFloat() && targets.size() == 1 && !out->isOutput() &&
-                    targets[0]->getOpType() == OpType::Add && !deferredInto.count(targets[0].get())) {
+                    targets[0]->getOpType() == OpType::Add && !deferredInto.count(targets[0].get()) &&
+                    !deferred.count(targets[0].get()) && !consumed.count(targets[0].get())) {
                     auto add = targets[0];
                     auto other = add->getInputs(0) == out ? add->getInputs(1) : add->getInputs(0);
                     if (other != out && other->getDims() == out->getDims() && other->getDType() == out->getDType() &&
@@ -197,7 +198,7 @@ const vector<ExecStep> &GraphObj::getSchedule() {
             auto out = op->getOutput();
             auto targets = out->getTargets();
             if (out->getDType().isFloat() && targets.size() == 1 && !out->isOutput() && targets[0]->getOpType() == OpType::Add &&
-                !deferredInto.count(targets[0].get())) {
+                !deferredInto.count(targets[0].get()) && !deferred.count(targets[0].get()) && !consumed.count(targets[0].get())) {
                 auto add = targets[0];
                 auto other = add->getInputs(0) == out ? add->getInputs(1) : add->getInputs(0);
                 if (other != out && other->getDims() == out->getDims() && other->getDType() == out->getDType() &&
@@ -247,7 +248,7 @@ const vector<ExecStep> &GraphObj::getSchedule() {
             auto out = op->getOutput();
             auto targets = out->getTargets();
             if (targets.size() == 1 && !out->isOutput() && targets[0]->getOpType() == OpType::Mul &&
-                !deferredInto.count(targets[0].get())) {
+                !deferredInto.count(targets[0].get()) && !deferred.count(targets[0].get()) && !consumed.count(targets[0].get())) {
                 auto mul = targets[0];
                 auto other = mul->getInputs(0) == out ? mul->getInputs(1) : mul->getInputs(0);
                 if (other != out && other->getDims() == out->getDims() && other->getDType() == out->getDType() &&
@@ -259,6 +260,14 @@ const vector<ExecStep> &GraphObj::getSchedule() {
             }
         }
         schedule.push_back(std::move(st));
+    }
+    // every operator is executed by exactly one step (a producer parked behind a consumer that never runs would be a
+    // silently skipped op)
+    {
+        std::unordered_map<OperatorObj *, int> seen;
+        for (auto &stp : schedule)
+            for (auto &m : stp.ops) ++seen[m.get()];
+        for (auto &o : ops) IT_ASSERT(seen[o.get()] == 1, "schedule: operator " + o->toString() + " is not covered by exactly one step");
     }
     scheduleEpoch = topologyEpoch;
     return schedule;

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) pad_rows_kernel(const T *__restrict__ w, 
     }
 }
 
-// Kernel selection.  ITB_GEMM_IMPL = tc | skinny | streamk | simt pins one implementation (A/B testing and the parity
+// Kernel selection.  ITB_GEMM_IMPL = tc | skinny | simt pins one implementation (A/B testing and the parity
 // tests that must exercise each kernel); unset = the production order below.
 static int run_gemm(int dtype, const GemmArgs &g, cudaStream_t st) {
     if (g.batch == 0 || g.m == 0 || g.n == 0) return 0;
@@ -146,7 +146,6 @@ static int run_gemm(int dtype, const GemmArgs &g, cudaStream_t st) {
     if (pin && pin[0]) {
         if (!strcmp(pin, "tc")) r = launch_gemm_tc(dtype, g, st);
         else if (!strcmp(pin, "skinny")) r = launch_gemm_skinny(dtype, g, st);
-        else if (!strcmp(pin, "streamk")) r = launch_gemm_streamk(dtype, g, st);
         else if (strcmp(pin, "simt")) ITB_FAIL("matmul: unknown ITB_GEMM_IMPL '%s'", pin);
         if (r >= 0) return r;
         return launch_gemm_simt(dtype, g, st);
@@ -184,10 +183,6 @@ extern "C" int it_b200_matmul_grouped(int dtype, const void *X, int n_groups, co
     auto st = (cudaStream_t)stream;
     GemmArgs g{X, W[0], nullptr, C[0], 1, m, N[0], k, (int64_t)m * k, 0, 0, 0, 0, 0, 0, ITB_MATMUL_B_CONST};
     const char *pin = std::getenv("ITB_GEMM_IMPL");
-    if (pin && !strcmp(pin, "streamk")) {
-        int r = launch_gemm_streamk_grouped(dtype, g, n_groups, W, C, N, st);
-        if (r >= 0) return r;
-    }
     if (!(pin && pin[0]) || !strcmp(pin, "skinny")) {
         int r = launch_gemm_skinny_grouped(dtype, g, n_groups, W, C, N, st);
         if (r >= 0) return r;

@@ -45,9 +45,6 @@ int launch_gemm_skinny(int dtype, const GemmArgs &g, cudaStream_t st);
 int launch_gemm_skinny_grouped(int dtype, const GemmArgs &g0, int ngroups, const void *const *Ws, void *const *Cs,
                                const int *Ns, cudaStream_t st);
 int launch_gemm_tc(int dtype, const GemmArgs &g, cudaStream_t st);
-int launch_gemm_streamk(int dtype, const GemmArgs &g, cudaStream_t st);
-int launch_gemm_streamk_grouped(int dtype, const GemmArgs &g0, int ngroups, const void *const *Ws, void *const *Cs,
-                                const int *Ns, cudaStream_t st);
 
 // ---- TMA descriptor creation (driver entry point fetched at run time; no link-time libcuda) ----
 // 2-D row-major tensor [rows, cols] of 2-byte elements, box [box_rows, box_cols], 128B swizzle.

@@ -285,12 +285,18 @@ static int launch_skinny_nb(const GemmArgs &g, int ngroups, const void *const *W
     }
     const int stages = Cfg::stages_for(budget_kb);
     const int smem_bytes = Cfg::smem_for(stages);
-    static int attr_smem = 0;
     auto kern = gemm_skinny_kernel<T, MT, NB>;
-    if (smem_bytes > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-        ITB_CHECK(e == cudaSuccess, "matmul(skinny): smem attribute: %s", cudaGetErrorString(e));
-        attr_smem = smem_bytes;
+    {
+        // the attribute is per DEVICE (a process may own runtimes on several GPUs): remember the largest request per device
+        static int attr_smem[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (smem_bytes > attr_smem[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+            ITB_CHECK(e == cudaSuccess, "matmul(skinny): smem attribute: %s", cudaGetErrorString(e));
+            attr_smem[dev] = smem_bytes;
+        }
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(tiles_n, splitk, 1);

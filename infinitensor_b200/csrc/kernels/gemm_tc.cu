@@ -403,12 +403,17 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
                          (uint64_t)g.stride_a, (uint32_t)p.mpad, TC_BK))
         ITB_FAIL("matmul(tcgen05): cuTensorMapEncodeTiled(X) failed");
 
-    static int attr_smem = 0;
     auto kern = gemm_tc_kernel<T>;
-    if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        ITB_CHECK(e == cudaSuccess, "matmul(tcgen05): smem attribute: %s", cudaGetErrorString(e));
-        attr_smem = smem;
+    {
+        static int attr_smem[64] = {0};  // per device (see gemm_skinny.cu)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (smem > attr_smem[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            ITB_CHECK(e == cudaSuccess, "matmul(tcgen05): smem attribute: %s", cudaGetErrorString(e));
+            attr_smem[dev] = smem;
+        }
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(tiles_n, splitk, (unsigned)(g.batch * p.m_chunks));

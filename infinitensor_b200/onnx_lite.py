@@ -565,6 +565,9 @@ class OnnxStub:
         elif op == "Transpose":
             perm = a.get("perm") or list(range(len(I(0).shape())))[::-1]
             T[out0] = h.transpose(I(0), None, [int(x) for x in perm])
+        elif op == "DepthToSpace":  # onnx.py:656-670
+            mode = a.get("mode", b"DCR")
+            T[out0] = h.depthToSpace(I(0), None, int(a["blocksize"]), mode.decode() if isinstance(mode, bytes) else mode)
         elif op == "Reshape":
             shape = self._ints(nd, 1, "shape", required=True)
             src = I(0).shape()
@@ -756,6 +759,10 @@ class OnnxExporter:
 
     def transpose(self, x, y, perm):
         return self._emit("Transpose", [x], self.inner.transpose(x.inner, self._in(y), perm), {"perm": [int(p) for p in perm]})
+
+    def depthToSpace(self, x, y, blocksize, mode):
+        return self._emit("DepthToSpace", [x], self.inner.depthToSpace(x.inner, self._in(y), blocksize, mode),
+                          {"blocksize": int(blocksize), "mode": mode})
 
     def reshape(self, x, y, shape):
         r = self.inner.reshape(x.inner, self._in(y), shape)

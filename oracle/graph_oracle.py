@@ -183,6 +183,21 @@ class OracleHandler:
         out = self._out(y, [x.dims[p] for p in perm], x.dt)
         return self._rec(lambda: O.transpose(x.value, perm), [x], [out])
 
+    def depthToSpace(self, x, y, blocksize, mode):
+        """reference src/operators/transpose.cc:68-107 (shape rule) + src/kernels/cuda/transpose.cc:48-90 (the rank-6 permute)"""
+        if isinstance(mode, bytes):
+            mode = mode.decode()
+        n, c, hh, ww = x.dims
+        b = int(blocksize)
+        out = self._out(y, [n, c // (b * b), hh * b, ww * b], x.dt)
+
+        def run():
+            v = np.asarray(x.value)
+            if mode == "CRD":
+                return np.ascontiguousarray(v.reshape(n, c // (b * b), b, b, hh, ww).transpose(0, 1, 4, 2, 5, 3)).reshape(out.dims)
+            return np.ascontiguousarray(v.reshape(n, b, b, c // (b * b), hh, ww).transpose(0, 3, 4, 1, 5, 2)).reshape(out.dims)
+        return self._rec(run, [x], [out])
+
     def reshape(self, x, y, shape):
         shape = list(np.empty(x.dims, dtype=np.bool_).reshape(shape).shape)
         out = self._out(y, shape, x.dt)
@@ -215,11 +230,16 @@ class OracleHandler:
         out = self._out(y, dims, data.dt)
         return self._rec(lambda: O.gather(data.value, indices.value, axis), [data, indices], [out])
 
-    def attentionKVCache(self, kc, vc, q, k, v, pos, y):
+    def attentionKVCache(self, kc, vc, q, k, v, pos, y, per_row_positions=False):
         out = self._out(y, q.dims, q.dt)
 
         def run():
             # in-place append into the cache INPUTS (attention_kvcache.cu:49-53,89-93)
+            if per_row_positions:  # the kernel of attention_kvcache.cu:8-145 applied to each batch row with its own position
+                pv = np.asarray(pos.value).ravel()
+                qv, kv, vv = (np.ascontiguousarray(t.value, np.float32) for t in (q, k, v))
+                return np.concatenate([O.attention_kvcache(kc.value[b:b + 1], vc.value[b:b + 1], qv[b:b + 1], kv[b:b + 1],
+                                                           vv[b:b + 1], int(pv[b]), q.dt) for b in range(q.dims[0])])
             return O.attention_kvcache(kc.value, vc.value, q.value, k.value, v.value, int(np.asarray(pos.value).ravel()[0]), q.dt)
         return self._rec(run, [kc, vc, q, k, v, pos], [out])
 

@@ -333,13 +333,16 @@ def conv2d(x, w, ph, pw, sh, sw, dh, dw, dt=F32):
     return host(y)
 
 
-def attention_kvcache(kc, vc, q, k, v, pos, dt=F32, pos_np_dtype=np.int64):
-    """Returns (out, kcache_after, vcache_after) as float32 numpy."""
+def attention_kvcache(kc, vc, q, k, v, pos, dt=F32, pos_np_dtype=np.int64, flags=0):
+    """Returns (out, kcache_after, vcache_after) as float32 numpy.  `pos`: one int (the reference's rule: element 0 for every
+    row) or a per-row sequence (flags gets ITB_POS_PER_ROW = 0x100)."""
     kcd, vcd = dev(kc, dt), dev(vc, dt)
     qd, kd, vd = dev(q, dt), dev(k, dt), dev(v, dt)
     B, H, Smax, D = kc.shape
-    pd = raw(np.array([pos], dtype=pos_np_dtype))
-    code = {np.int64: 7, np.int32: 6, np.uint32: 12}[pos_np_dtype]
+    if np.ndim(pos) > 0:
+        flags |= 0x100
+    pd = raw(np.atleast_1d(np.asarray(pos)).astype(pos_np_dtype))
+    code = {np.int64: 7, np.int32: 6, np.uint32: 12}[pos_np_dtype] | flags
     out = torch.empty_like(qd)
     wsb = L.lib.it_b200_attention_kvcache_workspace(B, H, Smax, D)
     ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device="cuda")

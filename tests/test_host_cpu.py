@@ -434,3 +434,83 @@ def test_skinny_gemm_split_k_partition_properties():
                 assert e > b, (tiles, ktiles, splitk, per)
                 covered += list(range(b, e))
             assert covered == list(range(ktiles)) and 1 <= splitk <= 8
+
+
+def test_attention_unit_partition_with_per_row_positions():
+    """Per-row positions (ITB_POS_PER_ROW): row b has its own chunk count, the units are the concatenation of every row's
+    H x nch_b (head, chunk) grid and `pre[b]` = units before row b (attention.cu: s_pre).  Same properties as the uniform case:
+    every unit owned once, a head's owners are consecutive CTAs, the closed forms for first / last CTA of a head hold."""
+    rng = np.random.default_rng(0)
+    for B, H in ((1, 1), (3, 2), (16, 4), (5, 9)):
+        for _ in range(6):
+            nch = rng.integers(1, 17, size=B).tolist()
+            pre = [0]
+            for b in range(B):
+                pre.append(pre[-1] + H * nch[b])
+            total = pre[-1]
+            for grid in (1, 3, 8, 31, 296):
+                G = min(grid, total)
+                owner = {}
+                for i in range(G):
+                    u0, u1 = i * total // G, (i + 1) * total // G
+                    assert u1 > u0
+                    b = 0
+                    while b + 1 < B and pre[b + 1] <= u0:
+                        b += 1
+                    assert pre[b] <= u0 < pre[b + 1]  # the kernel's starting-row search
+                    for u in range(u0, u1):
+                        owner[u] = i
+                assert len(owner) == total
+                for b in range(B):
+                    for hh in range(H):
+                        hu0 = pre[b] + hh * nch[b]
+                        first, last = ((hu0 + 1) * G - 1) // total, ((hu0 + nch[b]) * G - 1) // total
+                        assert sorted({owner[hu0 + c] for c in range(nch[b])}) == list(range(first, last + 1))
+                        assert last - first + 1 <= nch[b]
+
+
+def test_every_kernel_waits_for_its_predecessor():
+    """Programmatic dependent launch invariant the peer-memory all-reduce's epoch hand-over relies on (allreduce.cu header):
+    every __global__ kernel of the library that triggers its dependents also executes griddepcontrol.wait, so completion is
+    transitive along the stream.  Checked on the sources: each kernel body mentions pdl_wait() or calls a helper that does."""
+    kdir = os.path.join(ROOT, "infinitensor_b200", "csrc", "kernels")
+    bad = []
+    for f in sorted(os.listdir(kdir)):
+        if not f.endswith(".cu"):
+            continue
+        src = open(os.path.join(kdir, f)).read()
+        parts = re.split(r"__global__", src)
+        for body in parts[1:]:
+            name = re.search(r"(\w+)\s*\(", body.split("{", 1)[0].replace("__launch_bounds__", ""))
+            # the kernel's text runs to the next top-level `}` at column 0
+            end = body.find("\n}\n")
+            text = body[: end if end > 0 else len(body)]
+            if "pdl_trigger" in text and "pdl_wait" not in text:
+                bad.append(f"{f}:{name.group(1) if name else '?'}")
+            if "pdl_trigger" not in text and "pdl_wait" not in text:
+                bad.append(f"{f}:{name.group(1) if name else '?'} (no PDL calls at all)")
+    assert not bad, bad
+
+
+def test_depth_to_space_shapes_and_oracle(B):
+    """DepthToSpace (reference src/operators/transpose.cc:53-107): shape rule on the host core; the oracle handler follows the
+    ONNX definition -- checked against the worked example of the ONNX operator documentation (DCR mode)."""
+    from oracle.graph_oracle import OracleHandler
+    h = B.GraphHandler(B.HostPlanRuntime())
+    assert h.depthToSpace(h.tensor([1, 8, 2, 3], 1), None, 2, "DCR").shape() == [1, 2, 4, 6]
+    assert h.depthToSpace(h.tensor([2, 16, 5, 7], 10), None, 2, "CRD").shape() == [2, 4, 10, 14]
+    with pytest.raises(RuntimeError):
+        h.depthToSpace(h.tensor([1, 6, 2, 2], 1), None, 2, "DCR")
+    x = np.arange(48, dtype=np.float32).reshape(1, 8, 2, 3)
+    want = np.array([[[[0., 18., 1., 19., 2., 20.], [36., 54., 37., 55., 38., 56.], [3., 21., 4., 22., 5., 23.], [39., 57., 40., 58., 41., 59.]],
+                      [[9., 27., 10., 28., 11., 29.], [45., 63., 46., 64., 47., 65.], [12., 30., 13., 31., 14., 32.], [48., 66., 49., 67., 50., 68.]]]])
+    x2 = np.array([[[[0., 1., 2.], [3., 4., 5.]], [[9., 10., 11.], [12., 13., 14.]], [[18., 19., 20.], [21., 22., 23.]], [[27., 28., 29.], [30., 31., 32.]],
+                    [[36., 37., 38.], [39., 40., 41.]], [[45., 46., 47.], [48., 49., 50.]], [[54., 55., 56.], [57., 58., 59.]], [[63., 64., 65.], [66., 67., 68.]]]],
+                  np.float32)
+    oh = OracleHandler()
+    t = oh.tensor([1, 8, 2, 3], 1)
+    y = oh.depthToSpace(t, None, 2, "DCR")
+    t.copyin_numpy(x2)
+    oh.run()
+    assert np.array_equal(np.asarray(y.f32()).reshape(want.shape), want)
+    del x

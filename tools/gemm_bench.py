@@ -56,7 +56,7 @@ def run(impl, m, k, n, reps=40, nbuf=12):
 if __name__ == "__main__":
     if os.environ.get("GEMM_BENCH_SHAPES"):  # "m,k,n;m,k,n;..."
         SHAPES = [tuple(int(v) for v in t.split(",")) for t in os.environ["GEMM_BENCH_SHAPES"].split(";")]
-    impls = sys.argv[1:] or ["skinny", "tc", "streamk"]
+    impls = sys.argv[1:] or ["skinny", "tc"]
     print(f"{'shape':>22s} " + " ".join(f"{i:>22s}" for i in impls))
     for (m, k, n) in SHAPES:
         row = []

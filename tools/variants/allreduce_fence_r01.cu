@@ -15,13 +15,7 @@
 //   optionally RMS-normalises the new residual row in the same pass and stores that too;  (4) bumps epoch[row].
 // Double buffering by epoch parity makes a trailing barrier unnecessary (a rank can only start epoch e+2 after every
 // peer finished reading epoch e's buffer).  No host involvement: CUDA-graph-capturable, PDL-chained.
-// A peer that never shows up (crashed rank, start-up skew beyond the poll budget) does NOT trap the context: the poll
-// gives up after ~2^26 probes, raises *timeout_flag (host-mapped memory the runtime checks after every synchronise) and
-// lets the step finish with garbage, so every rank gets a recoverable infini::Exception instead of a sticky fatal error.
-// Ordering contract: epoch[row] is handed from one all-reduce launch to the next through TRANSITIVE completion -- every
-// kernel of this library executes griddepcontrol.wait on every path before it exits (tests/test_host_cpu.py checks the
-// sources), so "my predecessor finished" implies "everything before it finished".
-// (The first-generation fence.sys + release/acquire-flag protocol is kept, unbuilt, in tools/variants/.)
+// ITB_AR_PROTO=fence selects the first-generation protocol (plain rows + fence.sys + release/acquire flags).
 #include <algorithm>
 #include <cstdlib>
 #include <string>
@@ -68,8 +62,7 @@ __device__ __forceinline__ void st_volatile_v4(void *p, uint4 v) {
 template <typename T>
 __global__ void __launch_bounds__(512) allreduce_ll_kernel(ArPeers peers, int world, int rank, const T *__restrict__ in,
                                                            const T *__restrict__ residual, const T *__restrict__ norm_w,
-                                                           T *__restrict__ out, T *__restrict__ out_norm, int hidden,
-                                                           int *timeout_flag) {
+                                                           T *__restrict__ out, T *__restrict__ out_norm, int hidden) {
     constexpr int V = Vec16<T>::N;
     __shared__ float red[32];
     pdl_trigger();
@@ -81,7 +74,6 @@ __global__ void __launch_bounds__(512) allreduce_ll_kernel(ArPeers peers, int wo
     const int e = *epoch_p;  // only CTA `row` of this stream's kernels ever writes epoch[row]
     const int b = e & 1;
     const uint32_t tag = (uint32_t)(e + 1);
-    bool gave_up = false;
     const size_t slot = (((size_t)b * AR_MAX_WORLD + rank) * AR_MAX_ROWS + row) * AR_SLOT_BYTES;
 
     // (1) push: vector i of my partial row -> packets 2i, 2i+1 of my slot on every rank (own copy included)
@@ -113,13 +105,8 @@ __global__ void __launch_bounds__(512) allreduce_ll_kernel(ArPeers peers, int wo
         for (int p = 0; p < AR_MAX_WORLD; ++p)
             if (p < world) {
                 unsigned spins = 0;
-                while (!gave_up && (pa[p].y != tag || pa[p].w != tag || pc[p].y != tag || pc[p].w != tag)) {
-                    if (++spins > (1u << 26)) {  // a dead peer must neither hang the box nor kill the context
-                        gave_up = true;
-                        if (timeout_flag) *(volatile int *)timeout_flag = 1 + rank * 16 + p;
-                        else __trap();
-                        break;
-                    }
+                while (pa[p].y != tag || pa[p].w != tag || pc[p].y != tag || pc[p].w != tag) {
+                    if (++spins > (1u << 26)) __trap();  // a dead peer must not hang the box
                     pa[p] = ld_volatile_v4(src0 + p * kRankStride);
                     pc[p] = ld_volatile_v4(src0 + p * kRankStride + 16);
                 }
@@ -153,6 +140,87 @@ __global__ void __launch_bounds__(512) allreduce_ll_kernel(ArPeers peers, int wo
     if (threadIdx.x == 0) *epoch_p = e + 1;
 }
 
+template <typename T>
+__global__ void __launch_bounds__(512) allreduce_fused_kernel(ArPeers peers, int world, int rank, const T *__restrict__ in,
+                                                              const T *__restrict__ residual,
+                                                              const T *__restrict__ norm_w, T *__restrict__ out,
+                                                              T *__restrict__ out_norm, int hidden) {
+    constexpr int V = Vec16<T>::N;
+    __shared__ float red[32];
+    pdl_trigger();
+    const int row = blockIdx.x;
+    const int row_bytes = hidden * (int)sizeof(T);
+    char *local = (char *)peers.ws[rank];
+    int *epoch_p = (int *)(local + ar_epoch_off()) + row;
+    const int nv = hidden / V;
+    pdl_wait();  // `in` comes from the preceding row-split MatMul; epoch[row] from the previous all-reduce kernel
+    const int e = *epoch_p;  // only CTA `row` of this stream's kernels ever writes epoch[row]
+    const int b = e & 1;
+
+    // (1) push my partial row to every rank (own copy included: the sum below reads only local memory)
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const Vec16<T> v = ld16(in + (size_t)row * hidden + i * V);
+        for (int p = 0; p < world; ++p) {
+            char *dst = (char *)peers.ws[p] + ar_data_off() +
+                        (((size_t)b * AR_MAX_WORLD + rank) * AR_MAX_ROWS + row) * AR_MAX_ROW_BYTES;
+            st16((T *)dst + i * V, v);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    // (2) publish: flag[b][row][rank] = e + 1 on every rank
+    if (threadIdx.x < world) {
+        int *f = (int *)((char *)peers.ws[threadIdx.x] + ar_flags_off()) + ((size_t)b * AR_MAX_ROWS + row) * AR_MAX_WORLD + rank;
+        st_release_sys(f, e + 1);
+    }
+    // (3) wait for everybody's row
+    if (threadIdx.x < world) {
+        const int *f = (const int *)(local + ar_flags_off()) + ((size_t)b * AR_MAX_ROWS + row) * AR_MAX_WORLD + threadIdx.x;
+        unsigned spins = 0;
+        while (ld_acquire_sys(f) != e + 1) {
+            if (++spins > (1u << 28)) __trap();  // a dead peer must not hang the box
+        }
+    }
+    __syncthreads();
+    // (4) reduce in rank order from local memory, residual add, optional RMSNorm
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        float acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = 0.f;
+        for (int p = 0; p < world; ++p) {
+            const char *src = local + ar_data_off() + (((size_t)b * AR_MAX_WORLD + p) * AR_MAX_ROWS + row) * AR_MAX_ROW_BYTES;
+            Vec16<T> v;
+            *reinterpret_cast<uint4 *>(v.v) = __ldcg(reinterpret_cast<const uint4 *>((const T *)src + i * V));
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] += to_f(v.v[j]);
+        }
+        Vec16<T> r, o;
+        if (residual) r = ld16(residual + (size_t)row * hidden + i * V);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float x = round_t<T>(acc[j]);                          // the AllReduce output, as stored by the separate op
+            if (residual) x = round_t<T>(to_f(r.v[j]) + x);        // Add(residual, allreduce)
+            o.v[j] = from_f<T>(x);
+            ss += x * x;
+        }
+        st16(out + (size_t)row * hidden + i * V, o);
+    }
+    if (norm_w) {
+        // RMSNorm of the row just produced (rms_norm.cu:36-54 semantics: eps 1e-5, round before the weight)
+        const float rinv = rsqrtf(block_sum(ss, red) / (float)hidden + 0.00001f);
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+            const Vec16<T> x = ld16(out + (size_t)row * hidden + i * V), w = ld16(norm_w + i * V);
+            Vec16<T> o;
+#pragma unroll
+            for (int j = 0; j < V; ++j) o.v[j] = from_f<T>(round_t<T>(to_f(x.v[j]) * rinv) * to_f(w.v[j]));
+            st16(out_norm + (size_t)row * hidden + i * V, o);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *epoch_p = e + 1;
+}
+
 }  // namespace itb
 
 using namespace itb;
@@ -161,7 +229,7 @@ extern "C" int64_t it_b200_allreduce_workspace_bytes(void) { return (int64_t)ar_
 
 extern "C" int it_b200_allreduce_fused(int dtype, const void *in, const void *residual, const void *norm_w, void *out,
                                        void *out_norm, int tokens, int hidden, void *const *peer_ws, int world,
-                                       int rank, int *timeout_flag, void *stream) {
+                                       int rank, void *stream) {
     ITB_CHECK(world >= 1 && world <= AR_MAX_WORLD && rank >= 0 && rank < world, "allreduce_fused: bad world/rank %d/%d",
               world, rank);
     ITB_CHECK(tokens >= 0 && tokens <= AR_MAX_ROWS, "allreduce_fused: %d rows > %d", tokens, AR_MAX_ROWS);
@@ -177,11 +245,19 @@ extern "C" int it_b200_allreduce_fused(int dtype, const void *in, const void *re
         ITB_CHECK(peer_ws[p] != nullptr, "allreduce_fused: peer workspace %d not mapped", p);
         peers.ws[p] = peer_ws[p];
     }
+    static const bool fence_proto = [] {
+        const char *e = std::getenv("ITB_AR_PROTO");
+        return e && std::string(e) == "fence";
+    }();
     ITB_DISPATCH_FLOAT(dtype, "allreduce_fused", {
         int threads = std::min(512, std::max(32, ((hidden / Vec16<T>::N + 31) / 32) * 32));
-        cudaError_t e = launch_k(allreduce_ll_kernel<T>, dim3(tokens), dim3(threads), 0, (cudaStream_t)stream, peers, world,
-                                 rank, (const T *)in, (const T *)residual, (const T *)norm_w, (T *)out, (T *)out_norm,
-                                 hidden, timeout_flag);
+        cudaError_t e = fence_proto
+                            ? launch_k(allreduce_fused_kernel<T>, dim3(tokens), dim3(threads), 0, (cudaStream_t)stream, peers,
+                                       world, rank, (const T *)in, (const T *)residual, (const T *)norm_w, (T *)out,
+                                       (T *)out_norm, hidden)
+                            : launch_k(allreduce_ll_kernel<T>, dim3(tokens), dim3(threads), 0, (cudaStream_t)stream, peers, world,
+                                       rank, (const T *)in, (const T *)residual, (const T *)norm_w, (T *)out, (T *)out_norm,
+                                       hidden);
         ITB_CHECK(e == cudaSuccess, "allreduce_fused: launch failed: %s", cudaGetErrorString(e));
     });
     ITB_LAUNCH_CHECK("allreduce_fused");

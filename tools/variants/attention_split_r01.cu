@@ -2,9 +2,7 @@
 //
 // Replaces reference _attention_kvcache_kernel_128_1/_2 (src/kernels/cuda/attention_kvcache.cu:8-169,
 // wrapper attention_kvcache.cc:8-56).  Contract kept from the reference:
-//   * seq_length = position_id[0] + 1 for every batch row (.cu:17) -- unless the caller asks for PER-ROW positions
-//     (ITB_POS_PER_ROW: row b attends to position_id[b] + 1 rows and appends at position_id[b]; SURVEY 8(f-3): ragged
-//     batches cannot be served with the reference's element-0 rule)
+//   * seq_length = position_id[0] + 1 for every batch row (.cu:17)
 //   * k, v are appended IN PLACE into the cache INPUT tensors at position_id[0] (.cu:49-53, 89-93)
 //   * cache layout [B, H, S_max, 128] contiguous; q/k/v/out [B, H, 1, 128]; scale 1/sqrt(128) (.cu:72)
 // Differences by design: numerically stable online softmax instead of the reference's
@@ -32,7 +30,228 @@ template <typename T> struct RowCfg {
     static constexpr int RPW = 32 / LPR;        // rows per warp-load
 };
 
-template <typename P> __device__ __forceinline__ int read_pos(const void *p, int i) { return (int)((const P *)p)[i]; }
+template <typename P> __device__ __forceinline__ int read_pos(const void *p) { return (int)((const P *)p)[0]; }
+
+// partial layout in workspace: [BH, nsplit] x { m, l, acc[128] }
+// rotate-half RoPE of this lane's EPL dims of the q and k rows of one 128-wide head, arithmetic rounded to T exactly
+// like rope_kernel (norm.cu / reference rope.cu:21-29); the partner dims (+-64) live in lane ^ (LPR/2).  cs / sn are
+// the CTA's 64-entry cos / sin tables (already rounded to T) in shared memory.
+template <typename T, int EPL, int LPR>
+__device__ __forceinline__ void rope_rows(Vec16<T> &q, Vec16<T> &k, int col, const float *cs_t, const float *sn_t) {
+    auto exchange = [](const Vec16<T> &x) {
+        Vec16<T> o;
+        uint4 mine = *reinterpret_cast<const uint4 *>(x.v), other;
+        other.x = __shfl_xor_sync(0xffffffffu, mine.x, LPR / 2);
+        other.y = __shfl_xor_sync(0xffffffffu, mine.y, LPR / 2);
+        other.z = __shfl_xor_sync(0xffffffffu, mine.z, LPR / 2);
+        other.w = __shfl_xor_sync(0xffffffffu, mine.w, LPR / 2);
+        *reinterpret_cast<uint4 *>(o.v) = other;
+        return o;
+    };
+    const Vec16<T> qp = exchange(q), kp = exchange(k);
+    const bool lo = col < kD / 2;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+        const int c = (col + j) & (kD / 2 - 1);
+        const float cs = cs_t[c], sn = sn_t[c];
+        const float qa = round_t<T>(to_f(q.v[j]) * cs), qb = round_t<T>(to_f(qp.v[j]) * sn);
+        const float ka = round_t<T>(to_f(k.v[j]) * cs), kb = round_t<T>(to_f(kp.v[j]) * sn);
+        q.v[j] = from_f<T>(lo ? qa - qb : qa + qb);
+        k.v[j] = from_f<T>(lo ? ka - kb : ka + kb);
+    }
+}
+
+// ROPE = true: q and kin are the PRE-RoPE projections; RoPE (position rope_pos[b]) is applied on load, so the two
+// RoPE kernels of the layer disappear (the appended cache row is the rotated k, as in the unfused graph)
+template <typename T, int WARPS, int U, bool ROPE>
+__global__ void __launch_bounds__(WARPS * 32) attn_decode_kernel(T *__restrict__ kcache, T *__restrict__ vcache,
+                                                                 const T *__restrict__ q,
+                                                                 const T *__restrict__ kin,
+                                                                 const T *__restrict__ vin,
+                                                                 const void *__restrict__ position_id,
+                                                                 int pos_dtype, T *__restrict__ out, int Smax,
+                                                                 int nsplit, float *__restrict__ partial,
+                                                                 const void *__restrict__ rope_pos,
+                                                                 int rope_pos_dtype, int H) {
+    pdl_trigger();
+    pdl_wait();
+    using C = RowCfg<T>;
+    constexpr int EPL = C::EPL, LPR = C::LPR, RPW = C::RPW;
+    __shared__ float s_m[WARPS], s_l[WARPS];
+    __shared__ float s_acc[WARPS][kD];
+
+    const int bh = blockIdx.x, split = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane / LPR;         // which of the RPW rows this lane works on
+    const int col = (lane % LPR) * EPL; // first of this lane's EPL dims
+
+    int pos = pos_dtype == ITB_I64 ? read_pos<int64_t>(position_id) : read_pos<int32_t>(position_id);
+    if (pos < 0) pos = 0;
+    if (pos >= Smax) pos = Smax - 1;
+    const int seq = pos + 1;
+
+    // this split's [s_begin, s_end)
+    int chunk = (seq + nsplit - 1) / nsplit;
+    chunk = ((chunk + RPW - 1) / RPW) * RPW;
+    const int s_begin = split * chunk;
+    const int s_end = min(seq, s_begin + chunk);
+
+    T *kc = kcache + (int64_t)bh * Smax * kD;
+    T *vc = vcache + (int64_t)bh * Smax * kD;
+    const T *kn = kin + (int64_t)bh * kD;
+    const T *vn = vin + (int64_t)bh * kD;
+
+    Vec16<T> knew = ld16(kn + col);  // this lane's dims of the new k row
+    Vec16<T> qv = ld16(q + (int64_t)bh * kD + col);
+    if (ROPE) {
+        // 64 threads evaluate one (cos, sin) each -- the serial chain is one powf + sincos, not 8 per lane -- then every
+        // thread rotates its own copy of the q / k dims from the shared tables
+        __shared__ float s_cs[kD / 2], s_sn[kD / 2];
+        if (threadIdx.x < kD / 2) {
+            const int b = bh / H;
+            const float p = rope_pos_dtype == ITB_I64 ? (float)(int)((const int64_t *)rope_pos)[b]
+                                                      : (float)((const int32_t *)rope_pos)[b];
+            const float freq = p * powf(10000.f, -(float)(threadIdx.x * 2) / (float)kD);
+            s_cs[threadIdx.x] = round_t<T>(cosf(freq));
+            s_sn[threadIdx.x] = round_t<T>(sinf(freq));
+        }
+        __syncthreads();
+        rope_rows<T, EPL, LPR>(qv, knew, col, s_cs, s_sn);
+    }
+
+    // in-place append (one warp of the split that owns `pos`)
+    if (pos >= s_begin && pos < s_end && warp == 0 && lane < LPR) {
+        st16(kc + (int64_t)pos * kD + col, knew);
+        st16(vc + (int64_t)pos * kD + col, ld16(vn + col));
+    }
+
+    float qf[EPL];
+    {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) qf[j] = to_f(qv.v[j]) * 0.08838834764831845f;  // 1/sqrt(128)
+    }
+
+    float m = -INFINITY, l = 0.f, acc[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) acc[j] = 0.f;
+
+    // the cache rows [s_begin, min(s_end, pos)) stream from HBM; the appended row `pos` is handled after the loop from
+    // registers (keeps every hot-loop load a plain independent global load -- a post-load select costs the MLP).
+    const int s_stop = min(s_end, pos);
+    // warp w takes row groups w, w+WARPS, ... ; each group = RPW*U rows
+    for (int s0 = s_begin + warp * RPW * U; s0 < s_stop; s0 += WARPS * RPW * U) {
+        Vec16<T> kv[U], vv[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            int s = s0 + u * RPW + sub;
+            ok[u] = s < s_stop;
+            if (ok[u]) {
+                kv[u] = ld16_stream(kc + (int64_t)s * kD + col);
+                vv[u] = ld16_stream(vc + (int64_t)s * kD + col);
+            }
+        }
+        float sc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float d = 0.f;
+            if (ok[u]) {
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) d += qf[j] * to_f(kv[u].v[j]);
+            }
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            sc[u] = ok[u] ? d : -INFINITY;
+        }
+        float mx = m;
+#pragma unroll
+        for (int u = 0; u < U; ++u) mx = fmaxf(mx, sc[u]);
+        if (mx > -INFINITY) {
+            float corr = expf(m - mx);  // m = -inf -> 0
+            l *= corr;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) acc[j] *= corr;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (ok[u]) {
+                    float p = expf(sc[u] - mx);
+                    l += p;
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) acc[j] = fmaf(p, to_f(vv[u].v[j]), acc[j]);
+                }
+            }
+            m = mx;
+        }
+    }
+
+    // the appended row (k / v of this step), from registers: warp 0, sub-row 0 of the split that owns `pos`
+    if (warp == 0 && pos >= s_begin && pos < s_end) {
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) d += qf[j] * to_f(knew.v[j]);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (sub == 0) {
+            const Vec16<T> vnew = ld16(vn + col);
+            const float mx = fmaxf(m, d);
+            const float corr = expf(m - mx), pnew = expf(d - mx);
+            l = l * corr + pnew;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) acc[j] = fmaf(pnew, to_f(vnew.v[j]), acc[j] * corr);
+            m = mx;
+        }
+    }
+
+    // merge the RPW sub-rows inside the warp (lanes with equal col, different sub)
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+        float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        float l2 = __shfl_xor_sync(0xffffffffu, l, o);
+        float mx = fmaxf(m, m2);
+        float c1 = mx > -INFINITY ? expf(m - mx) : 0.f, c2 = mx > -INFINITY ? expf(m2 - mx) : 0.f;
+        l = l * c1 + l2 * c2;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            float a2 = __shfl_xor_sync(0xffffffffu, acc[j], o);
+            acc[j] = acc[j] * c1 + a2 * c2;
+        }
+        m = mx;
+    }
+    // merge warps through shared memory
+    if (sub == 0) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) s_acc[warp][col + j] = acc[j];
+        if (lane == 0) {
+            s_m[warp] = m;
+            s_l[warp] = l;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kD) {
+        int d = threadIdx.x;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) mx = fmaxf(mx, s_m[w]);
+        float L = 0.f, A = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            float c = s_m[w] > -INFINITY ? expf(s_m[w] - mx) : 0.f;
+            L += s_l[w] * c;
+            A += s_acc[w][d] * c;
+        }
+        if (nsplit == 1) {
+            out[(int64_t)bh * kD + d] = from_f<T>(A / L);
+        } else {
+            float *pp = partial + ((int64_t)bh * nsplit + split) * (kD + 2);
+            pp[2 + d] = A;
+            if (d == 0) {
+                pp[0] = mx;
+                pp[1] = L;
+            }
+        }
+    }
+}
+
 
 // ------------------------------------------------------------------------------------------------------------------
 // attn_stream_kernel: the production decode kernel.  Same arithmetic per cache row as attn_decode_kernel, but
@@ -80,13 +299,11 @@ __device__ __forceinline__ void rope_one(Vec16<T> &x, int col, const float *cs_t
     }
 }
 
-constexpr int AS_MAX_B = 1024;  // batch rows whose (position, chunk count) the CTA keeps in shared memory
-
 template <typename T, int WARPS, int U, bool ROPE>
 __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
     attn_stream_kernel(T *__restrict__ kcache, T *__restrict__ vcache, const T *__restrict__ q,
                        const T *__restrict__ kin, const T *__restrict__ vin, const void *__restrict__ position_id,
-                       int pos_flags, T *__restrict__ out, int Smax, int BH, float *__restrict__ partial,
+                       int pos_dtype, T *__restrict__ out, int Smax, int BH, float *__restrict__ partial,
                        int slots_per_head, int *__restrict__ tickets, const void *__restrict__ rope_pos,
                        int rope_pos_dtype, int H, int stages) {
     using C = RowCfg<T>;
@@ -100,18 +317,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
     __shared__ float s_acc[WARPS][kD];
     __shared__ float s_cs[kD / 2], s_sn[kD / 2];
     __shared__ int s_last;
-    __shared__ int s_pos[AS_MAX_B];       // clamped position of batch row b
-    __shared__ int s_pre[AS_MAX_B + 1];   // (head, chunk) units before batch row b; s_pre[B] = total
 
     pdl_trigger();
-    const int pos_dtype = pos_flags & 0xff;
-    const bool per_row = (pos_flags & ITB_POS_PER_ROW) != 0;
-    // ITB_POS_IN_STEP: the position tensor / RoPE positions / cache rows below the position may have been written by a
-    // kernel of THIS step (an ONNX graph that computes position_ids or concatenates the past in-graph): nothing is read
-    // ahead of griddepcontrol.wait.  Otherwise they are a whole step old (graph inputs, the previous step's appends) and
-    // the producer starts streaming while the previous kernel of the chain drains.
-    if (pos_flags & ITB_POS_IN_STEP) pdl_wait();
-    const int Bn = BH / H;
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
@@ -119,53 +326,28 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
         }
         fence_mbar_init();
     }
-    for (int b = threadIdx.x; b < Bn; b += blockDim.x) {
-        int p = pos_dtype == ITB_I64 ? read_pos<int64_t>(position_id, per_row ? b : 0)
-                                     : read_pos<int32_t>(position_id, per_row ? b : 0);
-        s_pos[b] = min(max(p, 0), Smax - 1);
-    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int b = 0; b < Bn; ++b) {
-            s_pre[b] = acc;
-            acc += H * (s_pos[b] / CH + 1);  // chunks per head of row b; the last one holds rows [.., pos) + the appended row
-        }
-        s_pre[Bn] = acc;
-    }
-    __syncthreads();
-    // Everything this step produced (q, k, v) is read by the consumers, after their wait; this kernel's own append
-    // touches row `pos` only, which the bulk loads never include.
+    // No griddepcontrol.wait yet: the position input and the cache rows BELOW `pos` were written by earlier steps (the
+    // append of row pos-1 is a whole step of launches upstream), so the producer starts streaming while the previous
+    // kernel of the chain drains.  Everything this step produced (q, k, v, RoPE positions) is read by the consumers,
+    // after their wait; this kernel's own append touches row `pos` only, which the bulk loads never include.
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t total = s_pre[Bn], G = min((int64_t)gridDim.x, total);
-    // this CTA's contiguous range of (head, chunk) units: [u0, u0 + nunits), starting at (bh, c) inside batch row b.
-    // G = CTAs that take part: never more than there are units, so every one owns >= 1 unit and the CTAs sharing a head
-    // are consecutive
-    if (blockIdx.x >= G) return;
-    int nunits, bh, c, brow, pos, nch;
+    int pos = pos_dtype == ITB_I64 ? read_pos<int64_t>(position_id) : read_pos<int32_t>(position_id);
+    if (pos < 0) pos = 0;
+    if (pos >= Smax) pos = Smax - 1;
+    const int nch = pos / CH + 1;  // chunks per head; the last one holds rows [.., pos) of the cache + the appended row
+    int nunits, bh, c;  // this CTA's contiguous range of (head, chunk) units: [u0, u0 + nunits), starting at (bh, c)
     {
+        // G = CTAs that take part: never more than there are units, so every one owns >= 1 unit and the CTAs sharing a
+        // head are consecutive
+        const int64_t total = (int64_t)BH * nch, G = min((int64_t)gridDim.x, total);
+        if (blockIdx.x >= G) return;
         const int64_t u0 = blockIdx.x * total / G, u1 = (blockIdx.x + 1) * total / G;
         nunits = (int)(u1 - u0);
-        brow = 0;
-        while (brow + 1 < Bn && s_pre[brow + 1] <= u0) ++brow;
-        pos = s_pos[brow];
-        nch = pos / CH + 1;
-        const int r = (int)(u0 - s_pre[brow]);
-        bh = brow * H + r / nch;
-        c = r % nch;
+        bh = (int)(u0 / nch);
+        c = (int)(u0 - (int64_t)bh * nch);
     }
-    auto next_unit = [&]() {  // (bh, c) -> the next unit; entering a new batch row refreshes its position
-        if (++c == nch) {
-            c = 0;
-            ++bh;
-            if (bh % H == 0 && bh < BH) {
-                brow = bh / H;
-                pos = s_pos[brow];
-                nch = pos / CH + 1;
-            }
-        }
-    };
 
     if (warp == WARPS) {
         // ---------------- producer: one elected lane streams chunks into the ring ----------------
@@ -184,7 +366,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
                 } else {
                     mbar_arrive(&full[st]);
                 }
-                next_unit();
+                if (++c == nch) { c = 0; ++bh; }
                 if (++st == stages) { st = 0; ph ^= 1; }
             }
         }
@@ -207,7 +389,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
         table_b = b;
     };
     if (ROPE) rope_table(bh / H);
-    pdl_wait();  // (a no-op the second time under ITB_POS_IN_STEP)
+    pdl_wait();
     const int sub = lane / LPR;
     const int col = (lane % LPR) * EPL;
     float qf[EPL], m = -INFINITY, l = 0.f, acc[EPL];
@@ -359,7 +541,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
             named_bar_sync(1, CONSUMERS);
             const bool whole = seg_from_start && last_chunk;
             // which CTAs share this head:  cta(u) = floor(((u + 1) G - 1) / total)
-            const int64_t hu0 = (int64_t)s_pre[brow] + (int64_t)(bh - brow * H) * nch;  // first unit of this head
+            const int64_t hu0 = (int64_t)bh * nch, total = (int64_t)BH * nch, G = min((int64_t)gridDim.x, total);
             const int first_cta = (int)(((hu0 + 1) * G - 1) / total);
             const int last_cta = (int)(((hu0 + nch) * G - 1) / total);
             const int nseg = last_cta - first_cta + 1;
@@ -414,8 +596,35 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
             }
             named_bar_sync(1, CONSUMERS);  // s_acc / s_m / s_last are reused by the next segment
         }
-        next_unit();
+        if (++c == nch) { c = 0; ++bh; }
     }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kD) attn_merge_kernel(const float *__restrict__ partial, T *__restrict__ out,
+                                                        int nsplit) {
+    pdl_trigger();
+    pdl_wait();
+    int bh = blockIdx.x, d = threadIdx.x;
+    const float *pp = partial + (int64_t)bh * nsplit * (kD + 2);
+    float mx = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) mx = fmaxf(mx, pp[s * (kD + 2)]);
+    float L = 0.f, A = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+        float ms = pp[s * (kD + 2)];
+        float c = ms > -INFINITY ? expf(ms - mx) : 0.f;
+        L += pp[s * (kD + 2) + 1] * c;
+        A += pp[s * (kD + 2) + 2 + d] * c;
+    }
+    out[(int64_t)bh * kD + d] = from_f<T>(A / L);
+}
+
+static int choose_nsplit(int BH, int Smax) {
+    // enough CTAs for >= 2 per SM; never split below 64 positions per CTA
+    int want = (2 * kNumSMs + BH - 1) / BH;
+    int cap = Smax / 64 > 0 ? Smax / 64 : 1;
+    int n = want < cap ? want : cap;
+    return n < 1 ? 1 : n;
 }
 
 }  // namespace itb
@@ -426,15 +635,26 @@ static int env_int(const char *name, int dflt) {
     const char *e = std::getenv(name);
     return e && *e ? std::atoi(e) : dflt;
 }
+// ITB_ATTN_IMPL=split selects the one-CTA-per-(head, split) kernel; default is the streaming kernel
+static bool attn_use_split() {
+    static const bool v = [] {
+        const char *e = std::getenv("ITB_ATTN_IMPL");
+        return e && std::string(e) == "split";
+    }();
+    return v;
+}
 static int stream_slots_per_head(int S_max) { return S_max / 32 + 1; }  // >= chunks per head for every dtype
 
 extern "C" int64_t it_b200_attention_kvcache_workspace(int B, int H, int S_max, int D) {
     (void)D;
-    return (int64_t)B * H * stream_slots_per_head(S_max) * (kD + 2) * sizeof(float);
+    int ns = choose_nsplit(B * H, S_max);
+    int64_t split = ns == 1 ? 0 : (int64_t)B * H * ns * (kD + 2) * sizeof(float);
+    int64_t stream = (int64_t)B * H * stream_slots_per_head(S_max) * (kD + 2) * sizeof(float);
+    return split > stream ? split : stream;
 }
 
 template <typename T, bool ROPE, int WARPS, int U>
-static int launch_attn_stream_cfg(T *kc, T *vc, const T *q, const T *k, const T *v, const void *position_id, int pos_flags,
+static int launch_attn_stream_cfg(T *kc, T *vc, const T *q, const T *k, const T *v, const void *position_id, int pos_dtype,
                               const void *rope_pos, int rope_pos_dtype, T *out, int BH, int H, int S_max,
                               float *workspace, cudaStream_t st) {
     constexpr int CH = WARPS * RowCfg<T>::RPW * U;
@@ -442,13 +662,16 @@ static int launch_attn_stream_cfg(T *kc, T *vc, const T *q, const T *k, const T 
     static const int per_sm = std::max(1, std::min(2, env_int("ITB_ATTN_CTAS_PER_SM", 2)));
     const size_t smem = (size_t)stages * 2 * CH * kD * sizeof(T);
     auto kern = attn_stream_kernel<T, WARPS, U, ROPE>;
-    // the attribute is per DEVICE: a process may own runtimes on several GPUs
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+        configured = true;
+    }
     int *tickets = stream_tickets(st, BH);
     if (!tickets) return 1;
     const int64_t max_units = (int64_t)BH * (S_max / CH + 1);
     const int grid = (int)std::min<int64_t>(max_units, (int64_t)per_sm * kNumSMs);
-    cudaError_t e = launch_k(kern, dim3(grid), dim3((WARPS + 1) * 32), smem, st, kc, vc, q, k, v, position_id, pos_flags,
+    cudaError_t e = launch_k(kern, dim3(grid), dim3((WARPS + 1) * 32), smem, st, kc, vc, q, k, v, position_id, pos_dtype,
                              out, S_max, BH, workspace, stream_slots_per_head(S_max), tickets, rope_pos, rope_pos_dtype,
                              H, stages);
     return e == cudaSuccess ? 0 : 1;
@@ -460,9 +683,8 @@ template <typename T, bool ROPE, typename... A> static int launch_attn_stream(A.
 }
 
 static int attention_impl(int dtype, void *k_cache, void *v_cache, const void *q, const void *k, const void *v,
-                          const void *position_id, int pos_flags, const void *rope_pos, int rope_pos_dtype, void *out,
+                          const void *position_id, int pos_dtype, const void *rope_pos, int rope_pos_dtype, void *out,
                           int B, int H, int S_max, int D, void *workspace, int64_t workspace_bytes, void *stream) {
-    const int pos_dtype = pos_flags & 0xff;
     ITB_CHECK(D == kD, "AttentionKVCache: head dim %d != 128 (reference attention_kvcache.cu:154)", D);
     ITB_CHECK(pos_dtype == ITB_I32 || pos_dtype == ITB_U32 || pos_dtype == ITB_I64,
               "AttentionKVCache: position dtype %d must be int32/uint32/int64", pos_dtype);
@@ -470,24 +692,45 @@ static int attention_impl(int dtype, void *k_cache, void *v_cache, const void *q
               "AttentionKVCache: rope position dtype %d must be int32/uint32/int64", rope_pos_dtype);
     ITB_CHECK(aligned16(k_cache) && aligned16(v_cache) && aligned16(q) && aligned16(k) && aligned16(v),
               "AttentionKVCache: tensors must be 16-byte aligned");
-    const int BH = B * H;
+    int BH = B * H;
     if (BH == 0) return 0;
-    ITB_CHECK(B <= AS_MAX_B && BH <= 65536, "AttentionKVCache: batch %d x heads %d beyond the kernel's limits (%d rows, 65536 heads)",
-              B, H, AS_MAX_B);
-    const int64_t need = it_b200_attention_kvcache_workspace(B, H, S_max, D);
-    ITB_CHECK(workspace && workspace_bytes >= need, "AttentionKVCache: workspace %lld < %lld bytes",
+    int ns = choose_nsplit(BH, S_max);
+    int64_t need = it_b200_attention_kvcache_workspace(B, H, S_max, D);
+    ITB_CHECK(ns == 1 || (workspace && workspace_bytes >= need), "AttentionKVCache: workspace %lld < %lld bytes",
               (long long)workspace_bytes, (long long)need);
     auto st = (cudaStream_t)stream;
+    if (!attn_use_split() && BH <= 65536) {
+        ITB_CHECK(workspace && workspace_bytes >= need, "AttentionKVCache: workspace %lld < %lld bytes",
+                  (long long)workspace_bytes, (long long)need);
+        ITB_DISPATCH_FLOAT(dtype, "AttentionKVCache", {
+            int rc = rope_pos ? launch_attn_stream<T, true>((T *)k_cache, (T *)v_cache, (const T *)q, (const T *)k,
+                                                            (const T *)v, position_id, pos_dtype, rope_pos,
+                                                            rope_pos_dtype, (T *)out, BH, H, S_max, (float *)workspace, st)
+                              : launch_attn_stream<T, false>((T *)k_cache, (T *)v_cache, (const T *)q, (const T *)k,
+                                                             (const T *)v, position_id, pos_dtype, nullptr, 0, (T *)out,
+                                                             BH, H, S_max, (float *)workspace, st);
+            ITB_CHECK(rc == 0, "AttentionKVCache: streaming kernel launch failed: %s",
+                      cudaGetErrorString(cudaGetLastError()));
+            ITB_LAUNCH_CHECK("AttentionKVCache");
+        });
+        return 0;
+    }
+    dim3 grid(BH, ns);
     ITB_DISPATCH_FLOAT(dtype, "AttentionKVCache", {
-        int rc = rope_pos ? launch_attn_stream<T, true>((T *)k_cache, (T *)v_cache, (const T *)q, (const T *)k,
-                                                        (const T *)v, position_id, pos_flags, rope_pos,
-                                                        rope_pos_dtype, (T *)out, BH, H, S_max, (float *)workspace, st)
-                          : launch_attn_stream<T, false>((T *)k_cache, (T *)v_cache, (const T *)q, (const T *)k,
-                                                         (const T *)v, position_id, pos_flags, nullptr, 0, (T *)out,
-                                                         BH, H, S_max, (float *)workspace, st);
-        ITB_CHECK(rc == 0, "AttentionKVCache: streaming kernel launch failed: %s",
-                  cudaGetErrorString(cudaGetLastError()));
+        constexpr int WARPS = 8, U = 4;  // measured: U=2 at 64 regs (4 CTAs/SM) is 11 % slower end-to-end -- per-thread MLP wins
+        if (rope_pos)
+            launch_k(attn_decode_kernel<T, WARPS, U, true>, dim3(grid), dim3(WARPS * 32), 0, st, (T *)k_cache, (T *)v_cache,
+                     (const T *)q, (const T *)k, (const T *)v, position_id, pos_dtype, (T *)out, S_max, ns,
+                     (float *)workspace, rope_pos, rope_pos_dtype, H);
+        else
+            launch_k(attn_decode_kernel<T, WARPS, U, false>, dim3(grid), dim3(WARPS * 32), 0, st, (T *)k_cache, (T *)v_cache,
+                     (const T *)q, (const T *)k, (const T *)v, position_id, pos_dtype, (T *)out, S_max, ns,
+                     (float *)workspace, rope_pos, rope_pos_dtype, H);
         ITB_LAUNCH_CHECK("AttentionKVCache");
+        if (ns > 1) {
+            launch_k(attn_merge_kernel<T>, dim3(BH), dim3(kD), 0, st, (const float *)workspace, (T *)out, ns);
+            ITB_LAUNCH_CHECK("AttentionKVCache.merge");
+        }
     });
     return 0;
 }
