@@ -47,17 +47,6 @@ template <typename P> __device__ __forceinline__ int read_pos(const void *p, int
 // The in-place append and the appended row's contribution are done by the CTA that owns the head's last chunk, from
 // registers; chunk loads stop at row pos-1, so the append never races the bulk reads.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar,
-                                             uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-        : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
 constexpr int AS_MAX_STAGES = 6;
 
 template <typename T, int EPL, int LPR>

@@ -33,65 +33,6 @@ constexpr int TC_W_BYTES = TC_BN * TC_BK * 2;  // 16 KB: two [64k x 64n] swizzle
 constexpr int TC_EPI_WARPS = 8;                      // two warps per TMEM lane quadrant, each takes half of the accumulator columns
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;  // + TMA producer warp + MMA issuer warp
 
-// ---- tcgen05 PTX wrappers -------------------------------------------------------------------
-__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
-                 "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, fp32 accumulate
-__host__ __device__ inline uint32_t umma_idesc_f16(int is_bf16, int a_mn_major, int b_mn_major, int M, int N) {
-    uint32_t d = 0;
-    d |= 1u << 4;                               // c_format = F32
-    d |= (uint32_t)(is_bf16 ? 1 : 0) << 7;      // a_format
-    d |= (uint32_t)(is_bf16 ? 1 : 0) << 10;     // b_format
-    d |= (uint32_t)(a_mn_major ? 1 : 0) << 15;  // a_major
-    d |= (uint32_t)(b_mn_major ? 1 : 0) << 16;  // b_major
-    d |= (uint32_t)(N >> 3) << 17;              // n_dim
-    d |= (uint32_t)(M >> 4) << 24;              // m_dim
-    return d;
-}
-
 #ifdef ITB_TC_TRACE
 __device__ unsigned long long g_tc_trace[16];
 #define TC_MARK(i)                                                                         \
