@@ -177,58 +177,66 @@ void CudaRuntimeObj::runWithoutSyncImpl(const Graph &graph, bool validate) const
     }();
     for (size_t i = 0; i < sched.size(); ++i) {
         const auto &st = sched[i];
-        const auto &op = st.ops.back();
         struct Range {
             bool on;
             Range(bool enable, const ExecStep &s) : on(enable) {
                 if (!on) return;
                 string name;
-                for (auto &m : s.ops) name += (name.empty() ? "" : "+") + string(m->getOpType().toString());
+                if (s.kind == ExecStep::DecoderStack) name = "DecoderStack";
+                else
+                    for (auto &m : s.ops) name += (name.empty() ? "" : "+") + string(m->getOpType().toString());
                 nvtxRangePushA(name.c_str());
             }
             ~Range() {
                 if (on) nvtxRangePop();
             }
         } range(nvtx, st);
-        switch (st.kind) {
-        case ExecStep::Alias:
-            // the planner made the output share the input's storage: nothing to launch
-            if (op->getInputs(0)->rawPtrOrNull() == op->getOutput()->rawPtrOrNull()) break;
-            [[fallthrough]];  // distinct storage (naive allocator): the ordinary copy kernel
-        case ExecStep::Single:
-            if (plan[i].record)
-                plan[i].kernel->compute(op, *plan[i].record, this);
-            else
-                plan[i].kernel->compute(op, this);
-            break;
-        case ExecStep::MatMulGroup: b200::runMatmulGroup(st.ops, this); break;
-        case ExecStep::MatMulAdd: {
-            const auto &mm = st.ops[0], &add = st.ops[1];
-            auto res = add->getInputs(0) == mm->getOutput() ? add->getInputs(1) : add->getInputs(0);
-            b200::runMatmul(mm, this, res, add->getOutput());
-            break;
-        }
-        case ExecStep::SiluMul: b200::runSiluMul(st.ops[0], st.ops[1], this); break;
-        case ExecStep::AttentionRope: b200::runAttentionRope(st.ops[0], st.ops[1], st.ops[2], this); break;
-        case ExecStep::ConvBnAct:
-            if (!b200::runConvBnAct(st.ops, this)) {
-                auto &reg = KernelRegistry::getInstance();
-                for (auto &m : st.ops) reg.getKernel(KernelAttrs{Device::CUDA, m->getOpType().underlying()})->compute(m, this);
-            }
-            break;
-        case ExecStep::AllReduceAddNorm:
-            if (!b200::runAllReduceAddNorm(st.ops, this)) {
-                // no NVLink peer comm (or shape outside its limits): the ordinary kernels, one by one
-                auto &reg = KernelRegistry::getInstance();
-                for (auto &m : st.ops) reg.getKernel(KernelAttrs{Device::CUDA, m->getOpType().underlying()})->compute(m, this);
-            }
-            break;
-        }
+        execStep(st, plan[i].kernel, plan[i].record ? &*plan[i].record : nullptr);
         cudaError_t err = cudaPeekAtLastError();
         if (err != cudaSuccess) {
             cudaGetLastError();
-            throw Exception(string("CUDA error: ") + cudaGetErrorString(err) + " in " + op->toString());
+            throw Exception(string("CUDA error: ") + cudaGetErrorString(err) + " in " + st.ops.back()->toString());
         }
+    }
+}
+
+// one schedule step; `kernel` / `record` = the resolved kernel of the step's last operator (nullptr: look it up)
+void CudaRuntimeObj::execStep(const ExecStep &st, Kernel *kernel, const PerfRecord *record) const {
+    const auto &op = st.ops.back();
+    auto &reg = KernelRegistry::getInstance();
+    auto single = [&](const Operator &o) {
+        Kernel *k = (kernel && o == op) ? kernel : reg.getKernel(KernelAttrs{Device::CUDA, o->getOpType().underlying()});
+        if (record && o == op) k->compute(o, *record, this);
+        else k->compute(o, this);
+    };
+    switch (st.kind) {
+    case ExecStep::Alias:
+        // the planner made the output share the input's storage: nothing to launch
+        if (op->getInputs(0)->rawPtrOrNull() == op->getOutput()->rawPtrOrNull()) break;
+        [[fallthrough]];  // distinct storage (naive allocator): the ordinary copy kernel
+    case ExecStep::Single: single(op); break;
+    case ExecStep::MatMulGroup: b200::runMatmulGroup(st.ops, this); break;
+    case ExecStep::MatMulAdd: {
+        const auto &mm = st.ops[0], &add = st.ops[1];
+        auto res = add->getInputs(0) == mm->getOutput() ? add->getInputs(1) : add->getInputs(0);
+        b200::runMatmul(mm, this, res, add->getOutput());
+        break;
+    }
+    case ExecStep::SiluMul: b200::runSiluMul(st.ops[0], st.ops[1], this); break;
+    case ExecStep::AttentionRope: b200::runAttentionRope(st.ops[0], st.ops[1], st.ops[2], this); break;
+    case ExecStep::ConvBnAct:
+        if (!b200::runConvBnAct(st.ops, this))
+            for (auto &m : st.ops) reg.getKernel(KernelAttrs{Device::CUDA, m->getOpType().underlying()})->compute(m, this);
+        break;
+    case ExecStep::AllReduceAddNorm:
+        if (!b200::runAllReduceAddNorm(st.ops, this))
+            // no NVLink peer comm (or shape outside its limits): the ordinary kernels, one by one
+            for (auto &m : st.ops) reg.getKernel(KernelAttrs{Device::CUDA, m->getOpType().underlying()})->compute(m, this);
+        break;
+    case ExecStep::DecoderStack:
+        if (!b200::runDecoderStack(st, this))
+            for (auto &sb : st.sub) execStep(sb, nullptr, nullptr);
+        break;
     }
 }
 

@@ -91,6 +91,7 @@ class CudaRuntimeObj : public RuntimeObj {
     mutable vector<PlanEntry> plan;
 
     void runWithoutSyncImpl(const Graph &graph, bool validate) const;
+    void execStep(const ExecStep &st, Kernel *kernel, const PerfRecord *record) const;
     vector<TensorSig> signature(const Graph &graph) const;
     void destroyEntry(CacheEntry &e) const;
     void recoverStream() const;
@@ -152,6 +153,8 @@ bool runAllReduceAddNorm(const OpVec &ops, const RuntimeObj *ctx);
 // Conv -> BatchNorm -> [Add] -> [Relu] in the GEMM epilogue; false = shape not taken (nothing launched)
 bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx);
 void runAttentionRope(const Operator &ropeQ, const Operator &ropeK, const Operator &att, const RuntimeObj *ctx);
+// L decoder layers through the persistent kernel; false = not taken (nothing launched): run `st.sub` step by step
+bool runDecoderStack(const ExecStep &st, const RuntimeObj *ctx);
 }  // namespace b200
 
 // Convenience base for kernels without tunable configs (reference cuda_kernel_wihtout_config.h:7-22)

@@ -510,12 +510,17 @@ void GraphObj::dataMalloc(bool useNaiveAllocator, size_t memPoolSize) {
             t = it->second;
         }
     };
-    if (!useNaiveAllocator)
-        for (auto &st : sched)
-            if (st.kind == ExecStep::Alias) {
-                auto in = st.ops[0]->getInputs(0), out = st.ops[0]->getOutput();
-                if (!in->isWeight() && !out->isWeight()) parent[out.get()] = in.get();
-            }
+    if (!useNaiveAllocator) {
+        auto aliasOf = [&](const ExecStep &st) {
+            if (st.kind != ExecStep::Alias) return;
+            auto in = st.ops[0]->getInputs(0), out = st.ops[0]->getOutput();
+            if (!in->isWeight() && !out->isWeight()) parent[out.get()] = in.get();
+        };
+        for (auto &st : sched) {
+            aliasOf(st);
+            for (auto &sb : st.sub) aliasOf(sb);  // aliases inside a DecoderStack step
+        }
+    }
     std::unordered_map<TensorObj *, int> refs;
     std::unordered_set<TensorObj *> pinnedRoots;
     auto pinned = [&](const Tensor &t) { return !t->getSource() || !t->hasTarget() || t->isOutput() || t->isInput(); };

@@ -359,10 +359,14 @@ struct ExecStep {
         SiluMul,      // Silu -> Mul: one pass
         AttentionRope,    // RoPE(q), RoPE(k) -> [aliases] -> AttentionKVCache: RoPE applied inside the attention kernel
         AllReduceAddNorm, // AllReduceSum -> Add(residual) [-> RMSNorm]: one NVLink peer-memory kernel (else 3 ops)
-        ConvBnAct         // Conv -> BatchNorm -> [Add(residual)] -> [Relu]: the tail runs in the tensor-core GEMM epilogue
+        ConvBnAct,        // Conv -> BatchNorm -> [Add(residual)] -> [Relu]: the tail runs in the tensor-core GEMM epilogue
                           // (bit-identical to the separate kernels); shapes the GEMM does not take run one by one
+        DecoderStack      // L consecutive Llama decoder layers (decode, <= 16 rows): ONE launch of the persistent kernel
+                          // (kernels/decode_stack.cu).  `sub` keeps the steps it replaces (8 launches + aliases per layer, in
+                          // order): executed one by one when the kernel does not take the shapes / storage
     } kind = Single;
     OpVec ops;
+    vector<ExecStep> sub;
 };
 
 // ---------------------------------------------------------------- Graph
