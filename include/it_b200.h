@@ -262,6 +262,9 @@ int it_b200_llama_decode_stack(int dtype, int n_layers, const itb_llama_layer *l
 /* stall diagnostics of the persistent kernel: returns a HOST pointer to 148 x 16 x 4 words that its wait sites report into
  * when a wait exceeds its budget (readable even after a trap killed the context); see tools/ds_debug.py */
 void *it_b200_decode_stack_debug(void);
+/* phase timeline of the persistent kernel: device buffer of >= 148 * n_phases * 2 uint64 (globaltimer at phase start /
+ * this CTA's barrier arrival), NULL switches it off; see tools/ds_trace.py */
+void it_b200_decode_stack_trace(void *dev_buf);
 int it_b200_decode_gemm_chain(int dtype, int rows, int n_phases, const int *ngroups, const void *const *W,
                               void *const *out, const int *n_per_group, const int *K, const int *xform,
                               const int *epi, const void *const *X, const void *const *X2,

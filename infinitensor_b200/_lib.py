@@ -71,6 +71,7 @@ _SIGS = {
                                           vp, c_int64, vp]),
     "it_b200_decode_stack_workspace": (c_int64, [c_int] * 6),
     "it_b200_decode_stack_debug": (vp, []),
+    "it_b200_decode_stack_trace": (None, [vp]),
     "it_b200_llama_decode_stack": (c_int, [c_int, c_int, vp, vp, vp, c_int, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp,
                                            c_int64, vp]),
     "it_b200_decode_gemm_chain": (c_int, [c_int, c_int, c_int, i32p, POINTER(vp), POINTER(vp), i32p, i32p, i32p, i32p,

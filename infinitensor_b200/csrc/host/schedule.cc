@@ -17,7 +17,11 @@ static bool fusionEnabled() {
 // ITB_FUSION_MASK (debug / A-B): bit 0 alias, 1 MatMul groups, 2 MatMul+Add, 3 Silu*Mul, 4 AllReduce+Add+Norm, 5 RoPE->Attention, 6 Conv+BatchNorm[+Add][+Relu], 7 decoder-layer stacks (persistent kernel); default all
 static int fusionMask() {
     const char *e = std::getenv("ITB_FUSION_MASK");
-    return e && e[0] ? std::atoi(e) : 255;
+    if (e && e[0]) return std::atoi(e);
+    // bit 7 (decoder-layer stacks on the persistent kernel) is opt-in: measured on the BASELINE shape it does not yet beat the
+    // eight tuned launches it replaces (165 vs 112 us per layer) -- ITB_DECODE_STACK=1 switches it on
+    const char *ds = std::getenv("ITB_DECODE_STACK");
+    return (ds && ds[0] == '1') ? 255 : 127;
 }
 
 static bool isKvCacheOperand(const Tensor &t) {

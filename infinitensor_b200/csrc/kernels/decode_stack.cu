@@ -51,11 +51,22 @@ constexpr int DS_KD = 128;                              // head dim (reference a
 constexpr int DS_CH = 64;                               // cache rows per chunk
 constexpr int DS_MAX_B = 64;                            // batch rows the attention bookkeeping holds
 constexpr int DS_CONS_WARPS = 8;
+constexpr int DS_NORMW_MAX = 4096;
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ds_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // 16-byte load that bypasses L1: everything an earlier PHASE of the same launch wrote (other SMs, same addresses re-used
@@ -90,12 +101,15 @@ __device__ __forceinline__ void grid_arrive(unsigned *bar, unsigned nctas) {
 }
 __device__ __forceinline__ void ds_report(int site, int phase, unsigned gc, unsigned extra);
 __device__ __forceinline__ void grid_wait(const unsigned *bar, unsigned gen0, unsigned target, int phase) {
+    // polled with RELAXED loads (an acquire load drags a whole-L1 invalidation, CCTL.IVALL, through the SM on every probe);
+    // one acquire fence once the generation has been seen
     unsigned spins = 0;
-    while ((unsigned)(ld_acquire_u32(bar + 1) - gen0) < target) {
+    while ((unsigned)(ld_relaxed_u32(bar + 1) - gen0) < target) {
         ++spins;
         if (spins == (1u << 18)) ds_report(3 /*DSW_X_GRID*/, phase, ld_acquire_u32(bar), ld_acquire_u32(bar + 1) - gen0);
         if (spins > (1u << 24)) __trap();  // a protocol bug must trap, not hang the box
     }
+    __threadfence();
     fence_proxy_async_all();
 }
 
@@ -144,12 +158,30 @@ __device__ __forceinline__ void ds_mark(int role, int phase) {
         r[1] = (unsigned)phase;
     }
 }
-__device__ __forceinline__ void ds_mbar_wait(uint64_t *bar, uint32_t parity, int site, int phase, unsigned gc) {
+__device__ __forceinline__ void ds_mbar_wait(uint64_t *bar, uint32_t parity, int site, int phase, unsigned gc, long long &waited) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         ++spins;
         if (spins == (1u << 20)) ds_report(site, phase, gc, parity);
         if (spins > (1u << 25)) __trap();
+    }
+    waited += clock64() - t0;
+}
+// chunk probe (tools/ds_trace.py): CTA 0, phase 5 (= second layer's q/k/v GEMM), first 64 chunks: globaltimer at
+//   0 W producer starts waiting for the stage   1 weight TMA issued   2 stage full (transform warp)   3 transform done
+//   4 MMA thread saw `ready`   5 MMAs + commit issued   6 activation TMA issued
+__device__ __forceinline__ void ds_probe(unsigned long long *trace, int nph, int p, int64_t i, int k) {
+    if (trace && blockIdx.x == 0 && p == 5 && i < 64)
+        trace[(size_t)gridDim.x * nph * 2 + (size_t)gridDim.x * 16 + (size_t)i * 8 + k] = ds_now();
+}
+// per-role accounting (tools/ds_trace.py): cycles spent blocked on an mbarrier vs. the role's whole life
+__device__ __forceinline__ void ds_role_stats(unsigned long long *trace, int nph, int role, long long waited, long long t_begin) {
+    if (trace) {
+        unsigned long long *r = trace + (size_t)gridDim.x * nph * 2 + ((size_t)blockIdx.x * 8 + role) * 2;
+        r[0] = (unsigned long long)waited;
+        r[1] = (unsigned long long)(clock64() - t_begin);
     }
 }
 
@@ -161,6 +193,7 @@ struct DsShared {
     volatile unsigned w_issued;    // ring stages the weight producer has claimed so far (global stage counter)
     unsigned gen0;                 // grid-barrier generation when this launch began
     float rinv[DS_ROWS];
+    alignas(16) unsigned short normw[DS_NORMW_MAX];  // the RMSNorm weight of the running phase (K <= DS_NORMW_MAX)
     float ss[DS_EPI_WARPS][DS_ROWS];
     int last_flag;
     // attention
@@ -285,23 +318,37 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();
             unsigned gc = 0;
+            long long waited = 0;
+            const long long t_begin = clock64();
             for (int p = 0; p < nph; ++p) {
                 const DsPhase &ph = phases[p];
                 ds_mark(0, p);
                 if (ph.kind == DS_GEMM) {
-                    int64_t u0, u1, geff;
-                    ds_range((int64_t)ph.ntiles * ph.kchunks, cta, nctas, u0, u1, geff);
+                    const int ntiles = ph.ntiles, kchunks = ph.kchunks, S = ph.nsplit, tpg = ph.tiles_per_group;
+                    const int nunits = ntiles * S;
                     const uint32_t tx = DS_W_BYTES + (ph.xform == DS_XF_SILU_MUL ? 2 : 1) * DS_X_BYTES;
-                    for (int64_t u = u0; u < u1; ++u, ++gc) {
-                        const int tile = (int)(u / ph.kchunks), kc = (int)(u % ph.kchunks);
-                        const int g = tile / ph.tiles_per_group, n0 = (tile % ph.tiles_per_group) * 128;
-                        const int s = gc % DS_STAGES;
-                        ds_mbar_wait(&sh.empty[s], ((gc / DS_STAGES) & 1) ^ 1, DSW_W_EMPTY, p, gc);
-                        mbar_expect_tx(&sh.full[s], tx);
-                        uint8_t *dst = ring + (size_t)s * DS_STAGE_BYTES;
-                        tma_load_2d(dst, &ph.mapW[g], &sh.full[s], n0, kc * 64, pol);
-                        tma_load_2d(dst + DS_W_BYTES / 2, &ph.mapW[g], &sh.full[s], n0 + 64, kc * 64, pol);
-                        sh.w_issued = gc + 1;
+                    int s = gc % DS_STAGES;
+                    uint32_t par = ((gc / DS_STAGES) & 1) ^ 1;
+                    int probe_i = 0;
+                    for (int unit = cta; unit < nunits; unit += nctas) {
+                        const int tile = unit % ntiles, sp = unit / ntiles;
+                        const int kb = sp * kchunks / S, ke = (sp + 1) * kchunks / S;
+                        const int n0 = (tile % tpg) * 128;
+                        const CUtensorMap *map = &ph.mapW[tile / tpg];
+                        for (int kc = kb; kc < ke; ++kc, ++gc, ++probe_i) {
+                            ds_probe(prog.trace, nph, p, probe_i, 0);
+                            ds_mbar_wait(&sh.empty[s], par, DSW_W_EMPTY, p, gc, waited);
+                            mbar_expect_tx(&sh.full[s], tx);
+                            uint8_t *dst = ring + (size_t)s * DS_STAGE_BYTES;
+                            tma_load_2d(dst, map, &sh.full[s], n0, kc * 64, pol);
+                            tma_load_2d(dst + DS_W_BYTES / 2, map, &sh.full[s], n0 + 64, kc * 64, pol);
+                            sh.w_issued = gc + 1;
+                            ds_probe(prog.trace, nph, p, probe_i, 1);
+                            if (++s == DS_STAGES) {
+                                s = 0;
+                                par ^= 1;
+                            }
+                        }
                     }
                 } else {
                     AttWalk w;
@@ -312,14 +359,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
                         const int rows = min(DS_CH, w.pos - w.c * DS_CH);
                         const uint32_t bytes = rows > 0 ? (uint32_t)rows * DS_KD * (uint32_t)sizeof(T) : 0;
                         const int64_t off = ((int64_t)w.bh * attS + (int64_t)w.c * DS_CH) * DS_KD;
-                        ds_mbar_wait(&sh.empty[sk], ((gc / DS_STAGES) & 1) ^ 1, DSW_W_EMPTY, p, gc);
+                        ds_mbar_wait(&sh.empty[sk], ((gc / DS_STAGES) & 1) ^ 1, DSW_W_EMPTY, p, gc, waited);
                         if (bytes) {
                             mbar_expect_tx(&sh.full[sk], bytes);
                             bulk_load_1d(ring + (size_t)sk * DS_STAGE_BYTES, kcache + off, bytes, &sh.full[sk], pol);
                         } else {
                             mbar_arrive(&sh.full[sk]);
                         }
-                        ds_mbar_wait(&sh.empty[sv], (((gc + 1) / DS_STAGES) & 1) ^ 1, DSW_W_EMPTY, p, gc + 1);
+                        ds_mbar_wait(&sh.empty[sv], (((gc + 1) / DS_STAGES) & 1) ^ 1, DSW_W_EMPTY, p, gc + 1, waited);
                         if (bytes) {
                             mbar_expect_tx(&sh.full[sv], bytes);
                             bulk_load_1d(ring + (size_t)sv * DS_STAGE_BYTES, vcache + off, bytes, &sh.full[sv], pol);
@@ -331,6 +378,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
                     }
                 }
             }
+            ds_role_stats(prog.trace, nph, 0, waited, t_begin);
             pdl_wait();
         }
     } else if (warp == DS_WARP_X) {
@@ -353,21 +401,29 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
                 ds_mark(1, p);
                 if (p > 0) grid_wait(prog.grid_bar, gen0, (unsigned)p, p);
                 sh.phase_done = p;
+                if (prog.trace) prog.trace[((size_t)cta * nph + p) * 2] = ds_now();
                 if (ph.kind == DS_GEMM) {
-                    int64_t u0, u1, geff;
-                    ds_range((int64_t)ph.ntiles * ph.kchunks, cta, nctas, u0, u1, geff);
-                    for (int64_t u = u0; u < u1; ++u, ++gc) {
-                        const int kc = (int)(u % ph.kchunks);
-                        const int s = gc % DS_STAGES;
-                        unsigned spins = 0;
-                        while (sh.w_issued <= gc) {
-                            ++spins;
-                            if (spins == (1u << 21)) ds_report(DSW_X_WISSUED, p, gc, sh.w_issued);
-                            if (spins > (1u << 27)) __trap();
+                    const int ntiles = ph.ntiles, kchunks = ph.kchunks, S = ph.nsplit;
+                    const int nunits = ntiles * S;
+                    const bool two = ph.xform == DS_XF_SILU_MUL;
+                    const CUtensorMap *mx = &ph.mapX, *mx2 = &ph.mapX2;
+                    int s = gc % DS_STAGES, probe_i = 0;
+                    for (int unit = cta; unit < nunits; unit += nctas) {
+                        const int sp = unit / ntiles;
+                        const int kb = sp * kchunks / S, ke = (sp + 1) * kchunks / S;
+                        for (int kc = kb; kc < ke; ++kc, ++gc, ++probe_i) {
+                            unsigned spins = 0;
+                            while (sh.w_issued <= gc) {
+                                ++spins;
+                                if (spins == (1u << 21)) ds_report(DSW_X_WISSUED, p, gc, sh.w_issued);
+                                if (spins > (1u << 27)) __trap();
+                            }
+                            uint8_t *dst = ring + (size_t)s * DS_STAGE_BYTES + DS_W_BYTES;
+                            tma_load_2d(dst, mx, &sh.full[s], kc * 64, 0, pol);
+                            if (two) tma_load_2d(dst + DS_X_BYTES, mx2, &sh.full[s], kc * 64, 0, pol);
+                            ds_probe(prog.trace, nph, p, probe_i, 6);
+                            if (++s == DS_STAGES) s = 0;
                         }
-                        uint8_t *dst = ring + (size_t)s * DS_STAGE_BYTES + DS_W_BYTES;
-                        tma_load_2d(dst, &ph.mapX, &sh.full[s], kc * 64, 0, pol);
-                        if (ph.xform == DS_XF_SILU_MUL) tma_load_2d(dst + DS_X_BYTES, &ph.mapX2, &sh.full[s], kc * 64, 0, pol);
                     }
                 } else {
                     gc += 2u * (unsigned)att_units_mine;
@@ -382,6 +438,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
                                                   /*B = X K-major*/ 0, 128, DS_ROWS);
             const uint32_t ring_u32 = smem_u32(ring);
             unsigned gc = 0, seg = 0;
+            long long waited = 0;
+            const long long t_begin = clock64();
             for (int p = 0; p < nph; ++p) {
                 const DsPhase &ph = phases[p];
                 ds_mark(2, p);
@@ -399,20 +457,20 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
                         if (spins > (1u << 27)) __trap();
                     }
                 }
-                int64_t u0, u1, geff;
-                ds_range((int64_t)ph.ntiles * ph.kchunks, cta, nctas, u0, u1, geff);
-                int64_t u = u0;
-                while (u < u1) {
-                    const int64_t tile_end = (u / ph.kchunks + 1) * ph.kchunks;
-                    const int64_t ue = tile_end < u1 ? tile_end : u1;
+                const int ntiles = ph.ntiles, kchunks = ph.kchunks, S = ph.nsplit;
+                const int nunits = ntiles * S;
+                int s = gc % DS_STAGES, probe_i = 0;
+                uint32_t par = (gc / DS_STAGES) & 1;
+                for (int unit = cta; unit < nunits; unit += nctas) {
+                    const int sp = unit / ntiles;
+                    const int kb = sp * kchunks / S, ke = (sp + 1) * kchunks / S;
                     const unsigned buf = seg % DS_ACC_BUFS;
-                    ds_mbar_wait(&sh.acc_empty[buf], ((seg / DS_ACC_BUFS) & 1) ^ 1, DSW_MMA_ACC, p, seg);
+                    ds_mbar_wait(&sh.acc_empty[buf], ((seg / DS_ACC_BUFS) & 1) ^ 1, DSW_MMA_ACC, p, seg, waited);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * DS_ROWS;
-                    bool first = true;
-                    for (; u < ue; ++u, ++gc) {
-                        const int s = gc % DS_STAGES;
-                        ds_mbar_wait(&sh.ready[s], (gc / DS_STAGES) & 1, DSW_MMA_READY, p, gc);
+                    for (int kc = kb; kc < ke; ++kc, ++gc, ++probe_i) {
+                        ds_mbar_wait(&sh.ready[s], par, DSW_MMA_READY, p, gc, waited);
+                        ds_probe(prog.trace, nph, p, probe_i, 4);
                         tc_fence_after();
                         const uint32_t wb = ring_u32 + s * DS_STAGE_BYTES, xb = wb + DS_W_BYTES;
 #pragma unroll
@@ -421,16 +479,21 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
                             const uint64_t a_desc = umma_desc_sw128(wb + kk * 2048, DS_W_BYTES / 2, 1024);
                             // B: [16 rows x 128 B], 8-row groups 1 KB apart, one k16 step = 32 B inside the row
                             const uint64_t b_desc = umma_desc_sw128(xb + kk * 32, 0, 1024);
-                            tc_mma_f16(d_tmem, a_desc, b_desc, idesc, (first && kk == 0) ? 0u : 1u);
+                            tc_mma_f16(d_tmem, a_desc, b_desc, idesc, (kc == kb && kk == 0) ? 0u : 1u);
                         }
-                        first = false;
                         mbar_arrive_n(&sh.empty[s], DS_CONS_WARPS - 1);  // the commit below is the 8th arrival
                         tc_commit(&sh.empty[s]);
+                        ds_probe(prog.trace, nph, p, probe_i, 5);
+                        if (++s == DS_STAGES) {
+                            s = 0;
+                            par ^= 1;
+                        }
                     }
                     tc_commit(&sh.acc_full[buf]);
                     ++seg;
                 }
             }
+            ds_role_stats(prog.trace, nph, 2, waited, t_begin);
         }
     }
 
@@ -443,31 +506,46 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
         const bool is_epi = warp < DS_EPI_WARPS;
         const int xt = threadIdx.x - DS_EPI_WARPS * 32;  // transform thread index 0..127
         unsigned gc = 0, seg = 0;
+        long long waited = 0;
+        const long long t_begin = clock64();
         const int rows = prog.rows;
         for (int p = 0; p < nph; ++p) {
             const DsPhase &ph = phases[p];
             if (threadIdx.x == 0) ds_mark(3, p);
             if (xt == 0) ds_mark(4, p);
             if (ph.kind == DS_GEMM) {
-                int64_t u0, u1, geff;
-                const int64_t total = (int64_t)ph.ntiles * ph.kchunks;
-                ds_range(total, cta, nctas, u0, u1, geff);
+                const int ntiles = ph.ntiles, kchunks = ph.kchunks, S = ph.nsplit, K = ph.K;
+                const int nunits = ntiles * S;
                 if (!is_epi) {
                     // ---------------- transform warps ----------------
-                    if (ph.xform == DS_XF_RMSNORM) {
+                    const int xform = ph.xform;
+                    const T *norm_w = (const T *)ph.norm_w;
+                    const bool w_in_smem = xform == DS_XF_RMSNORM && K <= DS_NORMW_MAX && K % 8 == 0;
+                    if (xform == DS_XF_RMSNORM) {
+                        named_bar_sync(3, DS_XF_WARPS * 32);  // the previous norm phase's readers of rinv / normw are done
+                        // the RMSNorm weight (a constant) goes to shared memory ahead of the phase barrier
+                        if (w_in_smem)
+                            for (int i = xt; i < K / 8; i += DS_XF_WARPS * 32)
+                                *reinterpret_cast<uint4 *>(&sh.normw[i * 8]) = *reinterpret_cast<const uint4 *>(norm_w + i * 8);
                         unsigned spins = 0;
                         while (sh.phase_done < p) {
                             ++spins;
                             if (spins == (1u << 21) && xt == 0) ds_report(DSW_XF_PHASE, p, gc, sh.phase_done);
                             if (spins > (1u << 27)) __trap();
                         }
-                        named_bar_sync(3, DS_XF_WARPS * 32);  // previous phase's rinv readers are done
                         if (ph.ss_in) {
-                            if (xt < DS_ROWS) {
-                                float ssum = 0.f;
-                                for (int t = 0; t < ph.ss_in_tiles; ++t) ssum += __ldcg(ph.ss_in + t * DS_ROWS + xt);
-                                sh.rinv[xt] = rsqrtf(ssum / (float)ph.K + 0.00001f);
-                            }
+                            // 8 threads per row, each sums every 8th tile's partial (independent loads in flight), then a
+                            // fixed xor tree over the 8 lanes: deterministic, ~1 L2 round trip instead of one per tile
+                            const int r = xt >> 3, c8 = xt & 7;
+                            const float *sp_ = ph.ss_in + r;
+                            const int nt = ph.ss_in_tiles;
+                            float part = 0.f;
+#pragma unroll 4
+                            for (int tt = c8; tt < nt; tt += 8) part += __ldcg(sp_ + tt * DS_ROWS);
+                            part += __shfl_xor_sync(0xffffffffu, part, 4);
+                            part += __shfl_xor_sync(0xffffffffu, part, 2);
+                            part += __shfl_xor_sync(0xffffffffu, part, 1);
+                            if (c8 == 0) sh.rinv[r] = rsqrtf(part / (float)K + 0.00001f);
                         } else {
                             // no producer phase (first layer: the rows come from the embedding gather): reduce them here
                             const T *xr = (const T *)ph.x_raw;
@@ -475,8 +553,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
                             for (int r = xw; r < DS_ROWS; r += DS_XF_WARPS) {
                                 float ssum = 0.f;
                                 if (r < rows)
-                                    for (int i = lane; i < ph.K / 8; i += 32) {
-                                        const Vec16<T> a = ld16_cg(xr + (int64_t)r * ph.K + i * 8);
+                                    for (int i = lane; i < K / 8; i += 32) {
+                                        const Vec16<T> a = ld16_cg(xr + (int64_t)r * K + i * 8);
 #pragma unroll
                                         for (int j = 0; j < Vec16<T>::N; ++j) {
                                             const float f = to_f(a.v[j]);
@@ -484,55 +562,71 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
                                         }
                                     }
                                 ssum = warp_sum(ssum);
-                                if (lane == 0) sh.rinv[r] = rsqrtf(ssum / (float)ph.K + 0.00001f);
+                                if (lane == 0) sh.rinv[r] = rsqrtf(ssum / (float)K + 0.00001f);
                             }
                         }
                         named_bar_sync(3, DS_XF_WARPS * 32);
                     }
                     const int t = xt >> 3, c = xt & 7;                       // row, 16-byte chunk of this thread
                     const int sw_off = t * 128 + ((c ^ (t & 7)) << 4);        // 128B-swizzled position inside the X box
-                    const float rinv = ph.xform == DS_XF_RMSNORM ? sh.rinv[t] : 0.f;
-                    for (int64_t u = u0; u < u1; ++u, ++gc) {
-                        const int s = gc % DS_STAGES;
-                        ds_mbar_wait(&sh.full[s], (gc / DS_STAGES) & 1, DSW_XF_FULL, p, gc);
-                        if (ph.xform != DS_XF_NONE) {
-                            const int kc = (int)(u % ph.kchunks);
-                            uint8_t *xs = ring + (size_t)s * DS_STAGE_BYTES + DS_W_BYTES;
-                            Vec16<T> a = *reinterpret_cast<const Vec16<T> *>(xs + sw_off), o;
-                            if (ph.xform == DS_XF_RMSNORM) {
-                                const int k0 = kc * 64 + c * 8;
-                                Vec16<T> w;
-                                if (k0 + 8 <= ph.K) w = ld16((const T *)ph.norm_w + k0);
-                                else
+                    const float rinv = xform == DS_XF_RMSNORM ? sh.rinv[t] : 0.f;
+                    int s = gc % DS_STAGES, probe_i = 0;
+                    uint32_t par = (gc / DS_STAGES) & 1;
+                    for (int unit = cta; unit < nunits; unit += nctas) {
+                        const int sp = unit / ntiles;
+                        const int kb = sp * kchunks / S, ke = (sp + 1) * kchunks / S;
+                        for (int kc = kb; kc < ke; ++kc, ++gc, ++probe_i) {
+                            ds_mbar_wait(&sh.full[s], par, DSW_XF_FULL, p, gc, waited);
+                            if (xt == 0) ds_probe(prog.trace, nph, p, probe_i, 2);
+                            if (xform != DS_XF_NONE) {
+                                uint8_t *xs = ring + (size_t)s * DS_STAGE_BYTES + DS_W_BYTES;
+                                Vec16<T> a = *reinterpret_cast<const Vec16<T> *>(xs + sw_off), o;
+                                if (xform == DS_XF_RMSNORM) {
+                                    const int k0 = kc * 64 + c * 8;
+                                    Vec16<T> w;
+                                    if (w_in_smem) {
+                                        if (k0 < K) w = *reinterpret_cast<const Vec16<T> *>(&sh.normw[k0]);
+                                        else
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) w.v[j] = k0 + j < ph.K ? ((const T *)ph.norm_w)[k0 + j] : from_f<T>(0.f);
+                                            for (int j = 0; j < 8; ++j) w.v[j] = from_f<T>(0.f);
+                                    } else {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) o.v[j] = from_f<T>(round_t<T>(to_f(a.v[j]) * rinv) * to_f(w.v[j]));
-                            } else {
-                                const Vec16<T> b = *reinterpret_cast<const Vec16<T> *>(xs + DS_X_BYTES + sw_off);
+                                        for (int j = 0; j < 8; ++j) w.v[j] = k0 + j < K ? norm_w[k0 + j] : from_f<T>(0.f);
+                                    }
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float g = to_f(a.v[j]);
-                                    o.v[j] = from_f<T>(round_t<T>(g / (1.f + expf(-g))) * to_f(b.v[j]));
+                                    for (int j = 0; j < 8; ++j) o.v[j] = from_f<T>(round_t<T>(to_f(a.v[j]) * rinv) * to_f(w.v[j]));
+                                } else {
+                                    const Vec16<T> b = *reinterpret_cast<const Vec16<T> *>(xs + DS_X_BYTES + sw_off);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float g = to_f(a.v[j]);
+                                        o.v[j] = from_f<T>(round_t<T>(g / (1.f + expf(-g))) * to_f(b.v[j]));
+                                    }
                                 }
+                                *reinterpret_cast<Vec16<T> *>(xs + sw_off) = o;
+                                fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                             }
-                            *reinterpret_cast<Vec16<T> *>(xs + sw_off) = o;
-                            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&sh.ready[s]);
+                            if (xt == 0) ds_probe(prog.trace, nph, p, probe_i, 3);
+                            if (++s == DS_STAGES) {
+                                s = 0;
+                                par ^= 1;
+                            }
                         }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&sh.ready[s]);
                     }
                 } else {
                     // ---------------- epilogue warps: accumulator -> (partial tile, ticket, fix-up) -> output ----------------
                     const int quad = warp & 3;
                     const int col = quad * 32 + lane;  // column inside the tile == TMEM lane
-                    int64_t u = u0;
-                    while (u < u1) {
-                        const int tile = (int)(u / ph.kchunks);
-                        const int64_t tile_u0 = (int64_t)tile * ph.kchunks, tile_end = tile_u0 + ph.kchunks;
-                        const int64_t ue = tile_end < u1 ? tile_end : u1;
+                    const int tpg = ph.tiles_per_group, npg = ph.n_per_group, epi = ph.epi;
+                    float *partial = ph.partial;
+                    int *tickets = ph.tickets;
+                    for (int unit = cta; unit < nunits; unit += nctas) {
+                        const int tile = unit % ntiles, sp = unit / ntiles;
+                        const int kb = sp * kchunks / S, ke = (sp + 1) * kchunks / S;
                         const unsigned buf = seg % DS_ACC_BUFS;
-                        ds_mbar_wait(&sh.acc_full[buf], (seg / DS_ACC_BUFS) & 1, DSW_EPI_ACC, p, seg);
+                        ds_mbar_wait(&sh.acc_full[buf], (seg / DS_ACC_BUFS) & 1, DSW_EPI_ACC, p, seg, waited);
                         tc_fence_after();
                         uint32_t v[16];
                         tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * DS_ROWS, v);
@@ -540,56 +634,55 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&sh.acc_empty[buf]);
                         ++seg;
-                        gc += (unsigned)(ue - u);
-                        // which CTAs hold parts of this tile:  cta(u) = floor(((u + 1) geff - 1) / total)
-                        const int first_cta = (int)(((tile_u0 + 1) * geff - 1) / total);
-                        const int last_cta = (int)((tile_end * geff - 1) / total);
-                        const int nseg = last_cta - first_cta + 1;
+                        gc += (unsigned)(ke - kb);
                         bool do_epi = true;
-                        if (nseg > 1) {
-                            float *slot = ph.partial + ((int64_t)tile * ph.slots_per_tile + (cta - first_cta)) * (DS_ROWS * 128);
+                        if (S > 1) {
+                            // split-K: every split parks its fp32 partial tile; the LAST to arrive (ticket) sums them in split order
+                            float *slot = partial + ((int64_t)tile * S + sp) * (DS_ROWS * 128);
 #pragma unroll
                             for (int j = 0; j < DS_ROWS; ++j) __stcg(slot + j * 128 + col, __uint_as_float(v[j]));
                             __threadfence();
                             named_bar_sync(1, DS_EPI_WARPS * 32);
                             if (threadIdx.x == 0) {
-                                const int old = atomicAdd(ph.tickets + tile, 1);
-                                sh.last_flag = old == nseg - 1;
-                                if (sh.last_flag) ph.tickets[tile] = 0;  // self-cleaning: every other sharer has arrived
+                                const int old = atomicAdd(tickets + tile, 1);
+                                sh.last_flag = old == S - 1;
+                                if (sh.last_flag) tickets[tile] = 0;  // self-cleaning: every other split has arrived
                                 __threadfence();
                             }
                             named_bar_sync(1, DS_EPI_WARPS * 32);
                             do_epi = sh.last_flag != 0;
                             if (do_epi) {
-                                const float *base = ph.partial + (int64_t)tile * ph.slots_per_tile * (DS_ROWS * 128);
+                                const float *base = partial + (int64_t)tile * S * (DS_ROWS * 128);
+                                float f[DS_ROWS];
 #pragma unroll
-                                for (int j = 0; j < DS_ROWS; ++j) {
-                                    float f = 0.f;
-                                    for (int sidx = 0; sidx < nseg; ++sidx) f += __ldcg(base + sidx * (DS_ROWS * 128) + j * 128 + col);
-                                    v[j] = __float_as_uint(f);
-                                }
+                                for (int j = 0; j < DS_ROWS; ++j) f[j] = 0.f;
+                                for (int sidx = 0; sidx < S; ++sidx)
+#pragma unroll
+                                    for (int j = 0; j < DS_ROWS; ++j) f[j] += __ldcg(base + sidx * (DS_ROWS * 128) + j * 128 + col);
+#pragma unroll
+                                for (int j = 0; j < DS_ROWS; ++j) v[j] = __float_as_uint(f[j]);
                             }
                         }
                         if (do_epi) {
-                            const int g = tile / ph.tiles_per_group, n = (tile % ph.tiles_per_group) * 128 + col;
-                            const bool nok = n < ph.n_per_group;
+                            const int g = tile / tpg, n = (tile % tpg) * 128 + col;
+                            const bool nok = n < npg;
                             T *out = (T *)ph.out[g];
-                            if (ph.epi == DS_EPI_STORE) {
+                            if (epi == DS_EPI_STORE) {
                                 if (nok)
 #pragma unroll
                                     for (int j = 0; j < DS_ROWS; ++j)
-                                        if (j < rows) out[(int64_t)j * ph.n_per_group + n] = from_f<T>(__uint_as_float(v[j]));
+                                        if (j < rows) out[(int64_t)j * npg + n] = from_f<T>(__uint_as_float(v[j]));
                             } else {
                                 const T *res = (const T *)ph.residual;
                                 float resv[DS_ROWS];
 #pragma unroll
-                                for (int j = 0; j < DS_ROWS; ++j) resv[j] = (nok && j < rows) ? ld_cg_f(res + (int64_t)j * ph.n_per_group + n) : 0.f;
+                                for (int j = 0; j < DS_ROWS; ++j) resv[j] = (nok && j < rows) ? ld_cg_f(res + (int64_t)j * npg + n) : 0.f;
                                 float sq[DS_ROWS];
 #pragma unroll
                                 for (int j = 0; j < DS_ROWS; ++j) {
                                     // MatMul output rounded as the separate kernel stores it, then Add(residual, .) rounded
                                     const float f = round_t<T>(resv[j] + round_t<T>(__uint_as_float(v[j])));
-                                    if (nok && j < rows) out[(int64_t)j * ph.n_per_group + n] = from_f<T>(f);
+                                    if (nok && j < rows) out[(int64_t)j * npg + n] = from_f<T>(f);
                                     sq[j] = (nok && j < rows) ? f * f : 0.f;
                                 }
                                 if (ph.ss_out) {
@@ -606,14 +699,19 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
                                 }
                             }
                         }
-                        u = ue;
                     }
                     // phase done for this CTA: publish and arrive at the grid barrier
                     named_bar_sync(1, DS_EPI_WARPS * 32);
                     if (threadIdx.x == 0 && p + 1 < nph) {
                         // never arrive at barrier p before barrier p-1 has completed (a CTA without work in this phase would
                         // otherwise mix its arrival into the previous barrier's count)
-                        while (sh.phase_done < p) {}
+                        unsigned spins = 0;
+                        while (sh.phase_done < p) {
+                            ++spins;
+                            if (spins == (1u << 21)) ds_report(DSW_EPI_ACC, p, gc, 0xFFFFu);
+                            if (spins > (1u << 27)) __trap();
+                        }
+                        if (prog.trace) prog.trace[((size_t)cta * nph + p) * 2 + 1] = ds_now();
                         grid_arrive(prog.grid_bar, (unsigned)nctas);
                     }
                 }
@@ -676,11 +774,43 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
                 const int nvalid = pos - c * DS_CH;
                 const int sk = gc % DS_STAGES, sv = (gc + 1) % DS_STAGES;
                 const unsigned char *kb = ring + (size_t)sk * DS_STAGE_BYTES, *vb = ring + (size_t)sv * DS_STAGE_BYTES;
-                ds_mbar_wait(&sh.full[sk], (gc / DS_STAGES) & 1, DSW_ATT_FULLK, p, gc);
-                ds_mbar_wait(&sh.full[sv], ((gc + 1) / DS_STAGES) & 1, DSW_ATT_FULLV, p, gc + 1);
+                ds_mbar_wait(&sh.full[sk], (gc / DS_STAGES) & 1, DSW_ATT_FULLK, p, gc, waited);
+                ds_mbar_wait(&sh.full[sv], ((gc + 1) / DS_STAGES) & 1, DSW_ATT_FULLV, p, gc + 1, waited);
                 const T *ks = reinterpret_cast<const T *>(kb) + (warp * U * RPW + sub) * DS_KD + colq;
                 const T *vs = reinterpret_cast<const T *>(vb) + (warp * U * RPW + sub) * DS_KD + colq;
-                {
+                if (nvalid >= DS_CH) {
+                    // full chunk (every chunk but a head's last): branch-free, so the U rows' load / dot / shuffle chains interleave
+                    float sc[U];
+#pragma unroll
+                    for (int uu = 0; uu < U; ++uu) {
+                        const Vec16<T> kv = ld16(ks + uu * RPW * DS_KD);
+                        float d = 0.f;
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) d += qf[j] * to_f(kv.v[j]);
+                        sc[uu] = d;
+                    }
+#pragma unroll
+                    for (int o = LPR / 2; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int uu = 0; uu < U; ++uu) sc[uu] += __shfl_xor_sync(0xffffffffu, sc[uu], o);
+                    }
+                    float mx = m;
+#pragma unroll
+                    for (int uu = 0; uu < U; ++uu) mx = fmaxf(mx, sc[uu]);
+                    const float corr = expf(m - mx);  // m = -inf -> 0
+                    l *= corr;
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) acc[j] *= corr;
+#pragma unroll
+                    for (int uu = 0; uu < U; ++uu) {
+                        const Vec16<T> vv = ld16(vs + uu * RPW * DS_KD);
+                        const float pe = expf(sc[uu] - mx);
+                        l += pe;
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) acc[j] = fmaf(pe, to_f(vv.v[j]), acc[j]);
+                    }
+                    m = mx;
+                } else {
                     float sc[U];
                     bool ok[U];
 #pragma unroll
@@ -834,8 +964,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const DsPro
                 att_next(w);
             }
             named_bar_sync(2, CONSUMERS);
-            if (threadIdx.x == 0 && p + 1 < nph) grid_arrive(prog.grid_bar, (unsigned)nctas);  // (phase_done >= p: waited above)
+            if (threadIdx.x == 0 && p + 1 < nph) {
+                if (prog.trace) prog.trace[((size_t)cta * nph + p) * 2 + 1] = ds_now();
+                grid_arrive(prog.grid_bar, (unsigned)nctas);  // (phase_done >= p: waited above)
+            }
         }
+        if (threadIdx.x == 0) ds_role_stats(prog.trace, nph, 3, waited, t_begin);
+        if (xt == 0) ds_role_stats(prog.trace, nph, 4, waited, t_begin);
     }
 
     __syncthreads();
@@ -866,16 +1001,34 @@ static DsDeviceState &ds_device_state() {
     return st[dev];
 }
 
-int ds_max_slots(int ntiles, int kchunks, int nctas) {
-    const int64_t total = (int64_t)ntiles * kchunks;
-    const int64_t geff = std::min<int64_t>(total, nctas);
-    const int64_t per = std::max<int64_t>(1, total / std::max<int64_t>(1, geff));  // smallest range length
-    return (int)((kchunks + per - 1) / per + 1);
+// split-K factor of a GEMM phase: units = ntiles x S are dealt to the persistent CTAs in WAVES (unit = cta + wave * nctas,
+// unit -> (split = unit / ntiles, tile = unit % ntiles)), so the CTAs of a wave stream ADJACENT column tiles over the SAME k
+// rows in lock-step -- the DRAM-page locality a row-major [K, N] weight needs (profiles/r01_gemm_bench.md: contiguous
+// per-CTA k ranges lose 25-55 %).  S = the smallest factor whose wave fill is within 2 % of the best.
+int ds_pick_split(int ntiles, int kchunks, int nctas) {
+    const int smax = std::max(1, std::min(16, kchunks / 2));
+    double eff[17] = {0};
+    double best_eff = 0.0;
+    for (int S = 1; S <= smax; ++S) {
+        const int64_t units = (int64_t)ntiles * S;
+        const int64_t waves = (units + nctas - 1) / nctas;
+        const int per = (kchunks + S - 1) / S;  // time ~ waves x (longest unit); work ~ ntiles x kchunks
+        eff[S] = (double)ntiles * kchunks / ((double)waves * per * nctas);
+        best_eff = std::max(best_eff, eff[S]);
+    }
+    for (int S = 1; S <= smax; ++S)
+        if (eff[S] >= best_eff - 0.02) return S;  // the smallest split within 2 % of the best: fewer partial tiles to park and sum
+    return 1;
 }
+int ds_max_slots(int ntiles, int kchunks, int nctas) { return ds_pick_split(ntiles, kchunks, nctas); }
 
 }  // namespace itb
 
 using namespace itb;
+
+static unsigned long long *g_ds_trace = nullptr;
+// phase timeline (tools/ds_trace.py): device buffer of >= 148 * nphases * 2 u64, or NULL to switch it off
+extern "C" void it_b200_decode_stack_trace(void *dev_buf) { g_ds_trace = (unsigned long long *)dev_buf; }
 
 // A cached program: phases in device memory + the tickets it owns (self-cleaning, so zeroed once)
 struct DsCacheEntry {
@@ -900,6 +1053,7 @@ static int ds_launch(int dtype, const DsPhase *dev_phases, int nph, int rows, co
     prog.rope_pos = rope_pos;
     prog.rope_pos_dtype = rope_pos_dtype;
     prog.grid_bar = ds.grid_bar;
+    prog.trace = g_ds_trace;
     const int smem = DS_STAGES * DS_STAGE_BYTES + 1024;
     cudaError_t e;
     if (dtype == ITB_BF16) {
@@ -948,7 +1102,8 @@ static bool ds_fill_gemm(DsPhase &ph, int rows, const DsGemmDesc &d, int nctas) 
     ph.residual = d.residual;
     ph.norm_w = d.norm_w;
     ph.x_raw = d.X;
-    ph.slots_per_tile = ds_max_slots(ph.ntiles, ph.kchunks, nctas);
+    ph.nsplit = ds_pick_split(ph.ntiles, ph.kchunks, nctas);
+    ph.slots_per_tile = ph.nsplit;
     return true;
 }
 

@@ -35,7 +35,8 @@ struct alignas(64) DsPhase {
     const void *x_raw;          // xform 1: the un-normalised rows [rows, K]
     const void *norm_w;         // xform 1: RMSNorm weight [K]
     float *partial;             // split-K partial tiles [ntiles][slots_per_tile][16][128] fp32
-    int slots_per_tile;
+    int slots_per_tile;         // == nsplit
+    int nsplit;                 // split-K factor S: units = ntiles x S, unit -> (split = unit / ntiles, tile = unit % ntiles)
     int *tickets;               // [ntiles], self-cleaning
     // ---- attention
     void *kcache, *vcache;      // [B, H, S_max, 128]
@@ -55,6 +56,7 @@ struct DsProgram {
     const void *rope_pos;   // per-row RoPE positions (nullptr: no RoPE)
     int rope_pos_dtype;
     unsigned int *grid_bar; // {count, generation}, zero-initialised once per device
+    unsigned long long *trace;  // optional (tools/ds_trace.py): [cta][phase][2] globaltimer at phase start / this CTA's arrival
 };
 
 // host side (decode_stack.cu)

@@ -269,7 +269,8 @@ def test_fused_schedule_and_alias_plan(B, monkeypatch):
     from infinitensor_b200 import graphs as G
     rt = B.HostPlanRuntime()
     cfg = G.LlamaConfig(layers=2, d_model=512, heads=4, head_dim=128, ffn=1024, vocab=128, s_max=32, batch=16)
-    # default: the two decoder layers collapse into ONE step of the persistent kernel (gather, final norm, logits remain)
+    # ITB_DECODE_STACK=1: the two decoder layers collapse into ONE step of the persistent kernel (gather, final norm, logits remain)
+    monkeypatch.setenv("ITB_DECODE_STACK", "1")
     h0 = B.GraphHandler(rt)
     G.build_llama_decode(h0, cfg)
     sc0 = [s for s in h0.schedule() if not s.startswith("Alias")]
@@ -279,7 +280,7 @@ def test_fused_schedule_and_alias_plan(B, monkeypatch):
     hb = B.GraphHandler(rt)
     G.build_llama_decode(hb, G.LlamaConfig(layers=1, d_model=512, heads=4, head_dim=128, ffn=1024, vocab=128, s_max=32, batch=17))
     assert not any(s.startswith("DecoderStack") for s in hb.schedule())
-    monkeypatch.setenv("ITB_FUSION_MASK", "127")  # the per-operator fusions underneath
+    monkeypatch.delenv("ITB_DECODE_STACK")  # default: the per-operator fusions
     h = B.GraphHandler(rt)
     G.build_llama_decode(h, cfg)
     sc = h.schedule()
@@ -297,7 +298,6 @@ def test_fused_schedule_and_alias_plan(B, monkeypatch):
     h.data_malloc()
     fused_bytes = h.arena_bytes()[1]
     assert h0.arena_bytes()[1] <= 1.5 * fused_bytes  # a stack keeps its layers' intermediates live together (~1.5 MB per 7B layer)
-    monkeypatch.delenv("ITB_FUSION_MASK")
     monkeypatch.setenv("ITB_NO_FUSION", "1")
     h2 = B.GraphHandler(rt)
     G.build_llama_decode(h2, cfg)
