@@ -233,6 +233,17 @@ int it_b200_attention_kvcache_rope(int dtype, void *k_cache, void *v_cache, cons
                                    int rope_pos_dtype, void *out, int B, int H, int S_max, int D, void *workspace,
                                    int64_t workspace_bytes, void *stream);
 
+/* ---- Fused prefill attention (q-len > 1) on tcgen05 / TMEM (attention_prefill.cu):
+ *      out[b,h] = softmax((q . k^T) (/ or *) scale + mask) . v, q / k / v / out [B, H, S, D] f16 / bf16, D = 64 or 128.
+ *      Replaces the chain the frontend lowers multi-token attention to -- Transpose(k) -> MatMul (matmul.cc:66-211) ->
+ *      Div / Mul by a scalar (element_wise.cc) -> Add(mask) -> Softmax(axis -1) (softmax.cu:242-404) -> MatMul -- and keeps
+ *      its rounding points (every intermediate rounded to the storage type).  scale: device scalar or NULL; mask: additive,
+ *      element (b,h,i,j) at mask[b*sb + h*sh + i*si + j*sj] (0 = broadcast) or NULL.  No causal assumption. ---- */
+int it_b200_attention_prefill(int dtype, const void *q, const void *k, const void *v, void *out, int B, int H, int S_q,
+                              int S_kv, int D, const void *scale, int scale_is_div, const void *mask,
+                              int64_t mask_stride_b, int64_t mask_stride_h, int64_t mask_stride_i,
+                              int64_t mask_stride_j, void *stream);
+
 /* ---- The persistent decode kernel (decode_stack.cu): a whole stack of Llama decoder layers in ONE launch.
  *      Per layer it replaces the eight launches of the fused schedule -- RMSNorm (rms_norm.cu:36-110), the q/k/v MatMuls
  *      (matmul.cc:66-211), RoPE x2 (rope.cu:7-88) + AttentionKVCache (attention_kvcache.cu:8-169), the o-proj MatMul + Add

@@ -416,6 +416,39 @@ void runAttentionRope(const Operator &ropeQ, const Operator &ropeK, const Operat
                                       P(att->getOutput()), d[0], d[1], d[2], d[3], ws, wsb, S()), att);
 }
 
+bool runPrefillAttention(const OpVec &ops, const RuntimeObj *) {
+    static const bool off = [] {
+        const char *e = std::getenv("ITB_NO_PREFILL_ATTENTION");
+        return e && e[0] == '1';
+    }();
+    if (off) return false;
+    auto tr = ops[0], mm1 = ops[1], sm = ops[ops.size() - 2], mm2 = ops.back();
+    Tensor q = mm1->getInputs(0), k = tr->getInputs(0), v = mm2->getInputs(1), out = mm2->getOutput();
+    const void *scale = nullptr, *maskp = nullptr;
+    int isDiv = 0;
+    int64_t ms[4] = {0, 0, 0, 0};
+    Tensor cur = mm1->getOutput();
+    auto &qd = q->getDims();
+    const Shape full = {qd[0], qd[1], qd[2], k->getDims()[2]};
+    for (size_t i = 2; i + 2 < ops.size(); ++i) {
+        auto &o = ops[i];
+        Tensor other = o->getInputs(0) == cur ? o->getInputs(1) : o->getInputs(0);
+        if (o->getOpType() == OpType::Add) {
+            auto st = bstrides(other->getDims(), full);
+            for (int d = 0; d < 4; ++d) ms[d] = st[d];
+            maskp = P(other);
+        } else {
+            scale = P(other);
+            isDiv = o->getOpType() == OpType::Div;
+        }
+        cur = o->getOutput();
+    }
+    (void)sm;
+    CK(it_b200_attention_prefill(DT(q), P(q), P(k), P(v), P(out), qd[0], qd[1], qd[2], k->getDims()[2], qd[3], scale, isDiv, maskp,
+                                 ms[0], ms[1], ms[2], ms[3], S()), mm2);
+    return true;
+}
+
 // DecoderStack: st.sub = per layer { RMSNorm | MatMulGroup{3} | AttentionRope | MatMulAdd | RMSNorm | MatMulGroup{2} | SiluMul |
 // MatMulAdd } with Alias steps in between (schedule.cc: matchDecoderLayer)
 bool runDecoderStack(const ExecStep &st, const RuntimeObj *ctx) {

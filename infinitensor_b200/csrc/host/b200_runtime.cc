@@ -233,6 +233,10 @@ void CudaRuntimeObj::execStep(const ExecStep &st, Kernel *kernel, const PerfReco
             // no NVLink peer comm (or shape outside its limits): the ordinary kernels, one by one
             for (auto &m : st.ops) reg.getKernel(KernelAttrs{Device::CUDA, m->getOpType().underlying()})->compute(m, this);
         break;
+    case ExecStep::PrefillAttention:
+        if (!b200::runPrefillAttention(st.ops, this))
+            for (auto &m : st.ops) reg.getKernel(KernelAttrs{Device::CUDA, m->getOpType().underlying()})->compute(m, this);
+        break;
     case ExecStep::DecoderStack:
         if (!b200::runDecoderStack(st, this))
             for (auto &sb : st.sub) execStep(sb, nullptr, nullptr);

@@ -153,6 +153,8 @@ bool runAllReduceAddNorm(const OpVec &ops, const RuntimeObj *ctx);
 // Conv -> BatchNorm -> [Add] -> [Relu] in the GEMM epilogue; false = shape not taken (nothing launched)
 bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx);
 void runAttentionRope(const Operator &ropeQ, const Operator &ropeK, const Operator &att, const RuntimeObj *ctx);
+// {Transpose(k), MatMul, [Div | Mul], [Add], Softmax, MatMul} as one fused tcgen05 attention kernel; false = not taken
+bool runPrefillAttention(const OpVec &ops, const RuntimeObj *ctx);
 // L decoder layers through the persistent kernel; false = not taken (nothing launched): run `st.sub` step by step
 bool runDecoderStack(const ExecStep &st, const RuntimeObj *ctx);
 }  // namespace b200

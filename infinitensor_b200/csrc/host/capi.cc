@@ -373,7 +373,7 @@ int itb_graph_step(itb_graph *g, int index, char *buf, int buf_len) {
     ITB_TRY({
         const auto &sc = g->g->getSchedule();
         IT_ASSERT(index >= 0 && index < (int)sc.size(), "bad step index");
-        static const char *kinds[] = {"Single", "Alias", "MatMulGroup", "MatMulAdd", "SiluMul", "AttentionRope", "AllReduceAddNorm", "ConvBnAct", "DecoderStack"};
+        static const char *kinds[] = {"Single", "Alias", "MatMulGroup", "MatMulAdd", "SiluMul", "AttentionRope", "AllReduceAddNorm", "ConvBnAct", "PrefillAttention", "DecoderStack"};
         std::string s = kinds[(int)sc[index].kind];
         s += ":";
         if (sc[index].kind == ExecStep::DecoderStack) {

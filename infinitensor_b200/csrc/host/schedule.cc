@@ -18,10 +18,11 @@ static bool fusionEnabled() {
 static int fusionMask() {
     const char *e = std::getenv("ITB_FUSION_MASK");
     if (e && e[0]) return std::atoi(e);
+    // (bit 8 = prefill attention chains, on by default)
     // bit 7 (decoder-layer stacks on the persistent kernel) is opt-in: measured on the BASELINE shape it does not yet beat the
     // eight tuned launches it replaces (165 vs 112 us per layer) -- ITB_DECODE_STACK=1 switches it on
     const char *ds = std::getenv("ITB_DECODE_STACK");
-    return (ds && ds[0] == '1') ? 255 : 127;
+    return ((ds && ds[0] == '1') ? 255 : 127) | 256;
 }
 
 static bool isKvCacheOperand(const Tensor &t) {
@@ -230,6 +231,68 @@ static void fuseDecoderStacks(vector<ExecStep> &sched) {
     sched.swap(out);
 }
 
+// Multi-token attention as the frontend lowers it (no fused op exists in the reference for q-len > 1):
+//   kt = Transpose(k, swap of the last two axes); s = MatMul(q, kt); [s = Div | Mul(s, scalar)]; [s = Add(s, mask)];
+//   p = Softmax(s, axis -1); out = MatMul(p, v)         q [B,H,Sq,D], k / v [B,H,Skv,D], D in {64, 128}, f16 / bf16
+// every link single-consumer.  Returns the chain {transpose, mm1, [scale], [add], softmax} for `mm2`, or empty.
+static OpVec matchPrefillChain(const Operator &mm2op) {
+    auto mm2 = as<MatmulObj>(mm2op);
+    if (!mm2 || mm2->getBias() || mm2->getTransA() || mm2->getTransB()) return {};
+    Tensor p = mm2->getInputs(0), v = mm2->getInputs(1);
+    auto half = [](const Tensor &t) { return t->getDType() == DataType::Float16 || t->getDType() == DataType::BFloat16; };
+    if (!half(p) || v->getDType() != p->getDType() || p->getRank() != 4 || v->getRank() != 4) return {};
+    auto sole = [](const Tensor &t) { return !t->isOutput() && t->getTargets().size() == 1; };
+    auto sm = p->getSource();
+    if (!sm || sm->getOpType() != OpType::Softmax || !sole(p) || as<SoftmaxObj>(sm)->getAxis() != 3) return {};
+    OpVec mid;
+    Tensor s = sm->getInputs(0);
+    auto src = s->getSource();
+    if (src && src->getOpType() == OpType::Add && sole(s)) {
+        // one operand continues the chain, the other is the mask (anything produced outside the chain, broadcastable)
+        Tensor a0 = src->getInputs(0), a1 = src->getInputs(1);
+        auto chainish = [](const Tensor &t) {
+            auto o = t->getSource();
+            return o && (o->getOpType() == OpType::MatMul || o->getOpType() == OpType::Div || o->getOpType() == OpType::Mul);
+        };
+        Tensor cont = chainish(a0) ? a0 : chainish(a1) ? a1 : nullptr;
+        if (!cont || cont->getDims() != s->getDims()) return {};
+        Tensor other = cont == a0 ? a1 : a0;
+        if (other->getDType() != s->getDType() || other->getRank() > 4) return {};
+        mid.insert(mid.begin(), src);
+        s = cont;
+        src = s->getSource();
+    }
+    if (src && (src->getOpType() == OpType::Div || src->getOpType() == OpType::Mul) && sole(s)) {
+        Tensor a0 = src->getInputs(0), a1 = src->getInputs(1);
+        const bool isDiv = src->getOpType() == OpType::Div;
+        Tensor cont = (a1->size() == 1 && !a1->getSource()) ? a0 : (!isDiv && a0->size() == 1 && !a0->getSource()) ? a1 : nullptr;
+        if (!cont || cont->getDims() != s->getDims()) return {};
+        Tensor scalar = cont == a0 ? a1 : a0;
+        if (scalar->getDType() != s->getDType()) return {};
+        mid.insert(mid.begin(), src);
+        s = cont;
+        src = s->getSource();
+    }
+    auto mm1 = src ? as<MatmulObj>(src) : nullptr;
+    if (!mm1 || !sole(s) || mm1->getBias() || mm1->getTransA() || mm1->getTransB()) return {};
+    Tensor q = mm1->getInputs(0), kt = mm1->getInputs(1);
+    auto tr = kt->getSource() ? as<TransposeObj>(kt->getSource()) : nullptr;
+    if (!tr || !sole(kt) || tr->getPermute() != vector<int>{0, 1, 3, 2}) return {};
+    Tensor k = tr->getInputs(0);
+    if (q->getRank() != 4 || k->getRank() != 4 || q->getDType() != p->getDType() || k->getDType() != p->getDType()) return {};
+    auto &qd = q->getDims();
+    auto &kd = k->getDims();
+    auto &vd = v->getDims();
+    const int D = qd[3];
+    if ((D != 64 && D != 128) || kd[3] != D || vd[3] != D || kd[0] != qd[0] || kd[1] != qd[1] || vd[0] != qd[0] || vd[1] != qd[1] ||
+        vd[2] != kd[2])
+        return {};
+    OpVec chain = {kt->getSource(), src};
+    chain.insert(chain.end(), mid.begin(), mid.end());
+    chain.push_back(sm);
+    return chain;
+}
+
 const vector<ExecStep> &GraphObj::getSchedule() {
     if (scheduleEpoch == getTopologyEpoch() && !schedule.empty()) return schedule;
     IT_ASSERT(topo_sort(), "graph has a cycle");
@@ -242,6 +305,19 @@ const vector<ExecStep> &GraphObj::getSchedule() {
     std::unordered_map<OperatorObj *, OpVec> deferredInto;  // consumer -> producer(s) executed with it
     std::unordered_set<OperatorObj *> deferred;
 
+    // prefill attention chains first: their members must not be claimed by the per-operator patterns below
+    if (fuse && (mask & 256))
+        for (auto &op : ops) {
+            if (op->getOpType() != OpType::MatMul) continue;
+            OpVec chain = matchPrefillChain(op);
+            if (chain.empty()) continue;
+            bool clash = deferredInto.count(op.get()) > 0;
+            for (auto &m : chain) clash = clash || deferred.count(m.get()) || deferredInto.count(m.get());
+            if (clash) continue;
+            for (auto &m : chain) deferred.insert(m.get());
+            deferredInto[op.get()] = chain;
+        }
+
     for (size_t i = 0; i < ops.size(); ++i) {
         const Operator &op = ops[i];
         if (consumed.count(op.get()) || deferred.count(op.get())) continue;
@@ -251,6 +327,13 @@ const vector<ExecStep> &GraphObj::getSchedule() {
         if (it != deferredInto.end()) {
             const OpVec &prod = it->second;
             auto pt = prod[0]->getOpType();
+            if (pt == OpType::Transpose) {
+                st.kind = ExecStep::PrefillAttention;
+                st.ops = prod;
+                st.ops.push_back(op);
+                schedule.push_back(std::move(st));
+                continue;
+            }
             if (pt == OpType::RoPE) {
                 // both RoPE(q) and RoPE(k) must have been folded; a lone one simply runs here, just before its consumer
                 Operator rq, rk;

@@ -1,0 +1,282 @@
+// attention_prefill.cu -- fused multi-token (prefill) attention on the 5th-generation tensor core, sm_100a.
+//
+//   out[b,h] = softmax( (q[b,h] . k[b,h]^T) (/ or *) scale  + mask ) . v[b,h]        q, k, v, out: [B, H, S, D] f16 / bf16
+//
+// SURVEY 8(f-3).  The reference has no such kernel: its frontend lowers attention with q-len > 1 to
+// Transpose -> MatMul -> Div -> Add(mask) -> Softmax -> MatMul (examples/python + pyinfinitensor/onnx.py; config C2, GPT-2),
+// five launches of matmul.cc:66-211 / element_wise.cc / softmax.cu:242-404 per head group plus the [B,H,S,S] score tensor's
+// round trips through HBM.  This kernel is the whole chain for one (batch, head, 128-query tile) per CTA:
+//   * Q, K, V tiles arrive by TMA (3-D tensor maps over [B*H, S, D], 128B swizzle) into shared memory;
+//   * S = Q K^T runs as tcgen05.mma (kind::f16, M = 128 queries, N = 128 keys, K = 16 per instruction, both operands K-major)
+//     into a [128 lanes x 128 columns] fp32 accumulator in TENSOR MEMORY;
+//   * each of the 128 threads owns one query row: it reads its row of S back with tcgen05.ld, applies the graph's own
+//     rounding points (MatMul output, Div / Mul by the scalar, Add mask -- each rounded to the storage type like the separate
+//     kernels), and the softmax: pass A accumulates the row maximum / sum over all key tiles (online), pass B recomputes S,
+//     writes P = exp(s - max) / sum (rounded like the Softmax kernel's output) as the K-major A operand into shared memory
+//     and the tensor core accumulates O += P V (V consumed as the MN-major B operand, straight from its [S, D] layout);
+//   * O leaves TMEM once, rounded to the storage type.
+// Two passes over K instead of rescaling O in TMEM: the extra QK^T costs 2 S^2 D flops on an idle tensor pipe, and the
+// result needs no correction step -- the probabilities are final when they meet V.
+// No causal shortcut: the mask is whatever tensor the graph adds (broadcast strides), so every graph the frontend emits is
+// reproduced, not only triangular ones.
+#include <cstring>
+
+#include "gemm.cuh"
+
+namespace itb {
+
+constexpr int AP_BQ = 128, AP_BK = 128;
+
+struct ApArgs {
+    int BH, H, Sq, Skv, D;
+    const void *scale;      // device scalar (nullptr: none)
+    int scale_is_div;       // 1: s / scale, 0: s * scale
+    const void *mask;       // additive mask (nullptr: none), element (b, h, i, j) at mask[b*mb + h*mh + i*mi + j*mj]
+    int64_t mb, mh, mi, mj;
+    void *out;              // [BH, Sq, D]
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_constant__ CUtensorMap mapQ,
+                                                                   const __grid_constant__ CUtensorMap mapK,
+                                                                   const __grid_constant__ CUtensorMap mapV, const ApArgs a) {
+    constexpr int DG = D / 64;                    // 64-column groups of the head dim
+    constexpr int QK_BYTES = AP_BQ * D * 2;       // one Q or K tile (DG boxes of [128 rows x 64 cols])
+    constexpr int V_BYTES = AP_BK * D * 2;        // one V tile (DG x 2 boxes of [64 kv rows x 64 cols])
+    constexpr int P_BYTES = AP_BQ * AP_BK * 2;    // probabilities, two k-blocks of [128 rows x 64 keys]
+    extern __shared__ uint8_t ap_smem_raw[];
+    uint8_t *smem = ap_smem_raw + ((1024u - (smem_u32(ap_smem_raw) & 1023u)) & 1023u);
+    uint8_t *q_sm = smem, *k_sm = q_sm + QK_BYTES, *v_sm = k_sm + QK_BYTES, *p_sm = v_sm + V_BYTES;
+    __shared__ __align__(8) uint64_t bar_load, bar_mma;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.y, q0 = blockIdx.x * AP_BQ;
+    const int row = threadIdx.x;  // query row inside the tile == TMEM lane
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_load, 1);
+        mbar_init(&bar_mma, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&mapQ);
+        tma_prefetch_desc(&mapK);
+        tma_prefetch_desc(&mapV);
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_s = tmem_slot, tmem_o = tmem_slot + 128;
+    pdl_wait();
+
+    const uint32_t idesc_s = umma_idesc_f16(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 0, 0, 128, AP_BK);
+    const uint32_t idesc_o = umma_idesc_f16(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 0, /*B = V, MN-major*/ 1, 128, D);
+    const uint64_t pol = l2_policy_evict_last();
+    uint32_t ph_load = 0, ph_mma = 0;
+
+    // Q tile once
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar_load, QK_BYTES);
+#pragma unroll
+        for (int g = 0; g < DG; ++g) tma_load_3d(q_sm + g * (AP_BQ * 128), &mapQ, &bar_load, g * 64, q0, bh, pol);
+    }
+    mbar_wait(&bar_load, ph_load);
+    ph_load ^= 1;
+
+    float sc = 1.f;
+    if (a.scale) sc = to_f(*(const T *)a.scale);
+    const int b = bh / a.H, h = bh % a.H;
+    const T *mrow = a.mask ? (const T *)a.mask + b * a.mb + h * a.mh + (int64_t)(q0 + row) * a.mi : nullptr;
+    const bool row_ok = q0 + row < a.Sq;
+    const int ntiles = (a.Skv + AP_BK - 1) / AP_BK;
+
+    // score of (this row, key j0 + c) from the raw accumulator value, with the graph's rounding points
+    auto score = [&](float acc, int j) -> float {
+        float s = round_t<T>(acc);                                      // MatMul output
+        if (a.scale) s = round_t<T>(a.scale_is_div ? s / sc : s * sc);  // Div / Mul by the scalar constant
+        if (mrow && row_ok) s = round_t<T>(s + to_f(mrow[(int64_t)j * a.mj]));  // Add(mask)
+        return s;
+    };
+    auto load_k = [&](int t) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar_load, QK_BYTES);
+#pragma unroll
+            for (int g = 0; g < DG; ++g) tma_load_3d(k_sm + g * (AP_BK * 128), &mapK, &bar_load, g * 64, t * AP_BK, bh, pol);
+        }
+    };
+    auto mma_s = [&]() {  // S = Q K^T into tmem_s
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            const uint32_t qb = smem_u32(q_sm), kb = smem_u32(k_sm);
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk) {
+                const uint32_t off = (kk >> 2) * (128 * 128) + (kk & 3) * 32;
+                tc_mma_f16(tmem_s, umma_desc_sw128(qb + off, 0, 1024), umma_desc_sw128(kb + off, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
+            }
+            tc_commit(&bar_mma);
+        }
+    };
+
+    // ---------------- pass A: row maximum and sum over all keys ----------------
+    float m = -INFINITY, l = 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+        load_k(t);
+        mbar_wait(&bar_load, ph_load);
+        ph_load ^= 1;
+        mma_s();
+        mbar_wait(&bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        const int j0 = t * AP_BK;
+#pragma unroll 1
+        for (int c0 = 0; c0 < AP_BK; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmem_s + ((uint32_t)(warp * 32) << 16) + c0, v);
+            float sv[16], mx = m;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                sv[j] = j0 + c0 + j < a.Skv ? score(__uint_as_float(v[j]), j0 + c0 + j) : -INFINITY;
+                mx = fmaxf(mx, sv[j]);
+            }
+            if (mx > -INFINITY) {
+                float add = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) add += expf(sv[j] - mx);  // exp(-inf) = 0
+                l = l * expf(m - mx) + add;
+                m = mx;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();  // every row has read S before the next tile's MMA overwrites it (and K is reloaded)
+    }
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+
+    // ---------------- pass B: P = softmax row (final), O += P V ----------------
+    for (int t = 0; t < ntiles; ++t) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar_load, QK_BYTES + V_BYTES);
+#pragma unroll
+            for (int g = 0; g < DG; ++g) tma_load_3d(k_sm + g * (AP_BK * 128), &mapK, &bar_load, g * 64, t * AP_BK, bh, pol);
+#pragma unroll
+            for (int g = 0; g < DG; ++g)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh)
+                    tma_load_3d(v_sm + g * (AP_BK * 128) + hh * (64 * 128), &mapV, &bar_load, g * 64, t * AP_BK + hh * 64, bh, pol);
+        }
+        mbar_wait(&bar_load, ph_load);
+        ph_load ^= 1;
+        mma_s();
+        mbar_wait(&bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        const int j0 = t * AP_BK;
+#pragma unroll 1
+        for (int c0 = 0; c0 < AP_BK; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmem_s + ((uint32_t)(warp * 32) << 16) + c0, v);
+            T pv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float pr = 0.f;
+                if (j0 + c0 + j < a.Skv && m > -INFINITY) pr = expf(score(__uint_as_float(v[j]), j0 + c0 + j) - m) * inv_l;
+                pv[j] = from_f<T>(pr);  // the Softmax kernel's output rounding
+            }
+            // P is the K-major A operand of the second MMA: k-block = 64 keys, rows of 128 B, 128B swizzle
+            uint8_t *blk = p_sm + (c0 >> 6) * (AP_BQ * 128) + row * 128;
+            const int chunk = (c0 & 63) >> 3;  // first of the two 16-byte chunks these 16 keys fill
+            *reinterpret_cast<uint4 *>(blk + (((chunk) ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4 *>(&pv[0]);
+            *reinterpret_cast<uint4 *>(blk + (((chunk + 1) ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4 *>(&pv[8]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            const uint32_t pb = smem_u32(p_sm), vb = smem_u32(v_sm);
+#pragma unroll
+            for (int kk = 0; kk < AP_BK / 16; ++kk) {
+                // A = P: k-block (kk >> 2), 32 B per k16 step inside the 128 B row;  B = V (MN-major): column groups V_BYTES / DG
+                // apart (LBO), 8-row key groups 1 KB apart (SBO), one k16 step = 16 key rows = 2 KB
+                const uint64_t ad = umma_desc_sw128(pb + (kk >> 2) * (AP_BQ * 128) + (kk & 3) * 32, 0, 1024);
+                const uint64_t bd = umma_desc_sw128(vb + kk * 2048, AP_BK * 128, 1024);
+                tc_mma_f16(tmem_o, ad, bd, idesc_o, (t > 0 || kk > 0) ? 1u : 0u);
+            }
+            tc_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, ph_mma);  // P, K, V are free again (and on the last tile: O is complete)
+        ph_mma ^= 1;
+        tc_fence_after();
+    }
+
+    // ---------------- epilogue: O row -> out ----------------
+    T *orow = (T *)a.out + ((int64_t)bh * a.Sq + q0 + row) * D;
+#pragma unroll 1
+    for (int c0 = 0; c0 < D; c0 += 16) {
+        uint32_t v[16];
+        if (ntiles > 0) tmem_ld_32x32b_x16(tmem_o + ((uint32_t)(warp * 32) << 16) + c0, v);
+        T ov[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ov[j] = from_f<T>(ntiles > 0 ? __uint_as_float(v[j]) : 0.f);
+        if (row_ok) {
+            *reinterpret_cast<uint4 *>(orow + c0) = *reinterpret_cast<const uint4 *>(&ov[0]);
+            *reinterpret_cast<uint4 *>(orow + c0 + 8) = *reinterpret_cast<const uint4 *>(&ov[8]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_slot, 256);
+    }
+    (void)lane;
+}
+
+template <typename T, int D>
+static int launch_ap(const void *q, const void *k, const void *v, const ApArgs &a, cudaStream_t st) {
+    CUtensorMap mq, mk, mv;
+    if (!make_tma_3d_b16(&mq, q, (uint64_t)a.BH, (uint64_t)a.Sq, (uint64_t)D, (uint64_t)D, (uint64_t)a.Sq * D, AP_BQ, 64) ||
+        !make_tma_3d_b16(&mk, k, (uint64_t)a.BH, (uint64_t)a.Skv, (uint64_t)D, (uint64_t)D, (uint64_t)a.Skv * D, AP_BK, 64) ||
+        !make_tma_3d_b16(&mv, v, (uint64_t)a.BH, (uint64_t)a.Skv, (uint64_t)D, (uint64_t)D, (uint64_t)a.Skv * D, 64, 64))
+        ITB_FAIL("attention_prefill: cuTensorMapEncodeTiled failed");
+    const int smem = 2 * AP_BQ * D * 2 + AP_BK * D * 2 + AP_BQ * AP_BK * 2 + 1024;
+    auto kern = attention_prefill_kernel<T, D>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    ITB_CHECK(e == cudaSuccess, "attention_prefill: smem attribute: %s", cudaGetErrorString(e));
+    e = launch_k(kern, dim3((a.Sq + AP_BQ - 1) / AP_BQ, a.BH), dim3(128), (size_t)smem, st, mq, mk, mv, a);
+    ITB_CHECK(e == cudaSuccess, "attention_prefill: launch failed: %s", cudaGetErrorString(e));
+    ITB_LAUNCH_CHECK("attention_prefill");
+    return 0;
+}
+
+}  // namespace itb
+
+using namespace itb;
+
+extern "C" int it_b200_attention_prefill(int dtype, const void *q, const void *k, const void *v, void *out, int B, int H, int S_q,
+                                         int S_kv, int D, const void *scale, int scale_is_div, const void *mask,
+                                         int64_t mask_stride_b, int64_t mask_stride_h, int64_t mask_stride_i,
+                                         int64_t mask_stride_j, void *stream) {
+    ITB_CHECK(dtype == ITB_F16 || dtype == ITB_BF16, "attention_prefill: dtype %d must be f16 / bf16", dtype);
+    ITB_CHECK(D == 64 || D == 128, "attention_prefill: head dim %d must be 64 or 128", D);
+    ITB_CHECK(B >= 0 && H >= 0 && S_q >= 0 && S_kv >= 0, "attention_prefill: negative dimension");
+    ITB_CHECK((int64_t)B * H <= 65535, "attention_prefill: B * H beyond the grid limit");
+    if ((int64_t)B * H * S_q == 0) return 0;
+    ITB_CHECK(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), "attention_prefill: tensors must be 16-byte aligned");
+    ApArgs a{};
+    a.BH = B * H;
+    a.H = H;
+    a.Sq = S_q;
+    a.Skv = S_kv;
+    a.D = D;
+    a.scale = scale;
+    a.scale_is_div = scale_is_div;
+    a.mask = mask;
+    a.mb = mask_stride_b;
+    a.mh = mask_stride_h;
+    a.mi = mask_stride_i;
+    a.mj = mask_stride_j;
+    a.out = out;
+    auto st = (cudaStream_t)stream;
+    if (dtype == ITB_BF16) return D == 64 ? launch_ap<__nv_bfloat16, 64>(q, k, v, a, st) : launch_ap<__nv_bfloat16, 128>(q, k, v, a, st);
+    return D == 64 ? launch_ap<__half, 64>(q, k, v, a, st) : launch_ap<__half, 128>(q, k, v, a, st);
+}

@@ -100,6 +100,45 @@ def test_gpt2_parity(dtype):
     assert np.abs(got - ref).max() / np.abs(ref).max() < tol
 
 
+def _gpt2_run(cfg, monkeypatch=None, env=None):
+    from infinitensor_b200 import backend as B, graphs as G
+    from oracle.graph_oracle import OracleHandler
+    if env:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+    rt = B.CudaRuntime(0)
+    h, oh = B.GraphHandler(rt), OracleHandler()
+    g, og = G.build_gpt2(h, cfg), G.build_gpt2(oh, cfg)
+    sched = h.schedule()
+    h.data_malloc()
+    G.fill_gpt2_weights_host(g)
+    G.fill_gpt2_weights_host(og)
+    ids = np.random.default_rng(1).integers(0, cfg.vocab, size=(cfg.batch, cfg.seq)).astype(np.int64)
+    pos = np.arange(cfg.seq, dtype=np.int64).reshape(1, -1).repeat(cfg.batch, 0)
+    for gg in (g, og):
+        gg.input_ids.copyin_numpy(ids)
+        gg.position_ids.copyin_numpy(pos)
+    h.run_with_cudagraph()
+    oh.run()
+    return G.from_storage(g.out.copyout_numpy(), cfg.dtype).astype(np.float64), og.out.f32().astype(np.float64), sched
+
+
+def test_gpt2_small_full_size_config2(monkeypatch):
+    """BASELINE config C2 at FULL size -- GPT-2-small, 12 layers, d = 768, 12 heads of 64, ffn 3072, vocab 50257, B = 1, S = 128,
+    fp16 -- one forward through the fused schedule (PrefillAttention per layer) and CUDA-graph replay against the CPU oracle
+    executing the operator graph; and the same graph with the attention chain unfused (ITB_FUSION_MASK without bit 8)."""
+    from infinitensor_b200 import graphs as G
+    cfg = G.GPT2Config()
+    got, ref, sched = _gpt2_run(cfg)
+    assert sum(s.startswith("PrefillAttention") for s in sched) == cfg.layers
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 1e-2, err  # end-to-end fp16, 12 layers (SURVEY 8(c): 1e-3 per op, accumulated)
+    got2, _, sched2 = _gpt2_run(cfg, monkeypatch, {"ITB_FUSION_MASK": "127"})
+    assert not any(s.startswith("PrefillAttention") for s in sched2)
+    assert np.abs(got2 - ref).max() / np.abs(ref).max() < 1e-2
+    assert np.abs(got - got2).max() / np.abs(ref).max() < 5e-3  # fused vs unfused chain: same rounding points, other sum order
+
+
 @pytest.mark.parametrize("dtype", [F32, F16])
 def test_resnet_parity(dtype):
     from infinitensor_b200 import backend as B, graphs as G

@@ -480,6 +480,39 @@ def test_depth_to_space_graph(mode, dt):
     assert np.array_equal(outs[0].astype(np.float32), outs[1].reshape(outs[0].shape).astype(np.float32))
 
 
+@pytest.mark.parametrize("dt", [F16, BF16])
+@pytest.mark.parametrize("B,H,Sq,Skv,D,masked,div", [(1, 12, 128, 128, 64, True, True), (2, 3, 16, 16, 64, True, True),
+                                                      (1, 2, 200, 200, 128, True, False), (2, 2, 96, 300, 64, False, True),
+                                                      (1, 4, 257, 129, 128, True, True), (1, 1, 128, 128, 64, False, False)])
+def test_attention_prefill_parity(K, B, H, Sq, Skv, D, masked, div, dt):
+    """the fused tcgen05 prefill attention against the oracle executing the operator chain it replaces --
+    MatMul(q, k^T) -> Div|Mul(scale) -> Add(mask) -> Softmax(-1) -> MatMul(., v), every intermediate rounded to the storage
+    type (config C2's attention block: [1,12,128,64] heads, causal additive mask, scale sqrt(64))."""
+    import torch
+    from infinitensor_b200 import _lib as L
+    q, k, v = rnd((B, H, Sq, D), 50, dt, 0.7), rnd((B, H, Skv, D), 51, dt, 0.7), rnd((B, H, Skv, D), 52, dt, 0.7)
+    scale = oracle.round_to(np.array([np.sqrt(D) if div else 1.0 / np.sqrt(D)], np.float32), dt)
+    big_neg = -65504.0 if dt == F16 else -3.0e38
+    mask = None
+    if masked:
+        mask = oracle.round_to(np.triu(np.full((Sq, Skv), big_neg, np.float32), 1 + max(0, Skv - Sq)).reshape(1, 1, Sq, Skv), dt)
+    s = oracle.matmul(q, np.ascontiguousarray(k.transpose(0, 1, 3, 2)), None, False, False, dt)
+    s = oracle.binary("div" if div else "mul", s, scale, dt)
+    if masked:
+        s = oracle.binary("add", s, mask, dt)
+    p = oracle.softmax(s, -1, dt)
+    ref = oracle.matmul(p, v, None, False, False, dt)
+    qd, kd, vd, sd = K.dev(q, dt), K.dev(k, dt), K.dev(v, dt), K.dev(scale, dt)
+    md = K.dev(mask, dt) if masked else None
+    out = torch.zeros((B, H, Sq, D), dtype=K.TORCH_DT[dt], device="cuda")
+    L.check(L.lib.it_b200_attention_prefill(dt, K.ptr(qd), K.ptr(kd), K.ptr(vd), K.ptr(out), B, H, Sq, Skv, D, K.ptr(sd), int(div),
+                                            K.ptr(md), 0, 0, Skv if masked else 0, 1 if masked else 0, K.stream()))
+    K.sync()
+    got = K.host(out)
+    tol = {F16: 2e-3, BF16: 1.6e-2}[dt]  # attention tolerance of SURVEY 8(c): 1e-3 (fp16) / 1e-2 (bf16) relative, P rounded once more
+    assert np.abs(got - ref).max() <= tol * max(np.abs(ref).max(), 1e-3), np.abs(got - ref).max() / np.abs(ref).max()
+
+
 def test_error_reporting(K):
     import torch
     from infinitensor_b200 import _lib as L

@@ -527,3 +527,27 @@ def test_depth_to_space_shapes_and_oracle(B):
     oh.run()
     assert np.array_equal(np.asarray(y.f32()).reshape(want.shape), want)
     del x
+
+
+def test_prefill_attention_schedule(B, monkeypatch):
+    """GPT-2's attention block -- Transpose(k) -> MatMul -> Div -> Add(mask) -> Softmax -> MatMul -- becomes ONE PrefillAttention
+    step per layer for f16 / bf16; fp32 graphs, 32-wide heads and ITB_FUSION_MASK without bit 8 keep the operators."""
+    from infinitensor_b200 import graphs as G
+    rt = B.HostPlanRuntime()
+    cfg = G.GPT2Config(layers=2, d_model=128, heads=2, ffn=256, vocab=500, n_pos=64, seq=16, batch=1, dtype=10)
+    h = B.GraphHandler(rt)
+    G.build_gpt2(h, cfg)
+    sc = h.schedule()
+    assert sc.count("PrefillAttention:Transpose+MatMul+Div+Add+Softmax+MatMul") == 2, sc
+    assert not any(s in ("Single:Softmax", "Single:Div") for s in sc)
+    h.data_malloc()
+    h32 = B.GraphHandler(rt)
+    G.build_gpt2(h32, G.GPT2Config(layers=1, d_model=128, heads=2, ffn=256, vocab=500, n_pos=64, seq=16, batch=1, dtype=1))
+    assert not any(s.startswith("PrefillAttention") for s in h32.schedule())
+    hs = B.GraphHandler(rt)
+    G.build_gpt2(hs, G.GPT2Config.tiny(10))  # 32-wide heads: not taken by the tensor-core kernel
+    assert not any(s.startswith("PrefillAttention") for s in hs.schedule())
+    monkeypatch.setenv("ITB_FUSION_MASK", "127")
+    hm = B.GraphHandler(rt)
+    G.build_gpt2(hm, cfg)
+    assert not any(s.startswith("PrefillAttention") for s in hm.schedule())
