@@ -52,8 +52,10 @@ void it_b200_tune_skinny(int nb, int splitk);
 
 /* ---- unary family: replaces unary.cu:31-143 + ActivationCudnn (unary.cc:70-122) ---- */
 enum { ITB_RELU = 0, ITB_SIGMOID, ITB_TANH, ITB_GELU, ITB_SILU, ITB_ERF, ITB_NEG, ITB_ABS,
-       ITB_SQRT, ITB_HARDSIGMOID, ITB_HARDSWISH, ITB_EXP };
+       ITB_SQRT, ITB_HARDSIGMOID, ITB_HARDSWISH, ITB_EXP, ITB_LEAKYRELU, ITB_ELU };
 int it_b200_unary(int op, int dtype, const void *x, void *y, int64_t n, void *stream);
+/* LeakyRelu (x > 0 ? x : alpha x; unary.cu:157-165) and Elu (x >= 0 ? x : alpha (exp x - 1); unary.cu:97-106) carry `alpha` */
+int it_b200_unary_alpha(int op, int dtype, const void *x, void *y, int64_t n, float alpha, void *stream);
 
 /* ---- binary with full numpy broadcast (rank <= 8): replaces ElementWiseCudnn
  *      (element_wise.cc:8-121) and element_wise.cu:9-131.  strides in elements, 0 = broadcast.

@@ -35,6 +35,7 @@ _SIGS = {
     "it_b200_tune_skinny": (None, [c_int, c_int]),
     "it_b200_launch_count": (c_longlong, []),
     "it_b200_unary": (c_int, [c_int, c_int, vp, vp, c_int64, vp]),
+    "it_b200_unary_alpha": (c_int, [c_int, c_int, vp, vp, c_int64, c_float, vp]),
     "it_b200_binary": (c_int, [c_int, c_int, vp, vp, vp, c_int, i64p, i64p, i64p, vp]),
     "it_b200_cast": (c_int, [c_int, c_int, vp, vp, c_int64, vp]),
     "it_b200_where": (c_int, [c_int, vp, vp, vp, vp, c_int, i64p, i64p, i64p, i64p, vp]),

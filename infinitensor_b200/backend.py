@@ -402,6 +402,12 @@ class GraphHandler:
     def unsqueeze(self, input, output, axes):
         return self._op1("Unsqueeze", [input], output, list(axes))
 
+    def leakyRelu(self, input, output, alpha):
+        return self._op1("LeakyRelu", [input], output, [], [float(alpha)])
+
+    def elu(self, input, output, alpha):
+        return self._op1("Elu", [input], output, [], [float(alpha)])
+
     def depthToSpace(self, input, output, blocksize, mode):
         if isinstance(mode, bytes):
             mode = mode.decode()

@@ -241,6 +241,8 @@ static Operator build_op(itb_graph *h, const string &name, const TensorVec &in, 
                                       (int)I(0, -1), (int)I(1, 1));
     case OpType::RMSNorm: need(2); return g->addOp<RMSNormObj>(in[0], in[1], o0);
     case OpType::RoPE: need(2); return g->addOp<RoPEObj>(in[0], in[1], o0);
+    case OpType::LeakyRelu: need(1); return g->addOp<LeakyReluObj>(in[0], o0, (float)F(0, 0.01));
+    case OpType::Elu: need(1); return g->addOp<EluObj>(in[0], o0, (float)F(0, 1.0));
     case OpType::Relu: case OpType::Sigmoid: case OpType::Tanh: case OpType::Gelu: case OpType::Silu:
     case OpType::Erf: case OpType::Neg: case OpType::Abs: case OpType::Sqrt: case OpType::HardSigmoid:
     case OpType::HardSwish: case OpType::Exp: case OpType::Identity:

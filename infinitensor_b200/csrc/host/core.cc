@@ -21,8 +21,8 @@ const DataType DataType::Undefine(0), DataType::Float32(1), DataType::UInt8(2), 
 static const char *kOpNames[] = {
     "Unknown", "Abs", "Add", "AllGather", "AllReduceAvg", "AllReduceMax", "AllReduceMin", "AllReduceProd",
     "AllReduceSum", "AttentionKVCache", "AveragePool", "BatchNormalization", "Cast", "Concat", "Conv",
-    "DepthToSpace", "Div", "Equal", "Erf", "Exp", "Expand", "Flatten", "Gather", "Gelu", "Greater", "HardSigmoid",
-    "HardSwish", "Identity", "LayerNormalization", "Less", "MatMul", "Max", "MaxPool", "Min", "Mul", "Neg", "Pad",
+    "DepthToSpace", "Div", "Elu", "Equal", "Erf", "Exp", "Expand", "Flatten", "Gather", "Gelu", "Greater", "HardSigmoid",
+    "HardSwish", "Identity", "LayerNormalization", "LeakyRelu", "Less", "MatMul", "Max", "MaxPool", "Min", "Mul", "Neg", "Pad",
     "Pow", "RMSNorm", "ReduceMean", "ReduceSum", "Relu", "Reshape", "RoPE", "Sigmoid", "Silu", "Slice", "Softmax",
     "Split", "Sqrt", "Squeeze", "Sub", "Tanh", "Transpose", "Unsqueeze", "Where"};
 static_assert(sizeof(kOpNames) / sizeof(kOpNames[0]) == OpType::NumOpTypes, "op name table out of sync");

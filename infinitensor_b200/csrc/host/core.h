@@ -87,8 +87,8 @@ struct OpType {
     using underlying_t = uint16_t;
     enum : underlying_t {
         Unknown, Abs, Add, AllGather, AllReduceAvg, AllReduceMax, AllReduceMin, AllReduceProd, AllReduceSum,
-        AttentionKVCache, AveragePool, BatchNormalization, Cast, Concat, Conv, DepthToSpace, Div, Equal, Erf, Exp,
-        Expand, Flatten, Gather, Gelu, Greater, HardSigmoid, HardSwish, Identity, LayerNormalization, Less, MatMul,
+        AttentionKVCache, AveragePool, BatchNormalization, Cast, Concat, Conv, DepthToSpace, Div, Elu, Equal, Erf, Exp,
+        Expand, Flatten, Gather, Gelu, Greater, HardSigmoid, HardSwish, Identity, LayerNormalization, LeakyRelu, Less, MatMul,
         Max, MaxPool, Min, Mul, Neg, Pad, Pow, RMSNorm, ReduceMean, ReduceSum, Relu, Reshape, RoPE, Sigmoid, Silu,
         Slice, Softmax, Split, Sqrt, Squeeze, Sub, Tanh, Transpose, Unsqueeze, Where, NumOpTypes
     } type;

@@ -131,6 +131,20 @@ DEFINE_UNARY_OBJ(Neg, OpType::Neg)
 DEFINE_UNARY_OBJ(Erf, OpType::Erf)
 DEFINE_UNARY_OBJ(Exp, OpType::Exp)
 DEFINE_UNARY_OBJ(Identity, OpType::Identity)
+// unary operators with a slope (reference include/operators/unary.h:50-62, 248-261)
+class LeakyReluObj : public UnaryObj {
+    float alphaValue;
+
+  public:
+    LeakyReluObj(GraphObj *graph, Tensor input, Tensor output, float alpha) : UnaryObj(OpType::LeakyRelu, graph, input, output), alphaValue(alpha) {}
+    float getAlpha() const { return alphaValue; }
+};
+class EluObj : public UnaryObj {
+  public:
+    float alpha;
+    EluObj(GraphObj *graph, Tensor input, Tensor output, float alpha) : UnaryObj(OpType::Elu, graph, input, output), alpha(alpha) {}
+    float getAlpha() const { return alpha; }
+};
 
 class ElementWiseObj : public OperatorObj {
   public:
@@ -327,6 +341,14 @@ class PoolingObj : public OperatorObj {
                int pw, int sh, int sw, int ceilMode);
     std::optional<vector<Shape>> inferShape(const TensorVec &inputs) override;
     auto getKDPS() const { return std::tuple{kh, kw, dh, dw, ph, pw, sh, sw}; }
+    int getKh() const { return kh; }
+    int getKw() const { return kw; }
+    int getDh() const { return dh; }
+    int getDw() const { return dw; }
+    int getPh() const { return ph; }
+    int getPw() const { return pw; }
+    int getSh() const { return sh; }
+    int getSw() const { return sw; }
     int getCeilMode() const { return ceilMode; }
 };
 class MaxPoolObj : public PoolingObj {

@@ -26,6 +26,7 @@
 namespace itb {
 
 constexpr int AP_BQ = 128, AP_BK = 128;
+constexpr int AP_MPAD = AP_BQ + 2;  // 65 words per key column: the transposing store hits 32 distinct banks
 
 struct ApArgs {
     int BH, H, Sq, Skv, D;
@@ -47,6 +48,9 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
     extern __shared__ uint8_t ap_smem_raw[];
     uint8_t *smem = ap_smem_raw + ((1024u - (smem_u32(ap_smem_raw) & 1023u)) & 1023u);
     uint8_t *q_sm = smem, *k_sm = q_sm + QK_BYTES, *v_sm = k_sm + QK_BYTES, *p_sm = v_sm + V_BYTES;
+    // the mask tile of the running (query tile, key tile), TRANSPOSED and padded: m_sm[j * AP_MPAD + i] -- every thread reads its own
+    // query row i for consecutive keys j (lanes = consecutive i: conflict-free), the cooperative fill writes with lanes = keys
+    T *m_sm = reinterpret_cast<T *>(p_sm + P_BYTES);
     __shared__ __align__(8) uint64_t bar_load, bar_mma;
     __shared__ uint32_t tmem_slot;
 
@@ -86,7 +90,26 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
     float sc = 1.f;
     if (a.scale) sc = to_f(*(const T *)a.scale);
     const int b = bh / a.H, h = bh % a.H;
-    const T *mrow = a.mask ? (const T *)a.mask + b * a.mb + h * a.mh + (int64_t)(q0 + row) * a.mi : nullptr;
+    const T *mbase = a.mask ? (const T *)a.mask + b * a.mb + h * a.mh : nullptr;
+    const bool mvec = mbase && a.mj == 1 && (a.mi & 7) == 0 && (((uintptr_t)mbase & 15) == 0);
+    // cooperative, coalesced fill of the mask tile (rows q0.., keys j0..): 16 threads cover one row's 128 keys with 16-byte loads
+    auto load_mask = [&](int j0) {
+        if (!mbase) return;
+        const int jc = (threadIdx.x & 15) * 8, r0 = threadIdx.x >> 4;
+        for (int r = r0; r < AP_BQ; r += 8) {
+            T vals[8];
+            const bool rok = q0 + r < a.Sq;
+            const T *src = mbase + (int64_t)(q0 + r) * a.mi + (int64_t)(j0 + jc) * a.mj;
+            if (rok && mvec && j0 + jc + 8 <= a.Skv && ((((int64_t)(q0 + r) * a.mi + j0 + jc) & 7) == 0)) {
+                *reinterpret_cast<uint4 *>(vals) = *reinterpret_cast<const uint4 *>(src);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) vals[e] = (rok && j0 + jc + e < a.Skv) ? src[(int64_t)e * a.mj] : from_f<T>(0.f);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) m_sm[(jc + e) * AP_MPAD + r] = vals[e];
+        }
+    };
     const bool row_ok = q0 + row < a.Sq;
     const int ntiles = (a.Skv + AP_BK - 1) / AP_BK;
 
@@ -94,7 +117,7 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
     auto score = [&](float acc, int j) -> float {
         float s = round_t<T>(acc);                                      // MatMul output
         if (a.scale) s = round_t<T>(a.scale_is_div ? s / sc : s * sc);  // Div / Mul by the scalar constant
-        if (mrow && row_ok) s = round_t<T>(s + to_f(mrow[(int64_t)j * a.mj]));  // Add(mask)
+        if (mbase && row_ok) s = round_t<T>(s + to_f(m_sm[(j % AP_BK) * AP_MPAD + row]));  // Add(mask)
         return s;
     };
     auto load_k = [&](int t) {
@@ -121,13 +144,15 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
     float m = -INFINITY, l = 0.f;
     for (int t = 0; t < ntiles; ++t) {
         load_k(t);
+        const int j0 = t * AP_BK;
+        load_mask(j0);  // (the previous tile's readers are behind the __syncthreads that closed it)
         mbar_wait(&bar_load, ph_load);
         ph_load ^= 1;
         mma_s();
+        __syncthreads();  // mask tile complete
         mbar_wait(&bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        const int j0 = t * AP_BK;
 #pragma unroll 1
         for (int c0 = 0; c0 < AP_BK; c0 += 16) {
             uint32_t v[16];
@@ -163,13 +188,15 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
                 for (int hh = 0; hh < 2; ++hh)
                     tma_load_3d(v_sm + g * (AP_BK * 128) + hh * (64 * 128), &mapV, &bar_load, g * 64, t * AP_BK + hh * 64, bh, pol);
         }
+        const int j0 = t * AP_BK;
+        load_mask(j0);  // (every reader of the previous tile's mask passed the __syncthreads before that tile's P.V)
         mbar_wait(&bar_load, ph_load);
         ph_load ^= 1;
         mma_s();
+        __syncthreads();  // mask tile complete
         mbar_wait(&bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        const int j0 = t * AP_BK;
 #pragma unroll 1
         for (int c0 = 0; c0 < AP_BK; c0 += 16) {
             uint32_t v[16];
@@ -238,7 +265,7 @@ static int launch_ap(const void *q, const void *k, const void *v, const ApArgs &
         !make_tma_3d_b16(&mk, k, (uint64_t)a.BH, (uint64_t)a.Skv, (uint64_t)D, (uint64_t)D, (uint64_t)a.Skv * D, AP_BK, 64) ||
         !make_tma_3d_b16(&mv, v, (uint64_t)a.BH, (uint64_t)a.Skv, (uint64_t)D, (uint64_t)D, (uint64_t)a.Skv * D, 64, 64))
         ITB_FAIL("attention_prefill: cuTensorMapEncodeTiled failed");
-    const int smem = 2 * AP_BQ * D * 2 + AP_BK * D * 2 + AP_BQ * AP_BK * 2 + 1024;
+    const int smem = 2 * AP_BQ * D * 2 + AP_BK * D * 2 + AP_BQ * AP_BK * 2 + AP_BK * AP_MPAD * 2 + 1024;
     auto kern = attention_prefill_kernel<T, D>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     ITB_CHECK(e == cudaSuccess, "attention_prefill: smem attribute: %s", cudaGetErrorString(e));

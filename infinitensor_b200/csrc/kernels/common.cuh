@@ -95,7 +95,10 @@ template <typename T> __device__ __forceinline__ float round_t(float v) { return
 
 // inference BatchNorm arithmetic, spelled with intrinsics so the stand-alone kernel and the conv epilogue round alike:
 //   y = scale * (x - mean) * rs + bias,  rs = 1 / sqrt(var + eps)      (reference batch_norm.cc:9-69 via cuDNN)
-__device__ __forceinline__ float bn_rs(float var, float eps) { return 1.0f / sqrtf(var + eps); }
+//   rs as the hardware reciprocal square root (what cudnnBatchNormalizationForwardInference evaluates): the reference's own
+//   golden vector (test_cuda_batch_norm.cc:49-52: (8 - 9) / sqrt(9) expected "-0.333333" within its relative 1e-6) holds for
+//   rsqrt(9) = 0.33333331 and NOT for the correctly rounded 1 / sqrt(9) = 0.33333334
+__device__ __forceinline__ float bn_rs(float var, float eps) { return rsqrtf(var + eps); }
 __device__ __forceinline__ float bn_apply(float x, float mean, float rs, float scale, float bias) {
     return __fmaf_rn(__fmul_rn(scale, __fsub_rn(x, mean)), rs, bias);
 }

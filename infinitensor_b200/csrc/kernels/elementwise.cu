@@ -12,7 +12,7 @@
 
 namespace itb {
 
-__device__ __forceinline__ float apply_unary(int op, float v) {
+__device__ __forceinline__ float apply_unary(int op, float v, float alpha = 0.f) {
     switch (op) {
     case ITB_RELU: return v > 0.f ? v : 0.f;
     case ITB_SIGMOID: return 1.f / (1.f + expf(-v));
@@ -26,13 +26,15 @@ __device__ __forceinline__ float apply_unary(int op, float v) {
     case ITB_HARDSIGMOID: return fmaxf(0.f, fminf(1.f, 0.2f * v + 0.5f));
     case ITB_HARDSWISH: return v * fmaxf(0.f, fminf(1.f, (1.f / 6.f) * v + 0.5f));
     case ITB_EXP: return expf(v);
+    case ITB_LEAKYRELU: return v > 0.f ? v : alpha * v;              // unary.cu:157-165
+    case ITB_ELU: return v >= 0.f ? v : alpha * (expf(v) - 1.f);     // unary.cu:97-106
     }
     return v;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) unary_kernel(int op, const T *__restrict__ x, T *__restrict__ y,
-                                                    int64_t n, bool vec) {
+                                                    int64_t n, bool vec, float alpha) {
     pdl_trigger();
     pdl_wait();
     constexpr int V = Vec16<T>::N;
@@ -43,12 +45,12 @@ __global__ void __launch_bounds__(256) unary_kernel(int op, const T *__restrict_
         for (int64_t i = tid; i < nv; i += nthreads) {
             Vec16<T> a = ld16_stream(x + i * V), r;
 #pragma unroll
-            for (int j = 0; j < V; ++j) r.v[j] = from_f<T>(apply_unary(op, to_f(a.v[j])));
+            for (int j = 0; j < V; ++j) r.v[j] = from_f<T>(apply_unary(op, to_f(a.v[j]), alpha));
             st16(y + i * V, r);
         }
-        for (int64_t i = nv * V + tid; i < n; i += nthreads) y[i] = from_f<T>(apply_unary(op, to_f(x[i])));
+        for (int64_t i = nv * V + tid; i < n; i += nthreads) y[i] = from_f<T>(apply_unary(op, to_f(x[i]), alpha));
     } else {
-        for (int64_t i = tid; i < n; i += nthreads) y[i] = from_f<T>(apply_unary(op, to_f(x[i])));
+        for (int64_t i = tid; i < n; i += nthreads) y[i] = from_f<T>(apply_unary(op, to_f(x[i]), alpha));
     }
 }
 
@@ -238,17 +240,21 @@ __global__ void __launch_bounds__(256) expand_kernel(const E *__restrict__ x, E 
 
 using namespace itb;
 
-extern "C" int it_b200_unary(int op, int dtype, const void *x, void *y, int64_t n, void *stream) {
-    ITB_CHECK(op >= ITB_RELU && op <= ITB_EXP, "unary: bad op %d", op);
+extern "C" int it_b200_unary_alpha(int op, int dtype, const void *x, void *y, int64_t n, float alpha, void *stream) {
+    ITB_CHECK(op >= ITB_RELU && op <= ITB_ELU, "unary: bad op %d", op);
     if (n == 0) return 0;
     auto st = (cudaStream_t)stream;
     ITB_DISPATCH_FLOAT(dtype, "unary", {
         bool vec = aligned16(x) && aligned16(y);
         int64_t items = vec ? (n + Vec16<T>::N - 1) / Vec16<T>::N : n;
-        launch_k(unary_kernel<T>, dim3(grid_for(items, 256)), dim3(256), 0, st, op, (const T *)x, (T *)y, n, vec);
+        launch_k(unary_kernel<T>, dim3(grid_for(items, 256)), dim3(256), 0, st, op, (const T *)x, (T *)y, n, vec, alpha);
     });
     ITB_LAUNCH_CHECK("unary");
     return 0;
+}
+extern "C" int it_b200_unary(int op, int dtype, const void *x, void *y, int64_t n, void *stream) {
+    ITB_CHECK(op >= ITB_RELU && op <= ITB_EXP, "unary: bad op %d", op);
+    return it_b200_unary_alpha(op, dtype, x, y, n, 0.f, stream);
 }
 
 extern "C" int it_b200_silu_mul(int dtype, const void *gate, const void *up, void *out, int64_t n, void *stream) {

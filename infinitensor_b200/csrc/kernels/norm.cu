@@ -274,6 +274,31 @@ __global__ void __launch_bounds__(256) rope_kernel(const P *__restrict__ pos, co
     }
 }
 
+// dim_model not a multiple of dim_head (the reference's own golden test runs dim_model = 32 against its hard-coded 128-wide
+// heads, test_cuda_rope.cc:17-35 / rope.cc:25): one thread per column; a rotation partner beyond the row counts as 0 (the
+// reference reads out of bounds there, quirk q2 -- its expected values are the cosines, i.e. partner = 0)
+template <typename T, typename P>
+__global__ void __launch_bounds__(256) rope_ragged_kernel(const P *__restrict__ pos, const T *__restrict__ x,
+                                                          T *__restrict__ y, int64_t rows, int dim_model, int dim_head) {
+    pdl_trigger();
+    pdl_wait();
+    const int half = dim_head >> 1;
+    const int64_t total = rows * dim_model;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / dim_model;
+        const int col = (int)(i - row * dim_model);
+        const int j = col % dim_head, c = j % half;
+        const bool lo = j < half;
+        const int pcol = lo ? col + half : col - half;
+        const float p = (float)(int)pos[row];
+        const float freq = p * powf(10000.f, -(float)(c * 2) / (float)dim_head);
+        const float cs = round_t<T>(cosf(freq)), sn = round_t<T>(sinf(freq));
+        const float xv = to_f(x[row * dim_model + col]), xp = pcol < dim_model ? to_f(x[row * dim_model + pcol]) : 0.f;
+        const float o = lo ? round_t<T>(xv * cs) - round_t<T>(xp * sn) : round_t<T>(xv * cs) + round_t<T>(xp * sn);
+        y[row * dim_model + col] = from_f<T>(o);
+    }
+}
+
 }  // namespace itb
 
 using namespace itb;
@@ -331,12 +356,23 @@ extern "C" int it_b200_rmsnorm_constw(int dtype, const void *x, const void *w, v
 
 extern "C" int it_b200_rope(int dtype, const void *pos, int pos_dtype, const void *x, void *y, int B, int S,
                             int dim_model, int dim_head, void *stream) {
-    ITB_CHECK(dim_head > 0 && dim_head % 2 == 0 && dim_model % dim_head == 0,
-              "rope: dim_model %d must be a multiple of dim_head %d", dim_model, dim_head);
+    ITB_CHECK(dim_head > 0 && dim_head % 2 == 0, "rope: dim_head %d must be even", dim_head);
     int64_t rows = (int64_t)B * S;
     if (rows == 0) return 0;
     int64_t total = rows * (dim_model / 2);
     auto st = (cudaStream_t)stream;
+    if (dim_model % dim_head != 0) {
+        ITB_CHECK(pos_dtype == ITB_I64 || pos_dtype == ITB_I32 || pos_dtype == ITB_U32, "rope: unsupported position dtype %d", pos_dtype);
+        ITB_DISPATCH_FLOAT(dtype, "rope", {
+            int g = grid_for(rows * dim_model, 256);
+            if (pos_dtype == ITB_I64)
+                launch_k(rope_ragged_kernel<T, int64_t>, dim3(g), dim3(256), 0, st, (const int64_t *)pos, (const T *)x, (T *)y, rows, dim_model, dim_head);
+            else
+                launch_k(rope_ragged_kernel<T, int32_t>, dim3(g), dim3(256), 0, st, (const int32_t *)pos, (const T *)x, (T *)y, rows, dim_model, dim_head);
+        });
+        ITB_LAUNCH_CHECK("rope");
+        return 0;
+    }
     ITB_DISPATCH_FLOAT(dtype, "rope", {
         int g = grid_for(total, 256);
         if (pos_dtype == ITB_I64)

@@ -189,6 +189,18 @@ def unary(name, x, dt=F32):
     return y
 
 
+def unary_alpha(name, x, alpha, dt=F32):
+    """LeakyRelu: x > 0 ? x : alpha * x (reference unary.cu:157-165); Elu: x >= 0 ? x : alpha * (expf(x) - 1) (unary.cu:97-106);
+    fp32 arithmetic on the (already rounded) inputs, one rounding to the storage type."""
+    x = _f32c(x)
+    a = np.float32(alpha)
+    if name == "leakyrelu":
+        y = np.where(x > 0, x, a * x)
+    else:
+        y = np.where(x >= 0, x, a * (np.exp(x, dtype=np.float32) - np.float32(1)))
+    return round_to(y.astype(np.float32), dt)
+
+
 def _bstrides(shape, out_shape):
     r = len(out_shape)
     shape = (1,) * (r - len(shape)) + tuple(shape)

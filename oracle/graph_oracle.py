@@ -154,6 +154,14 @@ class OracleHandler:
         out = self._out(y, x.dims, x.dt)
         return self._rec(lambda: O.unary(name, x.value, x.dt), [x], [out])
 
+    def leakyRelu(self, x, y, alpha):
+        out = self._out(y, x.dims, x.dt)
+        return self._rec(lambda: O.unary_alpha("leakyrelu", x.value, alpha, x.dt), [x], [out])
+
+    def elu(self, x, y, alpha):
+        out = self._out(y, x.dims, x.dt)
+        return self._rec(lambda: O.unary_alpha("elu", x.value, alpha, x.dt), [x], [out])
+
     def relu(self, x, y): return self._unary("relu", x, y)
     def silu(self, x, y): return self._unary("silu", x, y)
     def gelu(self, x, y): return self._unary("gelu", x, y)

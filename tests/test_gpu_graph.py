@@ -161,6 +161,33 @@ def test_resnet_parity(dtype):
     assert np.abs(got - ref).max() / np.abs(ref).max() < tol
 
 
+def test_resnet50_full_width_config4():
+    """BASELINE config C4 at FULL width and depth -- ResNet-50 (3-4-6-3 bottlenecks, 64..2048 channels, 224 x 224, 1000 classes),
+    fp16, batch 8 (the oracle's CPU convolutions stay within a minute; every conv / GEMM shape is the B = 64 one except the batch
+    fold) -- through the fused schedule (Conv+BN(+Add)(+ReLU) in the tcgen05 epilogue) against the CPU oracle executing the
+    operator graph, plus top-1 agreement."""
+    from infinitensor_b200 import backend as B, graphs as G
+    from oracle.graph_oracle import OracleHandler
+    cfg = G.ResNetConfig(batch=8)
+    rt = B.CudaRuntime(0)
+    h, oh = B.GraphHandler(rt), OracleHandler()
+    g, og = G.build_resnet50(h, cfg), G.build_resnet50(oh, cfg)
+    assert sum(s.startswith("ConvBnAct") for s in h.schedule()) == 53
+    h.data_malloc()
+    G.fill_resnet_weights_host(g)
+    G.fill_resnet_weights_host(og)
+    x = np.random.default_rng(3).standard_normal((cfg.batch, 3, cfg.image, cfg.image)).astype(np.float32)
+    g.input.copyin_numpy(G.to_storage(x, F16))
+    og.input.copyin_numpy(G.to_storage(x, F16))
+    h.run_with_cudagraph()
+    oh.run()
+    got = G.from_storage(g.out.copyout_numpy(), F16).astype(np.float64)
+    ref = og.out.f32().astype(np.float64)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 2e-2, err  # 53 fp16 convolutions deep: the per-op 1e-3 of SURVEY 8(c), accumulated
+    assert (got.argmax(-1) == ref.argmax(-1)).mean() >= 0.75
+
+
 def test_cudagraph_cache_semantics():
     """capture once / replay / invalidate on storage change / LRU (reference test/cuda/test_cudagraph.cc:80-320)."""
     from infinitensor_b200 import backend as B

@@ -513,6 +513,28 @@ def test_attention_prefill_parity(K, B, H, Sq, Skv, D, masked, div, dt):
     assert np.abs(got - ref).max() <= tol * max(np.abs(ref).max(), 1e-3), np.abs(got - ref).max() / np.abs(ref).max()
 
 
+@pytest.mark.parametrize("dt", [F32, F16, BF16])
+def test_leaky_relu_elu_parity(K, dt):
+    """LeakyRelu / Elu (reference unary.cu:97-106, 157-165; golden cases of test_cuda_unary.cc: alpha 0.1 / 1.0)."""
+    import torch
+    from infinitensor_b200 import _lib as L
+    x = rnd((3, 1000), 70, dt, 2.0)
+    xd = K.dev(x, dt)
+    for op, name, alpha in ((12, "leakyrelu", 0.1), (13, "elu", 1.0), (13, "elu", 0.5)):
+        y = torch.empty_like(xd)
+        L.check(L.lib.it_b200_unary_alpha(op, dt, K.ptr(xd), K.ptr(y), xd.numel(), alpha, K.stream()))
+        K.sync()
+        ref = oracle.unary_alpha(name, x, alpha, dt)
+        close(K.host(y), ref, 4 * EPS[dt] if dt != F32 else 2e-6, 1e-6)
+
+
+def test_rope_partial_head_golden(K):
+    """the reference's RoPE known-answer test as written: dim_model = 32 under 128-wide heads (test_cuda_rope.cc:17-35)."""
+    x = np.ones((1, 1, 32), np.float32)
+    out = K.rope(np.array([[1]]), x, pos_np_dtype=np.uint32)
+    close(out[0, 0], G.ROPE_COS, 2e-6, 1e-6)
+
+
 def test_error_reporting(K):
     import torch
     from infinitensor_b200 import _lib as L
