@@ -171,6 +171,18 @@ int it_b200_matmul(int dtype, const void *A, const void *B, const void *bias, vo
 int it_b200_matmul_grouped(int dtype, const void *X, int n_groups, const void *const *W, void *const *C,
                            const int *N, int m, int k, void *stream);
 
+/* ---- Weight-only FP8 (no counterpart in the reference, whose only quantised op is the int8 Cast, unary.cc:30-68).
+ *      Wq_i [K, N_i]: FP8 E4M3 (OCP "FN": 1-4-3, bias 7, max 448, no inf) codes, one byte each, row-major like the 16-bit weights;
+ *      scale_i [N_i] f32 per output column.  C_i[m, N_i] = X[m, K] . (Wq_i * scale_i): the codes are converted to the
+ *      activation type inside the GEMM main loop (exact), the column scale multiplies the fp32 sum in the epilogue; halves the
+ *      HBM bytes of a decode GEMM.  1..4 matrices sharing X per launch; residual (single matrix only, may be NULL) is added
+ *      after the product has been rounded, like MatMul -> Add.  m <= 64, K % 16 == 0, N_i % 16 == 0.
+ *      it_b200_dequantize_fp8 is the stand-alone DequantizeLinear (y = T(e4m3(xq) * scale[col])) of the unfused graph. ---- */
+int it_b200_matmul_fp8w(int dtype, const void *X, int n_groups, const void *const *Wq, const float *const *scale,
+                        void *const *C, const int *N, int m, int k, const void *residual, void *stream);
+int it_b200_dequantize_fp8(int dtype_out, const void *xq, const float *scale, void *y, int64_t rows, int64_t cols,
+                           void *stream);
+
 /* ---- SiLU(gate) * up in one pass (the fused form of Silu -> Mul; the Silu result is rounded to the storage
  *      dtype before the multiply, exactly as the two separate kernels would). ---- */
 int it_b200_silu_mul(int dtype, const void *gate, const void *up, void *out, int64_t n, void *stream);

@@ -50,7 +50,8 @@ class ActType(enum.IntEnum):  # reference export_values: Linear/Relu/Sigmoid/Tan
 
 
 _NP = {1: np.float32, 2: np.uint8, 3: np.int8, 4: np.uint16, 5: np.int16, 6: np.int32, 7: np.int64, 9: np.bool_,
-       10: np.float16, 11: np.float64, 12: np.uint32, 13: np.uint64, 16: np.uint16}  # bf16 travels as raw uint16
+       10: np.float16, 11: np.float64, 12: np.uint32, 13: np.uint64, 16: np.uint16,  # bf16 travels as raw uint16
+       17: np.uint8}  # FP8 E4M3 codes
 
 _h = c_void_p
 _sig = {
@@ -345,8 +346,11 @@ class GraphHandler:
     def conv(self, input, weight, output, ph, pw, sh, sw, dh, dw):
         return self._op1("Conv", [input, weight], output, [ph, pw, sh, sw, dh, dw])
 
-    def matmul(self, a, b, y, transA, transB, bias, act, matmul_compute_type="default"):
-        return self._op1("MatMul", [a, b] + ([bias] if bias is not None else []), y, [int(transA), int(transB), int(act)])
+    def matmul(self, a, b, y, transA, transB, bias, act, matmul_compute_type="default", w_scale=None):
+        """w_scale (extension, SURVEY 8(f-4)): `b` holds FP8 E4M3 codes (dtype 17) [K, N] and w_scale is its f32 per-column scale;
+        the product is X . (codes * scale), dequantised inside the GEMM."""
+        ins = [a, b] + ([bias] if bias is not None else []) + ([w_scale] if w_scale is not None else [])
+        return self._op1("MatMul", ins, y, [int(transA), int(transB), int(act), 1 if w_scale is not None else 0])
 
     def batchNormalization(self, input, output, mean, var, scale, bias, momentum, eps, training):
         return self._op1("BatchNormalization", [input, mean, var, scale, bias], output, [int(training)], [momentum, eps])

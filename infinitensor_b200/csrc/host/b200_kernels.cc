@@ -393,6 +393,19 @@ void runMatmul(const Operator &_op, const RuntimeObj *ctx, const Tensor &residua
         if (residual) act |= ITB_ACT_ROUND_BEFORE_BIAS;
     }
     if (B->isWeight()) act |= ITB_MATMUL_B_CONST;
+#ifndef ITB_SEAM_A
+    if (auto ws = op->getWScale()) {
+        // FP8 E4M3 weight, dequantised inside the GEMM (decode shapes: the skinny kernel); bias only as the fused residual
+        IT_ASSERT(!op->getBias() && !op->getTransA() && !op->getTransB() && bb == 1, "MatMul(fp8 weight): plain [.., K] x [K, N] only");
+        const int rows = (int)((int64_t)b * m);
+        const void *W[1] = {P(B)};
+        const float *Sc[1] = {ws->getRawDataPtr<float *>()};
+        void *Cp[1] = {P(C)};
+        int N[1] = {n};
+        CK(it_b200_matmul_fp8w(DTI(A), P(A), 1, W, Sc, Cp, N, rows, k, residual ? P(residual) : nullptr, S()), _op);
+        return;
+    }
+#endif
     // [b, m, k] x [k, n] with the weight broadcast over the batch (how the frontend emits every Linear layer of a
     // decode step: b = batch, m = 1) is ONE GEMM with M = b*m -- the reference instead runs b strided-batched GEMMs
     // with stride 0 (matmul.cc:124-168)
@@ -420,10 +433,16 @@ void runMatmulGroup(const OpVec &ops, const RuntimeObj *) {
     void *C[4];
     int N[4];
     IT_ASSERT(ops.size() <= 4);
+    const float *Sc[4] = {nullptr, nullptr, nullptr, nullptr};
     for (size_t i = 0; i < ops.size(); ++i) {
         W[i] = P(ops[i]->getInputs(1));
         C[i] = P(ops[i]->getOutput());
         N[i] = as<MatmulObj>(ops[i])->getN();
+        if (auto ws = as<MatmulObj>(ops[i])->getWScale()) Sc[i] = ws->getRawDataPtr<float *>();
+    }
+    if (Sc[0]) {  // FP8 weights (the schedule groups like with like)
+        CK(it_b200_matmul_fp8w(DTI(A), P(A), (int)ops.size(), W, Sc, C, N, (int)rows, k, nullptr, S()), ops[0]);
+        return;
     }
     CK(it_b200_matmul_grouped(DTI(A), P(A), (int)ops.size(), W, C, N, (int)rows, k, S()), ops[0]);
 }

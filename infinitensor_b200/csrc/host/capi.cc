@@ -225,8 +225,13 @@ static Operator build_op(itb_graph *h, const string &name, const TensorVec &in, 
     switch (t.underlying()) {
     case OpType::MatMul:
         need(2);
-        return g->addOp<MatmulObj>(in[0], in[1], o0, (bool)I(0), (bool)I(1), in.size() > 2 ? in[2] : nullptr,
-                                   (ActType)I(2), "default");
+    {
+        const bool scaled = I(3, 0) != 0;  // extension: the last input is the FP8 weight's per-column scale
+        need(scaled ? 3 : 2);
+        const size_t nb = in.size() - (scaled ? 1 : 0);
+        return g->addOp<MatmulObj>(in[0], in[1], o0, (bool)I(0), (bool)I(1), nb > 2 ? in[2] : nullptr, (ActType)I(2), "default",
+                                   scaled ? in.back() : nullptr);
+    }
     case OpType::Conv:
         need(2);
         return g->addOp<ConvObj>(in[0], in[1], o0, (int)I(0), (int)I(1), (int)I(2, 1), (int)I(3, 1), (int)I(4, 1),

@@ -16,7 +16,7 @@ namespace infini {
 const DataType DataType::Undefine(0), DataType::Float32(1), DataType::UInt8(2), DataType::Int8(3),
     DataType::UInt16(4), DataType::Int16(5), DataType::Int32(6), DataType::Int64(7), DataType::String(8),
     DataType::Bool(9), DataType::Float16(10), DataType::Double(11), DataType::UInt32(12), DataType::UInt64(13),
-    DataType::BFloat16(16);
+    DataType::BFloat16(16), DataType::Float8E4M3FN(17);
 
 static const char *kOpNames[] = {
     "Unknown", "Abs", "Add", "AllGather", "AllReduceAvg", "AllReduceMax", "AllReduceMin", "AllReduceProd",

@@ -61,20 +61,20 @@ class DataType {
 
   public:
     static const DataType Undefine, Float32, UInt8, Int8, UInt16, Int16, Int32, Int64, String, Bool, Float16,
-        Double, UInt32, UInt64, BFloat16;
+        Double, UInt32, UInt64, BFloat16, Float8E4M3FN;  // 17 = ONNX FLOAT8E4M3FN: quantised weights (not in the reference)
     constexpr DataType(int index = 1) : index(index) {}
     bool operator==(const DataType &o) const { return index == o.index; }
     bool operator!=(const DataType &o) const { return index != o.index; }
     bool operator<(const DataType &o) const { return index < o.index; }
     int getIndex() const { return index; }
     size_t getSize() const {
-        static const size_t sz[] = {0, 4, 1, 1, 2, 2, 4, 8, 0, 1, 2, 8, 4, 8, 0, 0, 2};
-        return index >= 0 && index <= 16 ? sz[index] : 0;
+        static const size_t sz[] = {0, 4, 1, 1, 2, 2, 4, 8, 0, 1, 2, 8, 4, 8, 0, 0, 2, 1};
+        return index >= 0 && index <= 17 ? sz[index] : 0;
     }
     string toString() const {
         static const char *nm[] = {"Undefine", "Float32", "UInt8", "Int8", "UInt16", "Int16", "Int32", "Int64",
-                                   "String", "Bool", "Float16", "Double", "UInt32", "UInt64", "?", "?", "BFloat16"};
-        return index >= 0 && index <= 16 ? nm[index] : "?";
+                                   "String", "Bool", "Float16", "Double", "UInt32", "UInt64", "?", "?", "BFloat16", "Float8E4M3FN"};
+        return index >= 0 && index <= 17 ? nm[index] : "?";
     }
     bool isFloat() const { return index == 1 || index == 10 || index == 16; }
 };

@@ -7,10 +7,23 @@
 namespace infini {
 
 // ---------------------------------------------------------------- MatMul (src/operators/matmul.cc:26-49)
+static TensorVec matmulInputs(Tensor A, Tensor B, Tensor bias, Tensor wScale) {
+    TensorVec v{A, B};
+    if (bias) v.push_back(bias);
+    if (wScale) v.push_back(wScale);
+    return v;
+}
 MatmulObj::MatmulObj(GraphObj *graph, Tensor A, Tensor B, Tensor C, bool transA, bool transB, Tensor bias,
-                     ActType act, string computeType)
-    : OperatorObj(OpType::MatMul, bias ? TensorVec{A, B, bias} : TensorVec{A, B}, {C}), transA(transA),
-      transB(transB), act(act), b(1), m(0), n(0), k(0), computeType(std::move(computeType)) {
+                     ActType act, string computeType, Tensor wScale)
+    : OperatorObj(OpType::MatMul, matmulInputs(A, B, bias, wScale), {C}), transA(transA),
+      transB(transB), act(act), b(1), m(0), n(0), k(0), computeType(std::move(computeType)), hasWScale(wScale != nullptr) {
+    if (wScale) {
+        IT_ASSERT(B->getDType() == DataType::Float8E4M3FN && wScale->getDType() == DataType::Float32,
+                  "MatMul: a weight scale goes with an FP8 E4M3 weight and is f32");
+        IT_ASSERT(B->getRank() == 2 && !transB && (int)wScale->size() == B->getDims()[1], "MatMul: one scale per output column of a [K, N] weight");
+    } else {
+        IT_ASSERT(B->getDType() != DataType::Float8E4M3FN, "MatMul: an FP8 weight needs its scale");
+    }
     IT_ASSERT(checkValid(graph));
 }
 std::optional<vector<Shape>> MatmulObj::inferShape(const TensorVec &ins) {

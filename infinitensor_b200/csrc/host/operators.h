@@ -18,14 +18,17 @@ class MatmulObj : public OperatorObj {
     ActType act;
     mutable int b, m, n, k;
     string computeType;
+    bool hasWScale = false;  // extension: B holds FP8 E4M3 codes, the LAST input is its per-column f32 scale
 
   public:
     MatmulObj(GraphObj *graph, Tensor A, Tensor B, Tensor C, bool transA = false, bool transB = false,
-              Tensor bias = nullptr, ActType act = ActType::None, string computeType = "default");
+              Tensor bias = nullptr, ActType act = ActType::None, string computeType = "default", Tensor wScale = nullptr);
+    Tensor getWScale() const { return hasWScale ? inputs.back() : nullptr; }
+    vector<DataType> inferDataType(const TensorVec &ins) const override { return {ins[0]->getDType()}; }
     std::optional<vector<Shape>> inferShape(const TensorVec &inputs) override;
     string toString() const override;
     vector<int> getWorkloadVector() const override;
-    Tensor getBias() const { return inputs.size() > 2 ? inputs[2] : nullptr; }
+    Tensor getBias() const { return inputs.size() > (hasWScale ? 3u : 2u) ? inputs[2] : nullptr; }
     ActType getAct() const { return act; }
     bool getTransA() const { return transA; }
     bool getTransB() const { return transB; }

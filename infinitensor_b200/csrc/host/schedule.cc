@@ -67,7 +67,8 @@ static bool groupableMatmul(const Operator &op) {
     if (!mm || mm->getBias() || mm->getTransA() || mm->getTransB()) return false;
     auto A = mm->getInputs(0), B = mm->getInputs(1);
     auto dt = A->getDType();
-    if (!(dt == DataType::Float16 || dt == DataType::BFloat16) || B->getDType() != dt) return false;
+    const bool fp8w = mm->getWScale() != nullptr;  // FP8 weight + per-column scale: grouped only with its own kind (checked by the caller)
+    if (!(dt == DataType::Float16 || dt == DataType::BFloat16) || (!fp8w && B->getDType() != dt)) return false;
     if (B->getRank() != 2 || !B->isWeight()) return false;
     if (rowsOf(A) > 64) return false;  // decode regime: the grouped kernel is the skinny GEMM
     return true;
@@ -395,6 +396,7 @@ const vector<ExecStep> &GraphObj::getSchedule() {
                     if (cand == op || consumed.count(cand.get()) || deferred.count(cand.get())) continue;
                     if (cand->getOpType() != OpType::MatMul || cand->getInputs(0) != A) continue;
                     if (pos[cand.get()] < (int)i || !groupableMatmul(cand) || as<MatmulObj>(cand)->getK() != k) continue;
+                    if ((as<MatmulObj>(cand)->getWScale() != nullptr) != (as<MatmulObj>(op)->getWScale() != nullptr)) continue;
                     st.ops.push_back(cand);
                 }
                 if (st.ops.size() > 1) {

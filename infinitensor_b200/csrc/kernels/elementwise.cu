@@ -236,9 +236,37 @@ __global__ void __launch_bounds__(256) expand_kernel(const E *__restrict__ x, E 
     }
 }
 
+// DequantizeLinear for FP8 E4M3 codes with a per-column scale: y[r][c] = T(e4m3(xq[r][c]) * scale[c])
+__device__ __forceinline__ float e4m3_to_f(uint8_t c) {
+    const unsigned short pair = c;
+    uint32_t h2;
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"(pair));
+    return __half2float(__ushort_as_half((unsigned short)(h2 & 0xffffu)));
+}
+template <typename T>
+__global__ void __launch_bounds__(256) dequant_fp8_kernel(const uint8_t *__restrict__ xq, const float *__restrict__ scale,
+                                                          T *__restrict__ y, int64_t n, int64_t cols) {
+    pdl_trigger();
+    pdl_wait();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = from_f<T>(e4m3_to_f(xq[i]) * scale[i % cols]);
+}
+
 }  // namespace itb
 
 using namespace itb;
+
+extern "C" int it_b200_dequantize_fp8(int dtype_out, const void *xq, const float *scale, void *y, int64_t rows, int64_t cols,
+                                      void *stream) {
+    const int64_t n = rows * cols;
+    if (n == 0) return 0;
+    ITB_DISPATCH_FLOAT(dtype_out, "dequantize_fp8", {
+        launch_k(dequant_fp8_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const uint8_t *)xq, scale, (T *)y,
+                 n, cols);
+    });
+    ITB_LAUNCH_CHECK("dequantize_fp8");
+    return 0;
+}
 
 extern "C" int it_b200_unary_alpha(int op, int dtype, const void *x, void *y, int64_t n, float alpha, void *stream) {
     ITB_CHECK(op >= ITB_RELU && op <= ITB_ELU, "unary: bad op %d", op);

@@ -47,6 +47,20 @@ bool make_tma_2d_b16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t
     return r == CUDA_SUCCESS;
 }
 
+bool make_tma_2d_u8(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                    uint32_t box_rows, uint32_t box_cols) {
+    auto fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // 3-D tensor [batch][rows][cols] of 2-byte elements (batch stride in elements), box [1, box_rows, box_cols], 128B swizzle
 bool make_tma_3d_b16(CUtensorMap *map, const void *base, uint64_t batch, uint64_t rows, uint64_t cols,
                      uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows, uint32_t box_cols) {
@@ -196,6 +210,18 @@ extern "C" int it_b200_matmul_grouped(int dtype, const void *X, int n_groups, co
         if (r) return r;
     }
     return 0;
+}
+
+extern "C" int it_b200_matmul_fp8w(int dtype, const void *X, int n_groups, const void *const *Wq, const float *const *scale,
+                                   void *const *C, const int *N, int m, int k, const void *residual, void *stream) {
+    ITB_CHECK(n_groups >= 1 && n_groups <= 4, "matmul_fp8w: 1..4 weight matrices per launch");
+    ITB_CHECK(!residual || n_groups == 1, "matmul_fp8w: a residual goes with a single weight matrix");
+    GemmArgs g{X, Wq[0], residual, C[0], 1, m, N[0], k, (int64_t)m * k, 0, 0, 0, 0, residual ? (int64_t)N[0] : 0, residual ? 1 : 0,
+               residual ? ITB_ACT_ROUND_BEFORE_BIAS : 0};
+    g.w_scale = scale[0];
+    int r = launch_gemm_skinny_fp8w(dtype, g, n_groups, Wq, scale, C, N, (cudaStream_t)stream);
+    ITB_CHECK(r >= 0, "matmul_fp8w: shape outside the decode kernel (m = %d <= 64, K = %d %% 16, N %% 16, f16 / bf16 activations)", m, k);
+    return r;
 }
 
 static void conv_out(int H, int W, int R, int S, int ph, int pw, int sh, int sw, int dh, int dw, int &OH, int &OW) {

@@ -28,6 +28,9 @@ struct GemmArgs {
     const void *residual = nullptr;
     int post_relu = 0;
     int no_splitk = 0;  // keep one CTA per output tile (conv GEMMs: same fp32 summation order with and without a tail)
+    // weight-only quantisation: B holds FP8 E4M3 codes [K, N] (one byte each); the kernel converts them to the
+    // activation type on their way into the tensor core and multiplies column n of the fp32 sum by w_scale[n] in the epilogue
+    const float *w_scale = nullptr;
 };
 
 __device__ __forceinline__ float gemm_act(int act, float v) {
@@ -45,11 +48,17 @@ int launch_gemm_skinny(int dtype, const GemmArgs &g, cudaStream_t st);
 int launch_gemm_skinny_grouped(int dtype, const GemmArgs &g0, int ngroups, const void *const *Ws, void *const *Cs,
                                const int *Ns, cudaStream_t st);
 int launch_gemm_tc(int dtype, const GemmArgs &g, cudaStream_t st);
+int launch_gemm_skinny_fp8w(int dtype, const GemmArgs &g0, int ngroups, const void *const *Wq, const float *const *scales,
+                            void *const *Cs, const int *Ns, cudaStream_t st);
 
 // ---- TMA descriptor creation (driver entry point fetched at run time; no link-time libcuda) ----
 // 2-D row-major tensor [rows, cols] of 2-byte elements, box [box_rows, box_cols], 128B swizzle.
 bool make_tma_2d_b16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols,
                      uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
+
+// 2-D row-major tensor [rows, cols] of BYTES (fp8 codes), box [box_rows, box_cols], no swizzle
+bool make_tma_2d_u8(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                    uint32_t box_rows, uint32_t box_cols);
 
 bool make_tma_3d_b16(CUtensorMap *map, const void *base, uint64_t batch, uint64_t rows, uint64_t cols,
                      uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows, uint32_t box_cols);

@@ -31,9 +31,11 @@ constexpr int SK_THREADS = 160;                // 4 consumer warps + 1 producer 
 
 // NB = 64-column boxes per tile: NB = 1 -> 64-wide tiles (128 B per weight row), NB = 2 -> 128-wide tiles (256 B
 // contiguous per row: better DRAM efficiency when there are enough column tiles to fill the machine)
-template <int MT, int NB> struct SkinnyCfg {
+// W8: the weight operand is FP8 E4M3 (one byte per element, [64k x 64n] boxes of 4 KB, unswizzled): half the bytes per stage
+template <int MT, int NB, bool W8 = false> struct SkinnyCfg {
     static constexpr int BN = NB * SK_BOX;
-    static constexpr int W_BYTES = NB * SK_BOX_BYTES;
+    static constexpr int BOX_BYTES = W8 ? SK_BOX_BYTES / 2 : SK_BOX_BYTES;
+    static constexpr int W_BYTES = NB * BOX_BYTES;
     static constexpr int X_BYTES = MT * 16 * SK_BK * 2;
     static constexpr int RED_BYTES = MT * 16 * BN * 4;
     static constexpr int stages_for(int budget_kb) {
@@ -52,15 +54,31 @@ struct SkinnyGroups {
     int n[SK_MAX_GROUPS];
     int tile_start[SK_MAX_GROUPS + 1];
     int ngroups;
+    const float *w_scale[SK_MAX_GROUPS];  // W8: per-output-column scale of each group's weight matrix
 };
 
-template <typename T, int MT, int NB>
+// two FP8 E4M3 codes (low byte = first element) -> two values of the activation type, exactly (every E4M3 value is
+// representable in f16 and in bf16)
+template <typename T> __device__ __forceinline__ uint32_t e4m3x2_to(uint32_t pair16);
+template <> __device__ __forceinline__ uint32_t e4m3x2_to<__half>(uint32_t pair16) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r) : "h"((unsigned short)pair16));
+    return r;
+}
+template <> __device__ __forceinline__ uint32_t e4m3x2_to<__nv_bfloat16>(uint32_t pair16) {
+    const uint32_t h2 = e4m3x2_to<__half>(pair16);
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&h2));
+    const __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
+    return *reinterpret_cast<const uint32_t *>(&b);
+}
+
+template <typename T, int MT, int NB, bool W8>
 __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_constant__ SkinnyGroups grp,
                                                                  const __grid_constant__ CUtensorMap mapX,
                                                                  GemmArgs g, int ktiles, int ktiles_per_split,
                                                                  int S) {
-    using Cfg = SkinnyCfg<MT, NB>;
-    constexpr int SK_BN = Cfg::BN, SK_W_BYTES = Cfg::W_BYTES;
+    using Cfg = SkinnyCfg<MT, NB, W8>;
+    constexpr int SK_BN = Cfg::BN, SK_W_BYTES = Cfg::W_BYTES, BOXB = Cfg::BOX_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled TMA tiles need 1024-byte alignment
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -119,7 +137,7 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
                 mbar_expect_tx(&full[it], SK_W_BYTES + Cfg::X_BYTES);
 #pragma unroll
                 for (int bx = 0; bx < NB; ++bx)
-                    tma_load_2d(w_sm + it * SK_W_BYTES + bx * SK_BOX_BYTES, mapWp, &full[it], n0 + bx * SK_BOX,
+                    tma_load_2d(w_sm + it * SK_W_BYTES + bx * BOXB, mapWp, &full[it], n0 + bx * SK_BOX,
                                 (kt_begin + it) * SK_BK, pol_w);
             }
             pdl_wait();
@@ -133,7 +151,7 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
                 const int k0 = (kt_begin + it) * SK_BK;
 #pragma unroll
                 for (int bx = 0; bx < NB; ++bx)
-                    tma_load_2d(w_sm + s * SK_W_BYTES + bx * SK_BOX_BYTES, mapWp, &full[s], n0 + bx * SK_BOX, k0, pol_w);
+                    tma_load_2d(w_sm + s * SK_W_BYTES + bx * BOXB, mapWp, &full[s], n0 + bx * SK_BOX, k0, pol_w);
                 tma_load_2d(x_sm + s * Cfg::X_BYTES, &mapX, &full[s], k0, 0, pol_x);
                 if (++s == S) {
                     s = 0;
@@ -165,9 +183,22 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
 #pragma unroll
                 for (int bx = 0; bx < NB; ++bx) {  // warp w owns columns [16w, 16w+16) of every 64-column box
                     uint32_t b0, b1, b2, b3;
+                    if constexpr (W8) {
+                        // FP8 weights: the box is [64 k][64 n] bytes, unswizzled.  B fragment of mma.m16n8k16 (col-major): lane
+                        // (g = lane / 4, t = lane % 4) holds {W[2t][g], W[2t+1][g]} and {W[2t+8][g], W[2t+9][g]} of each 8-column
+                        // tile -- two byte loads per register, converted to the activation type on the way (the "dequant" of
+                        // the main loop; the per-column scale is applied once, to the fp32 sum, in the epilogue)
+                        const uint8_t *tile = w_sm + s * SK_W_BYTES + bx * BOXB + (kk * 16 + 2 * (lane & 3)) * 64 + warp * 16 + (lane >> 2);
+                        auto frag = [&](const uint8_t *p) { return e4m3x2_to<T>((uint32_t)p[0] | ((uint32_t)p[64] << 8)); };
+                        b0 = frag(tile);
+                        b1 = frag(tile + 8 * 64);
+                        b2 = frag(tile + 8);
+                        b3 = frag(tile + 8 * 64 + 8);
+                    } else {
                     const int krow = kk * 16 + r8 + 8 * (mi & 1);
                     const int nchunk = warp * 2 + (mi >> 1);
                     ldmatrix_x4_trans(b0, b1, b2, b3, wb + bx * SK_BOX_BYTES + krow * 128 + ((nchunk ^ (krow & 7)) << 4));
+                    }
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
                         mma_m16n8k16<T>(acc[mt][bx * 2 + 0], a[mt], b0, b1);
@@ -216,6 +247,11 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
                 v.x += p.x;
                 v.y += p.y;
             }
+            if constexpr (W8) {  // dequantisation: column scale of the weight matrix
+                const float *sc = grp.w_scale[gi];
+                v.x *= sc[gn];
+                if (gn + 1 < gN) v.y *= sc[gn + 1];
+            }
             if (bias) {
                 if (round_first) {  // MatMul -> Add fusion: reproduce the unfused graph's rounding of the MatMul output
                     v.x = round_t<T>(v.x);
@@ -244,18 +280,20 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
 // tuning hook (tools/gemm_sweep.py): force the tile width (NB boxes of 64 columns) and the split-K factor; 0 = automatic
 static int g_nb_override = 0, g_splitk_override = 0;
 
-template <typename T, int MT, int NB>
+template <typename T, int MT, int NB, bool W8 = false>
 static int launch_skinny_nb(const GemmArgs &g, int ngroups, const void *const *Ws, void *const *Cs, const int *Ns,
-                            cudaStream_t st) {
-    using Cfg = SkinnyCfg<MT, NB>;
+                            cudaStream_t st, const float *const *scales = nullptr) {
+    using Cfg = SkinnyCfg<MT, NB, W8>;
     constexpr int SK_BN = Cfg::BN;
     SkinnyGroups grp{};
     CUtensorMap mapX;
     grp.ngroups = ngroups;
     int tiles_n = 0;
     for (int i = 0; i < ngroups; ++i) {
-        if (!make_tma_2d_b16(&grp.mapW[i], Ws[i], (uint64_t)g.k, (uint64_t)Ns[i], (uint64_t)Ns[i], SK_BK, SK_BOX, 128))
-            ITB_FAIL("matmul(skinny): cuTensorMapEncodeTiled(W) failed");
+        const bool okW = W8 ? make_tma_2d_u8(&grp.mapW[i], Ws[i], (uint64_t)g.k, (uint64_t)Ns[i], (uint64_t)Ns[i], SK_BK, SK_BOX)
+                            : make_tma_2d_b16(&grp.mapW[i], Ws[i], (uint64_t)g.k, (uint64_t)Ns[i], (uint64_t)Ns[i], SK_BK, SK_BOX, 128);
+        if (!okW) ITB_FAIL("matmul(skinny): cuTensorMapEncodeTiled(W) failed");
+        grp.w_scale[i] = scales ? scales[i] : nullptr;
         grp.C[i] = Cs[i];
         grp.n[i] = Ns[i];
         grp.tile_start[i] = tiles_n;
@@ -285,10 +323,10 @@ static int launch_skinny_nb(const GemmArgs &g, int ngroups, const void *const *W
     }
     const int stages = Cfg::stages_for(budget_kb);
     const int smem_bytes = Cfg::smem_for(stages);
-    auto kern = gemm_skinny_kernel<T, MT, NB>;
+    auto kern = gemm_skinny_kernel<T, MT, NB, W8>;
     {
         // the attribute is per DEVICE (a process may own runtimes on several GPUs): remember the largest request per device
-        static int attr_smem[64] = {0};
+        static int attr_smem[64] = {0};  // (one table per template instantiation)
         int dev = 0;
         cudaGetDevice(&dev);
         dev &= 63;
@@ -342,6 +380,17 @@ static bool skinny_ok(int dtype, const GemmArgs &g) {
     return true;
 }
 
+// FP8-weight variants (64-wide tiles below 2 x 148 x ... column tiles, 128-wide above, as for 16-bit weights)
+template <typename T, int MT>
+static int launch_skinny_w8_t(const GemmArgs &g, int ngroups, const void *const *Ws, void *const *Cs, const int *Ns,
+                              const float *const *scales, cudaStream_t st) {
+    int tiles64 = 0;
+    for (int i = 0; i < ngroups; ++i) tiles64 += (Ns[i] + 63) / 64;
+    const int nb = g_nb_override ? g_nb_override : (tiles64 > 2 * kNumSMs ? 2 : 1);
+    if (nb == 2) return launch_skinny_nb<T, MT, 2, true>(g, ngroups, Ws, Cs, Ns, st, scales);
+    return launch_skinny_nb<T, MT, 1, true>(g, ngroups, Ws, Cs, Ns, st, scales);
+}
+
 #define SK_GO(TT, ...)                                                                         \
     do {                                                                                       \
         if (mt == 1) return launch_skinny_t<TT, 1>(__VA_ARGS__);                               \
@@ -377,6 +426,30 @@ int launch_gemm_skinny_grouped(int dtype, const GemmArgs &g0, int ngroups, const
     SK_GO(__half, gc, ngroups, Ws, Cs, Ns, st);
 }
 #undef SK_GO
+
+// X[M,K] (f16 / bf16) . {Wq_i[K,N_i] FP8 E4M3 x scale_i[N_i]} -> {C_i[M,N_i]}: 1..4 weight matrices sharing X in one launch;
+// g0 carries bias / residual / act for the single-matrix case exactly like launch_gemm_skinny.  -1 = shape not taken.
+int launch_gemm_skinny_fp8w(int dtype, const GemmArgs &g0, int ngroups, const void *const *Wq, const float *const *scales,
+                            void *const *Cs, const int *Ns, cudaStream_t st) {
+    if (ngroups < 1 || ngroups > SK_MAX_GROUPS) return -1;
+    if (dtype != ITB_BF16 && dtype != ITB_F16) return -1;
+    if (g0.batch != 1 || g0.trans_a || g0.trans_b || g0.m > 64 || g0.m < 1) return -1;
+    if (g0.k % 16 != 0 || g0.k < 64 || !aligned16(g0.A)) return -1;
+    for (int i = 0; i < ngroups; ++i)
+        if (Ns[i] % 16 != 0 || Ns[i] < 64 || !aligned16(Wq[i]) || !scales[i] || ((uintptr_t)Cs[i] & 3)) return -1;
+    const int mt = (g0.m + 15) / 16;
+    GemmArgs gc = g0;
+    gc.act |= ITB_MATMUL_B_CONST;  // quantised weights are constants by contract
+#define SK8(TT)                                                                                            \
+    do {                                                                                                   \
+        if (mt == 1) return launch_skinny_w8_t<TT, 1>(gc, ngroups, Wq, Cs, Ns, scales, st);                \
+        if (mt == 2) return launch_skinny_w8_t<TT, 2>(gc, ngroups, Wq, Cs, Ns, scales, st);                \
+        return launch_skinny_w8_t<TT, 4>(gc, ngroups, Wq, Cs, Ns, scales, st);                             \
+    } while (0)
+    if (dtype == ITB_BF16) SK8(__nv_bfloat16);
+    SK8(__half);
+#undef SK8
+}
 
 }  // namespace itb
 

@@ -18,6 +18,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 F32, F16, BF16, I64, I32 = 1, 10, 16, 7, 6
+FP8 = 17  # FP8 E4M3 weight codes
 LINEAR = 0
 
 
@@ -64,6 +65,7 @@ class LlamaConfig:
     s_max: int = 1024
     batch: int = 16
     dtype: int = BF16
+    fp8_weights: bool = False  # the seven projection matrices of every layer + the logits head as FP8 E4M3 codes + f32 column scales
 
     @staticmethod
     def tiny(dtype=BF16, layers=2, batch=4):
@@ -79,10 +81,14 @@ class LlamaConfig:
         """weights read once + KV read/append + ~12 activation tensors per layer."""
         e = 2 if self.dtype in (F16, BF16) else 4
         d, f = self.d_model, self.ffn
-        w = self.layers * ((4 * d * d + 3 * d * f) // world + 2 * d) + d + d * self.vocab
+        proj = self.layers * ((4 * d * d + 3 * d * f) // world) + d * self.vocab
+        norms = self.layers * 2 * d + d
         kv = self.layers * 2 * self.batch * (self.heads // world) * self.head_dim * (pos + 2)
         act = self.layers * 12 * self.batch * d
-        return (w + kv + act) * e
+        if self.fp8_weights:  # one byte per projection weight + 4 bytes per output column
+            cols = self.layers * ((3 * d + 2 * f) // world + 2 * d) + self.vocab
+            return proj + 4 * cols + (norms + kv + act) * e
+        return (proj + norms + kv + act) * e
 
 
 @dataclass
@@ -111,6 +117,19 @@ def build_llama_decode(h, cfg: LlamaConfig, world: int = 1, rank: int = 0) -> Ll
         g.weights[name] = (t, tuple(shape), kind, shard)
         return t
 
+    def linear(x_, name, shape, shard=None):
+        """x . W: 16-bit weight, or (cfg.fp8_weights) FP8 E4M3 codes + per-column f32 scale dequantised inside the GEMM"""
+        if not cfg.fp8_weights:
+            return h.matmul(x_, weight(name, shape, "proj", shard), None, False, False, None, LINEAR)
+        assert world == 1, "fp8 weights: single GPU"
+        wq = h.tensor(list(shape), FP8)
+        wq.set_weight()
+        sc = h.tensor([shape[1]], F32)
+        sc.set_weight()
+        g.weights[name] = (wq, tuple(shape), "proj_fp8", shard)
+        g.weights[name + ".scale"] = (sc, (shape[1],), "scale", None)
+        return h.matmul(x_, wq, None, False, False, None, LINEAR, w_scale=sc)
+
     g.input_ids = h.tensor([B, 1], I64)
     g.position_ids = h.tensor([B, 1], I64)
     g.input_ids.set_input()
@@ -126,9 +145,9 @@ def build_llama_decode(h, cfg: LlamaConfig, world: int = 1, rank: int = 0) -> Ll
         g.k_caches.append(kc)
         g.v_caches.append(vc)
         hn = h.RMSNorm(x, weight(p + "ln1", (d,), "norm"), None)
-        q = h.matmul(hn, weight(p + "wq", (d, dl), "proj", ("col", d)), None, False, False, None, LINEAR)
-        k = h.matmul(hn, weight(p + "wk", (d, dl), "proj", ("col", d)), None, False, False, None, LINEAR)
-        v = h.matmul(hn, weight(p + "wv", (d, dl), "proj", ("col", d)), None, False, False, None, LINEAR)
+        q = linear(hn, p + "wq", (d, dl), ("col", d))
+        k = linear(hn, p + "wk", (d, dl), ("col", d))
+        v = linear(hn, p + "wv", (d, dl), ("col", d))
         q = h.RoPE(g.position_ids, q, None)
         k = h.RoPE(g.position_ids, k, None)
 
@@ -138,20 +157,20 @@ def build_llama_decode(h, cfg: LlamaConfig, world: int = 1, rank: int = 0) -> Ll
 
         attn = h.attentionKVCache(kc, vc, heads(q), heads(k), heads(v), g.position_ids, None)
         a = h.reshape(h.transpose(attn, None, [0, 2, 1, 3]), None, [B, 1, dl])
-        o = h.matmul(a, weight(p + "wo", (dl, d), "proj", ("row", d)), None, False, False, None, LINEAR)
+        o = linear(a, p + "wo", (dl, d), ("row", d))
         if world > 1:
             o = h.allReduceSum(o, None)
         x = h.add(x, o, None)
         hn = h.RMSNorm(x, weight(p + "ln2", (d,), "norm"), None)
-        gate = h.matmul(hn, weight(p + "wg", (d, f), "proj", ("col", cfg.ffn)), None, False, False, None, LINEAR)
-        up = h.matmul(hn, weight(p + "wu", (d, f), "proj", ("col", cfg.ffn)), None, False, False, None, LINEAR)
+        gate = linear(hn, p + "wg", (d, f), ("col", cfg.ffn))
+        up = linear(hn, p + "wu", (d, f), ("col", cfg.ffn))
         m = h.mul(h.silu(gate, None), up, None)
-        dn = h.matmul(m, weight(p + "wd", (f, d), "proj", ("row", cfg.ffn)), None, False, False, None, LINEAR)
+        dn = linear(m, p + "wd", (f, d), ("row", cfg.ffn))
         if world > 1:
             dn = h.allReduceSum(dn, None)
         x = h.add(x, dn, None)
     xf = h.RMSNorm(x, weight("ln_f", (d,), "norm"), None)
-    g.logits = h.matmul(xf, weight("lm_head", (d, V), "proj"), None, False, False, None, LINEAR)
+    g.logits = linear(xf, "lm_head", (d, V))
     g.logits.set_output()
     return g
 
@@ -185,9 +204,34 @@ def shard_weight(full: np.ndarray, shard, world: int, rank: int) -> np.ndarray:
     return np.ascontiguousarray(full[rank * n:(rank + 1) * n, :])
 
 
+def quantize_fp8_host(w: np.ndarray):
+    """per-output-column symmetric FP8 E4M3 quantisation (same rule as oracle.quantize_weight_fp8, restated so that the product
+    never imports the oracle): codes uint8 [K, N], scale f32 [N] = max|column| / 448; round to nearest, ties to even."""
+    w = np.asarray(w, np.float32)
+    scale = np.maximum(np.abs(w).max(axis=0), 1e-12).astype(np.float32) / np.float32(448.0)
+    x = (w / scale[None, :]).astype(np.float32)
+    table = np.zeros(127, np.float64)
+    for c in range(127):
+        e, m = (c >> 3) & 15, c & 7
+        table[c] = (m / 8.0) * 2.0 ** -6 if e == 0 else (1.0 + m / 8.0) * 2.0 ** (e - 7)
+    mag = np.minimum(np.abs(x).astype(np.float64), 448.0)
+    hi = np.clip(np.searchsorted(table, mag, side="left"), 0, 126)
+    lo = np.clip(hi - 1, 0, 126)
+    dlo, dhi = mag - table[lo], table[hi] - mag
+    code = np.where((dhi < dlo) | ((dhi == dlo) & (hi % 2 == 0)), hi, lo).astype(np.uint8)
+    return np.where(np.signbit(x), code | 0x80, code).astype(np.uint8), scale
+
+
 def fill_llama_weights_host(g: LlamaGraph, world: int = 1, rank: int = 0, seed: int = 0):
     """Small configs only (host RNG): full tensors are drawn, then sharded like parallel_opt.py does."""
     for name, (t, shape, kind, shard) in g.weights.items():
+        if kind == "scale":
+            continue  # written together with its codes
+        if kind == "proj_fp8":
+            codes, scale = quantize_fp8_host(llama_weight_values(name, list(shape), "proj", seed))
+            t.copyin_numpy(codes)
+            g.weights[name + ".scale"][0].copyin_numpy(scale)
+            continue
         full_shape = list(shape)
         if shard is not None and world > 1:
             full_shape[1 if shard[0] == "col" else 0] *= world

@@ -189,6 +189,62 @@ def unary(name, x, dt=F32):
     return y
 
 
+# ---- FP8 E4M3 ("FN": 1 sign, 4 exponent bits with bias 7, 3 mantissa bits, no infinities, 0x7f / 0xff = NaN, max 448) -- the
+# OCP 8-bit format of ONNX FLOAT8E4M3FN (type 17).  Restated from the format definition; the reference has no fp8 code.
+def _e4m3_table():
+    v = np.zeros(256, np.float32)
+    for c in range(256):
+        s, e, m = c >> 7, (c >> 3) & 15, c & 7
+        if e == 15 and m == 7:
+            val = np.nan
+        elif e == 0:
+            val = (m / 8.0) * 2.0 ** -6
+        else:
+            val = (1.0 + m / 8.0) * 2.0 ** (e - 7)
+        v[c] = -val if s else val
+    return v
+
+
+E4M3 = _e4m3_table()
+
+
+def e4m3_decode(codes):
+    return E4M3[np.asarray(codes, np.uint8)]
+
+
+def e4m3_quantize(x):
+    """float32 -> E4M3 codes, round to nearest, ties to the even code, saturating at +-448 (no NaN / inf inputs)."""
+    x = np.asarray(x, np.float32)
+    mag = np.minimum(np.abs(x).astype(np.float64), 448.0)
+    pos = E4M3[:127].astype(np.float64)            # codes 0..126: 0 .. 448, increasing
+    hi = np.clip(np.searchsorted(pos, mag, side="left"), 0, 126)
+    lo = np.clip(hi - 1, 0, 126)
+    dlo, dhi = mag - pos[lo], pos[hi] - mag
+    pick_hi = (dhi < dlo) | ((dhi == dlo) & (hi % 2 == 0))
+    code = np.where(pick_hi, hi, lo).astype(np.uint8)
+    return np.where(np.signbit(x), code | 0x80, code).astype(np.uint8)
+
+
+def quantize_weight_fp8(w):
+    """per-output-column symmetric quantisation of W [K, N]: scale[n] = max|W[:, n]| / 448; returns (codes uint8 [K,N], scale f32 [N])"""
+    w = np.asarray(w, np.float32)
+    scale = np.maximum(np.abs(w).max(axis=0), 1e-12).astype(np.float32) / np.float32(448.0)
+    return e4m3_quantize(w / scale[None, :]), scale
+
+
+def dequantize_fp8(codes, scale, dt=F32):
+    """DequantizeLinear: T(e4m3(code) * scale[col]) (one rounding to the storage type)"""
+    return round_to(e4m3_decode(codes) * np.asarray(scale, np.float32)[None, :], dt)
+
+
+def matmul_fp8w(x, codes, scale, dt=F32):
+    """X . (Wq * scale): fp32 accumulation over the EXACT code values, the column scale applied to the sum (what the GEMM's
+    epilogue does), one rounding to the storage type."""
+    x = _f32c(x)
+    acc = x.astype(np.float64) @ e4m3_decode(codes).astype(np.float64)
+    return round_to((acc * np.asarray(scale, np.float64)[None, :]).astype(np.float32), dt)
+
+
 def unary_alpha(name, x, alpha, dt=F32):
     """LeakyRelu: x > 0 ? x : alpha * x (reference unary.cu:157-165); Elu: x >= 0 ? x : alpha * (expf(x) - 1) (unary.cu:97-106);
     fp32 arithmetic on the (already rounded) inputs, one rounding to the storage type."""

@@ -14,7 +14,7 @@ import oracle as O
 
 F32, F16, BF16 = 1, 10, 16
 _FLOAT = (F32, F16, BF16)
-_NP = {1: np.float32, 2: np.uint8, 3: np.int8, 6: np.int32, 7: np.int64, 9: np.bool_, 10: np.float16, 12: np.uint32,
+_NP = {17: np.uint8, 1: np.float32, 2: np.uint8, 3: np.int8, 6: np.int32, 7: np.int64, 9: np.bool_, 10: np.float16, 12: np.uint32,
        16: np.uint16}
 
 
@@ -94,11 +94,14 @@ class OracleHandler:
         return outs[0] if len(outs) == 1 else outs
 
     # ---- operators
-    def matmul(self, a, b, y, transA, transB, bias, act, matmul_compute_type="default"):
+    def matmul(self, a, b, y, transA, transB, bias, act, matmul_compute_type="default", w_scale=None):
         m = a.dims[-1] if transA else a.dims[-2]
         n = b.dims[-2] if transB else b.dims[-1]
         batch = list(np.broadcast_shapes(tuple(a.dims[:-2]), tuple(b.dims[:-2])))
         out = self._out(y, batch + [m, n], a.dt)
+        if w_scale is not None:  # FP8 E4M3 weight codes + per-column scale: X . (codes * scale), scale applied to the fp32 sum
+            return self._rec(lambda: O.matmul_fp8w(np.asarray(a.value, np.float32).reshape(-1, a.dims[-1]), b.value, w_scale.value,
+                                                   a.dt).reshape(out.dims), [a, b, w_scale], [out])
         return self._rec(lambda: O.matmul(a.value, b.value, None if bias is None else bias.value, transA, transB, a.dt),
                          [a, b], [out])
 

@@ -60,6 +60,22 @@ def test_llama_decode_stack_baseline_width(monkeypatch):
     run_llama_parity(cfg=cfg, pos=511, steps=1)
 
 
+@pytest.mark.parametrize("dtype", [BF16, F16])
+def test_llama_decode_fp8_weights(dtype):
+    """SURVEY 8(f-4) through the graph: every projection (q/k/v grouped, o + residual, gate/up grouped, down + residual, logits)
+    with FP8 E4M3 weight codes + per-column scales dequantised inside the GEMM; the oracle executes the same graph with the
+    dequantised weights in fp32.  CUDA-graph replay, two steps."""
+    from infinitensor_b200 import backend as B, graphs as G
+    from tests.smoke_impl import run_llama_parity
+    cfg = G.LlamaConfig(layers=2, d_model=1024, heads=8, head_dim=128, ffn=2816, vocab=2048, s_max=128, batch=16, dtype=dtype,
+                        fp8_weights=True)
+    h = B.GraphHandler(B.CudaRuntime(0))
+    G.build_llama_decode(h, cfg)
+    sc = h.schedule()
+    assert sc.count("MatMulGroup:MatMul+MatMul+MatMul") == 2 and sc.count("MatMulAdd:MatMul+Add") == 4
+    run_llama_parity(cfg=cfg, pos=77, steps=2)
+
+
 def test_matmul_512_config1():
     """BASELINE config #1: MatmulObj fp32 512^3 through the graph API."""
     from infinitensor_b200 import backend as B, graphs as G

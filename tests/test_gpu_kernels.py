@@ -535,6 +535,41 @@ def test_rope_partial_head_golden(K):
     close(out[0, 0], G.ROPE_COS, 2e-6, 1e-6)
 
 
+@pytest.mark.parametrize("dt", [BF16, F16])
+@pytest.mark.parametrize("m,k,ns,res", [(16, 4096, [4096], False), (16, 4096, [4096, 4096, 4096], False), (16, 4096, [11008, 11008], False),
+                                        (16, 11008, [4096], True), (16, 4096, [32000], False), (5, 512, [64, 128], False),
+                                        (33, 1024, [256], True)])
+def test_matmul_fp8_weights_parity(K, m, k, ns, res, dt):
+    """weight-only FP8 E4M3 with the dequantisation inside the GEMM (codes -> activation type in the main loop,
+    per-column scale on the fp32 sum in the epilogue), 1..3 matrices sharing X; against the fp32 oracle fed the DEQUANTISED
+    weights.  Tolerance: the GEMM bound of SURVEY 8(c) on the dequantised operands."""
+    import ctypes, torch
+    from infinitensor_b200 import _lib as L
+    x = rnd((m, k), 80, dt, 0.5)
+    qs = [oracle.quantize_weight_fp8(np.random.default_rng(81 + i).standard_normal((k, n)).astype(np.float32) * 0.05) for i, n in enumerate(ns)]
+    resid = rnd((m, ns[0]), 90, dt, 1.0) if res else None
+    xd = K.dev(x, dt)
+    cd = [K.raw(c) for c, _ in qs]
+    sd = [K.raw(s) for _, s in qs]
+    od = [torch.zeros((m, n), dtype=K.TORCH_DT[dt], device="cuda") for n in ns]
+    rd = K.dev(resid, dt) if res else None
+    VP = ctypes.c_void_p
+    arr = lambda ts: (VP * len(ts))(*[t.data_ptr() for t in ts])
+    L.check(L.lib.it_b200_matmul_fp8w(dt, K.ptr(xd), len(ns), arr(cd), arr(sd), arr(od), L.i32arr(ns), m, k, K.ptr(rd), K.stream()))
+    K.sync()
+    for (codes, scale), o in zip(qs, od):
+        ref = oracle.matmul_fp8w(x, codes, scale, dt)
+        if res:
+            ref = oracle.binary("add", resid, ref, dt)
+        wmax = np.abs(oracle.e4m3_decode(codes)).max() * scale.max()
+        close(K.host(o), ref, 2 * EPS[dt], gemm_tol(dt, k, np.abs(x).max(), wmax))
+    # the stand-alone DequantizeLinear kernel: bit-exact against the oracle
+    y = torch.zeros((k, ns[0]), dtype=K.TORCH_DT[dt], device="cuda")
+    L.check(L.lib.it_b200_dequantize_fp8(dt, K.ptr(cd[0]), K.ptr(sd[0]), K.ptr(y), k, ns[0], K.stream()))
+    K.sync()
+    assert np.array_equal(K.host(y), oracle.dequantize_fp8(qs[0][0], qs[0][1], dt))
+
+
 def test_error_reporting(K):
     import torch
     from infinitensor_b200 import _lib as L

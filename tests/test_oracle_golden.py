@@ -200,3 +200,20 @@ def test_rounding_helpers():
     x = np.random.default_rng(5).standard_normal(4096).astype(np.float32) * 100
     assert np.array_equal(oracle.round_to(x, oracle.BF16), torch.from_numpy(x).bfloat16().float().numpy())
     assert np.array_equal(oracle.round_to(x, oracle.F16), torch.from_numpy(x).half().float().numpy())
+
+
+def test_fp8_e4m3_codec_known_answers():
+    """FP8 E4M3 (OCP FN) codec of the oracle pinned on the format's published corner values: 0x7e = 448 (max), 0x08 = 2^-6 (min
+    normal), 0x01 = 2^-9 (min subnormal), 0x38 = 1.0, 0xc0 = -2.0; quantisation rounds to nearest-even and saturates."""
+    import oracle
+    d = oracle.e4m3_decode
+    assert d([0x7E])[0] == 448.0 and d([0x08])[0] == 2.0 ** -6 and d([0x01])[0] == 2.0 ** -9 and d([0x38])[0] == 1.0 and d([0xC0])[0] == -2.0
+    assert np.isnan(d([0x7F])[0]) and d([0x00])[0] == 0.0
+    q = oracle.e4m3_quantize
+    assert q([1.0])[0] == 0x38 and q([-2.0])[0] == 0xC0 and q([1000.0])[0] == 0x7E and q([-1e9])[0] == 0xFE
+    assert q([1.0625])[0] == 0x38 and q([1.1875])[0] == 0x3A  # ties: 1.0625 between 1.0 (even) and 1.125; 1.1875 between 1.125 and 1.25 (even)
+    allc = np.array([c for c in range(256) if c not in (0x7F, 0xFF)], np.uint8)
+    assert np.array_equal(q(d(allc)) & 0x7F, allc & 0x7F)  # every code is a fixed point (the sign of zero aside)
+    w = np.random.default_rng(0).standard_normal((64, 32)).astype(np.float32)
+    codes, scale = oracle.quantize_weight_fp8(w)
+    assert np.abs(oracle.dequantize_fp8(codes, scale) - w).max() <= np.abs(w).max() * 2.0 ** -4 * 1.01
