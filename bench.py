@@ -1,0 +1,608 @@
+#!/usr/bin/env python
+"""bench.py -- Llama-7B-shape KV-cache decode (BASELINE.json configs[2] / [4]) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (the B200 backend through the graph API)
+  python bench.py --impl reference --gpus N ...             the reference's CPU path (oracle port) on the host cores
+
+A "step" is one decode step: 16 tokens (batch 16, q-len 1) at position p = 511 over a 1024-slot KV cache,
+32 layers, d = 4096, ffn = 11008, vocab = 32000, bf16 weights / activations / cache.
+For N > 1 the graph is tensor-parallel-sharded exactly where examples/distributed/parallel_opt.py cuts it
+(heads and MLP hidden; 2 in-graph NCCL all-reduces per layer), one process per GPU under torchrun.
+
+Timed regions (device time from CUDA events on the runtime's own stream, max over ranks):
+  value  : K CUDA-graph replays, inputs resident in HBM.
+  e2e    : K steps through the public API with HOST buffers: pinned-host -> device copy of input_ids and
+           position_ids, graph launch, device -> pinned-host copy of the logits, stream sync, every step.
+L2: one step streams >= 17 GB (N = 1) through a 126 MB L2, so successive steps cannot hit; no flush needed.
+PyTorch is plumbing only here: device RNG for the synthetic weights, pinned host buffers, CUDA events on an
+ExternalStream, torch.distributed for the barrier / max-over-ranks / NCCL-id broadcast.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tokens/sec (device-timed) Llama-7B-shape ONNX decode, 1/2/4/8 B200 + CPU ref"
+POS = 511
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=32, help="debug only: anything but 32 marks the line invalid")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="run the op loop without CUDA-graph replay (profiling aid)")
+    ap.add_argument("--weights", default="bf16", choices=["bf16", "fp8"],
+                    help="fp8: the projection weights as FP8 E4M3 codes + per-column scales, dequantised inside the GEMM (SURVEY 8(f-4)); "
+                         "an extra line beside the bf16 headline, never the headline itself")
+    ap.add_argument("--config", default="llama", choices=["llama", "gpt2", "resnet50"],
+                    help="llama (default) = BASELINE configs[2] / [4], the headline; gpt2 = configs[1]; resnet50 = configs[3] (single GPU)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_decode_sample(cfg, reps, threads, full_steps=1, budget_s=90.0):
+    """Times the reference's algorithm on the host: ONE decoder layer + final norm + logits MatMul of the same
+    workload (fp32 arrays holding bf16-rounded values, OpenMP over all host cores), extrapolated to 32 layers.
+    Returns (tokens_per_s, description)."""
+    import numpy as np
+    from infinitensor_b200 import graphs as G
+    from oracle.graph_oracle import OracleHandler
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers): set the env for a runtime that
+    # is not initialised yet and the ICV of one that is
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
+    except OSError:
+        pass
+    one = G.LlamaConfig(layers=1, d_model=cfg.d_model, heads=cfg.heads, head_dim=cfg.head_dim, ffn=cfg.ffn,
+                        vocab=cfg.vocab, s_max=cfg.s_max, batch=cfg.batch, dtype=cfg.dtype)
+    oh = OracleHandler()
+    g = G.build_llama_decode(oh, one)
+    rng = np.random.default_rng(0)
+    import oracle
+    for name, (t, shape, kind, _) in g.weights.items():
+        w = rng.standard_normal(shape, dtype=np.float32) * np.float32(0.02) + (np.float32(1) if kind == "norm" else 0)
+        t.value = oracle.round_to(w, one.dtype)
+    for c in g.k_caches + g.v_caches:
+        c.value = oracle.round_to(rng.standard_normal(c.dims, dtype=np.float32) * np.float32(0.5), one.dtype)
+    g.input_ids.copyin_numpy(rng.integers(0, one.vocab, size=(one.batch, 1)).astype(np.int64))
+    g.position_ids.copyin_numpy(np.full((one.batch, 1), POS, np.int64))
+    # split ops: [embedding] + layer ops + [final norm, logits]
+    ops = oh.ops
+    head_ops = ops[-2:]
+    layer_ops = ops[1:-2]
+
+    def run(opl):
+        for fn, ins, outs in opl:
+            res = fn()
+            if len(outs) == 1:
+                outs[0].value = res
+            else:
+                for o, r in zip(outs, res):
+                    o.value = r
+    run(ops)  # warm
+    x_in, x_out = ops[0][2][0], layer_ops[-1][2][0]   # residual stream entering / leaving the decoder layer
+    tl, th = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter(); run(layer_ops); t1 = time.perf_counter(); run(head_ops); t2 = time.perf_counter()
+        tl.append(t1 - t0); th.append(t2 - t1)
+    t_est = cfg.layers * statistics.median(tl) + statistics.median(th)
+    # FULL-DEPTH steps, measured (not extrapolated): the layer ops run cfg.layers times, each pass fed the previous pass's
+    # residual stream (the one layer's weights are re-used: 0.8 GB of fp32 per pass, far larger than the host caches, so
+    # every pass streams from DRAM like distinct layers would), then final norm + logits.  As many as fit `budget_s`.
+    n_full = max(1, min(full_steps, int(budget_s / max(t_est, 1e-6))))
+    full = []
+    for _ in range(n_full):
+        t0 = time.perf_counter()
+        run(ops[:1])
+        for _l in range(cfg.layers):
+            run(layer_ops)
+            x_in.value = x_out.value
+        run(head_ops)
+        full.append(time.perf_counter() - t0)
+    t_step = statistics.median(full)
+    desc = (f"{n_full} full-depth decode step(s) measured on {threads} host threads: embedding + {cfg.layers} x decoder-layer ops "
+            f"(one layer's weights re-used, residual stream chained) + final norm + logits MatMul, median {t_step * 1e3:.0f} ms/step; "
+            f"single-layer sample: {cfg.layers} x {statistics.median(tl) * 1e3:.1f} ms + {statistics.median(th) * 1e3:.1f} ms")
+    return cfg.batch / t_step, t_step, desc, n_full
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from infinitensor_b200 import graphs as G
+    cfg = G.LlamaConfig(layers=args.layers)
+    threads = os.cpu_count() or 1
+    tps, t_step, desc, n_full = cpu_decode_sample(cfg, 2, threads, full_steps=max(1, args.steps), budget_s=150.0)
+    line = {
+        "metric": METRIC, "value": round(tps, 3), "unit": "tokens/s", "n_gpus": args.gpus, "steps": n_full,
+        "steps_requested": args.steps, "warmup": 1, "ms_per_step": round(t_step * 1e3, 3), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "llama7b_shape_decode_bf16_b16_p511_smax1024", "layers": cfg.layers, "d_model": cfg.d_model,
+                   "heads": cfg.heads, "ffn": cfg.ffn, "vocab": cfg.vocab, "batch": cfg.batch, "position": POS,
+                   "s_max": cfg.s_max, "parallelism": "host-cpu"},
+        "cpu_baseline": {"value": round(tps, 3), "unit": "tokens/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": round(tps, 3), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                       "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from infinitensor_b200 import backend as B
+    from infinitensor_b200 import graphs as G
+    from infinitensor_b200 import _lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1 and args.gpus == 1, f"WORLD_SIZE {world} != --gpus {args.gpus}"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cfg = G.LlamaConfig(layers=args.layers, fp8_weights=args.weights == "fp8")
+    assert not (cfg.fp8_weights and world > 1), "--weights fp8 is a single-GPU line"
+    rt = B.CudaRuntime(local)
+    if world > 1:
+        box = [B.CudaRuntime.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        rt.init_comm_with_id(box[0], world, rank)
+        # NVLink peer-memory comm for the fused one-shot all-reduce (+ residual + RMSNorm)
+        if os.environ.get("ITB_NO_P2P", "0") != "1":
+            handles = [None] * world
+            dist.all_gather_object(handles, rt.p2p_export())
+            rt.p2p_import(handles, world, rank)
+    h = B.GraphHandler(rt)
+    g = G.build_llama_decode(h, cfg, world, rank)
+    h.data_malloc()
+    wbytes, abytes = h.arena_bytes()
+
+    # ---- synthetic weights / cache straight on the device (13 GB: host RNG would take minutes)
+    gen = torch.Generator(device="cuda")
+    ts = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def fill(t, std, mean=0.0, seed=0, shard=None, w=1, r=0):
+        """The FULL (unsharded) tensor is drawn from the seed, then this rank's slice is taken exactly like
+        parallel_opt.py:21-59 shards it -- so every world size sees the same model and the N > 1 logits can be compared
+        with the N = 1 graph (tp_parity below)."""
+        shape = list(t.shape())
+        if shard is not None and w > 1:
+            shape[{"col": 1, "row": 0, "head": 1}[shard]] *= w
+        gen.manual_seed(seed)
+        tmp = torch.empty(shape, dtype=torch.bfloat16, device="cuda").normal_(mean, std, generator=gen)
+        if shard is not None and w > 1:
+            ax = {"col": 1, "row": 0, "head": 1}[shard]
+            n = shape[ax] // w
+            tmp = tmp.narrow(ax, r * n, n).contiguous()
+        L.check(L.lib.it_b200_copy(ctypes.c_void_p(tmp.data_ptr()), ctypes.c_void_p(t.device_ptr()), t.nbytes(), ts))
+        torch.cuda.current_stream().synchronize()
+
+    def fill_fp8(t, tscale, seed):
+        """N(0, 0.02^2) weights quantised on the device: per-column scale = max|column| / 448, codes = E4M3(w / scale)"""
+        gen.manual_seed(seed)
+        wf = torch.empty(t.shape(), dtype=torch.float32, device="cuda").normal_(0.0, 0.02, generator=gen)
+        scale = (wf.abs().amax(dim=0).clamp_min(1e-12) / 448.0).contiguous()
+        codes = (wf / scale[None, :]).to(torch.float8_e4m3fn).view(torch.uint8).contiguous()
+        L.check(L.lib.it_b200_copy(ctypes.c_void_p(codes.data_ptr()), ctypes.c_void_p(t.device_ptr()), t.nbytes(), ts))
+        L.check(L.lib.it_b200_copy(ctypes.c_void_p(scale.data_ptr()), ctypes.c_void_p(tscale.device_ptr()), tscale.nbytes(), ts))
+        torch.cuda.current_stream().synchronize()
+
+    def fill_graph(gr, w, r):
+        for i, (name, (t, shape, kind, shard)) in enumerate(gr.weights.items()):
+            if kind == "scale":
+                continue
+            if kind == "proj_fp8":
+                fill_fp8(t, gr.weights[name + ".scale"][0], 1000 + i)
+                continue
+            fill(t, 0.02, 1.0 if kind == "norm" else 0.0, seed=1000 + i, shard=shard[0] if shard else None, w=w, r=r)
+        for li in range(cfg.layers):
+            fill(gr.k_caches[li], 0.5, seed=5000 + li, shard="head", w=w, r=r)
+            fill(gr.v_caches[li], 0.5, seed=7000 + li, shard="head", w=w, r=r)
+
+    fill_graph(g, world, rank)
+    ids_host = torch.from_numpy(np.random.default_rng(1).integers(0, cfg.vocab, size=(cfg.batch, 1)).astype(np.int64)).pin_memory()
+    pos_host = torch.full((cfg.batch, 1), POS, dtype=torch.int64).pin_memory()
+    logits_host = torch.empty((cfg.batch, 1, cfg.vocab), dtype=torch.bfloat16).pin_memory()
+    g.input_ids.copyin_numpy(ids_host.numpy())
+    g.position_ids.copyin_numpy(pos_host.numpy())
+
+    stream = torch.cuda.ExternalStream(rt.stream())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step = h.run if args.eager else h.run_with_cudagraph
+    launch_async = h.run_without_sync if args.eager else h.launch_cudagraph_async
+
+    # ranks finish building at slightly different times; the peer-memory all-reduce spins on its peers (bounded), so line
+    # them up before the first collective
+    barrier()
+    # one eager pass counts our kernel launches per step (graph replay re-issues exactly these)
+    l0 = rt.kernel_launches()
+    h.run()
+    launches_per_step = rt.kernel_launches() - l0
+    for _ in range(max(args.warmup, 3)):
+        step()
+
+    # ---- value: device-timed graph replays, inputs resident
+    # The clock sampler (a fork of nvidia-smi) starts BEFORE the barrier, and one UNTIMED replay follows the barrier: its
+    # in-graph all-reduces put the ranks in device lock-step, and it gives every host 2-3 ms of queued device work to
+    # enqueue e0 and the timed replays behind -- so no rank's start event can land while a peer is already spinning in a
+    # collective of the timed region (round 1's N = 2 line was inflated by exactly that skew).
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    launch_async()
+    e0.record(stream)
+    for _ in range(args.steps):
+        launch_async()
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    ms_mine = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(ms_mine)
+    ms_step = ms_total / args.steps
+    tok_s = cfg.batch * 1000.0 / ms_step
+    ms_ranks = [ms_mine / args.steps]
+    if world > 1:
+        allms = [None] * world
+        dist.all_gather_object(allms, ms_mine / args.steps)
+        ms_ranks = [float(x) for x in allms]
+
+    # ---- e2e: host buffers in, host logits out, every step
+    h2d = ids_host.numel() * 8 + pos_host.numel() * 8
+    d2h = logits_host.numel() * 2
+    for _ in range(3):
+        g.input_ids.copyin_async(ids_host.data_ptr(), ids_host.numel() * 8)
+        g.position_ids.copyin_async(pos_host.data_ptr(), pos_host.numel() * 8)
+        launch_async()
+        g.logits.copyout_async(logits_host.data_ptr(), d2h)
+        h.sync()
+    barrier()
+    launch_async()  # untimed: device lock-step across ranks, as above
+    h.sync()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        g.input_ids.copyin_async(ids_host.data_ptr(), ids_host.numel() * 8)
+        g.position_ids.copyin_async(pos_host.data_ptr(), pos_host.numel() * 8)
+        launch_async()
+        g.logits.copyout_async(logits_host.data_ptr(), d2h)
+        h.sync()  # the next token depends on this step's logits being on the host
+    e1.record(stream)
+    e1.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / args.steps
+    clocks = sampler.stop() if sampler else None
+    logits_finite = bool(torch.isfinite(logits_host.float()).all())
+
+    # ---- roofline of the dominant kernel (gemm_skinny_kernel): all MatMuls of one step, back to back on the
+    # runtime stream, CUDA events around them, repeated; algorithmic bytes = weight + activation in/out bytes
+    e = 2
+    d, dl, f, fl, V = cfg.d_model, cfg.d_model // world, cfg.ffn, cfg.ffn // world, cfg.vocab
+    # the launches the step's schedule issues for MatMul: grouped q/k/v, o, grouped gate/up, down per layer + logits
+    mm = []  # (list of weight tensors, K, N of each)
+    for li in range(cfg.layers):
+        p = f"l{li}."
+        mm.append(([g.weights[p + "wq"][0], g.weights[p + "wk"][0], g.weights[p + "wv"][0]], d, dl))
+        mm.append(([g.weights[p + "wo"][0]], dl, d))
+        mm.append(([g.weights[p + "wg"][0], g.weights[p + "wu"][0]], d, fl))
+        mm.append(([g.weights[p + "wd"][0]], fl, d))
+    mm.append(([g.weights["lm_head"][0]], d, V))
+    scratch_in = torch.zeros((cfg.batch, max(f, d)), dtype=torch.bfloat16, device="cuda")
+    scratch_out = [torch.zeros((cfg.batch, V), dtype=torch.bfloat16, device="cuda") for _ in range(3)]
+    rs = ctypes.c_void_p(rt.stream())
+    we = 1 if cfg.fp8_weights else e  # bytes per weight element
+    gemm_bytes = sum(len(ws) * (K_ * N_ * we + (4 * N_ if cfg.fp8_weights else 0) + cfg.batch * N_ * e) + cfg.batch * K_ * e for ws, K_, N_ in mm)
+    gemm_launches = len(mm)
+    calls = []
+    wname = {id(t): nme for nme, (t, _s, _k, _sh) in g.weights.items()}
+    for ws, K_, N_ in mm:
+        W = (ctypes.c_void_p * len(ws))(*[w.device_ptr() for w in ws])
+        C = (ctypes.c_void_p * len(ws))(*[scratch_out[i].data_ptr() for i in range(len(ws))])
+        N = (ctypes.c_int * len(ws))(*[N_] * len(ws))
+        Sc = None
+        if cfg.fp8_weights:
+            Sc = (ctypes.c_void_p * len(ws))(*[g.weights[wname[id(w)] + ".scale"][0].device_ptr() for w in ws])
+        calls.append((len(ws), W, C, N, K_, Sc))
+
+    def gemm_pass():
+        for n_, W, C, N, K_, Sc in calls:
+            if Sc is not None:
+                L.check(L.lib.it_b200_matmul_fp8w(16, ctypes.c_void_p(scratch_in.data_ptr()), n_, W, Sc, C, N, cfg.batch, K_, None, rs))
+            else:
+                L.check(L.lib.it_b200_matmul_grouped(16, ctypes.c_void_p(scratch_in.data_ptr()), n_, W, C, N, cfg.batch, K_, rs))
+    torch.cuda.synchronize()
+    for _ in range(2):
+        gemm_pass()
+    reps = max(3, min(args.steps, 10))
+    e0.record(stream)
+    for _ in range(reps):
+        gemm_pass()
+    e1.record(stream)
+    e1.synchronize()
+    gemm_ms = e0.elapsed_time(e1) / reps
+    achieved = gemm_bytes / (gemm_ms * 1e-3) / 1e9
+
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        try:
+            peak = float(json.load(open(pk))["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "gemm_skinny_traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            # measured DRAM bytes, average per launch, from an ncu capture of THIS world size's launch list (null when none
+            # was taken: per-launch bytes shrink with 1/N for the sharded GEMMs)
+            traffic = tj.get("by_world", {}).get(str(world), {}).get("dram_bytes_per_launch")
+            if traffic is None and world == 1:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    step_bytes = cfg.algorithmic_bytes(POS, world)
+
+    # ---- tensor-parallel parity, checked IN the bench (the driver's pytest box has one GPU, so this is where a broken
+    # sharded path must fail loudly): rank 0 builds the UNSHARDED graph of the same seeds on its own GPU, runs one step
+    # through the N = 1 path (itself oracle-checked at this width by tests/test_gpu_graph.py) and compares the logits the
+    # N ranks just produced (criterion below).
+    tp_parity = None
+    if world > 1 and os.environ.get("ITB_BENCH_NO_TP_PARITY", "0") != "1":
+        ok = [True]
+        if rank == 0:
+            h1 = B.GraphHandler(rt)
+            g1 = G.build_llama_decode(h1, cfg, 1, 0)
+            h1.data_malloc()
+            fill_graph(g1, 1, 0)
+            g1.input_ids.copyin_numpy(ids_host.numpy())
+            g1.position_ids.copyin_numpy(pos_host.numpy())
+            h1.run()
+            ref = G.from_storage(g1.logits.copyout_numpy(), cfg.dtype).astype(np.float64).reshape(cfg.batch, -1)
+            got = logits_host.float().numpy().astype(np.float64).reshape(cfg.batch, -1)
+            rel = float(np.abs(got - ref).max() / np.abs(ref).max())
+            rel_l2 = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+            agree = float((got.argmax(-1) == ref.argmax(-1)).mean())
+            # criterion: the reference's own end-to-end check -- rtol = atol = 1e-3 ELSE argmax-equal
+            # (examples/python/llama_kvcache_inference.py:133-141) -- plus bounds that separate rounding noise from a wrong
+            # shard: 32 bf16 layers with another fp32 summation order per row-split GEMM measure ~5e-2 of max on the worst
+            # of 512 k logits (random weights: logits are noise-like sums) and ~1e-2 in L2; a mis-sharded weight or a broken
+            # all-reduce gives O(1) on both and random argmax.
+            tp_parity = {"tp_parity_rel_err": rel, "rel_l2": rel_l2, "argmax_agreement": agree,
+                         "tolerance": {"argmax_agreement_min": 0.9, "rel_l2_max": 5e-2, "rel_to_max_max": 0.15},
+                         "against": "unsharded graph of the same seeds, one step on rank 0's GPU (N = 1 path)",
+                         "pass": bool(agree >= 0.9 and rel_l2 < 5e-2 and rel < 0.15 and logits_finite)}
+            ok[0] = tp_parity["pass"]
+            del h1, g1
+        dist.broadcast_object_list(ok, src=0)
+        if not ok[0]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "n_gpus": world, "invalid": "tensor-parallel parity FAILED",
+                                  "tp_parity": tp_parity}), flush=True)
+            dist.barrier()
+            dist.destroy_process_group()
+            return 3
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(tok_s, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "llama7b_shape_decode_bf16_b16_p511_smax1024", "layers": cfg.layers, "d_model": cfg.d_model,
+                       "heads": cfg.heads, "ffn": cfg.ffn, "vocab": cfg.vocab, "batch": cfg.batch, "position": POS,
+                       "s_max": cfg.s_max, "parallelism": f"tp{world}", "replay": "eager" if args.eager else "cuda_graph",
+                       "l2": "each step streams >= 17 GB (N=1) through a 126 MB L2; inputs >> L2, no flush",
+                       "weight_arena_bytes": wbytes, "activation_arena_bytes": abytes, "logits_finite": logits_finite},
+            "clocks": clocks,
+            "ms_per_step_ranks": [round(x, 4) for x in ms_ranks],
+            "tp_parity": tp_parity,
+            "tp_parity_rel_err": tp_parity["tp_parity_rel_err"] if tp_parity else None,
+            "e2e": {"value": round(cfg.batch * 1000.0 / e2e_ms, 2), "unit": "tokens/s", "ms_per_step": round(e2e_ms, 4),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "roofline": {"kernel": "gemm_skinny_kernel (every MatMul launch of one step: grouped q/k/v, o, grouped gate/up, down x layers + logits)", "bound": "hbm",
+                         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": traffic, "peak_source": peak_src, "launches": gemm_launches,
+                         "algorithmic_bytes_per_step": gemm_bytes, "ms_per_step_in_kernel": round(gemm_ms, 4)},
+            "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": round(step_bytes / (ms_step * 1e-3) / 1e9, 1),
+                              "peak": peak, "unit": "GB/s", "frac": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4)},
+        }
+        if args.layers != 32:
+            line["invalid"] = "debug run: --layers != 32"
+        if cfg.fp8_weights:
+            line["dtype"] = "bf16 activations / KV cache, fp8-e4m3 projection weights (weight-only, dequantised in the GEMM)"
+            line["headline"] = False
+            line["note"] = "SURVEY 8(f-4) line: NOT BASELINE.json's bf16 config -- reported beside the bf16 headline, never instead of it"
+            line["config"]["workload"] = "llama7b_shape_decode_fp8w_b16_p511_smax1024"
+            line["roofline"]["kernel"] = "gemm_skinny_kernel<W8> (fp8 weight codes converted in the main loop, column scale in the epilogue)"
+            line["roofline"]["traffic"] = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            tps, t_step, desc, _n = cpu_decode_sample(cfg, 2, threads, full_steps=1, budget_s=60.0)
+            line["cpu_baseline"] = {"value": round(tps, 3), "unit": "tokens/s", "cores": threads, "kind": "port", "sample": desc}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ BASELINE configs[1] / [3]
+def run_model_config(args):
+    """GPT-2-small (B = 1, S = 128, fp16) / ResNet-50 (B = 64, fp16) forward on ONE GPU: the same contract as the headline line
+    (device-timed CUDA-graph replays with resident inputs = value; host buffers in and out every step = e2e; clocks), with the
+    roofline that bounds each: GPT-2 streams 249 MB of weights per forward but is latency-bound (launch count reported);
+    ResNet-50 is tensor-bound (2 x 4.09 GMAC x batch against the measured dense bf16/fp16 peak)."""
+    import numpy as np
+    import torch
+    from infinitensor_b200 import backend as B
+    from infinitensor_b200 import graphs as G
+
+    assert args.gpus == 1, "configs[1] and [3] are single-GPU (replicas only)"
+    torch.cuda.set_device(0)
+    rt = B.CudaRuntime(0)
+    h = B.GraphHandler(rt)
+    if args.config == "gpt2":
+        cfg = G.GPT2Config()
+        g = G.build_gpt2(h, cfg)
+        h.data_malloc()
+        G.fill_gpt2_weights_host(g)
+        ids = torch.from_numpy(np.random.default_rng(1).integers(0, cfg.vocab, size=(cfg.batch, cfg.seq)).astype(np.int64)).pin_memory()
+        pos = torch.from_numpy(np.arange(cfg.seq, dtype=np.int64).reshape(1, -1).repeat(cfg.batch, 0)).pin_memory()
+        ins = [(g.input_ids, ids), (g.position_ids, pos)]
+        out_t, out_host = g.out, torch.empty((cfg.batch, cfg.seq, cfg.d_model), dtype=torch.float16).pin_memory()
+        units, unit = cfg.batch * cfg.seq, "tokens/s"
+        metric = "tokens/sec (device-timed) GPT-2-small forward, batch 1 x seq 128, fp16, 1 B200"
+        wbytes = (12 * 7087872 + 50257 * 768 + 1024 * 768) * 2
+        work = {"bound": "hbm", "per_step": wbytes, "unit": "GB/s", "what": "weight bytes read once per forward (SURVEY 8(d): 248.9 MB)"}
+        workload = {"workload": "gpt2_small_b1_s128_fp16", "layers": cfg.layers, "d_model": cfg.d_model, "heads": cfg.heads,
+                    "seq": cfg.seq, "batch": cfg.batch}
+    else:
+        cfg = G.ResNetConfig()
+        g = G.build_resnet50(h, cfg)
+        h.data_malloc()
+        G.fill_resnet_weights_host(g)
+        x = np.random.default_rng(3).standard_normal((cfg.batch, 3, cfg.image, cfg.image)).astype(np.float32)
+        xin = torch.from_numpy(G.to_storage(x, cfg.dtype).view(np.uint16).copy()).pin_memory()
+        ins = [(g.input, xin)]
+        out_t, out_host = g.out, torch.empty((cfg.batch, cfg.classes), dtype=torch.float16).pin_memory()
+        units, unit = cfg.batch, "images/s"
+        metric = "images/sec (device-timed) ResNet-50 forward, batch 64, fp16, conv/im2col-GEMM path, 1 B200"
+        work = {"bound": "tensor", "per_step": 2 * 4.09e9 * cfg.batch, "unit": "TFLOP/s", "what": "2 x 4.09 GMAC x batch (SURVEY 8(d))"}
+        workload = {"workload": "resnet50_b64_fp16", "batch": cfg.batch, "image": cfg.image}
+    for t, hbuf in ins:
+        t.copyin_async(hbuf.data_ptr(), hbuf.numel() * hbuf.element_size())
+    h.sync()
+    stream = torch.cuda.ExternalStream(rt.stream())
+    l0 = rt.kernel_launches()
+    h.run()
+    launches = rt.kernel_launches() - l0
+    for _ in range(max(args.warmup, 3)):
+        h.run_with_cudagraph()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(0)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        h.launch_cudagraph_async()
+    e1.record(stream)
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    h2d = sum(hb.numel() * hb.element_size() for _, hb in ins)
+    d2h = out_host.numel() * out_host.element_size()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        for t, hbuf in ins:
+            t.copyin_async(hbuf.data_ptr(), hbuf.numel() * hbuf.element_size())
+        h.launch_cudagraph_async()
+        out_t.copyout_async(out_host.data_ptr(), d2h)
+        h.sync()
+    e1.record(stream)
+    e1.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+    clocks = sampler.stop()
+    pk = {}
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if work["bound"] == "hbm":
+        peak, src = float(pk.get("hbm_gbs", 6650.0)), "MEASURED_PEAKS.json hbm_gbs" if pk else "fallback"
+        achieved = work["per_step"] / (ms * 1e-3) / 1e9
+    else:
+        peak, src = float(pk.get("bf16_tflops", 1590.0)), "MEASURED_PEAKS.json bf16_tflops (burst)" if pk else "fallback"
+        achieved = work["per_step"] / (ms * 1e-3) / 1e12
+    line = {"metric": metric, "value": round(units * 1e3 / ms, 1), "unit": unit, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16", "data": "synthetic", "config": dict(workload, replay="cuda_graph", parallelism="single GPU (replicas only)",
+                                                                   l2="working set < L2 for GPT-2 (latency-bound); ResNet activations 77 MB/layer stream"),
+            "clocks": clocks, "e2e": {"value": round(units * 1e3 / e2e_ms, 1), "unit": unit, "ms_per_step": round(e2e_ms, 4),
+                                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
+            "roofline": {"bound": work["bound"], "achieved": round(achieved, 2), "peak": peak, "unit": work["unit"],
+                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": src, "work_per_step": work["per_step"],
+                         "what": work["what"], "scheduled_steps": len(h.schedule())},
+            "output_finite": bool(torch.isfinite(out_host.float()).all())}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl != "reference" and a.config != "llama":
+        sys.exit(run_model_config(a))
+    sys.exit(run_reference(a) if a.impl == "reference" else run_b200(a))

@@ -358,7 +358,11 @@ void runMatmul(const Operator &_op, const RuntimeObj *ctx, const Tensor &residua
     auto op = as<MatmulObj>(_op);
     auto A = op->getInputs(0), B = op->getInputs(1);
     auto C = outOverride ? outOverride : op->getOutput();
+#ifdef ITB_SEAM_A
     IT_ASSERT(A->getDType() == B->getDType(), "MatMul operands must share a dtype");
+#else
+    IT_ASSERT(A->getDType() == B->getDType() || op->getWScale(), "MatMul operands must share a dtype (or B = FP8 codes + scale)");
+#endif
     auto [b_, m_, n, k] = op->getBMNK();
     int b = b_, m = m_;
     // batch rule of the reference (matmul.cc:124-137): full batch or stride-0 broadcast
