@@ -184,6 +184,12 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const __grid_co
                 for (int bx = 0; bx < NB; ++bx) {  // warp w owns columns [16w, 16w+16) of every 64-column box
                     uint32_t b0, b1, b2, b3;
                     if constexpr (W8) {
+                        // MEASURED (profiles/r02_fp8_gemm.md): this mma.sync path is INSTRUCTION-bound, not HBM-bound -- ~700 warp
+                        // instructions per 4 KB chunk (byte gathers + e4m3 -> bf16 conversion), ~1.1 TB/s of fp8 bytes, i.e. slower
+                        // than the bf16 GEMM.  Three rewrites (64B / 128B-swizzled boxes with 16-byte broadcast loads, a full-rate
+                        // FMUL conversion, a packed SIMD-in-register conversion) all landed within 10 % of it.  It halves the weight
+                        // footprint and is parity-exact; the bandwidth win needs the tensor core to consume the codes directly
+                        // (tcgen05 kind::f8f6f4 with quantised activations) -- see DESIGN.md section 9.
                         // FP8 weights: the box is [64 k][64 n] bytes, unswizzled.  B fragment of mma.m16n8k16 (col-major): lane
                         // (g = lane / 4, t = lane % 4) holds {W[2t][g], W[2t+1][g]} and {W[2t+8][g], W[2t+9][g]} of each 8-column
                         // tile -- two byte loads per register, converted to the activation type on the way (the "dequant" of
