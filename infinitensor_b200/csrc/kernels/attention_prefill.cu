@@ -96,18 +96,32 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
     auto load_mask = [&](int j0) {
         if (!mbase) return;
         const int jc = (threadIdx.x & 15) * 8, r0 = threadIdx.x >> 4;
-        for (int r = r0; r < AP_BQ; r += 8) {
-            T vals[8];
-            const bool rok = q0 + r < a.Sq;
-            const T *src = mbase + (int64_t)(q0 + r) * a.mi + (int64_t)(j0 + jc) * a.mj;
-            if (rok && mvec && j0 + jc + 8 <= a.Skv && ((((int64_t)(q0 + r) * a.mi + j0 + jc) & 7) == 0)) {
-                *reinterpret_cast<uint4 *>(vals) = *reinterpret_cast<const uint4 *>(src);
-            } else {
+        // 8 rows' loads in flight before the first transposing store (the stores may alias the mask as far as the compiler
+        // knows: issued row by row, the 16 dependent L2 round trips alone cost ~16 us per tile -- measured)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) vals[e] = (rok && j0 + jc + e < a.Skv) ? src[(int64_t)e * a.mj] : from_f<T>(0.f);
+        for (int hb = 0; hb < 2; ++hb) {
+            uint4 buf[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 8 * (hb * 8 + i);
+                const bool rok = q0 + r < a.Sq;
+                const T *src = mbase + (int64_t)(q0 + r) * a.mi + (int64_t)(j0 + jc) * a.mj;
+                if (rok && mvec && j0 + jc + 8 <= a.Skv && ((((int64_t)(q0 + r) * a.mi + j0 + jc) & 7) == 0)) {
+                    buf[i] = __ldg(reinterpret_cast<const uint4 *>(src));
+                } else {
+                    T vals[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) vals[e] = (rok && j0 + jc + e < a.Skv) ? src[(int64_t)e * a.mj] : from_f<T>(0.f);
+                    buf[i] = *reinterpret_cast<const uint4 *>(vals);
+                }
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) m_sm[(jc + e) * AP_MPAD + r] = vals[e];
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 8 * (hb * 8 + i);
+                const T *vals = reinterpret_cast<const T *>(&buf[i]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) m_sm[(jc + e) * AP_MPAD + r] = vals[e];
+            }
         }
     };
     const bool row_ok = q0 + row < a.Sq;
@@ -177,11 +191,13 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
 
     // ---------------- pass B: P = softmax row (final), O += P V ----------------
+    const bool single = ntiles == 1;  // one key tile (GPT-2's S = 128): K and the mask tile of pass A are still in shared memory
     for (int t = 0; t < ntiles; ++t) {
         if (threadIdx.x == 0) {
-            mbar_expect_tx(&bar_load, QK_BYTES + V_BYTES);
+            mbar_expect_tx(&bar_load, (single ? 0 : QK_BYTES) + V_BYTES);
+            if (!single)
 #pragma unroll
-            for (int g = 0; g < DG; ++g) tma_load_3d(k_sm + g * (AP_BK * 128), &mapK, &bar_load, g * 64, t * AP_BK, bh, pol);
+                for (int g = 0; g < DG; ++g) tma_load_3d(k_sm + g * (AP_BK * 128), &mapK, &bar_load, g * 64, t * AP_BK, bh, pol);
 #pragma unroll
             for (int g = 0; g < DG; ++g)
 #pragma unroll
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
                     tma_load_3d(v_sm + g * (AP_BK * 128) + hh * (64 * 128), &mapV, &bar_load, g * 64, t * AP_BK + hh * 64, bh, pol);
         }
         const int j0 = t * AP_BK;
-        load_mask(j0);  // (every reader of the previous tile's mask passed the __syncthreads before that tile's P.V)
+        if (!single) load_mask(j0);  // (every reader of the previous tile's mask passed the __syncthreads before that tile's P.V)
         mbar_wait(&bar_load, ph_load);
         ph_load ^= 1;
         mma_s();
