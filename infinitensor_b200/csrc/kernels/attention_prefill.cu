@@ -78,14 +78,23 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
     const uint64_t pol = l2_policy_evict_last();
     uint32_t ph_load = 0, ph_mma = 0;
 
-    // Q tile once
+    // Q tile once -- together with the first K tile (and V when there is only one key tile): one round trip instead of three
+    const int ntiles = (a.Skv + AP_BK - 1) / AP_BK;
+    const bool single = ntiles == 1;  // one key tile (GPT-2's S = 128): K, V and the mask tile stay in shared memory for both passes
     if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar_load, QK_BYTES);
+        mbar_expect_tx(&bar_load, QK_BYTES + (ntiles > 0 ? QK_BYTES : 0) + (single ? V_BYTES : 0));
 #pragma unroll
         for (int g = 0; g < DG; ++g) tma_load_3d(q_sm + g * (AP_BQ * 128), &mapQ, &bar_load, g * 64, q0, bh, pol);
+        if (ntiles > 0)
+#pragma unroll
+            for (int g = 0; g < DG; ++g) tma_load_3d(k_sm + g * (AP_BK * 128), &mapK, &bar_load, g * 64, 0, bh, pol);
+        if (single)
+#pragma unroll
+            for (int g = 0; g < DG; ++g)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh)
+                    tma_load_3d(v_sm + g * (AP_BK * 128) + hh * (64 * 128), &mapV, &bar_load, g * 64, hh * 64, bh, pol);
     }
-    mbar_wait(&bar_load, ph_load);
-    ph_load ^= 1;
 
     float sc = 1.f;
     if (a.scale) sc = to_f(*(const T *)a.scale);
@@ -125,7 +134,6 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
         }
     };
     const bool row_ok = q0 + row < a.Sq;
-    const int ntiles = (a.Skv + AP_BK - 1) / AP_BK;
 
     // score of (this row, key j0 + c) from the raw accumulator value, with the graph's rounding points
     auto score = [&](float acc, int j) -> float {
@@ -156,8 +164,12 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
 
     // ---------------- pass A: row maximum and sum over all keys ----------------
     float m = -INFINITY, l = 0.f;
+    if (ntiles == 0) {  // no keys: only Q was requested
+        mbar_wait(&bar_load, ph_load);
+        ph_load ^= 1;
+    }
     for (int t = 0; t < ntiles; ++t) {
-        load_k(t);
+        if (t > 0) load_k(t);  // (tile 0 came with Q)
         const int j0 = t * AP_BK;
         load_mask(j0);  // (the previous tile's readers are behind the __syncthreads that closed it)
         mbar_wait(&bar_load, ph_load);
@@ -191,13 +203,11 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
 
     // ---------------- pass B: P = softmax row (final), O += P V ----------------
-    const bool single = ntiles == 1;  // one key tile (GPT-2's S = 128): K and the mask tile of pass A are still in shared memory
     for (int t = 0; t < ntiles; ++t) {
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(&bar_load, (single ? 0 : QK_BYTES) + V_BYTES);
-            if (!single)
+        if (threadIdx.x == 0 && !single) {
+            mbar_expect_tx(&bar_load, QK_BYTES + V_BYTES);
 #pragma unroll
-                for (int g = 0; g < DG; ++g) tma_load_3d(k_sm + g * (AP_BK * 128), &mapK, &bar_load, g * 64, t * AP_BK, bh, pol);
+            for (int g = 0; g < DG; ++g) tma_load_3d(k_sm + g * (AP_BK * 128), &mapK, &bar_load, g * 64, t * AP_BK, bh, pol);
 #pragma unroll
             for (int g = 0; g < DG; ++g)
 #pragma unroll
@@ -205,9 +215,11 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
                     tma_load_3d(v_sm + g * (AP_BK * 128) + hh * (64 * 128), &mapV, &bar_load, g * 64, t * AP_BK + hh * 64, bh, pol);
         }
         const int j0 = t * AP_BK;
-        if (!single) load_mask(j0);  // (every reader of the previous tile's mask passed the __syncthreads before that tile's P.V)
-        mbar_wait(&bar_load, ph_load);
-        ph_load ^= 1;
+        if (!single) {
+            load_mask(j0);  // (every reader of the previous tile's mask passed the __syncthreads before that tile's P.V)
+            mbar_wait(&bar_load, ph_load);
+            ph_load ^= 1;
+        }
         mma_s();
         __syncthreads();  // mask tile complete
         mbar_wait(&bar_mma, ph_mma);
