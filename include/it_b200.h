@@ -204,6 +204,21 @@ int it_b200_conv2d_fused(int dtype, const void *x, const void *w, void *y, int N
                          const float *bn_var, const float *bn_scale, const float *bn_bias, float bn_eps,
                          const void *residual, int relu, void *workspace, int64_t workspace_bytes, void *stream);
 
+/* Implicit-GEMM Conv over NHWC activations (kernels/conv_nhwc.cu): x is [N, H, W, C], w stays in the reference's [F, C, R, S]
+ * order, y is [N, OH, OW, F] (y_nhwc = 1) or [N, F, OH, OW] (y_nhwc = 0, for a consumer outside the NHWC domain); `residual` is
+ * laid out like y.  No im2col matrix: the TMA unit's im2col mode feeds tcgen05 directly.  The optional tail
+ * BatchNorm (fp32 statistics, folded to y = a * conv + b) -> + residual -> ReLU is evaluated in fp32 and rounded ONCE (the NCHW
+ * entry point above rounds after every stage).  f16 / bf16, groups = 1, C % 8 == 0, F % 8 == 0, strides <= 8; _supported answers
+ * 1 for shapes the kernel takes.  Workspace: the filters re-ordered to [F][R*S][ceil64(C)] (0 bytes for 1x1 filters).
+ * Replaces cudnnConvolutionForward (reference src/kernels/cuda/conv.cc:143-168) for the layout the runtime's NHWC domain uses
+ * between Conv / Pool / Add / Relu steps (host/schedule.cc). */
+int it_b200_conv2d_nhwc_supported(int dtype, int C, int F, int R, int S, int ph, int pw, int sh, int sw, int dh, int dw,
+                                  int groups);
+int64_t it_b200_conv2d_nhwc_workspace(int dtype, int C, int F, int R, int S);
+int it_b200_conv2d_nhwc(int dtype, const void *x, const void *w, void *y, int y_nhwc, int N, int C, int H, int W, int F, int R,
+                        int S, int ph, int pw, int sh, int sw, int dh, int dw, const float *bn_mean, const float *bn_var,
+                        const float *bn_scale, const float *bn_bias, float bn_eps, const void *residual, int relu,
+                        void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ---- AttentionKVCache (decode, q-len 1): replaces _attention_kvcache_kernel_128_1/_2
  *      (attention_kvcache.cu:8-169).  Appends k,v IN PLACE into k_cache/v_cache at

@@ -66,6 +66,9 @@ _SIGS = {
     "it_b200_batchnorm_relu": (c_int, [c_int, vp, vp, vp, vp, vp, vp, c_int, c_int, c_int64, c_float, vp]),
     "it_b200_conv2d_fused": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, vp, vp, vp, c_float, vp, c_int, vp, c_int64, vp]),
     "it_b200_conv2d_workspace": (c_int64, [c_int] * 15),
+    "it_b200_conv2d_nhwc_supported": (c_int, [c_int] * 12),
+    "it_b200_conv2d_nhwc_workspace": (c_int64, [c_int] * 5),
+    "it_b200_conv2d_nhwc": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, vp, vp, vp, c_float, vp, c_int, vp, c_int64, vp]),
     "it_b200_conv2d": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, c_int64, vp]),
     "it_b200_attention_kvcache_workspace": (c_int64, [c_int] * 4),
     "it_b200_attention_kvcache_rope": (c_int, [c_int, vp, vp, vp, vp, vp, vp, c_int, vp, c_int, vp, c_int, c_int, c_int, c_int,

@@ -272,6 +272,29 @@ def conv2d_fused(x, w, ph, pw, sh, sw, dh, dw, bn, eps, residual, relu, dt=F16):
     return host(y)
 
 
+def conv2d_nhwc(x, w, ph, pw, sh, sw, dh, dw, bn=None, eps=1e-5, residual=None, relu=False, dt=F16, y_nhwc=True):
+    """x, residual and the result are NCHW numpy arrays; the permutation to / from NHWC happens here (host side)."""
+    N, C, H, W = x.shape
+    F, _, R, S = w.shape
+    OH = (H + 2 * ph - dh * (R - 1) - 1) // sh + 1
+    OW = (W + 2 * pw - dw * (S - 1) - 1) // sw + 1
+    xd, wd = dev(np.ascontiguousarray(x.transpose(0, 2, 3, 1)), dt), dev(w, dt)
+    y = torch.empty((N, OH, OW, F) if y_nhwc else (N, F, OH, OW), dtype=xd.dtype, device="cuda")
+    ms = [dev(np.asarray(v, np.float32)) for v in bn] if bn is not None else [None] * 4
+    rd = None
+    if residual is not None:
+        rd = dev(np.ascontiguousarray(residual.transpose(0, 2, 3, 1)) if y_nhwc else residual, dt)
+    assert L.lib.it_b200_conv2d_nhwc_supported(dt, C, F, R, S, ph, pw, sh, sw, dh, dw, 1) == 1
+    wsb = L.lib.it_b200_conv2d_nhwc_workspace(dt, C, F, R, S)
+    ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device="cuda")
+    L.check(L.lib.it_b200_conv2d_nhwc(dt, ptr(xd), ptr(wd), ptr(y), int(y_nhwc), N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw,
+                                      ptr(ms[0]), ptr(ms[1]), ptr(ms[2]), ptr(ms[3]), eps, ptr(rd), int(relu), ptr(ws), int(wsb),
+                                      stream()))
+    sync()
+    out = host(y)
+    return np.ascontiguousarray(out.transpose(0, 3, 1, 2)) if y_nhwc else out
+
+
 def matmul(a, b, bias=None, transA=False, transB=False, dt=F32, act=0):
     ad, bd = dev(a, dt), dev(b, dt)
     m = a.shape[-1] if transA else a.shape[-2]

@@ -411,6 +411,53 @@ def test_conv_fused_tail_bit_identical(K, dt):
           np.maximum(K.batch_norm(x, *[np.full(16, v, np.float32) for v in (0.1, 1.3, 0.9, -0.2)], 1e-5, dt=dt), 0), 0, 0)
 
 
+NHWC_CASES = [((2, 64, 56, 56), (256, 64, 1, 1), (0, 0, 1, 1, 1, 1)),      # 1x1, one k-tile, filters used as stored
+              ((2, 128, 28, 28), (128, 128, 3, 3), (1, 1, 1, 1, 1, 1)),   # 3x3 s1 p1
+              ((3, 256, 28, 28), (256, 256, 3, 3), (1, 1, 2, 2, 1, 1)),   # 3x3 s2 p1
+              ((2, 1024, 14, 14), (2048, 1024, 1, 1), (0, 0, 2, 2, 1, 1)),  # 1x1 s2 downsample, 8 filter tiles
+              ((5, 512, 7, 7), (512, 512, 3, 3), (1, 1, 1, 1, 1, 1)),     # P = 49: pixel tiles straddle images, ragged last tile
+              ((2, 2048, 7, 7), (512, 2048, 1, 1), (0, 0, 1, 1, 1, 1)),
+              ((3, 24, 19, 13), (40, 24, 3, 5), (1, 2, 2, 1, 1, 1)),      # ragged everything: C < 64, F < 64, asymmetric taps / pads / strides
+              ((2, 72, 11, 9), (304, 72, 3, 3), (2, 1, 1, 2, 2, 1)),      # C = 64 + 8, F = 256 + 48, dilation 2 along h
+              ((1, 8, 6, 6), (8, 8, 1, 1), (0, 0, 1, 1, 1, 1))]
+
+
+@pytest.mark.parametrize("dt", [F16, BF16])
+def test_conv_nhwc_parity(K, dt):
+    """Implicit-GEMM conv over NHWC activations (TMA im2col mode -> tcgen05) against the oracle's direct convolution."""
+    tol = {F16: 8e-3, BF16: 6e-2}[dt]
+    for ci, (xs, ws, args) in enumerate(NHWC_CASES):
+        x, w = rnd(xs, 126 + ci, dt), rnd(ws, 127 + ci, dt, 0.05)
+        want = oracle.conv2d(x, w, *args, dt=dt)
+        for y_nhwc in (True, False):
+            got = K.conv2d_nhwc(x, w, *args, dt=dt, y_nhwc=y_nhwc)
+            assert got.shape == want.shape
+            close(got, want, tol, tol)
+
+
+@pytest.mark.parametrize("dt", [F16, BF16])
+def test_conv_nhwc_fused_tail(K, dt):
+    """Conv -> BatchNorm -> [+ residual] -> [ReLU] in the implicit-GEMM epilogue (fp32, one rounding) against the oracle chain
+    (which rounds after every operator, like the reference's separate kernels)."""
+    tol = {F16: 2e-2, BF16: 1.5e-1}[dt]
+    for ci, (xs, ws, args) in enumerate(NHWC_CASES[:5] + NHWC_CASES[6:8]):
+        x, w = rnd(xs, 150 + ci, dt), rnd(ws, 160 + ci, dt, 0.05)
+        F = ws[0]
+        rng = np.random.default_rng(170 + ci)
+        bn = (rng.standard_normal(F).astype(np.float32) * 0.1, rng.uniform(0.5, 1.5, F).astype(np.float32),
+              rng.uniform(0.5, 1.5, F).astype(np.float32), rng.standard_normal(F).astype(np.float32) * 0.1)
+        conv = oracle.conv2d(x, w, *args, dt=dt)
+        res = rnd(conv.shape, 180 + ci, dt)
+        for use_res, relu, y_nhwc in [(False, False, True), (False, True, True), (True, True, True), (True, True, False)]:
+            ora = oracle.batch_norm(conv, *bn, 1e-5, dt)
+            if use_res:
+                ora = oracle.binary("add", ora, res, dt)
+            if relu:
+                ora = np.maximum(ora, 0)
+            got = K.conv2d_nhwc(x, w, *args, bn=bn, eps=1e-5, residual=res if use_res else None, relu=relu, dt=dt, y_nhwc=y_nhwc)
+            close(got, ora, tol, tol)
+
+
 @pytest.mark.parametrize("dt", [F32, F16, BF16])
 def test_conv_parity(K, dt):
     tol = {F32: 1e-4, F16: 4e-3, BF16: 3e-2}[dt]
