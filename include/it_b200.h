@@ -135,6 +135,10 @@ int it_b200_reduce(int dtype, int is_mean, const void *x, void *y, int rank, con
 int it_b200_pool2d(int dtype, int is_max, const void *x, void *y, int N, int C, int H, int W,
                    int kh, int kw, int dh, int dw, int ph, int pw, int sh, int sw, int OH, int OW,
                    void *stream);
+/* the same pooling over NHWC activations ([N, H, W, C] -> [N, OH, OW, C]; f16 / bf16, C % 8 == 0): the layout the runtime's NHWC
+ * domain keeps between Conv / Pool / Add / Relu steps (host/schedule.cc) */
+int it_b200_pool2d_nhwc(int dtype, int is_max, const void *x, void *y, int N, int C, int H, int W, int kh, int kw, int dh,
+                        int dw, int ph, int pw, int sh, int sw, int OH, int OW, void *stream);
 
 /* ---- BatchNormalization inference: replaces BatchNormCudnn (batch_norm.cc:9-69).
  *      mean/var/scale/bias are f32 (as the reference requires). ---- */
@@ -203,6 +207,16 @@ int it_b200_conv2d_fused(int dtype, const void *x, const void *w, void *y, int N
                          int S, int ph, int pw, int sh, int sw, int dh, int dw, int groups, const float *bn_mean,
                          const float *bn_var, const float *bn_scale, const float *bn_bias, float bn_eps,
                          const void *residual, int relu, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* it_b200_conv2d_fused with x in NCHW and y (and `residual`) in NHWC ([N, OH, OW, F]): the entry into the NHWC domain for a conv the
+ * implicit-GEMM kernel cannot take (the 3-channel stem).  _supported = 1 when the shape runs this way (f16 / bf16, groups 1,
+ * folded im2col GEMM, F % 8 == 0); otherwise the call returns 2 and launches nothing.  Same workspace as it_b200_conv2d. */
+int it_b200_conv2d_nchw_to_nhwc_supported(int dtype, int N, int C, int H, int W, int F, int R, int S, int ph, int pw, int sh,
+                                          int sw, int dh, int dw, int groups);
+int it_b200_conv2d_fused_nhwc_out(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W, int F, int R,
+                                  int S, int ph, int pw, int sh, int sw, int dh, int dw, int groups, const float *bn_mean,
+                                  const float *bn_var, const float *bn_scale, const float *bn_bias, float bn_eps,
+                                  const void *residual, int relu, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* Implicit-GEMM Conv over NHWC activations (kernels/conv_nhwc.cu): x is [N, H, W, C], w stays in the reference's [F, C, R, S]
  * order, y is [N, OH, OW, F] (y_nhwc = 1) or [N, F, OH, OW] (y_nhwc = 0, for a consumer outside the NHWC domain); `residual` is

@@ -53,6 +53,7 @@ _SIGS = {
     "it_b200_pad_slice": (c_int, [c_int, vp, vp, c_int, i64p, i64p, i64p, i64p, vp]),
     "it_b200_reduce": (c_int, [c_int, c_int, vp, vp, c_int, i64p, i32p, vp]),
     "it_b200_pool2d": (c_int, [c_int, c_int, vp, vp] + [c_int] * 14 + [vp]),
+    "it_b200_pool2d_nhwc": (c_int, [c_int, c_int, vp, vp] + [c_int] * 14 + [vp]),
     "it_b200_batchnorm": (c_int, [c_int, vp, vp, vp, vp, vp, vp, c_int, c_int, c_int64, c_float, vp]),
     "it_b200_matmul_workspace": (c_int64, [c_int, c_int64, c_int, c_int, c_int]),
     "it_b200_matmul": (c_int, [c_int, vp, vp, vp, vp, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_int, c_int,
@@ -66,6 +67,8 @@ _SIGS = {
     "it_b200_batchnorm_relu": (c_int, [c_int, vp, vp, vp, vp, vp, vp, c_int, c_int, c_int64, c_float, vp]),
     "it_b200_conv2d_fused": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, vp, vp, vp, c_float, vp, c_int, vp, c_int64, vp]),
     "it_b200_conv2d_workspace": (c_int64, [c_int] * 15),
+    "it_b200_conv2d_nchw_to_nhwc_supported": (c_int, [c_int] * 15),
+    "it_b200_conv2d_fused_nhwc_out": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, vp, vp, vp, c_float, vp, c_int, vp, c_int64, vp]),
     "it_b200_conv2d_nhwc_supported": (c_int, [c_int] * 12),
     "it_b200_conv2d_nhwc_workspace": (c_int64, [c_int] * 5),
     "it_b200_conv2d_nhwc": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, vp, vp, vp, c_float, vp, c_int, vp, c_int64, vp]),

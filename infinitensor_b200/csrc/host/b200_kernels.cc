@@ -607,10 +607,11 @@ bool runDecoderStack(const ExecStep &st, const RuntimeObj *ctx) {
     return true;
 }
 
-// Conv -> BatchNorm -> [Add(residual)] -> [Relu]: ops = {conv, bn, [add], [relu]}
-bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx) {
+// Conv -> BatchNorm -> [Add(residual)] -> [Relu]: ops = {conv, bn, [add], [relu]}; a lone Conv when ops.size() == 1.
+// layout (ExecStep::layout): bit 0 = x is NHWC -> implicit-GEMM kernel; bit 1 = y (and the residual) are NHWC
+bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx, int layout) {
     auto conv = as<ConvObj>(ops[0]);
-    auto bn = as<BatchNormObj>(ops[1]);
+    auto bn = ops.size() > 1 ? as<BatchNormObj>(ops[1]) : nullptr;
     Operator add, relu;
     for (size_t i = 2; i < ops.size(); ++i) {
         if (ops[i]->getOpType() == OpType::Add) add = ops[i];
@@ -620,15 +621,36 @@ bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx) {
     auto [n, c, h, wd, f, r, s] = conv->getNCHWFRS();
     auto [ph, pw, sh, sw, dh, dw] = conv->getPadStrideDilation();
     int g = conv->getNumGroups();
-    for (int i = 1; i <= 4; ++i)
-        if (bn->getInputs(i)->getDType() != DataType::Float32) return false;
+    for (int i = 1; bn && i <= 4; ++i)
+        if (bn->getInputs(i)->getDType() != DataType::Float32) {
+            IT_ASSERT(!layout, "NHWC conv step with non-fp32 BatchNorm statistics");
+            return false;
+        }
     Tensor res;
     if (add) {
         Tensor prev = bn->getOutput();
         res = add->getInputs(0) == prev ? add->getInputs(1) : add->getInputs(0);
     }
+    const float *bm = bn ? bn->getInputs(1)->getRawDataPtr<float *>() : nullptr, *bv = bn ? bn->getInputs(2)->getRawDataPtr<float *>() : nullptr,
+                *bs = bn ? bn->getInputs(3)->getRawDataPtr<float *>() : nullptr, *bb = bn ? bn->getInputs(4)->getRawDataPtr<float *>() : nullptr;
+    const float eps = bn ? bn->getEps() : 0.f;
+    if (layout & 1) {
+        int64_t wsb = it_b200_conv2d_nhwc_workspace(DTI(x), c, f, r, s);
+        void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
+        CK(it_b200_conv2d_nhwc(DTI(x), P(x), P(w), P(ops.back()->getOutput()), (layout & 2) ? 1 : 0, n, c, h, wd, f, r, s, ph, pw, sh, sw, dh,
+                               dw, bm, bv, bs, bb, eps, res ? P(res) : nullptr, relu ? 1 : 0, ws, wsb, S()), ops.back());
+        return true;
+    }
     int64_t wsb = it_b200_conv2d_workspace(DTI(x), n, c, h, wd, f, r, s, ph, pw, sh, sw, dh, dw, g);
     void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
+    if (layout & 2) {
+        int rc = it_b200_conv2d_fused_nhwc_out(DTI(x), P(x), P(w), P(ops.back()->getOutput()), n, c, h, wd, f, r, s, ph, pw, sh, sw, dh, dw, g,
+                                               bm, bv, bs, bb, eps, res ? P(res) : nullptr, relu ? 1 : 0, ws, wsb, S());
+        IT_ASSERT(rc != 2, "NHWC-output conv step on a shape the im2col GEMM does not scatter (schedule / kernel disagree)");
+        CK(rc, ops.back());
+        return true;
+    }
+    IT_ASSERT(bn, "runConvBnAct: a lone Conv runs through its registered kernel");
     int rc = it_b200_conv2d_fused(DTI(x), P(x), P(w), P(ops.back()->getOutput()), n, c, h, wd, f, r, s, ph, pw, sh, sw, dh,
                                   dw, g, bn->getInputs(1)->getRawDataPtr<float *>(),
                                   bn->getInputs(2)->getRawDataPtr<float *>(), bn->getInputs(3)->getRawDataPtr<float *>(),
@@ -637,6 +659,16 @@ bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx) {
     if (rc == 2) return false;
     CK(rc, ops.back());
     return true;
+}
+
+// MaxPool / AveragePool inside the NHWC domain
+void runPoolNhwc(const Operator &_op, const RuntimeObj *) {
+    auto op = as<PoolingObj>(_op);
+    auto x = op->getInputs(0), y = op->getOutput();
+    const auto &d = x->getDims();
+    const auto &o = y->getDims();
+    CK(it_b200_pool2d_nhwc(DTI(x), _op->getOpType() == OpType::MaxPool, P(x), P(y), d[0], d[1], d[2], d[3], op->getKh(), op->getKw(),
+                           op->getDh(), op->getDw(), op->getPh(), op->getPw(), op->getSh(), op->getSw(), o[2], o[3], S()), _op);
 }
 
 // AllReduceSum -> Add(residual) [-> RMSNorm] through the one-shot NVLink kernel

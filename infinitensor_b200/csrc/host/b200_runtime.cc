@@ -214,7 +214,11 @@ void CudaRuntimeObj::execStep(const ExecStep &st, Kernel *kernel, const PerfReco
         // the planner made the output share the input's storage: nothing to launch
         if (op->getInputs(0)->rawPtrOrNull() == op->getOutput()->rawPtrOrNull()) break;
         [[fallthrough]];  // distinct storage (naive allocator): the ordinary copy kernel
-    case ExecStep::Single: single(op); break;
+    case ExecStep::Single:
+        if (st.layout && op->getOpType() == OpType::Conv) b200::runConvBnAct(st.ops, this, st.layout);  // NHWC domain (schedule.cc)
+        else if (st.layout && (op->getOpType() == OpType::MaxPool || op->getOpType() == OpType::AveragePool)) b200::runPoolNhwc(op, this);
+        else single(op);  // (flat elementwise steps of the domain are layout-agnostic)
+        break;
     case ExecStep::MatMulGroup: b200::runMatmulGroup(st.ops, this); break;
     case ExecStep::MatMulAdd: {
         const auto &mm = st.ops[0], &add = st.ops[1];
@@ -225,7 +229,7 @@ void CudaRuntimeObj::execStep(const ExecStep &st, Kernel *kernel, const PerfReco
     case ExecStep::SiluMul: b200::runSiluMul(st.ops[0], st.ops[1], this); break;
     case ExecStep::AttentionRope: b200::runAttentionRope(st.ops[0], st.ops[1], st.ops[2], this); break;
     case ExecStep::ConvBnAct:
-        if (!b200::runConvBnAct(st.ops, this))
+        if (!b200::runConvBnAct(st.ops, this, st.layout))
             for (auto &m : st.ops) reg.getKernel(KernelAttrs{Device::CUDA, m->getOpType().underlying()})->compute(m, this);
         break;
     case ExecStep::AllReduceAddNorm:

@@ -151,7 +151,8 @@ void runSiluMul(const Operator &silu, const Operator &mul, const RuntimeObj *ctx
 // AllReduceSum -> Add(residual) [-> RMSNorm]: true if the fused NVLink kernel took it, false = run the ops one by one
 bool runAllReduceAddNorm(const OpVec &ops, const RuntimeObj *ctx);
 // Conv -> BatchNorm -> [Add] -> [Relu] in the GEMM epilogue; false = shape not taken (nothing launched)
-bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx);
+bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx, int layout = 0);
+void runPoolNhwc(const Operator &op, const RuntimeObj *ctx);
 void runAttentionRope(const Operator &ropeQ, const Operator &ropeK, const Operator &att, const RuntimeObj *ctx);
 // {Transpose(k), MatMul, [Div | Mul], [Add], Softmax, MatMul} as one fused tcgen05 attention kernel; false = not taken
 bool runPrefillAttention(const OpVec &ops, const RuntimeObj *ctx);

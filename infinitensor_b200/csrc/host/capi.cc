@@ -390,6 +390,9 @@ int itb_graph_step(itb_graph *g, int index, char *buf, int buf_len) {
             s += std::to_string(compute / 8) + "xLayer(" + std::to_string(compute) + " steps, " + std::to_string(sc[index].ops.size()) + " ops)";
         } else
             for (size_t i = 0; i < sc[index].ops.size(); ++i) s += (i ? "+" : "") + std::string(sc[index].ops[i]->getOpType().toString());
+        // NHWC domain: "@nhwc" = operands and result channel-innermost, "@>nhwc" = enters the domain, "@nhwc>" = leaves it
+        static const char *lay[] = {"", "@nhwc>", "@>nhwc", "@nhwc"};
+        s += lay[sc[index].layout & 3];
         snprintf(buf, buf_len, "%s", s.c_str());
     })
 }

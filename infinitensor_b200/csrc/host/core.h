@@ -369,6 +369,10 @@ struct ExecStep {
     } kind = Single;
     OpVec ops;
     vector<ExecStep> sub;
+    // NHWC domain (schedule.cc assignLayouts): bit 0 = the step's 4-D activation operands are stored [N, H, W, C], bit 1 = its
+    // result is.  The tensors keep their logical NCHW dims; only Conv / Pool / same-shape Add / Relu steps carry these bits, and
+    // graph inputs, outputs and every tensor some other operator reads stay NCHW.
+    int layout = 0;
 };
 
 // ---------------------------------------------------------------- Graph

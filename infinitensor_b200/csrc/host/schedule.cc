@@ -6,6 +6,7 @@
 #include <unordered_map>
 #include <unordered_set>
 
+#include "conv_shapes.h"
 #include "operators.h"
 
 namespace infini {
@@ -14,6 +15,7 @@ static bool fusionEnabled() {
     const char *e = std::getenv("ITB_NO_FUSION");
     return !(e && e[0] == '1');
 }
+// (bit 9 = NHWC domain for Conv / Pool / Add / Relu chains, on by default)
 // ITB_FUSION_MASK (debug / A-B): bit 0 alias, 1 MatMul groups, 2 MatMul+Add, 3 Silu*Mul, 4 AllReduce+Add+Norm, 5 RoPE->Attention, 6 Conv+BatchNorm[+Add][+Relu], 7 decoder-layer stacks (persistent kernel); default all
 static int fusionMask() {
     const char *e = std::getenv("ITB_FUSION_MASK");
@@ -22,7 +24,7 @@ static int fusionMask() {
     // bit 7 (decoder-layer stacks on the persistent kernel) is opt-in: measured on the BASELINE shape it does not yet beat the
     // eight tuned launches it replaces (165 vs 112 us per layer) -- ITB_DECODE_STACK=1 switches it on
     const char *ds = std::getenv("ITB_DECODE_STACK");
-    return ((ds && ds[0] == '1') ? 255 : 127) | 256;
+    return ((ds && ds[0] == '1') ? 255 : 127) | 256 | 512;
 }
 
 static bool isKvCacheOperand(const Tensor &t) {
@@ -294,6 +296,135 @@ static OpVec matchPrefillChain(const Operator &mm2op) {
     return chain;
 }
 
+// ---------------------------------------------------------------- NHWC domain
+// ResNet-style chains run fastest with channel-innermost activations: the implicit-GEMM conv (kernels/conv_nhwc.cu) reads them
+// through the TMA unit's im2col mode and no im2col matrix is ever written.  A tensor is stored NHWC only when EVERY step touching
+// it can work in that layout; the decision is a fixpoint over the schedule:
+//   Conv / Conv+BN[+Add][+Relu] : NHWC input needs the implicit-GEMM kernel's shape limits (it_b200_conv2d_nhwc_supported); its
+//                                 output (and residual, which must agree with the output) may be either layout.  With an NCHW
+//                                 input (the 3-channel stem) the im2col GEMM can still WRITE NHWC (it_b200_conv2d_nchw_to_nhwc_supported)
+//   MaxPool / AvgPool           : input and output agree (C % 8 == 0 for the NHWC kernel)
+//   Relu / Add of equal shapes  : flat elementwise, operands and result agree
+//   anything else, graph inputs / outputs / weights: NCHW
+// A [N, C, 1, 1] tensor is the same bytes either way and never constrains anything.
+namespace {
+struct LayoutPass {
+    enum Cls { Other, ConvStep, PoolStep, EltStep };
+    std::unordered_set<TensorObj *> nhwc;
+
+    static bool free4(const Tensor &t) {
+        auto &d = t->getDims();
+        return d.size() == 4 && d[2] * d[3] == 1;
+    }
+    static bool candidate(const Tensor &t) {
+        auto &d = t->getDims();
+        if (d.size() != 4 || free4(t)) return false;
+        auto dt = t->getDType();
+        if (!(dt == DataType::Float16 || dt == DataType::BFloat16)) return false;
+        return !t->isWeight() && !t->isInput() && !t->isOutput() && t->getSource() && !t->getTargets().empty();
+    }
+    static Cls classify(const ExecStep &st) {
+        const auto &op = st.ops.back();
+        if (st.kind == ExecStep::ConvBnAct) return ConvStep;
+        if (st.kind != ExecStep::Single) return Other;
+        auto ty = op->getOpType();
+        if (ty == OpType::Conv) return ConvStep;
+        if (ty == OpType::MaxPool || ty == OpType::AveragePool) {
+            auto &d = op->getInputs(0)->getDims();
+            return d.size() == 4 && d[1] % 8 == 0 ? PoolStep : Other;
+        }
+        if (ty == OpType::Relu) return EltStep;
+        if (ty == OpType::Add) {
+            auto &a = op->getInputs(0)->getDims(), &b = op->getInputs(1)->getDims();
+            return a == b && a == op->getOutput()->getDims() ? EltStep : Other;
+        }
+        return Other;
+    }
+    static Tensor convResidual(const ExecStep &st) {
+        for (size_t i = 2; i < st.ops.size(); ++i)
+            if (st.ops[i]->getOpType() == OpType::Add) {
+                Tensor prev = st.ops[i - 1]->getOutput();
+                return st.ops[i]->getInputs(0) == prev ? st.ops[i]->getInputs(1) : st.ops[i]->getInputs(0);
+            }
+        return nullptr;
+    }
+    bool is(const Tensor &t) const { return t && nhwc.count(t.get()) > 0; }
+    bool drop(const Tensor &t) { return t && nhwc.erase(t.get()) > 0; }
+
+    void run(vector<ExecStep> &schedule) {
+        // tensors written / read INSIDE a fused step never exist in memory; everything else a step touches is "external"
+        for (auto &st : schedule)
+            for (auto &op : st.ops) {
+                for (auto &t : op->getInputs())
+                    if (candidate(t)) nhwc.insert(t.get());
+                for (auto &t : op->getOutputs())
+                    if (candidate(t)) nhwc.insert(t.get());
+            }
+        bool changed = true;
+        while (changed) {
+            changed = false;
+            for (auto &st : schedule) {
+                Cls c = classify(st);
+                if (c == ConvStep) {
+                    auto conv = as<ConvObj>(st.ops[0]);
+                    Tensor x = conv->getInputs(0), y = st.ops.back()->getOutput(), res = convResidual(st);
+                    auto [n, ci, h, w, f, r, s] = conv->getNCHWFRS();
+                    auto [ph, pw, sh, sw, dh, dw] = conv->getPadStrideDilation();
+                    const int g = conv->getNumGroups(), dt = x->getDType().getIndex();
+                    // operands of the chain other than x / residual (weights, statistics) are never candidates
+                    if (is(x) && !itb::conv_nhwc_ok(dt, ci, f, r, s, ph, pw, sh, sw, dh, dw, g)) changed |= drop(x);
+                    if (is(y) && !is(x)) {
+                        const bool tail = st.kind == ExecStep::ConvBnAct;
+                        if (!tail || !itb::conv_nchw_to_nhwc_ok(dt, n, ci, h, w, f, r, s, ph, pw, sh, sw, dh, dw, g))
+                            changed |= drop(y);
+                    }
+                    if (res && !free4(res) && is(res) != is(y)) {
+                        changed |= drop(res);
+                        changed |= drop(y);
+                    }
+                    // everything else the chain reads (filters, statistics) is consumed in the reference's own order
+                    for (auto &m : st.ops)
+                        for (auto &t : m->getInputs())
+                            if (t != x && t != res) changed |= drop(t);
+                } else if (c == PoolStep || c == EltStep) {
+                    const auto &op = st.ops.back();
+                    bool all = true;
+                    auto visit = [&](const Tensor &t) {
+                        if (t->getDims().size() == 4 && !free4(t) && !is(t)) all = false;
+                    };
+                    for (auto &t : op->getInputs()) visit(t);
+                    visit(op->getOutput());
+                    if (!all) {
+                        for (auto &t : op->getInputs()) changed |= drop(t);
+                        changed |= drop(op->getOutput());
+                    }
+                } else {
+                    for (auto &op : st.ops) {
+                        for (auto &t : op->getInputs()) changed |= drop(t);
+                        for (auto &t : op->getOutputs()) changed |= drop(t);
+                    }
+                }
+            }
+        }
+        for (auto &st : schedule) {
+            Cls c = classify(st);
+            if (c == Other) continue;
+            const auto &last = st.ops.back();
+            const Tensor x = st.ops[0]->getInputs(0), y = last->getOutput();
+            bool in = is(x), out = is(y);
+            if (c != ConvStep) {
+                // (a pooled [N, C, 1, 1] result is layout-free: the NHWC kernel writes the same bytes)
+                for (auto &t : last->getInputs()) in = in || is(t);
+                out = out || (in && free4(y));
+                in = in || (out && free4(x));
+                if (in != out) in = out = false;  // cannot happen after the fixpoint; stay on the NCHW kernels
+            }
+            st.layout = (in ? 1 : 0) | (out ? 2 : 0);
+        }
+    }
+};
+}  // namespace
+
 const vector<ExecStep> &GraphObj::getSchedule() {
     if (scheduleEpoch == getTopologyEpoch() && !schedule.empty()) return schedule;
     IT_ASSERT(topo_sort(), "graph has a cycle");
@@ -509,6 +640,7 @@ const vector<ExecStep> &GraphObj::getSchedule() {
         schedule.push_back(std::move(st));
     }
     if (fuse && (mask & 128)) fuseDecoderStacks(schedule);
+    if (fuse && (mask & 512)) LayoutPass().run(schedule);
     // every operator is executed by exactly one step (a producer parked behind a consumer that never runs would be a
     // silently skipped op)
     {

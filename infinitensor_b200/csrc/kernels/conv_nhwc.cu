@@ -21,6 +21,7 @@
 
 #include <cudaTypedefs.h>
 
+#include "conv_shapes.h"
 #include "gemm.cuh"
 
 namespace itb {
@@ -300,11 +301,6 @@ static PFN_cuTensorMapEncodeIm2col_v12000 get_im2col_fn() {
     return fn;
 }
 
-static bool nhwc_shape_ok(int dtype, int C, int F, int R, int S, int ph, int pw, int sh, int sw, int dh, int dw, int groups) {
-    return (dtype == ITB_F16 || dtype == ITB_BF16) && groups == 1 && C % 8 == 0 && F % 8 == 0 && C >= 8 && F >= 8 && R >= 1 &&
-           S >= 1 && sh >= 1 && sw >= 1 && sh <= 8 && sw <= 8 && dh >= 1 && dw >= 1 && ph >= 0 && pw >= 0 && ph <= 127 &&
-           pw <= 127 && (R - 1) * dh - ph <= 128 && (S - 1) * dw - pw <= 128 && (R - 1) * dh < 65536 && (S - 1) * dw < 65536;
-}
 
 template <typename T>
 static int launch_conv_nhwc_t(bool is_bf16, const void *x, const void *wk, int Cp, void *y, int y_nhwc, int N, int C, int H,
@@ -393,7 +389,7 @@ static int nhwc_cp(int C, int R, int S) { return (R * S == 1) ? C : ((C + CV_BK 
 
 extern "C" int it_b200_conv2d_nhwc_supported(int dtype, int C, int F, int R, int S, int ph, int pw, int sh, int sw, int dh,
                                              int dw, int groups) {
-    return nhwc_shape_ok(dtype, C, F, R, S, ph, pw, sh, sw, dh, dw, groups) ? 1 : 0;
+    return conv_nhwc_ok(dtype, C, F, R, S, ph, pw, sh, sw, dh, dw, groups) ? 1 : 0;
 }
 
 extern "C" int64_t it_b200_conv2d_nhwc_workspace(int dtype, int C, int F, int R, int S) {
@@ -406,7 +402,7 @@ extern "C" int it_b200_conv2d_nhwc(int dtype, const void *x, const void *w, void
                                    const float *bn_mean, const float *bn_var, const float *bn_scale, const float *bn_bias,
                                    float bn_eps, const void *residual, int relu, void *workspace, int64_t workspace_bytes,
                                    void *stream) {
-    ITB_CHECK(nhwc_shape_ok(dtype, C, F, R, S, ph, pw, sh, sw, dh, dw, 1),
+    ITB_CHECK(conv_nhwc_ok(dtype, C, F, R, S, ph, pw, sh, sw, dh, dw, 1),
               "conv(nhwc): shape outside the implicit-GEMM kernel (f16/bf16, C %% 8 == 0, F %% 8 == 0, stride <= 8): C=%d F=%d %dx%d", C,
               F, R, S);
     ITB_CHECK((bn_scale == nullptr) == (bn_mean == nullptr) && (bn_scale == nullptr) == (bn_var == nullptr) &&

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "conv_shapes.h"
 #include "gemm.cuh"
 
 namespace itb {
@@ -224,26 +225,10 @@ extern "C" int it_b200_matmul_fp8w(int dtype, const void *X, int n_groups, const
     return r;
 }
 
-static void conv_out(int H, int W, int R, int S, int ph, int pw, int sh, int sw, int dh, int dw, int &OH, int &OW) {
-    OH = (H + 2 * ph - dh * (R - 1) - 1) / sh + 1;  // reference src/operators/conv.cc:85-114
-    OW = (W + 2 * pw - dw * (S - 1) - 1) / sw + 1;
-}
-
-static bool conv_is_1x1_direct(int R, int S, int ph, int pw, int sh, int sw) {
-    return R == 1 && S == 1 && ph == 0 && pw == 0 && sh == 1 && sw == 1;
-}
-
-// the folded im2col GEMM ([F, Kc] x [Kc, N*P], scattered back to NCHW by the epilogue) runs on the tcgen05 kernel
-static bool conv_fold_ok(int dtype, int N, int64_t P, int64_t Kc, int F, int groups) {
-    // (Kc itself need not be a multiple of 8: the im2col rows and a copy of the filters are zero-padded to Kp = ceil8(Kc))
-    return (dtype == ITB_F16 || dtype == ITB_BF16) && groups == 1 && (N * P) % 8 == 0 && ((Kc + 7) & ~7ll) >= 64 &&
-           N * P >= 64 && N * P < (1ll << 31) && F >= 1;
-}
-
 extern "C" int64_t it_b200_conv2d_workspace(int dtype, int N, int C, int H, int W, int F, int R, int S, int ph,
                                             int pw, int sh, int sw, int dh, int dw, int groups) {
     int OH, OW;
-    conv_out(H, W, R, S, ph, pw, sh, sw, dh, dw, OH, OW);
+    conv_out_hw(H, W, R, S, ph, pw, sh, sw, dh, dw, OH, OW);
     const int64_t P = (int64_t)OH * OW, Kc = (int64_t)C * R * S;
     const bool foldable = conv_fold_ok(dtype, N, P, Kc, F, groups);
     if (conv_is_1x1_direct(R, S, ph, pw, sh, sw) && (P % 8 == 0 || !foldable)) return 0;
@@ -265,11 +250,11 @@ struct ConvTail {
 // was launched; the caller executes the operators one by one)
 static int conv_impl(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W, int F, int R, int S,
                      int ph, int pw, int sh, int sw, int dh, int dw, int groups, const ConvTail &tail, void *workspace,
-                     int64_t workspace_bytes, void *stream) {
+                     int64_t workspace_bytes, void *stream, int y_nhwc = 0) {
     ITB_CHECK(groups >= 1 && C % groups == 0 && F % groups == 0, "conv: bad groups %d for C=%d F=%d", groups, C, F);
     auto st = (cudaStream_t)stream;
     int OH, OW;
-    conv_out(H, W, R, S, ph, pw, sh, sw, dh, dw, OH, OW);
+    conv_out_hw(H, W, R, S, ph, pw, sh, sw, dh, dw, OH, OW);
     if ((int64_t)N * F * OH * OW == 0) return 0;
     const int es = dtype_size(dtype);
     const int64_t P = (int64_t)OH * OW, Kc = (int64_t)C * R * S;
@@ -288,6 +273,10 @@ static int conv_impl(int dtype, const void *x, const void *w, void *y, int N, in
         g.residual = tail.residual;
         g.post_relu = tail.relu;
     };
+    // NHWC output (x stays NCHW): only the folded tensor-core GEMM scatters that way
+    if (y_nhwc && !(fold && F % 8 == 0 && aligned16(y) && (!tail.residual || aligned16(tail.residual)) &&
+                    (Kp != Kc || aligned16(w)) && aligned16(workspace)))
+        return 2;
     if (tail.any()) {
         // the tail is implemented by the tcgen05 epilogue: decide BEFORE launching anything
         const bool tc_batched = direct_tc && groups == 1 && (dtype == ITB_F16 || dtype == ITB_BF16) && Kc % 8 == 0 &&
@@ -343,8 +332,12 @@ static int conv_impl(int dtype, const void *x, const void *w, void *y, int N, in
         g.k = (int)Kp;
         g.stride_a = (int64_t)F * Kp;
         g.stride_b = Kp * N * P;
-        g.c_block = (int)P;
-        g.c_block_stride = (int64_t)F * P;
+        if (y_nhwc) {
+            g.c_nhwc = 1;
+        } else {
+            g.c_block = (int)P;
+            g.c_block_stride = (int64_t)F * P;
+        }
         g.no_splitk = 1;
         with_tail(g);
         int r = launch_gemm_tc(dtype, g, st);
@@ -418,4 +411,32 @@ extern "C" int it_b200_conv2d_fused(int dtype, const void *x, const void *w, voi
     t.relu = relu;
     return conv_impl(dtype, x, w, y, N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups, t, workspace, workspace_bytes,
                      stream);
+}
+
+// Conv over an NCHW input whose consumers live in the NHWC domain (the stem of a ResNet: C = 3 cannot feed the implicit-GEMM kernel):
+// the same im2col + tensor-core GEMM, the epilogue writes y (and reads `residual`) as [N, OH, OW, F].  _supported = the shape takes
+// that path (otherwise the call answers 2 and launches nothing).
+extern "C" int it_b200_conv2d_nchw_to_nhwc_supported(int dtype, int N, int C, int H, int W, int F, int R, int S, int ph, int pw,
+                                                     int sh, int sw, int dh, int dw, int groups) {
+    return conv_nchw_to_nhwc_ok(dtype, N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups) ? 1 : 0;
+}
+
+extern "C" int it_b200_conv2d_fused_nhwc_out(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W,
+                                             int F, int R, int S, int ph, int pw, int sh, int sw, int dh, int dw, int groups,
+                                             const float *bn_mean, const float *bn_var, const float *bn_scale,
+                                             const float *bn_bias, float bn_eps, const void *residual, int relu,
+                                             void *workspace, int64_t workspace_bytes, void *stream) {
+    ITB_CHECK((bn_scale == nullptr) == (bn_mean == nullptr) && (bn_scale == nullptr) == (bn_var == nullptr) &&
+                  (bn_scale == nullptr) == (bn_bias == nullptr),
+              "conv_fused: the four BatchNorm parameter vectors go together");
+    ConvTail t;
+    t.mean = bn_mean;
+    t.var = bn_var;
+    t.scale = bn_scale;
+    t.bias = bn_bias;
+    t.eps = bn_eps;
+    t.residual = residual;
+    t.relu = relu;
+    return conv_impl(dtype, x, w, y, N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups, t, workspace, workspace_bytes,
+                     stream, 1);
 }

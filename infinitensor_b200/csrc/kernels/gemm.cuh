@@ -20,6 +20,8 @@ struct GemmArgs {
     // Honoured by the tcgen05 kernel only (launch_gemm_tc is called directly for it).
     int c_block = 0;
     int64_t c_block_stride = 0;
+    // conv with an NHWC consumer: element (row m = filter, column gn = pixel) goes to C[gn * m_total + m] (tcgen05 kernel, batch 1)
+    int c_nhwc = 0;
     // optional fused conv tail (tcgen05 kernel only), applied per output ROW m (= conv filter) after the product has been
     // rounded to the storage dtype, each stage rounded like the separate kernel it replaces:
     //   BatchNorm (fp32 statistics, bn_scale != nullptr) -> + residual (same layout as C) -> ReLU

@@ -200,8 +200,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         const int nl = quad * 32 + lane;  // column inside the tile
         const int gn = n0 + nl;
         // element (m, gn) lives at C[c_off + m * c_ld] (plain row-major, or the conv scatter of GemmArgs::c_block)
-        const int64_t c_ld = g.c_block ? g.c_block : g.n;
-        const int64_t c_off = g.c_block ? (int64_t)(gn / g.c_block) * g.c_block_stride + gn % g.c_block : gn;
+        const int64_t c_ld = g.c_nhwc ? 1 : g.c_block ? g.c_block : g.n;
+        const int64_t c_off = g.c_nhwc ? (int64_t)gn * g.m
+                              : g.c_block ? (int64_t)(gn / g.c_block) * g.c_block_stride + gn % g.c_block : gn;
         const int mode = (bias || (g.act & 0xff)) ? 2 : tail ? 1 : 0;  // (launch_tc_t refuses bias/act together with a tail)
         for (int c0 = c_begin; c0 < c_end; c0 += 16) {
             uint32_t v[16];
@@ -220,9 +221,17 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                 const int rows = min(16, g.m - (m0 + c0));  // valid rows of this 16-row group
                 T *cp = C + c_off + (int64_t)(m0 + c0) * c_ld;
                 if (mode == 0) {
+                    if (g.c_nhwc && rows == 16) {  // 16 consecutive filters of one pixel: two 16-byte stores
+                        alignas(16) T tv[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j < rows) cp[(int64_t)j * c_ld] = from_f<T>(__uint_as_float(v[j]));
+                        for (int j = 0; j < 16; ++j) tv[j] = from_f<T>(__uint_as_float(v[j]));
+                        reinterpret_cast<uint4 *>(cp)[0] = reinterpret_cast<const uint4 *>(tv)[0];
+                        reinterpret_cast<uint4 *>(cp)[1] = reinterpret_cast<const uint4 *>(tv)[1];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < rows) cp[(int64_t)j * c_ld] = from_f<T>(__uint_as_float(v[j]));
+                    }
                 } else if (mode == 1) {
                     float resv[16];
                     if (g.residual) {  // all 16 residual loads in flight before the first (possibly aliasing) store
@@ -240,7 +249,18 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                         }
                         if (g.residual) f = round_t<T>(f + resv[j]);
                         if (g.post_relu) f = fmaxf(f, 0.f);
-                        if (j < rows) cp[(int64_t)j * c_ld] = from_f<T>(f);
+                        resv[j] = f;
+                    }
+                    if (g.c_nhwc && rows == 16) {
+                        alignas(16) T tv[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) tv[j] = from_f<T>(resv[j]);
+                        reinterpret_cast<uint4 *>(cp)[0] = reinterpret_cast<const uint4 *>(tv)[0];
+                        reinterpret_cast<uint4 *>(cp)[1] = reinterpret_cast<const uint4 *>(tv)[1];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < rows) cp[(int64_t)j * c_ld] = from_f<T>(resv[j]);
                     }
                 } else {
 #pragma unroll
@@ -402,6 +422,7 @@ int launch_gemm_tc(int dtype, const GemmArgs &g, cudaStream_t st) {
         if ((int64_t)g.batch * ((g.m + 255) / 256) > 65535) return -1;
     }
     if ((g.bn_scale || g.residual || g.post_relu) && (g.bias || (g.act & 0xff))) return -1;  // tail excludes bias / act
+    if (g.c_nhwc && (g.batch != 1 || g.m % 8 != 0 || g.bias || (g.act & 0xff) || !g.no_splitk)) return -1;
     if (dtype == ITB_BF16) return launch_tc_t<__nv_bfloat16>(g, st, true);
     return launch_tc_t<__half>(g, st, false);
 }

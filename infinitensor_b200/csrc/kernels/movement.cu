@@ -226,6 +226,46 @@ __global__ void __launch_bounds__(256) pool2d_kernel(int is_max, const T *__rest
     }
 }
 
+// the same pooling over NHWC activations ([N, H, W, C], C % 8 == 0; 2-byte types): one thread = 8 channels (16 bytes) of one output
+// pixel, so every tap is one coalesced 16-byte load along C.  Same arithmetic as pool2d_kernel (fp32 max / sum, count-include-pad).
+template <typename T>
+__global__ void __launch_bounds__(256) pool2d_nhwc_kernel(int is_max, const T *__restrict__ x, T *__restrict__ y, int64_t total,
+                                                          int C8, int H, int W, int kh, int kw, int dh, int dw, int ph, int pw,
+                                                          int sh, int sw, int OH, int OW) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int V = 8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        int64_t t = i / C8;
+        const int ow = (int)(t % OW);
+        t /= OW;
+        const int oh = (int)(t % OH);
+        const int64_t n = t / OH;
+        float acc[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = is_max ? -INFINITY : 0.f;
+        for (int r = 0; r < kh; ++r) {
+            const int ih = oh * sh - ph + r * dh;
+            if (ih < 0 || ih >= H) continue;
+            for (int s = 0; s < kw; ++s) {
+                const int iw = ow * sw - pw + s * dw;
+                if (iw < 0 || iw >= W) continue;
+                const Vec16<T> v = ld16(x + (((n * H + ih) * W + iw) * C8 + c8) * V);
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const float f = to_f(v.v[e]);
+                    acc[e] = is_max ? fmaxf(acc[e], f) : acc[e] + f;
+                }
+            }
+        }
+        Vec16<T> o;
+#pragma unroll
+        for (int e = 0; e < V; ++e) o.v[e] = from_f<T>(is_max ? acc[e] : acc[e] / (float)(kh * kw));
+        st16(y + i * V, o);
+    }
+}
+
 // y = scale[c] * (x - mean[c]) / sqrt(var[c] + eps) + bias[c] over NCHW (batch_norm.cc:9-69 semantics; fp32 parameters).
 // VEC: one thread = one 16-byte vector inside a single (n, c) plane (HW % V == 0), one channel lookup per vector.
 template <typename T, bool VEC>
@@ -499,6 +539,22 @@ extern "C" int it_b200_pool2d(int dtype, int is_max, const void *x, void *y, int
         launch_k(pool2d_kernel<T>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, is_max, (const T *)x, (T *)y, (int64_t)N * C, H, W, kh, kw, dh, dw, ph, pw, sh, sw, OH, OW);
     });
     ITB_LAUNCH_CHECK("pool2d");
+    return 0;
+}
+
+extern "C" int it_b200_pool2d_nhwc(int dtype, int is_max, const void *x, void *y, int N, int C, int H, int W, int kh, int kw,
+                                   int dh, int dw, int ph, int pw, int sh, int sw, int OH, int OW, void *stream) {
+    ITB_CHECK((dtype == ITB_F16 || dtype == ITB_BF16) && C % 8 == 0 && aligned16(x) && aligned16(y),
+              "pool2d(nhwc): f16 / bf16 with C %% 8 == 0 (C = %d)", C);
+    const int64_t total = (int64_t)N * OH * OW * (C / 8);
+    if (total == 0) return 0;
+    if (dtype == ITB_F16)
+        launch_k(pool2d_nhwc_kernel<__half>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, is_max, (const __half *)x,
+                 (__half *)y, total, C / 8, H, W, kh, kw, dh, dw, ph, pw, sh, sw, OH, OW);
+    else
+        launch_k(pool2d_nhwc_kernel<__nv_bfloat16>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, is_max,
+                 (const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, total, C / 8, H, W, kh, kw, dh, dw, ph, pw, sh, sw, OH, OW);
+    ITB_LAUNCH_CHECK("pool2d(nhwc)");
     return 0;
 }
 

@@ -225,6 +225,19 @@ def pool2d(kind, x, kh, kw, dh, dw, ph, pw, sh, sw, dt=F32):
     return host(out)
 
 
+def pool2d_nhwc(kind, x, kh, kw, dh, dw, ph, pw, sh, sw, dt=F16):
+    """x and the result are NCHW numpy arrays; permuted to / from NHWC on the host."""
+    N, C, H, W = x.shape
+    xd = dev(np.ascontiguousarray(x.transpose(0, 2, 3, 1)), dt)
+    OH = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+    OW = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    out = torch.empty((N, OH, OW, C), dtype=xd.dtype, device="cuda")
+    L.check(L.lib.it_b200_pool2d_nhwc(dt, 1 if kind == "max" else 0, ptr(xd), ptr(out), N, C, H, W, kh, kw, dh, dw, ph, pw,
+                                      sh, sw, OH, OW, stream()))
+    sync()
+    return np.ascontiguousarray(host(out).transpose(0, 3, 1, 2))
+
+
 def batch_norm(x, mean, var, scale, bias, eps, dt=F32):
     xd = dev(x, dt)
     ms = [dev(np.asarray(v, np.float32)) for v in (mean, var, scale, bias)]
@@ -249,27 +262,31 @@ def batch_norm_relu(x, mean, var, scale, bias, eps, dt=F32):
     return host(out)
 
 
-def conv2d_fused(x, w, ph, pw, sh, sw, dh, dw, bn, eps, residual, relu, dt=F16):
-    """Returns the fused result, or None when the C-ABI reports the shape as not taken (rc 2)."""
+def conv2d_fused(x, w, ph, pw, sh, sw, dh, dw, bn, eps, residual, relu, dt=F16, y_nhwc=False):
+    """Returns the fused result, or None when the C-ABI reports the shape as not taken (rc 2).  y_nhwc: the kernel writes y (and
+    reads the residual) as [N, OH, OW, F]; arguments and result here stay NCHW (permuted on the host)."""
     xd, wd = dev(x, dt), dev(w, dt)
     N, C, H, W = x.shape
     F, Cg, R, S = w.shape
     groups = C // Cg
     OH = (H + 2 * ph - dh * (R - 1) - 1) // sh + 1
     OW = (W + 2 * pw - dw * (S - 1) - 1) // sw + 1
-    y = torch.empty((N, F, OH, OW), dtype=xd.dtype, device="cuda")
+    y = torch.empty((N, OH, OW, F) if y_nhwc else (N, F, OH, OW), dtype=xd.dtype, device="cuda")
     ms = [dev(np.asarray(v, np.float32)) for v in bn] if bn is not None else [None] * 4
-    rd = dev(residual, dt) if residual is not None else None
+    rd = None
+    if residual is not None:
+        rd = dev(np.ascontiguousarray(residual.transpose(0, 2, 3, 1)) if y_nhwc else residual, dt)
     wsb = L.lib.it_b200_conv2d_workspace(dt, N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups)
     ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device="cuda")
-    rc = L.lib.it_b200_conv2d_fused(dt, ptr(xd), ptr(wd), ptr(y), N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups,
+    fn = L.lib.it_b200_conv2d_fused_nhwc_out if y_nhwc else L.lib.it_b200_conv2d_fused
+    rc = fn(dt, ptr(xd), ptr(wd), ptr(y), N, C, H, W, F, R, S, ph, pw, sh, sw, dh, dw, groups,
                                     ptr(ms[0]), ptr(ms[1]), ptr(ms[2]), ptr(ms[3]), eps, ptr(rd), int(relu), ptr(ws),
                                     int(wsb), stream())
     if rc == 2:
         return None
     L.check(rc)
     sync()
-    return host(y)
+    return np.ascontiguousarray(host(y).transpose(0, 3, 1, 2)) if y_nhwc else host(y)
 
 
 def conv2d_nhwc(x, w, ph, pw, sh, sw, dh, dw, bn=None, eps=1e-5, residual=None, relu=False, dt=F16, y_nhwc=True):

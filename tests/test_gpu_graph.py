@@ -330,6 +330,21 @@ def test_resnet_conv_tail_fusion_is_bit_identical(monkeypatch):
     assert np.array_equal(fused, plain)
 
 
+def test_resnet_nhwc_domain_matches_nchw(monkeypatch):
+    """The NHWC domain (implicit-GEMM convs, NHWC pools; fusion mask bit 9) against the NCHW schedule of the same graph: the
+    logits agree within fp16 accumulation noise (the NHWC epilogue rounds once per chain, the NCHW one after every operator) and
+    pick the same classes."""
+    from infinitensor_b200 import graphs as G
+    cfg = G.ResNetConfig(batch=4, image=64, dtype=F16)
+    s1, nhwc = _resnet_once(cfg, {}, monkeypatch)
+    s0, nchw = _resnet_once(cfg, {"ITB_FUSION_MASK": "383"}, monkeypatch)
+    assert sum("@nhwc" in s for s in s1) == 54 and s1[0].endswith("@>nhwc") and not any("@" in s for s in s0)
+    a, b = G.from_storage(nhwc, F16).astype(np.float64), G.from_storage(nchw, F16).astype(np.float64)
+    assert np.isfinite(a).all()
+    assert np.abs(a - b).max() / np.abs(b).max() < 2e-2
+    assert (a.argmax(-1) == b.argmax(-1)).all()
+
+
 @pytest.mark.parametrize("dtype", [F32, BF16])
 def test_onnx_stub_drives_the_backend(dtype):
     """an ONNX file (written by OnnxExporter, read by the package-free protobuf reader) lowered by

@@ -400,6 +400,10 @@ def test_conv_fused_tail_bit_identical(K, dt):
                 ref = np.maximum(ref, 0)
                 ora = None if ora is None else np.maximum(ora, 0)
             assert np.array_equal(got, ref), f"case {ci} res={use_res} relu={relu}: max diff {np.abs(got - ref).max()}"
+            if ci in (1, 2, 4) and K.L.lib.it_b200_conv2d_nchw_to_nhwc_supported(dt, *xs, ws[0], ws[2], ws[3], *args, 1):
+                # the same GEMM scattering its result as NHWC (entry into the NHWC domain): identical values
+                nh = K.conv2d_fused(x, w, *args, bn, 1e-5, res if use_res else None, relu, dt=dt, y_nhwc=True)
+                assert nh is not None and np.array_equal(nh, ref)
             if ora is not None:
                 close(got, ora, tol, tol)
     # fp32 / grouped / tiny-K convs are not taken: rc 2, the runtime runs the operators one by one
@@ -409,6 +413,15 @@ def test_conv_fused_tail_bit_identical(K, dt):
     x = rnd((2, 16, 8, 8), 92, dt)
     close(K.batch_norm_relu(x, *[np.full(16, v, np.float32) for v in (0.1, 1.3, 0.9, -0.2)], 1e-5, dt=dt),
           np.maximum(K.batch_norm(x, *[np.full(16, v, np.float32) for v in (0.1, 1.3, 0.9, -0.2)], 1e-5, dt=dt), 0), 0, 0)
+
+
+@pytest.mark.parametrize("dt", [F16, BF16])
+def test_pool_nhwc_parity(K, dt):
+    """NHWC pooling = the NCHW kernel on the permuted tensor, bit for bit (same fp32 arithmetic)."""
+    img = rnd((3, 24, 13, 11), 301, dt)
+    for kind, args in [("max", (3, 3, 1, 1, 1, 1, 2, 2)), ("avg", (3, 2, 1, 1, 1, 0, 2, 1)), ("avg", (13, 11, 1, 1, 0, 0, 1, 1)),
+                       ("max", (2, 2, 2, 1, 0, 1, 1, 2))]:
+        assert np.array_equal(K.pool2d_nhwc(kind, img, *args, dt=dt), K.pool2d(kind, img, *args, dt))
 
 
 NHWC_CASES = [((2, 64, 56, 56), (256, 64, 1, 1), (0, 0, 1, 1, 1, 1)),      # 1x1, one k-tile, filters used as stored

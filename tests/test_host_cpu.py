@@ -251,11 +251,21 @@ def test_conv_bn_act_schedule(B, monkeypatch):
     sc = h.schedule()
     kinds = collections.Counter(s.split(":")[0] for s in sc)
     assert kinds["ConvBnAct"] == 53
-    assert sc.count("ConvBnAct:Conv+BatchNormalization+Relu") == 1 + 16 * 2          # stem + conv1/conv2 of 16 blocks
-    assert sc.count("ConvBnAct:Conv+BatchNormalization+Add+Relu") == 16              # conv3 of every block
-    assert sc.count("ConvBnAct:Conv+BatchNormalization") == 4                        # the four downsample branches
+    # NHWC domain: the 3-channel stem reads the NCHW graph input and WRITES NHWC ("@>nhwc"); the max pool, every bottleneck conv
+    # (implicit GEMM) and the global average pool (whose [N, C, 1, 1] result is layout-free) stay inside it ("@nhwc")
+    assert sc.count("ConvBnAct:Conv+BatchNormalization+Relu@>nhwc") == 1             # stem
+    assert sc.count("ConvBnAct:Conv+BatchNormalization+Relu@nhwc") == 16 * 2         # conv1 / conv2 of 16 blocks
+    assert sc.count("ConvBnAct:Conv+BatchNormalization+Add+Relu@nhwc") == 16         # conv3 of every block
+    assert sc.count("ConvBnAct:Conv+BatchNormalization@nhwc") == 4                   # the four downsample branches
+    assert sc.count("Single:MaxPool@nhwc") == 1 and sc.count("Single:AveragePool@nhwc") == 1
     assert not any(s.startswith("Single:BatchNormalization") or s == "Single:Relu" or s == "Single:Add" for s in sc)
     h.data_malloc()
+    # bit 9 off: the same fusion, every tensor NCHW
+    monkeypatch.setenv("ITB_FUSION_MASK", str(127 | 256))
+    h3 = B.GraphHandler(rt)
+    G.build_resnet50(h3, G.ResNetConfig(batch=2, image=64))
+    sc3 = h3.schedule()
+    assert not any("@" in s for s in sc3) and sc3.count("ConvBnAct:Conv+BatchNormalization+Relu") == 1 + 16 * 2
     monkeypatch.setenv("ITB_FUSION_MASK", "63")
     h2 = B.GraphHandler(rt)
     G.build_resnet50(h2, G.ResNetConfig(batch=2, image=64))
