@@ -16,6 +16,7 @@
 // Replaces cudnnConvolutionForward + the separate BatchNorm / Add / Relu kernels (reference src/kernels/cuda/conv.cc:143-168,
 // batch_norm.cc:9-69, element_wise.cu) for the ResNet-style Conv -> BN -> [Add] -> [Relu] chains.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -32,6 +33,9 @@ constexpr int CV_EPI_WARPS = 8;
 constexpr int CV_EPI_THREADS = CV_EPI_WARPS * 32;
 constexpr int CV_THREADS = (CV_EPI_WARPS + 2) * 32;
 
+constexpr int CV_RING = 4;                  // staging slabs per epilogue warp
+constexpr int CV_SLAB_BYTES = 32 * 32 * 2;  // [32 pixels x 32 filters]
+
 struct ConvNhwcParams {
     void *y;
     const void *residual;  // same layout as y
@@ -40,9 +44,40 @@ struct ConvNhwcParams {
     int relu;
     int y_nhwc;
     int P, OW, M, F, FT, tiles_f, tiles, cchunks, Cp, RS, S, sh, sw, ph, pw, dh, dw;
-    int stages, b_bytes, tmem_cols;
+    int stages, b_bytes, tmem_cols, stg_off;
+    unsigned long long *trace;  // ITB_CONV_TRACE=1 (tools only): globaltimer stamps of CTA 0 -- [0..255] load issued, [256..511] stage
+                                // landed (MMA thread), [512..767] tile accumulator complete (epilogue), [768..1023] tile stored
     uint32_t idesc;
 };
+
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void cv_stamp(unsigned long long *trace, int slot) {
+    if (trace && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        trace[slot] = t;
+    }
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_im2col_4d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c, int w, int h, int n,
                                               uint16_t off_w, uint16_t off_h) {
@@ -88,18 +123,23 @@ template <> struct Pack2<__nv_bfloat16> {
 template <typename T>
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_nhwc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                   const __grid_constant__ CUtensorMap mapB,
+                                                                  const __grid_constant__ CUtensorMap mapY,
+                                                                  const __grid_constant__ CUtensorMap mapR,
                                                                   ConvNhwcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S = p.stages;
     uint8_t *a_sm = smem;
     uint8_t *b_sm = smem + S * CV_A_BYTES;
-    float2 *bn_sm = reinterpret_cast<float2 *>(b_sm + S * p.b_bytes);  // {a, b} of this filter tile: y = a * conv + b
+    float2 *bn_sm = reinterpret_cast<float2 *>(smem + p.stg_off + CV_EPI_WARPS * CV_RING * CV_SLAB_BYTES);  // {a, b}: y = a * conv + b
     uint64_t *full = reinterpret_cast<uint64_t *>(bn_sm + p.FT);
     uint64_t *empty = full + S;
     uint64_t *acc_full = empty + S;
     uint64_t *acc_empty = acc_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint64_t *res_bar = acc_empty + 2;  // [CV_EPI_WARPS][CV_RING]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + CV_EPI_WARPS * CV_RING);
+    // per epilogue warp: CV_RING slabs of [32 pixels x 32 filters] (2 KB, 64B swizzle) -- residual in by TMA, result out by TMA
+    uint8_t *stg_sm = smem + p.stg_off;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger();
@@ -112,6 +152,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_nhwc_kernel(const __grid_c
             mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], CV_EPI_WARPS);
         }
+        for (int i = 0; i < CV_EPI_WARPS * CV_RING; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == CV_EPI_WARPS + 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -126,54 +167,100 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_nhwc_kernel(const __grid_c
     const int ktiles = p.RS * p.cchunks;
 
     if (warp == CV_EPI_WARPS) {
-        // ===== TMA producer =====
+        // ===== TMA producer (one thread): the loop body is kept to a few dozen instructions -- a single thread retires one
+        // dependent instruction every ~5 cycles, and at ~130 instructions per k-tile (runtime divisions for the ring slot and the
+        // filter tap) this loop, not the memory system, set the pace of the whole kernel (measured: 0.48 us per k-tile) =====
         if (lane == 0) {
             const uint64_t pol_b = l2_policy_evict_last();  // the filters are re-read by every CTA
             pdl_wait();  // activations (and the repacked filters) come from the kernels before this one
-            uint32_t kit = 0;
+            const uint32_t a_base = smem_u32(a_sm), b_base = smem_u32(b_sm), full_base = smem_u32(full), empty_base = smem_u32(empty);
+            const uint32_t tx = CV_A_BYTES + p.b_bytes;
+            const uint64_t mA = reinterpret_cast<uint64_t>(&mapA), mB = reinterpret_cast<uint64_t>(&mapB);
+            int st = 0, fill = 0;
+            uint32_t ph = 0;
             for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
                 const int ft = t % p.tiles_f, mt = t / p.tiles_f;
                 const int m0 = mt * CV_BM;
                 const int n0 = m0 / p.P, pp = m0 - n0 * p.P;
                 const int oh0 = pp / p.OW, ow0 = pp - oh0 * p.OW;
                 const int wc = ow0 * p.sw - p.pw, hc = oh0 * p.sh - p.ph;  // base pixel of the tile's first output position
+                const int f0 = ft * p.FT;
+                int kb = 0;  // column of the filter matrix: (r*S + s) * Cp + channel
+                uint32_t off_w = 0, off_h = 0;
+                int s = 0;
                 for (int rs = 0; rs < p.RS; ++rs) {
-                    const int r = rs / p.S, s = rs - r * p.S;
-                    for (int cc = 0; cc < p.cchunks; ++cc, ++kit) {
-                        const int st = kit % S;
-                        if (kit >= (uint32_t)S) mbar_wait(&empty[st], ((kit / S) - 1) & 1);
-                        mbar_expect_tx(&full[st], CV_A_BYTES + p.b_bytes);
-                        tma_im2col_4d(a_sm + st * CV_A_BYTES, &mapA, &full[st], cc * CV_BK, wc, hc, n0, (uint16_t)(s * p.dw),
-                                      (uint16_t)(r * p.dh));
-                        tma_load_2d(b_sm + st * p.b_bytes, &mapB, &full[st], rs * p.Cp + cc * CV_BK, ft * p.FT, pol_b);
+                    const uint32_t offs = off_w | (off_h << 16);
+                    for (int c0 = 0; c0 < p.cchunks * CV_BK; c0 += CV_BK) {
+                        if (fill >= S) {
+                            uint32_t spins = 0;
+                            while (!mbar_try_wait_addr(empty_base + st * 8, ph ^ 1))
+                                if (++spins > (1u << 26)) __trap();
+                        } else {
+                            ++fill;
+                        }
+                        const uint32_t bar = full_base + st * 8;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+                        asm volatile(
+                            "{\n\t.reg .b16 ow, oh;\n\tmov.b32 {ow, oh}, %7;\n\t"
+                            "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+                            " [%0], [%1, {%3, %4, %5, %6}], [%2], {ow, oh};\n\t}"
+                            ::"r"(a_base + st * CV_A_BYTES), "l"(mA), "r"(bar), "r"(c0), "r"(wc), "r"(hc), "r"(n0), "r"(offs)
+                            : "memory");
+                        asm volatile(
+                            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+                            " [%0], [%1, {%3, %4}], [%2], %5;"
+                            ::"r"(b_base + st * p.b_bytes), "l"(mB), "r"(bar), "r"(kb + c0), "r"(f0), "l"(pol_b)
+                            : "memory");
+                        if (++st == S) {
+                            st = 0;
+                            ph ^= 1;
+                        }
+                    }
+                    kb += p.Cp;
+                    off_w += p.dw;
+                    if (++s == p.S) {
+                        s = 0;
+                        off_w = 0;
+                        off_h += p.dh;
                     }
                 }
             }
         }
         __syncwarp();
     } else if (warp == CV_EPI_WARPS + 1) {
-        // ===== MMA issuer (one thread) =====
+        // ===== MMA issuer (one thread; same economy: running ring slot / phase, descriptors advanced by adding to the address field) =====
         if (lane == 0) {
-            const uint32_t a_base = smem_u32(a_sm), b_base = smem_u32(b_sm);
-            uint32_t kit = 0;
-            int it = 0;
+            const uint32_t full_base = smem_u32(full);
+            // both operands K-major, 128 B rows: 8-row groups 1 KB apart (SBO), one k16 step = +32 B = +2 in the (address >> 4) field
+            const uint64_t a_desc0 = umma_desc_sw128(smem_u32(a_sm), 0, 1024), b_desc0 = umma_desc_sw128(smem_u32(b_sm), 0, 1024);
+            const uint32_t a_step = CV_A_BYTES >> 4, b_step = (uint32_t)p.b_bytes >> 4;
+            const uint32_t idesc = p.idesc;
+            int st = 0, it = 0;
+            uint32_t ph = 0;
             for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
                 const int buf = it & 1, use = it >> 1;
                 if (it >= 2) mbar_wait(&acc_empty[buf], (use - 1) & 1);  // the epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.FT);
-                for (int kt = 0; kt < ktiles; ++kt, ++kit) {
-                    const int st = kit % S;
-                    mbar_wait(&full[st], (kit / S) & 1);
+                uint32_t acc = 0;
+                for (int kt = 0; kt < ktiles; ++kt) {
+                    {
+                        uint32_t spins = 0;
+                        while (!mbar_try_wait_addr(full_base + st * 8, ph))
+                            if (++spins > (1u << 26)) __trap();
+                    }
                     tc_fence_after();
+                    const uint64_t a_desc = a_desc0 + (uint64_t)(st * a_step), b_desc = b_desc0 + (uint64_t)(st * b_step);
 #pragma unroll
                     for (int kk = 0; kk < CV_BK / 16; ++kk) {
-                        // both operands K-major, 128 B rows: 8-row groups 1 KB apart (SBO), one k16 step = +32 B
-                        const uint64_t a_desc = umma_desc_sw128(a_base + st * CV_A_BYTES + kk * 32, 0, 1024);
-                        const uint64_t b_desc = umma_desc_sw128(b_base + st * p.b_bytes + kk * 32, 0, 1024);
-                        tc_mma_f16(d_tmem, a_desc, b_desc, p.idesc, (kt > 0 || kk > 0) ? 1u : 0u);
+                        tc_mma_f16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, acc);
+                        acc = 1;
                     }
                     tc_commit(&empty[st]);
+                    if (++st == S) {
+                        st = 0;
+                        ph ^= 1;
+                    }
                 }
                 tc_commit(&acc_full[buf]);
             }
@@ -188,6 +275,23 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_nhwc_kernel(const __grid_c
         T *Y = (T *)p.y;
         const T *R = (const T *)p.residual;
         int cur_ft = -1, it = 0;
+        uint8_t *my_stg = stg_sm + warp * (CV_RING * CV_SLAB_BYTES);
+        uint64_t *my_bar = res_bar + warp * CV_RING;
+        const uint64_t pol_r = l2_policy_evict_first();  // the residual is read exactly once
+        uint32_t q = 0;                    // slabs this warp has processed
+        int pf_t = blockIdx.x, pf_c = cbeg;  // next residual slab to request (tile, first column)
+        if (p.y_nhwc && R && lane == 0) {
+            for (int i = 0; i < CV_RING - 1 && pf_t < p.tiles; ++i) {
+                mbar_expect_tx(&my_bar[i], CV_SLAB_BYTES);
+                tma_load_2d(my_stg + i * CV_SLAB_BYTES, &mapR, &my_bar[i], (pf_t % p.tiles_f) * p.FT + pf_c,
+                            (pf_t / p.tiles_f) * CV_BM + quad * 32, pol_r);
+                pf_c += 32;
+                if (pf_c >= cend) {
+                    pf_c = cbeg;
+                    pf_t += gridDim.x;
+                }
+            }
+        }
         for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
             const int ft = t % p.tiles_f, mt = t / p.tiles_f;
             const int buf = it & 1, use = it >> 1;
@@ -208,21 +312,28 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_nhwc_kernel(const __grid_c
             }
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after();
+            if (threadIdx.x == 0 && it < 256) cv_stamp(p.trace, 512 + it);
             const int64_t gm = (int64_t)mt * CV_BM + row;
             const bool ok = gm < p.M;
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.FT);
             if (p.y_nhwc) {
-                T *yrow = Y + gm * p.F + f0;
-                const T *rrow = R ? R + gm * p.F + f0 : nullptr;
-                for (int c0 = cbeg; c0 < cend; c0 += 32) {
+                // slab q of this warp = 32 pixels x 32 filters through ring buffer q % CV_RING: the residual slab lands there by TMA
+                // (requested CV_RING - 1 slabs ahead), the result overwrites it in place and leaves by TMA; the tensor maps clip
+                // the ragged last pixel tile and filter tile
+                const int m_row = mt * CV_BM + quad * 32;
+                for (int c0 = cbeg; c0 < cend; c0 += 32, ++q) {
+                    const int b = q & (CV_RING - 1);
+                    uint8_t *slab = my_stg + b * CV_SLAB_BYTES;
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_addr + (uint32_t)c0, v);
-                    if (!ok) continue;
+                    if (R) mbar_wait(&my_bar[b], (q / CV_RING) & 1);
+                    else if (lane == 0) bulk_wait_read<CV_RING - 1>();  // the store that last used this buffer has read it
+                    __syncwarp();
 #pragma unroll
                     for (int j8 = 0; j8 < 32; j8 += 8) {
-                        if (f0 + c0 + j8 >= p.F) break;  // F % 8 == 0
+                        uint4 *cell = reinterpret_cast<uint4 *>(slab + lane * 64 + (((j8 >> 3) ^ ((lane >> 1) & 3)) << 4));
                         uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-                        if (rrow) rv = *reinterpret_cast<const uint4 *>(rrow + c0 + j8);
+                        if (R) rv = *cell;
                         const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
                         uint32_t ow[4];
 #pragma unroll
@@ -237,8 +348,30 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_nhwc_kernel(const __grid_c
                             }
                             ow[e] = Pack2<T>::pack(x0, x1);
                         }
-                        *reinterpret_cast<uint4 *>(yrow + c0 + j8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                        *cell = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                     }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&mapY, slab, f0 + c0, m_row);
+                        bulk_commit();
+                        if (R) {
+                            // slab q + CV_RING - 1 goes into the buffer slab q - 1 used: its store must have read the buffer
+                            bulk_wait_read<1>();
+                            if (pf_t < p.tiles) {
+                                const int pb = (q + CV_RING - 1) & (CV_RING - 1);
+                                mbar_expect_tx(&my_bar[pb], CV_SLAB_BYTES);
+                                tma_load_2d(my_stg + pb * CV_SLAB_BYTES, &mapR, &my_bar[pb], (pf_t % p.tiles_f) * p.FT + pf_c,
+                                            (pf_t / p.tiles_f) * CV_BM + quad * 32, pol_r);
+                                pf_c += 32;
+                                if (pf_c >= cend) {
+                                    pf_c = cbeg;
+                                    pf_t += gridDim.x;
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
             } else {
                 // NCHW output: element (pixel gm = n*P + pp, filter f) at y[(n*F + f)*P + pp]; lanes = consecutive pixels
@@ -263,7 +396,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_nhwc_kernel(const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (threadIdx.x == 0 && it < 256) cv_stamp(p.trace, 768 + it);
         }
+        if (lane == 0) bulk_wait_all();  // every TMA store of this warp is complete before the CTA (and its shared memory) goes away
     }
     tc_fence_before();
     __syncthreads();
@@ -285,6 +420,34 @@ __global__ void __launch_bounds__(256) repack_filters_kernel(const T *__restrict
         const int rs = (int)(t % RS);
         const int64_t f = t / RS;
         out[i] = c < C ? w[(f * C + c) * RS + rs] : from_f<T>(0.f);
+    }
+}
+
+// the same for RS = 9 (3x3): one thread = 8 channels of one filter = 72 contiguous input elements (nine 16-byte loads), written as
+// nine 16-byte channel vectors -- both sides coalesced (the element-wise kernel above took 16.7 us for a 512x512x3x3 filter bank)
+template <typename T>
+__global__ void __launch_bounds__(256) repack_filters9_kernel(const T *__restrict__ w, T *__restrict__ out, int64_t items, int C,
+                                                              int Cp) {
+    pdl_trigger();
+    pdl_wait();
+    const int cp8 = Cp / 8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cp8);
+        const int64_t f = i / cp8;
+        alignas(16) T in[72];
+        const bool real = c8 * 8 < C;
+        if (real) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(w + (f * C + c8 * 8) * 9);
+#pragma unroll
+            for (int v = 0; v < 9; ++v) reinterpret_cast<uint4 *>(in)[v] = __ldg(src + v);
+        }
+#pragma unroll
+        for (int rs = 0; rs < 9; ++rs) {
+            alignas(16) T o[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c] = real ? in[c * 9 + rs] : from_f<T>(0.f);
+            *reinterpret_cast<uint4 *>(out + (f * 9 + rs) * Cp + c8 * 8) = *reinterpret_cast<const uint4 *>(o);
+        }
     }
 }
 
@@ -321,11 +484,25 @@ static int launch_conv_nhwc_t(bool is_bf16, const void *x, const void *wk, int C
     p.OW = OW;
     p.M = N * p.P;
     p.F = F;
-    p.FT = F >= 256 ? 256 : ((F + 63) / 64) * 64;  // 64, 128, 192 or 256 filter columns per tile
-    p.tiles_f = (F + p.FT - 1) / p.FT;
     const int tiles_m = (p.M + CV_BM - 1) / CV_BM;
-    p.tiles = tiles_m * p.tiles_f;
     p.cchunks = (C + CV_BK - 1) / CV_BK;
+    {
+        // filter columns per tile (UMMA N): 64 .. 256.  Every SM pulls its operands through its own L2 port (the measured bound of
+        // this kernel), so the choice minimises the bytes of the busiest SM = rounds x k-tiles x (16 KB pixels + FT x 128 B filters);
+        // few pixel tiles (7x7 / 14x14 maps) therefore take narrower filter tiles to put more SMs to work
+        const int fmax = std::min(256, ((F + 63) / 64) * 64);
+        int64_t best = -1;
+        for (int ft = fmax; ft >= 64; ft -= 64) {
+            const int64_t tiles = (int64_t)tiles_m * ((F + ft - 1) / ft);
+            const int64_t cost = ((tiles + kNumSMs - 1) / kNumSMs) * (16384 + ft * 128);
+            if (best < 0 || cost < best) {
+                best = cost;
+                p.FT = ft;
+            }
+        }
+    }
+    p.tiles_f = (F + p.FT - 1) / p.FT;
+    p.tiles = tiles_m * p.tiles_f;
     p.Cp = Cp;
     p.RS = R * S;
     p.S = S;
@@ -339,14 +516,24 @@ static int launch_conv_nhwc_t(bool is_bf16, const void *x, const void *wk, int C
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * p.FT) p.tmem_cols <<= 1;
     const int stage_bytes = CV_A_BYTES + p.b_bytes;
-    const int fixed = p.FT * 8 + 16 * 8 * 2 + 64 + 1024;
-    p.stages = std::max(2, std::min(8, (225 * 1024 - fixed) / stage_bytes));
+    const int stg_bytes = CV_EPI_WARPS * CV_RING * CV_SLAB_BYTES;  // 64 KB
+    const int fixed = stg_bytes + p.FT * 8 + (16 * 2 + 4 + CV_EPI_WARPS * CV_RING) * 8 + 64 + 1024;
+    // bytes in flight, not stage count, is what hides the L2 latency: 3 x 48 KB is as good as 4 (measured bound: L2 -> SM bandwidth)
+    p.stages = std::max(2, std::min(6, (225 * 1024 - fixed) / stage_bytes));
+    {
+        static const int st_env = [] {
+            const char *e = std::getenv("ITB_CONV_STAGES");
+            return e && e[0] ? std::atoi(e) : 0;
+        }();
+        if (st_env >= 2 && st_env <= p.stages) p.stages = st_env;
+    }
+    p.stg_off = p.stages * stage_bytes;
     p.idesc = umma_idesc_f16(is_bf16 ? 1 : 0, /*A K-major*/ 0, /*B K-major*/ 0, CV_BM, p.FT);
     const int smem = p.stages * stage_bytes + fixed;
 
     auto enc = get_im2col_fn();
     ITB_CHECK(enc, "conv(nhwc): cuTensorMapEncodeIm2col is not available from this driver");
-    alignas(64) CUtensorMap mapA, mapB;
+    alignas(64) CUtensorMap mapA, mapB, mapY, mapR;
     {
         cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
@@ -363,6 +550,12 @@ static int launch_conv_nhwc_t(bool is_bf16, const void *x, const void *wk, int C
     if (!make_tma_2d_b16(&mapB, wk, (uint64_t)F, (uint64_t)R * S * Cp, (uint64_t)R * S * Cp, (uint32_t)p.FT, CV_BK, 128))
         ITB_FAIL("conv(nhwc): cuTensorMapEncodeTiled(filters) failed");
 
+    // y / residual as [N*OH*OW rows][F columns] matrices, box [32 pixels x 32 filters], 64B swizzle (NHWC output only)
+    const void *ymat = y_nhwc ? y : wk, *rmat = (y_nhwc && residual) ? residual : ymat;
+    const uint64_t yrows = y_nhwc ? (uint64_t)p.M : (uint64_t)F, ycols = y_nhwc ? (uint64_t)F : (uint64_t)R * S * Cp;
+    if (!make_tma_2d_b16(&mapY, ymat, yrows, ycols, ycols, 32, 32, 64) || !make_tma_2d_b16(&mapR, rmat, yrows, ycols, ycols, 32, 32, 64))
+        ITB_FAIL("conv(nhwc): cuTensorMapEncodeTiled(output) failed");
+
     auto kern = conv_nhwc_kernel<T>;
     {
         static int attr_smem[64] = {0};
@@ -375,9 +568,36 @@ static int launch_conv_nhwc_t(bool is_bf16, const void *x, const void *wk, int C
             attr_smem[dev] = smem;
         }
     }
-    cudaError_t e = launch_k(kern, dim3(std::min(p.tiles, kNumSMs)), dim3(CV_THREADS), (size_t)smem, st, mapA, mapB, p);
+    static const bool tracing = [] {
+        const char *e = std::getenv("ITB_CONV_TRACE");
+        return e && e[0] == '1';
+    }();
+    static unsigned long long *trace_dev = nullptr;
+    if (tracing) {
+        if (!trace_dev) cudaMalloc(&trace_dev, 1024 * sizeof(unsigned long long));
+        cudaMemsetAsync(trace_dev, 0, 1024 * sizeof(unsigned long long), st);
+        p.trace = trace_dev;
+    }
+    cudaError_t e = launch_k(kern, dim3(std::min(p.tiles, kNumSMs)), dim3(CV_THREADS), (size_t)smem, st, mapA, mapB, mapY, mapR, p);
     ITB_CHECK(e == cudaSuccess, "conv(nhwc): launch failed: %s", cudaGetErrorString(e));
     count_launch();
+    if (tracing) {  // tools/conv_bench.py with CONV_BENCH_REPS=1: one line per launch
+        static unsigned long long h[1024];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        const unsigned long long t0 = h[0];
+        fprintf(stderr, "conv trace C=%d F=%d %dx%d M=%d FT=%d stages=%d ktiles/tile=%d tiles=%d\n", C, F, R, S, p.M, p.FT, p.stages,
+                p.RS * p.cchunks, p.tiles);
+        fprintf(stderr, "  issue :");
+        for (int i = 0; i < 40 && h[i]; ++i) fprintf(stderr, " %.2f", (double)(h[i] - t0) / 1e3);
+        fprintf(stderr, "\n  landed:");
+        for (int i = 0; i < 40 && h[256 + i]; ++i) fprintf(stderr, " %.2f", (double)(h[256 + i] - t0) / 1e3);
+        fprintf(stderr, "\n  acc   :");
+        for (int i = 0; i < 12 && h[512 + i]; ++i) fprintf(stderr, " %.2f", (double)(h[512 + i] - t0) / 1e3);
+        fprintf(stderr, "\n  stored:");
+        for (int i = 0; i < 12 && h[768 + i]; ++i) fprintf(stderr, " %.2f", (double)(h[768 + i] - t0) / 1e3);
+        fprintf(stderr, "\n");
+    }
     return 0;
 }
 
@@ -420,7 +640,15 @@ extern "C" int it_b200_conv2d_nhwc(int dtype, const void *x, const void *w, void
         ITB_CHECK(workspace && workspace_bytes >= need && aligned16(workspace), "conv(nhwc): workspace %lld < %lld bytes",
                   (long long)workspace_bytes, (long long)need);
         const int64_t total = (int64_t)F * R * S * Cp;
-        if (dtype == ITB_F16)
+        if (R * S == 9) {
+            const int64_t items = (int64_t)F * (Cp / 8);
+            if (dtype == ITB_F16)
+                launch_k(repack_filters9_kernel<__half>, dim3(grid_for(items, 256)), dim3(256), 0, st, (const __half *)w,
+                         (__half *)workspace, items, C, Cp);
+            else
+                launch_k(repack_filters9_kernel<__nv_bfloat16>, dim3(grid_for(items, 256)), dim3(256), 0, st, (const __nv_bfloat16 *)w,
+                         (__nv_bfloat16 *)workspace, items, C, Cp);
+        } else if (dtype == ITB_F16)
             launch_k(repack_filters_kernel<__half>, dim3(grid_for(total, 256)), dim3(256), 0, st, (const __half *)w,
                      (__half *)workspace, total, C, R * S, Cp);
         else

@@ -28,7 +28,7 @@ def vp(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def timeit(fn, reps=20, warm=3):
+def timeit(fn, reps=int(os.environ.get("CONV_BENCH_REPS", "20")), warm=int(os.environ.get("CONV_BENCH_WARM", "3"))):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -46,6 +46,9 @@ def main():
     if "--batch" in sys.argv:
         B = int(sys.argv[sys.argv.index("--batch") + 1])
     with_cudnn = "cudnn" in sys.argv
+    global LAYERS
+    if os.environ.get("CONV_BENCH_LAYERS"):  # indices into LAYERS, e.g. "1,2,9,21"
+        LAYERS = [LAYERS[int(i)] for i in os.environ["CONV_BENCH_LAYERS"].split(",")]
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     dt = 10  # ITB_F16
     tot = {"nchw": 0.0, "nhwc": 0.0, "cudnn": 0.0, "floor": 0.0}
