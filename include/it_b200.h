@@ -218,6 +218,15 @@ int it_b200_conv2d_fused_nhwc_out(int dtype, const void *x, const void *w, void 
                                   const float *bn_var, const float *bn_scale, const float *bn_bias, float bn_eps,
                                   const void *residual, int relu, void *workspace, int64_t workspace_bytes, void *stream);
 
+/* The stem of an image network (kernels/conv_stem.cu): x NCHW with C <= 4 channels, y NHWC [N, OH, OW, F], F <= 64 (F % 8 == 0),
+ * filters up to 7 x 8, strides <= 2, no dilation / groups, optional BatchNorm (folded, one rounding) + ReLU.  The input patch of a
+ * 16 x 16 output block is staged in shared memory and mma.sync fragments are built from it: no im2col matrix, no workspace. */
+int it_b200_conv2d_stem_supported(int dtype, int C, int F, int R, int S, int ph, int pw, int sh, int sw, int dh, int dw,
+                                  int groups);
+int it_b200_conv2d_stem(int dtype, const void *x, const void *w, void *y, int N, int C, int H, int W, int F, int R, int S, int ph,
+                        int pw, int sh, int sw, const float *bn_mean, const float *bn_var, const float *bn_scale,
+                        const float *bn_bias, float bn_eps, int relu, void *stream);
+
 /* Implicit-GEMM Conv over NHWC activations (kernels/conv_nhwc.cu): x is [N, H, W, C], w stays in the reference's [F, C, R, S]
  * order, y is [N, OH, OW, F] (y_nhwc = 1) or [N, F, OH, OW] (y_nhwc = 0, for a consumer outside the NHWC domain); `residual` is
  * laid out like y.  No im2col matrix: the TMA unit's im2col mode feeds tcgen05 directly.  The optional tail

@@ -69,6 +69,8 @@ _SIGS = {
     "it_b200_conv2d_workspace": (c_int64, [c_int] * 15),
     "it_b200_conv2d_nchw_to_nhwc_supported": (c_int, [c_int] * 15),
     "it_b200_conv2d_fused_nhwc_out": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, vp, vp, vp, c_float, vp, c_int, vp, c_int64, vp]),
+    "it_b200_conv2d_stem_supported": (c_int, [c_int] * 12),
+    "it_b200_conv2d_stem": (c_int, [c_int, vp, vp, vp] + [c_int] * 11 + [vp, vp, vp, vp, c_float, c_int, vp]),
     "it_b200_conv2d_nhwc_supported": (c_int, [c_int] * 12),
     "it_b200_conv2d_nhwc_workspace": (c_int64, [c_int] * 5),
     "it_b200_conv2d_nhwc": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, vp, vp, vp, c_float, vp, c_int, vp, c_int64, vp]),

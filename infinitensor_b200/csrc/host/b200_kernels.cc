@@ -643,7 +643,13 @@ bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx, int layout) {
     }
     int64_t wsb = it_b200_conv2d_workspace(DTI(x), n, c, h, wd, f, r, s, ph, pw, sh, sw, dh, dw, g);
     void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
+    if ((layout & 2) && !res && it_b200_conv2d_stem_supported(DTI(x), c, f, r, s, ph, pw, sh, sw, dh, dw, g)) {
+        CK(it_b200_conv2d_stem(DTI(x), P(x), P(w), P(ops.back()->getOutput()), n, c, h, wd, f, r, s, ph, pw, sh, sw, bm, bv, bs, bb, eps,
+                               relu ? 1 : 0, S()), ops.back());
+        return true;
+    }
     if (layout & 2) {
+        IT_ASSERT(bn, "NHWC-output conv step without a BatchNorm tail outside the stem kernel");
         int rc = it_b200_conv2d_fused_nhwc_out(DTI(x), P(x), P(w), P(ops.back()->getOutput()), n, c, h, wd, f, r, s, ph, pw, sh, sw, dh, dw, g,
                                                bm, bv, bs, bb, eps, res ? P(res) : nullptr, relu ? 1 : 0, ws, wsb, S());
         IT_ASSERT(rc != 2, "NHWC-output conv step on a shape the im2col GEMM does not scatter (schedule / kernel disagree)");

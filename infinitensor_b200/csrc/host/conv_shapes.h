@@ -41,4 +41,10 @@ inline bool conv_nhwc_ok(int dtype, int C, int F, int R, int S, int ph, int pw, 
            pw <= 127 && (R - 1) * dh - ph <= 128 && (S - 1) * dw - pw <= 128 && (R - 1) * dh < 65536 && (S - 1) * dw < 65536;
 }
 
+// NCHW input with <= 4 channels, NHWC output through the stem kernel (it_b200_conv2d_stem): no residual
+inline bool conv_stem_ok(int dtype, int C, int F, int R, int S, int ph, int pw, int sh, int sw, int dh, int dw, int groups) {
+    return (dtype == ITB_F16 || dtype == ITB_BF16) && groups == 1 && C >= 1 && C <= 4 && F >= 8 && F <= 64 && F % 8 == 0 && R >= 1 &&
+           R <= 7 && S >= 1 && S <= 8 && sh >= 1 && sh <= 2 && sw >= 1 && sw <= 2 && dh == 1 && dw == 1 && ph >= 0 && pw >= 0;
+}
+
 }  // namespace itb

@@ -374,8 +374,11 @@ struct LayoutPass {
                     // operands of the chain other than x / residual (weights, statistics) are never candidates
                     if (is(x) && !itb::conv_nhwc_ok(dt, ci, f, r, s, ph, pw, sh, sw, dh, dw, g)) changed |= drop(x);
                     if (is(y) && !is(x)) {
+                        // an NCHW input can still enter the domain: the stem kernel (<= 4 channels, no residual) or the
+                        // folded im2col GEMM scattering its result channel-innermost
                         const bool tail = st.kind == ExecStep::ConvBnAct;
-                        if (!tail || !itb::conv_nchw_to_nhwc_ok(dt, n, ci, h, w, f, r, s, ph, pw, sh, sw, dh, dw, g))
+                        const bool stem = !res && itb::conv_stem_ok(dt, ci, f, r, s, ph, pw, sh, sw, dh, dw, g);
+                        if (!stem && (!tail || !itb::conv_nchw_to_nhwc_ok(dt, n, ci, h, w, f, r, s, ph, pw, sh, sw, dh, dw, g)))
                             changed |= drop(y);
                     }
                     if (res && !free4(res) && is(res) != is(y)) {

@@ -289,6 +289,21 @@ def conv2d_fused(x, w, ph, pw, sh, sw, dh, dw, bn, eps, residual, relu, dt=F16, 
     return np.ascontiguousarray(host(y).transpose(0, 3, 1, 2)) if y_nhwc else host(y)
 
 
+def conv2d_stem(x, w, ph, pw, sh, sw, bn=None, eps=1e-5, relu=False, dt=F16):
+    """NCHW x (<= 4 channels) -> NHWC y through the stem kernel; the result is permuted back to NCHW on the host."""
+    N, C, H, W = x.shape
+    F, _, R, S = w.shape
+    OH, OW = (H + 2 * ph - R) // sh + 1, (W + 2 * pw - S) // sw + 1
+    xd, wd = dev(x, dt), dev(w, dt)
+    y = torch.empty((N, OH, OW, F), dtype=xd.dtype, device="cuda")
+    ms = [dev(np.asarray(v, np.float32)) for v in bn] if bn is not None else [None] * 4
+    assert L.lib.it_b200_conv2d_stem_supported(dt, C, F, R, S, ph, pw, sh, sw, 1, 1, 1) == 1
+    L.check(L.lib.it_b200_conv2d_stem(dt, ptr(xd), ptr(wd), ptr(y), N, C, H, W, F, R, S, ph, pw, sh, sw, ptr(ms[0]), ptr(ms[1]),
+                                      ptr(ms[2]), ptr(ms[3]), eps, int(relu), stream()))
+    sync()
+    return np.ascontiguousarray(host(y).transpose(0, 3, 1, 2))
+
+
 def conv2d_nhwc(x, w, ph, pw, sh, sw, dh, dw, bn=None, eps=1e-5, residual=None, relu=False, dt=F16, y_nhwc=True):
     """x, residual and the result are NCHW numpy arrays; the permutation to / from NHWC happens here (host side)."""
     N, C, H, W = x.shape

@@ -449,6 +449,28 @@ def test_conv_nhwc_parity(K, dt):
 
 
 @pytest.mark.parametrize("dt", [F16, BF16])
+def test_conv_stem_parity(K, dt):
+    """The stem kernel (NCHW input with <= 4 channels -> NHWC, fragments built from a shared-memory patch) against the oracle:
+    the ResNet stem, ragged image sizes (blocks cut by the border), 1..4 channels, small filters, stride 1, F < 64."""
+    tol = {F16: 8e-3, BF16: 6e-2}[dt]
+    for ci, (xs, ws, args) in enumerate([((2, 3, 64, 64), (64, 3, 7, 7), (3, 3, 2, 2)),
+                                         ((3, 3, 45, 37), (64, 3, 7, 7), (3, 3, 2, 2)),
+                                         ((2, 4, 19, 23), (24, 4, 3, 3), (1, 1, 1, 1)),
+                                         ((2, 1, 30, 17), (8, 1, 5, 8), (2, 0, 1, 2)),
+                                         ((1, 2, 33, 33), (40, 2, 1, 1), (0, 0, 2, 1))]):
+        x, w = rnd(xs, 226 + ci, dt), rnd(ws, 227 + ci, dt, 0.1)
+        ph, pw, sh, sw = args
+        want = oracle.conv2d(x, w, ph, pw, sh, sw, 1, 1, dt=dt)
+        close(K.conv2d_stem(x, w, *args, dt=dt), want, tol, tol)
+        F = ws[0]
+        rng = np.random.default_rng(240 + ci)
+        bn = (rng.standard_normal(F).astype(np.float32) * 0.1, rng.uniform(0.5, 1.5, F).astype(np.float32),
+              rng.uniform(0.5, 1.5, F).astype(np.float32), rng.standard_normal(F).astype(np.float32) * 0.1)
+        ora = np.maximum(oracle.batch_norm(want, *bn, 1e-5, dt), 0)
+        close(K.conv2d_stem(x, w, *args, bn=bn, relu=True, dt=dt), ora, 2.5 * tol, 2.5 * tol)
+
+
+@pytest.mark.parametrize("dt", [F16, BF16])
 def test_conv_nhwc_fused_tail(K, dt):
     """Conv -> BatchNorm -> [+ residual] -> [ReLU] in the implicit-GEMM epilogue (fp32, one rounding) against the oracle chain
     (which rounds after every operator, like the reference's separate kernels)."""
