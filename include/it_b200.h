@@ -234,9 +234,15 @@ int it_b200_conv2d_stem(int dtype, const void *x, const void *w, void *y, int N,
  * entry point above rounds after every stage).  f16 / bf16, groups = 1, C % 8 == 0, F % 8 == 0, strides <= 8; _supported answers
  * 1 for shapes the kernel takes.  Workspace: the filters re-ordered to [F][R*S][ceil64(C)] (0 bytes for 1x1 filters).
  * Replaces cudnnConvolutionForward (reference src/kernels/cuda/conv.cc:143-168) for the layout the runtime's NHWC domain uses
- * between Conv / Pool / Add / Relu steps (host/schedule.cc). */
+ * between Conv / Pool / Add / Relu steps (host/schedule.cc).
+ * workspace_bytes < 0: `workspace` already holds the filters as it_b200_conv_repack_filters wrote them (-workspace_bytes = their
+ * size) and is only read -- the runtime repacks every bank of a graph in one launch at the start of a step. */
 int it_b200_conv2d_nhwc_supported(int dtype, int C, int F, int R, int S, int ph, int pw, int sh, int sw, int dh, int dw,
                                   int groups);
+/* n filter banks [F_i, C_i, R_i, S_i] -> [F_i][R_i*S_i][ceil64(C_i)] (out[i]: it_b200_conv2d_nhwc_workspace bytes each), one launch per
+ * 24 banks */
+int it_b200_conv_repack_filters(int dtype, int n, const void *const *w, void *const *out, const int *F, const int *C, const int *R,
+                                const int *S, void *stream);
 int64_t it_b200_conv2d_nhwc_workspace(int dtype, int C, int F, int R, int S);
 int it_b200_conv2d_nhwc(int dtype, const void *x, const void *w, void *y, int y_nhwc, int N, int C, int H, int W, int F, int R,
                         int S, int ph, int pw, int sh, int sw, int dh, int dw, const float *bn_mean, const float *bn_var,

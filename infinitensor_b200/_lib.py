@@ -72,6 +72,7 @@ _SIGS = {
     "it_b200_conv2d_stem_supported": (c_int, [c_int] * 12),
     "it_b200_conv2d_stem": (c_int, [c_int, vp, vp, vp] + [c_int] * 11 + [vp, vp, vp, vp, c_float, c_int, vp]),
     "it_b200_conv2d_nhwc_supported": (c_int, [c_int] * 12),
+    "it_b200_conv_repack_filters": (c_int, [c_int, c_int, vp, vp, vp, vp, vp, vp, vp]),
     "it_b200_conv2d_nhwc_workspace": (c_int64, [c_int] * 5),
     "it_b200_conv2d_nhwc": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, vp, vp, vp, c_float, vp, c_int, vp, c_int64, vp]),
     "it_b200_conv2d": (c_int, [c_int, vp, vp, vp] + [c_int] * 14 + [vp, c_int64, vp]),

@@ -636,7 +636,16 @@ bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx, int layout) {
     const float eps = bn ? bn->getEps() : 0.f;
     if (layout & 1) {
         int64_t wsb = it_b200_conv2d_nhwc_workspace(DTI(x), c, f, r, s);
-        void *ws = wsb ? RT(ctx)->getWorkspace((size_t)wsb) : nullptr;
+        void *ws = nullptr;
+        if (wsb) {
+            auto packed = RT(ctx)->findPackedFilter(P(w));  // repacked at the start of this step (prepConvFilters)
+            if (packed.first && (int64_t)packed.second >= wsb) {
+                ws = packed.first;
+                wsb = -(int64_t)packed.second;
+            } else {
+                ws = RT(ctx)->getWorkspace((size_t)wsb);  // a step executed on its own (tune): repack in place
+            }
+        }
         CK(it_b200_conv2d_nhwc(DTI(x), P(x), P(w), P(ops.back()->getOutput()), (layout & 2) ? 1 : 0, n, c, h, wd, f, r, s, ph, pw, sh, sw, dh,
                                dw, bm, bv, bs, bb, eps, res ? P(res) : nullptr, relu ? 1 : 0, ws, wsb, S()), ops.back());
         return true;
@@ -665,6 +674,34 @@ bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx, int layout) {
     if (rc == 2) return false;
     CK(rc, ops.back());
     return true;
+}
+
+// every NHWC conv of the schedule with filters larger than 1x1: re-order all the filter banks in one launch, into buffers the
+// runtime keeps per weight tensor (so no conv waits for a repack kernel of its own)
+void prepConvFilters(const vector<ExecStep> &sched, const RuntimeObj *ctx) {
+    vector<const void *> src[2];
+    vector<void *> dst[2];
+    vector<int> nF[2], nC[2], nR[2], nS[2];
+    for (auto &st : sched) {
+        if (!(st.layout & 1) || st.ops[0]->getOpType() != OpType::Conv) continue;
+        auto conv = as<ConvObj>(st.ops[0]);
+        auto x = conv->getInputs(0), w = conv->getInputs(1);
+        auto [n, c, h, wd, f, r, s] = conv->getNCHWFRS();
+        (void)n; (void)h; (void)wd;
+        const int64_t bytes = it_b200_conv2d_nhwc_workspace(DTI(x), c, f, r, s);
+        if (bytes == 0) continue;
+        const int k = DTI(x) == ITB_F16 ? 0 : 1;
+        src[k].push_back(P(w));
+        dst[k].push_back(RT(ctx)->packedFilterBuffer(P(w), (size_t)bytes));
+        nF[k].push_back(f);
+        nC[k].push_back(c);
+        nR[k].push_back(r);
+        nS[k].push_back(s);
+    }
+    for (int k = 0; k < 2; ++k)
+        if (!src[k].empty())
+            CK(it_b200_conv_repack_filters(k == 0 ? ITB_F16 : ITB_BF16, (int)src[k].size(), src[k].data(), dst[k].data(), nF[k].data(),
+                                           nC[k].data(), nR[k].data(), nS[k].data(), S()), sched.front().ops.back());
 }
 
 // MaxPool / AveragePool inside the NHWC domain

@@ -29,7 +29,23 @@ CudaRuntimeObj::~CudaRuntimeObj() {
     if (p2pLocal) cudaFree(p2pLocal);
     if (p2pTimeoutHost) cudaFreeHost(p2pTimeoutHost);
     if (workspace) cudaFree(workspace);
+    for (auto &kv : packedFilters) cudaFree(kv.second.first);
     if (stream) cudaStreamDestroy(stream);
+}
+
+void *CudaRuntimeObj::packedFilterBuffer(const void *weights, size_t bytes) const {
+    auto it = packedFilters.find(weights);
+    if (it != packedFilters.end() && it->second.second >= bytes) return it->second.first;
+    IT_ASSERT(!capturing, "conv filter buffer requested during CUDA-graph capture (the eager pass before it allocates them)");
+    if (it != packedFilters.end()) {
+        checkCudaError(cudaStreamSynchronize(stream));
+        cudaFree(it->second.first);
+        packedFilters.erase(it);
+    }
+    void *p = nullptr;
+    checkCudaError(cudaMalloc(&p, bytes));
+    packedFilters[weights] = {p, bytes};
+    return p;
 }
 
 void *CudaRuntimeObj::alloc(size_t size) {
@@ -175,6 +191,7 @@ void CudaRuntimeObj::runWithoutSyncImpl(const Graph &graph, bool validate) const
         const char *e = std::getenv("ITB_NVTX");
         return e && e[0] == '1';
     }();
+    b200::prepConvFilters(sched, this);
     for (size_t i = 0; i < sched.size(); ++i) {
         const auto &st = sched[i];
         struct Range {

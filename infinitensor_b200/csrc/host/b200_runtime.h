@@ -11,6 +11,7 @@
 
 #include <list>
 #include <mutex>
+#include <unordered_map>
 
 #include "core.h"
 
@@ -57,6 +58,9 @@ class CudaRuntimeObj : public RuntimeObj {
     cudaStream_t stream = nullptr;
     mutable void *workspace = nullptr;
     mutable size_t workspaceSize = 0;
+    // conv filters re-ordered for the implicit-GEMM kernel, one buffer per weight tensor (keyed by its device address), refilled at
+    // the start of every step by ONE batched launch (b200::prepConvFilters) -- never a stale copy of weights the user has rewritten
+    mutable std::unordered_map<const void *, std::pair<void *, size_t>> packedFilters;
     Ref<CommunicatorObj> comm;
     void *p2pLocal = nullptr;
     void *p2pWs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -119,6 +123,11 @@ class CudaRuntimeObj : public RuntimeObj {
     // one scratch buffer, always the same base pointer (reference cuda_runtime.h:85-88)
     void *getWorkspace(size_t size) const;
     size_t getWorkspaceSize() const { return workspaceSize; }
+    void *packedFilterBuffer(const void *weights, size_t bytes) const;  // allocates on first use (outside CUDA-graph capture)
+    std::pair<void *, size_t> findPackedFilter(const void *weights) const {
+        auto it = packedFilters.find(weights);
+        return it == packedFilters.end() ? std::pair<void *, size_t>{nullptr, 0} : it->second;
+    }
     cudaStream_t getStream() const { return stream; }
 
     // NVLink peer-memory communicator for the fused one-shot all-reduce (kernels/allreduce.cu)
@@ -152,6 +161,7 @@ void runSiluMul(const Operator &silu, const Operator &mul, const RuntimeObj *ctx
 bool runAllReduceAddNorm(const OpVec &ops, const RuntimeObj *ctx);
 // Conv -> BatchNorm -> [Add] -> [Relu] in the GEMM epilogue; false = shape not taken (nothing launched)
 bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx, int layout = 0);
+void prepConvFilters(const vector<ExecStep> &sched, const RuntimeObj *ctx);
 void runPoolNhwc(const Operator &op, const RuntimeObj *ctx);
 void runAttentionRope(const Operator &ropeQ, const Operator &ropeK, const Operator &att, const RuntimeObj *ctx);
 // {Transpose(k), MatMul, [Div | Mul], [Add], Softmax, MatMul} as one fused tcgen05 attention kernel; false = not taken

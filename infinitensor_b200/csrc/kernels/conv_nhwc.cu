@@ -451,6 +451,55 @@ __global__ void __launch_bounds__(256) repack_filters9_kernel(const T *__restric
     }
 }
 
+// every filter bank of a graph in ONE launch (blockIdx.y = bank): the runtime repacks at the start of each step into buffers it
+// owns, so no conv waits behind its own repack kernel (16 dependent ~5 us launches per ResNet-50 step otherwise)
+constexpr int CV_REPACK_BATCH = 24;
+struct RepackBatch {
+    const void *src[CV_REPACK_BATCH];
+    void *dst[CV_REPACK_BATCH];
+    int F[CV_REPACK_BATCH], C[CV_REPACK_BATCH], RS[CV_REPACK_BATCH], Cp[CV_REPACK_BATCH];
+};
+template <typename T>
+__global__ void __launch_bounds__(256) repack_filters_batch_kernel(const __grid_constant__ RepackBatch b) {
+    pdl_trigger();
+    pdl_wait();  // the convs of the previous step may still read the buffers
+    const int e = blockIdx.y;
+    const T *__restrict__ w = (const T *)b.src[e];
+    T *__restrict__ out = (T *)b.dst[e];
+    const int C = b.C[e], RS = b.RS[e], Cp = b.Cp[e];
+    if (RS == 9) {
+        const int cp8 = Cp / 8;
+        const int64_t items = (int64_t)b.F[e] * cp8;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+            const int c8 = (int)(i % cp8);
+            const int64_t f = i / cp8;
+            alignas(16) T in[72];
+            const bool real = c8 * 8 < C;
+            if (real) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(w + (f * C + c8 * 8) * 9);
+#pragma unroll
+                for (int v = 0; v < 9; ++v) reinterpret_cast<uint4 *>(in)[v] = __ldg(src + v);
+            }
+#pragma unroll
+            for (int rs = 0; rs < 9; ++rs) {
+                alignas(16) T o[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o[c] = real ? in[c * 9 + rs] : from_f<T>(0.f);
+                *reinterpret_cast<uint4 *>(out + (f * 9 + rs) * Cp + c8 * 8) = *reinterpret_cast<const uint4 *>(o);
+            }
+        }
+    } else {
+        const int64_t total = (int64_t)b.F[e] * RS * Cp;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int c = (int)(i % Cp);
+            const int64_t t = i / Cp;
+            const int rs = (int)(t % RS);
+            const int64_t f = t / RS;
+            out[i] = c < C ? w[(f * C + c) * RS + rs] : from_f<T>(0.f);
+        }
+    }
+}
+
 static PFN_cuTensorMapEncodeIm2col_v12000 get_im2col_fn() {
     static PFN_cuTensorMapEncodeIm2col_v12000 fn = nullptr;
     static std::once_flag once;
@@ -635,7 +684,12 @@ extern "C" int it_b200_conv2d_nhwc(int dtype, const void *x, const void *w, void
     ITB_CHECK((int64_t)N * OH * OW < (1ll << 31) - CV_BM, "conv(nhwc): too many output pixels");
     const int Cp = nhwc_cp(C, R, S);
     const void *wk = w;
-    if (R * S > 1) {
+    if (R * S > 1 && workspace_bytes < 0) {
+        // filters already repacked by it_b200_conv_repack_filters (the runtime does that once per step for all convs)
+        ITB_CHECK(workspace && -workspace_bytes >= it_b200_conv2d_nhwc_workspace(dtype, C, F, R, S) && aligned16(workspace),
+                  "conv(nhwc): repacked filters too small");
+        wk = workspace;
+    } else if (R * S > 1) {
         const int64_t need = it_b200_conv2d_nhwc_workspace(dtype, C, F, R, S);
         ITB_CHECK(workspace && workspace_bytes >= need && aligned16(workspace), "conv(nhwc): workspace %lld < %lld bytes",
                   (long long)workspace_bytes, (long long)need);
@@ -662,4 +716,32 @@ extern "C" int it_b200_conv2d_nhwc(int dtype, const void *x, const void *w, void
                                           bn_var, bn_scale, bn_bias, bn_eps, residual, relu, st);
     return launch_conv_nhwc_t<__nv_bfloat16>(true, x, wk, Cp, y, y_nhwc, N, C, H, W, F, R, S, OH, OW, ph, pw, sh, sw, dh, dw,
                                              bn_mean, bn_var, bn_scale, bn_bias, bn_eps, residual, relu, st);
+}
+
+extern "C" int it_b200_conv_repack_filters(int dtype, int n, const void *const *w, void *const *out, const int *F, const int *C,
+                                           const int *R, const int *S, void *stream) {
+    ITB_CHECK(dtype == ITB_F16 || dtype == ITB_BF16, "conv_repack_filters: f16 / bf16");
+    auto st = (cudaStream_t)stream;
+    for (int base = 0; base < n; base += CV_REPACK_BATCH) {
+        const int cnt = std::min(CV_REPACK_BATCH, n - base);
+        RepackBatch b{};
+        int64_t most = 1;
+        for (int i = 0; i < CV_REPACK_BATCH; ++i) {
+            const int j = base + std::min(i, cnt - 1);  // unused slots repeat the last bank (never launched: gridDim.y = cnt)
+            ITB_CHECK(C[j] % 8 == 0 && aligned16(w[j]) && aligned16(out[j]), "conv_repack_filters: bank %d: C %% 8 == 0, 16-byte aligned", j);
+            b.src[i] = w[j];
+            b.dst[i] = out[j];
+            b.F[i] = F[j];
+            b.C[i] = C[j];
+            b.RS[i] = R[j] * S[j];
+            b.Cp[i] = nhwc_cp(C[j], R[j], S[j]);
+            most = std::max<int64_t>(most, (int64_t)F[j] * b.RS[i] * b.Cp[i] / (b.RS[i] == 9 ? 72 : 1));
+        }
+        const dim3 grid((unsigned)std::min<int64_t>((most + 255) / 256, 2 * kNumSMs), (unsigned)cnt);
+        cudaError_t e = dtype == ITB_F16 ? launch_k(repack_filters_batch_kernel<__half>, grid, dim3(256), 0, st, b)
+                                         : launch_k(repack_filters_batch_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, b);
+        ITB_CHECK(e == cudaSuccess, "conv_repack_filters: launch failed: %s", cudaGetErrorString(e));
+        count_launch();
+    }
+    return 0;
 }

@@ -266,6 +266,84 @@ __global__ void __launch_bounds__(256) pool2d_nhwc_kernel(int is_max, const T *_
     }
 }
 
+// 3x3 windows (the ResNet max pool) with the nine taps unrolled: all loads of a thread are issued before the first use (clamped
+// addresses, validity applied afterwards) -- the generic kernel above, one dependent load at a time behind its bounds checks, reached
+// 2 TB/s on [64, 112, 112, 64]
+template <typename T>
+__global__ void __launch_bounds__(256) pool2d_nhwc3x3_kernel(int is_max, const T *__restrict__ x, T *__restrict__ y, int64_t total,
+                                                             int C8, int H, int W, int ph, int pw, int sh, int sw, int OH, int OW) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int V = 8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        int64_t t = i / C8;
+        const int ow = (int)(t % OW);
+        t /= OW;
+        const int oh = (int)(t % OH);
+        const int64_t n = t / OH;
+        Vec16<T> v[9];
+        bool ok[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int ih = oh * sh - ph + r, iw = ow * sw - pw + s;
+                ok[r * 3 + s] = ih >= 0 && ih < H && iw >= 0 && iw < W;
+                const int ihc = min(max(ih, 0), H - 1), iwc = min(max(iw, 0), W - 1);
+                v[r * 3 + s] = ld16(x + (((n * H + ihc) * W + iwc) * C8 + c8) * V);
+            }
+        Vec16<T> o;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            float acc = is_max ? -INFINITY : 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const float f = to_f(v[k].v[e]);
+                if (ok[k]) acc = is_max ? fmaxf(acc, f) : acc + f;
+            }
+            o.v[e] = from_f<T>(is_max ? acc : acc / 9.f);
+        }
+        st16(y + i * V, o);
+    }
+}
+
+// global average pool ([N, H, W, C] -> [N, 1, 1, C]): block = 32 channel chunks x 8 pixel groups, shared-memory reduction over the groups
+// (the windowed kernel walks the H*W taps of one output serially: 31 us for [64, 7, 7, 2048])
+template <typename T>
+__global__ void __launch_bounds__(256) global_avgpool_nhwc_kernel(const T *__restrict__ x, T *__restrict__ y, int C8, int HW) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int V = 8;
+    __shared__ float part[8][32][V + 1];
+    const int cx = threadIdx.x & 31, pg = threadIdx.x >> 5;
+    const int c8 = blockIdx.x * 32 + cx;
+    const int64_t n = blockIdx.y;
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    if (c8 < C8)
+        for (int p = pg; p < HW; p += 8) {
+            const Vec16<T> v = ld16(x + ((n * HW + p) * C8 + c8) * V);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] += to_f(v.v[e]);
+        }
+#pragma unroll
+    for (int e = 0; e < V; ++e) part[pg][cx][e] = acc[e];
+    __syncthreads();
+    if (pg == 0 && c8 < C8) {
+        Vec16<T> o;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            float s = 0.f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) s += part[g][cx][e];
+            o.v[e] = from_f<T>(s / (float)HW);
+        }
+        st16(y + (n * C8 + c8) * V, o);
+    }
+}
+
 // y = scale[c] * (x - mean[c]) / sqrt(var[c] + eps) + bias[c] over NCHW (batch_norm.cc:9-69 semantics; fp32 parameters).
 // VEC: one thread = one 16-byte vector inside a single (n, c) plane (HW % V == 0), one channel lookup per vector.
 template <typename T, bool VEC>
@@ -548,6 +626,27 @@ extern "C" int it_b200_pool2d_nhwc(int dtype, int is_max, const void *x, void *y
               "pool2d(nhwc): f16 / bf16 with C %% 8 == 0 (C = %d)", C);
     const int64_t total = (int64_t)N * OH * OW * (C / 8);
     if (total == 0) return 0;
+    auto st = (cudaStream_t)stream;
+    if (!is_max && kh == H && kw == W && ph == 0 && pw == 0 && OH == 1 && OW == 1 && dh == 1 && dw == 1 && N <= 65535) {
+        const dim3 grid((unsigned)((C / 8 + 31) / 32), (unsigned)N);
+        if (dtype == ITB_F16)
+            launch_k(global_avgpool_nhwc_kernel<__half>, grid, dim3(256), 0, st, (const __half *)x, (__half *)y, C / 8, H * W);
+        else
+            launch_k(global_avgpool_nhwc_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, (const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, C / 8,
+                     H * W);
+        ITB_LAUNCH_CHECK("pool2d(nhwc, global average)");
+        return 0;
+    }
+    if (kh == 3 && kw == 3 && dh == 1 && dw == 1) {
+        if (dtype == ITB_F16)
+            launch_k(pool2d_nhwc3x3_kernel<__half>, dim3(grid_for(total, 256)), dim3(256), 0, st, is_max, (const __half *)x, (__half *)y,
+                     total, C / 8, H, W, ph, pw, sh, sw, OH, OW);
+        else
+            launch_k(pool2d_nhwc3x3_kernel<__nv_bfloat16>, dim3(grid_for(total, 256)), dim3(256), 0, st, is_max, (const __nv_bfloat16 *)x,
+                     (__nv_bfloat16 *)y, total, C / 8, H, W, ph, pw, sh, sw, OH, OW);
+        ITB_LAUNCH_CHECK("pool2d(nhwc, 3x3)");
+        return 0;
+    }
     if (dtype == ITB_F16)
         launch_k(pool2d_nhwc_kernel<__half>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, is_max, (const __half *)x,
                  (__half *)y, total, C / 8, H, W, kh, kw, dh, dw, ph, pw, sh, sw, OH, OW);

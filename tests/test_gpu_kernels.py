@@ -419,9 +419,13 @@ def test_conv_fused_tail_bit_identical(K, dt):
 def test_pool_nhwc_parity(K, dt):
     """NHWC pooling = the NCHW kernel on the permuted tensor, bit for bit (same fp32 arithmetic)."""
     img = rnd((3, 24, 13, 11), 301, dt)
-    for kind, args in [("max", (3, 3, 1, 1, 1, 1, 2, 2)), ("avg", (3, 2, 1, 1, 1, 0, 2, 1)), ("avg", (13, 11, 1, 1, 0, 0, 1, 1)),
+    for kind, args in [("max", (3, 3, 1, 1, 1, 1, 2, 2)), ("avg", (3, 3, 1, 1, 1, 1, 2, 1)), ("avg", (3, 2, 1, 1, 1, 0, 2, 1)),
                        ("max", (2, 2, 2, 1, 0, 1, 1, 2))]:
         assert np.array_equal(K.pool2d_nhwc(kind, img, *args, dt=dt), K.pool2d(kind, img, *args, dt))
+    # global average pool: its own kernel (pixel groups reduced through shared memory -> another fp32 summation order)
+    big = rnd((5, 264, 7, 7), 302, dt)
+    close(K.pool2d_nhwc("avg", big, 7, 7, 1, 1, 0, 0, 1, 1, dt=dt), K.pool2d("avg", big, 7, 7, 1, 1, 0, 0, 1, 1, dt), 2 * EPS[dt], 1e-6)
+    close(K.pool2d_nhwc("avg", img, 13, 11, 1, 1, 0, 0, 1, 1, dt=dt), K.pool2d("avg", img, 13, 11, 1, 1, 0, 0, 1, 1, dt), 2 * EPS[dt], 1e-6)
 
 
 NHWC_CASES = [((2, 64, 56, 56), (256, 64, 1, 1), (0, 0, 1, 1, 1, 1)),      # 1x1, one k-tile, filters used as stored
