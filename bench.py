@@ -540,9 +540,10 @@ def run_model_config(args):
         ins = [(g.input, xin)]
         out_t, out_host = g.out, torch.empty((cfg.batch, cfg.classes), dtype=torch.float16).pin_memory()
         units, unit = cfg.batch, "images/s"
-        metric = "images/sec (device-timed) ResNet-50 forward, batch 64, fp16, conv/im2col-GEMM path, 1 B200"
+        metric = "images/sec (device-timed) ResNet-50 forward, batch 64, fp16, conv/im2col-GEMM path (implicit: TMA im2col -> tcgen05, NHWC domain), 1 B200"
         work = {"bound": "tensor", "per_step": 2 * 4.09e9 * cfg.batch, "unit": "TFLOP/s", "what": "2 x 4.09 GMAC x batch (SURVEY 8(d))"}
-        workload = {"workload": "resnet50_b64_fp16", "batch": cfg.batch, "image": cfg.image}
+        workload = {"workload": "resnet50_b64_fp16", "batch": cfg.batch, "image": cfg.image,
+                    "nhwc_steps": sum("@" in s for s in h.schedule())}
     for t, hbuf in ins:
         t.copyin_async(hbuf.data_ptr(), hbuf.numel() * hbuf.element_size())
     h.sync()

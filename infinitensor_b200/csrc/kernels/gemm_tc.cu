@@ -110,16 +110,18 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     if (threadIdx.x == 0) TC_MARK(1);
 
     if (warp == TC_EPI_WARPS) {
-        // ===== TMA producer =====
+        // ===== TMA producer (one thread; running ring slot / phase instead of it % S, it / S: a lone thread retires a dependent
+        // instruction every ~5 cycles, and two runtime divisions per k-tile made this loop the pace-setter of M = 128 GEMMs) =====
         if (lane == 0) {
             const uint64_t pol_w = l2_policy_evict_first();
             const uint64_t pol_x = l2_policy_evict_last();
             // PDL: weight tiles of the first ring are requested before waiting for the predecessor kernel
             const int pre = min(S, my_kt);
             if (!(g.act & ITB_MATMUL_B_CONST)) pdl_wait();  // B produced upstream: no early prefetch
-            for (int it = 0; it < pre; ++it) {
-                mbar_expect_tx(&full[it], TC_W_BYTES + p.x_bytes);
-                const int k0 = (kt_begin + it) * TC_BK;
+            const uint32_t tx = TC_W_BYTES + p.x_bytes;
+            int k0 = kt_begin * TC_BK;
+            for (int it = 0; it < pre; ++it, k0 += TC_BK) {
+                mbar_expect_tx(&full[it], tx);
                 if (p.w_kmajor) {
                     tma_load_3d(w_sm + it * TC_W_BYTES, &mapW, &full[it], k0, n0, bw, pol_w);
                 } else {
@@ -130,44 +132,56 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             TC_MARK(2);
             pdl_wait();
             TC_MARK(3);
-            for (int it = 0; it < pre; ++it)
-                tma_load_3d(x_sm + it * p.x_bytes, &mapX, &full[it], (kt_begin + it) * TC_BK, m0, bx, pol_x);
-            for (int it = pre; it < my_kt; ++it) {
-                const int s = it % S;
-                mbar_wait(&empty[s], ((it / S) - 1) & 1);
-                mbar_expect_tx(&full[s], TC_W_BYTES + p.x_bytes);
-                const int k0 = (kt_begin + it) * TC_BK;
+            k0 = kt_begin * TC_BK;
+            for (int it = 0; it < pre; ++it, k0 += TC_BK) tma_load_3d(x_sm + it * p.x_bytes, &mapX, &full[it], k0, m0, bx, pol_x);
+            int s = 0;            // pre == S whenever the loop below runs
+            uint32_t ph = 0;      // parity of the `empty` phase to wait for: flips each time the ring wraps
+            for (int it = pre; it < my_kt; ++it, k0 += TC_BK) {
+                mbar_wait(&empty[s], ph);
+                mbar_expect_tx(&full[s], tx);
+                uint8_t *wdst = w_sm + s * TC_W_BYTES;
                 if (p.w_kmajor) {
-                    tma_load_3d(w_sm + s * TC_W_BYTES, &mapW, &full[s], k0, n0, bw, pol_w);
+                    tma_load_3d(wdst, &mapW, &full[s], k0, n0, bw, pol_w);
                 } else {
-                    tma_load_3d(w_sm + s * TC_W_BYTES, &mapW, &full[s], n0, k0, bw, pol_w);
-                    tma_load_3d(w_sm + s * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[s], n0 + 64, k0, bw, pol_w);
+                    tma_load_3d(wdst, &mapW, &full[s], n0, k0, bw, pol_w);
+                    tma_load_3d(wdst + TC_W_BYTES / 2, &mapW, &full[s], n0 + 64, k0, bw, pol_w);
                 }
                 tma_load_3d(x_sm + s * p.x_bytes, &mapX, &full[s], k0, m0, bx, pol_x);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
         }
         __syncwarp();
     } else if (warp == TC_EPI_WARPS + 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            const uint32_t w_base = smem_u32(w_sm), x_base = smem_u32(x_sm);
+            // A = W tile, MN-major: 64-column groups 8 KB apart (LBO), 8-row k groups 1 KB apart (SBO); one k16 step = 16 rows x
+            //     128 B = 2 KB  (trans_b: the tile is [128 n rows x 128 B of k], K-major like X: 8-row groups 1 KB apart, k16 = +32 B)
+            // B = X tile, K-major: 8-row groups 1 KB apart (SBO); one k16 step = 32 B inside the 128 B row
+            // descriptors are advanced by adding to their (address >> 4) field
+            const uint64_t a_desc0 = p.w_kmajor ? umma_desc_sw128(smem_u32(w_sm), 0, 1024) : umma_desc_sw128(smem_u32(w_sm), TC_W_BYTES / 2, 1024);
+            const uint64_t b_desc0 = umma_desc_sw128(smem_u32(x_sm), 0, 1024);
+            const uint32_t a_kk = p.w_kmajor ? 2u : 128u, a_st = TC_W_BYTES >> 4, b_st = (uint32_t)p.x_bytes >> 4;
+            const uint32_t idesc = p.idesc;
+            int s = 0;
+            uint32_t ph = 0, acc = 0;
             for (int it = 0; it < my_kt; ++it) {
-                const int s = it % S;
-                mbar_wait(&full[s], (it / S) & 1);
+                mbar_wait(&full[s], ph);
                 if (it == 0) TC_MARK(4);
                 tc_fence_after();
+                const uint64_t a_desc = a_desc0 + (uint64_t)(s * a_st), b_desc = b_desc0 + (uint64_t)(s * b_st);
 #pragma unroll
                 for (int kk = 0; kk < TC_BK / 16; ++kk) {
-                    // A = W tile, MN-major: 64-column groups 8 KB apart (LBO), 8-row k groups 1 KB apart (SBO);
-                    //     one k16 step = 16 rows x 128 B = 2 KB
-                    // (trans_b: the tile is [128 n rows x 128 B of k], K-major like X: 8-row groups 1 KB apart, k16 = +32 B)
-                    const uint64_t a_desc = p.w_kmajor ? umma_desc_sw128(w_base + s * TC_W_BYTES + kk * 32, 0, 1024)
-                                                       : umma_desc_sw128(w_base + s * TC_W_BYTES + kk * 2048, TC_W_BYTES / 2, 1024);
-                    // B = X tile, K-major: 8-row groups 1 KB apart (SBO); one k16 step = 32 B inside the 128 B row
-                    const uint64_t b_desc = umma_desc_sw128(x_base + s * p.x_bytes + kk * 32, 0, 1024);
-                    tc_mma_f16(tmem_base, a_desc, b_desc, p.idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                    tc_mma_f16(tmem_base, a_desc + (uint64_t)(kk * a_kk), b_desc + 2 * kk, idesc, acc);
+                    acc = 1;
                 }
                 tc_commit(&empty[s]);  // stage reusable once these MMAs have read it
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
             tc_commit(acc_full);  // accumulator complete (also fires when my_kt == 0)
             TC_MARK(5);
@@ -204,6 +218,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         const int64_t c_off = g.c_nhwc ? (int64_t)gn * g.m
                               : g.c_block ? (int64_t)(gn / g.c_block) * g.c_block_stride + gn % g.c_block : gn;
         const int mode = (bias || (g.act & 0xff)) ? 2 : tail ? 1 : 0;  // (launch_tc_t refuses bias/act together with a tail)
+        const float bias_col = (bias && g.bias_sm == 0 && gn < g.n) ? to_f(bias[(int64_t)gn * g.bias_sn]) : 0.f;
         for (int c0 = c_begin; c0 < c_end; c0 += 16) {
             uint32_t v[16];
             if (my_kt > 0) {
@@ -263,18 +278,43 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                             if (j < rows) cp[(int64_t)j * c_ld] = from_f<T>(resv[j]);
                     }
                 } else {
+                    // bias / activation: the bias of a Gemm is a row vector (bias_sm == 0) -> ONE value per thread (its column), and
+                    // the activation switch is taken once per 16 rows, not per element (the per-element form cost 8.7 us of a 23 us
+                    // GPT-2 projection: ~115 instructions per stored value)
+                    float bv[16];
+                    const bool rb = (g.act & ITB_ACT_ROUND_BEFORE_BIAS) != 0;
+                    if (bias && g.bias_sm == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) bv[j] = bias_col;
+                    } else if (bias) {
+                        const T *bp = bias + (int64_t)(m0 + c0) * g.bias_sm + (int64_t)gn * g.bias_sn;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) bv[j] = j < rows ? to_f(bp[(int64_t)j * g.bias_sm]) : 0.f;
+                    }
+                    float fo[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        if (j >= rows) break;
-                        const int m = m0 + c0 + j;
                         float f = __uint_as_float(v[j]);
-                        if (bias) {
-                            if (g.act & ITB_ACT_ROUND_BEFORE_BIAS) f = round_t<T>(f);
-                            f += to_f(bias[m * g.bias_sm + gn * g.bias_sn]);
-                        }
-                        f = gemm_act(g.act, f);
-                        cp[(int64_t)j * c_ld] = from_f<T>(f);
+                        if (bias) f = (rb ? round_t<T>(f) : f) + bv[j];
+                        fo[j] = f;
                     }
+                    switch (g.act & 0xff) {
+                    case 1:
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) fo[j] = fo[j] > 0.f ? fo[j] : 0.f;
+                        break;
+                    case 2:
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) fo[j] = 1.f / (1.f + expf(-fo[j]));
+                        break;
+                    case 3:
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) fo[j] = tanhf(fo[j]);
+                        break;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < rows) cp[(int64_t)j * c_ld] = from_f<T>(fo[j]);
                 }
             }
         }
