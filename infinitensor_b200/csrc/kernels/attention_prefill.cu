@@ -9,7 +9,10 @@
 //   * Q, K, V tiles arrive by TMA (3-D tensor maps over [B*H, S, D], 128B swizzle) into shared memory;
 //   * S = Q K^T runs as tcgen05.mma (kind::f16, M = 128 queries, N = 128 keys, K = 16 per instruction, both operands K-major)
 //     into a [128 lanes x 128 columns] fp32 accumulator in TENSOR MEMORY;
-//   * each of the 128 threads owns one query row: it reads its row of S back with tcgen05.ld, applies the graph's own
+//   * 512 threads: warp w reads TMEM lanes [32 (w & 3), +32) = query rows, and the four warps sharing a lane quadrant split each
+//     128-key tile into 32-column parts (w >> 2) -- one warp per scheduler, as in the first version (128 threads, a whole row
+//     each), left every dependent exp / round chain exposed: 40 us per (head, tile) at GPT-2's size; the parts' running
+//     (max, sum) meet once in shared memory after pass A.  Each thread reads its part of S back with tcgen05.ld, applies the graph's own
 //     rounding points (MatMul output, Div / Mul by the scalar, Add mask -- each rounded to the storage type like the separate
 //     kernels), and the softmax: pass A accumulates the row maximum / sum over all key tiles (online), pass B recomputes S,
 //     writes P = exp(s - max) / sum (rounded like the Softmax kernel's output) as the K-major A operand into shared memory
@@ -26,6 +29,7 @@
 namespace itb {
 
 constexpr int AP_BQ = 128, AP_BK = 128;
+constexpr int AP_PARTS = 4, AP_PCOLS = AP_BK / AP_PARTS, AP_THREADS = 128 * AP_PARTS;
 constexpr int AP_MPAD = AP_BQ + 2;  // 65 words per key column: the transposing store hits 32 distinct banks
 
 struct ApArgs {
@@ -38,7 +42,7 @@ struct ApArgs {
 };
 
 template <typename T, int D>
-__global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_constant__ CUtensorMap mapQ,
+__global__ void __launch_bounds__(AP_THREADS, 1) attention_prefill_kernel(const __grid_constant__ CUtensorMap mapQ,
                                                                    const __grid_constant__ CUtensorMap mapK,
                                                                    const __grid_constant__ CUtensorMap mapV, const ApArgs a) {
     constexpr int DG = D / 64;                    // 64-column groups of the head dim
@@ -53,10 +57,13 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
     T *m_sm = reinterpret_cast<T *>(p_sm + P_BYTES);
     __shared__ __align__(8) uint64_t bar_load, bar_mma;
     __shared__ uint32_t tmem_slot;
+    __shared__ float red_m[AP_PARTS][AP_BQ], red_l[AP_PARTS][AP_BQ];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.y, q0 = blockIdx.x * AP_BQ;
-    const int row = threadIdx.x;  // query row inside the tile == TMEM lane
+    const int quad = warp & 3, part = warp >> 2;
+    const int row = quad * 32 + lane;  // query row inside the tile == TMEM lane
+    const int pc0 = part * AP_PCOLS;   // this thread's columns of every key tile: [pc0, pc0 + 32)
     pdl_trigger();
     if (threadIdx.x == 0) {
         mbar_init(&bar_load, 1);
@@ -98,21 +105,25 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
 
     float sc = 1.f;
     if (a.scale) sc = to_f(*(const T *)a.scale);
+    // s / 2^k == s * 2^-k exactly (GPT-2: sqrt(64)): spares a division per score and pass
+    const bool div_pow2 = a.scale && a.scale_is_div && (__float_as_uint(sc) & 0x007fffffu) == 0u && sc != 0.f && fabsf(sc) < 1e30f && fabsf(sc) > 1e-30f;
+    const float sc_mul = a.scale ? (a.scale_is_div ? (div_pow2 ? 1.f / sc : 0.f) : sc) : 1.f;
+    const bool use_mul = a.scale && (!a.scale_is_div || div_pow2);
     const int b = bh / a.H, h = bh % a.H;
     const T *mbase = a.mask ? (const T *)a.mask + b * a.mb + h * a.mh : nullptr;
     const bool mvec = mbase && a.mj == 1 && (a.mi & 7) == 0 && (((uintptr_t)mbase & 15) == 0);
     // cooperative, coalesced fill of the mask tile (rows q0.., keys j0..): 16 threads cover one row's 128 keys with 16-byte loads
     auto load_mask = [&](int j0) {
         if (!mbase) return;
-        const int jc = (threadIdx.x & 15) * 8, r0 = threadIdx.x >> 4;
-        // 8 rows' loads in flight before the first transposing store (the stores may alias the mask as far as the compiler
-        // knows: issued row by row, the 16 dependent L2 round trips alone cost ~16 us per tile -- measured)
+        const int jc = (threadIdx.x & 15) * 8, r0 = threadIdx.x >> 4;  // 32 rows per sweep
+        // all four sweeps' loads in flight before the first transposing store (the stores may alias the mask as far as the
+        // compiler knows: issued row by row, the dependent L2 round trips alone cost ~16 us per tile -- measured)
+        {
+            constexpr int NSW = AP_BQ / (AP_THREADS / 16);
+            uint4 buf[NSW];
 #pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-            uint4 buf[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = r0 + 8 * (hb * 8 + i);
+            for (int i = 0; i < NSW; ++i) {
+                const int r = r0 + (AP_THREADS / 16) * i;
                 const bool rok = q0 + r < a.Sq;
                 const T *src = mbase + (int64_t)(q0 + r) * a.mi + (int64_t)(j0 + jc) * a.mj;
                 if (rok && mvec && j0 + jc + 8 <= a.Skv && ((((int64_t)(q0 + r) * a.mi + j0 + jc) & 7) == 0)) {
@@ -125,8 +136,8 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = r0 + 8 * (hb * 8 + i);
+            for (int i = 0; i < NSW; ++i) {
+                const int r = r0 + (AP_THREADS / 16) * i;
                 const T *vals = reinterpret_cast<const T *>(&buf[i]);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) m_sm[(jc + e) * AP_MPAD + r] = vals[e];
@@ -138,7 +149,7 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
     // score of (this row, key j0 + c) from the raw accumulator value, with the graph's rounding points
     auto score = [&](float acc, int j) -> float {
         float s = round_t<T>(acc);                                      // MatMul output
-        if (a.scale) s = round_t<T>(a.scale_is_div ? s / sc : s * sc);  // Div / Mul by the scalar constant
+        if (a.scale) s = round_t<T>(use_mul ? s * sc_mul : s / sc);  // Div / Mul by the scalar constant
         if (mbase && row_ok) s = round_t<T>(s + to_f(m_sm[(j % AP_BK) * AP_MPAD + row]));  // Add(mask)
         return s;
     };
@@ -180,9 +191,9 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
         ph_mma ^= 1;
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < AP_BK; c0 += 16) {
+        for (int c0 = pc0; c0 < pc0 + AP_PCOLS; c0 += 16) {
             uint32_t v[16];
-            tmem_ld_32x32b_x16(tmem_s + ((uint32_t)(warp * 32) << 16) + c0, v);
+            tmem_ld_32x32b_x16(tmem_s + ((uint32_t)(quad * 32) << 16) + c0, v);
             float sv[16], mx = m;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -199,6 +210,23 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
         }
         tc_fence_before();
         __syncthreads();  // every row has read S before the next tile's MMA overwrites it (and K is reloaded)
+    }
+    // the four column parts of a row meet: global maximum, sums rescaled to it (same order for every part -> identical values)
+    red_m[part][row] = m;
+    red_l[part][row] = l;
+    __syncthreads();
+    {
+        float mg = -INFINITY;
+#pragma unroll
+        for (int pp = 0; pp < AP_PARTS; ++pp) mg = fmaxf(mg, red_m[pp][row]);
+        float lg = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < AP_PARTS; ++pp) {
+            const float mp = red_m[pp][row];
+            if (mp > -INFINITY) lg += red_l[pp][row] * expf(mp - mg);
+        }
+        m = mg;
+        l = lg;
     }
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
 
@@ -220,15 +248,17 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
             mbar_wait(&bar_load, ph_load);
             ph_load ^= 1;
         }
-        mma_s();
-        __syncthreads();  // mask tile complete
-        mbar_wait(&bar_mma, ph_mma);
-        ph_mma ^= 1;
-        tc_fence_after();
+        if (!single) {  // (one key tile: S of pass A is still in tensor memory)
+            mma_s();
+            __syncthreads();  // mask tile complete
+            mbar_wait(&bar_mma, ph_mma);
+            ph_mma ^= 1;
+            tc_fence_after();
+        }
 #pragma unroll 1
-        for (int c0 = 0; c0 < AP_BK; c0 += 16) {
+        for (int c0 = pc0; c0 < pc0 + AP_PCOLS; c0 += 16) {
             uint32_t v[16];
-            tmem_ld_32x32b_x16(tmem_s + ((uint32_t)(warp * 32) << 16) + c0, v);
+            tmem_ld_32x32b_x16(tmem_s + ((uint32_t)(quad * 32) << 16) + c0, v);
             T pv[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -266,9 +296,9 @@ __global__ void __launch_bounds__(128, 1) attention_prefill_kernel(const __grid_
     // ---------------- epilogue: O row -> out ----------------
     T *orow = (T *)a.out + ((int64_t)bh * a.Sq + q0 + row) * D;
 #pragma unroll 1
-    for (int c0 = 0; c0 < D; c0 += 16) {
+    for (int c0 = part * (D / AP_PARTS); c0 < (part + 1) * (D / AP_PARTS); c0 += 16) {
         uint32_t v[16];
-        if (ntiles > 0) tmem_ld_32x32b_x16(tmem_o + ((uint32_t)(warp * 32) << 16) + c0, v);
+        if (ntiles > 0) tmem_ld_32x32b_x16(tmem_o + ((uint32_t)(quad * 32) << 16) + c0, v);
         T ov[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) ov[j] = from_f<T>(ntiles > 0 ? __uint_as_float(v[j]) : 0.f);
@@ -295,9 +325,17 @@ static int launch_ap(const void *q, const void *k, const void *v, const ApArgs &
         ITB_FAIL("attention_prefill: cuTensorMapEncodeTiled failed");
     const int smem = 2 * AP_BQ * D * 2 + AP_BK * D * 2 + AP_BQ * AP_BK * 2 + AP_BK * AP_MPAD * 2 + 1024;
     auto kern = attention_prefill_kernel<T, D>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    ITB_CHECK(e == cudaSuccess, "attention_prefill: smem attribute: %s", cudaGetErrorString(e));
-    e = launch_k(kern, dim3((a.Sq + AP_BQ - 1) / AP_BQ, a.BH), dim3(128), (size_t)smem, st, mq, mk, mv, a);
+    static int attr_smem[64] = {0};  // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    cudaError_t e = cudaSuccess;
+    if (smem > attr_smem[dev]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        ITB_CHECK(e == cudaSuccess, "attention_prefill: smem attribute: %s", cudaGetErrorString(e));
+        attr_smem[dev] = smem;
+    }
+    e = launch_k(kern, dim3((a.Sq + AP_BQ - 1) / AP_BQ, a.BH), dim3(AP_THREADS), (size_t)smem, st, mq, mk, mv, a);
     ITB_CHECK(e == cudaSuccess, "attention_prefill: launch failed: %s", cudaGetErrorString(e));
     ITB_LAUNCH_CHECK("attention_prefill");
     return 0;

@@ -165,6 +165,13 @@ static int run_gemm(int dtype, const GemmArgs &g, cudaStream_t st) {
         if (r >= 0) return r;
         return launch_gemm_simt(dtype, g, st);
     }
+    // decode rows with enough 128-wide column tiles to fill the SMs without split-K (logits): tcgen05 swap-AB
+    if (g.m <= 64 && g.batch == 1 && !g.trans_a && !g.trans_b && (g.n + 127) / 128 >= tc_min_tiles_decode()) {
+        GemmArgs gt = g;
+        gt.no_splitk = 1;
+        r = launch_gemm_tc(dtype, gt, st);
+        if (r >= 0) return r;
+    }
     r = launch_gemm_skinny(dtype, g, st);
     if (r >= 0) return r;
     r = launch_gemm_tc(dtype, g, st);
@@ -198,6 +205,10 @@ extern "C" int it_b200_matmul_grouped(int dtype, const void *X, int n_groups, co
     auto st = (cudaStream_t)stream;
     GemmArgs g{X, W[0], nullptr, C[0], 1, m, N[0], k, (int64_t)m * k, 0, 0, 0, 0, 0, 0, ITB_MATMUL_B_CONST};
     const char *pin = std::getenv("ITB_GEMM_IMPL");
+    if (!(pin && pin[0]) || !strcmp(pin, "tc")) {
+        int r = launch_gemm_tc_grouped(dtype, g, n_groups, W, C, N, st);  // only when its tiles fill the machine (gate/up)
+        if (r >= 0) return r;
+    }
     if (!(pin && pin[0]) || !strcmp(pin, "skinny")) {
         int r = launch_gemm_skinny_grouped(dtype, g, n_groups, W, C, N, st);
         if (r >= 0) return r;

@@ -50,6 +50,9 @@ int launch_gemm_skinny(int dtype, const GemmArgs &g, cudaStream_t st);
 int launch_gemm_skinny_grouped(int dtype, const GemmArgs &g0, int ngroups, const void *const *Ws, void *const *Cs,
                                const int *Ns, cudaStream_t st);
 int launch_gemm_tc(int dtype, const GemmArgs &g, cudaStream_t st);
+int launch_gemm_tc_grouped(int dtype, const GemmArgs &g0, int ngroups, const void *const *Ws, void *const *Cs, const int *Ns,
+                           cudaStream_t st);
+int tc_min_tiles_decode();  // column tiles (128 wide) from which a decode GEMM runs on the tcgen05 kernel instead of gemm_skinny
 int launch_gemm_skinny_fp8w(int dtype, const GemmArgs &g0, int ngroups, const void *const *Wq, const float *const *scales,
                             void *const *Cs, const int *Ns, cudaStream_t st);
 

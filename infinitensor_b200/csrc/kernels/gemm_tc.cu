@@ -47,6 +47,31 @@ __device__ unsigned long long g_tc_trace[16];
 #define TC_MARK(i) do {} while (0)
 #endif
 
+// 16 consecutive values -> two 16-byte stores (registers only: an address-taken T[16] costs a stack frame and 26 registers,
+// which halves the CTAs per SM of this kernel)
+template <typename T> __device__ __forceinline__ uint32_t tc_pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t tc_pack2<__half>(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+template <> __device__ __forceinline__ uint32_t tc_pack2<__nv_bfloat16>(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+template <typename T> __device__ __forceinline__ void tc_store16(T *dst, const float (&f)[16]) {
+    uint4 lo, hi;
+    lo.x = tc_pack2<T>(f[0], f[1]);
+    lo.y = tc_pack2<T>(f[2], f[3]);
+    lo.z = tc_pack2<T>(f[4], f[5]);
+    lo.w = tc_pack2<T>(f[6], f[7]);
+    hi.x = tc_pack2<T>(f[8], f[9]);
+    hi.y = tc_pack2<T>(f[10], f[11]);
+    hi.z = tc_pack2<T>(f[12], f[13]);
+    hi.w = tc_pack2<T>(f[14], f[15]);
+    reinterpret_cast<uint4 *>(dst)[0] = lo;
+    reinterpret_cast<uint4 *>(dst)[1] = hi;
+}
+
 struct TcParams {
     int mpad;        // UMMA N: rows of X rounded up to 16 (16..256)
     int tmem_cols;   // power of two >= max(32, mpad)
@@ -61,8 +86,19 @@ struct TcParams {
     uint32_t idesc;
 };
 
+// up to 4 weight matrices sharing the activation operand X (q/k/v, gate/up) in ONE launch: the column-tile index selects the
+// group (its tensor map, output pointer and width); a plain MatMul is the 1-group case
+constexpr int TC_MAX_GROUPS = 4;
+struct TcGroups {
+    CUtensorMap mapW[TC_MAX_GROUPS];
+    void *C[TC_MAX_GROUPS];
+    int n[TC_MAX_GROUPS];
+    int tile_start[TC_MAX_GROUPS + 1];
+    int ngroups;
+};
+
 template <typename T>
-__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW,
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcGroups grp,
                                                              const __grid_constant__ CUtensorMap mapX, GemmArgs g,
                                                              TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -79,7 +115,11 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
 
     cg::cluster_group cluster = cg::this_cluster();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * TC_BN;
+    int gi = 0;
+    while (gi + 1 < grp.ngroups && (int)blockIdx.x >= grp.tile_start[gi + 1]) ++gi;
+    const CUtensorMap *mapWp = &grp.mapW[gi];
+    const int n0 = ((int)blockIdx.x - grp.tile_start[gi]) * TC_BN;
+    const int Ng = grp.n[gi];  // columns of this group's weight matrix / output
     const int bz = (int)blockIdx.z / p.m_chunks;                  // batch index
     const int m0 = ((int)blockIdx.z % p.m_chunks) * p.mpad;      // first row of this CTA's row chunk
     const int bx = p.a_batched ? bz : 0, bw = p.b_batched ? bz : 0;
@@ -100,7 +140,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     }
     if (warp == TC_EPI_WARPS + 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     if (warp == TC_EPI_WARPS && lane == 0) {
-        tma_prefetch_desc(&mapW);
+        tma_prefetch_desc(mapWp);
         tma_prefetch_desc(&mapX);
     }
     tc_fence_before();
@@ -123,10 +163,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             for (int it = 0; it < pre; ++it, k0 += TC_BK) {
                 mbar_expect_tx(&full[it], tx);
                 if (p.w_kmajor) {
-                    tma_load_3d(w_sm + it * TC_W_BYTES, &mapW, &full[it], k0, n0, bw, pol_w);
+                    tma_load_3d(w_sm + it * TC_W_BYTES, mapWp, &full[it], k0, n0, bw, pol_w);
                 } else {
-                    tma_load_3d(w_sm + it * TC_W_BYTES, &mapW, &full[it], n0, k0, bw, pol_w);
-                    tma_load_3d(w_sm + it * TC_W_BYTES + TC_W_BYTES / 2, &mapW, &full[it], n0 + 64, k0, bw, pol_w);
+                    tma_load_3d(w_sm + it * TC_W_BYTES, mapWp, &full[it], n0, k0, bw, pol_w);
+                    tma_load_3d(w_sm + it * TC_W_BYTES + TC_W_BYTES / 2, mapWp, &full[it], n0 + 64, k0, bw, pol_w);
                 }
             }
             TC_MARK(2);
@@ -141,10 +181,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                 mbar_expect_tx(&full[s], tx);
                 uint8_t *wdst = w_sm + s * TC_W_BYTES;
                 if (p.w_kmajor) {
-                    tma_load_3d(wdst, &mapW, &full[s], k0, n0, bw, pol_w);
+                    tma_load_3d(wdst, mapWp, &full[s], k0, n0, bw, pol_w);
                 } else {
-                    tma_load_3d(wdst, &mapW, &full[s], n0, k0, bw, pol_w);
-                    tma_load_3d(wdst + TC_W_BYTES / 2, &mapW, &full[s], n0 + 64, k0, bw, pol_w);
+                    tma_load_3d(wdst, mapWp, &full[s], n0, k0, bw, pol_w);
+                    tma_load_3d(wdst + TC_W_BYTES / 2, mapWp, &full[s], n0 + 64, k0, bw, pol_w);
                 }
                 tma_load_3d(x_sm + s * p.x_bytes, &mapX, &full[s], k0, m0, bx, pol_x);
                 if (++s == S) {
@@ -191,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
 
     // ===== epilogue: warps 0..3 own TMEM lanes [32w, 32w+32) = output columns n0 + 32w + lane =====
     const T *bias = g.bias ? (const T *)g.bias + (int64_t)bz * g.bias_sb : nullptr;
-    T *C = (T *)g.C + (int64_t)bz * g.m * g.n;
+    T *C = (T *)grp.C[gi] + (int64_t)bz * g.m * Ng;
     const bool tail = g.bn_scale != nullptr || g.residual != nullptr || g.post_relu;
     if (warp < TC_EPI_WARPS) {
         pdl_wait();
@@ -214,11 +254,11 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         const int nl = quad * 32 + lane;  // column inside the tile
         const int gn = n0 + nl;
         // element (m, gn) lives at C[c_off + m * c_ld] (plain row-major, or the conv scatter of GemmArgs::c_block)
-        const int64_t c_ld = g.c_nhwc ? 1 : g.c_block ? g.c_block : g.n;
+        const int64_t c_ld = g.c_nhwc ? 1 : g.c_block ? g.c_block : Ng;
         const int64_t c_off = g.c_nhwc ? (int64_t)gn * g.m
                               : g.c_block ? (int64_t)(gn / g.c_block) * g.c_block_stride + gn % g.c_block : gn;
         const int mode = (bias || (g.act & 0xff)) ? 2 : tail ? 1 : 0;  // (launch_tc_t refuses bias/act together with a tail)
-        const float bias_col = (bias && g.bias_sm == 0 && gn < g.n) ? to_f(bias[(int64_t)gn * g.bias_sn]) : 0.f;
+        const float bias_col = (bias && g.bias_sm == 0 && gn < Ng) ? to_f(bias[(int64_t)gn * g.bias_sn]) : 0.f;
         for (int c0 = c_begin; c0 < c_end; c0 += 16) {
             uint32_t v[16];
             if (my_kt > 0) {
@@ -230,18 +270,17 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             if (nsplit > 1) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) red[(c0 + j) * TC_BN + nl] = __uint_as_float(v[j]);
-            } else if (gn < g.n) {
+            } else if (gn < Ng) {
                 // three specialisations of the per-element tail, chosen by CTA-uniform flags, so the common cases do
                 // not carry the generic bias / activation code (that alone made the epilogue instruction-bound)
                 const int rows = min(16, g.m - (m0 + c0));  // valid rows of this 16-row group
                 T *cp = C + c_off + (int64_t)(m0 + c0) * c_ld;
                 if (mode == 0) {
                     if (g.c_nhwc && rows == 16) {  // 16 consecutive filters of one pixel: two 16-byte stores
-                        alignas(16) T tv[16];
+                        float fv[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) tv[j] = from_f<T>(__uint_as_float(v[j]));
-                        reinterpret_cast<uint4 *>(cp)[0] = reinterpret_cast<const uint4 *>(tv)[0];
-                        reinterpret_cast<uint4 *>(cp)[1] = reinterpret_cast<const uint4 *>(tv)[1];
+                        for (int j = 0; j < 16; ++j) fv[j] = __uint_as_float(v[j]);
+                        tc_store16<T>(cp, fv);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
@@ -250,7 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                 } else if (mode == 1) {
                     float resv[16];
                     if (g.residual) {  // all 16 residual loads in flight before the first (possibly aliasing) store
-                        const T *rp = (const T *)g.residual + (int64_t)bz * g.m * g.n + c_off + (int64_t)(m0 + c0) * c_ld;
+                        const T *rp = (const T *)g.residual + (int64_t)bz * g.m * Ng + c_off + (int64_t)(m0 + c0) * c_ld;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) resv[j] = j < rows ? to_f(rp[(int64_t)j * c_ld]) : 0.f;
                     }
@@ -267,11 +306,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                         resv[j] = f;
                     }
                     if (g.c_nhwc && rows == 16) {
-                        alignas(16) T tv[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) tv[j] = from_f<T>(resv[j]);
-                        reinterpret_cast<uint4 *>(cp)[0] = reinterpret_cast<const uint4 *>(tv)[0];
-                        reinterpret_cast<uint4 *>(cp)[1] = reinterpret_cast<const uint4 *>(tv)[1];
+                        tc_store16<T>(cp, resv);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
@@ -281,40 +316,35 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                     // bias / activation: the bias of a Gemm is a row vector (bias_sm == 0) -> ONE value per thread (its column), and
                     // the activation switch is taken once per 16 rows, not per element (the per-element form cost 8.7 us of a 23 us
                     // GPT-2 projection: ~115 instructions per stored value)
-                    float bv[16];
                     const bool rb = (g.act & ITB_ACT_ROUND_BEFORE_BIAS) != 0;
-                    if (bias && g.bias_sm == 0) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) bv[j] = bias_col;
-                    } else if (bias) {
+                    if (bias) {
+                        const bool row_const = g.bias_sm == 0;
                         const T *bp = bias + (int64_t)(m0 + c0) * g.bias_sm + (int64_t)gn * g.bias_sn;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) bv[j] = j < rows ? to_f(bp[(int64_t)j * g.bias_sm]) : 0.f;
-                    }
-                    float fo[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float f = __uint_as_float(v[j]);
-                        if (bias) f = (rb ? round_t<T>(f) : f) + bv[j];
-                        fo[j] = f;
+                        for (int j = 0; j < 16; ++j) {
+                            float f = __uint_as_float(v[j]);
+                            if (rb) f = round_t<T>(f);
+                            f += row_const ? bias_col : (j < rows ? to_f(bp[(int64_t)j * g.bias_sm]) : 0.f);
+                            v[j] = __float_as_uint(f);
+                        }
                     }
                     switch (g.act & 0xff) {
                     case 1:
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) fo[j] = fo[j] > 0.f ? fo[j] : 0.f;
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) > 0.f ? __uint_as_float(v[j]) : 0.f);
                         break;
                     case 2:
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) fo[j] = 1.f / (1.f + expf(-fo[j]));
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(1.f / (1.f + expf(-__uint_as_float(v[j]))));
                         break;
                     case 3:
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) fo[j] = tanhf(fo[j]);
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(tanhf(__uint_as_float(v[j])));
                         break;
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (j < rows) cp[(int64_t)j * c_ld] = from_f<T>(fo[j]);
+                        if (j < rows) cp[(int64_t)j * c_ld] = from_f<T>(__uint_as_float(v[j]));
                 }
             }
         }
@@ -328,7 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             for (int r = 0; r < nsplit; ++r) peers[r] = (const float *)cluster.map_shared_rank(red, r);
             for (int idx = threadIdx.x; idx < p.mpad * TC_BN; idx += TC_EPI_WARPS * 32) {
                 const int m = m0 + idx / TC_BN, nl = idx % TC_BN, gn = n0 + nl;
-                if (m >= g.m || gn >= g.n) continue;
+                if (m >= g.m || gn >= Ng) continue;
                 float f = 0.f;
                 for (int r = 0; r < nsplit; ++r) f += peers[r][idx];
                 if (bias) {
@@ -336,7 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                     f += to_f(bias[m * g.bias_sm + gn * g.bias_sn]);
                 }
                 const int64_t off = g.c_block ? (int64_t)(gn / g.c_block) * g.c_block_stride + (int64_t)m * g.c_block + gn % g.c_block
-                                              : (int64_t)m * g.n + gn;
+                                              : (int64_t)m * Ng + gn;
                 C[off] = from_f<T>(gemm_act(g.act, f));
             }
         }
@@ -351,8 +381,19 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     }
 }
 
+// decode GEMMs (M <= 64) take this kernel once its 128-column tiles alone occupy every SM (measured, tools/gemm_bench.py: gate/up
+// 28.0 vs 34.2 us, logits 39.7 vs 41.0 us against the mma.sync kernel; with fewer tiles that kernel's cluster split-K wins)
+int tc_min_tiles_decode() {
+    static const int v = [] {
+        const char *e = std::getenv("ITB_TC_DECODE_MIN_TILES");
+        return e && e[0] ? std::atoi(e) : kNumSMs;
+    }();
+    return v;
+}
+
 template <typename T>
-static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
+static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16, int ngroups = 1, const void *const *Ws = nullptr,
+                       void *const *Cs = nullptr, const int *Ns = nullptr) {
     TcParams p{};
     p.mpad = g.m > 256 ? 256 : ((g.m + 15) / 16) * 16;
     p.m_chunks = (g.m + p.mpad - 1) / p.mpad;
@@ -361,7 +402,16 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
     p.tmem_cols = 32;
     while (p.tmem_cols < p.mpad) p.tmem_cols <<= 1;
     p.x_bytes = p.mpad * 128;
-    const int tiles_n = (g.n + TC_BN - 1) / TC_BN;
+    TcGroups grp{};
+    grp.ngroups = ngroups;
+    int tiles_n = 0;
+    for (int i = 0; i < ngroups; ++i) {
+        grp.C[i] = Cs ? Cs[i] : g.C;
+        grp.n[i] = Ns ? Ns[i] : g.n;
+        grp.tile_start[i] = tiles_n;
+        tiles_n += (grp.n[i] + TC_BN - 1) / TC_BN;
+    }
+    for (int i = ngroups; i <= TC_MAX_GROUPS; ++i) grp.tile_start[i] = tiles_n;
     p.ktiles = (g.k + TC_BK - 1) / TC_BK;
     // split-K only where the partial tile is small (decode regime); clusters of <= 8 CTAs
     int splitk = 1;
@@ -392,14 +442,18 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
                              /*B = X, K-major*/ 0, 128, p.mpad);
     const int smem = p.stages * stage_bytes + p.red_bytes + (2 * p.stages + 1) * 8 + 32 + 4 * p.mpad * 4 + 1024;
 
-    CUtensorMap mapW, mapX;
-    const bool w_ok = p.w_kmajor
-                          ? make_tma_3d_b16(&mapW, g.B, p.b_batched ? (uint64_t)g.batch : 1, (uint64_t)g.n, (uint64_t)g.k,
-                                            (uint64_t)g.k, (uint64_t)g.stride_b, TC_BN, TC_BK)
-                          : make_tma_3d_b16(&mapW, g.B, p.b_batched ? (uint64_t)g.batch : 1, (uint64_t)g.k, (uint64_t)g.n,
-                                            (uint64_t)g.n, (uint64_t)g.stride_b, TC_BK, 64);
-    if (!w_ok)
-        ITB_FAIL("matmul(tcgen05): cuTensorMapEncodeTiled(W) failed");
+    CUtensorMap mapX;
+    for (int i = 0; i < ngroups; ++i) {
+        const void *Wi = Ws ? Ws[i] : g.B;
+        const uint64_t ni = (uint64_t)grp.n[i];
+        const bool w_ok = p.w_kmajor
+                              ? make_tma_3d_b16(&grp.mapW[i], Wi, p.b_batched ? (uint64_t)g.batch : 1, ni, (uint64_t)g.k, (uint64_t)g.k,
+                                                (uint64_t)g.stride_b, TC_BN, TC_BK)
+                              : make_tma_3d_b16(&grp.mapW[i], Wi, p.b_batched ? (uint64_t)g.batch : 1, (uint64_t)g.k, ni, ni,
+                                                (uint64_t)g.stride_b, TC_BK, 64);
+        if (!w_ok) ITB_FAIL("matmul(tcgen05): cuTensorMapEncodeTiled(W) failed");
+    }
+    for (int i = ngroups; i < TC_MAX_GROUPS; ++i) grp.mapW[i] = grp.mapW[0];
     if (!make_tma_3d_b16(&mapX, g.A, p.a_batched ? (uint64_t)g.batch : 1, (uint64_t)g.m, (uint64_t)g.k, (uint64_t)g.k,
                          (uint64_t)g.stride_a, (uint32_t)p.mpad, TC_BK))
         ITB_FAIL("matmul(tcgen05): cuTensorMapEncodeTiled(X) failed");
@@ -430,7 +484,7 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapW, mapX, g, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, grp, mapX, g, p);
     ITB_CHECK(e == cudaSuccess, "matmul(tcgen05): launch failed: %s", cudaGetErrorString(e));
     itb::count_launch();
 #ifdef ITB_TC_TRACE
@@ -465,6 +519,32 @@ int launch_gemm_tc(int dtype, const GemmArgs &g, cudaStream_t st) {
     if (g.c_nhwc && (g.batch != 1 || g.m % 8 != 0 || g.bias || (g.act & 0xff) || !g.no_splitk)) return -1;
     if (dtype == ITB_BF16) return launch_tc_t<__nv_bfloat16>(g, st, true);
     return launch_tc_t<__half>(g, st, false);
+}
+
+// 2..4 weight matrices [K, N_i] sharing X (decode rows): one launch when 128-wide tiles alone fill the machine (no split-K).
+// -1 = not taken (the mma.sync kernel's cluster split-K is the better shape then)
+int launch_gemm_tc_grouped(int dtype, const GemmArgs &g0, int ngroups, const void *const *Ws, void *const *Cs, const int *Ns,
+                           cudaStream_t st) {
+    if (dtype != ITB_BF16 && dtype != ITB_F16) return -1;
+    if (ngroups < 1 || ngroups > TC_MAX_GROUPS) return -1;
+    if (g0.batch != 1 || g0.trans_a || g0.trans_b || g0.m < 1 || g0.m > 64 || g0.bias || (g0.act & 0xff) || g0.residual || g0.bn_scale ||
+        g0.post_relu || g0.c_block || g0.c_nhwc)
+        return -1;
+    if (g0.k % 8 != 0 || g0.k < 64 || !aligned16(g0.A)) return -1;
+    int tiles = 0;
+    for (int i = 0; i < ngroups; ++i) {
+        if (Ns[i] % 8 != 0 || Ns[i] < 64 || !aligned16(Ws[i]) || !aligned16(Cs[i])) return -1;
+        tiles += (Ns[i] + TC_BN - 1) / TC_BN;
+    }
+    if (tiles < tc_min_tiles_decode()) return -1;
+    GemmArgs g = g0;
+    g.B = Ws[0];
+    g.C = Cs[0];
+    g.n = Ns[0];
+    g.act |= ITB_MATMUL_B_CONST;
+    g.no_splitk = 1;
+    if (dtype == ITB_BF16) return launch_tc_t<__nv_bfloat16>(g, st, true, ngroups, Ws, Cs, Ns);
+    return launch_tc_t<__half>(g, st, false, ngroups, Ws, Cs, Ns);
 }
 
 }  // namespace itb

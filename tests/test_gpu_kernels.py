@@ -316,6 +316,21 @@ def test_matmul_grouped_parity(K, gemm_impl, dt):
             close(o, oracle.matmul(x, w, None, False, False, dt), 2 * EPS[dt], gemm_tol(dt, k, np.abs(x).max(), np.abs(w).max()))
 
 
+@pytest.mark.parametrize("gemm_impl", ["", "tc"], indirect=True)
+@pytest.mark.parametrize("dt", [BF16, F16])
+def test_matmul_grouped_tcgen05_parity(K, gemm_impl, dt):
+    """Grouped decode GEMMs whose 128-wide column tiles fill the machine (gate/up at the Llama-7B width: 2 x 86 tiles; ragged
+    widths; 3 groups) run as ONE tcgen05 launch (tile index -> group); production dispatch and the pinned kernel agree with the oracle."""
+    for m, k, ns in [(16, 4096, [11008, 11008]), (9, 320, [9600, 9608]), (33, 512, [6400, 6400, 6464])]:
+        x = rnd((m, k), 340, dt, 0.5)
+        ws = [rnd((k, n), 341 + i, dt, 0.05) for i, n in enumerate(ns)]
+        outs = K.matmul_grouped(x, ws, dt)
+        for w, o in zip(ws, outs):
+            close(o, oracle.matmul(x, w, None, False, False, dt), 2 * EPS[dt], gemm_tol(dt, k, np.abs(x).max(), np.abs(w).max()))
+    # logits-sized plain MatMul takes the same kernel by the dispatch rule (250 tiles)
+    _gemm_case(K, 16, 1024, 32000, dt)
+
+
 @pytest.mark.parametrize("gemm_impl", ["tc"], indirect=True)
 @pytest.mark.parametrize("dt", [BF16, F16])
 @pytest.mark.parametrize("m,k,n", TC_SHAPES)
