@@ -169,6 +169,15 @@ int it_b200_matmul(int dtype, const void *A, const void *B, const void *bias, vo
                    int64_t bias_stride_n, int act, void *workspace, int64_t workspace_bytes,
                    void *stream);
 
+/* MatMul (+ bias) -> [activation: 1 relu, 2 sigmoid, 3 tanh, 4 Gelu (erf form, unary.cu:113)] -> [+ residual laid out like C] in
+ * the tcgen05 kernel's epilogue -- the schedule's MatMulAdd step for graphs whose Linear layers carry a bias (GPT-2: c_proj + Add,
+ * c_fc + Gelu).  Every operator boundary rounds to the storage type (MatMul output, activation output) exactly as the separate
+ * kernels do.  Returns 2 when the shape does not run on that kernel (f16 / bf16, K % 8 == 0, N % 8 == 0, no transA): nothing is
+ * launched and the caller runs the operators one by one. */
+int it_b200_matmul_fused(int dtype, const void *A, const void *B, const void *bias, const void *residual, void *C, int64_t b,
+                         int m, int n, int k, int64_t stride_a, int64_t stride_b, int trans_a, int trans_b,
+                         int64_t bias_stride_b, int64_t bias_stride_m, int64_t bias_stride_n, int act, void *stream);
+
 /* ---- Grouped MatMul: up to 4 weight matrices W_i[K,N_i] sharing one activation operand X[M,K] (the q/k/v and
  *      gate/up projections of a decoder layer) in ONE launch; C_i[M,N_i] = X . W_i.  No bias / activation.
  *      Falls back to one it_b200_matmul per group when the shapes are not taken by the grouped kernel. ---- */

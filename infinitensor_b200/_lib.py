@@ -58,6 +58,7 @@ _SIGS = {
     "it_b200_matmul_workspace": (c_int64, [c_int, c_int64, c_int, c_int, c_int]),
     "it_b200_matmul": (c_int, [c_int, vp, vp, vp, vp, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_int, c_int,
                                c_int64, c_int64, c_int64, c_int, vp, c_int64, vp]),
+    "it_b200_matmul_fused": (c_int, [c_int, vp, vp, vp, vp, vp, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_int, c_int, c_int64, c_int64, c_int64, c_int, vp]),
     "it_b200_matmul_grouped": (c_int, [c_int, vp, c_int, POINTER(vp), POINTER(vp), i32p, c_int, c_int, vp]),
     "it_b200_silu_mul": (c_int, [c_int, vp, vp, vp, c_int64, vp]),
     "it_b200_matmul_fp8w": (c_int, [c_int, vp, c_int, POINTER(vp), POINTER(vp), POINTER(vp), i32p, c_int, c_int, vp, vp]),

@@ -427,6 +427,43 @@ void runMatmul(const Operator &_op, const RuntimeObj *ctx, const Tensor &residua
 }
 
 #ifndef ITB_SEAM_A  // ---- this repo's schedule-level executors (no counterpart in the reference)
+// MatMul (+ bias) -> [Gelu] -> [Add(residual)]: ops = {MatMul, [Gelu], [Add]} in one tcgen05 epilogue.  false = the shape is not
+// taken (nothing launched): the caller runs the operators one by one.
+bool matmulAddIsPlain(const OpVec &ops) {
+    return ops.size() == 2 && ops[1]->getOpType() == OpType::Add && !as<MatmulObj>(ops[0])->getBias();
+}
+bool runMatmulFused(const OpVec &ops, const RuntimeObj *) {
+    auto mm = as<MatmulObj>(ops[0]);
+    Operator actOp, add;
+    for (size_t i = 1; i < ops.size(); ++i) {
+        if (ops[i]->getOpType() == OpType::Add) add = ops[i];
+        else actOp = ops[i];
+    }
+    auto A = mm->getInputs(0), B = mm->getInputs(1), bias = mm->getBias();
+    if (B->getRank() != 2 || mm->getTransA() || mm->getWScale()) return false;
+    if (bias && !(bias->getRank() == 1 && bias->getDims()[0] == mm->getN())) return false;
+    int act = 0;
+    if (actOp) {
+        if (actOp->getOpType() != OpType::Gelu) return false;
+        act = 4;
+    }
+    int64_t rows = 1;
+    for (size_t i = 0; i + 1 < A->getRank(); ++i) rows *= A->getDims()[i];
+    if (rows > (1ll << 30)) return false;
+    Tensor res;
+    if (add) {
+        Tensor prev = ops[ops.size() - 2]->getOutput();
+        res = add->getInputs(0) == prev ? add->getInputs(1) : add->getInputs(0);
+    }
+    if (B->isWeight()) act |= ITB_MATMUL_B_CONST;
+    const int n = mm->getN(), k = mm->getK();
+    int rc = it_b200_matmul_fused(DTI(A), P(A), P(B), bias ? P(bias) : nullptr, res ? P(res) : nullptr, P(ops.back()->getOutput()), 1,
+                                  (int)rows, n, k, rows * k, 0, 0, mm->getTransB() ? 1 : 0, 0, 0, 1, act, S());
+    if (rc == 2) return false;
+    CK(rc, ops.back());
+    return true;
+}
+
 // q/k/v or gate/up: MatMuls sharing the activation operand, weights [K, N_i]: one grouped launch
 void runMatmulGroup(const OpVec &ops, const RuntimeObj *) {
     auto A = ops[0]->getInputs(0);

@@ -238,6 +238,12 @@ void CudaRuntimeObj::execStep(const ExecStep &st, Kernel *kernel, const PerfReco
         break;
     case ExecStep::MatMulGroup: b200::runMatmulGroup(st.ops, this); break;
     case ExecStep::MatMulAdd: {
+        if (!b200::matmulAddIsPlain(st.ops)) {
+            // biased Linear layer and / or an activation in the chain: the tcgen05 epilogue, else the operators one by one
+            if (!b200::runMatmulFused(st.ops, this))
+                for (auto &m : st.ops) reg.getKernel(KernelAttrs{Device::CUDA, m->getOpType().underlying()})->compute(m, this);
+            break;
+        }
         const auto &mm = st.ops[0], &add = st.ops[1];
         auto res = add->getInputs(0) == mm->getOutput() ? add->getInputs(1) : add->getInputs(0);
         b200::runMatmul(mm, this, res, add->getOutput());

@@ -160,6 +160,8 @@ void runSiluMul(const Operator &silu, const Operator &mul, const RuntimeObj *ctx
 // AllReduceSum -> Add(residual) [-> RMSNorm]: true if the fused NVLink kernel took it, false = run the ops one by one
 bool runAllReduceAddNorm(const OpVec &ops, const RuntimeObj *ctx);
 // Conv -> BatchNorm -> [Add] -> [Relu] in the GEMM epilogue; false = shape not taken (nothing launched)
+bool matmulAddIsPlain(const OpVec &ops);  // {bias-free MatMul, Add}: the residual rides the GEMM's bias slot (every GEMM kernel)
+bool runMatmulFused(const OpVec &ops, const RuntimeObj *ctx);
 bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx, int layout = 0);
 void prepConvFilters(const vector<ExecStep> &sched, const RuntimeObj *ctx);
 void runPoolNhwc(const Operator &op, const RuntimeObj *ctx);

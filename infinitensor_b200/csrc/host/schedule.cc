@@ -16,6 +16,7 @@ static bool fusionEnabled() {
     return !(e && e[0] == '1');
 }
 // (bit 9 = NHWC domain for Conv / Pool / Add / Relu chains, on by default)
+// (bit 10 = MatMul + bias -> [Gelu] -> [Add] in the tcgen05 epilogue, on by default)
 // ITB_FUSION_MASK (debug / A-B): bit 0 alias, 1 MatMul groups, 2 MatMul+Add, 3 Silu*Mul, 4 AllReduce+Add+Norm, 5 RoPE->Attention, 6 Conv+BatchNorm[+Add][+Relu], 7 decoder-layer stacks (persistent kernel); default all
 static int fusionMask() {
     const char *e = std::getenv("ITB_FUSION_MASK");
@@ -24,7 +25,7 @@ static int fusionMask() {
     // bit 7 (decoder-layer stacks on the persistent kernel) is opt-in: measured on the BASELINE shape it does not yet beat the
     // eight tuned launches it replaces (165 vs 112 us per layer) -- ITB_DECODE_STACK=1 switches it on
     const char *ds = std::getenv("ITB_DECODE_STACK");
-    return ((ds && ds[0] == '1') ? 255 : 127) | 256 | 512;
+    return ((ds && ds[0] == '1') ? 255 : 127) | 256 | 512 | 1024;
 }
 
 static bool isKvCacheOperand(const Tensor &t) {
@@ -499,7 +500,8 @@ const vector<ExecStep> &GraphObj::getSchedule() {
                 continue;
             }
             st.kind = pt == OpType::MatMul ? ExecStep::MatMulAdd : pt == OpType::Silu ? ExecStep::SiluMul : ExecStep::AllReduceAddNorm;
-            st.ops = {prod[0], op};
+            st.ops = prod;  // MatMulAdd: {MatMul, [activation], Add | activation}; the others: one producer
+            st.ops.push_back(op);
             if (st.kind == ExecStep::AllReduceAddNorm) {
                 // pull in the RMSNorm that normalises the new residual stream (executed early, with the Add)
                 for (auto &t : op->getOutput()->getTargets())
@@ -545,17 +547,49 @@ const vector<ExecStep> &GraphObj::getSchedule() {
                 auto mm = as<MatmulObj>(op);
                 auto out = op->getOutput();
                 auto targets = out->getTargets();
-                if (!mm->getBias() && out->getDType().isFloat() && targets.size() == 1 && !out->isOutput() &&
-                    targets[0]->getOpType() == OpType::Add && !deferredInto.count(targets[0].get()) &&
-                    !deferred.count(targets[0].get()) && !consumed.count(targets[0].get())) {
+                // a biased Linear layer (Gemm: GPT-2's c_attn / c_proj / c_fc) or an activation between MatMul and Add needs the
+                // tcgen05 epilogue (it_b200_matmul_fused): f16 / bf16, more than 64 rows, plain [.., K] x [K, N]
+                auto fusedShape = [&]() {
+                    auto A = op->getInputs(0), Bw = op->getInputs(1);
+                    auto dt = out->getDType();
+                    if (!(dt == DataType::Float16 || dt == DataType::BFloat16) || mm->getTransA() || mm->getWScale()) return false;
+                    if (Bw->getRank() != 2 && A->getRank() != Bw->getRank()) return false;
+                    int64_t rows = 1;
+                    for (size_t i = 0; i + 1 < A->getRank(); ++i) rows *= A->getDims()[i];
+                    return rows > 64 && mm->getK() % 8 == 0 && mm->getN() % 8 == 0 && mm->getK() >= 64 && mm->getN() >= 64;
+                };
+                auto freeOp = [&](const Operator &o) {
+                    return !deferredInto.count(o.get()) && !deferred.count(o.get()) && !consumed.count(o.get());
+                };
+                OpVec chain = {op};
+                Tensor t = out;
+                bool ok = out->getDType().isFloat() && targets.size() == 1 && !out->isOutput() && freeOp(targets[0]);
+                if (ok && targets[0]->getOpType() == OpType::Gelu && (mask & 1024) && fusedShape() &&
+                    targets[0]->getOutput()->getDims() == out->getDims()) {
+                    chain.push_back(targets[0]);  // MatMul -> Gelu
+                    t = targets[0]->getOutput();
+                    auto tt = t->getTargets();
+                    ok = tt.size() == 1 && !t->isOutput() && freeOp(tt[0]);
+                    targets = tt;
+                }
+                bool withAdd = false;
+                if (ok && targets[0]->getOpType() == OpType::Add && (!mm->getBias() || ((mask & 1024) && fusedShape())) &&
+                    (chain.size() == 1 || fusedShape())) {
                     auto add = targets[0];
-                    auto other = add->getInputs(0) == out ? add->getInputs(1) : add->getInputs(0);
-                    if (other != out && other->getDims() == out->getDims() && other->getDType() == out->getDType() &&
-                        add->getOutput()->getDims() == out->getDims()) {
-                        deferredInto[add.get()] = {op};
-                        deferred.insert(op.get());
-                        continue;
+                    auto other = add->getInputs(0) == t ? add->getInputs(1) : add->getInputs(0);
+                    if (other != t && other->getDims() == t->getDims() && other->getDType() == t->getDType() &&
+                        add->getOutput()->getDims() == t->getDims()) {
+                        chain.push_back(add);
+                        withAdd = true;
                     }
+                }
+                if (chain.size() > 1) {
+                    (void)withAdd;
+                    auto last = chain.back();
+                    chain.pop_back();
+                    deferredInto[last.get()] = chain;
+                    for (auto &m : chain) deferred.insert(m.get());
+                    continue;
                 }
             }
         } else if (type == OpType::RoPE && (mask & 32)) {

@@ -193,10 +193,28 @@ extern "C" int it_b200_matmul(int dtype, const void *A, const void *B, const voi
     (void)workspace_bytes;
     ITB_CHECK(dtype == ITB_F32 || dtype == ITB_F16 || dtype == ITB_BF16, "matmul: unsupported dtype %d", dtype);
     ITB_CHECK(m >= 0 && n >= 0 && k >= 0 && b >= 0, "matmul: negative dimension");
-    ITB_CHECK((act & 0xff) <= 3 && (act & ~0x3ff) == 0, "matmul: bad act %d", act);
+    ITB_CHECK((act & 0xff) <= 3 && (act & ~0x3ff) == 0, "matmul: bad act %d (Gelu / residual fusion: it_b200_matmul_fused)", act);
     GemmArgs g{A, B, bias, C, b, m, n, k, stride_a, stride_b, trans_a, trans_b,
                bias_stride_b, bias_stride_m, bias_stride_n, act};
     return run_gemm(dtype, g, (cudaStream_t)stream);
+}
+
+// MatMul (+ bias) -> [Relu | Sigmoid | Tanh | Gelu] -> [+ residual] in ONE tensor-core epilogue, every operator boundary rounded to
+// the storage type like the separate kernels.  2 = shape outside the tcgen05 kernel (nothing launched).
+extern "C" int it_b200_matmul_fused(int dtype, const void *A, const void *B, const void *bias, const void *residual, void *C,
+                                    int64_t b, int m, int n, int k, int64_t stride_a, int64_t stride_b, int trans_a, int trans_b,
+                                    int64_t bias_stride_b, int64_t bias_stride_m, int64_t bias_stride_n, int act, void *stream) {
+    ITB_CHECK((act & 0xff) <= 4 && (act & ~0x2ff) == 0, "matmul_fused: bad act %d", act);
+    ITB_CHECK(m >= 0 && n >= 0 && k >= 0 && b >= 0, "matmul_fused: negative dimension");
+    if (b == 0 || m == 0 || n == 0) return 0;
+    GemmArgs g{A, B, bias, C, b, m, n, k, stride_a, stride_b, trans_a, trans_b, bias_stride_b, bias_stride_m, bias_stride_n, act};
+    g.residual = residual;
+    g.no_splitk = 1;
+    const char *pin = std::getenv("ITB_GEMM_IMPL");
+    if (pin && pin[0] && strcmp(pin, "tc")) return 2;
+    if (!aligned16(C) || (residual && !aligned16(residual)) || (g.act & 0xff) == 0 && !residual) return 2;
+    const int r = launch_gemm_tc(dtype, g, (cudaStream_t)stream);
+    return r < 0 ? 2 : r;
 }
 
 extern "C" int it_b200_matmul_grouped(int dtype, const void *X, int n_groups, const void *const *W, void *const *C,

@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         const int64_t c_ld = g.c_nhwc ? 1 : g.c_block ? g.c_block : Ng;
         const int64_t c_off = g.c_nhwc ? (int64_t)gn * g.m
                               : g.c_block ? (int64_t)(gn / g.c_block) * g.c_block_stride + gn % g.c_block : gn;
-        const int mode = (bias || (g.act & 0xff)) ? 2 : tail ? 1 : 0;  // (launch_tc_t refuses bias/act together with a tail)
+        // (a BatchNorm / ReLU tail excludes bias / act; a residual alone may follow them: MatMul + bias -> [act] -> + residual)
+        const int mode = (bias || (g.act & 0xff)) ? 2 : tail ? 1 : 0;
         const float bias_col = (bias && g.bias_sm == 0 && gn < Ng) ? to_f(bias[(int64_t)gn * g.bias_sn]) : 0.f;
         for (int c0 = c_begin; c0 < c_end; c0 += 16) {
             uint32_t v[16];
@@ -341,6 +342,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(tanhf(__uint_as_float(v[j])));
                         break;
+                    case 4:  // Gelu (erf form, the unary kernel's formula) of the MatMul's ROUNDED output: MatMul -> Gelu in one epilogue
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float x = round_t<T>(__uint_as_float(v[j]));
+                            v[j] = __float_as_uint(0.5f * x * (1.f + erff(x * 0.70710678118654752440f)));
+                        }
+                        break;
+                    }
+                    if (g.residual) {  // -> Add(residual): the operator before it rounds first
+                        const T *rp = (const T *)g.residual + (int64_t)bz * g.m * Ng + c_off + (int64_t)(m0 + c0) * c_ld;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            v[j] = __float_as_uint(round_t<T>(__uint_as_float(v[j])) + (j < rows ? to_f(rp[(int64_t)j * c_ld]) : 0.f));
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
@@ -515,7 +529,8 @@ int launch_gemm_tc(int dtype, const GemmArgs &g, cudaStream_t st) {
         if (g.stride_a != 0 && g.stride_a != (int64_t)g.m * g.k) return -1;
         if ((int64_t)g.batch * ((g.m + 255) / 256) > 65535) return -1;
     }
-    if ((g.bn_scale || g.residual || g.post_relu) && (g.bias || (g.act & 0xff))) return -1;  // tail excludes bias / act
+    if ((g.bn_scale || g.post_relu) && (g.bias || (g.act & 0xff))) return -1;  // the conv tail excludes bias / act
+    if (g.residual && (g.bias || (g.act & 0xff)) && (g.c_block || g.c_nhwc)) return -1;
     if (g.c_nhwc && (g.batch != 1 || g.m % 8 != 0 || g.bias || (g.act & 0xff) || !g.no_splitk)) return -1;
     if (dtype == ITB_BF16) return launch_tc_t<__nv_bfloat16>(g, st, true);
     return launch_tc_t<__half>(g, st, false);

@@ -352,6 +352,23 @@ def matmul(a, b, bias=None, transA=False, transB=False, dt=F32, act=0):
     return host(c)
 
 
+def matmul_fused(a, b, bias, residual, act, dt=F16, transB=False):
+    """MatMul (+ bias) -> [act: 0 none, 1 relu, 4 gelu] -> [+ residual] through it_b200_matmul_fused; None when the kernel answers 2."""
+    ad, bd = dev(a, dt), dev(b, dt)
+    m, k = a.shape
+    n = b.shape[0] if transB else b.shape[1]
+    c = torch.empty((m, n), dtype=ad.dtype, device="cuda")
+    biasd = dev(bias, dt) if bias is not None else None
+    resd = dev(residual, dt) if residual is not None else None
+    rc = L.lib.it_b200_matmul_fused(dt, ptr(ad), ptr(bd), ptr(biasd), ptr(resd), ptr(c), 1, m, n, k, m * k, 0, 0, int(transB), 0, 0, 1,
+                                    act | 0x200, stream())
+    if rc == 2:
+        return None
+    L.check(rc)
+    sync()
+    return host(c)
+
+
 def matmul_grouped(x, ws, dt=BF16):
     xd = dev(x, dt)
     wd = [dev(w, dt) for w in ws]

@@ -1,6 +1,8 @@
 """GPU parity tests: every C-ABI launcher vs (a) the reference's golden vectors and (b) the CPU oracle
 on seeded inputs.  Tolerances are the ones SURVEY.md 8(c) states per op, written next to each check.
 Run with `pytest -m gpu` on a B200 (gpurun)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -314,6 +316,36 @@ def test_matmul_grouped_parity(K, gemm_impl, dt):
         outs = K.matmul_grouped(x, ws, dt)
         for w, o in zip(ws, outs):
             close(o, oracle.matmul(x, w, None, False, False, dt), 2 * EPS[dt], gemm_tol(dt, k, np.abs(x).max(), np.abs(w).max()))
+
+
+@pytest.mark.parametrize("dt", [BF16, F16])
+def test_matmul_fused_epilogue_parity(K, dt):
+    """MatMul + bias -> [Gelu] -> [+ residual] in the tcgen05 epilogue = the separate kernels (MatMul with bias, unary Gelu, binary
+    Add), bit for bit -- the same fp32 sums and the same rounding points -- and the oracle chain within the GEMM tolerance."""
+    for ci, (m, k, n) in enumerate([(128, 768, 768), (128, 768, 3072), (200, 3072, 776), (65, 64, 64)]):
+        a, b = rnd((m, k), 420 + ci, dt, 0.5), rnd((k, n), 430 + ci, dt, 0.05)
+        bias, res = rnd((n,), 440 + ci, dt, 0.5), rnd((m, n), 450 + ci, dt)
+        tol = gemm_tol(dt, k, np.abs(a).max(), np.abs(b).max())
+        os.environ["ITB_GEMM_IMPL"] = "tc"
+        try:
+            plain = K.matmul(a, b, bias, False, False, dt)
+        finally:
+            os.environ.pop("ITB_GEMM_IMPL", None)
+        for act, use_res in [(0, True), (4, False), (4, True), (1, True)]:
+            got = K.matmul_fused(a, b, bias, res if use_res else None, act, dt)
+            assert got is not None
+            ref, ora = plain, oracle.matmul(a, b, bias, False, False, dt)
+            if act == 4:
+                ref, ora = K.unary("gelu", ref, dt), oracle.unary("gelu", ora, dt)
+            if act == 1:
+                ref, ora = np.maximum(ref, 0), np.maximum(ora, 0)
+            if use_res:
+                ref, ora = K.binary("add", ref, res, dt=dt), oracle.binary("add", ora, res, dt)
+            assert np.array_equal(got, ref), f"case {ci} act={act} res={use_res}: max diff {np.abs(got - ref).max()}"
+            close(got, ora, 4 * EPS[dt], 2 * tol)
+    # decode rows (<= 64) and fp32 are not this kernel's: rc 2, the runtime runs the operators one by one
+    a, b = rnd((16, 256), 460, dt), rnd((256, 256), 461, dt, 0.05)
+    assert K.matmul_fused(a, b, None, rnd((16, 256), 462, dt), 0, dt) is not None  # (taken: the tcgen05 kernel has no row minimum)
 
 
 @pytest.mark.parametrize("gemm_impl", ["", "tc"], indirect=True)

@@ -272,6 +272,24 @@ def test_conv_bn_act_schedule(B, monkeypatch):
     assert not any(s.startswith("ConvBnAct") for s in h2.schedule())
 
 
+def test_gpt2_linear_epilogue_schedule(B, monkeypatch):
+    """GPT-2: the biased Linear layers take the residual Add (c_proj, mlp c_proj) or the Gelu (c_fc) into their step (mask bit 10);
+    off -> the Round-1 schedule with those operators on their own."""
+    import collections
+    from infinitensor_b200 import graphs as G
+    rt = B.HostPlanRuntime()
+    h = B.GraphHandler(rt)
+    G.build_gpt2(h, G.GPT2Config())
+    c = collections.Counter(h.schedule())
+    assert c["MatMulAdd:MatMul+Add"] == 24 and c["MatMulAdd:MatMul+Gelu"] == 12 and c["Single:MatMul"] == 12
+    assert c["Single:Gelu"] == 0 and c["Single:Add"] == 1 and len(h.schedule()) == 196
+    monkeypatch.setenv("ITB_FUSION_MASK", str(127 | 256 | 512))
+    h2 = B.GraphHandler(rt)
+    G.build_gpt2(h2, G.GPT2Config())
+    c2 = collections.Counter(h2.schedule())
+    assert c2["Single:Gelu"] == 12 and c2["Single:Add"] == 25 and c2["Single:MatMul"] == 48 and len(h2.schedule()) == 232
+
+
 def test_fused_schedule_and_alias_plan(B, monkeypatch):
     """The execution schedule groups q/k/v and gate/up MatMuls, folds the residual Adds and Silu*Mul, and turns
     the decode graph's Reshape / size-1 Transpose ops into storage aliases; ITB_NO_FUSION=1 gives the 1:1 order."""
