@@ -367,21 +367,36 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     }
     if (nsplit > 1) {
         cluster.sync();
-        if (split == 0 && warp < TC_EPI_WARPS) {
+        if (warp < TC_EPI_WARPS) {
+            // reduce-scatter over distributed shared memory: rank r finishes rows [r, r + 1) * mpad / nsplit of the tile -- every CTA
+            // of the cluster reads 1 / nsplit of each peer's partial (the first version had rank 0 read all of it: 8 x 64 KB at
+            // M = 128, slower than the serial k walk it replaced); partials are summed in rank order -> deterministic
             const float *peers[8];
             for (int r = 0; r < nsplit; ++r) peers[r] = (const float *)cluster.map_shared_rank(red, r);
-            for (int idx = threadIdx.x; idx < p.mpad * TC_BN; idx += TC_EPI_WARPS * 32) {
+            const int rows_per = (p.mpad + nsplit - 1) / nsplit;
+            const int r_begin = split * rows_per, r_end = min(p.mpad, r_begin + rows_per);
+            const bool rb = (g.act & ITB_ACT_ROUND_BEFORE_BIAS) != 0;
+            const int act = g.act & 0xff;
+            const T *resid = g.residual ? (const T *)g.residual + (int64_t)bz * g.m * Ng : nullptr;
+            for (int idx = r_begin * TC_BN + (int)threadIdx.x; idx < r_end * TC_BN; idx += TC_EPI_WARPS * 32) {
                 const int m = m0 + idx / TC_BN, nl = idx % TC_BN, gn = n0 + nl;
                 if (m >= g.m || gn >= Ng) continue;
                 float f = 0.f;
                 for (int r = 0; r < nsplit; ++r) f += peers[r][idx];
                 if (bias) {
-                    if (g.act & ITB_ACT_ROUND_BEFORE_BIAS) f = round_t<T>(f);
+                    if (rb) f = round_t<T>(f);
                     f += to_f(bias[m * g.bias_sm + gn * g.bias_sn]);
+                }
+                if (act == 4) {
+                    const float x = round_t<T>(f);
+                    f = 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+                } else {
+                    f = gemm_act(act, f);
                 }
                 const int64_t off = g.c_block ? (int64_t)(gn / g.c_block) * g.c_block_stride + (int64_t)m * g.c_block + gn % g.c_block
                                               : (int64_t)m * Ng + gn;
-                C[off] = from_f<T>(gemm_act(g.act, f));
+                if (resid) f = round_t<T>(f) + to_f(resid[off]);
+                C[off] = from_f<T>(f);
             }
         }
         cluster.sync();
@@ -393,6 +408,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
         if (lane == 0) TC_MARK(8);
     }
+}
+
+int tc_splitk_min_ktiles() {
+    static const int v = [] {
+        const char *e = std::getenv("ITB_TC_SPLITK_MIN_KTILES");
+        return e && e[0] ? std::atoi(e) : 24;
+    }();
+    return v;
 }
 
 // decode GEMMs (M <= 64) take this kernel once its 128-column tiles alone occupy every SM (measured, tools/gemm_bench.py: gate/up
@@ -429,13 +452,19 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16, int ngr
     p.ktiles = (g.k + TC_BK - 1) / TC_BK;
     // split-K only where the partial tile is small (decode regime); clusters of <= 8 CTAs
     int splitk = 1;
-    const bool tail = g.bn_scale || g.residual || g.post_relu;  // the fused conv tail lives in the direct epilogue only
-    // (measured: splitting the M = 128, few-column-tile GEMMs of GPT-2 over a cluster is SLOWER -- 2.47 vs 1.72 ms per forward --
-    //  the 64 KB fp32 partial tile per CTA through DSMEM costs more than the serial k walk it removes)
+    // the fused conv tail lives in the direct epilogue only (a residual after bias / activation is handled by the reduction too)
+    const bool tail = g.bn_scale || g.post_relu || (g.residual && !(g.bias || (g.act & 0xff)));
+    // (measured with rank 0 reducing alone: splitting the M = 128, few-column-tile GEMMs of GPT-2 over a cluster was SLOWER -- 2.47 vs
+    //  1.72 ms per forward -- 8 x 64 KB through one CTA's DSMEM reads; the reduce-scatter form below reads 1/8 of that per CTA)
     if (p.mpad <= 64 && g.batch == 1 && !tail && !g.no_splitk) {
         splitk = (2 * kNumSMs) / tiles_n;
         splitk = std::max(1, std::min(splitk, 8));
         splitk = std::min(splitk, std::max(1, p.ktiles / 4));
+    } else if (p.mpad <= 128 && g.batch == 1 && !tail && !g.c_block && !g.c_nhwc && p.ktiles >= tc_splitk_min_ktiles() &&
+               tiles_n * p.m_chunks * 4 <= kNumSMs) {
+        // a long serial k walk on a handful of CTAs (GPT-2's mlp c_proj: 48 k-tiles on 6 CTAs): split it over a cluster, >= 6 k-tiles each
+        splitk = std::min(8, std::min(p.ktiles / 6, kNumSMs / (tiles_n * p.m_chunks)));
+        splitk = std::max(1, splitk);
     }
     p.ktiles_per_split = (p.ktiles + splitk - 1) / splitk;
     splitk = (p.ktiles + p.ktiles_per_split - 1) / p.ktiles_per_split;

@@ -322,7 +322,7 @@ def test_matmul_grouped_parity(K, gemm_impl, dt):
 def test_matmul_fused_epilogue_parity(K, dt):
     """MatMul + bias -> [Gelu] -> [+ residual] in the tcgen05 epilogue = the separate kernels (MatMul with bias, unary Gelu, binary
     Add), bit for bit -- the same fp32 sums and the same rounding points -- and the oracle chain within the GEMM tolerance."""
-    for ci, (m, k, n) in enumerate([(128, 768, 768), (128, 768, 3072), (200, 3072, 776), (65, 64, 64)]):
+    for ci, (m, k, n) in enumerate([(128, 768, 768), (128, 768, 3072), (128, 3072, 768), (200, 3072, 776), (65, 64, 64)]):  # (third: split-K cluster)
         a, b = rnd((m, k), 420 + ci, dt, 0.5), rnd((k, n), 430 + ci, dt, 0.05)
         bias, res = rnd((n,), 440 + ci, dt, 0.5), rnd((m, n), 450 + ci, dt)
         tol = gemm_tol(dt, k, np.abs(a).max(), np.abs(b).max())
