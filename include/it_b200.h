@@ -258,6 +258,13 @@ int it_b200_conv2d_nhwc(int dtype, const void *x, const void *w, void *y, int y_
                         const float *bn_scale, const float *bn_bias, float bn_eps, const void *residual, int relu,
                         void *workspace, int64_t workspace_bytes, void *stream);
 
+/* L2 prefetch hint (optional, per host thread): [ptr, ptr + bytes) is constant data (weights) that the kernel AFTER the next launch
+ * will stream.  The next it_b200_attention_kvcache* launch spreads `cp.async.bulk.prefetch.L2` over its own run time -- the decode
+ * attention kernel uses ~70 % of HBM, the following projection's weights ride the rest and are then read from L2 -- and clears the
+ * hint.  Launchers that do not use it ignore it.  MEASURED on the C3 decode step: 3.735 ms with the hint vs 3.607 without (the
+ * attention kernel loses more to the extra traffic than the projection gains), so the hint is honoured only under ITB_L2_PREFETCH=1. */
+void it_b200_l2_prefetch_hint(const void *ptr, long long bytes);
+
 /* ---- AttentionKVCache (decode, q-len 1): replaces _attention_kvcache_kernel_128_1/_2
  *      (attention_kvcache.cu:8-169).  Appends k,v IN PLACE into k_cache/v_cache at
  *      position_id[0]; caches [B,H,S_max,D], q/k/v/out [B,H,1,D]; D == 128.

@@ -713,6 +713,22 @@ bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx, int layout) {
     return true;
 }
 
+// Step i is a decode attention launch: tell it which weights the next GEMM will stream (it_b200_l2_prefetch_hint) -- the attention
+// kernel leaves ~30 % of HBM idle and the next GEMM cannot become resident beside it, so its weights are prefetched into L2 meanwhile
+void setPrefetchHint(const vector<ExecStep> &sched, size_t i) {
+    const auto &st = sched[i];
+    if (st.ops.back()->getOpType() != OpType::AttentionKVCache) return;
+    for (size_t j = i + 1; j < sched.size() && j <= i + 6; ++j) {
+        const auto &nx = sched[j];
+        if (nx.kind == ExecStep::Alias) continue;
+        if (nx.ops[0]->getOpType() != OpType::MatMul) return;
+        auto w = nx.ops[0]->getInputs(1);
+        if (!w->isWeight() || w->getBytes() > (size_t)96 << 20) return;  // (leave room in the 126 MB L2 for the stream itself)
+        it_b200_l2_prefetch_hint(P(w), (long long)w->getBytes());
+        return;
+    }
+}
+
 // every NHWC conv of the schedule with filters larger than 1x1: re-order all the filter banks in one launch, into buffers the
 // runtime keeps per weight tensor (so no conv waits for a repack kernel of its own)
 void prepConvFilters(const vector<ExecStep> &sched, const RuntimeObj *ctx) {

@@ -208,6 +208,7 @@ void CudaRuntimeObj::runWithoutSyncImpl(const Graph &graph, bool validate) const
                 if (on) nvtxRangePop();
             }
         } range(nvtx, st);
+        b200::setPrefetchHint(sched, i);
         execStep(st, plan[i].kernel, plan[i].record ? &*plan[i].record : nullptr);
         cudaError_t err = cudaPeekAtLastError();
         if (err != cudaSuccess) {

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
                        const T *__restrict__ kin, const T *__restrict__ vin, const void *__restrict__ position_id,
                        int pos_flags, T *__restrict__ out, int Smax, int BH, float *__restrict__ partial,
                        int slots_per_head, int *__restrict__ tickets, const void *__restrict__ rope_pos,
-                       int rope_pos_dtype, int H, int stages) {
+                       int rope_pos_dtype, int H, int stages, const unsigned char *__restrict__ pf_ptr, long long pf_bytes) {
     using C = RowCfg<T>;
     constexpr int EPL = C::EPL, LPR = C::LPR, RPW = C::RPW;
     constexpr int CH = WARPS * RPW * U;                       // cache rows per chunk
@@ -161,7 +161,19 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 2)
         if (lane == 0) {
             const uint64_t policy = l2_policy_evict_first();
             int st = 0, ph = 0;
+            // L2 prefetch hint (it_b200_l2_prefetch_hint): this CTA's slice of the next GEMM's weights, 16 KB per unit it streams
+            long long pf_off = 0, pf_end = 0;
+            if (pf_bytes > 0) {
+                const long long per = (((pf_bytes + G - 1) / G) + 16383) & ~16383ll;
+                pf_off = (long long)blockIdx.x * per;
+                pf_end = min(pf_bytes, pf_off + per) & ~15ll;
+            }
+            const int pf_per_unit = nunits > 0 ? (int)((pf_end - pf_off + 16383) / 16384 + nunits - 1) / nunits : 0;
             for (int it = 0; it < nunits; ++it) {
+                for (int i = 0; i < pf_per_unit && pf_off < pf_end; ++i, pf_off += 16384) {
+                    const uint32_t n = (uint32_t)min(16384ll, pf_end - pf_off);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf_ptr + pf_off), "r"(n) : "memory");
+                }
                 mbar_wait(&empty[st], ph ^ 1);
                 const int rows = min(CH, pos - c * CH);
                 if (rows > 0) {
@@ -425,7 +437,7 @@ extern "C" int64_t it_b200_attention_kvcache_workspace(int B, int H, int S_max, 
 template <typename T, bool ROPE, int WARPS, int U>
 static int launch_attn_stream_cfg(T *kc, T *vc, const T *q, const T *k, const T *v, const void *position_id, int pos_flags,
                               const void *rope_pos, int rope_pos_dtype, T *out, int BH, int H, int S_max,
-                              float *workspace, cudaStream_t st) {
+                              float *workspace, cudaStream_t st, const void *pf_ptr, long long pf_bytes) {
     constexpr int CH = WARPS * RowCfg<T>::RPW * U;
     static const int stages = std::max(2, std::min(AS_MAX_STAGES, env_int("ITB_ATTN_STAGES", 2)));
     static const int per_sm = std::max(1, std::min(2, env_int("ITB_ATTN_CTAS_PER_SM", 2)));
@@ -439,7 +451,7 @@ static int launch_attn_stream_cfg(T *kc, T *vc, const T *q, const T *k, const T 
     const int grid = (int)std::min<int64_t>(max_units, (int64_t)per_sm * kNumSMs);
     cudaError_t e = launch_k(kern, dim3(grid), dim3((WARPS + 1) * 32), smem, st, kc, vc, q, k, v, position_id, pos_flags,
                              out, S_max, BH, workspace, stream_slots_per_head(S_max), tickets, rope_pos, rope_pos_dtype,
-                             H, stages);
+                             H, stages, (const unsigned char *)pf_ptr, pf_bytes);
     return e == cudaSuccess ? 0 : 1;
 }
 // consumer warps x rows per lane and chunk: 8 x 4 (default, measured best) or 16 x 2 (ITB_ATTN_WARPS=16)
@@ -467,13 +479,17 @@ static int attention_impl(int dtype, void *k_cache, void *v_cache, const void *q
     ITB_CHECK(workspace && workspace_bytes >= need, "AttentionKVCache: workspace %lld < %lld bytes",
               (long long)workspace_bytes, (long long)need);
     auto st = (cudaStream_t)stream;
+    const void *pf_ptr = nullptr;
+    long long pf_bytes = 0;
+    take_prefetch_hint(pf_ptr, pf_bytes);
+    if (!aligned16(pf_ptr)) pf_bytes = 0;
     ITB_DISPATCH_FLOAT(dtype, "AttentionKVCache", {
         int rc = rope_pos ? launch_attn_stream<T, true>((T *)k_cache, (T *)v_cache, (const T *)q, (const T *)k,
                                                         (const T *)v, position_id, pos_flags, rope_pos,
-                                                        rope_pos_dtype, (T *)out, BH, H, S_max, (float *)workspace, st)
+                                                        rope_pos_dtype, (T *)out, BH, H, S_max, (float *)workspace, st, pf_ptr, pf_bytes)
                           : launch_attn_stream<T, false>((T *)k_cache, (T *)v_cache, (const T *)q, (const T *)k,
                                                          (const T *)v, position_id, pos_flags, nullptr, 0, (T *)out,
-                                                         BH, H, S_max, (float *)workspace, st);
+                                                         BH, H, S_max, (float *)workspace, st, pf_ptr, pf_bytes);
         ITB_CHECK(rc == 0, "AttentionKVCache: streaming kernel launch failed: %s",
                   cudaGetErrorString(cudaGetLastError()));
         ITB_LAUNCH_CHECK("AttentionKVCache");
