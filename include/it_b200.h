@@ -163,6 +163,10 @@ int it_b200_batchnorm_relu(int dtype, const void *x, const float *mean, const fl
 #define ITB_MATMUL_B_CONST 0x200 /* OR into `act`: operand B is a constant (weight) that no kernel of the stream writes;
                                     lets the GEMM request its first weight tiles ahead of griddepcontrol.wait */
 int64_t it_b200_matmul_workspace(int dtype, int64_t b, int m, int n, int k);
+/* Kernel selection for this thread's following it_b200_matmul calls -- what MatMul's tune() records per shape in PerfEngine and its
+ * compute(op, record) re-applies (reference: the cuBLAS algorithm index of MatmulCublasPerfRecordObj, matmul.cc:12-24,187-208).
+ * impl: 0 production dispatch, 1 gemm_skinny (mma.sync + cluster split-K), 2 gemm_tc (tcgen05), 3 gemm_simt; skinny_nb: 0 auto, 1, 2. */
+void it_b200_matmul_select(int impl, int skinny_nb);
 int it_b200_matmul(int dtype, const void *A, const void *B, const void *bias, void *C, int64_t b,
                    int m, int n, int k, int64_t stride_a, int64_t stride_b, int trans_a,
                    int trans_b, int64_t bias_stride_b, int64_t bias_stride_m,

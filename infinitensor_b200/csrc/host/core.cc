@@ -288,7 +288,9 @@ void PerfEngine::savePerfEngineData(const string &path) const {
         for (size_t k = 0; k < perfKey.attrs.size(); ++k) out << (k ? "," : "") << perfKey.attrs[k];
         out << "],\"hashType\":" << (unsigned long long)perfKey.hash << ",\"opType\":" << (long long)perfKey.opType << "}],{\"data\":";
         out.precision(17);
-        out << rec->time << ",\"type\":0}]";
+        out << rec->time << ",\"type\":" << rec->type();
+        if (auto mr = std::dynamic_pointer_cast<MatmulPerfRecordObj>(rec)) out << ",\"impl\":" << mr->impl << ",\"nb\":" << mr->nb;
+        out << "}]";
         first = false;
     }
     out << "]}" << std::endl;
@@ -310,8 +312,17 @@ void PerfEngine::loadPerfEngineData(const string &path) {
         perfKey.hash = (HashType)pk.at("hashType").u64;
         perfKey.opType = (OpType::underlying_t)pk.at("opType").num;
         for (auto &a : pk.at("attrs").arr) perfKey.attrs.push_back((int)a.num);
-        IT_ASSERT((int)rec.at("type").num == 0, "perf-engine json: only the plain PerfRecord (type 0) is supported");
-        auto r = make_ref<PerfRecordObj>();
+        const int rtype = (int)rec.at("type").num;
+        IT_ASSERT(rtype == 0 || rtype == 1, "perf-engine json: record type " + std::to_string(rtype) + " is not one of this runtime's (0 plain, 1 MatMul)");
+        PerfRecord r;
+        if (rtype == 1) {
+            auto mr = make_ref<MatmulPerfRecordObj>();
+            mr->impl = (int)rec.at("impl").num;
+            mr->nb = (int)rec.at("nb").num;
+            r = mr;
+        } else {
+            r = make_ref<PerfRecordObj>();
+        }
         r->time = rec.at("data").num;
         fresh[Key{KernelAttrs{(Device)(int)ka.arr[0].num, (OpType::underlying_t)ka.arr[1].num}, perfKey}] = r;
     }

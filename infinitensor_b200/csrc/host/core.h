@@ -244,8 +244,16 @@ class OperatorObj : public std::enable_shared_from_this<OperatorObj> {
 struct PerfRecordObj {
     double time = 0;  // ms
     virtual ~PerfRecordObj() = default;
+    virtual int type() const { return 0; }  // JSON "type" (perf_engine.cc:7-62)
 };
 using PerfRecord = Ref<PerfRecordObj>;
+// what MatMul's tune() measured best for one (shape, dtype) key -- the counterpart of the reference's MatmulCublasPerfRecordObj
+// (matmul.cc:12-24: the cuBLAS algorithm index): which of this repo's GEMM kernels, and the skinny kernel's tile width
+struct MatmulPerfRecordObj : PerfRecordObj {
+    int impl = 0;  // 0 = the production dispatch order, 1 = gemm_skinny (mma.sync, cluster split-K), 2 = gemm_tc (tcgen05), 3 = gemm_simt
+    int nb = 0;    // skinny: 64-column boxes per tile (1 / 2; 0 = automatic)
+    int type() const override { return 1; }
+};
 
 class Kernel {
   public:

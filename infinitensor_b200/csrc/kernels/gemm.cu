@@ -154,9 +154,14 @@ __global__ void __launch_bounds__(256) pad_rows_kernel(const T *__restrict__ w, 
 
 // Kernel selection.  ITB_GEMM_IMPL = tc | skinny | simt pins one implementation (A/B testing and the parity
 // tests that must exercise each kernel); unset = the production order below.
+// per-thread kernel selection for the NEXT it_b200_matmul call(s) (it_b200_matmul_select: MatMul's tune() and tuned compute())
+static thread_local int g_sel_impl = 0;
+
 static int run_gemm(int dtype, const GemmArgs &g, cudaStream_t st) {
     if (g.batch == 0 || g.m == 0 || g.n == 0) return 0;
     const char *pin = std::getenv("ITB_GEMM_IMPL");
+    static const char *const sel_names[] = {"", "skinny", "tc", "simt"};
+    if (!(pin && pin[0]) && g_sel_impl >= 1 && g_sel_impl <= 3) pin = sel_names[g_sel_impl];
     int r = -1;
     if (pin && pin[0]) {
         if (!strcmp(pin, "tc")) r = launch_gemm_tc(dtype, g, st);
@@ -184,6 +189,14 @@ static int run_gemm(int dtype, const GemmArgs &g, cudaStream_t st) {
 using namespace itb;
 
 extern "C" int64_t it_b200_matmul_workspace(int, int64_t, int, int, int) { return 0; }
+
+extern "C" void it_b200_tune_skinny(int nb, int splitk);
+// impl: 0 production order, 1 gemm_skinny, 2 gemm_tc, 3 gemm_simt (a kernel that does not take the shape falls through to gemm_simt,
+// like ITB_GEMM_IMPL); skinny_nb: 1 / 2 = 64- / 128-column tiles, 0 automatic.  Stays in force on this thread until called again.
+extern "C" void it_b200_matmul_select(int impl, int skinny_nb) {
+    g_sel_impl = impl >= 0 && impl <= 3 ? impl : 0;
+    it_b200_tune_skinny(skinny_nb, 0);
+}
 
 extern "C" int it_b200_matmul(int dtype, const void *A, const void *B, const void *bias, void *C, int64_t b,
                               int m, int n, int k, int64_t stride_a, int64_t stride_b, int trans_a, int trans_b,

@@ -330,6 +330,41 @@ def test_resnet_conv_tail_fusion_is_bit_identical(monkeypatch):
     assert np.array_equal(fused, plain)
 
 
+def test_matmul_tune_records_a_kernel_choice_per_shape(tmp_path):
+    """run(tune=True): MatMul's tune() times the production dispatch and each GEMM kernel on the operator's own shape, stores the
+    winner (kernel + tile width) in PerfEngine; the next run re-applies it and gives the same result within the GEMM tolerance."""
+    import json
+    from infinitensor_b200 import backend as B, graphs as G
+    B.PerfEngine.clear()
+    rt = B.CudaRuntime(0)
+    h = B.GraphHandler(rt)
+    x = h.tensor([16, 1024], BF16)
+    x.set_input()
+    w1 = h.tensor([1024, 4096], BF16)
+    w1.set_weight()
+    w2 = h.tensor([4096, 512], BF16)
+    w2.set_weight()
+    y = h.matmul(h.matmul(x, w1, None, False, False, None, 0), w2, None, False, False, None, 0)
+    y.set_output()
+    h.data_malloc()
+    rng = np.random.default_rng(11)
+    x.copyin_numpy(G.to_storage(rng.standard_normal((16, 1024)).astype(np.float32) * 0.5, BF16))
+    w1.copyin_numpy(G.to_storage(rng.standard_normal((1024, 4096)).astype(np.float32) * 0.03, BF16))
+    w2.copyin_numpy(G.to_storage(rng.standard_normal((4096, 512)).astype(np.float32) * 0.03, BF16))
+    h.run()
+    before = G.from_storage(y.copyout_numpy(), BF16).astype(np.float64)
+    h.tune()
+    assert B.PerfEngine.size() == 2 and h.get_perf_time() > 0
+    out = tmp_path / "perf.json"
+    B.PerfEngine.save(str(out))
+    recs = [e[1] for e in json.loads(out.read_text())["data"]]
+    assert all(r["type"] == 1 and r["impl"] in (0, 1, 2) and r["nb"] in (0, 1, 2) and r["data"] > 0 for r in recs)
+    h.run()
+    after = G.from_storage(y.copyout_numpy(), BF16).astype(np.float64)
+    assert np.abs(after - before).max() <= 2.0 ** -6 * np.abs(before).max()
+    B.PerfEngine.clear()
+
+
 def test_resnet_nhwc_domain_matches_nchw(monkeypatch):
     """The NHWC domain (implicit-GEMM convs, NHWC pools; fusion mask bit 9) against the NCHW schedule of the same graph: the
     logits agree within fp16 accumulation noise (the NHWC epilogue rounds once per chain, the NCHW one after every operator) and

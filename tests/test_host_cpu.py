@@ -415,6 +415,15 @@ def test_perf_engine_json_roundtrip_in_the_reference_layout(B, tmp_path):
     assert B.PerfEngine.size() == 0
     with pytest.raises(RuntimeError):
         B.PerfEngine.load(str(tmp_path / "missing.json"))
+    # MatMul's tuned record (type 1: which GEMM kernel + tile width won on that shape) survives the round trip
+    tuned = {"data": [[[[2, 7], {"opType": 7, "hashType": 99, "attrs": [16, 4096, 11008, 0, 0]}], {"type": 1, "data": 0.018, "impl": 2, "nb": 0}],
+                      [[[2, 7], {"opType": 7, "hashType": 98, "attrs": [16, 4096, 4096, 0, 0]}], {"type": 1, "data": 0.010, "impl": 1, "nb": 1}]]}
+    p.write_text(json.dumps(tuned))
+    B.PerfEngine.load(str(p))
+    B.PerfEngine.save(str(out))
+    got = sorted((e[0][1]["hashType"], e[1]["type"], e[1]["impl"], e[1]["nb"], float(e[1]["data"])) for e in json.loads(out.read_text())["data"])
+    assert got == [(98, 1, 1, 1, 0.010), (99, 1, 2, 0, 0.018)]
+    B.PerfEngine.clear()
 
 
 def test_native_host_core(tmp_path):
