@@ -1207,11 +1207,10 @@ static int ds_run_cached(int dtype, int rows, const std::vector<uint8_t> &key_in
         ITB_CHECK(ce == cudaSuccess, "decode_stack: cudaMalloc(program): %s", cudaGetErrorString(ce));
         ce = cudaMemcpy(e.dev_phases, phs.data(), sizeof(DsPhase) * phs.size(), cudaMemcpyHostToDevice);
         ITB_CHECK(ce == cudaSuccess, "decode_stack: upload(program): %s", cudaGetErrorString(ce));
-        if (g_ds_cache.size() > 64) {
-            cudaFree(g_ds_cache.front().dev_phases);
-            cudaFree(g_ds_cache.front().tickets);
-            g_ds_cache.erase(g_ds_cache.begin());
-        }
+        // An evicted entry's device program may still be baked into a CUDA graph captured earlier (graph replay launches the kernel
+        // with the pointer it was captured with), so old programs are DROPPED from the lookup table but never freed: a few KB per
+        // (shape, pointer set) ever seen, bounded by what the process builds.
+        if (g_ds_cache.size() > 256) g_ds_cache.erase(g_ds_cache.begin());
         g_ds_cache.push_back(e);
         hit = &g_ds_cache.back();
     }
