@@ -321,6 +321,15 @@ int it_b200_attention_prefill(int dtype, const void *q, const void *k, const voi
                               int S_kv, int D, const void *scale, int scale_is_div, const void *mask,
                               int64_t mask_stride_b, int64_t mask_stride_h, int64_t mask_stride_i,
                               int64_t mask_stride_j, void *stream);
+/* The same kernel over STRIDED views of q / k / v / out: element (b, h, i, d) at base[b*st[0] + h*st[1] + i*st[2] + d] (strides in
+ * elements, multiples of 8; d contiguous).  The frontend's Split -> Reshape -> Transpose([0,2,1,3]) of a fused q/k/v projection
+ * output [B, S, 3 H D] and the Transpose -> Reshape behind the attention become addressing (4-D tensor maps, strided output rows):
+ * the schedule's PrefillAttention step absorbs those operators when every link has a single consumer. */
+int it_b200_attention_prefill_strided(int dtype, const void *q, const void *k, const void *v, void *out, int B, int H, int S_q,
+                                      int S_kv, int D, const int64_t *q_strides, const int64_t *k_strides,
+                                      const int64_t *v_strides, const int64_t *out_strides, const void *scale, int scale_is_div,
+                                      const void *mask, int64_t mask_stride_b, int64_t mask_stride_h, int64_t mask_stride_i,
+                                      int64_t mask_stride_j, void *stream);
 
 /* ---- The persistent decode kernel (decode_stack.cu): a whole stack of Llama decoder layers in ONE launch.
  *      Per layer it replaces the eight launches of the fused schedule -- RMSNorm (rms_norm.cu:36-110), the q/k/v MatMuls

@@ -86,6 +86,7 @@ _SIGS = {
                                           vp, c_int64, vp]),
     "it_b200_attention_prefill": (c_int, [c_int, vp, vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp, c_int, vp, c_int64, c_int64,
                                           c_int64, c_int64, vp]),
+    "it_b200_attention_prefill_strided": (c_int, [c_int, vp, vp, vp, vp] + [c_int] * 5 + [vp, vp, vp, vp, vp, c_int, vp, c_int64, c_int64, c_int64, c_int64, vp]),
     "it_b200_decode_stack_workspace": (c_int64, [c_int] * 6),
     "it_b200_decode_stack_debug": (vp, []),
     "it_b200_decode_stack_trace": (None, [vp]),

@@ -527,7 +527,10 @@ bool runPrefillAttention(const OpVec &ops, const RuntimeObj *) {
         return e && e[0] == '1';
     }();
     if (off) return false;
-    auto tr = ops[0], mm1 = ops[1], sm = ops[ops.size() - 2], mm2 = ops.back();
+    // extended form (schedule.cc extendPrefillChain): {Split, Rq, Tq, Rk, Tk, Rv, Tv, <chain>, mm2, Tout, Rout}
+    const bool ext = ops[0]->getOpType() == OpType::Split;
+    const size_t c0 = ext ? 7 : 0, cend = ext ? ops.size() - 2 : ops.size();  // [c0, cend) = Transpose(k), mm1, .., Softmax, mm2
+    auto tr = ops[c0], mm1 = ops[c0 + 1], sm = ops[cend - 2], mm2 = ops[cend - 1];
     Tensor q = mm1->getInputs(0), k = tr->getInputs(0), v = mm2->getInputs(1), out = mm2->getOutput();
     const void *scale = nullptr, *maskp = nullptr;
     int isDiv = 0;
@@ -535,7 +538,7 @@ bool runPrefillAttention(const OpVec &ops, const RuntimeObj *) {
     Tensor cur = mm1->getOutput();
     const auto &qd = q->getDims();
     const Shape full = {qd[0], qd[1], qd[2], k->getDims()[2]};
-    for (size_t i = 2; i + 2 < ops.size(); ++i) {
+    for (size_t i = c0 + 2; i + 2 < cend; ++i) {
         auto &o = ops[i];
         Tensor other = o->getInputs(0) == cur ? o->getInputs(1) : o->getInputs(0);
         if (o->getOpType() == OpType::Add) {
@@ -549,6 +552,17 @@ bool runPrefillAttention(const OpVec &ops, const RuntimeObj *) {
         cur = o->getOutput();
     }
     (void)sm;
+    if (ext) {
+        // q / k / v = thirds of every row of the projection output [B, S, 3 H D]; the result goes straight to [B, S, H D]
+        Tensor qkv = ops[0]->getInputs(0), fin = ops.back()->getOutput();
+        const int64_t B = qd[0], H = qd[1], Sq = qd[2], D = qd[3], d = H * D, row = qkv->getDims()[2];
+        const int64_t view[3] = {Sq * row, D, row}, ost[3] = {Sq * d, D, d};
+        const char *base = (const char *)P(qkv);
+        const int64_t es = (int64_t)qkv->getDType().getSize();
+        CK(it_b200_attention_prefill_strided(DTI(q), base, base + d * es, base + 2 * d * es, P(fin), (int)B, (int)H, (int)Sq, (int)k->getDims()[2],
+                                             (int)D, view, view, view, ost, scale, isDiv, maskp, ms[0], ms[1], ms[2], ms[3], S()), mm2);
+        return true;
+    }
     CK(it_b200_attention_prefill(DTI(q), P(q), P(k), P(v), P(out), qd[0], qd[1], qd[2], k->getDims()[2], qd[3], scale, isDiv, maskp,
                                  ms[0], ms[1], ms[2], ms[3], S()), mm2);
     return true;

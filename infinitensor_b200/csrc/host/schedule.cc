@@ -17,6 +17,7 @@ static bool fusionEnabled() {
 }
 // (bit 9 = NHWC domain for Conv / Pool / Add / Relu chains, on by default)
 // (bit 10 = MatMul + bias -> [Gelu] -> [Add] in the tcgen05 epilogue, on by default)
+// (bit 11 = the head split / merge around a prefill-attention chain folded into the attention step, on by default)
 // ITB_FUSION_MASK (debug / A-B): bit 0 alias, 1 MatMul groups, 2 MatMul+Add, 3 Silu*Mul, 4 AllReduce+Add+Norm, 5 RoPE->Attention, 6 Conv+BatchNorm[+Add][+Relu], 7 decoder-layer stacks (persistent kernel); default all
 static int fusionMask() {
     const char *e = std::getenv("ITB_FUSION_MASK");
@@ -25,7 +26,7 @@ static int fusionMask() {
     // bit 7 (decoder-layer stacks on the persistent kernel) is opt-in: measured on the BASELINE shape it does not yet beat the
     // eight tuned launches it replaces (165 vs 112 us per layer) -- ITB_DECODE_STACK=1 switches it on
     const char *ds = std::getenv("ITB_DECODE_STACK");
-    return ((ds && ds[0] == '1') ? 255 : 127) | 256 | 512 | 1024;
+    return ((ds && ds[0] == '1') ? 255 : 127) | 256 | 512 | 1024 | 2048;
 }
 
 static bool isKvCacheOperand(const Tensor &t) {
@@ -297,6 +298,59 @@ static OpVec matchPrefillChain(const Operator &mm2op) {
     return chain;
 }
 
+// The frontend's head split / merge around a prefill-attention chain (GPT-2):
+//   qkv [B, S, 3 H D] -> Split(axis 2, 3) -> 3 x { Reshape [B, S, H, D] -> Transpose [0,2,1,3] } -> chain -> Transpose [0,2,1,3] -> Reshape [B, S, H D]
+// When every link has a single consumer the whole neighbourhood runs as ONE PrefillAttention step: q / k / v become strided views of
+// the projection output and the result is written in its final layout (it_b200_attention_prefill_strided).  Returns the operators
+// in execution order -- {Split, Rq, Tq, Rk, Tk, Rv, Tv, <chain>, mm2, Tout, Rout} -- or {} when the pattern is not there.
+static OpVec extendPrefillChain(const OpVec &chain, const Operator &mm2op) {
+    auto sole = [](const Tensor &t) { return !t->isOutput() && t->getTargets().size() == 1; };
+    auto mm1 = chain[1];
+    Tensor q = mm1->getInputs(0), k = chain[0]->getInputs(0), v = mm2op->getInputs(1);
+    const vector<int> perm = {0, 2, 1, 3};
+    Operator split;
+    OpVec pre;
+    int part = 0;
+    for (auto &t : {q, k, v}) {
+        auto tr = t->getSource() ? as<TransposeObj>(t->getSource()) : nullptr;
+        if (!tr || !sole(t) || tr->getPermute() != perm) return {};
+        Tensor r = tr->getInputs(0);
+        auto rs = r->getSource();
+        if (!rs || rs->getOpType() != OpType::Reshape || !sole(r) || r->getRank() != 4) return {};
+        Tensor piece = rs->getInputs(0);
+        auto sp = piece->getSource() ? as<SplitObj>(piece->getSource()) : nullptr;
+        if (!sp || !sole(piece) || piece->getRank() != 3 || sp->getDim() != 2 || sp->numOutputs() != 3) return {};
+        if (split && sp != split) return {};
+        split = sp;
+        if (sp->getOutputs()[part] != piece) return {};  // q, k, v = parts 0, 1, 2 in this order
+        auto &pd = piece->getDims();
+        auto &rd = r->getDims();
+        if (rd[0] != pd[0] || rd[1] != pd[1] || rd[2] * rd[3] != pd[2]) return {};
+        pre.push_back(rs);
+        pre.push_back(tr);
+        ++part;
+    }
+    auto &d0 = split->getOutputs()[0]->getDims();
+    for (auto &o : split->getOutputs())
+        if (o->getDims() != d0) return {};
+    Tensor o = mm2op->getOutput();
+    if (!sole(o)) return {};
+    auto tout = as<TransposeObj>(o->getTargets()[0]);
+    if (!tout || tout->getPermute() != perm || !sole(tout->getOutput())) return {};
+    auto rout = tout->getOutput()->getTargets()[0];
+    if (rout->getOpType() != OpType::Reshape) return {};
+    auto &od = rout->getOutput()->getDims();
+    auto &qd = q->getDims();
+    if (od.size() != 3 || od[0] != qd[0] || od[1] != qd[2] || od[2] != qd[1] * qd[3]) return {};
+    OpVec all = {split};
+    all.insert(all.end(), pre.begin(), pre.end());
+    all.insert(all.end(), chain.begin(), chain.end());
+    all.push_back(mm2op);
+    all.push_back(tout);
+    all.push_back(rout);
+    return all;
+}
+
 // ---------------------------------------------------------------- NHWC domain
 // ResNet-style chains run fastest with channel-innermost activations: the implicit-GEMM conv (kernels/conv_nhwc.cu) reads them
 // through the TMA unit's im2col mode and no im2col matrix is ever written.  A tensor is stored NHWC only when EVERY step touching
@@ -450,6 +504,19 @@ const vector<ExecStep> &GraphObj::getSchedule() {
             bool clash = deferredInto.count(op.get()) > 0;
             for (auto &m : chain) clash = clash || deferred.count(m.get()) || deferredInto.count(m.get());
             if (clash) continue;
+            if (mask & 2048) {
+                // with the head split / merge around it: everything is parked behind the final Reshape
+                OpVec all = extendPrefillChain(chain, op);
+                bool ok = !all.empty();
+                for (auto &m : all) ok = ok && !deferred.count(m.get()) && !deferredInto.count(m.get());
+                if (ok) {
+                    auto last = all.back();
+                    all.pop_back();
+                    for (auto &m : all) deferred.insert(m.get());
+                    deferredInto[last.get()] = all;
+                    continue;
+                }
+            }
             for (auto &m : chain) deferred.insert(m.get());
             deferredInto[op.get()] = chain;
         }
@@ -463,7 +530,7 @@ const vector<ExecStep> &GraphObj::getSchedule() {
         if (it != deferredInto.end()) {
             const OpVec &prod = it->second;
             auto pt = prod[0]->getOpType();
-            if (pt == OpType::Transpose) {
+            if (pt == OpType::Transpose || pt == OpType::Split) {  // (Split first: the chain with its head split / merge)
                 st.kind = ExecStep::PrefillAttention;
                 st.ops = prod;
                 st.ops.push_back(op);

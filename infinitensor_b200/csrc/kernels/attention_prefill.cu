@@ -38,8 +38,22 @@ struct ApArgs {
     int scale_is_div;       // 1: s / scale, 0: s * scale
     const void *mask;       // additive mask (nullptr: none), element (b, h, i, j) at mask[b*mb + h*mh + i*mi + j*mj]
     int64_t mb, mh, mi, mj;
-    void *out;              // [BH, Sq, D]
+    void *out;              // element (b, h, i, d) at out[b*ob + h*oh + i*os + d]  ([B, H, S, D] dense: ob = H*S*D, oh = S*D, os = D)
+    int64_t ob, oh, os;
+    // q / k / v tensor maps: 0 = 3-D over a dense [B*H, S, D]; 1 = 4-D with dimensions (d, h, s, b); 2 = 4-D (d, s, h, b) -- strided
+    // views of e.g. a fused q/k/v projection output [B, S, 3 H D] (it_b200_attention_prefill_strided)
+    int map_mode;
 };
+
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+          "l"(policy)
+        : "memory");
+}
 
 template <typename T, int D>
 __global__ void __launch_bounds__(AP_THREADS, 1) attention_prefill_kernel(const __grid_constant__ CUtensorMap mapQ,
@@ -84,6 +98,13 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attention_prefill_kernel(const 
     const uint32_t idesc_o = umma_idesc_f16(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 0, /*B = V, MN-major*/ 1, 128, D);
     const uint64_t pol = l2_policy_evict_last();
     uint32_t ph_load = 0, ph_mma = 0;
+    const int b = bh / a.H, h = bh % a.H;
+    // one [rows x 64 columns] box of q / k / v: (column, sequence row) of head (b, h), whatever the tensor map's dimension order
+    auto ld = [&](void *dst, const CUtensorMap *m, int c_d, int c_s) {
+        if (a.map_mode == 0) tma_load_3d(dst, m, &bar_load, c_d, c_s, bh, pol);
+        else if (a.map_mode == 1) tma_load_4d(dst, m, &bar_load, c_d, h, c_s, b, pol);
+        else tma_load_4d(dst, m, &bar_load, c_d, c_s, h, b, pol);
+    };
 
     // Q tile once -- together with the first K tile (and V when there is only one key tile): one round trip instead of three
     const int ntiles = (a.Skv + AP_BK - 1) / AP_BK;
@@ -91,16 +112,16 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attention_prefill_kernel(const 
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bar_load, QK_BYTES + (ntiles > 0 ? QK_BYTES : 0) + (single ? V_BYTES : 0));
 #pragma unroll
-        for (int g = 0; g < DG; ++g) tma_load_3d(q_sm + g * (AP_BQ * 128), &mapQ, &bar_load, g * 64, q0, bh, pol);
+        for (int g = 0; g < DG; ++g) ld(q_sm + g * (AP_BQ * 128), &mapQ, g * 64, q0);
         if (ntiles > 0)
 #pragma unroll
-            for (int g = 0; g < DG; ++g) tma_load_3d(k_sm + g * (AP_BK * 128), &mapK, &bar_load, g * 64, 0, bh, pol);
+            for (int g = 0; g < DG; ++g) ld(k_sm + g * (AP_BK * 128), &mapK, g * 64, 0);
         if (single)
 #pragma unroll
             for (int g = 0; g < DG; ++g)
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh)
-                    tma_load_3d(v_sm + g * (AP_BK * 128) + hh * (64 * 128), &mapV, &bar_load, g * 64, hh * 64, bh, pol);
+                    ld(v_sm + g * (AP_BK * 128) + hh * (64 * 128), &mapV, g * 64, hh * 64);
     }
 
     float sc = 1.f;
@@ -109,7 +130,6 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attention_prefill_kernel(const 
     const bool div_pow2 = a.scale && a.scale_is_div && (__float_as_uint(sc) & 0x007fffffu) == 0u && sc != 0.f && fabsf(sc) < 1e30f && fabsf(sc) > 1e-30f;
     const float sc_mul = a.scale ? (a.scale_is_div ? (div_pow2 ? 1.f / sc : 0.f) : sc) : 1.f;
     const bool use_mul = a.scale && (!a.scale_is_div || div_pow2);
-    const int b = bh / a.H, h = bh % a.H;
     const T *mbase = a.mask ? (const T *)a.mask + b * a.mb + h * a.mh : nullptr;
     const bool mvec = mbase && a.mj == 1 && (a.mi & 7) == 0 && (((uintptr_t)mbase & 15) == 0);
     // cooperative, coalesced fill of the mask tile (rows q0.., keys j0..): 16 threads cover one row's 128 keys with 16-byte loads
@@ -157,7 +177,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attention_prefill_kernel(const 
         if (threadIdx.x == 0) {
             mbar_expect_tx(&bar_load, QK_BYTES);
 #pragma unroll
-            for (int g = 0; g < DG; ++g) tma_load_3d(k_sm + g * (AP_BK * 128), &mapK, &bar_load, g * 64, t * AP_BK, bh, pol);
+            for (int g = 0; g < DG; ++g) ld(k_sm + g * (AP_BK * 128), &mapK, g * 64, t * AP_BK);
         }
     };
     auto mma_s = [&]() {  // S = Q K^T into tmem_s
@@ -235,12 +255,12 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attention_prefill_kernel(const 
         if (threadIdx.x == 0 && !single) {
             mbar_expect_tx(&bar_load, QK_BYTES + V_BYTES);
 #pragma unroll
-            for (int g = 0; g < DG; ++g) tma_load_3d(k_sm + g * (AP_BK * 128), &mapK, &bar_load, g * 64, t * AP_BK, bh, pol);
+            for (int g = 0; g < DG; ++g) ld(k_sm + g * (AP_BK * 128), &mapK, g * 64, t * AP_BK);
 #pragma unroll
             for (int g = 0; g < DG; ++g)
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh)
-                    tma_load_3d(v_sm + g * (AP_BK * 128) + hh * (64 * 128), &mapV, &bar_load, g * 64, t * AP_BK + hh * 64, bh, pol);
+                    ld(v_sm + g * (AP_BK * 128) + hh * (64 * 128), &mapV, g * 64, t * AP_BK + hh * 64);
         }
         const int j0 = t * AP_BK;
         if (!single) {
@@ -294,7 +314,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attention_prefill_kernel(const 
     }
 
     // ---------------- epilogue: O row -> out ----------------
-    T *orow = (T *)a.out + ((int64_t)bh * a.Sq + q0 + row) * D;
+    T *orow = (T *)a.out + (int64_t)b * a.ob + (int64_t)h * a.oh + (int64_t)(q0 + row) * a.os;
 #pragma unroll 1
     for (int c0 = part * (D / AP_PARTS); c0 < (part + 1) * (D / AP_PARTS); c0 += 16) {
         uint32_t v[16];
@@ -316,13 +336,37 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attention_prefill_kernel(const 
     (void)lane;
 }
 
+// strides of a q / k / v view in elements: {batch, head, sequence row}; the head dimension is contiguous
+struct ApStrides {
+    int64_t b, h, s;
+};
+
 template <typename T, int D>
-static int launch_ap(const void *q, const void *k, const void *v, const ApArgs &a, cudaStream_t st) {
+static int launch_ap(const void *q, const void *k, const void *v, ApArgs a, cudaStream_t st, const ApStrides *sq = nullptr,
+                     const ApStrides *sk = nullptr, const ApStrides *sv = nullptr) {
     CUtensorMap mq, mk, mv;
-    if (!make_tma_3d_b16(&mq, q, (uint64_t)a.BH, (uint64_t)a.Sq, (uint64_t)D, (uint64_t)D, (uint64_t)a.Sq * D, AP_BQ, 64) ||
-        !make_tma_3d_b16(&mk, k, (uint64_t)a.BH, (uint64_t)a.Skv, (uint64_t)D, (uint64_t)D, (uint64_t)a.Skv * D, AP_BK, 64) ||
-        !make_tma_3d_b16(&mv, v, (uint64_t)a.BH, (uint64_t)a.Skv, (uint64_t)D, (uint64_t)D, (uint64_t)a.Skv * D, 64, 64))
-        ITB_FAIL("attention_prefill: cuTensorMapEncodeTiled failed");
+    if (!sq) {
+        a.map_mode = 0;
+        if (!make_tma_3d_b16(&mq, q, (uint64_t)a.BH, (uint64_t)a.Sq, (uint64_t)D, (uint64_t)D, (uint64_t)a.Sq * D, AP_BQ, 64) ||
+            !make_tma_3d_b16(&mk, k, (uint64_t)a.BH, (uint64_t)a.Skv, (uint64_t)D, (uint64_t)D, (uint64_t)a.Skv * D, AP_BK, 64) ||
+            !make_tma_3d_b16(&mv, v, (uint64_t)a.BH, (uint64_t)a.Skv, (uint64_t)D, (uint64_t)D, (uint64_t)a.Skv * D, 64, 64))
+            ITB_FAIL("attention_prefill: cuTensorMapEncodeTiled failed");
+    } else {
+        // 4-D maps, dimensions ordered by stride (TMA wants them ascending): (d, h, s, b) when heads are the inner stride (a fused
+        // projection's [B, S, H D] rows), (d, s, h, b) for [B, H, S, D]
+        const int B = a.BH / a.H;
+        const bool h_inner = sq->h < sq->s;
+        ITB_CHECK((sk->h < sk->s) == h_inner && (sv->h < sv->s) == h_inner, "attention_prefill: q / k / v views must share a dimension order");
+        a.map_mode = h_inner ? 1 : 2;
+        auto mk4 = [&](CUtensorMap *m, const void *base, const ApStrides &t, int S, uint32_t box_s) {
+            return h_inner ? make_tma_4d_b16(m, base, (uint64_t)D, (uint64_t)a.H, (uint64_t)S, (uint64_t)B, (uint64_t)t.h, (uint64_t)t.s,
+                                             (uint64_t)t.b, 64, 1, box_s, 1)
+                           : make_tma_4d_b16(m, base, (uint64_t)D, (uint64_t)S, (uint64_t)a.H, (uint64_t)B, (uint64_t)t.s, (uint64_t)t.h,
+                                             (uint64_t)t.b, 64, box_s, 1, 1);
+        };
+        if (!mk4(&mq, q, *sq, a.Sq, AP_BQ) || !mk4(&mk, k, *sk, a.Skv, AP_BK) || !mk4(&mv, v, *sv, a.Skv, 64))
+            ITB_FAIL("attention_prefill: cuTensorMapEncodeTiled (strided views) failed");
+    }
     const int smem = 2 * AP_BQ * D * 2 + AP_BK * D * 2 + AP_BQ * AP_BK * 2 + AP_BK * AP_MPAD * 2 + 1024;
     auto kern = attention_prefill_kernel<T, D>;
     static int attr_smem[64] = {0};  // per device
@@ -369,7 +413,53 @@ extern "C" int it_b200_attention_prefill(int dtype, const void *q, const void *k
     a.mi = mask_stride_i;
     a.mj = mask_stride_j;
     a.out = out;
+    a.ob = (int64_t)H * S_q * D;
+    a.oh = (int64_t)S_q * D;
+    a.os = D;
     auto st = (cudaStream_t)stream;
     if (dtype == ITB_BF16) return D == 64 ? launch_ap<__nv_bfloat16, 64>(q, k, v, a, st) : launch_ap<__nv_bfloat16, 128>(q, k, v, a, st);
     return D == 64 ? launch_ap<__half, 64>(q, k, v, a, st) : launch_ap<__half, 128>(q, k, v, a, st);
+}
+
+// The same attention over STRIDED views: element (b, h, i, d) of q at q[b*qs[0] + h*qs[1] + i*qs[2] + d] (likewise k, v, out) -- the
+// frontend's Split -> Reshape -> Transpose([0,2,1,3]) of a fused q/k/v projection and the Transpose -> Reshape after the attention
+// become addressing (4-D tensor maps, strided output rows) instead of five copy kernels per layer.
+extern "C" int it_b200_attention_prefill_strided(int dtype, const void *q, const void *k, const void *v, void *out, int B, int H,
+                                                 int S_q, int S_kv, int D, const int64_t *q_strides, const int64_t *k_strides,
+                                                 const int64_t *v_strides, const int64_t *out_strides, const void *scale,
+                                                 int scale_is_div, const void *mask, int64_t mask_stride_b, int64_t mask_stride_h,
+                                                 int64_t mask_stride_i, int64_t mask_stride_j, void *stream) {
+    ITB_CHECK(dtype == ITB_F16 || dtype == ITB_BF16, "attention_prefill: dtype %d must be f16 / bf16", dtype);
+    ITB_CHECK(D == 64 || D == 128, "attention_prefill: head dim %d must be 64 or 128", D);
+    ITB_CHECK(B >= 0 && H >= 0 && S_q >= 0 && S_kv >= 0, "attention_prefill: negative dimension");
+    ITB_CHECK((int64_t)B * H <= 65535, "attention_prefill: B * H beyond the grid limit");
+    if ((int64_t)B * H * S_q == 0) return 0;
+    ITB_CHECK(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), "attention_prefill: tensors must be 16-byte aligned");
+    for (int i = 0; i < 3; ++i)
+        ITB_CHECK(q_strides[i] % 8 == 0 && k_strides[i] % 8 == 0 && v_strides[i] % 8 == 0 && out_strides[i] % 8 == 0 && q_strides[i] > 0 &&
+                      k_strides[i] > 0 && v_strides[i] > 0,
+                  "attention_prefill: view strides must be positive multiples of 8 elements");
+    ApArgs a{};
+    a.BH = B * H;
+    a.H = H;
+    a.Sq = S_q;
+    a.Skv = S_kv;
+    a.D = D;
+    a.scale = scale;
+    a.scale_is_div = scale_is_div;
+    a.mask = mask;
+    a.mb = mask_stride_b;
+    a.mh = mask_stride_h;
+    a.mi = mask_stride_i;
+    a.mj = mask_stride_j;
+    a.out = out;
+    a.ob = out_strides[0];
+    a.oh = out_strides[1];
+    a.os = out_strides[2];
+    const ApStrides sq{q_strides[0], q_strides[1], q_strides[2]}, sk{k_strides[0], k_strides[1], k_strides[2]},
+        sv{v_strides[0], v_strides[1], v_strides[2]};
+    auto st = (cudaStream_t)stream;
+    if (dtype == ITB_BF16)
+        return D == 64 ? launch_ap<__nv_bfloat16, 64>(q, k, v, a, st, &sq, &sk, &sv) : launch_ap<__nv_bfloat16, 128>(q, k, v, a, st, &sq, &sk, &sv);
+    return D == 64 ? launch_ap<__half, 64>(q, k, v, a, st, &sq, &sk, &sv) : launch_ap<__half, 128>(q, k, v, a, st, &sq, &sk, &sv);
 }

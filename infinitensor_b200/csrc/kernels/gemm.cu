@@ -81,6 +81,21 @@ bool make_tma_3d_b16(CUtensorMap *map, const void *base, uint64_t batch, uint64_
     return r == CUDA_SUCCESS;
 }
 
+// 4-D tensor of 2-byte elements, dimensions d0 (contiguous) .. d3 with strides s1..s3 in elements (ascending), 128B swizzle
+bool make_tma_4d_b16(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t s1, uint64_t s2,
+                     uint64_t s3, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+    auto fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[4] = {d0, d1, d2, d3};
+    cuuint64_t gstride[3] = {s1 * 2, s2 * 2, s3 * 2};
+    cuuint32_t box[4] = {b0, b1, b2, b3};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // ---------------------------------------------------------------- im2col (NCHW -> [N][C*R*S, OH*OW])
 // FOLD = false: col[n][kc][p] (one [Kc, P] matrix per image);  FOLD = true: col[kc][n * P + p] (the batch folded into
 // the GEMM columns -- one [Kc, N*P] matrix, legal for TMA whenever N*P % 8 == 0 even if P is odd, e.g. 7x7 / 14x14 maps).

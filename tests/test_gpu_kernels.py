@@ -646,6 +646,39 @@ def test_attention_prefill_parity(K, B, H, Sq, Skv, D, masked, div, dt):
     assert np.abs(got - ref).max() <= tol * max(np.abs(ref).max(), 1e-3), np.abs(got - ref).max() / np.abs(ref).max()
 
 
+@pytest.mark.parametrize("dt", [F16, BF16])
+@pytest.mark.parametrize("B,H,S,D", [(1, 12, 128, 64), (2, 3, 200, 64), (2, 2, 72, 128)])
+def test_attention_prefill_strided_views(K, B, H, S, D, dt):
+    """q / k / v as strided views of a fused projection output [B, S, 3 H D] and the result written as [B, S, H D] (what the
+    schedule's extended PrefillAttention step passes) = the dense kernel on the materialised [B, H, S, D] copies, bit for bit."""
+    import torch
+    from infinitensor_b200 import _lib as L
+    d = H * D
+    qkv = rnd((B, S, 3 * d), 520, dt, 0.7)
+    parts = [np.ascontiguousarray(qkv[:, :, i * d:(i + 1) * d].reshape(B, S, H, D).transpose(0, 2, 1, 3)) for i in range(3)]
+    scale = oracle.round_to(np.array([np.sqrt(D)], np.float32), dt)
+    big_neg = -65504.0 if dt == F16 else -3.0e38
+    mask = oracle.round_to(np.triu(np.full((S, S), big_neg, np.float32), 1).reshape(1, 1, S, S), dt)
+    sd, md = K.dev(scale, dt), K.dev(mask, dt)
+    qd, kd, vd = [K.dev(t, dt) for t in parts]
+    dense = torch.zeros((B, H, S, D), dtype=K.TORCH_DT[dt], device="cuda")
+    L.check(L.lib.it_b200_attention_prefill(dt, K.ptr(qd), K.ptr(kd), K.ptr(vd), K.ptr(dense), B, H, S, S, D, K.ptr(sd), 1, K.ptr(md), 0, 0, S,
+                                            1, K.stream()))
+    xd = K.dev(qkv, dt)
+    out = torch.zeros((B, S, d), dtype=K.TORCH_DT[dt], device="cuda")
+    es = xd.element_size()
+    view = L.i64arr([S * 3 * d, D, 3 * d])
+    ost = L.i64arr([S * d, D, d])
+    import ctypes
+    base = xd.data_ptr()
+    L.check(L.lib.it_b200_attention_prefill_strided(dt, ctypes.c_void_p(base), ctypes.c_void_p(base + d * es), ctypes.c_void_p(base + 2 * d * es),
+                                                    K.ptr(out), B, H, S, S, D, view, view, view, ost, K.ptr(sd), 1, K.ptr(md), 0, 0, S, 1,
+                                                    K.stream()))
+    K.sync()
+    want = K.host(dense).transpose(0, 2, 1, 3).reshape(B, S, d)
+    assert np.array_equal(K.host(out), want)
+
+
 @pytest.mark.parametrize("dt", [F32, F16, BF16])
 def test_leaky_relu_elu_parity(K, dt):
     """LeakyRelu / Elu (reference unary.cu:97-106, 157-165; golden cases of test_cuda_unary.cc: alpha 0.1 / 1.0)."""

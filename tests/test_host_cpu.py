@@ -282,7 +282,15 @@ def test_gpt2_linear_epilogue_schedule(B, monkeypatch):
     G.build_gpt2(h, G.GPT2Config())
     c = collections.Counter(h.schedule())
     assert c["MatMulAdd:MatMul+Add"] == 24 and c["MatMulAdd:MatMul+Gelu"] == 12 and c["Single:MatMul"] == 12
-    assert c["Single:Gelu"] == 0 and c["Single:Add"] == 1 and len(h.schedule()) == 196
+    assert c["Single:Gelu"] == 0 and c["Single:Add"] == 1 and len(h.schedule()) == 88
+    # (bit 11) the head split / merge around each attention chain belongs to the attention step: no Split / Transpose launches left
+    ext = "PrefillAttention:Split+Reshape+Transpose+Reshape+Transpose+Reshape+Transpose+Transpose+MatMul+Div+Add+Softmax+MatMul+Transpose+Reshape"
+    assert c[ext] == 12 and not any(s.startswith(("Single:Transpose", "Single:Split", "Alias:")) for s in h.schedule())
+    monkeypatch.setenv("ITB_FUSION_MASK", str(127 | 256 | 512 | 1024))
+    h1 = B.GraphHandler(rt)
+    G.build_gpt2(h1, G.GPT2Config())
+    c1 = collections.Counter(h1.schedule())
+    assert c1["PrefillAttention:Transpose+MatMul+Div+Add+Softmax+MatMul"] == 12 and c1["Single:Transpose"] == 48 and len(h1.schedule()) == 196
     monkeypatch.setenv("ITB_FUSION_MASK", str(127 | 256 | 512))
     h2 = B.GraphHandler(rt)
     G.build_gpt2(h2, G.GPT2Config())
@@ -575,9 +583,14 @@ def test_prefill_attention_schedule(B, monkeypatch):
     h = B.GraphHandler(rt)
     G.build_gpt2(h, cfg)
     sc = h.schedule()
-    assert sc.count("PrefillAttention:Transpose+MatMul+Div+Add+Softmax+MatMul") == 2, sc
+    assert sum(s.startswith("PrefillAttention:") and s.endswith("Transpose+MatMul+Div+Add+Softmax+MatMul+Transpose+Reshape") for s in sc) == 2, sc
     assert not any(s in ("Single:Softmax", "Single:Div") for s in sc)
     h.data_malloc()
+    monkeypatch.setenv("ITB_FUSION_MASK", str(127 | 256))  # without bit 11: the bare chain
+    hb = B.GraphHandler(rt)
+    G.build_gpt2(hb, cfg)
+    assert hb.schedule().count("PrefillAttention:Transpose+MatMul+Div+Add+Softmax+MatMul") == 2
+    monkeypatch.delenv("ITB_FUSION_MASK")
     h32 = B.GraphHandler(rt)
     G.build_gpt2(h32, G.GPT2Config(layers=1, d_model=128, heads=2, ffn=256, vocab=500, n_pos=64, seq=16, batch=1, dtype=1))
     assert not any(s.startswith("PrefillAttention") for s in h32.schedule())
