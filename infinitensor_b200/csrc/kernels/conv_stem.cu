@@ -10,6 +10,9 @@
 //   warp w of 8: output rows 2w, 2w+1 of the block = two m16 tiles x 8 n8 tiles, fp32 accumulators in registers
 //   epilogue: BatchNorm (folded to one FMA) + ReLU, fp16/bf16 through a per-warp padded staging tile, 16-byte NHWC stores
 // Replaces cudnnConvolutionForward (+ BatchNorm + Relu kernels) for the stem (reference src/kernels/cuda/conv.cc:143-168).
+// A tcgen05 version (the patch copied into a K-major UMMA operand, one MMA thread, TMEM accumulators, TMA-store epilogue) was built
+// and measured: parity-green but 144 us vs this kernel's 114 us -- with one persistent CTA per SM its fetch / build / epilogue phases
+// run back to back on 9 warps and are latency-bound; kept unbuilt as tools/variants/conv_stem_tc.cu.
 #include <algorithm>
 
 #include "conv_shapes.h"

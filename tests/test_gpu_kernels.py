@@ -501,8 +501,8 @@ def test_conv_nhwc_parity(K, dt):
 
 @pytest.mark.parametrize("dt", [F16, BF16])
 def test_conv_stem_parity(K, dt):
-    """The stem kernel (NCHW input with <= 4 channels -> NHWC, fragments built from a shared-memory patch) against the oracle:
-    the ResNet stem, ragged image sizes (blocks cut by the border), 1..4 channels, small filters, stride 1, F < 64."""
+    """The stem kernel (NCHW input with <= 4 channels -> NHWC, mma.sync fragments built from a shared-memory patch) against the
+    oracle: the ResNet stem, ragged image sizes (blocks cut by the border), 1..4 channels, small filters, stride 1, F < 64."""
     tol = {F16: 8e-3, BF16: 6e-2}[dt]
     for ci, (xs, ws, args) in enumerate([((2, 3, 64, 64), (64, 3, 7, 7), (3, 3, 2, 2)),
                                          ((3, 3, 45, 37), (64, 3, 7, 7), (3, 3, 2, 2)),
