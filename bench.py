@@ -473,7 +473,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
-            "roofline": {"kernel": "gemm_skinny_kernel (every MatMul launch of one step: grouped q/k/v, o, grouped gate/up, down x layers + logits)", "bound": "hbm",
+            "roofline": {"kernel": "decode GEMMs (every MatMul launch of one step: grouped q/k/v, o, down on gemm_skinny_kernel [mma.sync + cluster split-K]; grouped gate/up and logits on gemm_tc_kernel [tcgen05]) x layers", "bound": "hbm",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src, "launches": gemm_launches,
                          "algorithmic_bytes_per_step": gemm_bytes, "ms_per_step_in_kernel": round(gemm_ms, 4)},

@@ -14,6 +14,8 @@ def launches(src, dst):
     agg = collections.defaultdict(lambda: [0, 0.0])
     by_grid = collections.defaultdict(lambda: [0, 0.0])
     for row in csv.DictReader(lines):
+        if not row.get("Metric Name", "gpu__time").startswith("gpu__time"):
+            continue  # (captures with extra metrics: only the durations are summed here)
         try:
             v = float(row["Metric Value"].replace(",", ""))
         except Exception:
