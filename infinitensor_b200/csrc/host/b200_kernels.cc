@@ -709,7 +709,6 @@ bool runConvBnAct(const OpVec &ops, const RuntimeObj *ctx, int layout) {
         return true;
     }
     if (layout & 2) {
-        IT_ASSERT(bn, "NHWC-output conv step without a BatchNorm tail outside the stem kernel");
         int rc = it_b200_conv2d_fused_nhwc_out(DTI(x), P(x), P(w), P(ops.back()->getOutput()), n, c, h, wd, f, r, s, ph, pw, sh, sw, dh, dw, g,
                                                bm, bv, bs, bb, eps, res ? P(res) : nullptr, relu ? 1 : 0, ws, wsb, S());
         IT_ASSERT(rc != 2, "NHWC-output conv step on a shape the im2col GEMM does not scatter (schedule / kernel disagree)");

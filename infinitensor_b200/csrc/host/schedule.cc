@@ -431,10 +431,8 @@ struct LayoutPass {
                     if (is(y) && !is(x)) {
                         // an NCHW input can still enter the domain: the stem kernel (<= 4 channels, no residual) or the
                         // folded im2col GEMM scattering its result channel-innermost
-                        const bool tail = st.kind == ExecStep::ConvBnAct;
                         const bool stem = !res && itb::conv_stem_ok(dt, ci, f, r, s, ph, pw, sh, sw, dh, dw, g);
-                        if (!stem && (!tail || !itb::conv_nchw_to_nhwc_ok(dt, n, ci, h, w, f, r, s, ph, pw, sh, sw, dh, dw, g)))
-                            changed |= drop(y);
+                        if (!stem && !itb::conv_nchw_to_nhwc_ok(dt, n, ci, h, w, f, r, s, ph, pw, sh, sw, dh, dw, g)) changed |= drop(y);
                     }
                     if (res && !free4(res) && is(res) != is(y)) {
                         changed |= drop(res);

@@ -365,6 +365,45 @@ def test_matmul_tune_records_a_kernel_choice_per_shape(tmp_path):
     B.PerfEngine.clear()
 
 
+@pytest.mark.parametrize("tail", ["none", "relu_out", "flatten"])
+def test_small_conv_net_enters_and_leaves_the_nhwc_domain(tail):
+    """Conv (no BatchNorm) -> Relu -> MaxPool 2x2 -> Conv 1x1 [-> Relu] [-> Flatten] in f16: the first conv reads the NCHW graph
+    input and writes NHWC through the im2col GEMM, Relu / MaxPool run on NHWC bytes, the implicit-GEMM conv writes the NCHW result
+    (`@nhwc>`); against the oracle executing the operator graph."""
+    from infinitensor_b200 import backend as B, graphs as G
+    from oracle.graph_oracle import OracleHandler
+    outs = []
+    rng = np.random.default_rng(17)
+    xv = rng.standard_normal((2, 16, 12, 12)).astype(np.float32)
+    w1v = (rng.standard_normal((24, 16, 3, 3)) * 0.1).astype(np.float32)
+    w2v = (rng.standard_normal((32, 24, 1, 1)) * 0.2).astype(np.float32)
+    for h in (B.GraphHandler(B.CudaRuntime(0)), OracleHandler()):
+        x = h.tensor([2, 16, 12, 12], F16)
+        x.set_input()
+        w1 = h.tensor([24, 16, 3, 3], F16)
+        w1.set_weight()
+        w2 = h.tensor([32, 24, 1, 1], F16)
+        w2.set_weight()
+        t = h.relu(h.conv(x, w1, None, 1, 1, 1, 1, 1, 1), None)
+        t = h.maxPool(t, None, 2, 2, 1, 1, 0, 0, 2, 2, 0)
+        t = h.conv(t, w2, None, 0, 0, 1, 1, 1, 1)
+        if tail == "relu_out":
+            t = h.relu(t, None)
+        elif tail == "flatten":
+            t = h.flatten(h.relu(t, None), None, 1)
+        t.set_output()
+        if isinstance(h, B.GraphHandler):
+            sc = h.schedule()
+            assert sc[0] == "Single:Conv@>nhwc" and sc[2] == "Single:MaxPool@nhwc" and sc[3] == "Single:Conv@nhwc>", sc
+        h.data_malloc()
+        for tt, v in ((x, xv), (w1, w1v), (w2, w2v)):
+            tt.copyin_numpy(G.to_storage(v, F16))
+        h.run()
+        outs.append(np.asarray(t.f32(), np.float64) if hasattr(t, "f32") else G.from_storage(t.copyout_numpy(), F16).astype(np.float64))
+    got, ref = outs[0].reshape(-1), outs[1].reshape(-1)
+    assert np.abs(got - ref).max() <= 4e-3 * max(np.abs(ref).max(), 1.0)
+
+
 def test_resnet_nhwc_domain_matches_nchw(monkeypatch):
     """The NHWC domain (implicit-GEMM convs, NHWC pools; fusion mask bit 9) against the NCHW schedule of the same graph: the
     logits agree within fp16 accumulation noise (the NHWC epilogue rounds once per chain, the NCHW one after every operator) and

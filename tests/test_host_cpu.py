@@ -272,6 +272,44 @@ def test_conv_bn_act_schedule(B, monkeypatch):
     assert not any(s.startswith("ConvBnAct") for s in h2.schedule())
 
 
+def test_nhwc_layout_pass_corner_cases(B):
+    """The NHWC domain's fixpoint (schedule.cc LayoutPass): a tensor is channel-innermost only when EVERY step touching it can work
+    that way -- a Conv chain ending in a layout-sensitive operator (Flatten of a [N, C, H, W] map), an fp32 graph, channels that are
+    not a multiple of 8, or a graph output in the middle all keep the reference layout where they must."""
+    rt = B.HostPlanRuntime()
+
+    def build(dt, c_mid, tail):
+        h = B.GraphHandler(rt)
+        x = h.tensor([2, 16, 12, 12], dt)
+        x.set_input()
+        w1 = h.tensor([c_mid, 16, 3, 3], dt)
+        w1.set_weight()
+        w2 = h.tensor([32, c_mid, 1, 1], dt)
+        w2.set_weight()
+        t = h.relu(h.conv(x, w1, None, 1, 1, 1, 1, 1, 1), None)
+        t = h.maxPool(t, None, 2, 2, 1, 1, 0, 0, 2, 2, 0)
+        t = h.conv(t, w2, None, 0, 0, 1, 1, 1, 1)
+        if tail == "relu_out":
+            t = h.relu(t, None)
+        elif tail == "flatten":
+            t = h.flatten(h.relu(t, None), None, 1)
+        t.set_output()
+        return h.schedule()
+
+    # f16, 8-multiple channels: the first conv reads the NCHW graph input and WRITES NHWC (the im2col GEMM scatters channel-innermost),
+    # Relu / MaxPool stay inside, the last conv reads NHWC and writes the NCHW graph output
+    assert build(10, 24, "none") == ["Single:Conv@>nhwc", "Single:Relu@nhwc", "Single:MaxPool@nhwc", "Single:Conv@nhwc>"]
+    # ... and with a Relu producing the output, that Relu (flat elementwise: operands and result agree) pulls the last conv's result to NCHW
+    assert build(10, 24, "relu_out") == ["Single:Conv@>nhwc", "Single:Relu@nhwc", "Single:MaxPool@nhwc", "Single:Conv@nhwc>", "Single:Relu"]
+    # fp32: nothing is NHWC
+    assert not any("@" in s for s in build(1, 24, "relu_out"))
+    # 20 mid channels (not a multiple of 8): no NHWC pool kernel, no implicit-GEMM conv -> the whole chain stays NCHW
+    assert not any("@" in s for s in build(10, 20, "relu_out"))
+    # Flatten reads [N, C, H, W] as [N, C*H*W]: its input stays NCHW
+    sc = build(10, 24, "flatten")
+    assert sc[:4] == ["Single:Conv@>nhwc", "Single:Relu@nhwc", "Single:MaxPool@nhwc", "Single:Conv@nhwc>"] and "@" not in sc[4] and "@" not in sc[5]
+
+
 def test_gpt2_linear_epilogue_schedule(B, monkeypatch):
     """GPT-2: the biased Linear layers take the residual Add (c_proj, mlp c_proj) or the Gelu (c_fc) into their step (mask bit 10);
     off -> the Round-1 schedule with those operators on their own."""
