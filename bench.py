@@ -439,11 +439,13 @@ def run_b200(args):
             # (examples/python/llama_kvcache_inference.py:133-141) -- plus bounds that separate rounding noise from a wrong
             # shard: 32 bf16 layers with another fp32 summation order per row-split GEMM measure ~5e-2 of max on the worst
             # of 512 k logits (random weights: logits are noise-like sums) and ~1e-2 in L2; a mis-sharded weight or a broken
-            # all-reduce gives O(1) on both and random argmax.
+            # all-reduce gives O(1) on both (rel_l2 ~ 1.4 for unrelated logits) and random argmax.  Measured on two B200s:
+            # rel_l2 = 4.75e-2, argmax agreement 1.0 -- the L2 bound therefore sits at 0.12, not at the 5e-2 first guessed (which
+            # N = 2 passed by 5 % and more shards need not).
             tp_parity = {"tp_parity_rel_err": rel, "rel_l2": rel_l2, "argmax_agreement": agree,
-                         "tolerance": {"argmax_agreement_min": 0.9, "rel_l2_max": 5e-2, "rel_to_max_max": 0.15},
+                         "tolerance": {"argmax_agreement_min": 0.9, "rel_l2_max": 0.12, "rel_to_max_max": 0.2},
                          "against": "unsharded graph of the same seeds, one step on rank 0's GPU (N = 1 path)",
-                         "pass": bool(agree >= 0.9 and rel_l2 < 5e-2 and rel < 0.15 and logits_finite)}
+                         "pass": bool(agree >= 0.9 and rel_l2 < 0.12 and rel < 0.2 and logits_finite)}
             ok[0] = tp_parity["pass"]
             del h1, g1
         dist.broadcast_object_list(ok, src=0)
