@@ -463,6 +463,8 @@ static int launch_tc_t(const GemmArgs &g, cudaStream_t st, bool is_bf16, int ngr
     } else if (p.mpad <= 128 && g.batch == 1 && !tail && !g.c_block && !g.c_nhwc && p.ktiles >= tc_splitk_min_ktiles() &&
                tiles_n * p.m_chunks * 4 <= kNumSMs) {
         // a long serial k walk on a handful of CTAs (GPT-2's mlp c_proj: 48 k-tiles on 6 CTAs): split it over a cluster, >= 6 k-tiles each
+        // (threshold measured: also splitting the K = 768 projections -- ITB_TC_SPLITK_MIN_KTILES=12 -- takes the forward from 0.78 to 1.22 ms:
+        //  two cluster syncs and the DSMEM exchange cost more than the 6 k-tiles they save)
         splitk = std::min(8, std::min(p.ktiles / 6, kNumSMs / (tiles_n * p.m_chunks)));
         splitk = std::max(1, splitk);
     }
