@@ -310,6 +310,55 @@ def test_nhwc_layout_pass_corner_cases(B):
     assert sc[:4] == ["Single:Conv@>nhwc", "Single:Relu@nhwc", "Single:MaxPool@nhwc", "Single:Conv@nhwc>"] and "@" not in sc[4] and "@" not in sc[5]
 
 
+def test_prefill_extension_and_linear_epilogue_negative_cases(B):
+    """The extended PrefillAttention step and the biased-Linear epilogue only swallow what is provably private to them."""
+    rt = B.HostPlanRuntime()
+    Bt, S, H, D = 1, 128, 2, 64
+    d = H * D
+
+    def attention_block(extra_reader=False, swap_kv=False, rows=128):
+        h = B.GraphHandler(rt)
+        x = h.tensor([Bt, rows, d], 10)
+        x.set_input()
+        w = h.tensor([d, 3 * d], 10)
+        w.set_weight()
+        b = h.tensor([3 * d], 10)
+        b.set_weight()
+        wo = h.tensor([d, d], 10)
+        wo.set_weight()
+        bo = h.tensor([d], 10)
+        bo.set_weight()
+        sc = h.tensor([1], 10)
+        sc.set_weight()
+        qkv = h.matmul(x, w, None, False, False, b, 0)
+        parts = h.split(qkv, None, 2, 3)
+        q, k, v = parts
+        if swap_kv:
+            k, v = v, k
+        heads = lambda t: h.transpose(h.reshape(t, None, [Bt, rows, H, D]), None, [0, 2, 1, 3])
+        if extra_reader:
+            side = h.relu(parts[0], None)  # a second consumer of the q third: it must stay a real tensor
+            side.set_output()
+        q, k, v = heads(q), heads(k), heads(v)
+        s_ = h.div(h.matmul(q, h.transpose(k, None, [0, 1, 3, 2]), None, False, False, None, 0), sc, None)
+        a = h.matmul(h.softmax(s_, None, -1), v, None, False, False, None, 0)
+        a = h.reshape(h.transpose(a, None, [0, 2, 1, 3]), None, [Bt, rows, d])
+        o = h.add(x, h.matmul(a, wo, None, False, False, bo, 0), None)
+        o.set_output()
+        return h.schedule()
+
+    ext = [s for s in attention_block() if s.startswith("PrefillAttention:Split")]
+    assert len(ext) == 1
+    sc = attention_block(extra_reader=True)  # the Split has an outside reader -> the bare chain, Split / Transposes on their own
+    assert any(s == "PrefillAttention:Transpose+MatMul+Div+Softmax+MatMul" for s in sc) and "Single:Split" in sc and sc.count("Single:Transpose") == 4
+    sc = attention_block(swap_kv=True)      # k / v are not thirds 1 / 2 in order -> not the strided-view pattern
+    assert not any(s.startswith("PrefillAttention:Split") for s in sc) and "Single:Split" in sc
+    # 16 rows (decode regime): the biased projections keep their Add outside (the tcgen05 epilogue is for > 64 rows), 32-row attention is
+    # still a prefill chain (q-len > 1) but never the biased-Linear fusion
+    sc = attention_block(rows=16)
+    assert "MatMulAdd:MatMul+Add" not in sc and "Single:Add" in sc
+
+
 def test_gpt2_linear_epilogue_schedule(B, monkeypatch):
     """GPT-2: the biased Linear layers take the residual Add (c_proj, mlp c_proj) or the Gelu (c_fc) into their step (mask bit 10);
     off -> the Round-1 schedule with those operators on their own."""
